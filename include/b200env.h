@@ -1,0 +1,183 @@
+/* b200env.h - C ABI of the B200-native vectorised humanoid(+ball) environment step.
+ *
+ * This is the drop-in boundary under the reference's Task surface ("Level A").
+ * The reference has no C ABI of its own: its tasks talk to Isaac Gym through pybind
+ * (`gym.simulate`, `gym.set_dof_position_target_tensor`, `gym.apply_rigid_body_force_tensors`,
+ * `gym.refresh_*_tensor`, `gym.set_*_tensor_indexed`, zero-copy `gymtorch.wrap_tensor` views).
+ * Each entry point below names the reference interface it replaces (paths relative to
+ * /root/reference).  The Python mirror of the Task classes (vid2player3d_b200/tasks) binds
+ * these with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: plain pointers + sizes, no torch types.  All `float*` / `int64_t*` buffers are
+ * DEVICE pointers owned by the caller (PyTorch storages), laid out exactly like the Isaac Gym
+ * tensors the reference wraps, so the reference's view/slice code keeps working.  Quaternions
+ * are xyzw, world is z-up.  Every call is asynchronous on `stream` (a cudaStream_t passed as
+ * void*), allocates nothing, and never synchronises the host.  Return 0 = ok; otherwise a
+ * negative code and b200env_last_error() describes it.
+ */
+#ifndef B200ENV_H
+#define B200ENV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_MAX_BODIES 32
+#define B200_MAX_DOF 96
+#define B200_MAX_KEY 8
+#define B200_ABI_VERSION 1
+
+/* Per-asset constant block produced by vid2player3d_b200/model_compiler.py from the MJCF/STL
+ * assets (replaces gym.load_asset + create_actor + set_actor_dof_properties:
+ * embodied_pose/env/tasks/humanoid_smpl_im.py:273-300,356-389).  Followed in memory by
+ * `float verts[nb][vmax][3]` (convex-hull vertices in the body frame). */
+typedef struct b200_model {
+  int32_t nb;        /* rigid bodies incl. welded ones (24, or 25 with Racket) */
+  int32_t nd;        /* actuated dof = 3 * spherical joints (69) */
+  int32_t vmax;      /* vertex stride per body */
+  int32_t max_depth; /* tree depth of the deepest body (root = 0) */
+  int32_t parent[B200_MAX_BODIES];
+  int32_t depth[B200_MAX_BODIES];
+  int32_t dof_of_body[B200_MAX_BODIES]; /* first dof index of the body's spherical joint, -1 = root / welded */
+  int32_t fixed[B200_MAX_BODIES];       /* 1 = welded to its parent (no joint) */
+  int32_t nverts[B200_MAX_BODIES];
+  float offset[B200_MAX_BODIES][3];  /* joint position in the parent frame */
+  float mass[B200_MAX_BODIES];       /* dynamics mass (welded children folded into parent, 0 for welded) */
+  float com[B200_MAX_BODIES][3];
+  float inertia[B200_MAX_BODIES][6]; /* about COM, body frame: xx yy zz xy xz yz */
+  float radius[B200_MAX_BODIES];     /* bounding radius of the hull about the body origin */
+  float kp[B200_MAX_DOF];            /* PD stiffness per dof, already scaled by mass/90*kp_scale */
+  float kd[B200_MAX_DOF];
+  float armature[B200_MAX_DOF];
+  float lim_lo[B200_MAX_DOF];
+  float lim_hi[B200_MAX_DOF];
+} b200_model_t;
+
+/* Simulation + task constants (replaces gymapi.SimParams / the yaml `sim:` block,
+ * embodied_pose/utils/config.py:198-231, cfg/amass_im.yaml:37-52, and the env: block entries
+ * read by humanoid_smpl_im.py:54-117). */
+typedef struct b200_cfg {
+  float sim_dt;             /* 1/60 */
+  int32_t substeps;         /* 2 */
+  int32_t control_freq_inv; /* 2 */
+  float gravity_z;          /* -9.81 */
+  float contact_kn, contact_cn, friction_mu, friction_vs; /* ground contact model */
+  float ang_damping, max_ang_vel;                         /* AssetOptions: 0.01, 100 */
+  float limit_k, limit_c;                                 /* joint-limit spring/damper */
+  float pd_tar_lim;                                       /* 0.5*pi (humanoid_smpl_im.py:73) */
+  float res_force_scale, res_torque_scale;                /* 31.85 (cfg/amass_im.yaml:24) */
+  int32_t max_episode_length;                             /* episodeLength */
+  int32_t enable_early_termination;
+  float termination_height[B200_MAX_BODIES];              /* humanoid_smpl_im.py:217-224 */
+  int32_t contact_body[B200_MAX_BODIES];                  /* 1 = excluded from the fall test (contactBodies) */
+  float body_pos_weight[B200_MAX_BODIES];                 /* humanoid_smpl_im.py:110-115 */
+  float k_dof, k_vel, k_pos, k_rot, w_dof, w_vel, w_pos, w_rot; /* reward_specs :682 */
+  int32_t num_key;
+  int32_t key_body[B200_MAX_KEY];                         /* keyBodies */
+  int32_t shape_dim;                                      /* motion_bodies width (11) */
+  float ground_tolerance;
+} b200_cfg_t;
+
+/* Reference MoCap buffer (embodied_pose/utils/motion_lib.py:68-93): flat device arrays. */
+typedef struct b200_motion_lib {
+  const float* gts;   /* [F,nb24,3] global translations */
+  const float* grs;   /* [F,nb24,4] global rotations */
+  const float* lrs;   /* [F,nb24,4] local rotations */
+  const float* grvs;  /* [F,3] */
+  const float* gravs; /* [F,3] */
+  const float* dvs;   /* [F,nd] */
+  const float* motion_lengths;  /* [M] */
+  const int64_t* num_frames;    /* [M] */
+  const float* motion_dt;       /* [M] */
+  const int64_t* length_starts; /* [M] */
+  const float* min_verts_h;     /* [M] */
+  int32_t num_motions;
+  int32_t num_lib_bodies; /* bodies per MoCap frame (24) */
+  int64_t total_frames;
+} b200_motion_lib_t;
+
+/* Torch-owned state / output tensors.  Layouts mirror the Isaac Gym tensors the reference
+ * wraps in _setup_tensors (embodied_pose/env/tasks/humanoid_smpl.py:66-113). */
+typedef struct b200_buffers {
+  float* root_states;      /* [N, actors_per_env, 13]  (humanoid = actor 0) */
+  int32_t actors_per_env;
+  float* dof_state;        /* [N, nd, 2] (pos, vel) */
+  float* rigid_body_state; /* [N, bodies_per_env, 13] */
+  float* contact_forces;   /* [N, bodies_per_env, 3] */
+  int32_t bodies_per_env;  /* >= nb (ball appended in vid2player) */
+  float* obs_buf;          /* [N, num_obs] */
+  int32_t num_obs;
+  float* rew_buf;          /* [N] */
+  float* sub_rewards;      /* [N,4] */
+  int64_t* reset_buf;      /* [N] */
+  int64_t* progress_buf;   /* [N] */
+  int64_t* terminate_buf;  /* [N] */
+  const int64_t* motion_ids; /* [N] _reset_ref_motion_ids */
+  float* ref_motion_times;   /* [N] _cur_ref_motion_times */
+  const float* motion_bodies;/* [N, shape_dim] _reset_ref_motion_bodies */
+  /* current targets (humanoid_smpl_im.py:594-624) */
+  float *t_root_pos, *t_root_rot, *t_dof_pos, *t_root_vel, *t_root_ang_vel, *t_dof_vel, *t_key_pos, *t_rb_pos, *t_rb_rot;
+  /* previous targets used by the reward (:626-636, :677-680) */
+  float *p_dof_pos, *p_dof_vel, *p_rb_pos, *p_rb_rot;
+  float* pd_targets;       /* [N, nd] last PD targets (set_dof_position_target_tensor argument) */
+  float* actions_used;     /* [N, num_actions] actions after zeroing reset envs (self.actions) */
+} b200_buffers_t;
+
+typedef struct b200env* b200env_handle;
+
+int b200env_abi_version(void);
+const char* b200env_last_error(void);
+
+/* replaces BaseTask.create_sim + gym.prepare_sim (base_task.py:48-49): builds nothing per env,
+ * uploads the constant block once.  `model` and `verts` are HOST pointers. */
+int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg_t* cfg, int32_t num_envs,
+                   int32_t device, b200env_handle* out);
+int b200env_destroy(b200env_handle h);
+/* replaces gym.acquire_*_tensor + gymtorch.wrap_tensor (humanoid_smpl.py:66-113) */
+int b200env_bind(b200env_handle h, const b200_buffers_t* bufs);
+/* replaces torch.load(motion_lib) residency (humanoid_smpl_im.py:420-440) */
+int b200env_set_motion_lib(b200env_handle h, const b200_motion_lib_t* ml);
+
+/* replaces BaseTask.step = pre_physics_step + _physics_step + post_physics_step
+ * (base_task.py:147-165; humanoid_smpl_im.py:125-157,398-418): ONE fused launch.
+ * actions: [N, nd+6] device. */
+int b200env_step(b200env_handle h, const float* actions, void* stream);
+
+/* replaces HumanoidSMPLIM._reset_envs for ref-state init (humanoid_smpl_im.py:442-450,489-528,
+ * 741-755; humanoid_smpl.py:153-173): env_ids [n] int64 device, motion_times [n] float device
+ * (sampled by the host like MotionLib.sample_time). */
+int b200env_reset(b200env_handle h, const int64_t* env_ids, const float* motion_times, int32_t n, void* stream);
+
+/* replaces MotionLib.get_motion_state(..., return_rigid_body=True, adjust_height=True)
+ * (motion_lib.py:164-266) for arbitrary (id, time) pairs, e.g. _init_context
+ * (humanoid_smpl_im.py:530-563).  Any output pointer may be NULL. */
+int b200env_motion_state(b200env_handle h, const int64_t* motion_ids, const float* motion_times, int32_t n,
+                         float* root_pos, float* root_rot, float* dof_pos, float* root_vel, float* root_ang_vel,
+                         float* dof_vel, float* key_pos, float* rb_pos, float* rb_rot, void* stream);
+
+/* replaces compute_humanoid_observations_imitation (humanoid_smpl_im.py:773-850 ==
+ * models/im_network_builder.py:262-338): obs [n,1+..=734 for 24 bodies]. */
+int b200env_obs_imitation(b200env_handle h, int32_t n, const float* body_pos, const float* body_rot,
+                          const float* target_pos, const float* target_rot, const float* dof_pos, const float* dof_vel,
+                          const float* target_dof_pos, const float* body_vel, const float* body_ang_vel,
+                          const float* motion_bodies, int32_t local_root_obs, int32_t root_height_obs, float* obs,
+                          void* stream);
+
+/* Physics-only control step on caller-provided arrays, float (prec=0) or double (prec=1):
+ * the same device code as b200env_step's physics, exposed so tests can compare it with the
+ * float64 CPU restatement (oracle/physics_ref.c).  root [n,13], dof_pos/dof_vel/pd_tar [n,nd],
+ * ext_wrench [n,6] (force, torque on body 0, world frame, first sim step only),
+ * rb_out [n,nb,13], contact_out [n,nb,3].  n_steps control steps are run back to back. */
+int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_steps, void* root, void* dof_pos,
+                         void* dof_vel, const void* pd_tar, const void* ext_wrench, void* rb_out, void* contact_out,
+                         void* stream);
+
+/* number of kernels launched by this handle so far (bench.py "gpu_launches") */
+int64_t b200env_launch_count(b200env_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ENV_H */

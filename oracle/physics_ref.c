@@ -1,0 +1,409 @@
+/* ORACLE (test infrastructure, not product code) - float64 CPU restatement of the articulated
+ * rigid-body control step of the B200 environment kernel (vid2player3d_b200/csrc).
+ *
+ * PARITY UNPINNED: in the reference this arithmetic lives inside NVIDIA Isaac Gym Preview 4
+ * (closed-source PhysX 5 binary, un-vendored, un-installable here).  The reference
+ * only fixes the INPUTS of the solver - the call sites `gym.simulate` (embodied_pose/env/tasks/
+ * base_task.py:450-454), the assets (data/assets/mjcf/smpl_mesh_humanoid_amass_v1.xml), the sim
+ * block (cfg/amass_im.yaml:37-52, utils/config.py:198-231), the actor properties
+ * (humanoid_smpl_im.py:273-276,356-389) and the actuation semantics (:125-157,391-396).  There is
+ * no golden trajectory in the reference.  This file therefore restates OUR model:
+ *
+ *   - 23 spherical joints (exp-map coordinates, child-frame relative angular velocity) + free root,
+ *   - Featherstone articulated-body algorithm written with classical accelerations in world-aligned
+ *     axes with each body's reference point at its own joint origin,
+ *   - implicit ("stable") PD drive + armature + joint-limit springs on the joint-space diagonal,
+ *   - compliant ground contact of every convex-hull vertex, implicit in the velocity (the
+ *     spring/damper/viscous-friction terms enter the body's articulated inertia as rank-1 updates),
+ *   - semi-implicit Euler on SO(3), h = sim_dt / substeps.
+ *
+ * It is deliberately written differently from the kernel (serial per env, full 6x6 matrices,
+ * generic matrix products) so that agreement is evidence, not tautology.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may call
+ * into this library.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../include/b200env.h"
+
+typedef double real;
+
+static void q_mul(const real* a, const real* b, real* o) {
+  real x1 = a[0], y1 = a[1], z1 = a[2], w1 = a[3], x2 = b[0], y2 = b[1], z2 = b[2], w2 = b[3];
+  o[0] = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
+  o[1] = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
+  o[2] = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
+  o[3] = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
+}
+static void q_norm(real* q) {
+  real n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int k = 0; k < 4; k++) q[k] /= n;
+}
+static void q_to_mat(const real* q, real R[3][3]) {
+  real x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0][0] = 1 - 2 * (y * y + z * z); R[0][1] = 2 * (x * y - z * w); R[0][2] = 2 * (x * z + y * w);
+  R[1][0] = 2 * (x * y + z * w); R[1][1] = 1 - 2 * (x * x + z * z); R[1][2] = 2 * (y * z - x * w);
+  R[2][0] = 2 * (x * z - y * w); R[2][1] = 2 * (y * z + x * w); R[2][2] = 1 - 2 * (x * x + y * y);
+}
+/* exp: rotation vector -> unit quaternion */
+static void q_exp(const real* v, real* q) {
+  real a2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  real a = sqrt(a2), s;
+  if (a < 1e-6) s = 0.5 - a2 / 48.0; else s = sin(0.5 * a) / a;
+  q[0] = s * v[0]; q[1] = s * v[1]; q[2] = s * v[2]; q[3] = cos(0.5 * a);
+}
+/* log: unit quaternion -> rotation vector with angle in [0, pi] */
+static void q_log(const real* qin, real* v) {
+  real q[4] = {qin[0], qin[1], qin[2], qin[3]};
+  if (q[3] < 0) for (int k = 0; k < 4; k++) q[k] = -q[k];
+  real s2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+  real s = sqrt(s2), f;
+  if (s < 1e-6) f = 2.0 + s2 / 3.0; else f = 2.0 * atan2(s, q[3]) / s;
+  v[0] = f * q[0]; v[1] = f * q[1]; v[2] = f * q[2];
+}
+static void cross(const real* a, const real* b, real* o) {
+  real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+static void matvec3(real M[3][3], const real* v, real* o) {
+  real t[3];
+  for (int i = 0; i < 3; i++) t[i] = M[i][0] * v[0] + M[i][1] * v[1] + M[i][2] * v[2];
+  o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
+}
+static void matTvec3(real M[3][3], const real* v, real* o) {
+  real t[3];
+  for (int i = 0; i < 3; i++) t[i] = M[0][i] * v[0] + M[1][i] * v[1] + M[2][i] * v[2];
+  o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
+}
+static void skew(const real* r, real X[3][3]) {
+  X[0][0] = 0; X[0][1] = -r[2]; X[0][2] = r[1];
+  X[1][0] = r[2]; X[1][1] = 0; X[1][2] = -r[0];
+  X[2][0] = -r[1]; X[2][1] = r[0]; X[2][2] = 0;
+}
+static int inv3(real M[3][3], real O[3][3]) {
+  real c00 = M[1][1] * M[2][2] - M[1][2] * M[2][1];
+  real c01 = M[1][2] * M[2][0] - M[1][0] * M[2][2];
+  real c02 = M[1][0] * M[2][1] - M[1][1] * M[2][0];
+  real det = M[0][0] * c00 + M[0][1] * c01 + M[0][2] * c02;
+  if (!(fabs(det) > 0)) return -1;
+  real id = 1.0 / det;
+  O[0][0] = c00 * id; O[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) * id; O[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) * id;
+  O[1][0] = c01 * id; O[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) * id; O[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) * id;
+  O[2][0] = c02 * id; O[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) * id; O[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) * id;
+  return 0;
+}
+/* solve the 6x6 SPD system M x = b by Cholesky */
+static int solve6(real M[6][6], const real* b, real* x) {
+  real L[6][6];
+  memset(L, 0, sizeof(L));
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j <= i; j++) {
+      real s = M[i][j];
+      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+      if (i == j) { if (!(s > 0)) return -1; L[i][i] = sqrt(s); }
+      else L[i][j] = s / L[j][j];
+    }
+  real y[6];
+  for (int i = 0; i < 6; i++) { real s = b[i]; for (int k = 0; k < i; k++) s -= L[i][k] * y[k]; y[i] = s / L[i][i]; }
+  for (int i = 5; i >= 0; i--) { real s = y[i]; for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k]; x[i] = s / L[i][i]; }
+  return 0;
+}
+
+typedef struct {
+  real Q[4], R[3][3], p[3], w[3], v[3];      /* world pose / velocity of the body origin */
+  real r[3];                                 /* p - p_parent */
+  real zeta[6];                              /* velocity-product acceleration */
+  real IA[6][6], bA[6];
+  real Dinv[3][3], u[3];
+  real A[6];                                 /* (alpha, a) */
+  real qj[4], wt[3];                         /* joint quaternion (child in parent), joint velocity (child frame) */
+} body_t;
+
+static void rank1(real IA[6][6], const real* J, real k) {
+  for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) IA[a][b] += k * J[a] * J[b];
+}
+
+/* one substep of length h for one env; ext = wrench (force, torque) on body 0 or NULL */
+static int substep(const b200_model_t* m, const float* verts, const b200_cfg_t* cfg, real h, body_t* B,
+                   const real* pd_tar, const real* ext, real* contact_f) {
+  int nb = m->nb;
+  real g[3] = {0, 0, cfg->gravity_z};
+  /* 1. kinematics */
+  q_to_mat(B[0].Q, B[0].R);
+  for (int i = 1; i < nb; i++) {
+    body_t* b = &B[i]; body_t* P = &B[m->parent[i]];
+    real off[3] = {m->offset[i][0], m->offset[i][1], m->offset[i][2]};
+    matvec3(P->R, off, b->r);
+    for (int k = 0; k < 3; k++) b->p[k] = P->p[k] + b->r[k];
+    real wxr[3]; cross(P->w, b->r, wxr);
+    for (int k = 0; k < 3; k++) b->v[k] = P->v[k] + wxr[k];
+    if (m->fixed[i]) {
+      memcpy(b->Q, P->Q, sizeof(b->Q)); memcpy(b->R, P->R, sizeof(b->R)); memcpy(b->w, P->w, sizeof(b->w));
+      continue;
+    }
+    q_mul(P->Q, b->qj, b->Q); q_norm(b->Q); q_to_mat(b->Q, b->R);
+    real wj[3]; matvec3(b->R, b->wt, wj);
+    for (int k = 0; k < 3; k++) b->w[k] = P->w[k] + wj[k];
+    cross(P->w, wj, &b->zeta[0]);
+    cross(P->w, wxr, &b->zeta[3]);
+  }
+  /* 2. rigid-body inertia, bias, external + contact + joint forces */
+  for (int i = 0; i < nb; i++) {
+    if (m->fixed[i]) { if (contact_f) contact_f[3 * i] = contact_f[3 * i + 1] = contact_f[3 * i + 2] = 0; continue; }
+    body_t* b = &B[i];
+    real ms = m->mass[i];
+    real cl[3] = {m->com[i][0], m->com[i][1], m->com[i][2]}, c[3];
+    matvec3(b->R, cl, c);
+    real Ib[3][3] = {{m->inertia[i][0], m->inertia[i][3], m->inertia[i][4]},
+                     {m->inertia[i][3], m->inertia[i][1], m->inertia[i][5]},
+                     {m->inertia[i][4], m->inertia[i][5], m->inertia[i][2]}};
+    real Io[3][3];
+    for (int a = 0; a < 3; a++) for (int d = 0; d < 3; d++) {
+      real s = 0;
+      for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++) s += b->R[a][k] * Ib[k][l] * b->R[d][l];
+      Io[a][d] = s + ms * ((a == d ? (c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) : 0.0) - c[a] * c[d]);
+    }
+    real Cx[3][3]; skew(c, Cx);
+    memset(b->IA, 0, sizeof(b->IA));
+    for (int a = 0; a < 3; a++) for (int d = 0; d < 3; d++) {
+      b->IA[a][d] = Io[a][d];
+      b->IA[a][3 + d] = ms * Cx[a][d];
+      b->IA[3 + a][d] = ms * Cx[d][a];
+      b->IA[3 + a][3 + d] = (a == d) ? ms : 0.0;
+    }
+    real Iw[3], wxIw[3], wxc[3], wxwxc[3], cxg[3];
+    matvec3(Io, b->w, Iw); cross(b->w, Iw, wxIw);
+    cross(b->w, c, wxc); cross(b->w, wxc, wxwxc);
+    cross(c, g, cxg);
+    for (int k = 0; k < 3; k++) { b->bA[k] = wxIw[k] - ms * cxg[k]; b->bA[3 + k] = ms * wxwxc[k] - ms * g[k]; }
+    if (i == 0 && ext) { /* force acts at the COM of body 0 (apply_rigid_body_force_tensors, ENV_SPACE) */
+      real cxF[3]; cross(c, ext, cxF);
+      for (int k = 0; k < 3; k++) { b->bA[k] -= ext[3 + k] + cxF[k]; b->bA[3 + k] -= ext[k]; }
+    }
+    /* ground contact of hull vertices (plane z = 0) */
+    real fsum[3] = {0, 0, 0};
+    if (m->nverts[i] > 0 && b->p[2] - m->radius[i] < 0) {
+      for (int k = 0; k < m->nverts[i]; k++) {
+        const float* vl = verts + ((size_t)i * m->vmax + k) * 3;
+        real vb[3] = {vl[0], vl[1], vl[2]}, rho[3];
+        matvec3(b->R, vb, rho);
+        real pen = -(b->p[2] + rho[2]);
+        if (!(pen > 0)) continue;
+        real wxrho[3], uu[3]; cross(b->w, rho, wxrho);
+        for (int a = 0; a < 3; a++) uu[a] = b->v[a] + wxrho[a];
+        real fn0 = cfg->contact_kn * pen - cfg->contact_cn * uu[2];
+        if (!(fn0 > 0)) continue;
+        real n[3] = {0, 0, 1}, tx[3] = {1, 0, 0}, ty[3] = {0, 1, 0};
+        real Jn[6], Jx[6], Jy[6];
+        cross(rho, n, Jn); cross(rho, tx, Jx); cross(rho, ty, Jy);
+        for (int a = 0; a < 3; a++) { Jn[3 + a] = n[a]; Jx[3 + a] = tx[a]; Jy[3 + a] = ty[a]; }
+        real kn_imp = h * cfg->contact_cn + h * h * cfg->contact_kn;
+        rank1(b->IA, Jn, kn_imp);
+        real ut = sqrt(uu[0] * uu[0] + uu[1] * uu[1]);
+        real ct = cfg->friction_mu * fn0 / fmax(ut, (real)cfg->friction_vs);
+        rank1(b->IA, Jx, h * ct); rank1(b->IA, Jy, h * ct);
+        for (int a = 0; a < 6; a++) b->bA[a] -= Jn[a] * fn0 - ct * (Jx[a] * uu[0] + Jy[a] * uu[1]);
+        fsum[0] += -ct * uu[0]; fsum[1] += -ct * uu[1]; fsum[2] += fn0;
+      }
+    }
+    if (contact_f) { contact_f[3 * i] = fsum[0]; contact_f[3 * i + 1] = fsum[1]; contact_f[3 * i + 2] = fsum[2]; }
+    /* joint drive: implicit PD + armature + limit springs (child frame, exp-map chart) */
+    if (i > 0) {
+      int d0 = m->dof_of_body[i];
+      real q[3]; q_log(b->qj, q);
+      real tau[3], e[3];
+      for (int k = 0; k < 3; k++) {
+        real kp = m->kp[d0 + k], kd = m->kd[d0 + k];
+        e[k] = m->armature[d0 + k] + h * kd + h * h * kp;
+        tau[k] = kp * (pd_tar[d0 + k] - q[k] - h * b->wt[k]) - kd * b->wt[k];
+        real lo = m->lim_lo[d0 + k], hi = m->lim_hi[d0 + k];
+        if (q[k] < lo) { tau[k] += cfg->limit_k * (lo - q[k] - h * b->wt[k]) - cfg->limit_c * b->wt[k]; e[k] += h * cfg->limit_c + h * h * cfg->limit_k; }
+        else if (q[k] > hi) { tau[k] += cfg->limit_k * (hi - q[k] - h * b->wt[k]) - cfg->limit_c * b->wt[k]; e[k] += h * cfg->limit_c + h * h * cfg->limit_k; }
+      }
+      matvec3(b->R, tau, b->u); /* u holds tau_w for now */
+      for (int a = 0; a < 3; a++) for (int d = 0; d < 3; d++) {
+        real s = 0;
+        for (int k = 0; k < 3; k++) s += b->R[a][k] * e[k] * b->R[d][k];
+        b->Dinv[a][d] = s; /* Dinv holds E_w for now */
+      }
+    }
+  }
+  /* 3. backward pass */
+  for (int i = nb - 1; i >= 1; i--) {
+    if (m->fixed[i]) continue;
+    body_t* b = &B[i]; body_t* P = &B[m->parent[i]];
+    real D[3][3];
+    for (int a = 0; a < 3; a++) for (int d = 0; d < 3; d++) D[a][d] = b->IA[a][d] + b->Dinv[a][d];
+    if (inv3(D, b->Dinv)) return -1;
+    for (int a = 0; a < 3; a++) b->u[a] -= b->bA[a];
+    real UD[6][3];
+    for (int a = 0; a < 6; a++) for (int d = 0; d < 3; d++) {
+      real s = 0; for (int k = 0; k < 3; k++) s += b->IA[a][k] * b->Dinv[k][d]; UD[a][d] = s;
+    }
+    real Ia[6][6], ba[6];
+    for (int a = 0; a < 6; a++) for (int d = 0; d < 6; d++) {
+      real s = 0; for (int k = 0; k < 3; k++) s += UD[a][k] * b->IA[d][k];
+      Ia[a][d] = b->IA[a][d] - s;
+    }
+    for (int a = 0; a < 6; a++) {
+      real s = b->bA[a];
+      for (int k = 0; k < 6; k++) s += Ia[a][k] * b->zeta[k];
+      for (int k = 0; k < 3; k++) s += UD[a][k] * b->u[k];
+      ba[a] = s;
+    }
+    /* Phi = [[1,0],[-[r]x,1]]  (A_child = Phi A_parent + ...);  parent += Phi^T Ia Phi, Phi^T ba */
+    real Phi[6][6]; memset(Phi, 0, sizeof(Phi));
+    real X[3][3]; skew(b->r, X);
+    for (int a = 0; a < 6; a++) Phi[a][a] = 1;
+    for (int a = 0; a < 3; a++) for (int d = 0; d < 3; d++) Phi[3 + a][d] = -X[a][d];
+    real T[6][6];
+    for (int a = 0; a < 6; a++) for (int d = 0; d < 6; d++) { real s = 0; for (int k = 0; k < 6; k++) s += Ia[a][k] * Phi[k][d]; T[a][d] = s; }
+    for (int a = 0; a < 6; a++) for (int d = 0; d < 6; d++) { real s = 0; for (int k = 0; k < 6; k++) s += Phi[k][a] * T[k][d]; P->IA[a][d] += s; }
+    for (int a = 0; a < 6; a++) { real s = 0; for (int k = 0; k < 6; k++) s += Phi[k][a] * ba[k]; P->bA[a] += s; }
+  }
+  /* 4. root */
+  real nb0[6]; for (int a = 0; a < 6; a++) nb0[a] = -B[0].bA[a];
+  if (solve6(B[0].IA, nb0, B[0].A)) return -2;
+  /* 5. forward pass */
+  for (int i = 1; i < nb; i++) {
+    if (m->fixed[i]) continue;
+    body_t* b = &B[i]; body_t* P = &B[m->parent[i]];
+    real Ap[6], axr[3]; cross(&P->A[0], b->r, axr);
+    for (int k = 0; k < 3; k++) { Ap[k] = P->A[k] + b->zeta[k]; Ap[3 + k] = P->A[3 + k] + axr[k] + b->zeta[3 + k]; }
+    real t[3];
+    for (int a = 0; a < 3; a++) { real s = b->u[a]; for (int k = 0; k < 6; k++) s -= b->IA[k][a] * Ap[k]; t[a] = s; }
+    real gam[3]; matvec3(b->Dinv, t, gam);
+    for (int k = 0; k < 3; k++) { b->A[k] = Ap[k] + gam[k]; b->A[3 + k] = Ap[3 + k]; }
+    real wd[3]; matTvec3(b->R, gam, wd);
+    /* 6a. integrate joint velocity, damping, clamp */
+    real damp = 1.0 - h * cfg->ang_damping;
+    for (int k = 0; k < 3; k++) b->wt[k] = (b->wt[k] + h * wd[k]) * damp;
+    real nn = sqrt(b->wt[0] * b->wt[0] + b->wt[1] * b->wt[1] + b->wt[2] * b->wt[2]);
+    if (nn > cfg->max_ang_vel) for (int k = 0; k < 3; k++) b->wt[k] *= cfg->max_ang_vel / nn;
+  }
+  /* 6b. root velocity + all positions */
+  {
+    body_t* b = &B[0];
+    real damp = 1.0 - h * cfg->ang_damping;
+    for (int k = 0; k < 3; k++) { b->w[k] = (b->w[k] + h * b->A[k]) * damp; b->v[k] += h * b->A[3 + k]; }
+    real nn = sqrt(b->w[0] * b->w[0] + b->w[1] * b->w[1] + b->w[2] * b->w[2]);
+    if (nn > cfg->max_ang_vel) for (int k = 0; k < 3; k++) b->w[k] *= cfg->max_ang_vel / nn;
+    for (int k = 0; k < 3; k++) b->p[k] += h * b->v[k];
+    real hv[3] = {h * b->w[0], h * b->w[1], h * b->w[2]}, dq[4], qn[4];
+    q_exp(hv, dq); q_mul(dq, b->Q, qn); q_norm(qn); memcpy(b->Q, qn, sizeof(qn));
+  }
+  for (int i = 1; i < nb; i++) {
+    if (m->fixed[i]) continue;
+    body_t* b = &B[i];
+    real hv[3] = {h * b->wt[0], h * b->wt[1], h * b->wt[2]}, dq[4], qn[4];
+    q_exp(hv, dq); q_mul(b->qj, dq, qn); q_norm(qn); memcpy(b->qj, qn, sizeof(qn));
+  }
+  return 0;
+}
+
+/* forward kinematics only: fills Q,R,p,w,v of every body from the current state */
+static void fk(const b200_model_t* m, body_t* B) {
+  q_to_mat(B[0].Q, B[0].R);
+  for (int i = 1; i < m->nb; i++) {
+    body_t* b = &B[i]; body_t* P = &B[m->parent[i]];
+    real off[3] = {m->offset[i][0], m->offset[i][1], m->offset[i][2]};
+    matvec3(P->R, off, b->r);
+    real wxr[3]; cross(P->w, b->r, wxr);
+    for (int k = 0; k < 3; k++) { b->p[k] = P->p[k] + b->r[k]; b->v[k] = P->v[k] + wxr[k]; }
+    if (m->fixed[i]) { memcpy(b->Q, P->Q, sizeof(b->Q)); memcpy(b->R, P->R, sizeof(b->R)); memcpy(b->w, P->w, sizeof(b->w)); continue; }
+    q_mul(P->Q, b->qj, b->Q); q_norm(b->Q); q_to_mat(b->Q, b->R);
+    real wj[3]; matvec3(b->R, b->wt, wj);
+    for (int k = 0; k < 3; k++) b->w[k] = P->w[k] + wj[k];
+  }
+}
+
+/* One control step (control_freq_inv sim steps x substeps) for n envs.  Same I/O contract as
+ * b200env_physics_only(prec=1) in include/b200env.h.  Returns 0, or -(env+1) on a failed solve. */
+int phys_ref_control_step(const b200_model_t* m, const float* verts, const b200_cfg_t* cfg, int n, double* root,
+                          double* dof_pos, double* dof_vel, const double* pd_tar, const double* ext_wrench,
+                          double* rb_out, double* contact_out) {
+  int nb = m->nb, nd = m->nd, fail = 0;
+  real h = (real)cfg->sim_dt / cfg->substeps;
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < n; e++) {
+    body_t B[B200_MAX_BODIES];
+    memset(B, 0, sizeof(B));
+    real* rs = root + (size_t)e * 13;
+    memcpy(B[0].p, rs, 3 * sizeof(real)); memcpy(B[0].Q, rs + 3, 4 * sizeof(real)); q_norm(B[0].Q);
+    memcpy(B[0].v, rs + 7, 3 * sizeof(real)); memcpy(B[0].w, rs + 10, 3 * sizeof(real));
+    for (int i = 1; i < nb; i++) {
+      if (m->fixed[i]) continue;
+      int d0 = m->dof_of_body[i];
+      q_exp(dof_pos + (size_t)e * nd + d0, B[i].qj);
+      memcpy(B[i].wt, dof_vel + (size_t)e * nd + d0, 3 * sizeof(real));
+    }
+    real cf[3 * B200_MAX_BODIES];
+    int err = 0;
+    for (int s = 0; s < cfg->control_freq_inv && !err; s++)
+      for (int k = 0; k < cfg->substeps && !err; k++)
+        err = substep(m, verts, cfg, h, B, pd_tar + (size_t)e * nd, (s == 0 && ext_wrench) ? ext_wrench + (size_t)e * 6 : 0, cf);
+    if (err) {
+#pragma omp critical
+      if (!fail) fail = -(e + 1);
+      continue;
+    }
+    fk(m, B);
+    memcpy(rs, B[0].p, 3 * sizeof(real)); memcpy(rs + 3, B[0].Q, 4 * sizeof(real));
+    memcpy(rs + 7, B[0].v, 3 * sizeof(real)); memcpy(rs + 10, B[0].w, 3 * sizeof(real));
+    for (int i = 1; i < nb; i++) {
+      if (m->fixed[i]) continue;
+      int d0 = m->dof_of_body[i];
+      q_log(B[i].qj, dof_pos + (size_t)e * nd + d0);
+      memcpy(dof_vel + (size_t)e * nd + d0, B[i].wt, 3 * sizeof(real));
+    }
+    for (int i = 0; i < nb; i++) {
+      real* o = rb_out + ((size_t)e * nb + i) * 13;
+      memcpy(o, B[i].p, 3 * sizeof(real)); memcpy(o + 3, B[i].Q, 4 * sizeof(real));
+      memcpy(o + 7, B[i].v, 3 * sizeof(real)); memcpy(o + 10, B[i].w, 3 * sizeof(real));
+      if (contact_out) memcpy(contact_out + ((size_t)e * nb + i) * 3, cf + 3 * i, 3 * sizeof(real));
+    }
+  }
+  return fail;
+}
+
+/* diagnostics for invariant tests: total mass, COM, linear momentum, angular momentum about the
+ * COM, kinetic energy and gravitational potential of one env state.  out[0..13]. */
+int phys_ref_diagnostics(const b200_model_t* m, const b200_cfg_t* cfg, const double* root, const double* dof_pos,
+                         const double* dof_vel, double* out) {
+  body_t B[B200_MAX_BODIES];
+  memset(B, 0, sizeof(B));
+  memcpy(B[0].p, root, 3 * sizeof(real)); memcpy(B[0].Q, root + 3, 4 * sizeof(real)); q_norm(B[0].Q);
+  memcpy(B[0].v, root + 7, 3 * sizeof(real)); memcpy(B[0].w, root + 10, 3 * sizeof(real));
+  for (int i = 1; i < m->nb; i++) {
+    if (m->fixed[i]) continue;
+    q_exp(dof_pos + m->dof_of_body[i], B[i].qj);
+    memcpy(B[i].wt, dof_vel + m->dof_of_body[i], 3 * sizeof(real));
+  }
+  fk(m, B);
+  real M = 0, com[3] = {0, 0, 0}, P[3] = {0, 0, 0}, L0[3] = {0, 0, 0}, ke = 0, pe = 0;
+  for (int i = 0; i < m->nb; i++) {
+    if (m->fixed[i]) continue;
+    body_t* b = &B[i];
+    real ms = m->mass[i], cl[3] = {m->com[i][0], m->com[i][1], m->com[i][2]}, c[3], x[3], wxc[3], vc[3];
+    matvec3(b->R, cl, c); cross(b->w, c, wxc);
+    for (int k = 0; k < 3; k++) { x[k] = b->p[k] + c[k]; vc[k] = b->v[k] + wxc[k]; }
+    real Ib[3][3] = {{m->inertia[i][0], m->inertia[i][3], m->inertia[i][4]},
+                     {m->inertia[i][3], m->inertia[i][1], m->inertia[i][5]},
+                     {m->inertia[i][4], m->inertia[i][5], m->inertia[i][2]}};
+    real wl[3], Iwl[3], Iw[3], xv[3];
+    matTvec3(b->R, b->w, wl); matvec3(Ib, wl, Iwl); matvec3(b->R, Iwl, Iw); cross(x, vc, xv);
+    M += ms;
+    for (int k = 0; k < 3; k++) { com[k] += ms * x[k]; P[k] += ms * vc[k]; L0[k] += Iw[k] + ms * xv[k]; }
+    ke += 0.5 * ms * (vc[0] * vc[0] + vc[1] * vc[1] + vc[2] * vc[2]) + 0.5 * (wl[0] * Iwl[0] + wl[1] * Iwl[1] + wl[2] * Iwl[2]);
+    pe += -ms * cfg->gravity_z * x[2];
+  }
+  for (int k = 0; k < 3; k++) com[k] /= M;
+  real cP[3]; cross(com, P, cP);
+  out[0] = M;
+  for (int k = 0; k < 3; k++) { out[1 + k] = com[k]; out[4 + k] = P[k]; out[7 + k] = L0[k] - cP[k]; }
+  out[10] = ke; out[11] = pe;
+  return 0;
+}

@@ -1,0 +1,56 @@
+"""ORACLE wrapper (test infrastructure): ctypes binding of oracle/build/libphysref.so, the float64
+CPU restatement of the articulated control step.  See oracle/physics_ref.c for the scope note
+("parity unpinned" versus Isaac Gym)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "build", "libphysref.so")
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "physics_ref.c")):
+        subprocess.check_call(["make", "-C", HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        _lib = C.CDLL(LIB)
+        _lib.phys_ref_control_step.restype = C.c_int
+        _lib.phys_ref_diagnostics.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def control_step(model, verts, cfg, root, dof_pos, dof_vel, pd_tar, ext_wrench=None, n_steps=1):
+    """In-place on float64 arrays root[n,13], dof_pos[n,nd], dof_vel[n,nd]; returns (rb[n,nb,13], contact[n,nb,3])."""
+    n = root.shape[0]
+    for a in (root, dof_pos, dof_vel, pd_tar):
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+    rb = np.zeros((n, model.nb, 13))
+    cf = np.zeros((n, model.nb, 3))
+    verts = np.ascontiguousarray(verts, np.float32)
+    for _ in range(n_steps):
+        rc = lib().phys_ref_control_step(C.byref(model), _p(verts), C.byref(cfg), C.c_int(n), _p(root), _p(dof_pos),
+                                         _p(dof_vel), _p(pd_tar), _p(ext_wrench), _p(rb), _p(cf))
+        if rc != 0:
+            raise RuntimeError(f"phys_ref_control_step failed for env {-rc - 1}")
+    return rb, cf
+
+
+def diagnostics(model, cfg, root, dof_pos, dof_vel):
+    out = np.zeros(12)
+    lib().phys_ref_diagnostics(C.byref(model), C.byref(cfg), _p(np.ascontiguousarray(root)), _p(np.ascontiguousarray(dof_pos)),
+                               _p(np.ascontiguousarray(dof_vel)), _p(out))
+    return dict(mass=out[0], com=out[1:4], P=out[4:7], L=out[7:10], ke=out[10], pe=out[11])

@@ -1,0 +1,282 @@
+"""GPU parity tests (run on the B200 box): CUDA path through the C ABI vs the oracles.
+
+Chain of trust: reference functions -> golden fixtures -> numpy oracle (tests/test_oracle_golden.py)
+-> these tests.  The physics half compares against oracle/physics_ref.c (float64 restatement of OUR
+model; parity with Isaac Gym / PhysX is unpinned)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from helpers import SIM_PARAMS, im_cfg, lib_dict, rand_quat
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model():
+    from vid2player3d_b200 import model_compiler
+    return model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+
+
+@pytest.fixture(scope="module")
+def small_lib(model):
+    from vid2player3d_b200 import motion_lib
+    flat = motion_lib.synthetic(model, num_motions=6, num_frames=60, seed=3, sigma=0.06, ragged=True)
+    flat.min_verts_h = np.linspace(-0.02, 0.03, 6).astype(np.float32)
+    flat.motion_bodies = np.random.default_rng(5).normal(size=(6, 11)).astype(np.float32)
+    return flat
+
+
+def make_task(n, lib, **kw):
+    from vid2player3d_b200.tasks import HumanoidSMPLIM
+    return HumanoidSMPLIM(im_cfg(n, lib, **kw), SIM_PARAMS, 1, "cuda", 0, True)
+
+
+def phys_states(model, n, seed, contact=True):
+    rng = np.random.default_rng(seed)
+    root = np.zeros((n, 13))
+    root[:, 0:2] = rng.uniform(-3, 3, (n, 2))
+    root[:, 2] = rng.uniform(0.7, 1.1, n) if contact else rng.uniform(3, 5, n)
+    root[:, 3:7] = rand_quat(rng, n)
+    root[: n // 2, 3:7] = [0.5, 0.5, 0.5, 0.5]  # upright half
+    root[:, 7:10] = rng.normal(0, 0.5, (n, 3))
+    root[:, 10:13] = rng.normal(0, 1.0, (n, 3))
+    q = rng.normal(0, 0.3, (n, 69))
+    qd = rng.normal(0, 1.5, (n, 69))
+    tar = q + rng.normal(0, 0.2, (n, 69))
+    ext = rng.normal(0, 30, (n, 6))
+    return root, q, qd, tar, ext
+
+
+def run_kernel_physics(task, root, q, qd, tar, ext, dtype, n_steps=1):
+    dev = task.device
+    t = lambda a: torch.tensor(a, dtype=dtype, device=dev).contiguous()  # noqa: E731
+    r, qq, vv, tt, ee = t(root), t(q), t(qd), t(tar), t(ext)
+    n = root.shape[0]
+    rb = torch.zeros(n, task.num_bodies, 13, dtype=dtype, device=dev)
+    cf = torch.zeros(n, task.num_bodies, 3, dtype=dtype, device=dev)
+    task._env.physics_only(r, qq, vv, tt, ee, rb, cf, n_steps=n_steps)
+    torch.cuda.synchronize()
+    return [x.double().cpu().numpy() for x in (r, qq, vv, rb, cf)]
+
+
+def run_oracle_physics(task, root, q, qd, tar, ext, n_steps=1):
+    from oracle import physics_ref
+    r, qq, vv = root.copy(), q.copy(), qd.copy()
+    rb, cf = physics_ref.control_step(task._model_struct, task._verts, task._cfg_struct, r, qq, vv, tar.copy(), ext.copy(),
+                                      n_steps=n_steps)
+    return r, qq, vv, rb, cf
+
+
+@pytest.mark.parametrize("contact", [False, True])
+def test_physics_f64_matches_oracle(model, small_lib, contact):
+    """same algorithm, float64 on both sides: agreement to round-off over 1 and 8 control steps"""
+    task = make_task(4, small_lib)
+    st = phys_states(model, 32, 11, contact)
+    for steps, tol in ((1, 1e-9), (8, 1e-7)):
+        k = run_kernel_physics(task, *st, torch.float64, steps)
+        o = run_oracle_physics(task, *st, steps)
+        for a, b, name in zip(k, o, ("root", "dof_pos", "dof_vel", "rb", "contact")):
+            scale = 1.0 if name != "contact" else 1e3
+            np.testing.assert_allclose(a, b, rtol=0, atol=tol * scale, err_msg=f"{name} steps={steps}")
+    if contact:
+        assert np.abs(o[4]).max() > 10.0  # the contact branch was exercised
+
+
+def test_physics_f32_config1_drop(model, small_lib):
+    """BASELINE config 1: one humanoid, default pose (identity root at z=0.89), zero action, 60 control
+    steps incl. ground impact; float32 kernel vs float64 restatement, tolerance 1e-4 on q and 1e-3 on qd
+    (north_star: joint q/qd within 1e-4 - qd is held to 1e-3 through the impact)."""
+    task = make_task(4, small_lib)
+    root = np.zeros((1, 13)); root[0, 2] = 0.89; root[0, 6] = 1.0
+    q = np.zeros((1, 69)); qd = np.zeros((1, 69)); tar = np.zeros((1, 69)); ext = np.zeros((1, 6))
+    worst_q = worst_qd = 0.0
+    for steps in (10, 30, 60):
+        k = run_kernel_physics(task, root, q, qd, tar, ext, torch.float32, steps)
+        o = run_oracle_physics(task, root, q, qd, tar, ext, steps)
+        worst_q = max(worst_q, np.abs(k[1] - o[1]).max(), np.abs(k[0][:, :7] - o[0][:, :7]).max())
+        worst_qd = max(worst_qd, np.abs(k[2] - o[2]).max())
+    print(f"config1 drop: max |dq| {worst_q:.3e}  max |dqd| {worst_qd:.3e}")
+    assert o[0][0, 2] < 0.3 and np.abs(o[4]).max() > 100  # it did land
+    assert worst_q < 1e-4
+    assert worst_qd < 1e-3
+
+
+def test_physics_f32_random_one_step(model, small_lib):
+    task = make_task(4, small_lib)
+    st = phys_states(model, 256, 5, True)
+    k = run_kernel_physics(task, *st, torch.float32, 1)
+    o = run_oracle_physics(task, *st, 1)
+    assert np.abs(k[1] - o[1]).max() < 1e-4 and np.abs(k[0] - o[0]).max() < 1e-4
+    assert np.abs(k[2] - o[2]).max() < 2e-3
+    assert np.abs(k[3] - o[3]).max() < 2e-3
+
+
+def test_motion_state_golden():
+    """b200env_motion_state vs fixtures from the reference's MotionLib.get_motion_state"""
+    from vid2player3d_b200 import motion_lib
+    g = golden("motion_state.npz")
+    flat = motion_lib.FlatMotionLib(**{k[4:]: g[k] for k in g if k.startswith("lib_")})
+    task = make_task(4, flat)
+    dev = task.device
+    n = len(g["motion_ids"])
+    ids = torch.tensor(g["motion_ids"], device=dev)
+    times = torch.tensor(g["motion_times"], device=dev)
+    shapes = dict(root_pos=(n, 3), root_rot=(n, 4), dof_pos=(n, 69), root_vel=(n, 3), root_ang_vel=(n, 3), dof_vel=(n, 69),
+                  key_pos=(n, 4, 3), rb_pos=(n, 24, 3), rb_rot=(n, 24, 4))
+    out = {k: torch.zeros(*s, device=dev) for k, s in shapes.items()}
+    task._env.motion_state(ids, times, out)
+    for k in shapes:
+        np.testing.assert_allclose(out[k].cpu().numpy(), g[k], rtol=0, atol=1e-5, err_msg=k)
+
+
+def test_obs_imitation_golden(small_lib):
+    """b200env_obs_imitation vs fixtures from the reference's compute_humanoid_observations_imitation (1e-5)"""
+    g = golden("obs_imitation.npz")
+    task = make_task(4, small_lib)
+    names = ("body_pos", "body_rot", "target_pos", "target_rot", "dof_pos", "dof_vel", "target_dof_pos", "body_vel",
+             "body_ang_vel", "motion_bodies")
+    args = [torch.tensor(g[k], device=task.device) for k in names]
+    obs = task.compute_imitation_obs(*args, True, True)
+    np.testing.assert_allclose(obs.cpu().numpy(), g["obs"], rtol=0, atol=1e-5)
+    obs = task.compute_imitation_obs(*args, False, False)
+    np.testing.assert_allclose(obs.cpu().numpy(), g["obs_nolocal_noheight"], rtol=0, atol=1e-5)
+
+
+def snapshot(task):
+    g = lambda t: t.detach().cpu().numpy().copy()  # noqa: E731
+    return dict(root=g(task._root_states), dofs=g(task._dof_state.view(task.num_envs, -1, 2)),
+                rbs=g(task._rigid_body_state.view(task.num_envs, -1, 13)), obs=g(task.obs_buf), rew=g(task.rew_buf),
+                sub=g(task._sub_rewards), reset=g(task.reset_buf), term=g(task._terminate_buf), prog=g(task.progress_buf),
+                times=g(task._cur_ref_motion_times), t_dof=g(task._target_dof_pos), t_dofv=g(task._target_dof_vel),
+                t_rbp=g(task._target_rb_pos), t_rbr=g(task._target_rb_rot), t_key=g(task._target_key_pos),
+                t_rootp=g(task._target_root_pos), t_rootr=g(task._target_root_rot), t_rootv=g(task._target_root_vel),
+                pd=g(task._pd_target_dof_pos), acts=g(task.actions), cf=g(task._contact_forces))
+
+
+def test_fused_step_vs_oracle(model, small_lib):
+    """reset + 12 fused steps on 64 envs vs (numpy task oracle + float64 physics oracle), re-synchronised to
+    the GPU state every step so that each step's arithmetic is checked in isolation."""
+    from oracle import physics_ref, ref_port as R
+    torch.manual_seed(0)
+    N = 64
+    task = make_task(N, small_lib, episodeLength=10)
+    ml = lib_dict(small_lib, model)
+    task.reset()
+    torch.cuda.synchronize()
+    s = snapshot(task)
+    mids = task._reset_ref_motion_ids.cpu().numpy()
+    t0 = task._reset_ref_motion_times.cpu().numpy()
+    # reset state = MoCap state at t0 (humanoid_smpl_im.py:489-528)
+    ms = R.get_motion_state(ml, mids, t0)
+    np.testing.assert_allclose(s["root"][:, 0:3], ms[0], atol=1e-5)
+    np.testing.assert_allclose(s["root"][:, 3:7], ms[1], atol=1e-5)
+    np.testing.assert_allclose(s["dofs"][..., 0], ms[2], atol=1e-5)
+    np.testing.assert_allclose(s["root"][:, 7:10], ms[3], atol=1e-5)
+    np.testing.assert_allclose(s["dofs"][..., 1], ms[5], atol=1e-5)
+    np.testing.assert_allclose(s["rbs"][..., 0:3], ms[7], atol=1e-5)
+    np.testing.assert_allclose(s["rbs"][..., 3:7], ms[8], atol=1e-5)
+    assert np.all(s["rbs"][..., 7:] == 0) and np.all(s["prog"] == 0) and np.all(s["reset"] == 0) and np.all(s["term"] == 0)
+    np.testing.assert_allclose(s["obs"], R.compute_humanoid_obs_raw(s["rbs"][..., 0:3], s["rbs"][..., 3:7], s["dofs"][..., 0],
+                                                                   s["dofs"][..., 1], s["rbs"][..., 7:10], s["rbs"][..., 10:13],
+                                                                   ml["motion_bodies"][mids]), atol=1e-6)
+    orc = R.ImTaskOracle(ml, mids, s["times"], s["prog"], s["reset"], s["term"], np.float32(2) * np.float32(1.0 / 60.0), 10,
+                         task._termination_heights.cpu().numpy(), task._contact_body_ids.cpu().numpy(),
+                         np.ones(24, np.float32), ml["motion_bodies"][mids])
+    np.testing.assert_allclose(s["t_dof"], orc.t_dof_pos, atol=1e-5)
+    np.testing.assert_allclose(s["t_rbp"], orc.t_rb_pos, atol=1e-5)
+    n_reset_seen = 0
+    for step in range(12):
+        actions = torch.clamp(torch.randn(N, 75, device=task.device), -1, 1)
+        if step == 3:
+            actions[:, :69] *= 3
+        before = s
+        task.step(actions)
+        torch.cuda.synchronize()
+        s = snapshot(task)
+        a_used, pd, f, tq = orc.pre_physics(actions.cpu().numpy(), before["dofs"][..., 0], before["rbs"][:, 0, 3:7])
+        np.testing.assert_allclose(s["acts"], a_used, atol=0)
+        np.testing.assert_allclose(s["pd"], pd, atol=1e-6)
+        # physics: float64 oracle from the same pre-step state
+        root = before["root"].astype(np.float64); q = before["dofs"][..., 0].astype(np.float64).copy()
+        qd = before["dofs"][..., 1].astype(np.float64).copy()
+        ext = np.concatenate([f, tq], -1).astype(np.float64)
+        rb, cf = physics_ref.control_step(task._model_struct, task._verts, task._cfg_struct, root, q, qd, pd.astype(np.float64), ext)
+        np.testing.assert_allclose(s["root"], root, atol=2e-4, err_msg=f"root step {step}")
+        np.testing.assert_allclose(s["dofs"][..., 0], q, atol=2e-4, err_msg=f"q step {step}")
+        np.testing.assert_allclose(s["dofs"][..., 1], qd, atol=5e-3, err_msg=f"qd step {step}")
+        np.testing.assert_allclose(s["rbs"], rb, atol=5e-3, err_msg=f"rb step {step}")
+        # task logic on the GPU's own post-physics state: obs / reward / reset / targets within 1e-5
+        obs, rew, sub = orc.post_physics(s["rbs"], s["dofs"])
+        np.testing.assert_allclose(s["obs"], obs, atol=1e-6)
+        np.testing.assert_allclose(s["rew"], rew, atol=1e-5)
+        np.testing.assert_allclose(s["sub"], sub, atol=1e-5)
+        assert np.array_equal(s["reset"], orc.reset_buf) and np.array_equal(s["term"], orc.terminate_buf)
+        assert np.array_equal(s["prog"], orc.progress)
+        np.testing.assert_allclose(s["times"], orc.ref_times, atol=1e-6)
+        np.testing.assert_allclose(s["t_dof"], orc.t_dof_pos, atol=1e-5)
+        np.testing.assert_allclose(s["t_dofv"], orc.t_dof_vel, atol=1e-5)
+        np.testing.assert_allclose(s["t_rbp"], orc.t_rb_pos, atol=1e-5)
+        np.testing.assert_allclose(s["t_rbr"], orc.t_rb_rot, atol=1e-5)
+        np.testing.assert_allclose(s["t_key"], orc.t_key_pos, atol=1e-5)
+        np.testing.assert_allclose(s["t_rootp"], orc.t_root_pos, atol=1e-5)
+        np.testing.assert_allclose(s["t_rootr"], orc.t_root_rot, atol=1e-5)
+        np.testing.assert_allclose(s["t_rootv"], orc.t_root_vel, atol=1e-5)
+        n_reset_seen = int(s["reset"].sum())
+    assert n_reset_seen == N  # episodeLength 10: every env hit the sticky reset flag, rewards went to zero
+    assert np.all(s["rew"] == 0)
+
+
+def test_full_size_properties(model):
+    """BASELINE size (8192 envs): determinism, finiteness, obs/state consistency, resets."""
+    from vid2player3d_b200 import motion_lib
+    flat = motion_lib.synthetic(model, num_motions=64, num_frames=300, seed=7)
+    N = 8192
+    outs = []
+    for rep in range(2):
+        torch.manual_seed(123)
+        task = make_task(N, flat, episodeLength=300)
+        task.reset()
+        g = torch.Generator(device=task.device).manual_seed(9)
+        for step in range(40):
+            a = torch.rand(N, 75, device=task.device, generator=g) * 2 - 1
+            task.step(a)
+        torch.cuda.synchronize()
+        outs.append((task.obs_buf.clone(), task.rew_buf.clone(), task.reset_buf.clone(), task._root_states.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)  # bit-identical across runs (no atomics, fixed reduction order)
+    obs, rew, reset, root = outs[0]
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert (rew >= 0).all() and (rew <= 1.0 + 1e-6).all()
+    assert torch.equal(obs[:, :72], task._rigid_body_pos.reshape(N, -1))
+    assert torch.equal(obs[:, 72:168], task._rigid_body_rot.reshape(N, -1))
+    assert torch.equal(obs[:, 168:237], task._dof_pos)
+    assert torch.equal(obs[:, 237:306], task._dof_vel)
+    qn = task._rigid_body_rot.norm(dim=-1)
+    assert (qn - 1).abs().max() < 1e-4
+    assert task._env.launch_count >= 41
+
+
+def test_empty_and_partial_reset(model, small_lib):
+    task = make_task(16, small_lib)
+    task.reset()
+    task.reset(torch.zeros(0, dtype=torch.long, device=task.device))  # empty id list is a no-op
+    for _ in range(3):
+        task.step(torch.zeros(16, 75, device=task.device))
+    torch.cuda.synchronize()
+    before = task.progress_buf.clone()
+    ids = torch.tensor([3, 7], device=task.device)
+    task.reset(ids)
+    torch.cuda.synchronize()
+    assert task.progress_buf[3] == 0 and task.progress_buf[7] == 0
+    keep = torch.ones(16, dtype=torch.bool, device=task.device); keep[ids] = False
+    assert torch.equal(task.progress_buf[keep], before[keep])
+    assert task.context_feat.shape == (16, 48, 378) and task.context_mask.shape == (16, 48)
+
+
+def test_missing_arguments_fail_loudly(small_lib):
+    from vid2player3d_b200 import native
+    task = make_task(4, small_lib)
+    with pytest.raises(RuntimeError):
+        native._check(native.lib().b200env_step(task._env._h, None, None))

@@ -1,0 +1,159 @@
+"""CPU-side checks: C ABI exports, struct layouts, shim cross-checks, model compiler, host logic."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vid2player3d_b200 import build, native
+    lib = build.build()
+    hdr = open(os.path.join(ROOT, "include", "b200env.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200env_[a-z_]+)\s*\(", hdr)))
+    assert declared == sorted(native.SYMBOLS)
+    L = C.CDLL(lib)  # loads without a GPU; no compute call is made here
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.b200env_abi_version() == 1
+
+
+def test_struct_layouts_match_header(tmp_path):
+    from vid2player3d_b200 import abi
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s/include/b200env.h"\n'
+                   'int main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n",sizeof(b200_model_t),sizeof(b200_cfg_t),'
+                   'sizeof(b200_motion_lib_t),sizeof(b200_buffers_t),offsetof(b200_model_t,kp),offsetof(b200_cfg_t,key_body));}' % ROOT)
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(abi.Model), C.sizeof(abi.Cfg), C.sizeof(abi.MotionLibView), C.sizeof(abi.Buffers), abi.Model.kp.offset,
+            abi.Cfg.key_body.offset]
+    assert got == want
+
+
+def test_no_gpu_means_loud_failure():
+    """the product path has no CPU fallback: creating an env without a CUDA device raises"""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from vid2player3d_b200 import abi, model_compiler, native
+    mod = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    m, v = abi.pack_model(mod, 1.0)
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA error"):
+        native.Env(m, v, abi.make_cfg(mod), 4, 0)
+    from vid2player3d_b200.tasks import BaseTask
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        BaseTask({"device_type": "cpu", "headless": True, "env": {"numEnvs": 1}})
+
+
+def test_shim_quaternion_helpers_match_poselib_conventions():
+    """the only foreign arithmetic of the oracle (isaacgym.torch_utils) is cross-checked against the
+    reference's own poselib definitions when the reference tree is present, else against closed forms"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "vid2player3d_b200", "shim"))
+    from isaacgym import torch_utils as IG
+    g = torch.Generator().manual_seed(0)
+    a = torch.nn.functional.normalize(torch.randn(64, 4, generator=g), dim=-1)
+    b = torch.nn.functional.normalize(torch.randn(64, 4, generator=g), dim=-1)
+    v = torch.randn(64, 3, generator=g)
+    if os.path.isdir("/root/reference/poselib"):
+        sys.path.insert(0, "/root/reference/poselib")
+        from poselib.core import rotation3d as P
+        assert torch.allclose(IG.quat_mul(a, b), P.quat_mul(a, b), atol=1e-6)
+        assert torch.allclose(IG.quat_conjugate(a), P.quat_conjugate(a))
+        ang = torch.rand(64, generator=g) * 6 - 3
+        assert torch.allclose(IG.quat_from_angle_axis(ang, v), P.quat_from_angle_axis(ang, v), atol=1e-6)
+        assert torch.allclose(IG.quat_rotate(a, v), P.quat_rotate(a, v), atol=1e-5)
+    # closed forms
+    ident = torch.tensor([[0.0, 0, 0, 1]]).repeat(64, 1)
+    assert torch.allclose(IG.quat_mul(a, IG.quat_conjugate(a)), ident, atol=1e-6)
+    assert torch.allclose(IG.quat_rotate(a, v).norm(dim=-1), v.norm(dim=-1), atol=1e-5)
+    assert torch.allclose(IG.normalize_angle(torch.tensor([3.5, -3.5, 0.1])), torch.tensor([3.5 - 2 * np.pi, 2 * np.pi - 3.5, 0.1]), atol=1e-6)
+
+
+def test_compiled_models():
+    from vid2player3d_b200 import abi, model_compiler
+    m = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    assert len(m["parent"]) == 24 and len(m["kp"]) == 69
+    assert m["parent"].tolist() == [-1, 0, 1, 2, 3, 0, 5, 6, 7, 0, 9, 10, 11, 12, 11, 14, 15, 16, 17, 11, 19, 20, 21, 22]
+    assert abs(m["mass"].sum() - 102.418) < 0.01  # SURVEY.md 7 sanity value
+    f = model_compiler.load_compiled("smpl_mesh_humanoid_federer")
+    assert len(f["parent"]) == 25 and f["fixed"][-1] == 1 and str(f["body_names"][-1]) == "Racket"
+    assert abs(f["dyn_mass"].sum() - f["mass"].sum()) < 1e-9 and f["dyn_mass"][-1] == 0
+    ms, verts = abi.pack_model(f, 1.0)
+    assert ms.nb == 25 and ms.vmax % 4 == 0 and verts.shape == (25, ms.vmax, 3)
+    # principal inertias positive, triangle inequality
+    for I in m["inertia"]:
+        w = np.linalg.eigvalsh(I)
+        assert w.min() > 0 and w[0] + w[1] >= w[2] * (1 - 1e-9)
+
+
+def test_model_compiler_reproduces_committed_blob():
+    ref = "/root/reference/embodied_pose/data/assets/mjcf/smpl_mesh_humanoid_amass_v1.xml"
+    if not os.path.exists(ref):
+        pytest.skip("reference assets not present on this box")
+    from vid2player3d_b200 import model_compiler
+    a = model_compiler.compile_mjcf(ref)
+    b = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    for k in ("mass", "com", "inertia", "verts", "kp", "limits", "offset"):
+        np.testing.assert_allclose(a[k], b[k], atol=1e-12)
+
+
+def test_synthetic_motion_lib_is_consistent():
+    """FK consistency of the synthetic MoCap buffer: grs/gts follow from lrs and the skeleton"""
+    from vid2player3d_b200 import model_compiler, motion_lib
+    from oracle import ref_port as R
+    m = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    flat = motion_lib.synthetic(m, num_motions=3, num_frames=20, seed=1, ragged=True)
+    assert flat.length_starts.tolist() == [0] + np.cumsum(flat.num_frames)[:-1].tolist()
+    assert flat.gts.shape[0] == flat.num_frames.sum()
+    np.testing.assert_allclose(np.linalg.norm(flat.grs, axis=-1), 1, atol=1e-6)
+    f = 7
+    for b in range(1, 24):
+        p = m["parent"][b]
+        want = R.quat_mul(flat.grs[f, p].astype(np.float64), flat.lrs[f, b].astype(np.float64))
+        np.testing.assert_allclose(want, flat.grs[f, b], atol=1e-5)
+        np.testing.assert_allclose(flat.gts[f, p] + R.my_quat_rotate(flat.grs[f, p].astype(np.float64), m["offset"][b]),
+                                   flat.gts[f, b], atol=1e-5)
+
+
+def test_physics_oracle_invariants():
+    """float64 restatement: momentum drift is O(h) (refining the step shrinks it), weight is carried at rest"""
+    from vid2player3d_b200 import abi, model_compiler
+    from oracle import physics_ref as P
+    mod = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    rng = np.random.default_rng(0)
+    drift = []
+    for substeps in (2, 20):
+        md = dict(mod); md["armature"] = np.zeros(69)
+        m0, verts = abi.pack_model(md, 0.0)
+        cfg0 = abi.make_cfg(mod, gravity_z=0.0, ang_damping=0.0, substeps=substeps)
+        root = np.zeros((1, 13)); root[:, 2] = 5; root[:, 6] = 1; root[:, 7:10] = [1, 0.5, 0.2]; root[:, 10:13] = [0.5, -1, 2]
+        rs = np.random.default_rng(1)
+        q = rs.normal(0, 0.3, (1, 69)); qd = rs.normal(0, 2, (1, 69)); tar = np.zeros((1, 69))
+        d0 = P.diagnostics(m0, cfg0, root[0], q[0], qd[0])
+        P.control_step(m0, verts, cfg0, root, q, qd, tar, n_steps=15)
+        d1 = P.diagnostics(m0, cfg0, root[0], q[0], qd[0])
+        drift.append(max(np.abs(d1["P"] - d0["P"]).max(), np.abs(d1["L"] - d0["L"]).max()))
+    assert drift[1] < 0.2 * drift[0]
+    # lying drop (config 1) comes to rest carrying its weight
+    m, verts = abi.pack_model(mod, mod["mass"].sum() / 90.0)
+    cfg = abi.make_cfg(mod)
+    root = np.zeros((1, 13)); root[0, 2] = 0.89; root[0, 6] = 1
+    q = np.zeros((1, 69)); qd = np.zeros((1, 69)); tar = np.zeros((1, 69))
+    rb, cf = P.control_step(m, verts, cfg, root, q, qd, tar, n_steps=60)
+    assert abs(cf[0, :, 2].sum() - mod["mass"].sum() * 9.81) < 2.0
+    assert np.abs(qd).max() < 0.05 and abs(root[0, 9]) < 1e-3
+
+
+def test_vec_task_and_parse_task_surface():
+    from vid2player3d_b200.tasks import parse_task as pt
+    with pytest.raises(Exception, match="Unrecognized task"):
+        class A:  # noqa: D401
+            task = "Nope"; device_id = 0; rl_device = "cpu"; physics_engine = 1; device = "cuda"; headless = True
+        pt(A, {"env": {}}, {}, None)

@@ -1,0 +1,145 @@
+"""ctypes mirror of include/b200env.h (structs + packing helpers).  Product code: the native
+binding (native.py) and the tests' oracle wrapper both build their arguments from these."""
+import ctypes as C
+
+import numpy as np
+
+MAX_BODIES, MAX_DOF, MAX_KEY = 32, 96, 8
+ABI_VERSION = 1
+
+
+class Model(C.Structure):
+    _fields_ = [
+        ("nb", C.c_int32), ("nd", C.c_int32), ("vmax", C.c_int32), ("max_depth", C.c_int32),
+        ("parent", C.c_int32 * MAX_BODIES), ("depth", C.c_int32 * MAX_BODIES),
+        ("dof_of_body", C.c_int32 * MAX_BODIES), ("fixed", C.c_int32 * MAX_BODIES),
+        ("nverts", C.c_int32 * MAX_BODIES),
+        ("offset", (C.c_float * 3) * MAX_BODIES), ("mass", C.c_float * MAX_BODIES),
+        ("com", (C.c_float * 3) * MAX_BODIES), ("inertia", (C.c_float * 6) * MAX_BODIES),
+        ("radius", C.c_float * MAX_BODIES),
+        ("kp", C.c_float * MAX_DOF), ("kd", C.c_float * MAX_DOF), ("armature", C.c_float * MAX_DOF),
+        ("lim_lo", C.c_float * MAX_DOF), ("lim_hi", C.c_float * MAX_DOF),
+    ]
+
+
+class Cfg(C.Structure):
+    _fields_ = [
+        ("sim_dt", C.c_float), ("substeps", C.c_int32), ("control_freq_inv", C.c_int32), ("gravity_z", C.c_float),
+        ("contact_kn", C.c_float), ("contact_cn", C.c_float), ("friction_mu", C.c_float), ("friction_vs", C.c_float),
+        ("ang_damping", C.c_float), ("max_ang_vel", C.c_float), ("limit_k", C.c_float), ("limit_c", C.c_float),
+        ("pd_tar_lim", C.c_float), ("res_force_scale", C.c_float), ("res_torque_scale", C.c_float),
+        ("max_episode_length", C.c_int32), ("enable_early_termination", C.c_int32),
+        ("termination_height", C.c_float * MAX_BODIES), ("contact_body", C.c_int32 * MAX_BODIES),
+        ("body_pos_weight", C.c_float * MAX_BODIES),
+        ("k_dof", C.c_float), ("k_vel", C.c_float), ("k_pos", C.c_float), ("k_rot", C.c_float),
+        ("w_dof", C.c_float), ("w_vel", C.c_float), ("w_pos", C.c_float), ("w_rot", C.c_float),
+        ("num_key", C.c_int32), ("key_body", C.c_int32 * MAX_KEY), ("shape_dim", C.c_int32),
+        ("ground_tolerance", C.c_float),
+    ]
+
+
+class MotionLibView(C.Structure):
+    _fields_ = [
+        ("gts", C.c_void_p), ("grs", C.c_void_p), ("lrs", C.c_void_p), ("grvs", C.c_void_p), ("gravs", C.c_void_p),
+        ("dvs", C.c_void_p), ("motion_lengths", C.c_void_p), ("num_frames", C.c_void_p), ("motion_dt", C.c_void_p),
+        ("length_starts", C.c_void_p), ("min_verts_h", C.c_void_p),
+        ("num_motions", C.c_int32), ("num_lib_bodies", C.c_int32), ("total_frames", C.c_int64),
+    ]
+
+
+class Buffers(C.Structure):
+    _fields_ = [
+        ("root_states", C.c_void_p), ("actors_per_env", C.c_int32),
+        ("dof_state", C.c_void_p), ("rigid_body_state", C.c_void_p), ("contact_forces", C.c_void_p),
+        ("bodies_per_env", C.c_int32),
+        ("obs_buf", C.c_void_p), ("num_obs", C.c_int32),
+        ("rew_buf", C.c_void_p), ("sub_rewards", C.c_void_p), ("reset_buf", C.c_void_p), ("progress_buf", C.c_void_p),
+        ("terminate_buf", C.c_void_p), ("motion_ids", C.c_void_p), ("ref_motion_times", C.c_void_p),
+        ("motion_bodies", C.c_void_p),
+        ("t_root_pos", C.c_void_p), ("t_root_rot", C.c_void_p), ("t_dof_pos", C.c_void_p), ("t_root_vel", C.c_void_p),
+        ("t_root_ang_vel", C.c_void_p), ("t_dof_vel", C.c_void_p), ("t_key_pos", C.c_void_p), ("t_rb_pos", C.c_void_p),
+        ("t_rb_rot", C.c_void_p),
+        ("p_dof_pos", C.c_void_p), ("p_dof_vel", C.c_void_p), ("p_rb_pos", C.c_void_p), ("p_rb_rot", C.c_void_p),
+        ("pd_targets", C.c_void_p), ("actions_used", C.c_void_p),
+    ]
+
+
+def _fill(arr, values):
+    for i, v in enumerate(values):
+        arr[i] = v
+
+
+def pack_model(model, pd_scale=1.0, kd_scale=None):
+    """model: dict from model_compiler.  pd_scale = humanoid_mass/90 * kp_scale
+    (humanoid_smpl_im.py:376-383).  Returns (Model, verts float32 [nb,vmax,3])."""
+    kd_scale = pd_scale if kd_scale is None else kd_scale
+    nb, nd = len(model["parent"]), len(model["kp"])
+    assert nb <= MAX_BODIES and nd <= MAX_DOF
+    m = Model()
+    m.nb, m.nd = nb, nd
+    vmax = int(max(4, (int(model["nverts"].max()) + 3) // 4 * 4))
+    m.vmax = vmax
+    m.max_depth = int(model["depth"].max())
+    _fill(m.parent, [int(x) for x in model["parent"]])
+    _fill(m.depth, [int(x) for x in model["depth"]])
+    _fill(m.dof_of_body, [int(x) for x in model["dof_of_body"]])
+    _fill(m.fixed, [int(x) for x in model["fixed"]])
+    _fill(m.nverts, [int(x) for x in model["nverts"]])
+    for i in range(nb):
+        _fill(m.offset[i], [float(x) for x in model["offset"][i]])
+        _fill(m.com[i], [float(x) for x in model["dyn_com"][i]])
+        I = model["dyn_inertia"][i]
+        _fill(m.inertia[i], [float(I[0, 0]), float(I[1, 1]), float(I[2, 2]), float(I[0, 1]), float(I[0, 2]), float(I[1, 2])])
+    _fill(m.mass, [float(x) for x in model["dyn_mass"]])
+    _fill(m.radius, [float(x) for x in model["radius"]])
+    _fill(m.kp, [float(x) * pd_scale for x in model["kp"]])
+    _fill(m.kd, [float(x) * kd_scale for x in model["kd"]])
+    _fill(m.armature, [float(x) for x in model["armature"]])
+    _fill(m.lim_lo, [float(x) for x in model["limits"][:, 0]])
+    _fill(m.lim_hi, [float(x) for x in model["limits"][:, 1]])
+    verts = np.ascontiguousarray(model["verts"][:, :vmax], dtype=np.float32)
+    return m, verts
+
+
+DEFAULT_PHYSICS = dict(contact_kn=6.0e4, contact_cn=6.0e2, friction_mu=1.0, friction_vs=0.05,
+                       ang_damping=0.01, max_ang_vel=100.0, limit_k=2000.0, limit_c=20.0)
+
+
+def make_cfg(model, *, sim_dt=1.0 / 60.0, substeps=2, control_freq_inv=2, gravity_z=-9.81, pd_tar_lim=0.5 * np.pi,
+             res_force_scale=31.85, res_torque_scale=None, max_episode_length=300, enable_early_termination=True,
+             termination_body_height=-0.5, termination_head_height=1.0, contact_bodies=("R_Ankle", "L_Ankle"),
+             key_bodies=("R_Ankle", "L_Ankle", "L_Hand", "R_Hand"), body_pos_weights=None, reward_specs=None,
+             shape_dim=11, ground_tolerance=0.0, **physics):
+    names = [str(x) for x in model["body_names"]]
+    nb = len(names)
+    c = Cfg()
+    c.sim_dt, c.substeps, c.control_freq_inv, c.gravity_z = sim_dt, substeps, control_freq_inv, gravity_z
+    ph = dict(DEFAULT_PHYSICS)
+    ph.update(physics)
+    for k, v in ph.items():
+        setattr(c, k, v)
+    c.pd_tar_lim = pd_tar_lim
+    c.res_force_scale = res_force_scale
+    c.res_torque_scale = res_force_scale if res_torque_scale is None else res_torque_scale
+    c.max_episode_length = int(max_episode_length)
+    c.enable_early_termination = int(bool(enable_early_termination))
+    th = [termination_body_height] * nb  # humanoid_smpl_im.py:217-224
+    if "Head" in names:
+        hid = names.index("Head")
+        th[hid] = max(termination_head_height, th[hid])
+    _fill(c.termination_height, th)
+    _fill(c.contact_body, [1 if n in contact_bodies else 0 for n in names])
+    w = [1.0] * nb
+    for val, bodies in (body_pos_weights or {}).items():
+        for b in bodies:
+            w[names.index(b)] = float(val)
+    _fill(c.body_pos_weight, w)
+    rs = {'k_dof': 60, 'k_vel': 0.2, 'k_pos': 100, 'k_rot': 40, 'w_dof': 0.6, 'w_vel': 0.1, 'w_pos': 0.2, 'w_rot': 0.1}
+    rs.update(reward_specs or {})
+    for k, v in rs.items():
+        setattr(c, k, float(v))
+    c.num_key = len(key_bodies)
+    _fill(c.key_body, [names.index(k) for k in key_bodies])
+    c.shape_dim = shape_dim
+    c.ground_tolerance = ground_tolerance
+    return c

@@ -1,0 +1,1395 @@
+// b200env.cu - B200 (sm_100a) kernels + C ABI of the vectorised humanoid environment step.
+//
+// One warp per env, one lane per rigid body.  Per-asset constants (tree tables, inertias, PD
+// gains, convex-hull vertices) are staged once per CTA into shared memory with a TMA bulk copy
+// (cp.async.bulk + mbarrier).  The three articulated-body passes run level by level over the
+// kinematic tree with warp shuffles between parent and child lanes; everything between the
+// state load and the obs/reward/reset store stays in registers.  No tensor cores: there is no
+// dense contraction on this path (BASELINE.json north_star).
+//
+// Reference behaviour being replaced (paths relative to /root/reference/embodied_pose):
+//   BaseTask.step                      env/tasks/base_task.py:147-165
+//   pre_physics_step / PD target clamp env/tasks/humanoid_smpl_im.py:125-157, 391-396
+//   gym.simulate x controlFreqInv      env/tasks/base_task.py:450-454   (physics: DESIGN.md 3)
+//   post_physics_step                  env/tasks/humanoid_smpl_im.py:398-418
+//   MotionLib.get_motion_state         utils/motion_lib.py:164-266, 427-436, 460-488
+//   obs / reward / reset               env/tasks/humanoid_smpl_im.py:653-668, 773-850, 918-987
+//   quaternion helpers                 utils/torch_utils.py:70-243
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200env.h"
+
+#define FULL 0xffffffffu
+#define WARPS_PER_CTA 4
+#define SCRATCH_FLOATS 320
+#define MAX_CHILD 4
+#define MAX_LEVELS 16
+
+// ------------------------------------------------------------------------------------------
+// device-side constant block: header | tree tables | hull vertices   (all 16-byte multiples)
+struct DevTree {
+  int32_t child[B200_MAX_BODIES][MAX_CHILD];  // dynamic (non-welded) children, -1 padded
+  int32_t maxch[MAX_LEVELS];                  // max #children over the bodies of each depth
+};
+struct DevBlob {
+  b200_model_t m;
+  DevTree t;
+  // float verts[nb][vmax][3] follows
+};
+static_assert(sizeof(b200_model_t) % 16 == 0, "model block must be a 16-byte multiple for the bulk copy");
+static_assert(sizeof(DevBlob) % 16 == 0, "blob header must be a 16-byte multiple");
+
+struct b200env {
+  int device;
+  int num_envs;
+  b200_model_t model;
+  b200_cfg_t cfg;
+  b200_buffers_t bufs;
+  b200_motion_lib_t ml;
+  bool bound, has_ml;
+  void* d_blob;
+  size_t blob_bytes;
+  b200_cfg_t* d_cfg;
+  int64_t launches;
+};
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+#define CUDA_OK(x)                                                   \
+  do {                                                               \
+    cudaError_t _e = (x);                                            \
+    if (_e != cudaSuccess) return fail(-10, "CUDA error: %s", cudaGetErrorString(_e)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// small math (templated on float / double)
+template <typename T> __device__ __forceinline__ T shfl(T v, int src) { return __shfl_sync(FULL, v, src); }
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+template <typename T> __device__ __forceinline__ void cross3(const T* a, const T* b, T* o) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+template <typename T> __device__ __forceinline__ void qmul(const T* a, const T* b, T* o) {
+  T x1 = a[0], y1 = a[1], z1 = a[2], w1 = a[3], x2 = b[0], y2 = b[1], z2 = b[2], w2 = b[3];
+  o[0] = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
+  o[1] = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
+  o[2] = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
+  o[3] = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
+}
+template <typename T> __device__ __forceinline__ void qnormalize(T* q) {
+  T n = T(1) / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
+}
+// rotate v by unit quaternion q:  v + 2 w (qv x v) + 2 qv x (qv x v)
+template <typename T> __device__ __forceinline__ void qrot(const T* q, const T* v, T* o) {
+  T t[3], u[3];
+  cross3(q, v, t);
+  t[0] *= T(2); t[1] *= T(2); t[2] *= T(2);
+  cross3(q, t, u);
+  o[0] = v[0] + q[3] * t[0] + u[0];
+  o[1] = v[1] + q[3] * t[1] + u[1];
+  o[2] = v[2] + q[3] * t[2] + u[2];
+}
+template <typename T> __device__ __forceinline__ void qmat(const T* q, T* R) {  // row-major 3x3
+  T x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+}
+template <typename T> __device__ __forceinline__ void mv3(const T* R, const T* v, T* o) {
+  T a = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  T b = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  T c = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+template <typename T> __device__ __forceinline__ void mtv3(const T* R, const T* v, T* o) {
+  T a = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+  T b = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+  T c = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+// rotation vector -> quaternion (exact exponential)
+template <typename T> __device__ __forceinline__ void qexp(const T* v, T* q) {
+  T a2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  T a = sqrt(a2), s;
+  if (a < T(1e-6)) s = T(0.5) - a2 / T(48); else s = sin(T(0.5) * a) / a;
+  q[0] = s * v[0]; q[1] = s * v[1]; q[2] = s * v[2]; q[3] = cos(T(0.5) * a);
+}
+// quaternion -> rotation vector, angle in [0, pi]
+template <typename T> __device__ __forceinline__ void qlog(const T* qi, T* v) {
+  T sg = qi[3] < T(0) ? T(-1) : T(1);
+  T x = sg * qi[0], y = sg * qi[1], z = sg * qi[2], w = sg * qi[3];
+  T s2 = x * x + y * y + z * z;
+  T s = sqrt(s2), f;
+  if (s < T(1e-6)) f = T(2) + s2 / T(3); else f = T(2) * atan2(s, w) / s;
+  v[0] = f * x; v[1] = f * y; v[2] = f * z;
+}
+// symmetric 3x3 stored as [xx, yy, zz, xy, xz, yz]
+template <typename T> __device__ __forceinline__ void sym_mv(const T* S, const T* v, T* o) {
+  T a = S[0] * v[0] + S[3] * v[1] + S[4] * v[2];
+  T b = S[3] * v[0] + S[1] * v[1] + S[5] * v[2];
+  T c = S[4] * v[0] + S[5] * v[1] + S[2] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+template <typename T> __device__ __forceinline__ void sym_inv(const T* S, T* O) {
+  T c00 = S[1] * S[2] - S[5] * S[5];
+  T c01 = S[5] * S[4] - S[3] * S[2];
+  T c02 = S[3] * S[5] - S[1] * S[4];
+  T det = S[0] * c00 + S[3] * c01 + S[4] * c02;
+  T id = T(1) / det;
+  O[0] = c00 * id;
+  O[1] = (S[0] * S[2] - S[4] * S[4]) * id;
+  O[2] = (S[0] * S[1] - S[3] * S[3]) * id;
+  O[3] = c01 * id;
+  O[4] = c02 * id;
+  O[5] = (S[3] * S[4] - S[0] * S[5]) * id;
+}
+// full 3x3 (row-major) from symmetric
+template <typename T> __device__ __forceinline__ void sym_full(const T* S, T* F) {
+  F[0] = S[0]; F[1] = S[3]; F[2] = S[4];
+  F[3] = S[3]; F[4] = S[1]; F[5] = S[5];
+  F[6] = S[4]; F[7] = S[5]; F[8] = S[2];
+}
+
+// ------------------------------------------------------------------------------------------
+// per-lane (per-body) state
+template <typename T> struct Lane {
+  T Q[4], p[3], w[3], v[3];  // world pose and velocity of the body origin
+  T qj[4], wt[3];            // joint rotation (child in parent) and joint velocity (child frame)
+};
+struct LaneConst {
+  int par, depth, dof0;
+  bool active, dyn;  // dyn: takes part in the dynamics (not welded)
+};
+
+template <typename T> struct PhysCfg {
+  T h, gz, kn, cn, mu, vs, damp, wmax, limk, limc;
+  int substeps, cfi;
+};
+template <typename T> __device__ __forceinline__ PhysCfg<T> make_phys_cfg(const b200_cfg_t& c) {
+  PhysCfg<T> p;
+  p.h = T(c.sim_dt) / T(c.substeps);
+  p.gz = T(c.gravity_z); p.kn = T(c.contact_kn); p.cn = T(c.contact_cn); p.mu = T(c.friction_mu);
+  p.vs = T(c.friction_vs); p.damp = T(1) - p.h * T(c.ang_damping); p.wmax = T(c.max_ang_vel);
+  p.limk = T(c.limit_k); p.limc = T(c.limit_c);
+  p.substeps = c.substeps; p.cfi = c.control_freq_inv;
+  return p;
+}
+
+// forward kinematics, level by level: fills Q,p,w,v (world) of every lane from the root state and
+// the joint state.  Optionally returns r = p - p_parent and the velocity-product terms zeta.
+template <typename T, bool WITH_ZETA>
+__device__ __forceinline__ void fk_pass(const b200_model_t& M, const LaneConst& lc, int lane, Lane<T>& L, T* r, T* zeta) {
+  for (int d = 1; d <= M.max_depth; d++) {
+    T pQ[4], pp[3], pw[3], pv[3];
+#pragma unroll
+    for (int k = 0; k < 4; k++) pQ[k] = shfl(L.Q[k], lc.par);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { pp[k] = shfl(L.p[k], lc.par); pw[k] = shfl(L.w[k], lc.par); pv[k] = shfl(L.v[k], lc.par); }
+    if (lc.active && lc.depth == d) {
+      T off[3] = {T(M.offset[lane][0]), T(M.offset[lane][1]), T(M.offset[lane][2])};
+      T rr[3], wxr[3];
+      qrot(pQ, off, rr);
+      cross3(pw, rr, wxr);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { L.p[k] = pp[k] + rr[k]; L.v[k] = pv[k] + wxr[k]; }
+      if (WITH_ZETA) { r[0] = rr[0]; r[1] = rr[1]; r[2] = rr[2]; }
+      if (!lc.dyn) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) L.Q[k] = pQ[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) L.w[k] = pw[k];
+      } else {
+        qmul(pQ, L.qj, L.Q);
+        qnormalize(L.Q);
+        T wj[3];
+        qrot(L.Q, L.wt, wj);
+#pragma unroll
+        for (int k = 0; k < 3; k++) L.w[k] = pw[k] + wj[k];
+        if (WITH_ZETA) { cross3(pw, wj, zeta); cross3(pw, wxr, zeta + 3); }
+      }
+    }
+  }
+}
+
+// One substep of length h (float64 restatement: oracle/physics_ref.c::substep).
+template <typename T>
+__device__ __forceinline__ void substep(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c,
+                                        const LaneConst& lc, int lane, Lane<T>& L, const T* pdtar, bool ext_on,
+                                        const T* extF, const T* extT, T* cf) {
+  const b200_model_t& M = B.m;
+  T r[3] = {0, 0, 0}, zeta[6] = {0, 0, 0, 0, 0, 0};
+  fk_pass<T, true>(M, lc, lane, L, r, zeta);
+
+  // articulated inertia  [[A, Bm], [Bm^T, C]]  (A, C symmetric) and bias (bn, bf)
+  T A[6] = {0, 0, 0, 0, 0, 0}, Bm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, C[6] = {0, 0, 0, 0, 0, 0};
+  T bn[3] = {0, 0, 0}, bf[3] = {0, 0, 0};
+  T E[6] = {0, 0, 0, 0, 0, 0}, u[3] = {0, 0, 0};
+  T R[9];
+  qmat(L.Q, R);
+  cf[0] = cf[1] = cf[2] = T(0);
+  if (lc.dyn) {
+    const T ms = T(M.mass[lane]);
+    T cl[3] = {T(M.com[lane][0]), T(M.com[lane][1]), T(M.com[lane][2])}, cw[3];
+    mv3(R, cl, cw);
+    // Io = R Ib R^T + m (|c|^2 1 - c c^T)
+    {
+      T Ib[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) Ib[k] = T(M.inertia[lane][k]);
+      T F[9], RF[9];
+      sym_full(Ib, F);
+      // RF = R * F
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) RF[i * 3 + j] = R[i * 3] * F[j] + R[i * 3 + 1] * F[3 + j] + R[i * 3 + 2] * F[6 + j];
+      T c2 = cw[0] * cw[0] + cw[1] * cw[1] + cw[2] * cw[2];
+      A[0] = RF[0] * R[0] + RF[1] * R[1] + RF[2] * R[2] + ms * (c2 - cw[0] * cw[0]);
+      A[1] = RF[3] * R[3] + RF[4] * R[4] + RF[5] * R[5] + ms * (c2 - cw[1] * cw[1]);
+      A[2] = RF[6] * R[6] + RF[7] * R[7] + RF[8] * R[8] + ms * (c2 - cw[2] * cw[2]);
+      A[3] = RF[0] * R[3] + RF[1] * R[4] + RF[2] * R[5] - ms * cw[0] * cw[1];
+      A[4] = RF[0] * R[6] + RF[1] * R[7] + RF[2] * R[8] - ms * cw[0] * cw[2];
+      A[5] = RF[3] * R[6] + RF[4] * R[7] + RF[5] * R[8] - ms * cw[1] * cw[2];
+    }
+    // Bm = m [c]x
+    Bm[1] = -ms * cw[2]; Bm[2] = ms * cw[1];
+    Bm[3] = ms * cw[2]; Bm[5] = -ms * cw[0];
+    Bm[6] = -ms * cw[1]; Bm[7] = ms * cw[0];
+    C[0] = C[1] = C[2] = ms;
+    // bias: [w x Io w ; m w x (w x c)] - gravity wrench
+    {
+      T Iw[3], t1[3], t2[3];
+      sym_mv(A, L.w, Iw);
+      cross3(L.w, Iw, bn);
+      cross3(L.w, cw, t1);
+      cross3(L.w, t1, t2);
+      // c x (m g) with g = (0,0,gz):  (c_y gz, -c_x gz, 0) * m
+      bn[0] -= ms * cw[1] * c.gz;
+      bn[1] += ms * cw[0] * c.gz;
+      bf[0] = ms * t2[0]; bf[1] = ms * t2[1]; bf[2] = ms * t2[2] - ms * c.gz;
+    }
+    if (lane == 0 && ext_on) {  // residual wrench: force at the COM + torque, world frame
+      T cxF[3];
+      cross3(cw, extF, cxF);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { bn[k] -= extT[k] + cxF[k]; bf[k] -= extF[k]; }
+    }
+    // ground contact of the hull vertices, implicit in the velocity
+    const int nv = M.nverts[lane];
+    if (nv > 0 && L.p[2] - T(M.radius[lane]) < T(0)) {
+      const float* vb = verts + (size_t)lane * M.vmax * 3;
+      const T kimp = c.h * c.cn + c.h * c.h * c.kn;
+      for (int k = 0; k < nv; k++) {
+        T vl[3] = {T(vb[3 * k]), T(vb[3 * k + 1]), T(vb[3 * k + 2])};
+        T rz = R[6] * vl[0] + R[7] * vl[1] + R[8] * vl[2];
+        T pen = -(L.p[2] + rz);
+        if (!(pen > T(0))) continue;
+        T rx = R[0] * vl[0] + R[1] * vl[1] + R[2] * vl[2];
+        T ry = R[3] * vl[0] + R[4] * vl[1] + R[5] * vl[2];
+        T ux = L.v[0] + L.w[1] * rz - L.w[2] * ry;
+        T uy = L.v[1] + L.w[2] * rx - L.w[0] * rz;
+        T uz = L.v[2] + L.w[0] * ry - L.w[1] * rx;
+        T fn0 = c.kn * pen - c.cn * uz;
+        if (!(fn0 > T(0))) continue;
+        T ut = sqrt(ux * ux + uy * uy);
+        T ct = c.mu * fn0 / (ut > c.vs ? ut : c.vs);
+        T hct = c.h * ct;
+        // Jn = [(ry, -rx, 0); (0,0,1)], Jx = [(0, rz, -ry); (1,0,0)], Jy = [(-rz, 0, rx); (0,1,0)]
+        A[0] += kimp * ry * ry + hct * rz * rz;
+        A[1] += kimp * rx * rx + hct * rz * rz;
+        A[2] += hct * (ry * ry + rx * rx);
+        A[3] += -kimp * ry * rx;
+        A[4] += -hct * rz * rx;
+        A[5] += -hct * rz * ry;
+        Bm[2] += kimp * ry;   // (Jn_ang)(Jn_lin)^T : column z
+        Bm[5] += -kimp * rx;
+        Bm[3] += hct * rz;    // Jx: ang (0,rz,-ry) x lin ex -> column x
+        Bm[6] += -hct * ry;
+        Bm[1] += -hct * rz;   // Jy: ang (-rz,0,rx) x lin ey -> column y
+        Bm[7] += hct * rx;
+        C[0] += hct; C[1] += hct; C[2] += kimp;
+        // wrench W = Jn fn0 - ct (Jx ux + Jy uy);  b -= W
+        T fx = -ct * ux, fy = -ct * uy;
+        bn[0] -= ry * fn0 - rz * fy;
+        bn[1] -= -rx * fn0 + rz * fx;
+        bn[2] -= -ry * fx + rx * fy;
+        bf[0] -= fx; bf[1] -= fy; bf[2] -= fn0;
+        cf[0] += fx; cf[1] += fy; cf[2] += fn0;
+      }
+    }
+    // joint drive (child frame, exp-map chart): implicit PD + armature + limit springs
+    if (lane > 0) {
+      T q[3], tau[3], e[3];
+      qlog(L.qj, q);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        T kp = T(M.kp[lc.dof0 + k]), kd = T(M.kd[lc.dof0 + k]);
+        e[k] = T(M.armature[lc.dof0 + k]) + c.h * kd + c.h * c.h * kp;
+        tau[k] = kp * (pdtar[k] - q[k] - c.h * L.wt[k]) - kd * L.wt[k];
+        T lo = T(M.lim_lo[lc.dof0 + k]), hi = T(M.lim_hi[lc.dof0 + k]);
+        if (q[k] < lo) { tau[k] += c.limk * (lo - q[k] - c.h * L.wt[k]) - c.limc * L.wt[k]; e[k] += c.h * c.limc + c.h * c.h * c.limk; }
+        else if (q[k] > hi) { tau[k] += c.limk * (hi - q[k] - c.h * L.wt[k]) - c.limc * L.wt[k]; e[k] += c.h * c.limc + c.h * c.h * c.limk; }
+      }
+      mv3(R, tau, u);  // tau_w
+      // E_w = R diag(e) R^T
+      E[0] = R[0] * R[0] * e[0] + R[1] * R[1] * e[1] + R[2] * R[2] * e[2];
+      E[1] = R[3] * R[3] * e[0] + R[4] * R[4] * e[1] + R[5] * R[5] * e[2];
+      E[2] = R[6] * R[6] * e[0] + R[7] * R[7] * e[1] + R[8] * R[8] * e[2];
+      E[3] = R[0] * R[3] * e[0] + R[1] * R[4] * e[1] + R[2] * R[5] * e[2];
+      E[4] = R[0] * R[6] * e[0] + R[1] * R[7] * e[1] + R[2] * R[8] * e[2];
+      E[5] = R[3] * R[6] * e[0] + R[4] * R[7] * e[1] + R[5] * R[8] * e[2];
+    }
+  }
+
+  // ---- backward pass: leaves -> root, one tree level at a time
+  T Dinv[6] = {0, 0, 0, 0, 0, 0};
+  for (int d = M.max_depth; d >= 1; d--) {
+    T out[27];
+#pragma unroll
+    for (int k = 0; k < 27; k++) out[k] = T(0);
+    if (lc.dyn && lc.depth == d) {
+      T D[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) D[k] = A[k] + E[k];
+      sym_inv(D, Dinv);
+      u[0] -= bn[0]; u[1] -= bn[1]; u[2] -= bn[2];
+      T Af[9], Df[9];
+      sym_full(A, Af);
+      sym_full(Dinv, Df);
+      // G = Dinv * A ; K = Dinv * Bm   (3x3 full)
+      T G[9], K[9];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          G[i * 3 + j] = Df[i * 3] * Af[j] + Df[i * 3 + 1] * Af[3 + j] + Df[i * 3 + 2] * Af[6 + j];
+          K[i * 3 + j] = Df[i * 3] * Bm[j] + Df[i * 3 + 1] * Bm[3 + j] + Df[i * 3 + 2] * Bm[6 + j];
+        }
+      // Ia blocks: aA = A - A G (sym), aB = Bm - A K, aC = C - Bm^T K (sym)
+      T aA[6], aB[9], aC[6];
+      aA[0] = A[0] - (Af[0] * G[0] + Af[1] * G[3] + Af[2] * G[6]);
+      aA[1] = A[1] - (Af[3] * G[1] + Af[4] * G[4] + Af[5] * G[7]);
+      aA[2] = A[2] - (Af[6] * G[2] + Af[7] * G[5] + Af[8] * G[8]);
+      aA[3] = A[3] - (Af[0] * G[1] + Af[1] * G[4] + Af[2] * G[7]);
+      aA[4] = A[4] - (Af[0] * G[2] + Af[1] * G[5] + Af[2] * G[8]);
+      aA[5] = A[5] - (Af[3] * G[2] + Af[4] * G[5] + Af[5] * G[8]);
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) aB[i * 3 + j] = Bm[i * 3 + j] - (Af[i * 3] * K[j] + Af[i * 3 + 1] * K[3 + j] + Af[i * 3 + 2] * K[6 + j]);
+      aC[0] = C[0] - (Bm[0] * K[0] + Bm[3] * K[3] + Bm[6] * K[6]);
+      aC[1] = C[1] - (Bm[1] * K[1] + Bm[4] * K[4] + Bm[7] * K[7]);
+      aC[2] = C[2] - (Bm[2] * K[2] + Bm[5] * K[5] + Bm[8] * K[8]);
+      aC[3] = C[3] - (Bm[0] * K[1] + Bm[3] * K[4] + Bm[6] * K[7]);
+      aC[4] = C[4] - (Bm[0] * K[2] + Bm[3] * K[5] + Bm[6] * K[8]);
+      aC[5] = C[5] - (Bm[1] * K[2] + Bm[4] * K[5] + Bm[7] * K[8]);
+      // ba = b + Ia zeta + Ucol Dinv u
+      T s[3], an[3], af[3], t1[3], t2[3];
+      sym_mv(Dinv, u, s);
+      sym_mv(aA, zeta, t1);
+      mv3(aB, zeta + 3, t2);
+      T As[3];
+      sym_mv(A, s, As);
+#pragma unroll
+      for (int k = 0; k < 3; k++) an[k] = bn[k] + t1[k] + t2[k] + As[k];
+      mtv3(aB, zeta, t1);
+      sym_mv(aC, zeta + 3, t2);
+      T Bts[3];
+      mtv3(Bm, s, Bts);
+#pragma unroll
+      for (int k = 0; k < 3; k++) af[k] = bf[k] + t1[k] + t2[k] + Bts[k];
+      // shift to the parent's origin (X = [r]x):  B' = aB + X aC ; A' = aA + X B'^T + (X aB^T)^T
+      T Cf[9];
+      sym_full(aC, Cf);
+      T Bp[9];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {  // column j of X*Cf = r x (column j of Cf)
+        T col[3] = {Cf[j], Cf[3 + j], Cf[6 + j]}, x[3];
+        cross3(r, col, x);
+        Bp[j] = aB[j] + x[0]; Bp[3 + j] = aB[3 + j] + x[1]; Bp[6 + j] = aB[6 + j] + x[2];
+      }
+      T P1[9], P2[9];  // P1 = X Bp^T (column j = r x row j of Bp), P2 = X aB^T
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        T x[3];
+        cross3(r, Bp + 3 * j, x);
+        P1[j] = x[0]; P1[3 + j] = x[1]; P1[6 + j] = x[2];
+        cross3(r, aB + 3 * j, x);
+        P2[j] = x[0]; P2[3 + j] = x[1]; P2[6 + j] = x[2];
+      }
+      out[0] = aA[0] + P1[0] + P2[0];
+      out[1] = aA[1] + P1[4] + P2[4];
+      out[2] = aA[2] + P1[8] + P2[8];
+      out[3] = aA[3] + P1[1] + P2[3];
+      out[4] = aA[4] + P1[2] + P2[6];
+      out[5] = aA[5] + P1[5] + P2[7];
+#pragma unroll
+      for (int k = 0; k < 9; k++) out[6 + k] = Bp[k];
+#pragma unroll
+      for (int k = 0; k < 6; k++) out[15 + k] = aC[k];
+      T rxf[3];
+      cross3(r, af, rxf);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { out[21 + k] = an[k] + rxf[k]; out[24 + k] = af[k]; }
+    }
+    const int rounds = B.t.maxch[d - 1];
+    for (int cix = 0; cix < rounds; cix++) {
+      int src = (lc.active && lc.depth == d - 1) ? B.t.child[lane][cix] : -1;
+      const bool has = src >= 0;
+      src = has ? src : lane;
+#pragma unroll
+      for (int k = 0; k < 27; k++) {
+        T val = shfl(out[k], src);
+        if (has) {
+          if (k < 6) A[k] += val;
+          else if (k < 15) Bm[k - 6] += val;
+          else if (k < 21) C[k - 15] += val;
+          else if (k < 24) bn[k - 21] += val;
+          else bf[k - 24] += val;
+        }
+      }
+    }
+  }
+
+  // ---- root: solve [[A,Bm],[Bm^T,C]] [alpha; a] = -[bn; bf] by block elimination
+  T acc[6] = {0, 0, 0, 0, 0, 0};  // (alpha, a) of this body
+  if (lane == 0) {
+    T Ci[6];
+    sym_inv(C, Ci);
+    T Cif[9];
+    sym_full(Ci, Cif);
+    T BC[9];  // Bm * Ci
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) BC[i * 3 + j] = Bm[i * 3] * Cif[j] + Bm[i * 3 + 1] * Cif[3 + j] + Bm[i * 3 + 2] * Cif[6 + j];
+    T S[6];  // A - Bm Ci Bm^T
+    S[0] = A[0] - (BC[0] * Bm[0] + BC[1] * Bm[1] + BC[2] * Bm[2]);
+    S[1] = A[1] - (BC[3] * Bm[3] + BC[4] * Bm[4] + BC[5] * Bm[5]);
+    S[2] = A[2] - (BC[6] * Bm[6] + BC[7] * Bm[7] + BC[8] * Bm[8]);
+    S[3] = A[3] - (BC[0] * Bm[3] + BC[1] * Bm[4] + BC[2] * Bm[5]);
+    S[4] = A[4] - (BC[0] * Bm[6] + BC[1] * Bm[7] + BC[2] * Bm[8]);
+    S[5] = A[5] - (BC[3] * Bm[6] + BC[4] * Bm[7] + BC[5] * Bm[8]);
+    T Si[6];
+    sym_inv(S, Si);
+    T rhs[3], t[3];
+    mv3(BC, bf, t);
+#pragma unroll
+    for (int k = 0; k < 3; k++) rhs[k] = -bn[k] + t[k];
+    sym_mv(Si, rhs, acc);
+    mtv3(Bm, acc, t);
+#pragma unroll
+    for (int k = 0; k < 3; k++) t[k] = -bf[k] - t[k];
+    sym_mv(Ci, t, acc + 3);
+  }
+
+  // ---- forward pass: root -> leaves
+  for (int d = 1; d <= M.max_depth; d++) {
+    T pa[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) pa[k] = shfl(acc[k], lc.par);
+    if (lc.dyn && lc.depth == d) {
+      T axr[3], Ap[6];
+      cross3(pa, r, axr);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { Ap[k] = pa[k] + zeta[k]; Ap[3 + k] = pa[3 + k] + axr[k] + zeta[3 + k]; }
+      // t = u - Ucol^T A' = u - A Ap_ang - Bm Ap_lin
+      T t1[3], t2[3], t[3], gam[3], wd[3];
+      sym_mv(A, Ap, t1);
+      mv3(Bm, Ap + 3, t2);
+#pragma unroll
+      for (int k = 0; k < 3; k++) t[k] = u[k] - t1[k] - t2[k];
+      sym_mv(Dinv, t, gam);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { acc[k] = Ap[k] + gam[k]; acc[3 + k] = Ap[3 + k]; }
+      mtv3(R, gam, wd);
+#pragma unroll
+      for (int k = 0; k < 3; k++) L.wt[k] = (L.wt[k] + c.h * wd[k]) * c.damp;
+      T nn = sqrt(L.wt[0] * L.wt[0] + L.wt[1] * L.wt[1] + L.wt[2] * L.wt[2]);
+      if (nn > c.wmax) { T sc = c.wmax / nn; L.wt[0] *= sc; L.wt[1] *= sc; L.wt[2] *= sc; }
+    }
+  }
+
+  // ---- integrate
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { L.w[k] = (L.w[k] + c.h * acc[k]) * c.damp; L.v[k] += c.h * acc[3 + k]; }
+    T nn = sqrt(L.w[0] * L.w[0] + L.w[1] * L.w[1] + L.w[2] * L.w[2]);
+    if (nn > c.wmax) { T sc = c.wmax / nn; L.w[0] *= sc; L.w[1] *= sc; L.w[2] *= sc; }
+    T hv[3] = {c.h * L.w[0], c.h * L.w[1], c.h * L.w[2]}, dq[4], qn[4];
+#pragma unroll
+    for (int k = 0; k < 3; k++) L.p[k] += c.h * L.v[k];
+    qexp(hv, dq);
+    qmul(dq, L.Q, qn);
+    qnormalize(qn);
+#pragma unroll
+    for (int k = 0; k < 4; k++) L.Q[k] = qn[k];
+  } else if (lc.dyn) {
+    T hv[3] = {c.h * L.wt[0], c.h * L.wt[1], c.h * L.wt[2]}, dq[4], qn[4];
+    qexp(hv, dq);
+    qmul(L.qj, dq, qn);
+    qnormalize(qn);
+#pragma unroll
+    for (int k = 0; k < 4; k++) L.qj[k] = qn[k];
+  }
+}
+
+// control_freq_inv sim steps x substeps; external wrench only during the first sim step
+template <typename T>
+__device__ __forceinline__ void control_step(const DevBlob& B, const float* verts, const PhysCfg<T>& c, const LaneConst& lc,
+                                             int lane, Lane<T>& L, const T* pdtar, const T* extF, const T* extT, T* cf) {
+  for (int s = 0; s < c.cfi; s++)
+    for (int k = 0; k < c.substeps; k++) substep<T>(B, verts, c, lc, lane, L, pdtar, s == 0, extF, extT, cf);
+  T dummy[3], dz[6];
+  fk_pass<T, false>(B.m, lc, lane, L, dummy, dz);
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA bulk load of the constant block into shared memory (one elected thread issues it)
+__device__ __forceinline__ void load_blob(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
+  const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar);
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(gsrc), "r"(bytes), "r"(mb)
+                 : "memory");
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mb)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ LaneConst lane_const(const b200_model_t& M, int lane) {
+  LaneConst lc;
+  lc.active = lane < M.nb;
+  lc.par = lc.active ? (M.parent[lane] < 0 ? 0 : M.parent[lane]) : 0;
+  lc.depth = lc.active ? M.depth[lane] : -1;
+  lc.dof0 = lc.active ? M.dof_of_body[lane] : -1;
+  lc.dyn = lc.active && !M.fixed[lane];
+  return lc;
+}
+
+// ------------------------------------------------------------------------------------------
+// reference float32 helpers (utils/torch_utils.py) - op order kept close to the reference
+__device__ __forceinline__ void ref_quat_rotate(const float* q, const float* v, float* o) {  // my_quat_rotate :70-79
+  float qw = q[3];
+  float a = 2.0f * qw * qw - 1.0f;
+  float cx = q[1] * v[2] - q[2] * v[1], cy = q[2] * v[0] - q[0] * v[2], cz = q[0] * v[1] - q[1] * v[0];
+  float d = q[0] * v[0] + q[1] * v[1] + q[2] * v[2];
+  o[0] = v[0] * a + cx * qw * 2.0f + q[0] * d * 2.0f;
+  o[1] = v[1] * a + cy * qw * 2.0f + q[1] * d * 2.0f;
+  o[2] = v[2] * a + cz * qw * 2.0f + q[2] * d * 2.0f;
+}
+__device__ __forceinline__ void ref_tan_norm(const float* q, float* o) {  // quat_to_tan_norm :122-134
+  const float ex[3] = {1.f, 0.f, 0.f}, ez[3] = {0.f, 0.f, 1.f};
+  ref_quat_rotate(q, ex, o);
+  ref_quat_rotate(q, ez, o + 3);
+}
+__device__ __forceinline__ float ref_normalize_angle(float x) { return atan2f(sinf(x), cosf(x)); }
+__device__ __forceinline__ void ref_quat_to_angle_axis(const float* q, float& angle, float* axis) {  // :82-102
+  float sin_theta = sqrtf(1.0f - q[3] * q[3]);
+  angle = ref_normalize_angle(2.0f * acosf(q[3]));
+  bool mask = fabsf(sin_theta) > 1e-5f;
+  if (mask) { axis[0] = q[0] / sin_theta; axis[1] = q[1] / sin_theta; axis[2] = q[2] / sin_theta; }
+  else { angle = 0.f; axis[0] = 0.f; axis[1] = 0.f; axis[2] = 1.f; }
+}
+__device__ __forceinline__ void ref_exp_map_to_quat(const float* e, float* q) {  // :143-166
+  float angle = sqrtf(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+  float ax[3] = {e[0] / angle, e[1] / angle, e[2] / angle};
+  angle = ref_normalize_angle(angle);
+  if (!(fabsf(angle) > 1e-5f)) { angle = 0.f; ax[0] = 0.f; ax[1] = 0.f; ax[2] = 1.f; }
+  float n = fmaxf(sqrtf(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]), 1e-9f);  // quat_from_angle_axis: normalize(axis)
+  float s = sinf(angle * 0.5f), cw = cosf(angle * 0.5f);
+  q[0] = ax[0] / n * s; q[1] = ax[1] / n * s; q[2] = ax[2] / n * s; q[3] = cw;
+  float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]), 1e-9f);  // quat_unit
+  q[0] /= qn; q[1] /= qn; q[2] /= qn; q[3] /= qn;
+}
+__device__ __forceinline__ void ref_slerp(const float* q0, const float* q1in, float t, float* o) {  // :168-190
+  float c = q0[0] * q1in[0] + q0[1] * q1in[1] + q0[2] * q1in[2] + q0[3] * q1in[3];
+  float sg = c < 0.f ? -1.f : 1.f;
+  float q1[4] = {sg * q1in[0], sg * q1in[1], sg * q1in[2], sg * q1in[3]};
+  c = fabsf(c);
+  float half = acosf(c);
+  float sh = sqrtf(1.0f - c * c);
+  float ra = sinf((1.f - t) * half) / sh, rb = sinf(t * half) / sh;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float v = ra * q0[k] + rb * q1[k];
+    if (fabsf(sh) < 0.001f) v = 0.5f * q0[k] + 0.5f * q1[k];
+    if (fabsf(c) >= 1.f) v = q0[k];
+    o[k] = v;
+  }
+}
+__device__ __forceinline__ void ref_remove_base_rot(const float* q, float* o) {  // humanoid_smpl_im.py:766-770
+  const float b[4] = {-0.5f, -0.5f, -0.5f, 0.5f};
+  qmul(q, b, o);
+}
+__device__ __forceinline__ float ref_calc_heading(const float* q) {  // :192-203
+  const float ex[3] = {1.f, 0.f, 0.f};
+  float d[3];
+  ref_quat_rotate(q, ex, d);
+  return atan2f(d[1], d[0]);
+}
+__device__ __forceinline__ void ref_heading_quat(float heading, float* q) {  // quat_from_angle_axis(heading, z)
+  float s = sinf(heading * 0.5f), c = cosf(heading * 0.5f);
+  float n = fmaxf(sqrtf(s * s + c * c), 1e-9f);
+  q[0] = 0.f; q[1] = 0.f; q[2] = s / n; q[3] = c / n;
+}
+
+// MoCap sampling for one (motion id, time): lane b returns its body's blended pose.
+struct MotionSample {
+  float rb_pos[3], rb_rot[4], dof[3];
+  float root_vel[3], root_ang_vel[3];  // every lane holds the same values
+  int64_t f0;
+};
+__device__ __forceinline__ MotionSample sample_motion(const b200_motion_lib_t& ml, const b200_model_t& M, int64_t mid,
+                                                      float time, int lane, float ground_tol) {
+  MotionSample s;
+  const float len = ml.motion_lengths[mid];
+  const int64_t nf = ml.num_frames[mid];
+  const float dt = ml.motion_dt[mid];
+  // _calc_frame_blend (motion_lib.py:427-436), float32 op by op (no fma contraction)
+  float phase = __fdiv_rn(time, len);
+  phase = fminf(fmaxf(phase, 0.0f), 1.0f);
+  int64_t i0 = (int64_t)__fmul_rn(phase, (float)(nf - 1));
+  int64_t i1 = (i0 + 1 < nf - 1) ? i0 + 1 : nf - 1;
+  float blend = __fdiv_rn(__fsub_rn(time, __fmul_rn((float)i0, dt)), dt);
+  const int64_t f0 = i0 + ml.length_starts[mid], f1 = i1 + ml.length_starts[mid];
+  s.f0 = f0;
+  const int nbl = ml.num_lib_bodies;
+  const float minvh = ml.min_verts_h[mid] - ground_tol;
+  const float omb = __fsub_rn(1.0f, blend);
+  if (lane < nbl) {
+    const float* g0 = ml.gts + (f0 * nbl + lane) * 3;
+    const float* g1 = ml.gts + (f1 * nbl + lane) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) s.rb_pos[k] = __fadd_rn(__fmul_rn(omb, g0[k]), __fmul_rn(blend, g1[k]));
+    s.rb_pos[2] -= minvh;
+    const float4 r0 = *reinterpret_cast<const float4*>(ml.grs + (f0 * nbl + lane) * 4);
+    const float4 r1 = *reinterpret_cast<const float4*>(ml.grs + (f1 * nbl + lane) * 4);
+    float a[4] = {r0.x, r0.y, r0.z, r0.w}, b[4] = {r1.x, r1.y, r1.z, r1.w};
+    ref_slerp(a, b, blend, s.rb_rot);
+    const float4 l0 = *reinterpret_cast<const float4*>(ml.lrs + (f0 * nbl + lane) * 4);
+    const float4 l1 = *reinterpret_cast<const float4*>(ml.lrs + (f1 * nbl + lane) * 4);
+    float la[4] = {l0.x, l0.y, l0.z, l0.w}, lb[4] = {l1.x, l1.y, l1.z, l1.w}, lq[4];
+    ref_slerp(la, lb, blend, lq);
+    float ang, ax[3];
+    ref_quat_to_angle_axis(lq, ang, ax);  // quat_to_exp_map (:113-120)
+    s.dof[0] = ang * ax[0]; s.dof[1] = ang * ax[1]; s.dof[2] = ang * ax[2];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { s.rb_pos[k] = 0.f; s.dof[k] = 0.f; }
+    s.rb_rot[0] = s.rb_rot[1] = s.rb_rot[2] = 0.f; s.rb_rot[3] = 1.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) { s.root_vel[k] = ml.grvs[f0 * 3 + k]; s.root_ang_vel[k] = ml.gravs[f0 * 3 + k]; }
+  return s;
+}
+
+// write one MoCap sample as the "target" rows of env e
+__device__ __forceinline__ void store_targets(const b200_buffers_t& bf, const b200_cfg_t& cfg, const b200_motion_lib_t& ml,
+                                              const b200_model_t& M, const MotionSample& s, int64_t e, int lane, int dof0) {
+  const int nbl = ml.num_lib_bodies, nd = M.nd;
+  if (lane < nbl) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) bf.t_rb_pos[(e * nbl + lane) * 3 + k] = s.rb_pos[k];
+    *reinterpret_cast<float4*>(bf.t_rb_rot + (e * nbl + lane) * 4) = make_float4(s.rb_rot[0], s.rb_rot[1], s.rb_rot[2], s.rb_rot[3]);
+    if (dof0 >= 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) bf.t_dof_pos[e * nd + dof0 + k] = s.dof[k];
+    }
+    for (int k = 0; k < cfg.num_key; k++)
+      if (cfg.key_body[k] == lane) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) bf.t_key_pos[(e * cfg.num_key + k) * 3 + j] = s.rb_pos[j];
+      }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      bf.t_root_pos[e * 3 + k] = s.rb_pos[k];
+      bf.t_root_vel[e * 3 + k] = s.root_vel[k];
+      bf.t_root_ang_vel[e * 3 + k] = s.root_ang_vel[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) bf.t_root_rot[e * 4 + k] = s.rb_rot[k];
+  }
+  for (int k = lane; k < nd; k += 32) bf.t_dof_vel[e * nd + k] = ml.dvs[s.f0 * nd + k];
+}
+
+// raw-state observation row (humanoid_smpl_im.py:653-668, obs_names :198)
+__device__ __forceinline__ void store_obs_raw(float* obs, int nb, int nd, int shape_dim, int lane, bool is_body, int dof0,
+                                              const float* pos, const float* rot, const float* vel, const float* angvel,
+                                              const float* dq, const float* dqd, const float* motion_bodies) {
+  int o = 0;
+  if (is_body) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) obs[o + lane * 3 + k] = pos[k];
+  }
+  o += nb * 3;
+  if (is_body) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) obs[o + lane * 4 + k] = rot[k];
+  }
+  o += nb * 4;
+  if (is_body && dof0 >= 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { obs[o + dof0 + k] = dq[k]; obs[o + nd + dof0 + k] = dqd[k]; }
+  }
+  o += 2 * nd;
+  if (is_body) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { obs[o + lane * 3 + k] = vel[k]; obs[o + nb * 3 + lane * 3 + k] = angvel[k]; }
+  }
+  o += nb * 6;
+  if (lane < shape_dim) obs[o + lane] = motion_bodies[lane];
+}
+
+// ------------------------------------------------------------------------------------------
+// fused env step:  pre-physics -> substeps -> MoCap target -> obs -> reward -> reset
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
+            b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  load_blob(smem, gblob, blob_bytes, &mbar);
+  const DevBlob& B = *reinterpret_cast<const DevBlob*>(smem);
+  const b200_model_t& M = B.m;
+  const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
+  float* scratch_all = reinterpret_cast<float*>(smem + ((blob_bytes + 15) & ~15u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* scr = scratch_all + warp * SCRATCH_FLOATS;
+  const b200_cfg_t& cfg = *gcfg;
+  const int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+  if (e >= num_envs) return;
+
+  const LaneConst lc = lane_const(M, lane);
+  const int nb = M.nb, nd = M.nd, na = nd + 6;
+  const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
+
+  // ---- load state rows (coalesced) into the warp's scratch
+  const float* rs = bf.root_states + e * bf.actors_per_env * 13;
+  const float* ds = bf.dof_state + e * nd * 2;
+  const float* ac = actions + e * na;
+  const bool was_reset = bf.reset_buf[e] == 1;
+  if (lane < 13) scr[lane] = rs[lane];
+  for (int k = lane; k < nd * 2; k += 32) scr[16 + k] = ds[k];
+  for (int k = lane; k < na; k += 32) {
+    float a = was_reset ? 0.0f : ac[k];  // actions[self.reset_buf == 1] = 0   (:126)
+    scr[16 + 2 * B200_MAX_DOF + k] = a;
+    bf.actions_used[e * na + k] = a;
+  }
+  __syncwarp();
+
+  Lane<float> L;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { L.Q[k] = 0.f; L.qj[k] = 0.f; }
+  L.Q[3] = 1.f; L.qj[3] = 1.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { L.p[k] = 0.f; L.w[k] = 0.f; L.v[k] = 0.f; L.wt[k] = 0.f; }
+  float pdtar[3] = {0.f, 0.f, 0.f};
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { L.p[k] = scr[k]; L.v[k] = scr[7 + k]; L.w[k] = scr[10 + k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) L.Q[k] = scr[3 + k];
+    qnormalize(L.Q);
+  }
+  if (lc.dyn && lane > 0) {
+    float q[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      q[k] = scr[16 + (lc.dof0 + k) * 2];
+      L.wt[k] = scr[16 + (lc.dof0 + k) * 2 + 1];
+      float a = scr[16 + 2 * B200_MAX_DOF + lc.dof0 + k];
+      // _action_to_pd_targets (:391-396): clamp(action, q -+ pd_tar_lim)
+      pdtar[k] = fmaxf(fminf(a, q[k] + cfg.pd_tar_lim), q[k] - cfg.pd_tar_lim);
+      bf.pd_targets[e * nd + lc.dof0 + k] = pdtar[k];
+    }
+    qexp(q, L.qj);
+  }
+  // residual root wrench rotated by the heading of the de-based root rotation (:141-154)
+  float extF[3] = {0.f, 0.f, 0.f}, extT[3] = {0.f, 0.f, 0.f};
+  if (lane == 0 && cfg.res_force_scale > 0.f) {
+    const float* rq = bf.rigid_body_state + e * bf.bodies_per_env * 13 + 3;  // self._rigid_body_rot[:, 0]
+    float q0[4] = {rq[0], rq[1], rq[2], rq[3]}, qb[4], hq[4];
+    ref_remove_base_rot(q0, qb);
+    ref_heading_quat(ref_calc_heading(qb), hq);
+    float f[3], t[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      f[k] = scr[16 + 2 * B200_MAX_DOF + nd + k] * cfg.res_force_scale;
+      t[k] = scr[16 + 2 * B200_MAX_DOF + nd + 3 + k] * cfg.res_torque_scale;
+    }
+    ref_quat_rotate(hq, f, extF);
+    ref_quat_rotate(hq, t, extT);
+  }
+  // previous targets <- current targets (:626-636); the reward below uses them (:677-680)
+  {
+    const int nbl = ml.num_lib_bodies;
+    for (int k = lane; k < nd; k += 32) { bf.p_dof_pos[e * nd + k] = bf.t_dof_pos[e * nd + k]; bf.p_dof_vel[e * nd + k] = bf.t_dof_vel[e * nd + k]; }
+    for (int k = lane; k < nbl * 3; k += 32) bf.p_rb_pos[e * nbl * 3 + k] = bf.t_rb_pos[e * nbl * 3 + k];
+    for (int k = lane; k < nbl * 4; k += 32) bf.p_rb_rot[e * nbl * 4 + k] = bf.t_rb_rot[e * nbl * 4 + k];
+  }
+  __syncwarp();  // the reward below reads p_* rows written by other lanes of this warp
+
+  // ---- physics
+  float cf[3];
+  control_step<float>(B, verts, pc, lc, lane, L, pdtar, extF, extT, cf);
+
+  // ---- write back the simulation state (what gym.refresh_* exposes)
+  float dq[3] = {0.f, 0.f, 0.f};
+  if (lane == 0) {
+    float* wrs = bf.root_states + e * bf.actors_per_env * 13;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { wrs[k] = L.p[k]; wrs[7 + k] = L.v[k]; wrs[10 + k] = L.w[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) wrs[3 + k] = L.Q[k];
+  }
+  if (lc.dyn && lane > 0) {
+    qlog(L.qj, dq);
+    float* wds = bf.dof_state + e * nd * 2;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { wds[(lc.dof0 + k) * 2] = dq[k]; wds[(lc.dof0 + k) * 2 + 1] = L.wt[k]; }
+  }
+  if (lc.active) {
+    float* rb = bf.rigid_body_state + (e * bf.bodies_per_env + lane) * 13;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { rb[k] = L.p[k]; rb[7 + k] = L.v[k]; rb[10 + k] = L.w[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) rb[3 + k] = L.Q[k];
+    float* cfo = bf.contact_forces + (e * bf.bodies_per_env + lane) * 3;
+    cfo[0] = cf[0]; cfo[1] = cf[1]; cfo[2] = cf[2];
+  }
+
+  // ---- post-physics (:398-418)
+  const int64_t progress = bf.progress_buf[e] + 1;
+  const float ref_t = __fadd_rn(bf.ref_motion_times[e], __fmul_rn((float)cfg.control_freq_inv, cfg.sim_dt));
+  const float step_dt = __fmul_rn((float)cfg.control_freq_inv, cfg.sim_dt);
+  const int64_t mid = bf.motion_ids[e];
+  if (lane == 0) { bf.progress_buf[e] = progress; bf.ref_motion_times[e] = ref_t; }
+  const MotionSample ms = sample_motion(ml, M, mid, __fadd_rn(ref_t, step_dt), lane, cfg.ground_tolerance);
+  store_targets(bf, cfg, ml, M, ms, e, lane, lc.dof0);
+
+  // observation
+  const int nbl = ml.num_lib_bodies;
+  const bool is_body = lane < nbl;
+  store_obs_raw(bf.obs_buf + e * bf.num_obs, nbl, nd, cfg.shape_dim, lane, is_body, lc.dof0, L.p, L.Q, L.v, L.w, dq, L.wt,
+                bf.motion_bodies + e * cfg.shape_dim);
+
+  // reward against the PREVIOUS targets (compute_humanoid_reward :918-953)
+  float s_dof = 0.f, s_vel = 0.f, s_pos = 0.f, s_rot = 0.f;
+  if (is_body) {
+    if (lc.dof0 >= 0) {
+      float tq[3], tv[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { tq[k] = bf.p_dof_pos[e * nd + lc.dof0 + k]; tv[k] = bf.p_dof_vel[e * nd + lc.dof0 + k]; }
+      float qa[4], qb[4], oa[6], ob[6];
+      ref_exp_map_to_quat(dq, qa);
+      ref_exp_map_to_quat(tq, qb);
+      ref_tan_norm(qa, oa);
+      ref_tan_norm(qb, ob);
+#pragma unroll
+      for (int k = 0; k < 6; k++) { float d = oa[k] - ob[k]; s_dof += d * d; }
+#pragma unroll
+      for (int k = 0; k < 3; k++) { float d = tv[k] - L.wt[k]; s_vel += d * d; }
+    }
+    const float wgt = cfg.body_pos_weight[lane];
+    float tr[4], cj[4], dqr[4];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { float d = (bf.p_rb_pos[(e * nbl + lane) * 3 + k] - L.p[k]) * wgt; s_pos += d * d; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) tr[k] = bf.p_rb_rot[(e * nbl + lane) * 4 + k];
+    cj[0] = -L.Q[0]; cj[1] = -L.Q[1]; cj[2] = -L.Q[2]; cj[3] = L.Q[3];
+    qmul(tr, cj, dqr);
+    float ang, ax[3];
+    ref_quat_to_angle_axis(dqr, ang, ax);
+    s_rot = ang * ang;
+  }
+  s_dof = warp_sum(s_dof); s_vel = warp_sum(s_vel); s_pos = warp_sum(s_pos); s_rot = warp_sum(s_rot);
+  // reset (compute_humanoid_reset :956-987 + caller :724-739)
+  bool fall = false;
+  if (is_body && cfg.enable_early_termination) fall = (L.p[2] < cfg.termination_height[lane]) && !cfg.contact_body[lane];
+  const bool any_fall = __any_sync(FULL, fall);
+  if (lane == 0) {
+    const int njoint = nd / 3;
+    float r_dof = expf(-cfg.k_dof * (s_dof / (float)(njoint * 6)));
+    float r_vel = expf(-cfg.k_vel * (s_vel / (float)nd));
+    float r_pos = expf(-cfg.k_pos * (s_pos / 3.0f / (float)nbl));
+    float r_rot = expf(-cfg.k_rot * (s_rot / (float)nbl));
+    float rew = cfg.w_dof * r_dof + cfg.w_vel * r_vel + cfg.w_pos * r_pos + cfg.w_rot * r_rot;
+    if (was_reset) { rew = 0.f; r_dof = r_vel = r_pos = r_rot = 0.f; }  // :688-691
+    bf.rew_buf[e] = rew;
+    float* sr = bf.sub_rewards + e * 4;
+    sr[0] = r_dof; sr[1] = r_vel; sr[2] = r_pos; sr[3] = r_rot;
+    int64_t terminated = (cfg.enable_early_termination && any_fall && progress > 1) ? 1 : 0;
+    const bool cond = (progress >= (int64_t)cfg.max_episode_length - 1) || (ref_t >= ml.motion_lengths[mid]);
+    int64_t reset = cond ? 1 : terminated;
+    if (was_reset) { reset = 1; terminated = bf.terminate_buf[e]; }
+    bf.reset_buf[e] = reset;
+    bf.terminate_buf[e] = terminated;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// reset: ref-state init from the MoCap buffer (_reset_ref_state_init :489-528, _set_env_state :741-755)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+reset_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf, b200_motion_lib_t ml,
+             const int64_t* __restrict__ env_ids, const float* __restrict__ times, int n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * WARPS_PER_CTA + warp;
+  if (i >= n) return;
+  const b200_model_t& M = gblob->m;
+  const b200_cfg_t& cfg = *gcfg;
+  const int64_t e = env_ids[i];
+  const float t = times[i];
+  const int64_t mid = bf.motion_ids[e];
+  const int nd = M.nd, nbl = ml.num_lib_bodies;
+  const int dof0 = lane < M.nb ? M.dof_of_body[lane] : -1;
+  const MotionSample s = sample_motion(ml, M, mid, t, lane, cfg.ground_tolerance);
+  const bool is_body = lane < nbl;
+  float zero3[3] = {0.f, 0.f, 0.f};
+  if (lane == 0) {
+    float* rs = bf.root_states + e * bf.actors_per_env * 13;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { rs[k] = s.rb_pos[k]; rs[7 + k] = s.root_vel[k]; rs[10 + k] = s.root_ang_vel[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) rs[3 + k] = s.rb_rot[k];
+    bf.progress_buf[e] = 0; bf.reset_buf[e] = 0; bf.terminate_buf[e] = 0;  // humanoid_smpl.py:170-172
+    bf.ref_motion_times[e] = t;
+  }
+  float dv[3] = {0.f, 0.f, 0.f};
+  if (is_body) {
+    float* rb = bf.rigid_body_state + (e * bf.bodies_per_env + lane) * 13;  // :746-749 (+ _refresh_sim_tensors :457-463)
+#pragma unroll
+    for (int k = 0; k < 3; k++) { rb[k] = s.rb_pos[k]; rb[7 + k] = 0.f; rb[10 + k] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) rb[3 + k] = s.rb_rot[k];
+    if (dof0 >= 0) {
+      float* ds = bf.dof_state + e * nd * 2;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { dv[k] = ml.dvs[s.f0 * nd + dof0 + k]; ds[(dof0 + k) * 2] = s.dof[k]; ds[(dof0 + k) * 2 + 1] = dv[k]; }
+    }
+  } else if (lane < M.nb) {  // welded extra bodies (Racket): placed by the first step's FK; park at the parent pose
+    float* rb = bf.rigid_body_state + (e * bf.bodies_per_env + lane) * 13;
+    const int par = M.parent[lane];
+    const float* prow = bf.rigid_body_state + (e * bf.bodies_per_env + par) * 13;
+    (void)prow;
+#pragma unroll
+    for (int k = 0; k < 13; k++) rb[k] = (k == 6) ? 1.f : 0.f;
+  }
+  // targets = MoCap state one control step ahead (:525 -> _set_target_motion_state :594-624)
+  const float step_dt = __fmul_rn((float)cfg.control_freq_inv, cfg.sim_dt);
+  const MotionSample tg = sample_motion(ml, M, mid, __fadd_rn(t, step_dt), lane, cfg.ground_tolerance);
+  store_targets(bf, cfg, ml, M, tg, e, lane, dof0);
+  // _compute_observations(env_ids) (humanoid_smpl.py:158)
+  store_obs_raw(bf.obs_buf + e * bf.num_obs, nbl, nd, cfg.shape_dim, lane, is_body, dof0, s.rb_pos, s.rb_rot, zero3, zero3, s.dof, dv,
+                bf.motion_bodies + e * cfg.shape_dim);
+}
+
+// MotionLib.get_motion_state for arbitrary (id, time) pairs
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+motion_state_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __restrict__ gcfg, b200_motion_lib_t ml,
+                    const int64_t* __restrict__ ids, const float* __restrict__ times, int n, float* root_pos, float* root_rot,
+                    float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* key_pos, float* rb_pos,
+                    float* rb_rot) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+  if (i >= n) return;
+  const b200_model_t& M = gblob->m;
+  const b200_cfg_t& cfg = *gcfg;
+  const int nd = M.nd, nbl = ml.num_lib_bodies;
+  const int dof0 = lane < M.nb ? M.dof_of_body[lane] : -1;
+  const MotionSample s = sample_motion(ml, M, ids[i], times[i], lane, cfg.ground_tolerance);
+  if (lane < nbl) {
+    if (rb_pos) for (int k = 0; k < 3; k++) rb_pos[(i * nbl + lane) * 3 + k] = s.rb_pos[k];
+    if (rb_rot) for (int k = 0; k < 4; k++) rb_rot[(i * nbl + lane) * 4 + k] = s.rb_rot[k];
+    if (dof_pos && dof0 >= 0) for (int k = 0; k < 3; k++) dof_pos[i * nd + dof0 + k] = s.dof[k];
+    if (key_pos)
+      for (int k = 0; k < cfg.num_key; k++)
+        if (cfg.key_body[k] == lane) for (int j = 0; j < 3; j++) key_pos[(i * cfg.num_key + k) * 3 + j] = s.rb_pos[j];
+  }
+  if (lane == 0) {
+    for (int k = 0; k < 3; k++) {
+      if (root_pos) root_pos[i * 3 + k] = s.rb_pos[k];
+      if (root_vel) root_vel[i * 3 + k] = s.root_vel[k];
+      if (root_ang_vel) root_ang_vel[i * 3 + k] = s.root_ang_vel[k];
+    }
+    if (root_rot) for (int k = 0; k < 4; k++) root_rot[i * 4 + k] = s.rb_rot[k];
+  }
+  if (dof_vel) for (int k = lane; k < nd; k += 32) dof_vel[i * nd + k] = ml.dvs[s.f0 * nd + k];
+}
+
+// compute_humanoid_observations_imitation (humanoid_smpl_im.py:773-850): warp per env, lane per body
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restrict__ body_pos, const float* __restrict__ body_rot,
+                     const float* __restrict__ target_pos, const float* __restrict__ target_rot, const float* __restrict__ dof_pos,
+                     const float* __restrict__ dof_vel, const float* __restrict__ target_dof_pos, const float* __restrict__ body_vel,
+                     const float* __restrict__ body_ang_vel, const float* __restrict__ motion_bodies, int local_root_obs,
+                     int root_height_obs, float* __restrict__ obs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+  if (e >= n) return;
+  const int W = 1 + (nb - 1) * 3 + nb * 6 + nb * 3 + nb * 3 + nd + 1 + 6 + 2 + 2 + nd + nb * 3 + nb * 6 + shape_dim;
+  float* o = obs + e * W;
+  const bool act = lane < nb;
+  float p[3] = {0, 0, 0}, q[4] = {0, 0, 0, 1}, v[3] = {0, 0, 0}, w[3] = {0, 0, 0}, tp[3] = {0, 0, 0}, tq[4] = {0, 0, 0, 1};
+  if (act) {
+    const int64_t i3 = (e * nb + lane) * 3, i4 = (e * nb + lane) * 4;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { p[k] = body_pos[i3 + k]; v[k] = body_vel[i3 + k]; w[k] = body_ang_vel[i3 + k]; tp[k] = target_pos[i3 + k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) { q[k] = body_rot[i4 + k]; tq[k] = target_rot[i4 + k]; }
+  }
+  float rp[3], rq[4], trp[3], trq[4];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { rp[k] = shfl(p[k], 0); trp[k] = shfl(tp[k], 0); }
+#pragma unroll
+  for (int k = 0; k < 4; k++) { rq[k] = shfl(q[k], 0); trq[k] = shfl(tq[k], 0); }
+  float root_rot[4], hq[4], t_root_rot[4];
+  ref_remove_base_rot(rq, root_rot);
+  const float heading = ref_calc_heading(root_rot);
+  ref_heading_quat(-heading, hq);
+  ref_remove_base_rot(trq, t_root_rot);
+  const float t_heading = ref_calc_heading(t_root_rot);
+  int off = 0;
+  if (lane == 0) o[0] = root_height_obs ? rp[2] : 0.f;
+  off = 1;
+  if (act) {
+    float d[3] = {p[0] - rp[0], p[1] - rp[1], p[2] - rp[2]}, l[3];
+    ref_quat_rotate(hq, d, l);
+    if (lane > 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) o[off + (lane - 1) * 3 + k] = l[k];
+    }
+  }
+  off += (nb - 1) * 3;
+  if (act) {
+    float lq[4], tn[6];
+    qmul(hq, q, lq);
+    ref_tan_norm(lq, tn);
+    if (lane == 0 && local_root_obs) ref_tan_norm(root_rot, tn);  // quirk kept (:806-809)
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[off + lane * 6 + k] = tn[k];
+  }
+  off += nb * 6;
+  if (act) {
+    float l[3];
+    ref_quat_rotate(hq, v, l);
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[off + lane * 3 + k] = l[k];
+    ref_quat_rotate(hq, w, l);
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[off + nb * 3 + lane * 3 + k] = l[k];
+  }
+  off += nb * 6;
+  for (int k = lane; k < nd; k += 32) o[off + k] = dof_vel[e * nd + k];
+  off += nd;
+  if (lane == 0) {
+    o[off] = rp[2] - trp[2];
+    float cj[4] = {-root_rot[0], -root_rot[1], -root_rot[2], root_rot[3]}, rel[4], tn[6];
+    qmul(t_root_rot, cj, rel);
+    ref_tan_norm(rel, tn);
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[off + 1 + k] = tn[k];
+    float d[3] = {trp[0] - rp[0], trp[1] - rp[1], trp[2] - rp[2]}, l[3];
+    ref_quat_rotate(hq, d, l);
+    o[off + 7] = l[0]; o[off + 8] = l[1];
+    const float dh = t_heading - heading;
+    o[off + 9] = cosf(dh); o[off + 10] = sinf(dh);
+  }
+  off += 11;
+  for (int k = lane; k < nd; k += 32) o[off + k] = target_dof_pos[e * nd + k] - dof_pos[e * nd + k];
+  off += nd;
+  if (act) {
+    float d[3] = {tp[0] - p[0], tp[1] - p[1], tp[2] - p[2]}, l[3];
+    ref_quat_rotate(hq, d, l);
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[off + lane * 3 + k] = l[k];
+  }
+  off += nb * 3;
+  if (act) {
+    float cj[4] = {-q[0], -q[1], -q[2], q[3]}, rel[4], tn[6];
+    qmul(cj, tq, rel);
+    ref_tan_norm(rel, tn);
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[off + lane * 6 + k] = tn[k];
+  }
+  off += nb * 6;
+  if (lane < shape_dim) o[off + lane] = motion_bodies[e * shape_dim + lane];
+}
+
+// physics-only entry used by the parity tests (float or double)
+template <typename T>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+physics_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, int n, int n_steps,
+               T* root, T* dof_pos, T* dof_vel, const T* pd_tar, const T* ext, T* rb_out, T* contact_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  load_blob(smem, gblob, blob_bytes, &mbar);
+  const DevBlob& B = *reinterpret_cast<const DevBlob*>(smem);
+  const b200_model_t& M = B.m;
+  const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+  if (e >= n) return;
+  const LaneConst lc = lane_const(M, lane);
+  const int nb = M.nb, nd = M.nd;
+  const PhysCfg<T> pc = make_phys_cfg<T>(*gcfg);
+  Lane<T> L;
+  for (int k = 0; k < 4; k++) { L.Q[k] = 0; L.qj[k] = 0; }
+  L.Q[3] = 1; L.qj[3] = 1;
+  for (int k = 0; k < 3; k++) { L.p[k] = 0; L.w[k] = 0; L.v[k] = 0; L.wt[k] = 0; }
+  T pdt[3] = {0, 0, 0}, eF[3] = {0, 0, 0}, eT[3] = {0, 0, 0}, cf[3] = {0, 0, 0};
+  if (lane == 0) {
+    const T* rs = root + e * 13;
+    for (int k = 0; k < 3; k++) { L.p[k] = rs[k]; L.v[k] = rs[7 + k]; L.w[k] = rs[10 + k]; }
+    for (int k = 0; k < 4; k++) L.Q[k] = rs[3 + k];
+    qnormalize(L.Q);
+    if (ext) for (int k = 0; k < 3; k++) { eF[k] = ext[e * 6 + k]; eT[k] = ext[e * 6 + 3 + k]; }
+  }
+  if (lc.dyn && lane > 0) {
+    T q[3];
+    for (int k = 0; k < 3; k++) { q[k] = dof_pos[e * nd + lc.dof0 + k]; L.wt[k] = dof_vel[e * nd + lc.dof0 + k]; pdt[k] = pd_tar[e * nd + lc.dof0 + k]; }
+    qexp(q, L.qj);
+  }
+  for (int s = 0; s < n_steps; s++) {
+    control_step<T>(B, verts, pc, lc, lane, L, pdt, eF, eT, cf);
+    if (s + 1 < n_steps && lc.dyn && lane > 0) {  // the state crosses control steps as exp-map coordinates
+      T q[3];
+      qlog(L.qj, q);
+      qexp(q, L.qj);
+    }
+  }
+  if (lane == 0) {
+    T* rs = root + e * 13;
+    for (int k = 0; k < 3; k++) { rs[k] = L.p[k]; rs[7 + k] = L.v[k]; rs[10 + k] = L.w[k]; }
+    for (int k = 0; k < 4; k++) rs[3 + k] = L.Q[k];
+  }
+  if (lc.dyn && lane > 0) {
+    T q[3];
+    qlog(L.qj, q);
+    for (int k = 0; k < 3; k++) { dof_pos[e * nd + lc.dof0 + k] = q[k]; dof_vel[e * nd + lc.dof0 + k] = L.wt[k]; }
+  }
+  if (lc.active) {
+    T* rb = rb_out + (e * nb + lane) * 13;
+    for (int k = 0; k < 3; k++) { rb[k] = L.p[k]; rb[7 + k] = L.v[k]; rb[10 + k] = L.w[k]; }
+    for (int k = 0; k < 4; k++) rb[3 + k] = L.Q[k];
+    if (contact_out) for (int k = 0; k < 3; k++) contact_out[(e * nb + lane) * 3 + k] = cf[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+extern "C" {
+
+int b200env_abi_version(void) { return B200_ABI_VERSION; }
+const char* b200env_last_error(void) { return g_err; }
+
+int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg_t* cfg, int32_t num_envs, int32_t device,
+                   b200env_handle* out) {
+  if (!model || !verts || !cfg || !out) return fail(-1, "b200env_create: null argument%s");
+  if (model->nb < 1 || model->nb > B200_MAX_BODIES || model->nd > B200_MAX_DOF || model->nd % 3)
+    return fail(-2, "b200env_create: model dimensions out of range%s");
+  if (model->max_depth >= MAX_LEVELS) return fail(-2, "b200env_create: kinematic tree too deep%s");
+  if (model->vmax % 4) return fail(-2, "b200env_create: vmax must be a multiple of 4%s");
+  if (num_envs < 1) return fail(-2, "b200env_create: num_envs must be positive%s");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(-3, "b200env_create: no CUDA device - this library has no CPU fallback%s");
+  CUDA_OK(cudaSetDevice(device));
+  b200env* h = new b200env();
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  h->num_envs = num_envs;
+  h->model = *model;
+  h->cfg = *cfg;
+  // tree tables
+  DevBlob hb;
+  memset(&hb, 0, sizeof(hb));
+  hb.m = *model;
+  for (int b = 0; b < B200_MAX_BODIES; b++)
+    for (int c = 0; c < MAX_CHILD; c++) hb.t.child[b][c] = -1;
+  int cnt[B200_MAX_BODIES] = {0};
+  for (int b = 1; b < model->nb; b++) {
+    if (model->fixed[b]) continue;
+    int p = model->parent[b];
+    if (p < 0 || p >= b) { delete h; return fail(-2, "b200env_create: bodies must be in topological order%s"); }
+    if (cnt[p] >= MAX_CHILD) { delete h; return fail(-2, "b200env_create: too many children per body%s"); }
+    hb.t.child[p][cnt[p]++] = b;
+  }
+  for (int b = 0; b < model->nb; b++)
+    if (cnt[b] > hb.t.maxch[model->depth[b]]) hb.t.maxch[model->depth[b]] = cnt[b];
+  const size_t vbytes = (size_t)model->nb * model->vmax * 3 * sizeof(float);
+  h->blob_bytes = sizeof(DevBlob) + ((vbytes + 15) & ~(size_t)15);
+  CUDA_OK(cudaMalloc(&h->d_blob, h->blob_bytes));
+  CUDA_OK(cudaMemset(h->d_blob, 0, h->blob_bytes));
+  CUDA_OK(cudaMemcpy(h->d_blob, &hb, sizeof(hb), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy((char*)h->d_blob + sizeof(DevBlob), verts, vbytes, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&h->d_cfg, sizeof(b200_cfg_t)));
+  CUDA_OK(cudaMemcpy(h->d_cfg, cfg, sizeof(b200_cfg_t), cudaMemcpyHostToDevice));
+  *out = h;
+  return 0;
+}
+
+int b200env_destroy(b200env_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_blob);
+  cudaFree(h->d_cfg);
+  delete h;
+  return 0;
+}
+
+int b200env_bind(b200env_handle h, const b200_buffers_t* bufs) {
+  if (!h || !bufs) return fail(-1, "b200env_bind: null argument%s");
+  const void* req[] = {bufs->root_states, bufs->dof_state, bufs->rigid_body_state, bufs->contact_forces, bufs->obs_buf, bufs->rew_buf,
+                       bufs->sub_rewards, bufs->reset_buf, bufs->progress_buf, bufs->terminate_buf, bufs->motion_ids,
+                       bufs->ref_motion_times, bufs->motion_bodies, bufs->t_root_pos, bufs->t_root_rot, bufs->t_dof_pos,
+                       bufs->t_root_vel, bufs->t_root_ang_vel, bufs->t_dof_vel, bufs->t_key_pos, bufs->t_rb_pos, bufs->t_rb_rot,
+                       bufs->p_dof_pos, bufs->p_dof_vel, bufs->p_rb_pos, bufs->p_rb_rot, bufs->pd_targets, bufs->actions_used};
+  for (size_t i = 0; i < sizeof(req) / sizeof(req[0]); i++)
+    if (!req[i]) return fail(-1, "b200env_bind: a required buffer pointer is null%s");
+  if (bufs->bodies_per_env < h->model.nb || bufs->actors_per_env < 1) return fail(-2, "b200env_bind: bad bodies/actors per env%s");
+  if (((uintptr_t)bufs->t_rb_rot | (uintptr_t)bufs->p_rb_rot) & 15) return fail(-2, "b200env_bind: quaternion rows must be 16-byte aligned%s");
+  h->bufs = *bufs;
+  h->bound = true;
+  return 0;
+}
+
+int b200env_set_motion_lib(b200env_handle h, const b200_motion_lib_t* ml) {
+  if (!h || !ml) return fail(-1, "b200env_set_motion_lib: null argument%s");
+  if (!ml->gts || !ml->grs || !ml->lrs || !ml->grvs || !ml->gravs || !ml->dvs || !ml->motion_lengths || !ml->num_frames ||
+      !ml->motion_dt || !ml->length_starts || !ml->min_verts_h)
+    return fail(-1, "b200env_set_motion_lib: null array%s");
+  if (ml->num_lib_bodies < 1 || ml->num_lib_bodies > h->model.nb) return fail(-2, "b200env_set_motion_lib: body count mismatch%s");
+  if (((uintptr_t)ml->grs | (uintptr_t)ml->lrs) & 15) return fail(-2, "b200env_set_motion_lib: grs/lrs must be 16-byte aligned%s");
+  h->ml = *ml;
+  h->has_ml = true;
+  return 0;
+}
+
+static size_t step_smem(const b200env* h) { return ((h->blob_bytes + 15) & ~(size_t)15) + WARPS_PER_CTA * SCRATCH_FLOATS * sizeof(float); }
+
+int b200env_step(b200env_handle h, const float* actions, void* stream) {
+  if (!h || !actions) return fail(-1, "b200env_step: null argument%s");
+  if (!h->bound || !h->has_ml) return fail(-4, "b200env_step: bind buffers and a motion lib first%s");
+  cudaSetDevice(h->device);
+  const int grid = (h->num_envs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const size_t smem = step_smem(h);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_OK(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  step_kernel<<<grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg,
+                                                                        h->bufs, h->ml, actions, h->num_envs);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int b200env_reset(b200env_handle h, const int64_t* env_ids, const float* motion_times, int32_t n, void* stream) {
+  if (!h) return fail(-1, "b200env_reset: null handle%s");
+  if (n == 0) return 0;
+  if (!env_ids || !motion_times || n < 0) return fail(-1, "b200env_reset: bad arguments%s");
+  if (!h->bound || !h->has_ml) return fail(-4, "b200env_reset: bind buffers and a motion lib first%s");
+  cudaSetDevice(h->device);
+  const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  reset_kernel<<<grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->bufs, h->ml, env_ids,
+                                                                      motion_times, n);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int b200env_motion_state(b200env_handle h, const int64_t* motion_ids, const float* motion_times, int32_t n, float* root_pos,
+                         float* root_rot, float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* key_pos,
+                         float* rb_pos, float* rb_rot, void* stream) {
+  if (!h) return fail(-1, "b200env_motion_state: null handle%s");
+  if (n == 0) return 0;
+  if (!motion_ids || !motion_times || n < 0) return fail(-1, "b200env_motion_state: bad arguments%s");
+  if (!h->has_ml) return fail(-4, "b200env_motion_state: set a motion lib first%s");
+  cudaSetDevice(h->device);
+  const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  motion_state_kernel<<<grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->ml, motion_ids,
+                                                                             motion_times, n, root_pos, root_rot, dof_pos, root_vel,
+                                                                             root_ang_vel, dof_vel, key_pos, rb_pos, rb_rot);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int b200env_obs_imitation(b200env_handle h, int32_t n, const float* body_pos, const float* body_rot, const float* target_pos,
+                          const float* target_rot, const float* dof_pos, const float* dof_vel, const float* target_dof_pos,
+                          const float* body_vel, const float* body_ang_vel, const float* motion_bodies, int32_t local_root_obs,
+                          int32_t root_height_obs, float* obs, void* stream) {
+  if (!h) return fail(-1, "b200env_obs_imitation: null handle%s");
+  if (n == 0) return 0;
+  if (!body_pos || !body_rot || !target_pos || !target_rot || !dof_pos || !dof_vel || !target_dof_pos || !body_vel || !body_ang_vel ||
+      !motion_bodies || !obs || n < 0)
+    return fail(-1, "b200env_obs_imitation: bad arguments%s");
+  cudaSetDevice(h->device);
+  const int nbl = h->has_ml ? h->ml.num_lib_bodies : (h->model.fixed[h->model.nb - 1] ? h->model.nb - 1 : h->model.nb);
+  const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  obs_imitation_kernel<<<grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(n, nbl, h->model.nd, h->cfg.shape_dim, body_pos, body_rot,
+                                                                              target_pos, target_rot, dof_pos, dof_vel, target_dof_pos,
+                                                                              body_vel, body_ang_vel, motion_bodies, local_root_obs,
+                                                                              root_height_obs, obs);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_steps, void* root, void* dof_pos, void* dof_vel,
+                         const void* pd_tar, const void* ext_wrench, void* rb_out, void* contact_out, void* stream) {
+  if (!h || !root || !dof_pos || !dof_vel || !pd_tar || !rb_out) return fail(-1, "b200env_physics_only: null argument%s");
+  if (n <= 0 || n_steps <= 0) return fail(-2, "b200env_physics_only: n and n_steps must be positive%s");
+  cudaSetDevice(h->device);
+  const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const size_t smem = (h->blob_bytes + 15) & ~(size_t)15;
+  if (prec == 0) {
+    CUDA_OK(cudaFuncSetAttribute(physics_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    physics_kernel<float><<<grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(
+        (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, n, n_steps, (float*)root, (float*)dof_pos, (float*)dof_vel,
+        (const float*)pd_tar, (const float*)ext_wrench, (float*)rb_out, (float*)contact_out);
+  } else if (prec == 1) {
+    CUDA_OK(cudaFuncSetAttribute(physics_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    physics_kernel<double><<<grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(
+        (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, n, n_steps, (double*)root, (double*)dof_pos, (double*)dof_vel,
+        (const double*)pd_tar, (const double*)ext_wrench, (double*)rb_out, (double*)contact_out);
+  } else {
+    return fail(-2, "b200env_physics_only: prec must be 0 (float) or 1 (double)%s");
+  }
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int64_t b200env_launch_count(b200env_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+"""ctypes binding of libb200env.so (C ABI: include/b200env.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or no GPU is visible the
+product path raises.  (CPU restatements live in oracle/ and are test infrastructure.)
+"""
+import ctypes as C
+import os
+
+from . import abi
+from .build import LIB
+
+_lib = None
+
+SYMBOLS = ["b200env_abi_version", "b200env_last_error", "b200env_create", "b200env_destroy", "b200env_bind",
+           "b200env_set_motion_lib", "b200env_step", "b200env_reset", "b200env_motion_state", "b200env_obs_imitation",
+           "b200env_physics_only", "b200env_launch_count"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise RuntimeError(f"{LIB} not built - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the B200 environment has no CPU fallback)")
+        L = C.CDLL(LIB)
+        L.b200env_last_error.restype = C.c_char_p
+        L.b200env_launch_count.restype = C.c_int64
+        L.b200env_launch_count.argtypes = [C.c_void_p]
+        for name in SYMBOLS:
+            getattr(L, name)
+        if L.b200env_abi_version() != abi.ABI_VERSION:
+            raise RuntimeError("libb200env.so ABI version mismatch - rebuild")
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(f"b200env error {rc}: {lib().b200env_last_error().decode()}")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Env:
+    """Owns one b200env handle.  All tensors passed in must live on `device` and be contiguous."""
+
+    def __init__(self, model_struct, verts, cfg_struct, num_envs, device_index):
+        self._h = C.c_void_p()
+        self._keep = []
+        import numpy as np
+        verts = np.ascontiguousarray(verts, np.float32)
+        _check(lib().b200env_create(C.byref(model_struct), verts.ctypes.data_as(C.c_void_p), C.byref(cfg_struct),
+                                    C.c_int32(num_envs), C.c_int32(device_index), C.byref(self._h)))
+        self.model, self.cfg, self.num_envs = model_struct, cfg_struct, num_envs
+
+    def close(self):
+        if self._h:
+            lib().b200env_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bind(self, tensors, actors_per_env, bodies_per_env, num_obs):
+        b = abi.Buffers()
+        for name, _ in abi.Buffers._fields_:
+            if name in ("actors_per_env", "bodies_per_env", "num_obs"):
+                continue
+            t = tensors[name]
+            assert t.is_cuda and t.is_contiguous(), name
+            setattr(b, name, t.data_ptr())
+        b.actors_per_env, b.bodies_per_env, b.num_obs = actors_per_env, bodies_per_env, num_obs
+        self._keep.append(tensors)
+        _check(lib().b200env_bind(self._h, C.byref(b)))
+
+    def set_motion_lib(self, t, num_lib_bodies):
+        v = abi.MotionLibView()
+        for k in ("gts", "grs", "lrs", "grvs", "gravs", "dvs", "motion_lengths", "num_frames", "motion_dt", "length_starts",
+                  "min_verts_h"):
+            assert t[k].is_cuda and t[k].is_contiguous(), k
+            setattr(v, k, t[k].data_ptr())
+        v.num_motions = t["motion_lengths"].shape[0]
+        v.num_lib_bodies = num_lib_bodies
+        v.total_frames = t["gts"].shape[0]
+        self._keep.append(t)
+        _check(lib().b200env_set_motion_lib(self._h, C.byref(v)))
+
+    def step(self, actions):
+        assert actions.is_cuda and actions.is_contiguous() and actions.dtype.is_floating_point
+        _check(lib().b200env_step(self._h, _ptr(actions), _stream()))
+
+    def reset(self, env_ids, motion_times):
+        n = int(env_ids.shape[0])
+        if n:
+            _check(lib().b200env_reset(self._h, _ptr(env_ids), _ptr(motion_times), C.c_int32(n), _stream()))
+
+    def motion_state(self, ids, times, out):
+        """out: dict name -> tensor or None for root_pos, root_rot, dof_pos, root_vel, root_ang_vel, dof_vel, key_pos,
+        rb_pos, rb_rot."""
+        names = ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "key_pos", "rb_pos", "rb_rot")
+        _check(lib().b200env_motion_state(self._h, _ptr(ids), _ptr(times), C.c_int32(int(ids.shape[0])),
+                                          *[_ptr(out.get(k)) for k in names], _stream()))
+
+    def obs_imitation(self, body_pos, body_rot, target_pos, target_rot, dof_pos, dof_vel, target_dof_pos, body_vel,
+                      body_ang_vel, motion_bodies, local_root_obs, root_height_obs, obs):
+        n = int(body_pos.shape[0])
+        _check(lib().b200env_obs_imitation(self._h, C.c_int32(n), _ptr(body_pos), _ptr(body_rot), _ptr(target_pos),
+                                           _ptr(target_rot), _ptr(dof_pos), _ptr(dof_vel), _ptr(target_dof_pos),
+                                           _ptr(body_vel), _ptr(body_ang_vel), _ptr(motion_bodies),
+                                           C.c_int32(int(local_root_obs)), C.c_int32(int(root_height_obs)), _ptr(obs),
+                                           _stream()))
+
+    def physics_only(self, root, dof_pos, dof_vel, pd_tar, ext_wrench, rb_out, contact_out, n_steps=1):
+        import torch
+        prec = {torch.float32: 0, torch.float64: 1}[root.dtype]
+        for t in (dof_pos, dof_vel, pd_tar, rb_out):
+            assert t.dtype == root.dtype and t.is_cuda and t.is_contiguous()
+        _check(lib().b200env_physics_only(self._h, C.c_int32(prec), C.c_int32(int(root.shape[0])), C.c_int32(n_steps),
+                                          _ptr(root), _ptr(dof_pos), _ptr(dof_vel), _ptr(pd_tar), _ptr(ext_wrench),
+                                          _ptr(rb_out), _ptr(contact_out), _stream()))
+
+    @property
+    def launch_count(self):
+        return int(lib().b200env_launch_count(self._h))
