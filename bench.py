@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py - env-steps/s of the vid2player3d rollout hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--envs 8192] [--impl b200|reference]
+
+One "step" = one `task.step(actions)` over all envs of a rank (2 sim steps x 2 substeps of the articulated
+step + MoCap target + obs + reward + reset), random policy, with `task.reset()` of all envs every 32 steps
+like the reference's ImitatorAgent.play_steps (agents/im_agent.py:305-409) - resets are inside the timed
+region.  Workload = embodied_pose amass_im (BASELINE config 2 at the metric's 8192 envs): SMPL humanoid,
+24 bodies / 69 dof, synthetic MoCap library (64 motions x 300 frames, seed 7), episodeLength 300.
+Multi-GPU: envs shard across ranks, no data-path collective ("weak": 8192 envs per GPU).
+
+Timing: every step is bracketed by CUDA events on the launching stream; an L2 flush (256 MiB memset) runs
+between timed steps, outside the event pairs.  value = envs * K / sum(step times), max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ALGO_BYTES_PER_ENV_STEP = 9792  # SURVEY.md 8(d), embodied_pose configs; derivation in DESIGN.md 5
+HORIZON = 32
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=640)
+    p.add_argument("--warmup", type=int, default=64)
+    p.add_argument("--envs", type=int, default=8192, help="envs per GPU")
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--cpu-sample-envs", type=int, default=1024)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_workload(envs, device_index, seed):
+    import torch
+    from helpers import SIM_PARAMS, im_cfg
+    from vid2player3d_b200 import model_compiler, motion_lib
+    from vid2player3d_b200.tasks import HumanoidSMPLIM, VecTaskPythonWrapper
+    model = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    flat = motion_lib.synthetic(model, num_motions=64, num_frames=300, seed=7, sigma=0.05)
+    torch.manual_seed(seed)
+    task = HumanoidSMPLIM(im_cfg(envs, flat, episodeLength=300), SIM_PARAMS, 1, "cuda", device_index, True)
+    return model, flat, task, VecTaskPythonWrapper(task, task.device, 5.0, 1.0)
+
+
+def cpu_reference_arm(model, flat, sample_envs, steps, warmup, seed=7):
+    """The CPU restatement of the same env step (oracle/physics_ref.c with OpenMP over envs + oracle/ref_port.py
+    numpy obs/reward/reset/MoCap), timed on the host cores on a bounded sample of the workload's envs.
+    Stand-in for the reference's Isaac Gym CPU pipeline, which cannot run here."""
+    import numpy as np
+    from helpers import lib_dict
+    from oracle import physics_ref, ref_port as R
+    from vid2player3d_b200 import abi
+    rng = np.random.default_rng(seed)
+    n = sample_envs
+    ms, verts = abi.pack_model(model, float(model["mass"].sum()) / 90.0)
+    cfg = abi.make_cfg(model)
+    ml = lib_dict(flat, model)
+    mids = rng.integers(0, flat.num_motions(), n)
+    t0 = (rng.random(n) * np.maximum(ml["motion_lengths"][mids] - 32 / 30.0, 0)).astype(np.float32)
+    st = R.get_motion_state(ml, mids, t0)
+    root = np.concatenate([st[0], st[1], st[3], st[4]], -1).astype(np.float64)
+    q, qd = st[2].astype(np.float64), st[5].astype(np.float64)
+    rbs = np.zeros((n, 24, 13), np.float32)
+    rbs[..., 0:3], rbs[..., 3:7] = st[7], st[8]
+    orc = R.ImTaskOracle(ml, mids, t0, np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64),
+                         np.float32(2) * np.float32(1 / 60), 300, np.full(24, -0.5, np.float32), np.array([3, 7]),
+                         np.ones(24, np.float32), ml["motion_bodies"][mids])
+
+    def one_step():
+        nonlocal rbs
+        a = (rng.random((n, 75)) * 2 - 1).astype(np.float32)
+        _, pd, f, t = orc.pre_physics(a, q.astype(np.float32), rbs[:, 0, 3:7])
+        rb, _ = physics_ref.control_step(ms, verts, cfg, root, q, qd, pd.astype(np.float64), np.concatenate([f, t], -1).astype(np.float64))
+        rbs = rb.astype(np.float32)
+        dofs = np.stack([q, qd], -1).astype(np.float32)
+        orc.post_physics(rbs, dofs)
+
+    for _ in range(warmup):
+        one_step()
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t_start
+    return n * steps / dt, dt / steps * 1e3
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    workload = (f"embodied_pose amass_im: {args.envs} envs/GPU, SMPL humanoid 24 bodies/69 dof, synthetic MoCap 64x300 frames, "
+                f"random policy, reset(all) every {HORIZON} steps")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from vid2player3d_b200 import model_compiler, motion_lib
+        from oracle import physics_ref
+        physics_ref.build()
+        model = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+        flat = motion_lib.synthetic(model, num_motions=64, num_frames=300, seed=7, sigma=0.05)
+        steps, warm = min(args.steps, 40), min(args.warmup, 3)
+        v, ms_step = cpu_reference_arm(model, flat, args.cpu_sample_envs, steps, warm)
+        sample = f"{args.cpu_sample_envs} of {args.envs} envs x {steps} steps, OpenMP over envs + numpy"
+        print(json.dumps({
+            "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 physics / f32 task logic", "data": "synthetic",
+            "config": {"workload": workload, "note": "CPU restatement of the same step (oracle/); the reference's Isaac Gym CPU "
+                       "pipeline cannot be installed here (closed binary, py3.8) - stand-in, labelled as such"},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    model, flat, task, vec = build_workload(args.envs, local_rank, 7 + rank)  # seed += rank like run.py:37
+    dev = task.device
+    N, K, W = args.envs, args.steps, args.warmup
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    pool = [torch.rand(N, task.num_actions, device=dev, generator=gen) * 2 - 1 for _ in range(16)]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm (`value`) ----------------
+    def run(nsteps, timed):
+        evs = []
+        for i in range(nsteps):
+            if timed:
+                flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if i % HORIZON == 0:
+                task.reset()
+            task.step(pool[i % len(pool)])
+            if timed:
+                e1.record()
+                evs.append((e0, e1, i % HORIZON == 0))
+        return evs
+
+    task.reset()
+    run(max(W, 3), False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = task._env.launch_count
+    t_wall = time.perf_counter()
+    evs = run(K, True)
+    barrier()
+    wall = time.perf_counter() - t_wall
+    launches = task._env.launch_count - launches0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b, _ in evs]
+    total_ms = sum(step_ms)
+    plain = [m for m, (_, _, r) in zip(step_ms, evs) if not r]
+    kernel_ms = sum(plain) / max(len(plain), 1)  # steps without a reset = exactly one step_kernel launch
+
+    # back-to-back (hot L2), single event pair: informational
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(K, False)
+    e1.record()
+    barrier()
+    hot_ms = e0.elapsed_time(e1)
+
+    # ---------------- end-to-end arm through the VecTask API with host buffers ----------------
+    host_actions = [p.cpu().pin_memory() for p in pool[:4]]
+    host_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    host_reset = torch.empty(N, dtype=torch.long).pin_memory()
+    dev_act = torch.empty(N, task.num_actions, device=dev)
+
+    def run_e2e(nsteps):
+        for i in range(nsteps):
+            if i % HORIZON == 0:
+                vec.reset()
+            dev_act.copy_(host_actions[i % len(host_actions)], non_blocking=True)
+            obs, rew, reset, _ = vec.step(dev_act)
+            host_rew.copy_(rew, non_blocking=True)
+            host_reset.copy_(reset, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller consumes rew/reset on the host every step
+
+    run_e2e(max(W // 4, 3))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_e2e(K)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # max over ranks
+    t = torch.tensor([total_ms, hot_ms, e2e_ms, kernel_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, hot_ms, e2e_ms, kernel_ms = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_envs = N * world
+    value = total_envs * K / (total_ms * 1e-3)
+    peak, peak_src = peaks()
+    achieved = ALGO_BYTES_PER_ENV_STEP * N / (kernel_ms * 1e-3) / 1e9  # per-GPU, dominant kernel = step_kernel
+    out = {
+        "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload, "envs_per_gpu": N, "sim": "dt 1/60 x controlFreqInv 2 x substeps 2", "obs": 461,
+                   "l2": "flushed (256 MiB memset) between timed steps; per-step CUDA events summed",
+                   "value_hot_l2_back_to_back": total_envs * K / (hot_ms * 1e-3), "wall_s_timed_loop": wall,
+                   "target_env_steps_per_s_1gpu": 4.0e6},
+        "clocks": clocks,
+        "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": N * task.num_actions * 4,
+                "d2h_bytes_per_step": N * 4 + N * 8,
+                "api": "VecTaskPythonWrapper.step/reset, pinned host actions in, reward+reset out, host sync every step"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "step_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "peak_source": peak_src,
+                     "note": "latency / FP32-issue bound along the 9-level kinematic chain, not HBM bound (DESIGN.md 5)"},
+    }
+    if not args.no_cpu_baseline:
+        from oracle import physics_ref
+        physics_ref.build()
+        v, _ = cpu_reference_arm(model, flat, args.cpu_sample_envs, 24, 2)
+        out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                               "sample": f"{args.cpu_sample_envs} of {N} envs x 24 steps (OpenMP physics restatement + numpy task logic)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

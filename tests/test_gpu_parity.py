@@ -103,14 +103,41 @@ def test_physics_f32_config1_drop(model, small_lib):
     assert worst_qd < 1e-3
 
 
+def settled_contact_states(task, model, n, seed, settle_steps=25):
+    """physically reachable contact states: drop random poses from ~1.4 m and let the float64 restatement run
+    `settle_steps` control steps, so bodies rest on / slide over the ground with natural penetrations."""
+    from oracle import physics_ref
+    rng = np.random.default_rng(seed)
+    root, q, qd, tar, ext = phys_states(model, n, seed, False)
+    root[:, 2] = rng.uniform(1.1, 1.5, n)
+    root[:, 7:13] *= 0.3
+    qd *= 0.3
+    physics_ref.control_step(task._model_struct, task._verts, task._cfg_struct, root, q, qd, tar, None, n_steps=settle_steps)
+    return root, q, qd, tar, np.zeros_like(ext)
+
+
 def test_physics_f32_random_one_step(model, small_lib):
+    """float32 kernel vs float64 restatement, one control step from 256 random states:
+    (a) free flight (smooth dynamics): every env within 1e-5 / 1e-3;
+    (b) natural ground contact: the model is non-smooth (a hull vertex is in or out, friction regularisation),
+        so a small fraction of envs may flip a vertex; the bulk must agree to 1e-4 on q."""
     task = make_task(4, small_lib)
-    st = phys_states(model, 256, 5, True)
+    st = phys_states(model, 256, 6, False)
     k = run_kernel_physics(task, *st, torch.float32, 1)
     o = run_oracle_physics(task, *st, 1)
-    assert np.abs(k[1] - o[1]).max() < 1e-4 and np.abs(k[0] - o[0]).max() < 1e-4
-    assert np.abs(k[2] - o[2]).max() < 2e-3
-    assert np.abs(k[3] - o[3]).max() < 2e-3
+    assert np.abs(k[1] - o[1]).max() < 1e-5 and np.abs(k[0] - o[0]).max() < 1e-5
+    assert np.abs(k[2] - o[2]).max() < 1e-3
+    st = settled_contact_states(task, model, 256, 5)
+    k = run_kernel_physics(task, *st, torch.float32, 1)
+    o = run_oracle_physics(task, *st, 1)
+    eq = np.maximum(np.abs(k[1] - o[1]).max(axis=1), np.abs(k[0] - o[0]).max(axis=1))
+    ev = np.abs(k[2] - o[2]).max(axis=1)
+    print(f"contact states: |dq| median {np.median(eq):.2e} p95 {np.quantile(eq, 0.95):.2e} max {eq.max():.2e}; "
+          f"|dqd| median {np.median(ev):.2e} p95 {np.quantile(ev, 0.95):.2e} max {ev.max():.2e}; "
+          f"contact force max {np.abs(o[4]).max():.0f} N")
+    assert np.abs(o[4]).max() > 50.0
+    assert eq.max() < 1e-4
+    assert np.quantile(ev, 0.95) < 5e-3
 
 
 def test_motion_state_golden():
@@ -155,6 +182,16 @@ def snapshot(task):
                 pd=g(task._pd_target_dof_pos), acts=g(task.actions), cf=g(task._contact_forces))
 
 
+def close_expmap(a, b, atol=1e-5):
+    """exp-map joint coordinates from the reference's float32 quat_to_exp_map (torch_utils.py:82-120): for joint
+    angles below ~1e-3 rad, sin_theta = sqrt(1 - w*w) is quantised to {0, 3.4e-4, ...} and the result jumps between
+    0 and ~1e-3 on a 1-ulp change of w, so such entries (|value| < 2e-3) are only held to 2e-3; the rest to 1e-5."""
+    tiny = (np.abs(a) < 2e-3) & (np.abs(b) < 2e-3)
+    np.testing.assert_allclose(a[~tiny], b[~tiny], rtol=0, atol=atol)
+    np.testing.assert_allclose(a[tiny], b[tiny], rtol=0, atol=2e-3)
+    assert (np.abs(a - b) > atol).mean() < 0.01
+
+
 def test_fused_step_vs_oracle(model, small_lib):
     """reset + 12 fused steps on 64 envs vs (numpy task oracle + float64 physics oracle), re-synchronised to
     the GPU state every step so that each step's arithmetic is checked in isolation."""
@@ -172,7 +209,7 @@ def test_fused_step_vs_oracle(model, small_lib):
     ms = R.get_motion_state(ml, mids, t0)
     np.testing.assert_allclose(s["root"][:, 0:3], ms[0], atol=1e-5)
     np.testing.assert_allclose(s["root"][:, 3:7], ms[1], atol=1e-5)
-    np.testing.assert_allclose(s["dofs"][..., 0], ms[2], atol=1e-5)
+    close_expmap(s["dofs"][..., 0], ms[2])
     np.testing.assert_allclose(s["root"][:, 7:10], ms[3], atol=1e-5)
     np.testing.assert_allclose(s["dofs"][..., 1], ms[5], atol=1e-5)
     np.testing.assert_allclose(s["rbs"][..., 0:3], ms[7], atol=1e-5)
@@ -184,7 +221,7 @@ def test_fused_step_vs_oracle(model, small_lib):
     orc = R.ImTaskOracle(ml, mids, s["times"], s["prog"], s["reset"], s["term"], np.float32(2) * np.float32(1.0 / 60.0), 10,
                          task._termination_heights.cpu().numpy(), task._contact_body_ids.cpu().numpy(),
                          np.ones(24, np.float32), ml["motion_bodies"][mids])
-    np.testing.assert_allclose(s["t_dof"], orc.t_dof_pos, atol=1e-5)
+    close_expmap(s["t_dof"], orc.t_dof_pos)
     np.testing.assert_allclose(s["t_rbp"], orc.t_rb_pos, atol=1e-5)
     n_reset_seen = 0
     for step in range(12):
@@ -215,7 +252,7 @@ def test_fused_step_vs_oracle(model, small_lib):
         assert np.array_equal(s["reset"], orc.reset_buf) and np.array_equal(s["term"], orc.terminate_buf)
         assert np.array_equal(s["prog"], orc.progress)
         np.testing.assert_allclose(s["times"], orc.ref_times, atol=1e-6)
-        np.testing.assert_allclose(s["t_dof"], orc.t_dof_pos, atol=1e-5)
+        close_expmap(s["t_dof"], orc.t_dof_pos)
         np.testing.assert_allclose(s["t_dofv"], orc.t_dof_vel, atol=1e-5)
         np.testing.assert_allclose(s["t_rbp"], orc.t_rb_pos, atol=1e-5)
         np.testing.assert_allclose(s["t_rbr"], orc.t_rb_rot, atol=1e-5)

@@ -611,7 +611,8 @@ __device__ __forceinline__ void ref_tan_norm(const float* q, float* o) {  // qua
 }
 __device__ __forceinline__ float ref_normalize_angle(float x) { return atan2f(sinf(x), cosf(x)); }
 __device__ __forceinline__ void ref_quat_to_angle_axis(const float* q, float& angle, float* axis) {  // :82-102
-  float sin_theta = sqrtf(1.0f - q[3] * q[3]);
+  // 1 - w*w cancels for small angles: keep torch's unfused rounding (no fma contraction)
+  float sin_theta = sqrtf(__fsub_rn(1.0f, __fmul_rn(q[3], q[3])));
   angle = ref_normalize_angle(2.0f * acosf(q[3]));
   bool mask = fabsf(sin_theta) > 1e-5f;
   if (mask) { axis[0] = q[0] / sin_theta; axis[1] = q[1] / sin_theta; axis[2] = q[2] / sin_theta; }
@@ -634,7 +635,7 @@ __device__ __forceinline__ void ref_slerp(const float* q0, const float* q1in, fl
   float q1[4] = {sg * q1in[0], sg * q1in[1], sg * q1in[2], sg * q1in[3]};
   c = fabsf(c);
   float half = acosf(c);
-  float sh = sqrtf(1.0f - c * c);
+  float sh = sqrtf(__fsub_rn(1.0f, __fmul_rn(c, c)));  // unfused like torch (cancellation near c = 1)
   float ra = sinf((1.f - t) * half) / sh, rb = sinf(t * half) / sh;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
