@@ -23,10 +23,18 @@
 #include "../../include/b200env.h"
 
 #define FULL 0xffffffffu
-#define WARPS_PER_CTA 4
+#ifndef WARPS_PER_CTA
+#define WARPS_PER_CTA 8  // A/B on B200 (profiles/r1_notes.md): 8 warps x 2 CTAs/SM, barrier per substep
+#endif
+#ifndef STEP_SYNC
+#define STEP_SYNC 1  // 1: CTA barrier at every substep boundary keeps the warps of a CTA on the same code (I-cache sharing)
+#endif
 #define SCRATCH_FLOATS 320
 #define MAX_CHILD 4
 #define MAX_LEVELS 16
+#ifndef STEP_MIN_CTAS
+#define STEP_MIN_CTAS 2
+#endif
 
 // ------------------------------------------------------------------------------------------
 // device-side constant block: header | tree tables | hull vertices   (all 16-byte multiples)
@@ -53,6 +61,9 @@ struct b200env {
   void* d_blob;
   size_t blob_bytes;
   b200_cfg_t* d_cfg;
+  unsigned long long* d_ticket;
+  unsigned long long ticket_base;
+  int step_grid;
   int64_t launches;
 };
 
@@ -75,6 +86,13 @@ template <typename T> __device__ __forceinline__ T warp_sum(T v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
+// fast reciprocal / rsqrt for the float path (MUFU, ~2 ulp); exact for the double (test) path
+__device__ __forceinline__ float rcp_(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
+__device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float sqrt_(float x) { return x * rsqrtf(fmaxf(x, 1e-37f)); }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 template <typename T> __device__ __forceinline__ void cross3(const T* a, const T* b, T* o) {
   T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   o[0] = x; o[1] = y; o[2] = z;
@@ -87,7 +105,7 @@ template <typename T> __device__ __forceinline__ void qmul(const T* a, const T* 
   o[3] = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
 }
 template <typename T> __device__ __forceinline__ void qnormalize(T* q) {
-  T n = T(1) / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  T n = rsqrt_(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
 }
 // rotate v by unit quaternion q:  v + 2 w (qv x v) + 2 qv x (qv x v)
@@ -125,13 +143,23 @@ template <typename T> __device__ __forceinline__ void qexp(const T* v, T* q) {
   if (a < T(1e-6)) s = T(0.5) - a2 / T(48); else s = sin(T(0.5) * a) / a;
   q[0] = s * v[0]; q[1] = s * v[1]; q[2] = s * v[2]; q[3] = cos(T(0.5) * a);
 }
+// exponential for the per-substep increments (|v| = h*|omega| <= h*max_ang_vel < 1 rad): even-power series,
+// truncation error < 2e-9 for |v| <= 2; the double path keeps sin/cos
+__device__ __forceinline__ void qexp_small(const float* v, float* q) {
+  const float a2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  if (a2 > 4.0f) { qexp(v, q); return; }
+  const float s = 0.5f + a2 * (-1.0f / 48.0f + a2 * (1.0f / 3840.0f + a2 * (-1.0f / 645120.0f + a2 * (1.0f / 185794560.0f))));
+  const float c = 1.0f + a2 * (-0.125f + a2 * (1.0f / 384.0f + a2 * (-1.0f / 46080.0f + a2 * (1.0f / 10321920.0f + a2 * (-1.0f / 3715891200.0f)))));
+  q[0] = s * v[0]; q[1] = s * v[1]; q[2] = s * v[2]; q[3] = c;
+}
+__device__ __forceinline__ void qexp_small(const double* v, double* q) { qexp(v, q); }
 // quaternion -> rotation vector, angle in [0, pi]
 template <typename T> __device__ __forceinline__ void qlog(const T* qi, T* v) {
   T sg = qi[3] < T(0) ? T(-1) : T(1);
   T x = sg * qi[0], y = sg * qi[1], z = sg * qi[2], w = sg * qi[3];
   T s2 = x * x + y * y + z * z;
-  T s = sqrt(s2), f;
-  if (s < T(1e-6)) f = T(2) + s2 / T(3); else f = T(2) * atan2(s, w) / s;
+  T s = sqrt_(s2), f;
+  if (s < T(1e-6)) f = T(2) + s2 * T(1.0 / 3.0); else f = T(2) * atan2(s, w) * rcp_(s);
   v[0] = f * x; v[1] = f * y; v[2] = f * z;
 }
 // symmetric 3x3 stored as [xx, yy, zz, xy, xz, yz]
@@ -146,7 +174,7 @@ template <typename T> __device__ __forceinline__ void sym_inv(const T* S, T* O) 
   T c01 = S[5] * S[4] - S[3] * S[2];
   T c02 = S[3] * S[5] - S[1] * S[4];
   T det = S[0] * c00 + S[3] * c01 + S[4] * c02;
-  T id = T(1) / det;
+  T id = rcp_(det);
   O[0] = c00 * id;
   O[1] = (S[0] * S[2] - S[4] * S[4]) * id;
   O[2] = (S[0] * S[1] - S[3] * S[3]) * id;
@@ -302,8 +330,8 @@ __device__ __forceinline__ void substep(const DevBlob& B, const float* __restric
         T uz = L.v[2] + L.w[0] * ry - L.w[1] * rx;
         T fn0 = c.kn * pen - c.cn * uz;
         if (!(fn0 > T(0))) continue;
-        T ut = sqrt(ux * ux + uy * uy);
-        T ct = c.mu * fn0 / (ut > c.vs ? ut : c.vs);
+        T ut = sqrt_(ux * ux + uy * uy);
+        T ct = c.mu * fn0 * rcp_(ut > c.vs ? ut : c.vs);
         T hct = c.h * ct;
         // Jn = [(ry, -rx, 0); (0,0,1)], Jx = [(0, rz, -ry); (1,0,0)], Jy = [(-rz, 0, rx); (0,1,0)]
         A[0] += kimp * ry * ry + hct * rz * rz;
@@ -516,8 +544,8 @@ __device__ __forceinline__ void substep(const DevBlob& B, const float* __restric
       mtv3(R, gam, wd);
 #pragma unroll
       for (int k = 0; k < 3; k++) L.wt[k] = (L.wt[k] + c.h * wd[k]) * c.damp;
-      T nn = sqrt(L.wt[0] * L.wt[0] + L.wt[1] * L.wt[1] + L.wt[2] * L.wt[2]);
-      if (nn > c.wmax) { T sc = c.wmax / nn; L.wt[0] *= sc; L.wt[1] *= sc; L.wt[2] *= sc; }
+      T n2 = L.wt[0] * L.wt[0] + L.wt[1] * L.wt[1] + L.wt[2] * L.wt[2];
+      if (n2 > c.wmax * c.wmax) { T sc = c.wmax * rsqrt_(n2); L.wt[0] *= sc; L.wt[1] *= sc; L.wt[2] *= sc; }
     }
   }
 
@@ -525,19 +553,19 @@ __device__ __forceinline__ void substep(const DevBlob& B, const float* __restric
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 3; k++) { L.w[k] = (L.w[k] + c.h * acc[k]) * c.damp; L.v[k] += c.h * acc[3 + k]; }
-    T nn = sqrt(L.w[0] * L.w[0] + L.w[1] * L.w[1] + L.w[2] * L.w[2]);
-    if (nn > c.wmax) { T sc = c.wmax / nn; L.w[0] *= sc; L.w[1] *= sc; L.w[2] *= sc; }
+    T n2 = L.w[0] * L.w[0] + L.w[1] * L.w[1] + L.w[2] * L.w[2];
+    if (n2 > c.wmax * c.wmax) { T sc = c.wmax * rsqrt_(n2); L.w[0] *= sc; L.w[1] *= sc; L.w[2] *= sc; }
     T hv[3] = {c.h * L.w[0], c.h * L.w[1], c.h * L.w[2]}, dq[4], qn[4];
 #pragma unroll
     for (int k = 0; k < 3; k++) L.p[k] += c.h * L.v[k];
-    qexp(hv, dq);
+    qexp_small(hv, dq);
     qmul(dq, L.Q, qn);
     qnormalize(qn);
 #pragma unroll
     for (int k = 0; k < 4; k++) L.Q[k] = qn[k];
   } else if (lc.dyn) {
     T hv[3] = {c.h * L.wt[0], c.h * L.wt[1], c.h * L.wt[2]}, dq[4], qn[4];
-    qexp(hv, dq);
+    qexp_small(hv, dq);
     qmul(L.qj, dq, qn);
     qnormalize(qn);
 #pragma unroll
@@ -548,9 +576,13 @@ __device__ __forceinline__ void substep(const DevBlob& B, const float* __restric
 // control_freq_inv sim steps x substeps; external wrench only during the first sim step
 template <typename T>
 __device__ __forceinline__ void control_step(const DevBlob& B, const float* verts, const PhysCfg<T>& c, const LaneConst& lc,
-                                             int lane, Lane<T>& L, const T* pdtar, const T* extF, const T* extT, T* cf) {
+                                             int lane, Lane<T>& L, const T* pdtar, const T* extF, const T* extT, T* cf,
+                                             bool cta_sync = false) {
   for (int s = 0; s < c.cfi; s++)
-    for (int k = 0; k < c.substeps; k++) substep<T>(B, verts, c, lc, lane, L, pdtar, s == 0, extF, extT, cf);
+    for (int k = 0; k < c.substeps; k++) {
+      if (cta_sync) __syncthreads();
+      substep<T>(B, verts, c, lc, lane, L, pdtar, s == 0, extF, extT, cf);
+    }
   T dummy[3], dz[6];
   fk_pass<T, false>(B.m, lc, lane, L, dummy, dz);
 }
@@ -772,9 +804,12 @@ __device__ __forceinline__ void store_obs_raw(float* obs, int nb, int nd, int sh
 
 // ------------------------------------------------------------------------------------------
 // fused env step:  pre-physics -> substeps -> MoCap target -> obs -> reward -> reset
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+// Persistent: the grid is sized to the resident CTA slots; each warp pulls env indices from a global ticket
+// counter (monotonic across launches: ticket - base = env index) so the tail is balanced per env, not per CTA.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, STEP_MIN_CTAS)
 step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
-            b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs) {
+            b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs, unsigned long long* __restrict__ ticket,
+            unsigned long long base) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t mbar;
   load_blob(smem, gblob, blob_bytes, &mbar);
@@ -785,12 +820,21 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* scr = scratch_all + warp * SCRATCH_FLOATS;
   const b200_cfg_t& cfg = *gcfg;
-  const int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
-  if (e >= num_envs) return;
-
   const LaneConst lc = lane_const(M, lane);
-  const int nb = M.nb, nd = M.nd, na = nd + 6;
+  const int nd = M.nd, na = nd + 6;
   const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
+
+ __shared__ unsigned long long s_tk;
+ for (;;) {
+  // one ticket per CTA = a batch of WARPS_PER_CTA consecutive envs (CTA-uniform control flow -> barriers are legal)
+  __syncthreads();
+  if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)WARPS_PER_CTA) - base;
+  __syncthreads();
+  const int64_t e0 = (int64_t)s_tk;
+  if (e0 >= num_envs) break;
+  const bool full_batch = e0 + WARPS_PER_CTA <= num_envs;
+  const int64_t e = e0 + warp;
+  if (!full_batch && e >= num_envs) continue;  // ragged last batch: no CTA barriers below (full_batch is CTA-uniform)
 
   // ---- load state rows (coalesced) into the warp's scratch
   const float* rs = bf.root_states + e * bf.actors_per_env * 13;
@@ -860,7 +904,7 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
 
   // ---- physics
   float cf[3];
-  control_step<float>(B, verts, pc, lc, lane, L, pdtar, extF, extT, cf);
+  control_step<float>(B, verts, pc, lc, lane, L, pdtar, extF, extT, cf, STEP_SYNC && full_batch);
 
   // ---- write back the simulation state (what gym.refresh_* exposes)
   float dq[3] = {0.f, 0.f, 0.f};
@@ -954,6 +998,7 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
     bf.reset_buf[e] = reset;
     bf.terminate_buf[e] = terminated;
   }
+ }  // ticket loop
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1253,6 +1298,8 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   CUDA_OK(cudaMemcpy((char*)h->d_blob + sizeof(DevBlob), verts, vbytes, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&h->d_cfg, sizeof(b200_cfg_t)));
   CUDA_OK(cudaMemcpy(h->d_cfg, cfg, sizeof(b200_cfg_t), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMalloc(&h->d_ticket, sizeof(unsigned long long)));
+  CUDA_OK(cudaMemset(h->d_ticket, 0, sizeof(unsigned long long)));
   *out = h;
   return 0;
 }
@@ -1262,6 +1309,7 @@ int b200env_destroy(b200env_handle h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_blob);
   cudaFree(h->d_cfg);
+  cudaFree(h->d_ticket);
   delete h;
   return 0;
 }
@@ -1294,22 +1342,29 @@ int b200env_set_motion_lib(b200env_handle h, const b200_motion_lib_t* ml) {
   return 0;
 }
 
+static int need_ctas(const b200env* h) { return (h->num_envs + WARPS_PER_CTA - 1) / WARPS_PER_CTA; }
 static size_t step_smem(const b200env* h) { return ((h->blob_bytes + 15) & ~(size_t)15) + WARPS_PER_CTA * SCRATCH_FLOATS * sizeof(float); }
 
 int b200env_step(b200env_handle h, const float* actions, void* stream) {
   if (!h || !actions) return fail(-1, "b200env_step: null argument%s");
   if (!h->bound || !h->has_ml) return fail(-4, "b200env_step: bind buffers and a motion lib first%s");
   cudaSetDevice(h->device);
-  const int grid = (h->num_envs + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   const size_t smem = step_smem(h);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (h->step_grid == 0) {
     CUDA_OK(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    int per_sm = 0, sms = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel, WARPS_PER_CTA * 32, smem));
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const int need = need_ctas(h);
+    h->step_grid = per_sm * sms < need ? per_sm * sms : need;
+    if (h->step_grid < 1) return fail(-5, "b200env_step: step_kernel does not fit on this device%s");
   }
-  step_kernel<<<grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg,
-                                                                        h->bufs, h->ml, actions, h->num_envs);
+  step_kernel<<<h->step_grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes,
+                                                                                 h->d_cfg, h->bufs, h->ml, actions, h->num_envs,
+                                                                                 h->d_ticket, h->ticket_base);
   CUDA_OK(cudaGetLastError());
+  // every CTA takes one final (failing) batch ticket: the next launch's tickets start after them
+  h->ticket_base += (unsigned long long)(need_ctas(h) + h->step_grid) * WARPS_PER_CTA;
   h->launches++;
   return 0;
 }
