@@ -1,0 +1,70 @@
+/* b200env_v2p.h - C ABI of the vid2player rows of the rollout hot path.
+ * Stateless entry points: plain device pointers + sizes, asynchronous on `stream`, no allocation, no host sync.
+ * Bool tensors are 1 byte per element (torch.bool storage).  Paths below are relative to /root/reference/vid2player. */
+#ifndef B200ENV_V2P_H
+#define B200ENV_V2P_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* b200v2p_last_error(void);
+
+/* replaces HumanoidSMPLIMMVAE._smpl_to_sim + _forward_kinematics (env/tasks/humanoid_smpl_im_mvae.py:897-946, utils/hybrik.py:597-652):
+ * joint_rotmat [n,24,3,3] and rest [24,3] in SMPL joint order; outputs in MuJoCo body order (smpl_2_mujoco);
+ * prev_* NULL -> zero velocities. */
+int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rotmat, const float* rest, const int32_t* parents,
+                        const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
+                        float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, void* stream);
+
+/* replaces apply_external_force_to_ball (env/tasks/humanoid_smpl_im_mvae.py:711-739): drag + Magnus lift, bounce flag */
+int b200v2p_ball_aero(int32_t n, const float* ball_states, int32_t stride, uint8_t* has_bounce, uint8_t* has_bounce_now, float* bounce_pos,
+                      float* force, int32_t substeps, float spin_scale, void* stream);
+
+/* replaces _reset_balls + TennisBallGeneratorOffline.generate (:503-524, utils/tennis_ball.py:435-456): pool [P,307] */
+int b200v2p_ball_reset(int32_t n, const int64_t* env_ids, const int64_t* pool_index, const float* pool, float* ball_states, int32_t stride,
+                       float* ball_pos, float* ball_vel, uint8_t* has_bounce, float* bounce_pos, uint8_t* has_contact, float* traj,
+                       void* stream);
+
+/* replaces _update_state_from_sim (:799-860), substeps > 2 contact detector */
+typedef struct b200v2p_state {
+  int32_t n, bodies_per_env, ball_stride, root_stride, racket_body, wrist_body;
+  float grip_normal[3];
+  const float* rigid_body_state; /* [n, bodies_per_env, 13] */
+  const float* root_states;      /* humanoid root row per env, stride root_stride floats */
+  const float* ball_states;      /* ball root row per env, stride ball_stride floats */
+  uint8_t *has_contact, *has_contact_now;
+  float *root_pos, *root_vel, *racket_pos, *racket_vel, *racket_normal, *ball_pos, *ball_vel, *ball_vspin;
+} b200v2p_state_t;
+int b200v2p_update_state(const b200v2p_state_t* s, void* stream);
+
+/* replaces PhysicsMVAEController.post_physics_step's device work (env/tasks/physics_mvae_controller.py:441-452):
+ * _update_state (:271-314, incl. TennisBallOutEstimator.estimate utils/tennis_ball_out_estimator.py:164-205),
+ * _compute_reward (:368-406, jit :493-602), _compute_observations (:316-360), _compute_reset (:408-436). */
+typedef struct b200v2p_ctrl {
+  int32_t n, bodies_per_env, ball_stride, racket_body, num_obs, obs_traj_len, use_target, reward_type, early_termination,
+      max_episode_length, est_nx, est_ny;
+  float scale_pos, scale_phase, scale_bounce_pos, scale_bounce_time, w_pos, w_ball_pos;
+  float court_min[2], court_max[2];
+  float est_params[15]; /* VEL_X, VEL_Y, VSPIN, TRAJ_X, TRAJ_Y ranges (lo, hi, step) */
+  const float* rigid_body_state;
+  const float* ball_states;
+  const float *root_pos, *root_vel, *racket_pos, *racket_normal, *ball_pos;
+  const uint8_t *has_contact, *has_contact_now, *has_bounce, *has_bounce_now;
+  const float* bounce_pos;
+  const float* ball_traj; /* [n,100,3] */
+  const float* target_bounce_pos;
+  const float* phase;
+  const int64_t *swing_type, *swing_type_cycle, *tar_action, *tar_time, *tar_time_total, *progress_buf;
+  const float *est_x, *est_y; /* estimator tables [rows, est_nx], [rows, est_ny, 2]; NULL = no estimator (dual mode) */
+  uint8_t *bounce_in, *est_bounce_in, *reset_reaction, *reset_recovery;
+  float *est_bounce_pos, *est_bounce_time, *est_max_height, *distance;
+  float *obs_buf, *rew_buf, *sub_rewards; /* sub_rewards [n,2] */
+  int64_t *reset_buf, *terminate_buf;
+} b200v2p_ctrl_t;
+int b200v2p_controller_post(const b200v2p_ctrl_t* c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

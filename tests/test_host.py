@@ -14,9 +14,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     from vid2player3d_b200 import build, native
     lib = build.build()
-    hdr = open(os.path.join(ROOT, "include", "b200env.h")).read()
-    declared = sorted(set(re.findall(r"\b(b200env_[a-z_]+)\s*\(", hdr)))
-    assert declared == sorted(native.SYMBOLS)
+    from vid2player3d_b200 import native_v2p
+    hdr = open(os.path.join(ROOT, "include", "b200env.h")).read() + open(os.path.join(ROOT, "include", "b200env_v2p.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200(?:env|v2p)_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared == sorted(native.SYMBOLS + native_v2p.SYMBOLS)
     L = C.CDLL(lib)  # loads without a GPU; no compute call is made here
     for name in declared:
         assert hasattr(L, name), name
@@ -35,6 +36,12 @@ def test_struct_layouts_match_header(tmp_path):
     want = [C.sizeof(abi.Model), C.sizeof(abi.Cfg), C.sizeof(abi.MotionLibView), C.sizeof(abi.Buffers), abi.Model.kp.offset,
             abi.Cfg.key_body.offset]
     assert got == want
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s/include/b200env_v2p.h"\n'
+                   'int main(){printf("%%zu %%zu %%zu %%zu\\n",sizeof(b200v2p_state_t),sizeof(b200v2p_ctrl_t),'
+                   'offsetof(b200v2p_state_t,root_pos),offsetof(b200v2p_ctrl_t,est_x));}' % ROOT)
+    subprocess.check_call(["gcc", str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [C.sizeof(abi.V2PState), C.sizeof(abi.V2PCtrl), abi.V2PState.root_pos.offset, abi.V2PCtrl.est_x.offset]
 
 
 def test_no_gpu_means_loud_failure():

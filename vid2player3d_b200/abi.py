@@ -143,3 +143,38 @@ def make_cfg(model, *, sim_dt=1.0 / 60.0, substeps=2, control_freq_inv=2, gravit
     c.shape_dim = shape_dim
     c.ground_tolerance = ground_tolerance
     return c
+
+
+# ---------------------------------------------------------------- include/b200env_v2p.h
+class V2PState(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("bodies_per_env", C.c_int32), ("ball_stride", C.c_int32), ("root_stride", C.c_int32),
+        ("racket_body", C.c_int32), ("wrist_body", C.c_int32), ("grip_normal", C.c_float * 3),
+        ("rigid_body_state", C.c_void_p), ("root_states", C.c_void_p), ("ball_states", C.c_void_p),
+        ("has_contact", C.c_void_p), ("has_contact_now", C.c_void_p),
+        ("root_pos", C.c_void_p), ("root_vel", C.c_void_p), ("racket_pos", C.c_void_p), ("racket_vel", C.c_void_p),
+        ("racket_normal", C.c_void_p), ("ball_pos", C.c_void_p), ("ball_vel", C.c_void_p), ("ball_vspin", C.c_void_p),
+    ]
+
+
+class V2PCtrl(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("bodies_per_env", C.c_int32), ("ball_stride", C.c_int32), ("racket_body", C.c_int32),
+        ("num_obs", C.c_int32), ("obs_traj_len", C.c_int32), ("use_target", C.c_int32), ("reward_type", C.c_int32),
+        ("early_termination", C.c_int32), ("max_episode_length", C.c_int32), ("est_nx", C.c_int32), ("est_ny", C.c_int32),
+        ("scale_pos", C.c_float), ("scale_phase", C.c_float), ("scale_bounce_pos", C.c_float), ("scale_bounce_time", C.c_float),
+        ("w_pos", C.c_float), ("w_ball_pos", C.c_float),
+        ("court_min", C.c_float * 2), ("court_max", C.c_float * 2), ("est_params", C.c_float * 15),
+        ("rigid_body_state", C.c_void_p), ("ball_states", C.c_void_p),
+        ("root_pos", C.c_void_p), ("root_vel", C.c_void_p), ("racket_pos", C.c_void_p), ("racket_normal", C.c_void_p),
+        ("ball_pos", C.c_void_p),
+        ("has_contact", C.c_void_p), ("has_contact_now", C.c_void_p), ("has_bounce", C.c_void_p), ("has_bounce_now", C.c_void_p),
+        ("bounce_pos", C.c_void_p), ("ball_traj", C.c_void_p), ("target_bounce_pos", C.c_void_p), ("phase", C.c_void_p),
+        ("swing_type", C.c_void_p), ("swing_type_cycle", C.c_void_p), ("tar_action", C.c_void_p), ("tar_time", C.c_void_p),
+        ("tar_time_total", C.c_void_p), ("progress_buf", C.c_void_p),
+        ("est_x", C.c_void_p), ("est_y", C.c_void_p),
+        ("bounce_in", C.c_void_p), ("est_bounce_in", C.c_void_p), ("reset_reaction", C.c_void_p), ("reset_recovery", C.c_void_p),
+        ("est_bounce_pos", C.c_void_p), ("est_bounce_time", C.c_void_p), ("est_max_height", C.c_void_p), ("distance", C.c_void_p),
+        ("obs_buf", C.c_void_p), ("rew_buf", C.c_void_p), ("sub_rewards", C.c_void_p),
+        ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p),
+    ]

@@ -1,0 +1,458 @@
+// b200env_v2p.cu - kernels + C ABI for the vid2player rows of the hot path:
+// SMPL-FK targets, ball aerodynamics / reset, state-from-sim, and the high-level env's
+// bounce/estimator bookkeeping + reward + observation + reset FSM fused into one launch.
+// Reference (paths relative to /root/reference/vid2player):
+//   _smpl_to_sim / _forward_kinematics        env/tasks/humanoid_smpl_im_mvae.py:897-946, utils/hybrik.py:597-652
+//   rotation_matrix_to_quaternion/_angle_axis utils/konia_transform.py:348-438, 558-655
+//   apply_external_force_to_ball              env/tasks/humanoid_smpl_im_mvae.py:711-739 (+ utils/tennis_ball.py:15-37)
+//   _reset_balls + offline pool               env/tasks/humanoid_smpl_im_mvae.py:503-524, utils/tennis_ball.py:422-456
+//   _update_state_from_sim                    env/tasks/humanoid_smpl_im_mvae.py:799-860
+//   controller post_physics_step              env/tasks/physics_mvae_controller.py:271-314,333-360,368-436,481-602
+//   TennisBallOutEstimator.estimate           utils/tennis_ball_out_estimator.py:126-205
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/b200env_v2p.h"
+
+#define FULL 0xffffffffu
+#define V2P_WARPS 4
+
+static thread_local char g_verr[256] = "";
+static int vfail(int code, const char* msg) {
+  snprintf(g_verr, sizeof(g_verr), "%s", msg);
+  return code;
+}
+#define V_CUDA_OK()                                                        \
+  do {                                                                     \
+    cudaError_t _e = cudaGetLastError();                                   \
+    if (_e != cudaSuccess) return vfail(-10, cudaGetErrorString(_e));      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ konia conversions
+__device__ __forceinline__ float safe_div(float num, float den) {  // safe_zero_division, eps 1e-6
+  if (fabsf(den) < 1e-6f) den += 1e-6f;
+  return num / den;
+}
+// rotation matrix (row-major) -> quaternion wxyz  (konia_transform.py:348-438)
+__device__ __forceinline__ void rotmat_to_quat_wxyz(const float* m, float* q) {
+  const float m00 = m[0], m01 = m[1], m02 = m[2], m10 = m[3], m11 = m[4], m12 = m[5], m20 = m[6], m21 = m[7], m22 = m[8];
+  const float trace = m00 + m11 + m22;
+  if (trace > 0.0f) {
+    float sq = sqrtf(fmaxf(trace + 1.0f, 1e-6f)) * 2.0f;
+    q[0] = 0.25f * sq; q[1] = safe_div(m21 - m12, sq); q[2] = safe_div(m02 - m20, sq); q[3] = safe_div(m10 - m01, sq);
+  } else if ((m00 > m11) && (m00 > m22)) {
+    float sq = sqrtf(fmaxf(1.0f + m00 - m11 - m22, 1e-6f)) * 2.0f;
+    q[0] = safe_div(m21 - m12, sq); q[1] = 0.25f * sq; q[2] = safe_div(m01 + m10, sq); q[3] = safe_div(m02 + m20, sq);
+  } else if (m11 > m22) {
+    float sq = sqrtf(fmaxf(1.0f + m11 - m00 - m22, 1e-6f)) * 2.0f;
+    q[0] = safe_div(m02 - m20, sq); q[1] = safe_div(m01 + m10, sq); q[2] = 0.25f * sq; q[3] = safe_div(m12 + m21, sq);
+  } else {
+    float sq = sqrtf(fmaxf(1.0f + m22 - m00 - m11, 1e-6f)) * 2.0f;
+    q[0] = safe_div(m10 - m01, sq); q[1] = safe_div(m02 + m20, sq); q[2] = safe_div(m12 + m21, sq); q[3] = 0.25f * sq;
+  }
+}
+__device__ __forceinline__ float safe_atan2(float y, float x) {  // torch_safe_atan2 (:41-49)
+  if (fabsf(y) < 1e-6f && fabsf(x) < 1e-6f) y += 1e-6f;
+  return atan2f(y, x);
+}
+// quaternion wxyz -> rotation vector (konia_transform.py:558-628)
+__device__ __forceinline__ void quat_wxyz_to_angle_axis(const float* q, float* aa) {
+  const float c = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+  const float s2 = q1 * q1 + q2 * q2 + q3 * q3;
+  const float s = sqrtf(fmaxf(s2, 1e-6f));
+  const float two_theta = 2.0f * (c < 0.0f ? safe_atan2(-s, -c) : safe_atan2(s, c));
+  const float k = s2 > 0.0f ? safe_div(two_theta, s) : 2.0f;
+  aa[0] = q1 * k; aa[1] = q2 * k; aa[2] = q3 * k;
+}
+// quaternion (given in the converter's WXYZ slot order) -> rotation matrix (konia_transform.py:474-555)
+__device__ __forceinline__ void quat_wxyz_to_rotmat(const float* qi, float* m) {
+  const float n = fmaxf(sqrtf(qi[0] * qi[0] + qi[1] * qi[1] + qi[2] * qi[2] + qi[3] * qi[3]), 1e-12f);
+  const float w = qi[0] / n, x = qi[1] / n, y = qi[2] / n, z = qi[3] / n;
+  const float tx = 2.0f * x, ty = 2.0f * y, tz = 2.0f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  m[0] = 1.0f - (tyy + tzz); m[1] = txy - twz; m[2] = txz + twy;
+  m[3] = txy + twz; m[4] = 1.0f - (txx + tzz); m[5] = tyz - twx;
+  m[6] = txz - twy; m[7] = tyz + twx; m[8] = 1.0f - (txx + tyy);
+}
+__device__ __forceinline__ void qmul_xyzw(const float* a, const float* b, float* o) {
+  const float x1 = a[0], y1 = a[1], z1 = a[2], w1 = a[3], x2 = b[0], y2 = b[1], z2 = b[2], w2 = b[3];
+  o[0] = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
+  o[1] = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
+  o[2] = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
+  o[3] = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
+}
+
+// ------------------------------------------------------------------------------------------ a13: SMPL FK targets
+__global__ void __launch_bounds__(V2P_WARPS * 32)
+smpl_to_sim_kernel(int n, const float* __restrict__ root_pos, const float* __restrict__ rotmat, const float* __restrict__ rest,
+                   const int32_t* __restrict__ parents, const int32_t* __restrict__ smpl_2_mujoco, float dt,
+                   const float* __restrict__ prev_root_pos, const float* __restrict__ prev_rb_rot, float* root_rot, float* dof_pos,
+                   float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * V2P_WARPS + warp;
+  if (e >= n) return;
+  const bool act = lane < 24;
+  const int j = act ? lane : 0;
+  const int par = parents[j] < 0 ? 0 : parents[j];
+  int mj = 0;  // mujoco index of SMPL joint j (inverse of smpl_2_mujoco)
+  for (int k = 0; k < 24; k++)
+    if (smpl_2_mujoco[k] == j) mj = k;
+  float Rl[9], G[9], P[3], rel[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) Rl[k] = rotmat[(e * 24 + j) * 9 + k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) rel[k] = rest[j * 3 + k] - (j > 0 ? rest[par * 3 + k] : 0.0f);
+  // local angle-axis -> dof targets (root excluded), mujoco order
+  if (act && mj > 0) {
+    float q[4], aa[3];
+    rotmat_to_quat_wxyz(Rl, q);
+    quat_wxyz_to_angle_axis(q, aa);
+#pragma unroll
+    for (int k = 0; k < 3; k++) dof_pos[e * 69 + (mj - 1) * 3 + k] = aa[k];
+  }
+  // FK chain (hybrik.py:597-652): G_j = G_parent R_j ; P_j = G_parent rel_j + P_parent
+  bool done = (lane == 0);
+#pragma unroll
+  for (int k = 0; k < 9; k++) G[k] = Rl[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) P[k] = rel[k];
+  for (int it = 0; it < 9; it++) {
+    float pG[9], pP[3];
+#pragma unroll
+    for (int k = 0; k < 9; k++) pG[k] = __shfl_sync(FULL, G[k], par);
+#pragma unroll
+    for (int k = 0; k < 3; k++) pP[k] = __shfl_sync(FULL, P[k], par);
+    const bool pdone = __shfl_sync(FULL, (int)done, par) != 0;
+    if (act && !done && pdone) {
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) G[r * 3 + c] = pG[r * 3] * Rl[c] + pG[r * 3 + 1] * Rl[3 + c] + pG[r * 3 + 2] * Rl[6 + c];
+        P[r] = pG[r * 3] * rel[0] + pG[r * 3 + 1] * rel[1] + pG[r * 3 + 2] * rel[2] + pP[r];
+      }
+      done = true;
+    }
+  }
+  float qw[4], q[4];
+  rotmat_to_quat_wxyz(G, qw);
+  q[0] = qw[1]; q[1] = qw[2]; q[2] = qw[3]; q[3] = qw[0];
+  if (act) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) rb_pos[(e * 24 + mj) * 3 + k] = P[k] - (rest[k] - root_pos[e * 3 + k]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) rb_rot[(e * 24 + mj) * 4 + k] = q[k];
+    if (mj == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) root_rot[e * 4 + k] = q[k];
+    }
+    if (prev_root_pos && prev_rb_rot) {
+      // diff = quat_normalize(quat_mul(conj(prev), cur)) ; axis*angle/dt   (:909-919)
+      const float* pq = prev_rb_rot + (e * 24 + mj) * 4;
+      float cj[4] = {-pq[0], -pq[1], -pq[2], pq[3]}, d[4];
+      qmul_xyzw(cj, q, d);
+      const float sg = d[3] < 0.0f ? -1.0f : 1.0f;  // quat_pos
+#pragma unroll
+      for (int k = 0; k < 4; k++) d[k] *= sg;
+      const float nn = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]), 1e-9f);
+#pragma unroll
+      for (int k = 0; k < 4; k++) d[k] /= nn;
+      // quat_to_angle_axis (utils/torch_utils.py:82-102)
+      float st = sqrtf(__fsub_rn(1.0f, __fmul_rn(d[3], d[3])));
+      float ang = 2.0f * acosf(d[3]);
+      ang = atan2f(sinf(ang), cosf(ang));
+      float ax[3];
+      if (fabsf(st) > 1e-5f) { ax[0] = d[0] / st; ax[1] = d[1] / st; ax[2] = d[2] / st; }
+      else { ang = 0.0f; ax[0] = 0.0f; ax[1] = 0.0f; ax[2] = 1.0f; }
+      float dv[3] = {ax[0] * ang / dt, ax[1] * ang / dt, ax[2] * ang / dt};
+      if (mj == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          root_ang_vel[e * 3 + k] = dv[k] / dt;  // reference quirk: divided by dt twice (:917-919)
+          root_vel[e * 3 + k] = (root_pos[e * 3 + k] - prev_root_pos[e * 3 + k]) / dt;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) dof_vel[e * 69 + (mj - 1) * 3 + k] = dv[k];
+      }
+    } else {
+      if (mj == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { root_ang_vel[e * 3 + k] = 0.0f; root_vel[e * 3 + k] = 0.0f; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) dof_vel[e * 69 + (mj - 1) * 3 + k] = 0.0f;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ a10: ball aerodynamics
+#define BALL_R 0.032f
+#define BALL_KF 0.0019462794807519486f  // rho*pi*R^2/2, rho = 1.21 (tennis_ball.py:17-22)
+#define BALL_CD 0.55f
+__device__ __forceinline__ void ball_aero_force(const float* vel, const float* angvel, float spin_scale, float* force) {
+  float vs = sqrtf(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+  if (vs == 0.0f) vs += 1.0f;
+  const float vn[3] = {vel[0] / vs, vel[1] / vs, vel[2] / vs};
+  // vel_tan = vn x (0,0,-1)
+  const float vt[3] = {-vn[1], vn[0], 0.0f};
+  const float vspin = sqrtf(angvel[0] * angvel[0] + angvel[1] * angvel[1] + angvel[2] * angvel[2]) / 6.283185307179586f;
+  float cl = 1.0f / (2.0f + fabsf(vs / (vspin * spin_scale + 1e-6f)));
+  cl = cl * (vspin > 0.0f ? -1.0f : 1.0f);
+  // vel_tan x vn
+  const float cx = vt[1] * vn[2] - vt[2] * vn[1], cy = vt[2] * vn[0] - vt[0] * vn[2], cz = vt[0] * vn[1] - vt[1] * vn[0];
+  const float kd = -BALL_KF * BALL_CD * vs, kl = -BALL_KF * cl * vs * vs;
+  force[0] = kd * vel[0] + kl * cx;
+  force[1] = kd * vel[1] + kl * cy;
+  force[2] = kd * vel[2] + kl * cz;
+}
+__global__ void ball_aero_kernel(int n, const float* __restrict__ ball_states, int stride, uint8_t* has_bounce, uint8_t* has_bounce_now,
+                                 float* bounce_pos, float* force, int substeps, float spin_scale) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float* b = ball_states + e * stride;
+  float f[3];
+  ball_aero_force(b + 7, b + 10, spin_scale, f);
+  force[e * 3] = f[0]; force[e * 3 + 1] = f[1]; force[e * 3 + 2] = f[2];
+  const float thr = substeps > 2 ? BALL_R * 6.0f : BALL_R * 4.0f;
+  const bool now = !has_bounce[e] && (b[2] <= thr);
+  if (now) {
+    has_bounce_now[e] = 1; has_bounce[e] = 1;
+    bounce_pos[e * 3] = b[0]; bounce_pos[e * 3 + 1] = b[1]; bounce_pos[e * 3 + 2] = b[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ a17: ball reset from the pool
+__global__ void ball_reset_kernel(int n, const int64_t* __restrict__ env_ids, const int64_t* __restrict__ pool_index,
+                                  const float* __restrict__ pool, float* ball_states, int stride, float* ball_pos, float* ball_vel,
+                                  uint8_t* has_bounce, float* bounce_pos, uint8_t* has_contact, float* traj) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int64_t e = env_ids[i];
+  const float* row = pool + pool_index[i] * 307;
+  for (int k = threadIdx.x; k < 300; k += blockDim.x) traj[e * 300 + k] = row[7 + k];
+  if (threadIdx.x == 0) {
+    float* b = ball_states + e * stride;
+    const float v[3] = {row[3], row[4], row[5]};
+    // ang vel = vspin * 2pi * normalize(v x (0,0,-1))   (:508-509)
+    float c[3] = {-v[1], v[0], 0.0f};
+    const float nn = fmaxf(sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]), 1e-12f);
+    const float s = row[6] * 3.141592653589793f * 2.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { b[k] = row[k]; b[7 + k] = v[k]; b[10 + k] = s * (c[k] / nn); ball_pos[e * 3 + k] = row[k]; ball_vel[e * 3 + k] = v[k]; bounce_pos[e * 3 + k] = 0.0f; }
+    has_bounce[e] = 0; has_contact[e] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ a11 / a12: state from sim
+__global__ void update_state_kernel(b200v2p_state_t s) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= s.n) return;
+  const float* rb = s.rigid_body_state + e * s.bodies_per_env * 13;
+  const float* ball = s.ball_states + e * s.ball_stride;
+  // velocity-jump contact detector (substeps > 2): uses the ball velocity of the previous control step (:800-808)
+  const bool now = !s.has_contact[e] && (ball[8] > 0.0f) && ((ball[8] - s.ball_vel[e * 3 + 1]) > 10.0f);
+  s.has_contact_now[e] = now ? 1 : 0;
+  if (now) s.has_contact[e] = 1;
+  const float* wq = rb + s.wrist_body * 13 + 3;
+  const float qw[4] = {wq[3], wq[0], wq[1], wq[2]};
+  float m[9];
+  quat_wxyz_to_rotmat(qw, m);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    s.root_pos[e * 3 + k] = rb[k];
+    s.root_vel[e * 3 + k] = s.root_states[e * s.root_stride + 7 + k];
+    s.racket_pos[e * 3 + k] = rb[s.racket_body * 13 + k];
+    s.racket_vel[e * 3 + k] = rb[s.racket_body * 13 + 7 + k];
+    s.racket_normal[e * 3 + k] = m[k * 3] * s.grip_normal[0] + m[k * 3 + 1] * s.grip_normal[1] + m[k * 3 + 2] * s.grip_normal[2];
+    s.ball_pos[e * 3 + k] = ball[k];
+    s.ball_vel[e * 3 + k] = ball[7 + k];
+  }
+  s.ball_vspin[e] = sqrtf(ball[10] * ball[10] + ball[11] * ball[11] + ball[12] * ball[12]) / 6.283185307179586f;
+}
+
+// ------------------------------------------------------------------------------------------ a14-a16: controller post step
+__device__ __forceinline__ bool in_court(float x, float y) { return x > -4.11f && x < 4.11f && y > 0.0f && y < 11.89f; }
+__device__ __forceinline__ float est_index(float v, const float* r) {  // clamp + round (:126-162)
+  v = fminf(fmaxf(v, r[0]), r[1] - r[2]);
+  return rintf((v - r[0]) / r[2]);
+}
+__global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p_ctrl_t c) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * V2P_WARPS + warp;
+  if (e >= c.n) return;
+  const float* rb = c.rigid_body_state + e * c.bodies_per_env * 13;
+  const float rp[3] = {c.root_pos[e * 3], c.root_pos[e * 3 + 1], c.root_pos[e * 3 + 2]};
+  const float bp[3] = {c.ball_pos[e * 3], c.ball_pos[e * 3 + 1], c.ball_pos[e * 3 + 2]};
+  const float kp[3] = {c.racket_pos[e * 3], c.racket_pos[e * 3 + 1], c.racket_pos[e * 3 + 2]};
+  const bool has_contact = c.has_contact[e] != 0;
+  // ---- _update_state (:271-314): true bounce in court, estimated bounce of the outgoing ball
+  if (lane == 0) {
+    if (c.tar_action[e] == 0 && c.has_bounce_now[e]) c.bounce_in[e] = in_court(c.bounce_pos[e * 3], c.bounce_pos[e * 3 + 1]) ? 1 : 0;
+    if (c.has_contact_now[e] && c.est_x) {
+      const float* b = c.ball_states + e * c.ball_stride;
+      const float *VX = c.est_params, *VY = c.est_params + 3, *VS = c.est_params + 6, *TX = c.est_params + 9, *TY = c.est_params + 12;
+      bool valid = (b[8] > VX[0]) && (b[9] > VY[0]) && (b[9] < VY[1]) && (b[2] < TY[1]);
+      const float x_net = b[0] + b[7] * fabsf(b[1] / b[8]);
+      valid = valid && (x_net > -4.0f) && (x_net < 4.0f);
+      if (valid) {
+        const float vel_x = sqrtf(b[7] * b[7] + b[8] * b[8]);
+        const float vspin = sqrtf(b[10] * b[10] + b[11] * b[11] + b[12] * b[12]) / 6.283185307179586f;
+        const float d1 = (VY[1] - VY[0]) / VY[2], d2 = (VS[1] - VS[0]) / VS[2];
+        const int64_t ti = (int64_t)(est_index(vel_x, VX) * d1 * d2 + est_index(b[9], VY) * d2 + est_index(vspin, VS));
+        const float* tx = c.est_x + ti * c.est_nx;
+        const float* ty = c.est_y + ti * c.est_ny * 2;
+        const int hi = (int)est_index(b[2], TY);
+        float bx = b[0] + ty[hi * 2] * b[7] / vel_x, by = b[1] + ty[hi * 2] * b[8] / vel_x, bt = ty[hi * 2 + 1];
+        const float net_dist = -b[1] / b[8] * vel_x;
+        const int ni = (int)est_index(net_dist, TX);
+        if (tx[ni] + b[2] < 1.07f) { bx = 0.0f; by = 0.0f; bt = 0.0f; }  // into the net (NET_HEIGHT)
+        float mx = tx[0];
+        for (int k = 1; k < c.est_nx; k++) mx = fmaxf(mx, tx[k]);
+        c.est_bounce_pos[e * 3] = bx; c.est_bounce_pos[e * 3 + 1] = by;
+        c.est_bounce_time[e] = bt;
+        c.est_max_height[e] = b[2] + mx;
+        c.est_bounce_in[e] = in_court(bx, by) ? 1 : 0;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- reward (:368-406, jit :493-602)
+  if (lane == 0) {
+    const float phase = c.phase[e];
+    float d2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) d2 += (bp[k] - kp[k]) * (bp[k] - kp[k]);
+    float rew = 0.0f, s0 = 0.0f, s1 = 0.0f;
+    const float tp[3] = {c.target_bounce_pos[e * 3], c.target_bounce_pos[e * 3 + 1], c.target_bounce_pos[e * 3 + 2]};
+    if (c.reward_type == 0) {  // reach
+      const float cp = c.swing_type[e] == -1 ? 3.0f : 3.14159265358979323846f;
+      s0 = (c.tar_action[e] == 1 ? 1.0f : 0.0f) * expf(-c.scale_pos * d2) * expf(-c.scale_phase * (phase - cp) * (phase - cp));
+      rew = s0 * c.w_pos;
+    } else {
+      const int64_t st = c.reward_type == 1 ? c.swing_type[e] : c.swing_type_cycle[e];
+      const float cp = st >= 2 ? 3.0f : 3.14159265358979323846f;
+      s0 = (has_contact ? 0.0f : 1.0f) * expf(-c.scale_pos * d2) * expf(-c.scale_phase * (phase - cp) * (phase - cp)) + (has_contact ? 1.0f : 0.0f);
+      if (c.reward_type == 1) {  // return
+        float err = 0.0f;
+        const float* src = c.has_bounce[e] ? (c.bounce_pos + e * 3) : bp;
+#pragma unroll
+        for (int k = 0; k < 3; k++) err += (src[k] - tp[k]) * (src[k] - tp[k]);
+        s1 = (has_contact ? 1.0f : 0.0f) * fminf(fmaxf((400.0f - err) / 400.0f, 0.0f), 1.0f);
+      } else {  // return_w_estimate
+        float err = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) err += (c.est_bounce_pos[e * 3 + k] - tp[k]) * (c.est_bounce_pos[e * 3 + k] - tp[k]);
+        s1 = (c.est_bounce_in[e] ? 1.0f : 0.0f) * expf(-c.scale_bounce_pos * err) * expf(-c.scale_bounce_time * c.est_bounce_time[e]);
+      }
+      rew = c.w_pos * s0 + c.w_ball_pos * s1;
+    }
+    c.rew_buf[e] = rew;
+    c.sub_rewards[e * 2] = s0; c.sub_rewards[e * 2 + 1] = s1;
+  }
+  // ---- observation (:316-360): actor 225 | ball trajectory 3*L relative to the racket | target - root xy
+  float* o = c.obs_buf + e * c.num_obs;
+  bool nan = false;
+  if (lane < 3) { o[lane] = rp[lane]; o[3 + lane] = c.root_vel[e * 3 + lane]; o[222 + lane] = c.racket_normal[e * 3 + lane]; nan |= isnan(o[lane]) || isnan(o[3 + lane]) || isnan(o[222 + lane]); }
+  if (lane < 24) {
+    const float* b1 = rb + (lane + 1) * 13;  // bodies 1..24 (23 humanoid + Racket) relative to the root
+#pragma unroll
+    for (int k = 0; k < 3; k++) { float v = b1[k] - rp[k]; o[6 + lane * 3 + k] = v; nan |= isnan(v); }
+    const float* q = rb + lane * 13 + 3;  // xyzw fed to the WXYZ converter as is (reference quirk, :339)
+    float m[9];
+    quat_wxyz_to_rotmat(q, m);
+    float* r6 = o + 78 + lane * 6;  // rotmat_to_rot6d: cat(mat[...,0], mat[...,1]) = first and second COLUMN
+    r6[0] = m[0]; r6[1] = m[3]; r6[2] = m[6]; r6[3] = m[1]; r6[4] = m[4]; r6[5] = m[7];
+#pragma unroll
+    for (int k = 0; k < 6; k++) nan |= isnan(r6[k]);
+  }
+  const float* rk = rb + c.racket_body * 13;
+  for (int k = lane; k < c.obs_traj_len * 3; k += 32) { float v = c.ball_traj[e * 300 + k] - rk[k % 3]; o[225 + k] = v; nan |= isnan(v); }
+  if (c.use_target && lane < 2) { float v = c.target_bounce_pos[e * 3 + lane] - rp[lane]; o[225 + c.obs_traj_len * 3 + lane] = v; nan |= isnan(v); }
+  const bool has_nan = __any_sync(FULL, nan);
+  // ---- reset FSM (:408-436)
+  if (lane == 0) {
+    const bool out = rp[0] < c.court_min[0] || rp[1] < c.court_min[1] || rp[0] > c.court_max[0] || rp[1] > c.court_max[1];
+    bool terminate = out || has_nan;
+    int64_t reset = (c.progress_buf[e] >= (int64_t)c.max_episode_length - 1) ? 1 : (terminate ? 1 : 0);
+    bool reaction = c.tar_time[e] == c.tar_time_total[e];
+    const bool behind = bp[1] < rp[1] - 1.0f;
+    bool recovery = (c.tar_action[e] == 1) && (has_contact || behind);
+    c.distance[e] += sqrtf(c.root_vel[e * 3] * c.root_vel[e * 3] + c.root_vel[e * 3 + 1] * c.root_vel[e * 3 + 1]);  // _compute_stats
+    if (c.early_termination) {
+      terminate = terminate || (recovery && !has_contact) || behind;
+      if (c.reward_type == 2) terminate = terminate || (has_contact && !c.est_bounce_in[e]);
+    }
+    if (terminate) { reset = 1; recovery = false; }
+    reaction = reaction || (reset != 0);
+    c.terminate_buf[e] = terminate ? 1 : 0;
+    c.reset_buf[e] = reset;
+    c.reset_reaction[e] = reaction ? 1 : 0;
+    c.reset_recovery[e] = recovery ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* b200v2p_last_error(void) { return g_verr; }
+
+int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rotmat, const float* rest, const int32_t* parents,
+                        const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
+                        float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !root_pos || !joint_rotmat || !rest || !parents || !smpl_2_mujoco || !root_rot || !dof_pos || !root_vel || !root_ang_vel ||
+      !dof_vel || !rb_pos || !rb_rot)
+    return vfail(-1, "b200v2p_smpl_to_sim: bad arguments");
+  if (!(dt > 0)) return vfail(-2, "b200v2p_smpl_to_sim: dt must be positive");
+  smpl_to_sim_kernel<<<(n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      n, root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, prev_root_pos, prev_rb_rot, root_rot, dof_pos, root_vel, root_ang_vel,
+      dof_vel, rb_pos, rb_rot);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_ball_aero(int32_t n, const float* ball_states, int32_t stride, uint8_t* has_bounce, uint8_t* has_bounce_now, float* bounce_pos,
+                      float* force, int32_t substeps, float spin_scale, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !ball_states || !has_bounce || !has_bounce_now || !bounce_pos || !force || stride < 13) return vfail(-1, "b200v2p_ball_aero: bad arguments");
+  ball_aero_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, ball_states, stride, has_bounce, has_bounce_now, bounce_pos, force,
+                                                                     substeps, spin_scale);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_ball_reset(int32_t n, const int64_t* env_ids, const int64_t* pool_index, const float* pool, float* ball_states, int32_t stride,
+                       float* ball_pos, float* ball_vel, uint8_t* has_bounce, float* bounce_pos, uint8_t* has_contact, float* traj,
+                       void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !env_ids || !pool_index || !pool || !ball_states || !ball_pos || !ball_vel || !has_bounce || !bounce_pos || !has_contact || !traj)
+    return vfail(-1, "b200v2p_ball_reset: bad arguments");
+  ball_reset_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(n, env_ids, pool_index, pool, ball_states, stride, ball_pos, ball_vel, has_bounce,
+                                                        bounce_pos, has_contact, traj);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_update_state(const b200v2p_state_t* s, void* stream) {
+  if (!s) return vfail(-1, "b200v2p_update_state: null");
+  if (s->n == 0) return 0;
+  update_state_kernel<<<(s->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*s);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_controller_post(const b200v2p_ctrl_t* c, void* stream) {
+  if (!c) return vfail(-1, "b200v2p_controller_post: null");
+  if (c->n == 0) return 0;
+  if (c->obs_traj_len < 0 || c->obs_traj_len > 100 || c->num_obs < 225 + 3 * c->obs_traj_len + (c->use_target ? 2 : 0))
+    return vfail(-2, "b200v2p_controller_post: observation width / trajectory length mismatch");
+  if (c->reward_type < 0 || c->reward_type > 2) return vfail(-2, "b200v2p_controller_post: reward_type must be 0 (reach), 1 (return) or 2 (return_w_estimate)");
+  controller_post_kernel<<<(c->n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(*c);
+  V_CUDA_OK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,80 @@
+"""ctypes binding of the vid2player entry points (include/b200env_v2p.h) - same library, no CPU fallback."""
+import ctypes as C
+
+from . import abi
+from .native import _ptr, _stream, lib
+
+SYMBOLS = ["b200v2p_last_error", "b200v2p_smpl_to_sim", "b200v2p_ball_aero", "b200v2p_ball_reset", "b200v2p_update_state",
+           "b200v2p_controller_post"]
+GRIP_NORMAL = {'eastern': (0.0, 1.0, 0.0), 'semi_western': (0.0, 2.0 ** -0.5, 2.0 ** -0.5)}
+REWARD_TYPES = {'reach': 0, 'return': 1, 'return_w_estimate': 2}
+
+
+def _check(rc):
+    if rc != 0:
+        L = lib()
+        L.b200v2p_last_error.restype = C.c_char_p
+        raise RuntimeError(f"b200v2p error {rc}: {L.b200v2p_last_error().decode()}")
+
+
+def _c(t):
+    assert t is None or (t.is_cuda and t.is_contiguous()), "tensors must be contiguous CUDA tensors"
+    return _ptr(t)
+
+
+def smpl_to_sim(root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, out, prev_root_pos=None, prev_rb_rot=None):
+    """out: dict with root_rot[n,4] dof_pos[n,69] root_vel[n,3] root_ang_vel[n,3] dof_vel[n,69] rb_pos[n,24,3] rb_rot[n,24,4]"""
+    n = int(root_pos.shape[0])
+    _check(lib().b200v2p_smpl_to_sim(C.c_int32(n), _c(root_pos), _c(joint_rotmat), _c(rest), _c(parents), _c(smpl_2_mujoco), C.c_float(dt),
+                                     _c(prev_root_pos), _c(prev_rb_rot), _c(out["root_rot"]), _c(out["dof_pos"]), _c(out["root_vel"]),
+                                     _c(out["root_ang_vel"]), _c(out["dof_vel"]), _c(out["rb_pos"]), _c(out["rb_rot"]), _stream()))
+
+
+def ball_aero(ball_states, has_bounce, has_bounce_now, bounce_pos, force, substeps, spin_scale):
+    n = int(ball_states.shape[0])
+    _check(lib().b200v2p_ball_aero(C.c_int32(n), _c(ball_states), C.c_int32(ball_states.stride(0)), _c(has_bounce), _c(has_bounce_now),
+                                   _c(bounce_pos), _c(force), C.c_int32(substeps), C.c_float(spin_scale), _stream()))
+
+
+def ball_reset(env_ids, pool_index, pool, ball_states, ball_pos, ball_vel, has_bounce, bounce_pos, has_contact, traj):
+    _check(lib().b200v2p_ball_reset(C.c_int32(int(env_ids.shape[0])), _c(env_ids), _c(pool_index), _c(pool), _c(ball_states),
+                                    C.c_int32(ball_states.stride(0)), _c(ball_pos), _c(ball_vel), _c(has_bounce), _c(bounce_pos),
+                                    _c(has_contact), _c(traj), _stream()))
+
+
+def update_state(n, bodies_per_env, rigid_body_state, root_states, root_stride, ball_states, ball_stride, t, grip='eastern',
+                 racket_body=24, wrist_body=22):
+    s = abi.V2PState()
+    s.n, s.bodies_per_env, s.ball_stride, s.root_stride, s.racket_body, s.wrist_body = n, bodies_per_env, ball_stride, root_stride, racket_body, wrist_body
+    for i, v in enumerate(GRIP_NORMAL[grip]):
+        s.grip_normal[i] = v
+    s.rigid_body_state, s.root_states, s.ball_states = rigid_body_state.data_ptr(), root_states.data_ptr(), ball_states.data_ptr()
+    for k in ("has_contact", "has_contact_now", "root_pos", "root_vel", "racket_pos", "racket_vel", "racket_normal", "ball_pos", "ball_vel",
+              "ball_vspin"):
+        assert t[k].is_cuda and t[k].is_contiguous(), k
+        setattr(s, k, t[k].data_ptr())
+    _check(lib().b200v2p_update_state(C.byref(s), _stream()))
+
+
+def controller_post(cfg, t):
+    """cfg: dict of scalars (see abi.V2PCtrl); t: dict of tensors keyed like the struct's pointer fields (est_x/est_y may be None)."""
+    c = abi.V2PCtrl()
+    for k in ("n", "bodies_per_env", "ball_stride", "racket_body", "num_obs", "obs_traj_len", "use_target", "reward_type",
+              "early_termination", "max_episode_length", "est_nx", "est_ny", "scale_pos", "scale_phase", "scale_bounce_pos",
+              "scale_bounce_time", "w_pos", "w_ball_pos"):
+        setattr(c, k, cfg[k])
+    for k in ("court_min", "court_max", "est_params"):
+        for i, v in enumerate(cfg[k]):
+            getattr(c, k)[i] = float(v)
+    scalars = {f for f, _ in abi.V2PCtrl._fields_ if f in cfg}
+    for name, _ in abi.V2PCtrl._fields_:
+        if name in scalars:
+            continue
+        x = t.get(name)
+        if x is None:
+            assert name in ("est_x", "est_y"), name
+            setattr(c, name, None)
+        else:
+            assert x.is_cuda and x.is_contiguous(), name
+            setattr(c, name, x.data_ptr())
+    _check(lib().b200v2p_controller_post(C.byref(c), _stream()))
