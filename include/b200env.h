@@ -27,7 +27,7 @@ extern "C" {
 #define B200_MAX_BODIES 32
 #define B200_MAX_DOF 96
 #define B200_MAX_KEY 8
-#define B200_ABI_VERSION 1
+#define B200_ABI_VERSION 2
 
 /* Per-asset constant block produced by vid2player3d_b200/model_compiler.py from the MJCF/STL
  * assets (replaces gym.load_asset + create_actor + set_actor_dof_properties:
@@ -78,6 +78,16 @@ typedef struct b200_cfg {
   int32_t key_body[B200_MAX_KEY];                         /* keyBodies */
   int32_t shape_dim;                                      /* motion_bodies width (11) */
   float ground_tolerance;
+  /* --- vid2player physics player env (vid2player/env/tasks/humanoid_smpl_im_mvae.py) --- */
+  int32_t task_mode;   /* 0: HumanoidSMPLIM (MoCap target + obs + reward + reset fused in the step)
+                          1: HumanoidSMPLIMMVAE player step (:663-797): physics + ball, no task logic in the step */
+  int32_t pd_mode;     /* 0: clamp(action, q +- lim) (embodied_pose :391-396); 1: clamp(target_dof + action, q +- lim) (:693-709) */
+  int32_t has_ball;    /* 1: actor 1 of every env is the tennis ball (tennis_ball.urdf: r 0.032, m 0.057, I 4e-5) */
+  int32_t racket_body; /* body index of the welded Racket (24), -1 = none */
+  float ball_mass, ball_inertia, ball_radius, spin_scale;
+  float ball_e_ground, ball_mu_ground, ball_e_racket, ball_mu_racket, bounce_threshold_velocity;
+  float racket_head_center[3]; /* racket frame: cylinder fromto="0 0 0 0 0.0425 0" size 0.15 (federer.xml:190) */
+  float racket_head_halfthick, racket_head_radius;
 } b200_cfg_t;
 
 /* Reference MoCap buffer (embodied_pose/utils/motion_lib.py:68-93): flat device arrays. */
@@ -123,6 +133,11 @@ typedef struct b200_buffers {
   float *p_dof_pos, *p_dof_vel, *p_rb_pos, *p_rb_rot;
   float* pd_targets;       /* [N, nd] last PD targets (set_dof_position_target_tensor argument) */
   float* actions_used;     /* [N, num_actions] actions after zeroing reset envs (self.actions) */
+  /* vid2player player env only (may be NULL when cfg.has_ball == 0); bool tensors, 1 byte each */
+  uint8_t* has_bounce;       /* [N] _has_bounce */
+  uint8_t* has_bounce_now;   /* [N] _has_bounce_now (cleared at the start of every step, :688) */
+  float* bounce_pos;         /* [N,3] _bounce_pos */
+  uint8_t* racket_hit_now;   /* [N] exact racket-ball impact during this step (contact-force sensor path, :771-779) */
 } b200_buffers_t;
 
 typedef struct b200env* b200env_handle;
@@ -169,10 +184,11 @@ int b200env_obs_imitation(b200env_handle h, int32_t n, const float* body_pos, co
  * the same device code as b200env_step's physics, exposed so tests can compare it with the
  * float64 CPU restatement (oracle/physics_ref.c).  root [n,13], dof_pos/dof_vel/pd_tar [n,nd],
  * ext_wrench [n,6] (force, torque on body 0, world frame, first sim step only),
- * rb_out [n,nb,13], contact_out [n,nb,3].  n_steps control steps are run back to back. */
+ * rb_out [n,nb,13], contact_out [n,nb,3].  n_steps control steps are run back to back.
+ * ball: in/out [n,13] (pos, quat unused, lin vel, ang vel) or NULL; ball_hits [n] counts racket impacts (or NULL). */
 int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_steps, void* root, void* dof_pos,
                          void* dof_vel, const void* pd_tar, const void* ext_wrench, void* rb_out, void* contact_out,
-                         void* stream);
+                         void* ball, int32_t* ball_hits, void* stream);
 
 /* number of kernels launched by this handle so far (bench.py "gpu_launches") */
 int64_t b200env_launch_count(b200env_handle h);

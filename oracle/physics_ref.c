@@ -127,8 +127,9 @@ static void rank1(real IA[6][6], const real* J, real k) {
 }
 
 /* one substep of length h for one env; ext = wrench (force, torque) on body 0 or NULL */
+struct ball_s;
 static int substep(const b200_model_t* m, const float* verts, const b200_cfg_t* cfg, real h, body_t* B,
-                   const real* pd_tar, const real* ext, real* contact_f) {
+                   const real* pd_tar, const real* ext, real* contact_f, const real* racket_react /* F[3], X[3] or NULL */) {
   int nb = m->nb;
   real g[3] = {0, 0, cfg->gravity_z};
   /* 1. kinematics */
@@ -179,6 +180,11 @@ static int substep(const b200_model_t* m, const float* verts, const b200_cfg_t* 
     cross(b->w, c, wxc); cross(b->w, wxc, wxwxc);
     cross(c, g, cxg);
     for (int k = 0; k < 3; k++) { b->bA[k] = wxIw[k] - ms * cxg[k]; b->bA[3 + k] = ms * wxwxc[k] - ms * g[k]; }
+    if (racket_react && cfg->racket_body >= 0 && i == m->parent[cfg->racket_body]) { /* last racket impact's reaction on the wrist */
+      real dx[3] = {racket_react[3] - b->p[0], racket_react[4] - b->p[1], racket_react[5] - b->p[2]}, t[3];
+      cross(dx, racket_react, t);
+      for (int k = 0; k < 3; k++) { b->bA[k] -= t[k]; b->bA[3 + k] -= racket_react[k]; }
+    }
     if (i == 0 && ext) { /* force acts at the COM of body 0 (apply_rigid_body_force_tensors, ENV_SPACE) */
       real cxF[3]; cross(c, ext, cxF);
       for (int k = 0; k < 3; k++) { b->bA[k] -= ext[3 + k] + cxF[k]; b->bA[3 + k] -= ext[k]; }
@@ -320,13 +326,112 @@ static void fk(const b200_model_t* m, body_t* B) {
   }
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Tennis ball (vid2player): our model, float64 restatement of csrc/b200env.cu::ball_substep.
+ * Reference inputs honoured: tennis_ball.urdf (r, m, I), aerodynamic force of apply_external_force_to_ball
+ * (vid2player/env/tasks/humanoid_smpl_im_mvae.py:711-739, refreshed once per sim step :752-756), material
+ * restitution / friction (:414-416,436-438; PhysX "average" combine), racket head cylinder (federer.xml:190).
+ * Parity vs PhysX is unpinned like the rest of the physics. */
+typedef struct {
+  real p[3], v[3], w[3], fa[3], rF[3], rX[3];
+  int hits, has_bounce, bounce_now;
+  real bpos[3];
+} ball_t;
+
+static void q_rot(const real* q, const real* v, real* o) {
+  real R[3][3]; q_to_mat(q, R); matvec3(R, v, o);
+}
+static void q_rot_inv(const real* q, const real* v, real* o) {
+  real R[3][3]; q_to_mat(q, R); matTvec3(R, v, o);
+}
+static void ball_aero_ref(const real* vel, const real* angvel, real spin_scale, real* f) {
+  const real KF = 0.0019462794807519486, CD = 0.55, PI2 = 6.283185307179586;
+  real vs = sqrt(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+  if (vs == 0) vs += 1;
+  real vn[3] = {vel[0] / vs, vel[1] / vs, vel[2] / vs}, down[3] = {0, 0, -1}, vt[3], c[3];
+  cross(vn, down, vt);
+  real vspin = sqrt(angvel[0] * angvel[0] + angvel[1] * angvel[1] + angvel[2] * angvel[2]) / PI2;
+  real cl = 1.0 / (2.0 + fabs(vs / (vspin * spin_scale + 1e-6)));
+  if (vspin > 0) cl = -cl;
+  cross(vt, vn, c);
+  for (int k = 0; k < 3; k++) f[k] = -KF * CD * vs * vel[k] - KF * cl * vs * vs * c[k];
+}
+static void ball_impulse_ref(const b200_cfg_t* cfg, ball_t* B, const real* n, const real* vo, real e, real mu, real* J) {
+  real m = cfg->ball_mass, I = cfg->ball_inertia, R = cfg->ball_radius;
+  real rn[3] = {-R * n[0], -R * n[1], -R * n[2]}, wxr[3], u[3];
+  cross(B->w, rn, wxr);
+  for (int k = 0; k < 3; k++) u[k] = B->v[k] + wxr[k] - vo[k];
+  real un = u[0] * n[0] + u[1] * n[1] + u[2] * n[2];
+  J[0] = J[1] = J[2] = 0;
+  if (!(un < 0)) return;
+  real jn = ((-un > cfg->bounce_threshold_velocity) ? (1.0 + e) : 1.0) * (-un) * m;
+  real ut[3] = {u[0] - un * n[0], u[1] - un * n[1], u[2] - un * n[2]};
+  real utn = sqrt(ut[0] * ut[0] + ut[1] * ut[1] + ut[2] * ut[2]), jt = 0;
+  if (utn > 1e-9) {
+    real stick = m * utn / (1.0 + m * R * R / I);
+    jt = mu * jn < stick ? mu * jn : stick;
+    for (int k = 0; k < 3; k++) ut[k] /= utn;
+  }
+  real rxJ[3];
+  for (int k = 0; k < 3; k++) J[k] = jn * n[k] - jt * ut[k];
+  cross(rn, J, rxJ);
+  for (int k = 0; k < 3; k++) { B->v[k] += J[k] / m; B->w[k] += rxJ[k] / I; }
+}
+static void ball_substep_ref(const b200_cfg_t* cfg, real h, ball_t* B, const body_t* racket) {
+  real m = cfg->ball_mass, R = cfg->ball_radius;
+  for (int k = 0; k < 3; k++) B->v[k] += h * B->fa[k] / m;
+  B->v[2] += h * cfg->gravity_z;
+  for (int k = 0; k < 3; k++) B->rF[k] = 0;
+  real thit = -1, nl = 0;
+  if (racket) {
+    real d[3], wxd[3], vrel[3], d0[3], vr[3];
+    for (int k = 0; k < 3; k++) d[k] = B->p[k] - racket->p[k];
+    cross(racket->w, d, wxd);
+    for (int k = 0; k < 3; k++) vrel[k] = B->v[k] - racket->v[k] - wxd[k];
+    q_rot_inv(racket->Q, d, d0); q_rot_inv(racket->Q, vrel, vr);
+    for (int k = 0; k < 3; k++) d0[k] -= cfg->racket_head_center[k];
+    real H = cfg->racket_head_halfthick + R, Rad = cfg->racket_head_radius + R;
+    if (fabs(d0[1]) < H) {
+      if (d0[0] * d0[0] + d0[2] * d0[2] < Rad * Rad) { thit = 0; nl = d0[1] >= 0 ? 1 : -1; }
+    } else {
+      real t = -1;
+      if (d0[1] >= H && vr[1] < 0) t = (d0[1] - H) / (-vr[1]);
+      else if (d0[1] <= -H && vr[1] > 0) t = (-H - d0[1]) / vr[1];
+      if (t >= 0 && t <= h) {
+        real hx = d0[0] + t * vr[0], hz = d0[2] + t * vr[2];
+        if (hx * hx + hz * hz < Rad * Rad) { thit = t; nl = d0[1] >= 0 ? 1 : -1; }
+      }
+    }
+    if (thit >= 0) {
+      real ny[3] = {0, nl, 0}, n[3], J[3], xc[3], dx[3], wxx[3], vo[3], vb[3];
+      q_rot(racket->Q, ny, n);
+      for (int k = 0; k < 3; k++) { xc[k] = B->p[k] + thit * B->v[k] - R * n[k]; dx[k] = xc[k] - racket->p[k]; vb[k] = B->v[k]; }
+      cross(racket->w, dx, wxx);
+      for (int k = 0; k < 3; k++) vo[k] = racket->v[k] + wxx[k];
+      ball_impulse_ref(cfg, B, n, vo, cfg->ball_e_racket, cfg->ball_mu_racket, J);
+      if (J[0] != 0 || J[1] != 0 || J[2] != 0) {
+        for (int k = 0; k < 3; k++) { B->rF[k] = -J[k] / h; B->rX[k] = xc[k]; B->p[k] += thit * vb[k] + (h - thit) * B->v[k]; }
+        B->hits++;
+      } else thit = -1;
+    }
+  }
+  if (thit < 0) for (int k = 0; k < 3; k++) B->p[k] += h * B->v[k];
+  if (B->p[2] < R && B->v[2] < 0) {
+    real n[3] = {0, 0, 1}, vo[3] = {0, 0, 0}, J[3];
+    ball_impulse_ref(cfg, B, n, vo, cfg->ball_e_ground, cfg->ball_mu_ground, J);
+    B->p[2] = R;
+  }
+}
+
 /* One control step (control_freq_inv sim steps x substeps) for n envs.  Same I/O contract as
  * b200env_physics_only(prec=1) in include/b200env.h.  Returns 0, or -(env+1) on a failed solve. */
-int phys_ref_control_step(const b200_model_t* m, const float* verts, const b200_cfg_t* cfg, int n, double* root,
-                          double* dof_pos, double* dof_vel, const double* pd_tar, const double* ext_wrench,
-                          double* rb_out, double* contact_out) {
+int phys_ref_control_step_ball(const b200_model_t* m, const float* verts, const b200_cfg_t* cfg, int n, double* root,
+                               double* dof_pos, double* dof_vel, const double* pd_tar, const double* ext_wrench,
+                               double* rb_out, double* contact_out, double* ballio, int32_t* hits) {
   int nb = m->nb, nd = m->nd, fail = 0;
   real h = (real)cfg->sim_dt / cfg->substeps;
+  const int with_ball = cfg->has_ball && ballio != 0;
 #pragma omp parallel for schedule(static)
   for (int e = 0; e < n; e++) {
     body_t B[B200_MAX_BODIES];
@@ -340,11 +445,27 @@ int phys_ref_control_step(const b200_model_t* m, const float* verts, const b200_
       q_exp(dof_pos + (size_t)e * nd + d0, B[i].qj);
       memcpy(B[i].wt, dof_vel + (size_t)e * nd + d0, 3 * sizeof(real));
     }
+    ball_t ball;
+    memset(&ball, 0, sizeof(ball));
+    if (with_ball) {
+      real* bs = ballio + (size_t)e * 13;
+      memcpy(ball.p, bs, 3 * sizeof(real)); memcpy(ball.v, bs + 7, 3 * sizeof(real)); memcpy(ball.w, bs + 10, 3 * sizeof(real));
+    }
     real cf[3 * B200_MAX_BODIES];
     int err = 0;
-    for (int s = 0; s < cfg->control_freq_inv && !err; s++)
-      for (int k = 0; k < cfg->substeps && !err; k++)
-        err = substep(m, verts, cfg, h, B, pd_tar + (size_t)e * nd, (s == 0 && ext_wrench) ? ext_wrench + (size_t)e * 6 : 0, cf);
+    for (int s = 0; s < cfg->control_freq_inv && !err; s++) {
+      if (with_ball) {
+        ball_aero_ref(ball.v, ball.w, cfg->spin_scale, ball.fa);
+        real thr = cfg->substeps > 2 ? cfg->ball_radius * 6 : cfg->ball_radius * 4;
+        if (!ball.has_bounce && ball.p[2] <= thr) { ball.has_bounce = 1; ball.bounce_now = 1; memcpy(ball.bpos, ball.p, sizeof(ball.bpos)); }
+      }
+      for (int k = 0; k < cfg->substeps && !err; k++) {
+        real react[6] = {ball.rF[0], ball.rF[1], ball.rF[2], ball.rX[0], ball.rX[1], ball.rX[2]};
+        err = substep(m, verts, cfg, h, B, pd_tar + (size_t)e * nd, (s == 0 && ext_wrench) ? ext_wrench + (size_t)e * 6 : 0, cf,
+                      with_ball ? react : 0);
+        if (with_ball && !err) ball_substep_ref(cfg, h, &ball, cfg->racket_body >= 0 ? &B[cfg->racket_body] : 0);
+      }
+    }
     if (err) {
 #pragma omp critical
       if (!fail) fail = -(e + 1);
@@ -365,8 +486,19 @@ int phys_ref_control_step(const b200_model_t* m, const float* verts, const b200_
       memcpy(o + 7, B[i].v, 3 * sizeof(real)); memcpy(o + 10, B[i].w, 3 * sizeof(real));
       if (contact_out) memcpy(contact_out + ((size_t)e * nb + i) * 3, cf + 3 * i, 3 * sizeof(real));
     }
+    if (with_ball) {
+      real* bs = ballio + (size_t)e * 13;
+      memcpy(bs, ball.p, 3 * sizeof(real)); memcpy(bs + 7, ball.v, 3 * sizeof(real)); memcpy(bs + 10, ball.w, 3 * sizeof(real));
+      if (hits) hits[e] = ball.hits;
+    }
   }
   return fail;
+}
+
+int phys_ref_control_step(const b200_model_t* m, const float* verts, const b200_cfg_t* cfg, int n, double* root,
+                          double* dof_pos, double* dof_vel, const double* pd_tar, const double* ext_wrench,
+                          double* rb_out, double* contact_out) {
+  return phys_ref_control_step_ball(m, verts, cfg, n, root, dof_pos, dof_vel, pd_tar, ext_wrench, rb_out, contact_out, 0, 0);
 }
 
 /* diagnostics for invariant tests: total mass, COM, linear momentum, angular momentum about the

@@ -25,6 +25,7 @@ def lib():
             build()
         _lib = C.CDLL(LIB)
         _lib.phys_ref_control_step.restype = C.c_int
+        _lib.phys_ref_control_step_ball.restype = C.c_int
         _lib.phys_ref_diagnostics.restype = C.c_int
     return _lib
 
@@ -33,19 +34,26 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def control_step(model, verts, cfg, root, dof_pos, dof_vel, pd_tar, ext_wrench=None, n_steps=1):
-    """In-place on float64 arrays root[n,13], dof_pos[n,nd], dof_vel[n,nd]; returns (rb[n,nb,13], contact[n,nb,3])."""
+def control_step(model, verts, cfg, root, dof_pos, dof_vel, pd_tar, ext_wrench=None, n_steps=1, ball=None, hits=None):
+    """In-place on float64 arrays root[n,13], dof_pos[n,nd], dof_vel[n,nd] (and ball[n,13], hits[n] int32 when given);
+    returns (rb[n,nb,13], contact[n,nb,3])."""
     n = root.shape[0]
     for a in (root, dof_pos, dof_vel, pd_tar):
         assert a.dtype == np.float64 and a.flags.c_contiguous
     rb = np.zeros((n, model.nb, 13))
     cf = np.zeros((n, model.nb, 3))
     verts = np.ascontiguousarray(verts, np.float32)
+    total = np.zeros(n, np.int32)
+    step_hits = np.zeros(n, np.int32) if hits is not None else None
     for _ in range(n_steps):
-        rc = lib().phys_ref_control_step(C.byref(model), _p(verts), C.byref(cfg), C.c_int(n), _p(root), _p(dof_pos),
-                                         _p(dof_vel), _p(pd_tar), _p(ext_wrench), _p(rb), _p(cf))
+        rc = lib().phys_ref_control_step_ball(C.byref(model), _p(verts), C.byref(cfg), C.c_int(n), _p(root), _p(dof_pos),
+                                              _p(dof_vel), _p(pd_tar), _p(ext_wrench), _p(rb), _p(cf), _p(ball), _p(step_hits))
         if rc != 0:
             raise RuntimeError(f"phys_ref_control_step failed for env {-rc - 1}")
+        if hits is not None:
+            total += step_hits
+    if hits is not None:
+        hits[:] = total  # racket impacts accumulated over the n_steps control steps
     return rb, cf
 
 

@@ -317,3 +317,101 @@ def test_missing_arguments_fail_loudly(small_lib):
     task = make_task(4, small_lib)
     with pytest.raises(RuntimeError):
         native._check(native.lib().b200env_step(task._env._h, None, None))
+
+
+# --------------------------------------------------------------------------------------- ball + racket (vid2player)
+def make_ball_env(n=4, substeps=6):
+    """native env on the federer asset (24 bodies + welded Racket) with the tennis ball enabled"""
+    from vid2player3d_b200 import abi, model_compiler, native
+    mod = model_compiler.load_compiled("smpl_mesh_humanoid_federer")
+    ms, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    cfg = abi.make_cfg(mod, substeps=substeps, ball={}, task_mode=1, pd_mode=1)
+    return mod, ms, verts, cfg, native.Env(ms, verts, cfg, n, 0)
+
+
+def ball_scene(mod, ms, verts, cfg, n, seed):
+    """random flying humanoids; balls aimed at the racket head (half), at the ground with spin (quarter), free (rest)"""
+    import ctypes
+    from oracle import physics_ref
+    from vid2player3d_b200 import abi
+    root, q, qd, tar, ext = phys_states(mod, n, seed, False)
+    root[:, 2] = np.random.default_rng(seed).uniform(1.5, 2.5, n)
+    tiny = abi.Cfg.from_buffer_copy(cfg)
+    tiny.sim_dt = 1e-12
+    r0, q0, v0 = root.copy(), q.copy(), qd.copy()
+    rb, _ = physics_ref.control_step(ms, verts, tiny, r0, q0, v0, tar.copy(), None)
+    rng = np.random.default_rng(seed + 1)
+    ball = np.zeros((n, 13)); ball[:, 6] = 1
+    from scipy.spatial.transform import Rotation
+    for e in range(n):
+        Rr = Rotation.from_quat(rb[e, 24, 3:7]).as_matrix()
+        pr, vr = rb[e, 24, 0:3], rb[e, 24, 7:10]
+        kind = e % 4
+        if kind in (0, 1):
+            side = 1.0 if kind == 0 else -1.0
+            off = np.array([rng.uniform(-0.08, 0.08), 0.02125 + side * rng.uniform(0.06, 0.10), rng.uniform(-0.08, 0.08)])
+            ball[e, 0:3] = pr + Rr @ off
+            ball[e, 7:10] = vr + Rr @ np.array([rng.normal(0, 3), -side * rng.uniform(15, 30), rng.normal(0, 3)])
+            ball[e, 10:13] = rng.normal(0, 40, 3)
+        elif kind == 2:
+            ball[e, 0:3] = [rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(0.033, 0.08)]
+            ball[e, 7:10] = [rng.normal(0, 8), rng.normal(0, 8), -rng.uniform(0.05, 12)]
+            ball[e, 10:13] = rng.normal(0, 60, 3)
+        else:
+            ball[e, 0:3] = [rng.uniform(-3, 3), rng.uniform(5, 9), rng.uniform(1, 2)]
+            ball[e, 7:10] = [rng.normal(0, 2), -rng.uniform(20, 30), rng.normal(2, 2)]
+            ball[e, 10:13] = rng.normal(0, 40, 3)
+    return root, q, qd, tar, ext, ball
+
+
+@pytest.mark.parametrize("substeps", [2, 6])
+def test_ball_physics_f64_matches_oracle(substeps):
+    """humanoid + welded racket + ball (aero, swept racket impact with reaction on the wrist, ground bounce):
+    double-precision kernel vs float64 restatement, 1 and 3 control steps"""
+    from oracle import physics_ref
+    mod, ms, verts, cfg, env = make_ball_env(4, substeps)
+    n = 64
+    root, q, qd, tar, ext, ball = ball_scene(mod, ms, verts, cfg, n, 17)
+    for steps, tol in ((1, 1e-9), (3, 1e-7)):
+        t = lambda a: torch.tensor(a, dtype=torch.float64, device="cuda:0").contiguous()  # noqa: E731
+        r, qq, vv, tt, ee, bb = t(root), t(q), t(qd), t(tar), t(ext), t(ball)
+        rb = torch.zeros(n, 25, 13, dtype=torch.float64, device="cuda:0")
+        cf = torch.zeros(n, 25, 3, dtype=torch.float64, device="cuda:0")
+        hits = torch.zeros(n, dtype=torch.int32, device="cuda:0")
+        env.physics_only(r, qq, vv, tt, ee, rb, cf, n_steps=steps, ball=bb, ball_hits=hits)
+        torch.cuda.synchronize()
+        ro, qo, vo, bo = root.copy(), q.copy(), qd.copy(), ball.copy()
+        ho = np.zeros(n, np.int32)
+        rbo, _ = physics_ref.control_step(ms, verts, cfg, ro, qo, vo, tar.copy(), ext.copy(), n_steps=steps, ball=bo, hits=ho)
+        assert np.array_equal(hits.cpu().numpy(), ho)
+        np.testing.assert_allclose(bb.cpu().numpy(), bo, rtol=0, atol=tol * 10)
+        np.testing.assert_allclose(r.cpu().numpy(), ro, rtol=0, atol=tol)
+        np.testing.assert_allclose(qq.cpu().numpy(), qo, rtol=0, atol=tol)
+        np.testing.assert_allclose(vv.cpu().numpy(), vo, rtol=0, atol=tol * 100)
+        np.testing.assert_allclose(rb.cpu().numpy(), rbo, rtol=0, atol=tol * 100)
+    assert (ho > 0).sum() >= n // 4            # racket impacts happened ...
+    hit = ho > 0
+    assert np.all(np.linalg.norm(bo[hit, 7:10] - ball[hit, 7:10], axis=1) > 5.0)   # ... and turned the ball around
+    ground = np.arange(n) % 4 == 2
+    assert np.all(bo[ground, 2] >= cfg.ball_radius - 1e-9)
+
+
+def test_ball_physics_f32_vs_oracle():
+    from oracle import physics_ref
+    mod, ms, verts, cfg, env = make_ball_env(4, 6)
+    n = 64
+    root, q, qd, tar, ext, ball = ball_scene(mod, ms, verts, cfg, n, 23)
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda:0").contiguous()  # noqa: E731
+    r, qq, vv, tt, ee, bb = t(root), t(q), t(qd), t(tar), t(ext), t(ball)
+    rb = torch.zeros(n, 25, 13, device="cuda:0"); cf = torch.zeros(n, 25, 3, device="cuda:0")
+    hits = torch.zeros(n, dtype=torch.int32, device="cuda:0")
+    env.physics_only(r, qq, vv, tt, ee, rb, cf, n_steps=1, ball=bb, ball_hits=hits)
+    torch.cuda.synchronize()
+    ro, qo, vo, bo = root.copy(), q.copy(), qd.copy(), ball.copy()
+    ho = np.zeros(n, np.int32)
+    physics_ref.control_step(ms, verts, cfg, ro, qo, vo, tar.copy(), ext.copy(), ball=bo, hits=ho)
+    same = hits.cpu().numpy() == ho                      # a grazing impact may flip in float32
+    assert same.mean() > 0.95
+    np.testing.assert_allclose(bb.cpu().numpy()[same, 0:3], bo[same, 0:3], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(bb.cpu().numpy()[same, 7:10], bo[same, 7:10], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(qq.cpu().numpy()[same], qo[same], rtol=0, atol=1e-4)

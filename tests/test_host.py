@@ -21,7 +21,8 @@ def test_library_exports_every_declared_symbol():
     L = C.CDLL(lib)  # loads without a GPU; no compute call is made here
     for name in declared:
         assert hasattr(L, name), name
-    assert L.b200env_abi_version() == 1
+    from vid2player3d_b200 import abi
+    assert L.b200env_abi_version() == abi.ABI_VERSION
 
 
 def test_struct_layouts_match_header(tmp_path):

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 MAX_BODIES, MAX_DOF, MAX_KEY = 32, 96, 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Model(C.Structure):
@@ -35,6 +35,11 @@ class Cfg(C.Structure):
         ("w_dof", C.c_float), ("w_vel", C.c_float), ("w_pos", C.c_float), ("w_rot", C.c_float),
         ("num_key", C.c_int32), ("key_body", C.c_int32 * MAX_KEY), ("shape_dim", C.c_int32),
         ("ground_tolerance", C.c_float),
+        ("task_mode", C.c_int32), ("pd_mode", C.c_int32), ("has_ball", C.c_int32), ("racket_body", C.c_int32),
+        ("ball_mass", C.c_float), ("ball_inertia", C.c_float), ("ball_radius", C.c_float), ("spin_scale", C.c_float),
+        ("ball_e_ground", C.c_float), ("ball_mu_ground", C.c_float), ("ball_e_racket", C.c_float), ("ball_mu_racket", C.c_float),
+        ("bounce_threshold_velocity", C.c_float),
+        ("racket_head_center", C.c_float * 3), ("racket_head_halfthick", C.c_float), ("racket_head_radius", C.c_float),
     ]
 
 
@@ -61,6 +66,7 @@ class Buffers(C.Structure):
         ("t_rb_rot", C.c_void_p),
         ("p_dof_pos", C.c_void_p), ("p_dof_vel", C.c_void_p), ("p_rb_pos", C.c_void_p), ("p_rb_rot", C.c_void_p),
         ("pd_targets", C.c_void_p), ("actions_used", C.c_void_p),
+        ("has_bounce", C.c_void_p), ("has_bounce_now", C.c_void_p), ("bounce_pos", C.c_void_p), ("racket_hit_now", C.c_void_p),
     ]
 
 
@@ -109,7 +115,7 @@ def make_cfg(model, *, sim_dt=1.0 / 60.0, substeps=2, control_freq_inv=2, gravit
              res_force_scale=31.85, res_torque_scale=None, max_episode_length=300, enable_early_termination=True,
              termination_body_height=-0.5, termination_head_height=1.0, contact_bodies=("R_Ankle", "L_Ankle"),
              key_bodies=("R_Ankle", "L_Ankle", "L_Hand", "R_Hand"), body_pos_weights=None, reward_specs=None,
-             shape_dim=11, ground_tolerance=0.0, **physics):
+             shape_dim=11, ground_tolerance=0.0, task_mode=0, pd_mode=0, ball=None, **physics):
     names = [str(x) for x in model["body_names"]]
     nb = len(names)
     c = Cfg()
@@ -142,7 +148,26 @@ def make_cfg(model, *, sim_dt=1.0 / 60.0, substeps=2, control_freq_inv=2, gravit
     _fill(c.key_body, [names.index(k) for k in key_bodies])
     c.shape_dim = shape_dim
     c.ground_tolerance = ground_tolerance
+    c.task_mode, c.pd_mode = task_mode, pd_mode
+    c.racket_body = names.index("Racket") if "Racket" in names else -1
+    c.has_ball = 0
+    if ball is not None:
+        b = dict(DEFAULT_BALL)
+        b.update(ball)
+        c.has_ball = 1
+        for k in ("ball_mass", "ball_inertia", "ball_radius", "spin_scale", "ball_e_ground", "ball_mu_ground", "ball_e_racket",
+                  "ball_mu_racket", "bounce_threshold_velocity", "racket_head_halfthick", "racket_head_radius"):
+            setattr(c, k, b[k])
+        _fill(c.racket_head_center, b["racket_head_center"])
     return c
+
+
+# tennis_ball.urdf (r 0.032, m 0.057, I 4e-5); restitution/friction: PhysX "average" combine of the material values the
+# reference sets (humanoid_smpl_im_mvae.py:414-416,436-438: ball & racket 0.9 / 0.2 & 0.8; plane 0.5 / 1.0 from
+# cfg/controller/federer.yaml:14-23); racket head = cylinder fromto "0 0 0 0 0.0425 0" size 0.15 (federer.xml:190)
+DEFAULT_BALL = dict(ball_mass=0.057, ball_inertia=4e-5, ball_radius=0.032, spin_scale=5.0, ball_e_ground=0.7, ball_mu_ground=0.6,
+                    ball_e_racket=0.9, ball_mu_racket=0.5, bounce_threshold_velocity=0.2, racket_head_center=(0.0, 0.02125, 0.0),
+                    racket_head_halfthick=0.02125, racket_head_radius=0.15)
 
 
 # ---------------------------------------------------------------- include/b200env_v2p.h

@@ -203,6 +203,19 @@ struct LaneConst {
 template <typename T> struct PhysCfg {
   T h, gz, kn, cn, mu, vs, damp, wmax, limk, limc;
   int substeps, cfi;
+  // tennis ball (vid2player): lane BALL_LANE integrates it next to the humanoid
+  int has_ball, racket_body, wrist_body;
+  T bm, bI, bR, spin_scale, eg, mug, er, mur, vth, hc[3], hh, hr;
+};
+#define BALL_LANE 31
+// ball state held by lane BALL_LANE (float64 restatement: oracle/physics_ref.c::ball_substep)
+template <typename T> struct Ball {
+  T p[3], v[3], w[3];   // position, linear and angular velocity (world)
+  T fa[3];              // aerodynamic force, refreshed once per sim step like the reference (humanoid_smpl_im_mvae.py:752-756)
+  T rF[3], rX[3];       // reaction force on the racket from the last impact (applied to the wrist link next substep) and its point
+  int hits;             // racket impacts so far
+  int has_bounce, bounce_now;
+  T bpos[3];
 };
 template <typename T> __device__ __forceinline__ PhysCfg<T> make_phys_cfg(const b200_cfg_t& c) {
   PhysCfg<T> p;
@@ -211,6 +224,12 @@ template <typename T> __device__ __forceinline__ PhysCfg<T> make_phys_cfg(const 
   p.vs = T(c.friction_vs); p.damp = T(1) - p.h * T(c.ang_damping); p.wmax = T(c.max_ang_vel);
   p.limk = T(c.limit_k); p.limc = T(c.limit_c);
   p.substeps = c.substeps; p.cfi = c.control_freq_inv;
+  p.has_ball = c.has_ball; p.racket_body = c.racket_body; p.wrist_body = 0;
+  p.bm = T(c.ball_mass); p.bI = T(c.ball_inertia); p.bR = T(c.ball_radius); p.spin_scale = T(c.spin_scale);
+  p.eg = T(c.ball_e_ground); p.mug = T(c.ball_mu_ground); p.er = T(c.ball_e_racket); p.mur = T(c.ball_mu_racket);
+  p.vth = T(c.bounce_threshold_velocity);
+  p.hc[0] = T(c.racket_head_center[0]); p.hc[1] = T(c.racket_head_center[1]); p.hc[2] = T(c.racket_head_center[2]);
+  p.hh = T(c.racket_head_halfthick); p.hr = T(c.racket_head_radius);
   return p;
 }
 
@@ -250,11 +269,116 @@ __device__ __forceinline__ void fk_pass(const b200_model_t& M, const LaneConst& 
   }
 }
 
+
+// drag + Magnus lift on the ball (apply_external_force_to_ball, humanoid_smpl_im_mvae.py:711-739; constants tennis_ball.py:15-37)
+template <typename T> __device__ __forceinline__ void ball_aero(const T* vel, const T* angvel, T spin_scale, T* force) {
+  const T KF = T(0.0019462794807519486), CD = T(0.55);
+  T vs = sqrt_(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+  if (vs == T(0)) vs += T(1);
+  const T iv = rcp_(vs);
+  const T vn[3] = {vel[0] * iv, vel[1] * iv, vel[2] * iv};
+  const T vt[3] = {-vn[1], vn[0], T(0)};  // vn x (0,0,-1)
+  const T vspin = sqrt_(angvel[0] * angvel[0] + angvel[1] * angvel[1] + angvel[2] * angvel[2]) * T(0.15915494309189535);
+  T cl = rcp_(T(2) + fabs(vs * rcp_(vspin * spin_scale + T(1e-6))));
+  cl = vspin > T(0) ? -cl : cl;
+  const T cx = vt[1] * vn[2] - vt[2] * vn[1], cy = vt[2] * vn[0] - vt[0] * vn[2], cz = vt[0] * vn[1] - vt[1] * vn[0];
+  const T kd = -KF * CD * vs, kl = -KF * cl * vs * vs;
+  force[0] = kd * vel[0] + kl * cx; force[1] = kd * vel[1] + kl * cy; force[2] = kd * vel[2] + kl * cz;
+}
+// impulse on a sphere at contact normal n (pointing from the obstacle into the ball), obstacle point velocity vo:
+// restitution e on the normal part, Coulomb friction mu capped at the sticking impulse (spin coupled through I).
+template <typename T>
+__device__ __forceinline__ void ball_impulse(const PhysCfg<T>& c, Ball<T>& B, const T* n, const T* vo, T e, T mu, T* J) {
+  // contact point on the ball: -R n ; u = v + w x (-R n) - vo
+  T rn[3] = {-c.bR * n[0], -c.bR * n[1], -c.bR * n[2]}, wxr[3];
+  cross3(B.w, rn, wxr);
+  T u[3] = {B.v[0] + wxr[0] - vo[0], B.v[1] + wxr[1] - vo[1], B.v[2] + wxr[2] - vo[2]};
+  const T un = u[0] * n[0] + u[1] * n[1] + u[2] * n[2];
+  J[0] = J[1] = J[2] = T(0);
+  if (!(un < T(0))) return;
+  const T jn = (-un > c.vth ? (T(1) + e) : T(1)) * (-un) * c.bm;
+  T ut[3] = {u[0] - un * n[0], u[1] - un * n[1], u[2] - un * n[2]};
+  const T utn = sqrt_(ut[0] * ut[0] + ut[1] * ut[1] + ut[2] * ut[2]);
+  T jt = T(0);
+  if (utn > T(1e-9)) {
+    const T stick = c.bm * utn * rcp_(T(1) + c.bm * c.bR * c.bR * rcp_(c.bI));
+    jt = mu * jn < stick ? mu * jn : stick;
+    const T iu = rcp_(utn);
+    ut[0] *= iu; ut[1] *= iu; ut[2] *= iu;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) J[k] = jn * n[k] - jt * ut[k];
+  T rxJ[3];
+  cross3(rn, J, rxJ);
+  const T im = rcp_(c.bm), iI = rcp_(c.bI);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { B.v[k] += J[k] * im; B.w[k] += rxJ[k] * iI; }
+}
+// one substep of the ball: gravity + aero, swept test against the racket head (a cylinder of half thickness hh and
+// radius hr centred at hc in the racket frame; pose/velocity of the racket at the START of the substep), ground bounce.
+template <typename T>
+__device__ __forceinline__ void ball_substep(const PhysCfg<T>& c, Ball<T>& B, bool has_racket, const T* rQ, const T* rp, const T* rv, const T* rw) {
+  const T im = rcp_(c.bm);
+  B.v[0] += c.h * B.fa[0] * im; B.v[1] += c.h * B.fa[1] * im; B.v[2] += c.h * (c.gz + B.fa[2] * im);
+  B.rF[0] = B.rF[1] = B.rF[2] = T(0);
+  T thit = T(-1), nl = T(0);
+  if (has_racket) {
+    T d[3] = {B.p[0] - rp[0], B.p[1] - rp[1], B.p[2] - rp[2]}, wxd[3];
+    cross3(rw, d, wxd);
+    T vrel_w[3] = {B.v[0] - rv[0] - wxd[0], B.v[1] - rv[1] - wxd[1], B.v[2] - rv[2] - wxd[2]};
+    T cq[4] = {-rQ[0], -rQ[1], -rQ[2], rQ[3]}, d0[3], vr[3];
+    qrot(cq, d, d0);
+    qrot(cq, vrel_w, vr);
+    d0[0] -= c.hc[0]; d0[1] -= c.hc[1]; d0[2] -= c.hc[2];
+    const T H = c.hh + c.bR, Rad = c.hr + c.bR;
+    if (fabs(d0[1]) < H) {
+      if (d0[0] * d0[0] + d0[2] * d0[2] < Rad * Rad) { thit = T(0); nl = d0[1] >= T(0) ? T(1) : T(-1); }
+    } else {
+      T t = T(-1);
+      if (d0[1] >= H && vr[1] < T(0)) t = (d0[1] - H) * rcp_(-vr[1]);
+      else if (d0[1] <= -H && vr[1] > T(0)) t = (-H - d0[1]) * rcp_(vr[1]);
+      if (t >= T(0) && t <= c.h) {
+        const T hx = d0[0] + t * vr[0], hz = d0[2] + t * vr[2];
+        if (hx * hx + hz * hz < Rad * Rad) { thit = t; nl = d0[1] >= T(0) ? T(1) : T(-1); }
+      }
+    }
+    if (thit >= T(0)) {
+      const T ny[3] = {T(0), nl, T(0)};
+      T n[3], J[3], vo[3];
+      qrot(rQ, ny, n);
+      T xc[3] = {B.p[0] + thit * B.v[0] - c.bR * n[0], B.p[1] + thit * B.v[1] - c.bR * n[1], B.p[2] + thit * B.v[2] - c.bR * n[2]};
+      T dx[3] = {xc[0] - rp[0], xc[1] - rp[1], xc[2] - rp[2]}, wxx[3];
+      cross3(rw, dx, wxx);
+      vo[0] = rv[0] + wxx[0]; vo[1] = rv[1] + wxx[1]; vo[2] = rv[2] + wxx[2];
+      const T vb[3] = {B.v[0], B.v[1], B.v[2]};
+      ball_impulse(c, B, n, vo, c.er, c.mur, J);
+      if (J[0] != T(0) || J[1] != T(0) || J[2] != T(0)) {
+        const T ih = rcp_(c.h);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { B.rF[k] = -J[k] * ih; B.rX[k] = xc[k]; B.p[k] += thit * vb[k] + (c.h - thit) * B.v[k]; }
+        B.hits++;
+      } else {
+        thit = T(-1);
+      }
+    }
+  }
+  if (thit < T(0)) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) B.p[k] += c.h * B.v[k];
+  }
+  if (B.p[2] < c.bR && B.v[2] < T(0)) {  // ground
+    const T n[3] = {T(0), T(0), T(1)}, vo[3] = {T(0), T(0), T(0)};
+    T J[3];
+    ball_impulse(c, B, n, vo, c.eg, c.mug, J);
+    B.p[2] = c.bR;
+  }
+}
+
 // One substep of length h (float64 restatement: oracle/physics_ref.c::substep).
 template <typename T>
 __device__ __forceinline__ void substep(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c,
                                         const LaneConst& lc, int lane, Lane<T>& L, const T* pdtar, bool ext_on,
-                                        const T* extF, const T* extT, T* cf) {
+                                        const T* extF, const T* extT, T* cf, Ball<T>& ball) {
   const b200_model_t& M = B.m;
   T r[3] = {0, 0, 0}, zeta[6] = {0, 0, 0, 0, 0, 0};
   fk_pass<T, true>(M, lc, lane, L, r, zeta);
@@ -266,6 +390,11 @@ __device__ __forceinline__ void substep(const DevBlob& B, const float* __restric
   T R[9];
   qmat(L.Q, R);
   cf[0] = cf[1] = cf[2] = T(0);
+  T rF[3] = {0, 0, 0}, rX[3] = {0, 0, 0};
+  if (c.has_ball && c.racket_body >= 0) {  // (warp-uniform branch) fetch the ball lane's last racket reaction
+#pragma unroll
+    for (int k = 0; k < 3; k++) { rF[k] = shfl(ball.rF[k], BALL_LANE); rX[k] = shfl(ball.rX[k], BALL_LANE); }
+  }
   if (lc.dyn) {
     const T ms = T(M.mass[lane]);
     T cl[3] = {T(M.com[lane][0]), T(M.com[lane][1]), T(M.com[lane][2])}, cw[3];
@@ -306,6 +435,14 @@ __device__ __forceinline__ void substep(const DevBlob& B, const float* __restric
       bn[0] -= ms * cw[1] * c.gz;
       bn[1] += ms * cw[0] * c.gz;
       bf[0] = ms * t2[0]; bf[1] = ms * t2[1]; bf[2] = ms * t2[2] - ms * c.gz;
+    }
+    if (c.has_ball && c.racket_body >= 0) {  // reaction of the previous substep's racket impact, applied to the wrist link
+      if (lane == M.parent[c.racket_body]) {
+        T dx[3] = {rX[0] - L.p[0], rX[1] - L.p[1], rX[2] - L.p[2]}, t[3];
+        cross3(dx, rF, t);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { bn[k] -= t[k]; bf[k] -= rF[k]; }
+      }
     }
     if (lane == 0 && ext_on) {  // residual wrench: force at the COM + torque, world frame
       T cxF[3];
@@ -571,18 +708,44 @@ __device__ __forceinline__ void substep(const DevBlob& B, const float* __restric
 #pragma unroll
     for (int k = 0; k < 4; k++) L.qj[k] = qn[k];
   }
+  // ---- ball (lane BALL_LANE); the welded racket lane still holds its start-of-substep pose and velocity
+  if (c.has_ball) {
+    T rQ[4] = {0, 0, 0, 1}, rp[3] = {0, 0, 0}, rv[3] = {0, 0, 0}, rw[3] = {0, 0, 0};
+    const bool has_racket = c.racket_body >= 0;
+    if (has_racket) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) rQ[k] = shfl(L.Q[k], c.racket_body);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { rp[k] = shfl(L.p[k], c.racket_body); rv[k] = shfl(L.v[k], c.racket_body); rw[k] = shfl(L.w[k], c.racket_body); }
+    }
+    if (lane == BALL_LANE) ball_substep<T>(c, ball, has_racket, rQ, rp, rv, rw);
+  }
 }
 
+template <typename T> __device__ __forceinline__ void ball_clear(Ball<T>& b) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) { b.p[k] = 0; b.v[k] = 0; b.w[k] = 0; b.fa[k] = 0; b.rF[k] = 0; b.rX[k] = 0; b.bpos[k] = 0; }
+  b.hits = 0; b.has_bounce = 0; b.bounce_now = 0;
+}
 // control_freq_inv sim steps x substeps; external wrench only during the first sim step
 template <typename T>
 __device__ __forceinline__ void control_step(const DevBlob& B, const float* verts, const PhysCfg<T>& c, const LaneConst& lc,
                                              int lane, Lane<T>& L, const T* pdtar, const T* extF, const T* extT, T* cf,
-                                             bool cta_sync = false) {
-  for (int s = 0; s < c.cfi; s++)
+                                             Ball<T>& ball, bool cta_sync = false) {
+  for (int s = 0; s < c.cfi; s++) {
+    if (c.has_ball && lane == BALL_LANE) {  // once per sim step, like apply_external_force_to_ball (:752-756)
+      ball_aero<T>(ball.v, ball.w, c.spin_scale, ball.fa);
+      const T thr = c.substeps > 2 ? c.bR * T(6) : c.bR * T(4);
+      if (!ball.has_bounce && ball.p[2] <= thr) {
+        ball.has_bounce = 1; ball.bounce_now = 1;
+        ball.bpos[0] = ball.p[0]; ball.bpos[1] = ball.p[1]; ball.bpos[2] = ball.p[2];
+      }
+    }
     for (int k = 0; k < c.substeps; k++) {
       if (cta_sync) __syncthreads();
-      substep<T>(B, verts, c, lc, lane, L, pdtar, s == 0, extF, extT, cf);
+      substep<T>(B, verts, c, lc, lane, L, pdtar, s == 0, extF, extT, cf, ball);
     }
+  }
   T dummy[3], dz[6];
   fk_pass<T, false>(B.m, lc, lane, L, dummy, dz);
 }
@@ -844,7 +1007,7 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
   if (lane < 13) scr[lane] = rs[lane];
   for (int k = lane; k < nd * 2; k += 32) scr[16 + k] = ds[k];
   for (int k = lane; k < na; k += 32) {
-    float a = was_reset ? 0.0f : ac[k];  // actions[self.reset_buf == 1] = 0   (:126)
+    float a = (was_reset && cfg.task_mode == 0) ? 0.0f : ac[k];  // actions[self.reset_buf == 1] = 0   (:126, embodied_pose only)
     scr[16 + 2 * B200_MAX_DOF + k] = a;
     bf.actions_used[e * na + k] = a;
   }
@@ -871,7 +1034,9 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
       q[k] = scr[16 + (lc.dof0 + k) * 2];
       L.wt[k] = scr[16 + (lc.dof0 + k) * 2 + 1];
       float a = scr[16 + 2 * B200_MAX_DOF + lc.dof0 + k];
-      // _action_to_pd_targets (:391-396): clamp(action, q -+ pd_tar_lim)
+      // _action_to_pd_targets: clamp(action, q -+ lim) (humanoid_smpl_im.py:391-396) or, for the vid2player player env,
+      // clamp(target_dof + action, q -+ lim) (humanoid_smpl_im_mvae.py:693-709, no_scale_action / pd_target_base target_pos)
+      if (cfg.pd_mode == 1) a += bf.t_dof_pos[e * nd + lc.dof0 + k];
       pdtar[k] = fmaxf(fminf(a, q[k] + cfg.pd_tar_lim), q[k] - cfg.pd_tar_lim);
       bf.pd_targets[e * nd + lc.dof0 + k] = pdtar[k];
     }
@@ -904,7 +1069,30 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
 
   // ---- physics
   float cf[3];
-  control_step<float>(B, verts, pc, lc, lane, L, pdtar, extF, extT, cf, STEP_SYNC && full_batch);
+  Ball<float> ball;
+  ball_clear(ball);
+  float* ball_row = bf.root_states + (e * bf.actors_per_env + 1) * 13;  // actor 1 = ball (only dereferenced if has_ball)
+  if (cfg.has_ball && lane == BALL_LANE) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { ball.p[k] = ball_row[k]; ball.v[k] = ball_row[7 + k]; ball.w[k] = ball_row[10 + k]; }
+    ball.has_bounce = bf.has_bounce[e];
+  }
+  control_step<float>(B, verts, pc, lc, lane, L, pdtar, extF, extT, cf, ball, STEP_SYNC && full_batch);
+  if (cfg.has_ball && lane == BALL_LANE) {
+    float* brb = bf.rigid_body_state + (e * bf.bodies_per_env + bf.bodies_per_env - 1) * 13;  // last rigid-body row = ball
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      ball_row[k] = ball.p[k]; ball_row[7 + k] = ball.v[k]; ball_row[10 + k] = ball.w[k];
+      brb[k] = ball.p[k]; brb[7 + k] = ball.v[k]; brb[10 + k] = ball.w[k];
+    }
+    bf.has_bounce_now[e] = ball.bounce_now;   // cleared at the start of the step (:688), set by the aero pass (:730-734)
+    if (ball.bounce_now) {
+      bf.has_bounce[e] = 1;
+#pragma unroll
+      for (int k = 0; k < 3; k++) bf.bounce_pos[e * 3 + k] = ball.bpos[k];
+    }
+    bf.racket_hit_now[e] = ball.hits > 0;
+  }
 
   // ---- write back the simulation state (what gym.refresh_* exposes)
   float dq[3] = {0.f, 0.f, 0.f};
@@ -931,6 +1119,10 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
     cfo[0] = cf[0]; cfo[1] = cf[1]; cfo[2] = cf[2];
   }
 
+  if (cfg.task_mode == 1) {  // vid2player player env: post_physics_step (:785-797) only advances progress; obs / targets
+    if (lane == 0) bf.progress_buf[e] += 1;  // are produced by post_mvae_step, rewards / resets by the controller
+    continue;
+  }
   // ---- post-physics (:398-418)
   const int64_t progress = bf.progress_buf[e] + 1;
   const float ref_t = __fadd_rn(bf.ref_motion_times[e], __fmul_rn((float)cfg.control_freq_inv, cfg.sim_dt));
@@ -1193,7 +1385,7 @@ obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restri
 template <typename T>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 physics_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, int n, int n_steps,
-               T* root, T* dof_pos, T* dof_vel, const T* pd_tar, const T* ext, T* rb_out, T* contact_out) {
+               T* root, T* dof_pos, T* dof_vel, const T* pd_tar, const T* ext, T* rb_out, T* contact_out, T* ballio, int32_t* hits) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t mbar;
   load_blob(smem, gblob, blob_bytes, &mbar);
@@ -1223,8 +1415,16 @@ physics_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b20
     for (int k = 0; k < 3; k++) { q[k] = dof_pos[e * nd + lc.dof0 + k]; L.wt[k] = dof_vel[e * nd + lc.dof0 + k]; pdt[k] = pd_tar[e * nd + lc.dof0 + k]; }
     qexp(q, L.qj);
   }
+  Ball<T> ball;
+  ball_clear(ball);
+  const bool with_ball = pc.has_ball && ballio != nullptr;
+  PhysCfg<T> pcb = pc;
+  pcb.has_ball = with_ball;
+  if (with_ball && lane == BALL_LANE) {
+    for (int k = 0; k < 3; k++) { ball.p[k] = ballio[e * 13 + k]; ball.v[k] = ballio[e * 13 + 7 + k]; ball.w[k] = ballio[e * 13 + 10 + k]; }
+  }
   for (int s = 0; s < n_steps; s++) {
-    control_step<T>(B, verts, pc, lc, lane, L, pdt, eF, eT, cf);
+    control_step<T>(B, verts, pcb, lc, lane, L, pdt, eF, eT, cf, ball);
     if (s + 1 < n_steps && lc.dyn && lane > 0) {  // the state crosses control steps as exp-map coordinates
       T q[3];
       qlog(L.qj, q);
@@ -1247,6 +1447,10 @@ physics_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b20
     for (int k = 0; k < 4; k++) rb[3 + k] = L.Q[k];
     if (contact_out) for (int k = 0; k < 3; k++) contact_out[(e * nb + lane) * 3 + k] = cf[k];
   }
+  if (with_ball && lane == BALL_LANE) {
+    for (int k = 0; k < 3; k++) { ballio[e * 13 + k] = ball.p[k]; ballio[e * 13 + 7 + k] = ball.v[k]; ballio[e * 13 + 10 + k] = ball.w[k]; }
+    if (hits) hits[e] = ball.hits;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1264,6 +1468,8 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   if (model->max_depth >= MAX_LEVELS) return fail(-2, "b200env_create: kinematic tree too deep%s");
   if (model->vmax % 4) return fail(-2, "b200env_create: vmax must be a multiple of 4%s");
   if (num_envs < 1) return fail(-2, "b200env_create: num_envs must be positive%s");
+  if (cfg->has_ball && model->nb > BALL_LANE) return fail(-2, "b200env_create: has_ball needs nb <= 31 (lane 31 integrates the ball)%s");
+  if (cfg->has_ball && cfg->racket_body >= model->nb) return fail(-2, "b200env_create: racket_body out of range%s");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(-3, "b200env_create: no CUDA device - this library has no CPU fallback%s");
@@ -1324,6 +1530,10 @@ int b200env_bind(b200env_handle h, const b200_buffers_t* bufs) {
   for (size_t i = 0; i < sizeof(req) / sizeof(req[0]); i++)
     if (!req[i]) return fail(-1, "b200env_bind: a required buffer pointer is null%s");
   if (bufs->bodies_per_env < h->model.nb || bufs->actors_per_env < 1) return fail(-2, "b200env_bind: bad bodies/actors per env%s");
+  if (h->cfg.has_ball) {
+    if (bufs->actors_per_env < 2 || bufs->bodies_per_env < h->model.nb + 1) return fail(-2, "b200env_bind: has_ball needs 2 actors and nb+1 rigid-body rows per env%s");
+    if (!bufs->has_bounce || !bufs->has_bounce_now || !bufs->bounce_pos || !bufs->racket_hit_now) return fail(-1, "b200env_bind: ball flag buffers are null%s");
+  }
   if (((uintptr_t)bufs->t_rb_rot | (uintptr_t)bufs->p_rb_rot) & 15) return fail(-2, "b200env_bind: quaternion rows must be 16-byte aligned%s");
   h->bufs = *bufs;
   h->bound = true;
@@ -1347,7 +1557,7 @@ static size_t step_smem(const b200env* h) { return ((h->blob_bytes + 15) & ~(siz
 
 int b200env_step(b200env_handle h, const float* actions, void* stream) {
   if (!h || !actions) return fail(-1, "b200env_step: null argument%s");
-  if (!h->bound || !h->has_ml) return fail(-4, "b200env_step: bind buffers and a motion lib first%s");
+  if (!h->bound || (!h->has_ml && h->cfg.task_mode == 0)) return fail(-4, "b200env_step: bind buffers and a motion lib first%s");
   cudaSetDevice(h->device);
   const size_t smem = step_smem(h);
   if (h->step_grid == 0) {
@@ -1422,7 +1632,8 @@ int b200env_obs_imitation(b200env_handle h, int32_t n, const float* body_pos, co
 }
 
 int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_steps, void* root, void* dof_pos, void* dof_vel,
-                         const void* pd_tar, const void* ext_wrench, void* rb_out, void* contact_out, void* stream) {
+                         const void* pd_tar, const void* ext_wrench, void* rb_out, void* contact_out, void* ball, int32_t* ball_hits,
+                         void* stream) {
   if (!h || !root || !dof_pos || !dof_vel || !pd_tar || !rb_out) return fail(-1, "b200env_physics_only: null argument%s");
   if (n <= 0 || n_steps <= 0) return fail(-2, "b200env_physics_only: n and n_steps must be positive%s");
   cudaSetDevice(h->device);
@@ -1432,12 +1643,12 @@ int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_st
     CUDA_OK(cudaFuncSetAttribute(physics_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     physics_kernel<float><<<grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(
         (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, n, n_steps, (float*)root, (float*)dof_pos, (float*)dof_vel,
-        (const float*)pd_tar, (const float*)ext_wrench, (float*)rb_out, (float*)contact_out);
+        (const float*)pd_tar, (const float*)ext_wrench, (float*)rb_out, (float*)contact_out, (float*)ball, ball_hits);
   } else if (prec == 1) {
     CUDA_OK(cudaFuncSetAttribute(physics_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     physics_kernel<double><<<grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>(
         (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, n, n_steps, (double*)root, (double*)dof_pos, (double*)dof_vel,
-        (const double*)pd_tar, (const double*)ext_wrench, (double*)rb_out, (double*)contact_out);
+        (const double*)pd_tar, (const double*)ext_wrench, (double*)rb_out, (double*)contact_out, (double*)ball, ball_hits);
   } else {
     return fail(-2, "b200env_physics_only: prec must be 0 (float) or 1 (double)%s");
   }

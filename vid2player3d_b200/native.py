@@ -76,6 +76,8 @@ class Env:
         for name, _ in abi.Buffers._fields_:
             if name in ("actors_per_env", "bodies_per_env", "num_obs"):
                 continue
+            if name in ("has_bounce", "has_bounce_now", "bounce_pos", "racket_hit_now") and name not in tensors:
+                continue  # ball flag buffers: only for the vid2player player env
             t = tensors[name]
             assert t.is_cuda and t.is_contiguous(), name
             setattr(b, name, t.data_ptr())
@@ -120,14 +122,14 @@ class Env:
                                            C.c_int32(int(local_root_obs)), C.c_int32(int(root_height_obs)), _ptr(obs),
                                            _stream()))
 
-    def physics_only(self, root, dof_pos, dof_vel, pd_tar, ext_wrench, rb_out, contact_out, n_steps=1):
+    def physics_only(self, root, dof_pos, dof_vel, pd_tar, ext_wrench, rb_out, contact_out, n_steps=1, ball=None, ball_hits=None):
         import torch
         prec = {torch.float32: 0, torch.float64: 1}[root.dtype]
         for t in (dof_pos, dof_vel, pd_tar, rb_out):
             assert t.dtype == root.dtype and t.is_cuda and t.is_contiguous()
         _check(lib().b200env_physics_only(self._h, C.c_int32(prec), C.c_int32(int(root.shape[0])), C.c_int32(n_steps),
                                           _ptr(root), _ptr(dof_pos), _ptr(dof_vel), _ptr(pd_tar), _ptr(ext_wrench),
-                                          _ptr(rb_out), _ptr(contact_out), _stream()))
+                                          _ptr(rb_out), _ptr(contact_out), _ptr(ball), _ptr(ball_hits), _stream()))
 
     @property
     def launch_count(self):
