@@ -25,3 +25,17 @@ def lib_dict(flat, model, key_names=("R_Ankle", "L_Ankle", "L_Hand", "R_Hand")):
 def rand_quat(rng, *shape):
     q = rng.normal(size=shape + (4,))
     return q / np.linalg.norm(q, axis=-1, keepdims=True)
+
+
+def v2p_cfg(num_envs, substeps=6, reward_type="return_w_estimate", early_termination=False, **v2p_over):
+    """mirrors vid2player/cfg/controller/federer.yaml (single player)"""
+    v2p = dict(player="federer", grip="eastern", court_min=[-5, -16], court_max=[5, -10], racket_friction=0.8, ball_friction=0.2,
+               restitution=0.9, spin_scale=5, reward_weights={'pos': 0.1, 'ball_pos': 0.9},
+               reward_scales={'pos': 50, 'phase': 10, 'bounce_pos': 1, 'bounce_time': 0.5}, reward_type=reward_type,
+               obs_ball_traj_length=10, use_history_ball_obs=False, use_random_ball_target="continuous", vae_action_scale=1.5,
+               add_residual_dof="euler", residual_dof_scale=0.4, reset_reaction_nframes=70, random_walk_in_recovery=True)
+    v2p.update(v2p_over)
+    env = dict(numEnvs=num_envs, episodeLength=300, enableEarlyTermination=early_termination, is_train=True,
+               physics=dict(assetFileName="smpl_mesh_humanoid_federer.xml", substeps=substeps, residual_force_scale=31.85, plane_restitution=0.5),
+               vid2player=v2p)
+    return dict(name="PhysicsMVAEController", env=env, seed=10)

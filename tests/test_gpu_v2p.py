@@ -122,3 +122,68 @@ def test_controller_post_golden(rtype):
             got = t[k].cpu().numpy()
             want = g[gk]
             assert np.array_equal(got.astype(np.int64), want.astype(np.int64)), k
+
+
+def test_controller_end_to_end():
+    """config-3 style rollout (synthetic motion generator, zero-residual low-level policy): 150 high-level steps"""
+    from helpers import SIM_PARAMS, v2p_cfg
+    from oracle import ref_port_v2p as V
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    torch.manual_seed(0)
+    N = 256
+    env = PhysicsMVAEController(v2p_cfg(N), SIM_PARAMS, 1, "cuda", 0, True)
+    assert env.num_obs == 257 and env.num_actions == 35
+    env.reset()
+    task = env._physics_player.task
+    torch.cuda.synchronize()
+    assert torch.isfinite(env.obs_buf).all()
+    y0 = task._ball_pos[:, 1].clone()
+    assert (y0 > 11).all() and (task._ball_vel[:, 1] < -15).all()          # launched from the far side towards the player
+    bounced, resets, hits = 0, 0, 0
+    for step in range(150):
+        a = torch.clamp(torch.randn(N, 35, device=DEV), -5, 5)
+        env.step(a)
+        done = env.reset_buf.nonzero(as_tuple=False).flatten()
+        resets += len(done)
+        env.reset(done)                                                      # agent loop: env_reset(done_indices)
+        bounced = max(bounced, int(task._has_bounce.sum()))
+        hits += int(task._has_racket_ball_contact_now.sum())
+    torch.cuda.synchronize()
+    assert torch.isfinite(env.obs_buf).all() and torch.isfinite(env.rew_buf).all()
+    assert bounced > N // 4                       # balls reached the ground on the player's side
+    assert (env.progress_buf > 0).any() and (env._num_reset_reaction > 1).any()   # reaction tasks were re-armed (tar_time FSM)
+    close(env.obs_buf[:, 0:3], task._root_pos.cpu().numpy(), 0)
+    # the fused post kernel agrees with the numpy oracle on the live GPU state
+    g = lambda t: t.detach().cpu().numpy()  # noqa: E731
+    rbs = g(task._rigid_body_state.view(N, 26, 13))
+    obs = V.controller_obs(rbs[:, :25], g(task._root_pos), g(task._root_vel), g(task._racket_normal), g(env._ball_traj),
+                           g(env._target_bounce_pos), 10)
+    close(env.obs_buf, obs, 2e-6)
+    qn = task._rigid_body_rot.norm(dim=-1)
+    assert (qn - 1).abs().max() < 1e-4
+    assert (task._ball_pos[:, 2] >= 0.0319).all()  # never below the ground
+
+
+def test_racket_hit_is_detected():
+    """aim the ball at the racket face: the swept impact fires, the velocity-jump detector (substeps > 2) or the exact flag sees it"""
+    from helpers import SIM_PARAMS, v2p_cfg
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    torch.manual_seed(1)
+    N = 64
+    env = PhysicsMVAEController(v2p_cfg(N), SIM_PARAMS, 1, "cuda", 0, True)
+    env.reset()
+    task = env._physics_player.task
+    env.step(torch.zeros(N, 35, device=DEV))      # one step so the racket row comes from the simulated FK
+    n = task._racket_normal
+    centre = task._racket_pos + 0.02125 * n
+    ball = task._ball_root_states
+    ball[:, 0:3] = centre + 0.25 * n
+    ball[:, 7:10] = task._racket_vel - 25.0 * n
+    ball[:, 10:13] = 0
+    task._ball_vel.copy_(ball[:, 7:10])
+    v_before = ball[:, 7:10].clone()
+    env.step(torch.zeros(N, 35, device=DEV))
+    torch.cuda.synchronize()
+    assert task._racket_hit_now.float().mean() > 0.9
+    dv = (task._ball_root_states[:, 7:10] - v_before).norm(dim=-1)
+    assert (dv[task._racket_hit_now] > 20).all()   # restitution 0.9: the normal velocity is reversed

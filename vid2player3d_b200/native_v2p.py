@@ -30,15 +30,16 @@ def smpl_to_sim(root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, out, p
                                      _c(out["root_ang_vel"]), _c(out["dof_vel"]), _c(out["rb_pos"]), _c(out["rb_rot"]), _stream()))
 
 
-def ball_aero(ball_states, has_bounce, has_bounce_now, bounce_pos, force, substeps, spin_scale):
-    n = int(ball_states.shape[0])
-    _check(lib().b200v2p_ball_aero(C.c_int32(n), _c(ball_states), C.c_int32(ball_states.stride(0)), _c(has_bounce), _c(has_bounce_now),
+def ball_aero(ball_states, has_bounce, has_bounce_now, bounce_pos, force, substeps, spin_scale, stride=None):
+    n = int(has_bounce.shape[0])
+    _check(lib().b200v2p_ball_aero(C.c_int32(n), _c(ball_states), C.c_int32(stride or ball_states.stride(0)), _c(has_bounce), _c(has_bounce_now),
                                    _c(bounce_pos), _c(force), C.c_int32(substeps), C.c_float(spin_scale), _stream()))
 
 
-def ball_reset(env_ids, pool_index, pool, ball_states, ball_pos, ball_vel, has_bounce, bounce_pos, has_contact, traj):
+def ball_reset(env_ids, pool_index, pool, ball_states, ball_pos, ball_vel, has_bounce, bounce_pos, has_contact, traj, stride=None):
+    """ball_states: first ball row; `stride` floats between consecutive envs' ball rows (26 when the ball is actor 1 of 2)"""
     _check(lib().b200v2p_ball_reset(C.c_int32(int(env_ids.shape[0])), _c(env_ids), _c(pool_index), _c(pool), _c(ball_states),
-                                    C.c_int32(ball_states.stride(0)), _c(ball_pos), _c(ball_vel), _c(has_bounce), _c(bounce_pos),
+                                    C.c_int32(stride or ball_states.stride(0)), _c(ball_pos), _c(ball_vel), _c(has_bounce), _c(bounce_pos),
                                     _c(has_contact), _c(traj), _stream()))
 
 

@@ -1,0 +1,282 @@
+"""HumanoidSMPLIMMVAE mirror - the vid2player physics-player env
+(vid2player/env/tasks/humanoid_smpl_im_mvae.py): humanoid (+ welded racket) + tennis ball per env, targets from a
+kinematic motion generator (the MVAE player in the reference), 734-d imitation obs computed IN the env, and a `step`
+that runs PD actuation + articulated dynamics + ball flight / bounce / racket impact as one fused CUDA launch.
+
+Same attribute surface as the reference class for what the high-level controller reads
+(physics_mvae_controller.py:271-301,336-357): `_root_pos _root_vel _racket_pos _racket_vel _racket_normal _ball_pos
+_ball_vel _ball_vspin _ball_root_states _rigid_body_pos _rigid_body_rot _has_bounce _has_bounce_now _bounce_pos
+_has_racket_ball_contact(_now)`, methods `reset(h_ids, b_ids) -> traj`, `post_mvae_step()`, `step(actions)`.
+"""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .. import abi, ball as ball_data, model_compiler, native, native_v2p
+from .base_task import BaseTask
+
+SMPL_NAMES = ["Pelvis", "L_Hip", "R_Hip", "Torso", "L_Knee", "R_Knee", "Spine", "L_Ankle", "R_Ankle", "Chest", "L_Toe", "R_Toe",
+              "Neck", "L_Thorax", "R_Thorax", "Head", "L_Shoulder", "R_Shoulder", "L_Elbow", "R_Elbow", "L_Wrist", "R_Wrist",
+              "L_Hand", "R_Hand"]
+SMPL_PARENTS = [-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21]
+
+
+class HumanoidSMPLIMMVAE(BaseTask):
+    def __init__(self, cfg, sim_params, physics_engine, device_type, device_id, headless):
+        self.cfg = cfg
+        env = cfg["env"]
+        self.cfg_v2p = env["vid2player"]
+        self._is_train = env.get("is_train", True)
+        self.sim_dt = float(getattr(sim_params, "dt", 1.0 / 60.0) if not isinstance(sim_params, dict) else sim_params.get("dt", 1.0 / 60.0))
+        self.sim_substeps = int(cfg.get("sim", {}).get("substeps", 2))
+        self.residual_force_scale = env.get("residual_force_scale", 0.0)
+        self.residual_torque_scale = env.get("residual_torque_scale", self.residual_force_scale)
+        self.kp_scale = env.get("kp_scale", 1.0)
+        self.kd_scale = env.get("kd_scale", self.kp_scale)
+        self.no_scale_action = env.get("no_scale_action", True)
+        self.max_episode_length = env["episodeLength"]
+        self._local_root_obs = env.get("localRootObs", True)
+        self._root_height_obs = env.get("rootHeightObs", True)
+        if self.cfg_v2p.get("fix_head_orientation"):
+            raise NotImplementedError("fix_head_orientation (humanoid_smpl_im_mvae.py:605-634) is not on the kernel path yet")
+        if self.cfg_v2p.get("dual_mode"):
+            raise NotImplementedError("dual mode (humanoid_smpl_im_mvae_dual.py) is a later row (DESIGN.md 8)")
+        self._num_humanoid_bodies = 24
+        self._racket_body_id = self._racket_body_id_true = 24
+        self._racket_hand_body_id, self._racket_wrist_body_id, self._free_hand_body_id, self._head_body_id = 23, 22, 18, 13
+        cfg["device_type"], cfg["device_id"], cfg["headless"] = device_type, device_id, True
+        self.device = "cuda:" + str(device_id)
+
+        name = os.path.splitext(os.path.basename(env["asset"]["assetFileName"]))[0]
+        self._model = model_compiler.load_compiled(name)
+        self.body_names = [str(x) for x in self._model["body_names"]]
+        self.num_bodies = len(self.body_names)          # 25 = humanoid + Racket (the ball is a separate actor)
+        assert self.num_bodies == 25 and self.body_names[-1] == "Racket"
+        self.num_dof = self._num_dof = len(self._model["kp"])
+        self._num_actions = self.num_dof + (6 if self.residual_force_scale > 0 else 0)
+        self._dof_offsets = list(range(0, self.num_dof + 1, 3))
+        self._dof_obs_size = 23 * 6
+        self._num_obs = 1 + 23 * 3 + 24 * 6 + 24 * 6 + self.num_dof + 11 + self.num_dof + 24 * 9 + 11   # 734 (:1046-1132)
+        env["numObservations"], env["numActions"] = self._num_obs, self._num_actions
+        self._build_mujoco_smpl_transform()
+        super().__init__(cfg=cfg)
+        self.dt = self.control_freq_inv * self.sim_dt
+        self._terminate_buf = torch.ones(self.num_envs, device=self.device, dtype=torch.long)
+        self._mvae_player = None
+        self._controller = None
+        self._setup_tensors()
+
+    def _build_mujoco_smpl_transform(self):
+        """:218-237"""
+        mj = self.body_names[:24]
+        self._smpl_2_mujoco = [SMPL_NAMES.index(q) for q in mj]
+        self._mujoco_2_smpl = [mj.index(q) for q in SMPL_NAMES]
+
+    def get_obs_size(self):
+        return self._num_obs
+
+    def get_action_size(self):
+        return self._num_actions
+
+    def create_sim(self):
+        env = self.cfg["env"]
+        mass = float(self._model["mass"].sum())
+        pd_scale = mass / env.get("default_humanoid_mass", 90.0)
+        self._model_struct, self._verts = abi.pack_model(self._model, pd_scale * self.kp_scale, pd_scale * self.kd_scale)
+        v2p = self.cfg_v2p
+        ball = dict(spin_scale=v2p.get("spin_scale", 1.0))
+        rest = v2p.get("restitution", 0.9)
+        plane_rest = env.get("plane", {}).get("restitution", 0.0)
+        ball["ball_e_racket"] = rest                                            # racket & ball share `restitution` (:414,436)
+        ball["ball_e_ground"] = 0.5 * (rest + plane_rest)                        # PhysX average combine
+        ball["ball_mu_racket"] = 0.5 * (v2p.get("racket_friction", 0.8) + v2p.get("ball_friction", 0.2))
+        ball["ball_mu_ground"] = 0.5 * (env.get("plane", {}).get("dynamicFriction", 1.0) + v2p.get("ball_friction", 0.2))
+        self._cfg_struct = abi.make_cfg(
+            self._model, sim_dt=self.sim_dt, substeps=self.sim_substeps, control_freq_inv=env.get("controlFrequencyInv", 2),
+            pd_tar_lim=0.5 * np.pi, res_force_scale=self.residual_force_scale, res_torque_scale=self.residual_torque_scale,
+            max_episode_length=self.max_episode_length, enable_early_termination=False, contact_bodies=tuple(env.get("contactBodies", ())),
+            key_bodies=tuple(env.get("keyBodies", ())), friction_mu=env.get("plane", {}).get("dynamicFriction", 1.0),
+            task_mode=1, pd_mode=1, ball=ball, **self.cfg.get("b200_physics", {}))
+        self._env = native.Env(self._model_struct, self._verts, self._cfg_struct, self.num_envs, self.device_id)
+
+    def _setup_tensors(self):
+        """:135-189 - Isaac layouts: 2 actors / env (humanoid, ball), 26 rigid bodies / env (25 + ball)"""
+        N, dev, D = self.num_envs, self.device, self.num_dof
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float)  # noqa: E731
+        b = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bool)   # noqa: E731
+        self._root_states = f(N * 2, 13)
+        self._root_states[:, 6] = 1.0
+        rs = self._root_states.view(N, 2, 13)
+        self._humanoid_root_states, self._ball_root_states = rs[:, 0], rs[:, 1]
+        self._humanoid_root_states[:, 2] = 0.89
+        self._dof_state = f(N * D, 2)
+        self._dof_pos, self._dof_vel = self._dof_state.view(N, D, 2)[..., 0], self._dof_state.view(N, D, 2)[..., 1]
+        self._rigid_body_state = f(N * 26, 13)
+        self._rigid_body_state[:, 6] = 1.0
+        rbs = self._rigid_body_state.view(N, 26, 13)
+        self._rigid_body_pos, self._rigid_body_rot = rbs[:, :25, 0:3], rbs[:, :25, 3:7]
+        self._rigid_body_vel, self._rigid_body_ang_vel = rbs[:, :25, 7:10], rbs[:, :25, 10:13]
+        self._contact_force_tensor = f(N * 26, 3)
+        self._contact_forces = self._contact_force_tensor.view(N, 26, 3)
+        for k in ("_root_pos", "_root_vel", "_racket_pos", "_racket_vel", "_racket_normal", "_ball_pos", "_ball_vel", "_bounce_pos",
+                  "_target_root_pos", "_prev_target_root_pos", "_target_root_vel", "_target_root_ang_vel"):
+            setattr(self, k, f(N, 3))
+        self._ball_vspin = f(N)
+        for k in ("_has_bounce", "_has_bounce_now", "_has_racket_ball_contact", "_has_racket_ball_contact_now", "_racket_hit_now"):
+            setattr(self, k, b(N))
+        self._target_root_rot = f(N, 4)
+        self._target_dof_pos, self._target_dof_vel = f(N, D), f(N, D)
+        self._target_rb_pos, self._target_rb_rot = f(N, 24, 3), f(N, 24, 4)
+        self._target_rb_rot[..., 3] = 1.0
+        self._prev_target_dof_pos, self._prev_target_dof_vel = f(N, D), f(N, D)
+        self._prev_target_rb_pos, self._prev_target_rb_rot = f(N, 24, 3), f(N, 24, 4)
+        self._prev_target_rb_rot[..., 3] = 1.0
+        self._pd_target_dof_pos = f(N, D)
+        self.actions = f(N, self._num_actions)
+        self._reset_ref_motion_bodies = f(N, 11)
+        self._sub_rewards4, self._key_dummy = f(N, 4), f(N, max(1, self._cfg_struct.num_key), 3)
+        self._zero_ids = torch.zeros(N, device=dev, dtype=torch.long)
+        self._zero_t = f(N)
+        t = dict(root_states=self._root_states, dof_state=self._dof_state, rigid_body_state=self._rigid_body_state,
+                 contact_forces=self._contact_force_tensor, obs_buf=self.obs_buf, rew_buf=self.rew_buf, sub_rewards=self._sub_rewards4,
+                 reset_buf=self.reset_buf, progress_buf=self.progress_buf, terminate_buf=self._terminate_buf, motion_ids=self._zero_ids,
+                 ref_motion_times=self._zero_t, motion_bodies=self._reset_ref_motion_bodies, t_root_pos=self._target_root_pos,
+                 t_root_rot=self._target_root_rot, t_dof_pos=self._target_dof_pos, t_root_vel=self._target_root_vel,
+                 t_root_ang_vel=self._target_root_ang_vel, t_dof_vel=self._target_dof_vel, t_key_pos=self._key_dummy,
+                 t_rb_pos=self._target_rb_pos, t_rb_rot=self._target_rb_rot, p_dof_pos=self._prev_target_dof_pos,
+                 p_dof_vel=self._prev_target_dof_vel, p_rb_pos=self._prev_target_rb_pos, p_rb_rot=self._prev_target_rb_rot,
+                 pd_targets=self._pd_target_dof_pos, actions_used=self.actions, has_bounce=self._has_bounce,
+                 has_bounce_now=self._has_bounce_now, bounce_pos=self._bounce_pos, racket_hit_now=self._racket_hit_now)
+        self._env.bind(t, actors_per_env=2, bodies_per_env=26, num_obs=self.num_obs)
+        # SMPL kinematic constants for the FK targets (rest joints of the shipped skeleton, SMPL joint order)
+        pos = np.zeros((24, 3))
+        for i in range(24):
+            pos[i] = self._model["offset"][i] + (pos[self._model["parent"][i]] if self._model["parent"][i] >= 0 else 0)
+        rest = np.stack([pos[self.body_names.index(n)] for n in SMPL_NAMES]).astype(np.float32)
+        self._smpl = SimpleNamespace(joint_pos_bind=torch.tensor(rest, device=dev).unsqueeze(0).repeat(N, 1, 1),
+                                     parents=torch.tensor(SMPL_PARENTS, device=dev))
+        self._rest_t = torch.tensor(rest, device=dev).contiguous()
+        self._parents_t = torch.tensor(SMPL_PARENTS, device=dev, dtype=torch.int32)
+        self._s2m_t = torch.tensor(self._smpl_2_mujoco, device=dev, dtype=torch.int32)
+        self._tmp = dict(root_rot=f(N, 4), dof_pos=f(N, D), root_vel=f(N, 3), root_ang_vel=f(N, 3), dof_vel=f(N, D), rb_pos=f(N, 24, 3),
+                         rb_rot=f(N, 24, 4))
+        # incoming-ball pool (TennisBallGeneratorOffline, utils/tennis_ball.py:422-456)
+        pool = self.cfg_v2p.get("ball_pool", None)
+        if pool is None:
+            path = self.cfg_v2p.get("ball_traj_file")
+            pool = np.load(path) if path and os.path.exists(path) else ball_data.synthetic_pool(2048, seed=10, spin_scale=self.cfg_v2p.get("spin_scale", 1.0))
+        self._ball_pool = torch.tensor(np.asarray(pool, np.float32), device=dev).contiguous()
+        self._ball_traj_buf = f(N, 100, 3)
+        self.extras["terminate"] = self._terminate_buf
+
+    # ------------------------------------------------------------------ targets + obs (post_mvae_step :593-598)
+    def _smpl_to_sim_into(self, root_pos, joint_rotmat, out, prev_root_pos=None, prev_rb_rot=None):
+        native_v2p.smpl_to_sim(root_pos.contiguous(), joint_rotmat.contiguous(), self._rest_t, self._parents_t, self._s2m_t, self.dt, out,
+                               prev_root_pos=prev_root_pos, prev_rb_rot=prev_rb_rot)
+
+    def _set_target_motion_state(self):
+        """:600-661 (fix_head_orientation off): targets = FK of the motion generator's pose, velocities by finite difference
+        against the previous targets."""
+        root = self._mvae_player._root_pos.clone()
+        if self.cfg_v2p.get('add_residual_root') and self._controller is not None:
+            root += self._controller._res_root_actions
+        out = dict(root_rot=self._target_root_rot, dof_pos=self._target_dof_pos, root_vel=self._target_root_vel,
+                   root_ang_vel=self._target_root_ang_vel, dof_vel=self._target_dof_vel, rb_pos=self._target_rb_pos, rb_rot=self._target_rb_rot)
+        prev_rot = self._prev_target_rb_rot.clone()     # the kernel overwrites rb_rot rows it also reads as "previous"
+        self._smpl_to_sim_into(root, self._mvae_player._joint_rotmat, out, self._prev_target_root_pos, prev_rot)
+        self._target_root_pos.copy_(root)
+
+    def _compute_observations(self):
+        """:862-895 -> compute_humanoid_observations_imitation (:1046-1132) into obs_buf"""
+        rbs = self._rigid_body_state.view(self.num_envs, 26, 13)
+        c = lambda x: x.contiguous()  # noqa: E731
+        self._env.obs_imitation(c(rbs[:, :24, 0:3]), c(rbs[:, :24, 3:7]), self._target_rb_pos, self._target_rb_rot, c(self._dof_pos),
+                                c(self._dof_vel), self._target_dof_pos, c(rbs[:, :24, 7:10]), c(rbs[:, :24, 10:13]),
+                                self._reset_ref_motion_bodies, self._local_root_obs, self._root_height_obs, self.obs_buf)
+
+    def post_mvae_step(self):
+        self._set_target_motion_state()
+        self._compute_observations()
+
+    # ------------------------------------------------------------------ step (BaseTask.step :147-165 with :663-797)
+    def step(self, actions):
+        self._prev_target_root_pos.copy_(self._target_root_pos)          # _save_prev_target_motion_state (:741-750)
+        self._has_racket_ball_contact_now.zero_()                        # pre_physics_step :689
+        self._env.step(actions.to(self.device, dtype=torch.float).contiguous())
+        self._update_state_from_sim()
+
+    def _update_state_from_sim(self):
+        """:799-860"""
+        t = dict(has_contact=self._has_racket_ball_contact, has_contact_now=self._has_racket_ball_contact_now, root_pos=self._root_pos,
+                 root_vel=self._root_vel, racket_pos=self._racket_pos, racket_vel=self._racket_vel, racket_normal=self._racket_normal,
+                 ball_pos=self._ball_pos, ball_vel=self._ball_vel, ball_vspin=self._ball_vspin)
+        if self.sim_substeps <= 2:
+            # contact-force sensor path (:771-779): the step kernel reports the exact racket impact
+            now = self._racket_hit_now & ~self._has_racket_ball_contact
+            self._has_racket_ball_contact |= now
+            keep = self._has_racket_ball_contact.clone()
+            native_v2p.update_state(self.num_envs, 26, self._rigid_body_state, self._root_states, 26, self._root_states[1:], 26, t,
+                                    grip=self.cfg_v2p.get('grip', 'eastern'))
+            self._has_racket_ball_contact.copy_(keep)
+            self._has_racket_ball_contact_now.copy_(now)
+        else:
+            native_v2p.update_state(self.num_envs, 26, self._rigid_body_state, self._root_states, 26, self._root_states[1:], 26, t,
+                                    grip=self.cfg_v2p.get('grip', 'eastern'))
+
+    # ------------------------------------------------------------------ reset (:447-524, 562-581)
+    def reset(self, reset_humanoid_env_ids, reset_ball_env_ids):
+        traj = None
+        if len(reset_humanoid_env_ids) > 0:
+            self._reset_actors(reset_humanoid_env_ids)
+        if len(reset_ball_env_ids) > 0:
+            traj = self._reset_balls(reset_ball_env_ids)
+        if len(reset_humanoid_env_ids) > 0:
+            self.progress_buf[reset_humanoid_env_ids] = 0
+            self.reset_buf[reset_humanoid_env_ids] = 0
+            self._terminate_buf[reset_humanoid_env_ids] = 0
+        return traj
+
+    def _reset_actors(self, env_ids):
+        """:463-501: sim state <- FK of the motion generator's initial pose (zero velocities)"""
+        self._smpl_to_sim_into(self._mvae_player._root_pos.clone(), self._mvae_player._joint_rotmat, self._tmp)
+        root_pos = self._mvae_player._root_pos
+        rs, rbs = self._humanoid_root_states, self._rigid_body_state.view(self.num_envs, 26, 13)
+        rs[env_ids, 0:3], rs[env_ids, 3:7] = root_pos[env_ids], self._tmp["root_rot"][env_ids]
+        rs[env_ids, 7:13] = 0
+        rbs[env_ids, :24, 0:3], rbs[env_ids, :24, 3:7] = self._tmp["rb_pos"][env_ids], self._tmp["rb_rot"][env_ids]
+        rbs[env_ids, :25, 7:13] = 0
+        # welded racket row: parent (R_Wrist) pose + rotated offset, so the controller's first obs is consistent
+        wq, wp = self._tmp["rb_rot"][env_ids, 22], self._tmp["rb_pos"][env_ids, 22]
+        off = torch.tensor(self._model["offset"][24], device=self.device, dtype=torch.float).expand(len(env_ids), 3)
+        qv, qw = wq[:, :3], wq[:, 3:4]
+        tt = 2.0 * torch.cross(qv, off, dim=-1)
+        rbs[env_ids, 24, 0:3] = wp + off + qw * tt + torch.cross(qv, tt, dim=-1)
+        rbs[env_ids, 24, 3:7] = wq
+        self._dof_pos[env_ids] = self._tmp["dof_pos"][env_ids]
+        self._dof_vel[env_ids] = 0
+        self._prev_target_root_pos[env_ids] = root_pos[env_ids]
+        self._prev_target_rb_rot[env_ids] = self._tmp["rb_rot"][env_ids]
+        self._root_pos[env_ids] = root_pos[env_ids]
+        self._root_vel[env_ids] = 0
+        self._pd_target_dof_pos[env_ids] = self._tmp["dof_pos"][env_ids]
+        self._target_root_pos[env_ids] = root_pos[env_ids]
+
+    def _reset_balls(self, env_ids):
+        """:503-524 with the random branch of TennisBallGeneratorOffline.generate (tennis_ball.py:436-444)"""
+        P = self._ball_pool.shape[0]
+        idx = torch.randint(0, P, (len(env_ids),), device=self.device)
+        other = self._ball_pos[env_ids, 1] > 0
+        if other.any():
+            j = ((self._ball_pos[env_ids, 0] + 4) / 8 * P).long() + torch.randint(-1000, 1000, (len(env_ids),), device=self.device)
+            idx = torch.where(other, torch.clamp(j, 0, P - 1), idx)
+        native_v2p.ball_reset(env_ids.contiguous(), idx.contiguous(), self._ball_pool, self._root_states[1:], self._ball_pos, self._ball_vel,
+                              self._has_bounce, self._bounce_pos, self._has_racket_ball_contact, self._ball_traj_buf, stride=26)
+        rbs = self._rigid_body_state.view(self.num_envs, 26, 13)
+        rbs[env_ids, 25, 0:3] = self._ball_root_states[env_ids, 0:3]
+        rbs[env_ids, 25, 7:13] = self._ball_root_states[env_ids, 7:13]
+        return self._ball_traj_buf[env_ids]
+
+    def render_vis(self, init=False):
+        return

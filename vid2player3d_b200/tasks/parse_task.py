@@ -1,8 +1,10 @@
 """parse_task mirror (embodied_pose/utils/parse_task.py:19-42): same signature and error behaviour."""
 from .humanoid_smpl_im import HumanoidSMPLIM
+from .humanoid_smpl_im_mvae import HumanoidSMPLIMMVAE
+from .physics_mvae_controller import PhysicsMVAEController
 from .vec_task import VecTaskPythonWrapper
 
-TASKS = {"HumanoidSMPLIM": HumanoidSMPLIM}
+TASKS = {"HumanoidSMPLIM": HumanoidSMPLIM, "HumanoidSMPLIMMVAE": HumanoidSMPLIMMVAE, "PhysicsMVAEController": PhysicsMVAEController}
 
 
 def warn_task_name():

@@ -1,0 +1,352 @@
+"""PhysicsMVAEController mirror - the high-level vid2player env the PPO agent sees
+(vid2player/env/tasks/physics_mvae_controller.py).  It owns a kinematic motion generator (the MVAE player in the
+reference; PyTorch, stays PyTorch) and the physics player (low-level policy + HumanoidSMPLIMMVAE).  One `step`:
+
+  pre_physics_step  (:247-269)  split the action, advance the motion generator, task.post_mvae_step()  [1 FK + 1 obs launch]
+  physics_step      (:362-366)  low-level policy (PyTorch MLP) -> task.step                         [1 fused physics launch + 1]
+  post_physics_step (:441-452)  bounce / estimator bookkeeping, reward, obs, reset FSM               [1 fused launch]
+
+The MVAE checkpoints and the trained low-level policy are not released (README.md:13), so `SyntheticMotionPlayer` and a
+zero-residual policy stand in for tests and benchmarks; any object with the MVAEPlayer attribute surface
+(`_root_pos _joint_rotmat _phase_pred _swing_type _swing_type_cycle reset(ids) step(a, res)`) can be plugged in through
+cfg['env']['motion_player'], and any callable obs->action through cfg['env']['low_level_policy'].
+"""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .. import ball as ball_data, native_v2p
+from .humanoid_smpl_im_mvae import HumanoidSMPLIMMVAE
+
+BASE_ROTMAT = [[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]  # quaternion (.5,.5,.5,.5): SMPL y-up -> world z-up
+
+
+def _aa_to_rotmat(aa):
+    angle = aa.norm(dim=-1, keepdim=True).clamp_min(1e-8)
+    ax = aa / angle
+    x, y, z = ax.unbind(-1)
+    c, s = torch.cos(angle[..., 0]), torch.sin(angle[..., 0])
+    C = 1 - c
+    return torch.stack([c + x * x * C, x * y * C - z * s, x * z * C + y * s, y * x * C + z * s, c + y * y * C, y * z * C - x * s,
+                        z * x * C - y * s, z * y * C + x * s, c + z * z * C], -1).view(*aa.shape[:-1], 3, 3)
+
+
+class SyntheticMotionPlayer:
+    """Stand-in for MVAEPlayer (vid2player/players/mvae_player.py:184-431): a mean-reverting random walk of the 24 SMPL joint
+    rotations driven by the 32-d latent action, a slow planar root drift, a 2*pi/60 per step phase clock and a cycling swing type."""
+
+    def __init__(self, num_envs, device, seed=10, court_min=(-5.0, -16.0), court_max=(5.0, -10.0)):
+        self.N, self.device = num_envs, device
+        self.gen = torch.Generator(device=device).manual_seed(seed)
+        self._aa = torch.zeros(num_envs, 24, 3, device=device)
+        self._root_pos = torch.zeros(num_envs, 3, device=device)
+        self._joint_rotmat = torch.eye(3, device=device).repeat(num_envs, 24, 1, 1)
+        self._phase_pred = torch.zeros(num_envs, device=device)
+        self._swing_type = torch.zeros(num_envs, device=device, dtype=torch.long)
+        self._swing_type_cycle = -torch.ones(num_envs, device=device, dtype=torch.long)
+        self._heading = torch.zeros(num_envs, device=device)
+        self._base = torch.tensor(BASE_ROTMAT, device=device)
+        self._proj = torch.randn(32, 72, device=device, generator=self.gen) * 0.02
+        self.court_min, self.court_max = court_min, court_max
+
+    def _update_rotmat(self):
+        R = _aa_to_rotmat(self._aa)
+        c, s = torch.cos(self._heading), torch.sin(self._heading)
+        z, o = torch.zeros_like(c), torch.ones_like(c)
+        H = torch.stack([c, -s, z, s, c, z, z, z, o], -1).view(-1, 3, 3)
+        R[:, 0] = H @ self._base @ R[:, 0]
+        self._joint_rotmat = R.contiguous()
+
+    def reset(self, env_ids):
+        n = len(env_ids)
+        r = torch.rand(n, 3, device=self.device, generator=self.gen)
+        self._root_pos[env_ids, 0] = self.court_min[0] + 1 + r[:, 0] * (self.court_max[0] - self.court_min[0] - 2)
+        self._root_pos[env_ids, 1] = self.court_min[1] + 1 + r[:, 1] * (self.court_max[1] - self.court_min[1] - 2)
+        self._root_pos[env_ids, 2] = 0.95
+        self._aa[env_ids] = 0.05 * torch.randn(n, 24, 3, device=self.device, generator=self.gen)
+        self._heading[env_ids] = math.pi / 2 + 0.2 * (r[:, 2] - 0.5)       # facing +y (the net)
+        self._phase_pred[env_ids] = 0
+        self._swing_type[env_ids] = 0
+        self._swing_type_cycle[env_ids] = -1
+        self._update_rotmat()
+
+    def step(self, mvae_actions, res_dof_actions=None):
+        drive = (mvae_actions[:, :32] @ self._proj).view(self.N, 24, 3)
+        noise = 0.02 * torch.randn(self.N, 24, 3, device=self.device, generator=self.gen)
+        self._aa = 0.97 * self._aa + drive + noise
+        self._aa[:, 0] *= 0.3
+        if res_dof_actions is not None and res_dof_actions.numel():
+            self._aa[:, 21] += res_dof_actions[:, :3] * 0.1          # residual on the racket wrist (add_residual_dof)
+        self._root_pos[:, :2] += 0.01 * torch.randn(self.N, 2, device=self.device, generator=self.gen)
+        self._phase_pred = torch.remainder(self._phase_pred + 2 * math.pi / 60, 2 * math.pi)
+        wrap = self._phase_pred < 2 * math.pi / 60
+        self._swing_type = torch.where(wrap, (self._swing_type + 1) % 4, self._swing_type)
+        self._swing_type_cycle = torch.where(self._phase_pred > 2.0, self._swing_type, self._swing_type_cycle)
+        self._update_rotmat()
+
+
+class PhysicsMVAEController:
+    def __init__(self, cfg, sim_params, physics_engine, device_type, device_id, headless):
+        self.cfg = cfg
+        env = cfg["env"]
+        self.cfg_v2p = env["vid2player"]
+        cfg["device_type"], cfg["device_id"], cfg["headless"] = device_type, device_id, headless
+        if device_type not in ("cuda", "GPU"):
+            raise RuntimeError("the B200 environment runs on a CUDA device only (no CPU pipeline)")
+        self._max_episode_length = env["episodeLength"]
+        self._enable_early_termination = env.get("enableEarlyTermination", False)
+        self._is_train = env.get("is_train", True)
+        self.device_type, self.device_id = device_type, device_id
+        self.device = "cuda:" + str(device_id)
+        self.headless = headless
+        self.num_envs = N = env["numEnvs"]
+        self._sim_params, self._physics_engine = sim_params, physics_engine
+        self._num_mvae_action = 32
+        self._num_res_dof_action = 3 if self.cfg_v2p.get('add_residual_dof') else 0
+        self._num_actions = self._num_mvae_action + self._num_res_dof_action + (3 if self.cfg_v2p.get('add_residual_root') else 0)
+        self._obs_ball_traj_length = self.cfg_v2p.get('obs_ball_traj_length', 100)
+        self._num_actor_obs = 3 + 3 + 24 * 3 + 24 * 6 + 3
+        self._num_task_obs = 3 * self._obs_ball_traj_length + (2 if self.cfg_v2p.get('use_random_ball_target', False) else 0)
+        self.num_obs = env["numObservations"] = self._num_actor_obs + self._num_task_obs
+        self.num_actions = env["numActions"] = self._num_actions
+        self.num_states = env.get("numStates", 0)
+        self.create_sim()
+        dev = self.device
+        f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float)  # noqa: E731
+        b = lambda *s: torch.zeros(*s, device=dev, dtype=torch.bool)   # noqa: E731
+        i64 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.long)  # noqa: E731
+        self.obs_buf, self.rew_buf = f(N, self.num_obs), f(N)
+        self.states_buf = f(N, self.num_states)
+        self.reset_buf = torch.ones(N, device=dev, dtype=torch.long)
+        self.progress_buf = i64(N)
+        self._terminate_buf = torch.ones(N, device=dev, dtype=torch.long)
+        self.extras = {}
+        self._sub_rewards = f(N, 2)
+        self._has_init = False
+        self._num_humanoid_bodies, self._racket_body_id, self._head_body_id = 24, 24, 13
+        self._ball_traj = f(N, 100, 3)
+        self._bounce_in, self._est_bounce_in = b(N), b(N)
+        self._est_bounce_pos, self._est_bounce_time, self._est_max_height = f(N, 3), f(N), f(N)
+        self._court_min = torch.tensor(self.cfg_v2p.get('court_min', [-5, -16]), device=dev, dtype=torch.float)
+        self._court_max = torch.tensor(self.cfg_v2p.get('court_max', [5, -10]), device=dev, dtype=torch.float)
+        self._tar_time, self._tar_time_total, self._tar_action = i64(N), i64(N), i64(N)
+        self._target_bounce_pos = f(N, 3)
+        self._target_bounce_pos[:] = torch.tensor([0.0, 10.0, 0.0], device=dev)
+        self._target_bounce_min = torch.tensor([-3.0, 9.0, 0.0], device=dev)
+        self._target_bounce_max = torch.tensor([3.0, 11.0, 0.0], device=dev)
+        self._reset_reaction_buf = torch.ones(N, device=dev, dtype=torch.bool)
+        self._reset_recovery_buf = b(N)
+        self._num_reset_reaction, self._num_reset = i64(N), i64(N)
+        self._distance = f(N)
+        self._res_root_actions = f(N, 3)
+        self._mvae_actions_random = f(N, self._num_mvae_action)
+        # outgoing-ball estimator tables on the device (the reference keeps them on the CPU and syncs every contact step)
+        if not self.cfg_v2p.get('dual_mode'):
+            tabs = self.cfg_v2p.get('ball_out_tables', None)
+            if tabs is None:
+                tabs = ball_data.synthetic_out_tables(spin_scale=self.cfg_v2p.get('spin_scale', 1.0))
+            self._est_x = torch.tensor(tabs[0], device=dev).contiguous()
+            self._est_y = torch.tensor(tabs[1], device=dev).contiguous()
+            self._est_params = np.asarray(tabs[2], np.float64).reshape(-1)
+        else:
+            self._est_x = self._est_y = None
+            self._est_params = np.zeros(15)
+        scales = self.cfg_v2p.get('reward_scales', {})
+        weights = self.cfg_v2p.get('reward_weights', {})
+        rtype = self.cfg_v2p.get('reward_type', 'return')
+        self._sub_rewards_names = 'pos_reward' if rtype == 'reach' else 'pos_reward,ball_pos_reward'
+        self._post_cfg = dict(
+            n=N, bodies_per_env=26, ball_stride=26, racket_body=24, num_obs=self.num_obs, obs_traj_len=self._obs_ball_traj_length,
+            use_target=int(bool(self.cfg_v2p.get('use_random_ball_target', False))), reward_type=native_v2p.REWARD_TYPES[rtype],
+            early_termination=int(bool(self._enable_early_termination)), max_episode_length=int(self._max_episode_length),
+            est_nx=int(self._est_x.shape[1]) if self._est_x is not None else 0, est_ny=int(self._est_y.shape[1]) if self._est_y is not None else 0,
+            scale_pos=float(scales.get('pos', 5.0)), scale_phase=float(scales.get('phase', 10.0)),
+            scale_bounce_pos=float(scales.get('bounce_pos', 0.05)), scale_bounce_time=float(scales.get('bounce_time', 0.1)),
+            w_pos=float(weights.get('pos', 1.0 if rtype == 'reach' else 0.0)), w_ball_pos=float(weights.get('ball_pos', 0.0)),
+            court_min=self._court_min.tolist(), court_max=self._court_max.tolist(), est_params=self._est_params)
+
+    # ------------------------------------------------------------------ construction (:118-158)
+    def create_sim(self):
+        env = self.cfg["env"]
+        phys = env.get("physics", {})
+        pcfg = {"env": dict(numEnvs=self.num_envs, episodeLength=self._max_episode_length, controlFrequencyInv=env.get("controlFrequencyInv", 2),
+                            residual_force_scale=phys.get("residual_force_scale", 31.85), is_train=self._is_train,
+                            asset=dict(assetFileName=phys.get("assetFileName", "smpl_mesh_humanoid_federer.xml")),
+                            plane=dict(staticFriction=1.0, dynamicFriction=1.0, restitution=phys.get("plane_restitution", 0.0)),
+                            vid2player={k: v for k, v in self.cfg_v2p.items() if k != 'fix_head_orientation'},
+                            keyBodies=[], contactBodies=[]),
+                "sim": {"substeps": phys.get("substeps", 2)}, "b200_physics": self.cfg.get("b200_physics", {})}
+        task = HumanoidSMPLIMMVAE(pcfg, self._sim_params, self._physics_engine, "cuda", self.device_id, True)
+        policy = env.get("low_level_policy", None)
+        if policy is None:
+            zeros = torch.zeros(self.num_envs, task.num_actions, device=self.device)
+            policy = lambda obs: zeros  # noqa: E731  (zero residual: PD targets = kinematic targets)
+        self._low_level_policy = policy
+
+        def run_one_step():   # ImitatorPlayer.run_one_step (players/im_player.py:187-202)
+            obs = torch.clamp(task.obs_buf, -5.0, 5.0)
+            with torch.no_grad():
+                action = self._low_level_policy(obs)
+            task.step(torch.clamp(action, -1.0, 1.0))
+        self._physics_player = SimpleNamespace(task=task, run_one_step=run_one_step)
+        player = env.get("motion_player", None)
+        if player is None:
+            player = SyntheticMotionPlayer(self.num_envs, self.device, seed=self.cfg.get("seed", 10),
+                                           court_min=self.cfg_v2p.get('court_min', [-5, -16]), court_max=self.cfg_v2p.get('court_max', [5, -10]))
+        self._mvae_player = player
+        task._mvae_player = player
+        task._controller = self
+
+    def get_action_size(self):
+        return self._num_actions
+
+    def get_actor_obs_size(self):
+        return self._num_actor_obs
+
+    def get_task_obs_size(self):
+        return self._num_task_obs
+
+    # ------------------------------------------------------------------ reset (:167-245)
+    def reset(self, env_ids=None):
+        if env_ids is None:
+            if self._has_init and self.num_envs > 1:
+                return
+            env_ids = torch.arange(self.num_envs, device=self.device, dtype=torch.long)
+        self._reset_envs(env_ids)
+
+    def _reset_envs(self, env_ids):
+        task = self._physics_player.task
+        reaction_ids = self._reset_reaction_buf.nonzero(as_tuple=False).flatten()
+        recovery_ids = self._reset_recovery_buf.nonzero(as_tuple=False).flatten()
+        all_ids = (self._reset_reaction_buf | self._reset_recovery_buf).nonzero(as_tuple=False).flatten()
+        if len(env_ids) > 0:
+            self.progress_buf[env_ids] = 0
+            self.reset_buf[env_ids] = 0
+            self._terminate_buf[env_ids] = 0
+            self._reset_reaction_buf[env_ids] = False
+            self._reset_recovery_buf[env_ids] = False
+            self._num_reset_reaction[env_ids] = 0
+            self._distance[env_ids] = 0
+            self._mvae_player.reset(env_ids)
+            self._num_reset[env_ids] += 1
+        if len(env_ids) > 0 or len(reaction_ids) > 0:
+            traj = task.reset(env_ids, reaction_ids)
+            if traj is not None:
+                self._ball_traj[reaction_ids] = traj
+        if len(env_ids) > 0:
+            task._update_state_from_sim()
+        if len(recovery_ids) > 0:
+            self._tar_action[recovery_ids] = 0
+            task._has_bounce[recovery_ids] = False
+            task._bounce_pos[recovery_ids] = 0
+        if len(reaction_ids) > 0:
+            self._reset_reaction_tasks(reaction_ids)
+        if len(all_ids) > 0:
+            self._compute_observations()
+        self._has_init = True
+
+    def _reset_reaction_tasks(self, env_ids):
+        """:203-240"""
+        self._tar_time[env_ids] = 0
+        self._tar_action[env_ids] = 1
+        self._num_reset_reaction[env_ids] += 1
+        self._bounce_in[env_ids] = False
+        self._est_bounce_pos[env_ids] = 0
+        self._est_bounce_time[env_ids] = 0
+        self._est_bounce_in[env_ids] = False
+        self._est_max_height[env_ids] = 0
+        self._mvae_player._swing_type_cycle[env_ids] = -1
+        self._tar_time_total[env_ids] = self.cfg_v2p.get('reset_reaction_nframes', 70) + torch.randint(-5, 5, (len(env_ids),), device=self.device)
+        mode = self.cfg_v2p.get('use_random_ball_target')
+        if mode == 'continuous':
+            self._target_bounce_pos[env_ids] = torch.rand((3,), device=self.device) * (self._target_bounce_max - self._target_bounce_min) + self._target_bounce_min
+        elif mode:
+            seed = torch.rand(len(env_ids), device=self.device)
+            x = torch.where(seed < 0.33, -3.0, torch.where(seed > 0.67, 3.0, 0.0))
+            self._target_bounce_pos[env_ids, 0], self._target_bounce_pos[env_ids, 1], self._target_bounce_pos[env_ids, 2] = x, 10.0, 0.0
+
+    # ------------------------------------------------------------------ step (:247-269, 362-366, 441-459)
+    def pre_physics_step(self, actions):
+        self._actions = actions.clone()
+        na = self._num_mvae_action
+        self._mvae_actions = actions[:, :na].clone() * self.cfg_v2p.get('vae_action_scale', 1.0)
+        if self.cfg_v2p.get('random_walk_in_recovery', False):
+            in_rec = self._tar_action == 0
+            rnd = torch.clamp(torch.randn_like(self._mvae_actions), -5, 5)
+            self._mvae_actions = torch.where(in_rec[:, None], rnd, self._mvae_actions)
+        self._res_dof_actions = torch.empty(0, device=self.device)
+        if self.cfg_v2p.get('add_residual_dof'):
+            self._res_dof_actions = actions[:, na:na + self._num_res_dof_action].clone() * self.cfg_v2p.get('residual_dof_scale', 0.1)
+        self._mvae_player.step(self._mvae_actions, self._res_dof_actions)
+        if self.cfg_v2p.get('add_residual_root'):
+            o = na + self._num_res_dof_action
+            self._res_root_actions = actions[:, o:o + 3].clone() * self.cfg_v2p.get('residual_root_scale', 0.02)
+        self._physics_player.task.post_mvae_step()
+
+    def physics_step(self):
+        self._physics_player.run_one_step()
+        self._ball_traj = self._ball_traj.roll(-1, dims=1)
+        self._ball_traj[:, -1] = 0
+
+    def post_physics_step(self):
+        self._tar_time += 1
+        self.progress_buf += 1
+        self._compute_post()
+        self.extras["terminate"] = self._terminate_buf
+        self.extras["sub_rewards"] = self._sub_rewards
+        self.extras["sub_rewards_names"] = self._sub_rewards_names
+
+    def _tensors(self):
+        t, p = self._physics_player.task, self._mvae_player
+        return dict(rigid_body_state=t._rigid_body_state, ball_states=t._root_states[1:], root_pos=t._root_pos, root_vel=t._root_vel,
+                    racket_pos=t._racket_pos, racket_normal=t._racket_normal, ball_pos=t._ball_pos, has_contact=t._has_racket_ball_contact,
+                    has_contact_now=t._has_racket_ball_contact_now, has_bounce=t._has_bounce, has_bounce_now=t._has_bounce_now,
+                    bounce_pos=t._bounce_pos, ball_traj=self._ball_traj.contiguous(), target_bounce_pos=self._target_bounce_pos,
+                    phase=p._phase_pred.contiguous(), swing_type=p._swing_type.contiguous(), swing_type_cycle=p._swing_type_cycle.contiguous(),
+                    tar_action=self._tar_action, tar_time=self._tar_time, tar_time_total=self._tar_time_total, progress_buf=self.progress_buf,
+                    est_x=self._est_x, est_y=self._est_y, bounce_in=self._bounce_in, est_bounce_in=self._est_bounce_in,
+                    reset_reaction=self._reset_reaction_buf, reset_recovery=self._reset_recovery_buf, est_bounce_pos=self._est_bounce_pos,
+                    est_bounce_time=self._est_bounce_time, est_max_height=self._est_max_height, distance=self._distance, obs_buf=self.obs_buf,
+                    rew_buf=self.rew_buf, sub_rewards=self._sub_rewards, reset_buf=self.reset_buf, terminate_buf=self._terminate_buf)
+
+    def _compute_post(self):
+        """_update_state + _compute_reward + _compute_observations + _compute_reset as ONE launch (:271-436)"""
+        self._ball_traj = self._ball_traj.contiguous()
+        native_v2p.controller_post(self._post_cfg, self._tensors())
+        t = self._physics_player.task
+        self._root_pos, self._root_vel, self._racket_pos, self._racket_vel, self._racket_normal = t._root_pos, t._root_vel, t._racket_pos, t._racket_vel, t._racket_normal
+        self._ball_pos, self._ball_vel, self._ball_vspin = t._ball_pos, t._ball_vel, t._ball_vspin
+        self._phase_pred = self._mvae_player._phase_pred
+
+    def _compute_observations(self, env_ids=None):
+        """used on reset: the observation rows are refreshed by the same kernel (reward / reset flags of a reset env are rewritten
+        by the next step before anyone reads them)"""
+        keep = (self.rew_buf.clone(), self.reset_buf.clone(), self._terminate_buf.clone(), self._reset_reaction_buf.clone(),
+                self._reset_recovery_buf.clone(), self._distance.clone(), self._sub_rewards.clone())
+        self._compute_post()
+        self.rew_buf.copy_(keep[0]); self.reset_buf.copy_(keep[1]); self._terminate_buf.copy_(keep[2])
+        self._reset_reaction_buf.copy_(keep[3]); self._reset_recovery_buf.copy_(keep[4]); self._distance.copy_(keep[5])
+        self._sub_rewards.copy_(keep[6])
+
+    def step(self, actions):
+        self.pre_physics_step(actions.to(self.device, dtype=torch.float))
+        self.physics_step()
+        self.post_physics_step()
+
+    def get_aux_losses(self, model_res_dict):
+        """:461-472 (autograd-carrying, PyTorch)"""
+        specs = self.cfg_v2p.get('aux_loss_specs', dict())
+        dof_res = model_res_dict['mus'][:, self._num_mvae_action:self._num_mvae_action + self._num_res_dof_action]
+        loss = (dof_res ** 2).sum(dim=-1).mean()
+        return {'aux_dof_res_loss': loss}, {'aux_dof_res_loss': specs.get('dof_res', 0) * loss}
+
+    def register_model(self, model):
+        self.model = model
+
+    def pre_epoch(self, epoch):
+        self._epoch_num = epoch
+
+    def render_vis(self):
+        return
