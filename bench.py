@@ -32,12 +32,13 @@ HORIZON = 32
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=640)
+    p.add_argument("--steps", type=int, default=1600)
     p.add_argument("--warmup", type=int, default=64)
     p.add_argument("--envs", type=int, default=8192, help="envs per GPU")
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--cpu-sample-envs", type=int, default=1024)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-federer", action="store_true", help="skip the secondary vid2player federer (config 3) measurement")
     return p.parse_args()
 
 
@@ -100,6 +101,48 @@ def build_workload(envs, device_index, seed):
     torch.manual_seed(seed)
     task = HumanoidSMPLIM(im_cfg(envs, flat, episodeLength=300), SIM_PARAMS, 1, "cuda", device_index, True)
     return model, flat, task, VecTaskPythonWrapper(task, task.device, 5.0, 1.0)
+
+
+def federer_workload(envs, device_index, steps=96, warmup=16):
+    """BASELINE config 3 (vid2player federer single-player): 8192 envs, humanoid + racket + ball, substeps 6, episode 300,
+    reward return_w_estimate with synthetic estimator tables, synthetic motion generator in place of the (unreleased) MVAE and a
+    zero-residual low-level policy.  Returns high-level env-steps/s and the per-launch split."""
+    import torch
+    from helpers import SIM_PARAMS, v2p_cfg
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    torch.manual_seed(10)
+    env = PhysicsMVAEController(v2p_cfg(envs), SIM_PARAMS, 1, "cuda", device_index, True)
+    dev = env.device
+    env.reset()
+    acts = [torch.clamp(torch.randn(envs, env.num_actions, device=dev), -5, 5) for _ in range(8)]
+
+    def run(n):
+        for i in range(n):
+            env.step(acts[i % 8])
+            env.reset(env.reset_buf.nonzero(as_tuple=False).flatten())
+    run(warmup)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = env._physics_player.task._env.launch_count
+    e0.record()
+    run(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    # physics launch alone
+    task = env._physics_player.task
+    a75 = torch.zeros(envs, task.num_actions, device=dev)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(20):
+        task._env.step(a75)
+    p1.record()
+    torch.cuda.synchronize()
+    return {"env_steps_per_s": envs * steps / (ms * 1e-3), "ms_per_step": ms / steps, "physics_kernel_ms": p0.elapsed_time(p1) / 20,
+            "steps": steps, "step_kernel_launches": task._env.launch_count - l0 - 20,
+            "workload": f"vid2player federer single: {envs} envs, humanoid+racket+ball, substeps 6 (12 per step), return_w_estimate, "
+                        "synthetic motion generator + zero-residual low-level policy (MVAE / policy checkpoints unreleased)",
+            "roofline_frac_hbm": 10900 * envs / (p0.elapsed_time(p1) / 20 * 1e-3) / 1e9 / peaks()[0]}
 
 
 def cpu_reference_arm(model, flat, sample_envs, steps, warmup, seed=7):
@@ -293,6 +336,11 @@ def main():
                      "peak_source": peak_src,
                      "note": "latency / FP32-issue bound along the 9-level kinematic chain, not HBM bound (DESIGN.md 5)"},
     }
+    if not args.no_federer and world == 1:
+        try:
+            out["config"]["federer"] = federer_workload(N, local_rank)
+        except Exception as ex:  # secondary measurement must never break the contract line
+            out["config"]["federer"] = {"error": repr(ex)[:200]}
     if not args.no_cpu_baseline:
         from oracle import physics_ref
         physics_ref.build()
