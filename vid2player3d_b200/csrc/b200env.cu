@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/b200env.h"
@@ -32,15 +33,23 @@
 #define SCRATCH_FLOATS 320
 #define MAX_CHILD 4
 #define MAX_LEVELS 16
+#ifndef POST_SYNC
+#define POST_SYNC 1
+#endif
 #ifndef STEP_MIN_CTAS
 #define STEP_MIN_CTAS 2
 #endif
 
 // ------------------------------------------------------------------------------------------
 // device-side constant block: header | tree tables | hull vertices   (all 16-byte multiples)
+#define PK_SLOTS 8
 struct DevTree {
   int32_t child[B200_MAX_BODIES][MAX_CHILD];  // dynamic (non-welded) children, -1 padded
   int32_t maxch[MAX_LEVELS];                  // max #children over the bodies of each depth
+  // packed (4 envs / warp) variant: the s-th body of every tree depth, and each body's rank among its siblings
+  int32_t lvl_all[MAX_LEVELS][PK_SLOTS];      // all bodies of the depth (kinematics), -1 padded
+  int32_t lvl_dyn[MAX_LEVELS][PK_SLOTS];      // non-welded bodies of the depth (dynamics), -1 padded
+  int32_t child_rank[B200_MAX_BODIES];
 };
 struct DevBlob {
   b200_model_t m;
@@ -64,6 +73,8 @@ struct b200env {
   unsigned long long* d_ticket;
   unsigned long long ticket_base;
   int step_grid;
+  int packed;        // 1: 4-envs-per-warp kernels (packed.cuh); 0: lane-per-body kernels.  env B200ENV_KERNEL=lane|packed
+  int packed_ok;     // tree fits the packed layout (<= 8 bodies per depth, <= 25 bodies)
   int64_t launches;
 };
 
@@ -235,9 +246,14 @@ template <typename T> __device__ __forceinline__ PhysCfg<T> make_phys_cfg(const 
 
 // forward kinematics, level by level: fills Q,p,w,v (world) of every lane from the root state and
 // the joint state.  Optionally returns r = p - p_parent and the velocity-product terms zeta.
+#ifndef LEVEL_SYNC
+#define LEVEL_SYNC 0  // 1: CTA barrier at every tree level (keeps all warps of the CTA in the same code region: I-cache sharing)
+#endif
 template <typename T, bool WITH_ZETA>
-__device__ __forceinline__ void fk_pass(const b200_model_t& M, const LaneConst& lc, int lane, Lane<T>& L, T* r, T* zeta) {
+__device__ __forceinline__ void fk_pass(const b200_model_t& M, const LaneConst& lc, int lane, Lane<T>& L, T* r, T* zeta,
+                                        bool lsync = false) {
   for (int d = 1; d <= M.max_depth; d++) {
+    if (LEVEL_SYNC && lsync) __syncthreads();
     T pQ[4], pp[3], pw[3], pv[3];
 #pragma unroll
     for (int k = 0; k < 4; k++) pQ[k] = shfl(L.Q[k], lc.par);
@@ -378,10 +394,10 @@ __device__ __forceinline__ void ball_substep(const PhysCfg<T>& c, Ball<T>& B, bo
 template <typename T>
 __device__ __forceinline__ void substep(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c,
                                         const LaneConst& lc, int lane, Lane<T>& L, const T* pdtar, bool ext_on,
-                                        const T* extF, const T* extT, T* cf, Ball<T>& ball) {
+                                        const T* extF, const T* extT, T* cf, Ball<T>& ball, bool lsync = false) {
   const b200_model_t& M = B.m;
   T r[3] = {0, 0, 0}, zeta[6] = {0, 0, 0, 0, 0, 0};
-  fk_pass<T, true>(M, lc, lane, L, r, zeta);
+  fk_pass<T, true>(M, lc, lane, L, r, zeta, lsync);
 
   // articulated inertia  [[A, Bm], [Bm^T, C]]  (A, C symmetric) and bias (bn, bf)
   T A[6] = {0, 0, 0, 0, 0, 0}, Bm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, C[6] = {0, 0, 0, 0, 0, 0};
@@ -520,6 +536,7 @@ __device__ __forceinline__ void substep(const DevBlob& B, const float* __restric
   // ---- backward pass: leaves -> root, one tree level at a time
   T Dinv[6] = {0, 0, 0, 0, 0, 0};
   for (int d = M.max_depth; d >= 1; d--) {
+    if (LEVEL_SYNC && lsync) __syncthreads();
     T out[27];
 #pragma unroll
     for (int k = 0; k < 27; k++) out[k] = T(0);
@@ -661,6 +678,7 @@ __device__ __forceinline__ void substep(const DevBlob& B, const float* __restric
 
   // ---- forward pass: root -> leaves
   for (int d = 1; d <= M.max_depth; d++) {
+    if (LEVEL_SYNC && lsync) __syncthreads();
     T pa[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) pa[k] = shfl(acc[k], lc.par);
@@ -743,12 +761,14 @@ __device__ __forceinline__ void control_step(const DevBlob& B, const float* vert
     }
     for (int k = 0; k < c.substeps; k++) {
       if (cta_sync) __syncthreads();
-      substep<T>(B, verts, c, lc, lane, L, pdtar, s == 0, extF, extT, cf, ball);
+      substep<T>(B, verts, c, lc, lane, L, pdtar, s == 0, extF, extT, cf, ball, cta_sync);
     }
   }
   T dummy[3], dz[6];
   fk_pass<T, false>(B.m, lc, lane, L, dummy, dz);
 }
+
+#include "packed.cuh"
 
 // ------------------------------------------------------------------------------------------
 // TMA bulk load of the constant block into shared memory (one elected thread issues it)
@@ -965,40 +985,13 @@ __device__ __forceinline__ void store_obs_raw(float* obs, int nb, int nd, int sh
   if (lane < shape_dim) obs[o + lane] = motion_bodies[lane];
 }
 
-// ------------------------------------------------------------------------------------------
-// fused env step:  pre-physics -> substeps -> MoCap target -> obs -> reward -> reset
-// Persistent: the grid is sized to the resident CTA slots; each warp pulls env indices from a global ticket
-// counter (monotonic across launches: ticket - base = env index) so the tail is balanced per env, not per CTA.
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, STEP_MIN_CTAS)
-step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
-            b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs, unsigned long long* __restrict__ ticket,
-            unsigned long long base) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ __align__(8) uint64_t mbar;
-  load_blob(smem, gblob, blob_bytes, &mbar);
-  const DevBlob& B = *reinterpret_cast<const DevBlob*>(smem);
-  const b200_model_t& M = B.m;
-  const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
-  float* scratch_all = reinterpret_cast<float*>(smem + ((blob_bytes + 15) & ~15u));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* scr = scratch_all + warp * SCRATCH_FLOATS;
-  const b200_cfg_t& cfg = *gcfg;
-  const LaneConst lc = lane_const(M, lane);
+// ---- per-env prologue (lane = body): state rows -> registers, PD targets, residual wrench, previous targets, ball
+__device__ __forceinline__ void step_prologue(const b200_buffers_t& bf, const b200_motion_lib_t& ml, const b200_cfg_t& cfg,
+                                              const b200_model_t& M, const LaneConst& lc, int lane, float* scr,
+                                              const float* __restrict__ actions, int64_t e, Lane<float>& L, float* pdtar, float* extF,
+                                              float* extT, Ball<float>& ball) {
   const int nd = M.nd, na = nd + 6;
-  const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
-
- __shared__ unsigned long long s_tk;
- for (;;) {
-  // one ticket per CTA = a batch of WARPS_PER_CTA consecutive envs (CTA-uniform control flow -> barriers are legal)
-  __syncthreads();
-  if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)WARPS_PER_CTA) - base;
-  __syncthreads();
-  const int64_t e0 = (int64_t)s_tk;
-  if (e0 >= num_envs) break;
-  const bool full_batch = e0 + WARPS_PER_CTA <= num_envs;
-  const int64_t e = e0 + warp;
-  if (!full_batch && e >= num_envs) continue;  // ragged last batch: no CTA barriers below (full_batch is CTA-uniform)
-
+  __syncwarp();  // scratch reuse when called back to back
   // ---- load state rows (coalesced) into the warp's scratch
   const float* rs = bf.root_states + e * bf.actors_per_env * 13;
   const float* ds = bf.dof_state + e * nd * 2;
@@ -1008,18 +1001,17 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
   for (int k = lane; k < nd * 2; k += 32) scr[16 + k] = ds[k];
   for (int k = lane; k < na; k += 32) {
     float a = (was_reset && cfg.task_mode == 0) ? 0.0f : ac[k];  // actions[self.reset_buf == 1] = 0   (:126, embodied_pose only)
-    scr[16 + 2 * B200_MAX_DOF + k] = a;
+    scr[16 + 2 * nd + k] = a;
     bf.actions_used[e * na + k] = a;
   }
   __syncwarp();
 
-  Lane<float> L;
 #pragma unroll
   for (int k = 0; k < 4; k++) { L.Q[k] = 0.f; L.qj[k] = 0.f; }
   L.Q[3] = 1.f; L.qj[3] = 1.f;
 #pragma unroll
   for (int k = 0; k < 3; k++) { L.p[k] = 0.f; L.w[k] = 0.f; L.v[k] = 0.f; L.wt[k] = 0.f; }
-  float pdtar[3] = {0.f, 0.f, 0.f};
+  pdtar[0] = pdtar[1] = pdtar[2] = 0.f;
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 3; k++) { L.p[k] = scr[k]; L.v[k] = scr[7 + k]; L.w[k] = scr[10 + k]; }
@@ -1033,7 +1025,7 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
     for (int k = 0; k < 3; k++) {
       q[k] = scr[16 + (lc.dof0 + k) * 2];
       L.wt[k] = scr[16 + (lc.dof0 + k) * 2 + 1];
-      float a = scr[16 + 2 * B200_MAX_DOF + lc.dof0 + k];
+      float a = scr[16 + 2 * nd + lc.dof0 + k];
       // _action_to_pd_targets: clamp(action, q -+ lim) (humanoid_smpl_im.py:391-396) or, for the vid2player player env,
       // clamp(target_dof + action, q -+ lim) (humanoid_smpl_im_mvae.py:693-709, no_scale_action / pd_target_base target_pos)
       if (cfg.pd_mode == 1) a += bf.t_dof_pos[e * nd + lc.dof0 + k];
@@ -1043,7 +1035,7 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
     qexp(q, L.qj);
   }
   // residual root wrench rotated by the heading of the de-based root rotation (:141-154)
-  float extF[3] = {0.f, 0.f, 0.f}, extT[3] = {0.f, 0.f, 0.f};
+  extF[0] = extF[1] = extF[2] = 0.f; extT[0] = extT[1] = extT[2] = 0.f;
   if (lane == 0 && cfg.res_force_scale > 0.f) {
     const float* rq = bf.rigid_body_state + e * bf.bodies_per_env * 13 + 3;  // self._rigid_body_rot[:, 0]
     float q0[4] = {rq[0], rq[1], rq[2], rq[3]}, qb[4], hq[4];
@@ -1052,8 +1044,8 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
     float f[3], t[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      f[k] = scr[16 + 2 * B200_MAX_DOF + nd + k] * cfg.res_force_scale;
-      t[k] = scr[16 + 2 * B200_MAX_DOF + nd + 3 + k] * cfg.res_torque_scale;
+      f[k] = scr[16 + 2 * nd + nd + k] * cfg.res_force_scale;
+      t[k] = scr[16 + 2 * nd + nd + 3 + k] * cfg.res_torque_scale;
     }
     ref_quat_rotate(hq, f, extF);
     ref_quat_rotate(hq, t, extT);
@@ -1067,9 +1059,6 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
   }
   __syncwarp();  // the reward below reads p_* rows written by other lanes of this warp
 
-  // ---- physics
-  float cf[3];
-  Ball<float> ball;
   ball_clear(ball);
   float* ball_row = bf.root_states + (e * bf.actors_per_env + 1) * 13;  // actor 1 = ball (only dereferenced if has_ball)
   if (cfg.has_ball && lane == BALL_LANE) {
@@ -1077,22 +1066,39 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
     for (int k = 0; k < 3; k++) { ball.p[k] = ball_row[k]; ball.v[k] = ball_row[7 + k]; ball.w[k] = ball_row[10 + k]; }
     ball.has_bounce = bf.has_bounce[e];
   }
-  control_step<float>(B, verts, pc, lc, lane, L, pdtar, extF, extT, cf, ball, STEP_SYNC && full_batch);
-  if (cfg.has_ball && lane == BALL_LANE) {
-    float* brb = bf.rigid_body_state + (e * bf.bodies_per_env + bf.bodies_per_env - 1) * 13;  // last rigid-body row = ball
+}
+
+// ball rows + flags of env e (called by the lane that carries the ball)
+__device__ __forceinline__ void ball_writeback(const b200_buffers_t& bf, int64_t e, const Ball<float>& ball) {
+  float* ball_row = bf.root_states + (e * bf.actors_per_env + 1) * 13;
+  float* brb = bf.rigid_body_state + (e * bf.bodies_per_env + bf.bodies_per_env - 1) * 13;  // last rigid-body row = ball
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      ball_row[k] = ball.p[k]; ball_row[7 + k] = ball.v[k]; ball_row[10 + k] = ball.w[k];
-      brb[k] = ball.p[k]; brb[7 + k] = ball.v[k]; brb[10 + k] = ball.w[k];
-    }
-    bf.has_bounce_now[e] = ball.bounce_now;   // cleared at the start of the step (:688), set by the aero pass (:730-734)
-    if (ball.bounce_now) {
-      bf.has_bounce[e] = 1;
-#pragma unroll
-      for (int k = 0; k < 3; k++) bf.bounce_pos[e * 3 + k] = ball.bpos[k];
-    }
-    bf.racket_hit_now[e] = ball.hits > 0;
+  for (int k = 0; k < 3; k++) {
+    ball_row[k] = ball.p[k]; ball_row[7 + k] = ball.v[k]; ball_row[10 + k] = ball.w[k];
+    brb[k] = ball.p[k]; brb[7 + k] = ball.v[k]; brb[10 + k] = ball.w[k];
   }
+  bf.has_bounce_now[e] = ball.bounce_now;   // cleared at the start of the step (:688), set by the aero pass (:730-734)
+  if (ball.bounce_now) {
+    bf.has_bounce[e] = 1;
+#pragma unroll
+    for (int k = 0; k < 3; k++) bf.bounce_pos[e * 3 + k] = ball.bpos[k];
+  }
+  bf.racket_hit_now[e] = ball.hits > 0;
+}
+__device__ __forceinline__ void ball_load(const b200_buffers_t& bf, int64_t e, Ball<float>& ball) {
+  const float* ball_row = bf.root_states + (e * bf.actors_per_env + 1) * 13;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { ball.p[k] = ball_row[k]; ball.v[k] = ball_row[7 + k]; ball.w[k] = ball_row[10 + k]; }
+  ball.has_bounce = bf.has_bounce[e];
+}
+
+// ---- per-env epilogue (lane = body): write back the state, ball flags, MoCap target, obs, reward, reset
+__device__ __forceinline__ void step_epilogue(const b200_buffers_t& bf, const b200_motion_lib_t& ml, const b200_cfg_t& cfg,
+                                              const b200_model_t& M, const LaneConst& lc, int lane, int64_t e, const Lane<float>& L,
+                                              const float* cf, const Ball<float>& ball, bool ball_in_lane31 = true) {
+  const int nd = M.nd;
+  const bool was_reset = bf.reset_buf[e] == 1;  // still the pre-step value: reset_buf is only written at the end of this function
+  if (cfg.has_ball && lane == BALL_LANE && ball_in_lane31) ball_writeback(bf, e, ball);
 
   // ---- write back the simulation state (what gym.refresh_* exposes)
   float dq[3] = {0.f, 0.f, 0.f};
@@ -1121,7 +1127,7 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
 
   if (cfg.task_mode == 1) {  // vid2player player env: post_physics_step (:785-797) only advances progress; obs / targets
     if (lane == 0) bf.progress_buf[e] += 1;  // are produced by post_mvae_step, rewards / resets by the controller
-    continue;
+    return;
   }
   // ---- post-physics (:398-418)
   const int64_t progress = bf.progress_buf[e] + 1;
@@ -1190,7 +1196,247 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
     bf.reset_buf[e] = reset;
     bf.terminate_buf[e] = terminated;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused env step:  pre-physics -> substeps -> MoCap target -> obs -> reward -> reset
+// Persistent: the grid is sized to the resident CTA slots; each warp pulls env indices from a global ticket
+// counter (monotonic across launches: ticket - base = env index) so the tail is balanced per env, not per CTA.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, STEP_MIN_CTAS)
+step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
+            b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs, unsigned long long* __restrict__ ticket,
+            unsigned long long base) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  load_blob(smem, gblob, blob_bytes, &mbar);
+  const DevBlob& B = *reinterpret_cast<const DevBlob*>(smem);
+  const b200_model_t& M = B.m;
+  const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
+  float* scratch_all = reinterpret_cast<float*>(smem + ((blob_bytes + 15) & ~15u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* scr = scratch_all + warp * SCRATCH_FLOATS;
+  const b200_cfg_t& cfg = *gcfg;
+  const LaneConst lc = lane_const(M, lane);
+  const int nd = M.nd, na = nd + 6;
+  const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
+
+ __shared__ unsigned long long s_tk;
+ for (;;) {
+  // one ticket per CTA = a batch of WARPS_PER_CTA consecutive envs (CTA-uniform control flow -> barriers are legal)
+  __syncthreads();
+  if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)WARPS_PER_CTA) - base;
+  __syncthreads();
+  const int64_t e0 = (int64_t)s_tk;
+  if (e0 >= num_envs) break;
+  const bool full_batch = e0 + WARPS_PER_CTA <= num_envs;
+  const int64_t e = e0 + warp;
+  if (!full_batch && e >= num_envs) continue;  // ragged last batch: no CTA barriers below (full_batch is CTA-uniform)
+
+  Lane<float> L;
+  float pdtar[3], extF[3], extT[3], cf[3];
+  Ball<float> ball;
+  step_prologue(bf, ml, cfg, M, lc, lane, scr, actions, e, L, pdtar, extF, extT, ball);
+  control_step<float>(B, verts, pc, lc, lane, L, pdtar, extF, extT, cf, ball, STEP_SYNC && full_batch);
+#if POST_SYNC
+  if (full_batch) __syncthreads();  // re-align the CTA's warps: the once-per-step epilogue is straight-line code, fetched once per CTA
+#endif
+  step_epilogue(bf, ml, cfg, M, lc, lane, e, L, cf, ball);
  }  // ticket loop
+}
+
+
+// ------------------------------------------------------------------------------------------
+// packed variant of the fused step: 4 envs per warp in the physics (packed.cuh), lane-per-body prologue / epilogue per env
+#define PK_WARPS 7          // 7 warps x 4 envs x 7.2 KB records + 20 KB constants = 227 KB of shared memory: one CTA per SM
+#define PK_SCRATCH 232
+template <typename T> __device__ __forceinline__ void pk_store_state(T* env, const LaneConst& lc, int lane, const Lane<T>& L, const T* pd,
+                                                                     const T* extF, const T* extT) {
+  if (lc.active) {
+    T* rec = env + lane * REC;
+    if (lane == 0) { st(rec + R_Q, L.Q, 4); st(rec + R_P, L.p, 3); st(rec + R_W, L.w, 3); st(rec + R_V, L.v, 3); }
+    else if (lc.dyn) { st(rec + R_QJ, L.qj, 4); st(rec + R_WT, L.wt, 3); st(rec + R_PD, pd, 3); }
+  }
+  if (lane == 0) {
+    T* ext = env + ENV_EXT;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { ext[k] = extF[k]; ext[3 + k] = extT[k]; ext[6 + k] = T(0); ext[9 + k] = T(0); }
+  }
+}
+template <typename T> __device__ __forceinline__ void pk_load_state(const T* env, const LaneConst& lc, int lane, Lane<T>& L, T* cf) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) { L.Q[k] = 0; L.qj[k] = 0; }
+  L.Q[3] = 1; L.qj[3] = 1;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { L.p[k] = 0; L.w[k] = 0; L.v[k] = 0; L.wt[k] = 0; cf[k] = 0; }
+  if (lc.active) {
+    const T* rec = env + lane * REC;
+    ld(rec + R_Q, L.Q, 4); ld(rec + R_P, L.p, 3); ld(rec + R_W, L.w, 3); ld(rec + R_V, L.v, 3);
+    if (lc.dyn) {
+      ld(rec + R_CF, cf, 3);
+      if (lane > 0) { ld(rec + R_QJ, L.qj, 4); ld(rec + R_WT, L.wt, 3); }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PK_WARPS * 32, 1)
+step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
+                   b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs, unsigned long long* __restrict__ ticket,
+                   unsigned long long base) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  load_blob(smem, gblob, blob_bytes, &mbar);
+  const DevBlob& B = *reinterpret_cast<const DevBlob*>(smem);
+  const b200_model_t& M = B.m;
+  const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
+  float* scratch_all = reinterpret_cast<float*>(smem + ((blob_bytes + 15) & ~15u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* scr = scratch_all + warp * PK_SCRATCH;
+  float* wrec = scratch_all + PK_WARPS * PK_SCRATCH + (size_t)warp * EPW * ENV_STRIDE;
+  const b200_cfg_t& cfg = *gcfg;
+  const LaneConst lc = lane_const(M, lane);
+  const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
+  const int g = lane >> 3, s = lane & 7;
+  constexpr int BATCH = PK_WARPS * EPW;
+
+  __shared__ unsigned long long s_tk;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)BATCH) - base;
+    __syncthreads();
+    const int64_t e0 = (int64_t)s_tk;
+    if (e0 >= num_envs) break;
+    const bool full_batch = e0 + BATCH <= num_envs;
+    const int64_t eb = e0 + (int64_t)warp * EPW;
+    if (!full_batch && eb >= num_envs) continue;
+
+    for (int k = 0; k < EPW; k++) {
+      const int64_t e = eb + k;
+      if (e >= num_envs) break;
+      Lane<float> L;
+      float pdtar[3], extF[3], extT[3];
+      Ball<float> dummy;
+      step_prologue(bf, ml, cfg, M, lc, lane, scr, actions, e, L, pdtar, extF, extT, dummy);
+      pk_store_state<float>(wrec + k * ENV_STRIDE, lc, lane, L, pdtar, extF, extT);
+    }
+    __syncwarp();
+    const bool valid = eb + g < num_envs;
+    Ball<float> ball;
+    ball_clear(ball);
+    if (cfg.has_ball && valid && s == BALL_SLOT) ball_load(bf, eb + g, ball);
+    control_step_packed<float>(B, verts, pc, wrec, lane, valid, ball, STEP_SYNC && full_batch);
+#if POST_SYNC
+    if (full_batch) __syncthreads();
+#endif
+    if (cfg.has_ball && valid && s == BALL_SLOT) ball_writeback(bf, eb + g, ball);
+    for (int k = 0; k < EPW; k++) {
+      const int64_t e = eb + k;
+      if (e >= num_envs) break;
+      Lane<float> L;
+      float cf[3];
+      pk_load_state<float>(wrec + k * ENV_STRIDE, lc, lane, L, cf);
+      step_epilogue(bf, ml, cfg, M, lc, lane, e, L, cf, ball, false);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+physics_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, int n, int n_steps,
+                      T* root, T* dof_pos, T* dof_vel, const T* pd_tar, const T* ext, T* rb_out, T* contact_out, T* ballio, int32_t* hits) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  load_blob(smem, gblob, blob_bytes, &mbar);
+  const DevBlob& B = *reinterpret_cast<const DevBlob*>(smem);
+  const b200_model_t& M = B.m;
+  const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  T* wrec = reinterpret_cast<T*>(smem + ((blob_bytes + 15) & ~15u)) + (size_t)warp * EPW * ENV_STRIDE;
+  const int64_t eb = ((int64_t)blockIdx.x * WARPS + warp) * EPW;
+  if (eb >= n) return;
+  const LaneConst lc = lane_const(M, lane);
+  const int nb = M.nb, nd = M.nd;
+  PhysCfg<T> pc = make_phys_cfg<T>(*gcfg);
+  const bool with_ball = pc.has_ball && ballio != nullptr;
+  pc.has_ball = with_ball;
+  const int g = lane >> 3, s = lane & 7;
+  for (int k = 0; k < EPW; k++) {
+    const int64_t e = eb + k;
+    if (e >= n) break;
+    Lane<T> L;
+    for (int j = 0; j < 4; j++) { L.Q[j] = 0; L.qj[j] = 0; }
+    L.Q[3] = 1; L.qj[3] = 1;
+    for (int j = 0; j < 3; j++) { L.p[j] = 0; L.w[j] = 0; L.v[j] = 0; L.wt[j] = 0; }
+    T pdt[3] = {0, 0, 0}, eF[3] = {0, 0, 0}, eT[3] = {0, 0, 0};
+    if (lane == 0) {
+      const T* rs = root + e * 13;
+      for (int j = 0; j < 3; j++) { L.p[j] = rs[j]; L.v[j] = rs[7 + j]; L.w[j] = rs[10 + j]; }
+      for (int j = 0; j < 4; j++) L.Q[j] = rs[3 + j];
+      qnormalize(L.Q);
+      if (ext) for (int j = 0; j < 3; j++) { eF[j] = ext[e * 6 + j]; eT[j] = ext[e * 6 + 3 + j]; }
+    }
+    if (lc.dyn && lane > 0) {
+      T q[3];
+      for (int j = 0; j < 3; j++) { q[j] = dof_pos[e * nd + lc.dof0 + j]; L.wt[j] = dof_vel[e * nd + lc.dof0 + j]; pdt[j] = pd_tar[e * nd + lc.dof0 + j]; }
+      qexp(q, L.qj);
+    }
+    pk_store_state<T>(wrec + k * ENV_STRIDE, lc, lane, L, pdt, eF, eT);
+  }
+  __syncwarp();
+  const bool valid = eb + g < n;
+  Ball<T> ball;
+  ball_clear(ball);
+  if (with_ball && valid && s == BALL_SLOT) {
+    const int64_t e = eb + g;
+    for (int j = 0; j < 3; j++) { ball.p[j] = ballio[e * 13 + j]; ball.v[j] = ballio[e * 13 + 7 + j]; ball.w[j] = ballio[e * 13 + 10 + j]; }
+  }
+  for (int st_ = 0; st_ < n_steps; st_++) {
+    control_step_packed<T>(B, verts, pc, wrec, lane, valid, ball, false);
+    if (st_ + 1 < n_steps) {  // the state crosses control steps as exp-map coordinates
+      for (int k = 0; k < EPW; k++) {
+        if (eb + k >= n) break;
+        if (lc.dyn && lane > 0) {
+          T* rec = wrec + k * ENV_STRIDE + lane * REC;
+          T qj[4], q[3];
+          ld(rec + R_QJ, qj, 4);
+          qlog(qj, q);
+          qexp(q, qj);
+          st(rec + R_QJ, qj, 4);
+        }
+        if (lane == 0) {  // the racket reaction does not carry over a control step in the lane kernel either (ball.rF is per substep)
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int k = 0; k < EPW; k++) {
+    const int64_t e = eb + k;
+    if (e >= n) break;
+    Lane<T> L;
+    T cf[3];
+    pk_load_state<T>(wrec + k * ENV_STRIDE, lc, lane, L, cf);
+    if (lane == 0) {
+      T* rs = root + e * 13;
+      for (int j = 0; j < 3; j++) { rs[j] = L.p[j]; rs[7 + j] = L.v[j]; rs[10 + j] = L.w[j]; }
+      for (int j = 0; j < 4; j++) rs[3 + j] = L.Q[j];
+    }
+    if (lc.dyn && lane > 0) {
+      T q[3];
+      qlog(L.qj, q);
+      for (int j = 0; j < 3; j++) { dof_pos[e * nd + lc.dof0 + j] = q[j]; dof_vel[e * nd + lc.dof0 + j] = L.wt[j]; }
+    }
+    if (lc.active) {
+      T* rb = rb_out + (e * nb + lane) * 13;
+      for (int j = 0; j < 3; j++) { rb[j] = L.p[j]; rb[7 + j] = L.v[j]; rb[10 + j] = L.w[j]; }
+      for (int j = 0; j < 4; j++) rb[3 + j] = L.Q[j];
+      if (contact_out) for (int j = 0; j < 3; j++) contact_out[(e * nb + lane) * 3 + j] = cf[j];
+    }
+  }
+  if (with_ball && valid && s == BALL_SLOT) {
+    const int64_t e = eb + g;
+    for (int j = 0; j < 3; j++) { ballio[e * 13 + j] = ball.p[j]; ballio[e * 13 + 7 + j] = ball.v[j]; ballio[e * 13 + 10 + j] = ball.w[j]; }
+    if (hits) hits[e] = ball.hits;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1496,6 +1742,23 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   }
   for (int b = 0; b < model->nb; b++)
     if (cnt[b] > hb.t.maxch[model->depth[b]]) hb.t.maxch[model->depth[b]] = cnt[b];
+  h->packed_ok = model->nb <= B200_MAX_BODIES_PK;
+  {
+    int na[MAX_LEVELS] = {0}, ndy[MAX_LEVELS] = {0}, rk[B200_MAX_BODIES] = {0};
+    for (int d = 0; d < MAX_LEVELS; d++)
+      for (int k = 0; k < PK_SLOTS; k++) { hb.t.lvl_all[d][k] = -1; hb.t.lvl_dyn[d][k] = -1; }
+    for (int b = 0; b < model->nb; b++) {
+      const int d = model->depth[b];
+      if (na[d] >= PK_SLOTS) { h->packed_ok = 0; continue; }
+      hb.t.lvl_all[d][na[d]++] = b;
+      if (!model->fixed[b]) {
+        hb.t.lvl_dyn[d][ndy[d]++] = b;
+        if (b > 0) hb.t.child_rank[b] = rk[model->parent[b]]++;
+      }
+    }
+  }
+  const char* kv = getenv("B200ENV_KERNEL");
+  h->packed = h->packed_ok && !(kv && strcmp(kv, "lane") == 0);
   const size_t vbytes = (size_t)model->nb * model->vmax * 3 * sizeof(float);
   h->blob_bytes = sizeof(DevBlob) + ((vbytes + 15) & ~(size_t)15);
   CUDA_OK(cudaMalloc(&h->d_blob, h->blob_bytes));
@@ -1559,6 +1822,26 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
   if (!h || !actions) return fail(-1, "b200env_step: null argument%s");
   if (!h->bound || (!h->has_ml && h->cfg.task_mode == 0)) return fail(-4, "b200env_step: bind buffers and a motion lib first%s");
   cudaSetDevice(h->device);
+  if (h->packed) {
+    const size_t psmem = ((h->blob_bytes + 15) & ~(size_t)15) + PK_WARPS * PK_SCRATCH * sizeof(float) + (size_t)PK_WARPS * EPW * ENV_STRIDE * sizeof(float);
+    const int batch = PK_WARPS * EPW;
+    const int need = (h->num_envs + batch - 1) / batch;
+    if (h->step_grid == 0) {
+      CUDA_OK(cudaFuncSetAttribute(step_kernel_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      int per_sm = 0, sms = 0;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed, PK_WARPS * 32, psmem));
+      CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+      h->step_grid = per_sm * sms < need ? per_sm * sms : need;
+      if (h->step_grid < 1) return fail(-5, "b200env_step: step_kernel_packed does not fit on this device%s");
+    }
+    step_kernel_packed<<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes,
+                                                                                      h->d_cfg, h->bufs, h->ml, actions, h->num_envs,
+                                                                                      h->d_ticket, h->ticket_base);
+    CUDA_OK(cudaGetLastError());
+    h->ticket_base += (unsigned long long)(need + h->step_grid) * batch;
+    h->launches++;
+    return 0;
+  }
   const size_t smem = step_smem(h);
   if (h->step_grid == 0) {
     CUDA_OK(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1637,6 +1920,29 @@ int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_st
   if (!h || !root || !dof_pos || !dof_vel || !pd_tar || !rb_out) return fail(-1, "b200env_physics_only: null argument%s");
   if (n <= 0 || n_steps <= 0) return fail(-2, "b200env_physics_only: n and n_steps must be positive%s");
   cudaSetDevice(h->device);
+  if (h->packed) {
+    const size_t bsm = (h->blob_bytes + 15) & ~(size_t)15;
+    if (prec == 0) {
+      constexpr int W = 4;
+      const size_t sm = bsm + (size_t)W * EPW * ENV_STRIDE * sizeof(float);
+      CUDA_OK(cudaFuncSetAttribute(physics_kernel_packed<float, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      physics_kernel_packed<float, W><<<(n + W * EPW - 1) / (W * EPW), W * 32, sm, (cudaStream_t)stream>>>(
+          (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, n, n_steps, (float*)root, (float*)dof_pos, (float*)dof_vel,
+          (const float*)pd_tar, (const float*)ext_wrench, (float*)rb_out, (float*)contact_out, (float*)ball, ball_hits);
+    } else if (prec == 1) {
+      constexpr int W = 2;
+      const size_t sm = bsm + (size_t)W * EPW * ENV_STRIDE * sizeof(double);
+      CUDA_OK(cudaFuncSetAttribute(physics_kernel_packed<double, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      physics_kernel_packed<double, W><<<(n + W * EPW - 1) / (W * EPW), W * 32, sm, (cudaStream_t)stream>>>(
+          (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, n, n_steps, (double*)root, (double*)dof_pos, (double*)dof_vel,
+          (const double*)pd_tar, (const double*)ext_wrench, (double*)rb_out, (double*)contact_out, (double*)ball, ball_hits);
+    } else {
+      return fail(-2, "b200env_physics_only: prec must be 0 (float) or 1 (double)%s");
+    }
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+  }
   const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   const size_t smem = (h->blob_bytes + 15) & ~(size_t)15;
   if (prec == 0) {

@@ -1,0 +1,436 @@
+// packed.cuh - "4 envs per warp" variant of the articulated control step (included by b200env.cu).
+//
+// Why: ncu of the lane-per-body kernel (profiles/r1a_step_kernel_ncu.md) shows the three tree passes running with 2-8 of 32
+// lanes active - at most 5 bodies share a tree depth.  Here a warp owns EPW = 4 envs; lane = (env slot g = lane/8, body slot
+// s = lane%8) and at every tree level slot s handles the s-th body of that depth (host table DevTree::lvl_*), so the level
+// loops run on up to 20 lanes and are executed once for 4 envs.  Bodies change lanes from level to level, therefore the
+// per-body quantities live in per-warp shared-memory records instead of registers; parent<->child exchange is a plain
+// shared-memory read (no shuffles).  The arithmetic is the same as substep<T>() - same model, same oracle.
+#pragma once
+
+#define EPW 4     // envs per warp
+#define SLOTS 8   // lanes per env
+// record layout (element offsets); REC is odd -> consecutive bodies fall on different banks
+enum {
+  R_Q = 0, R_P = 4, R_W = 7, R_V = 10,   // world pose / velocity of the body origin
+  R_QJ = 13, R_WT = 17, R_PD = 20,      // joint state + PD target
+  R_R = 23, R_ZETA = 26,                // p - p_parent, velocity-product terms
+  R_A = 32, R_BM = 38, R_C = 47, R_BN = 53, R_BF = 56,  // articulated inertia + bias (27 contiguous); R_BN.. reused as (alpha,a) after the backward pass
+  R_E = 59,                             // E_w, then D^-1
+  R_U = 65, R_CF = 68, REC = 71
+};
+#define R_ACC R_BN
+#define ENV_EXT (B200_MAX_BODIES_PK * REC)  // per-env extras: extF[3] extT[3] reactF[3] reactX[3]
+#define B200_MAX_BODIES_PK 25
+#define ENV_STRIDE (ENV_EXT + 14)           // odd (1789): the 4 env groups of a warp start on different banks
+
+template <typename T> __device__ __forceinline__ void ld(const T* p, T* r, int n) {
+#pragma unroll
+  for (int k = 0; k < 27; k++) if (k < n) r[k] = p[k];
+}
+template <typename T> __device__ __forceinline__ void st(T* p, const T* r, int n) {
+#pragma unroll
+  for (int k = 0; k < 27; k++) if (k < n) p[k] = r[k];
+}
+
+// kinematics of one body from its parent's record
+template <typename T, bool WITH_ZETA>
+__device__ __forceinline__ void pk_fk(const b200_model_t& M, T* env, int b) {
+  T* rec = env + b * REC;
+  const T* par = env + M.parent[b] * REC;
+  T pQ[4], pp[3], pw[3], pv[3];
+  ld(par + R_Q, pQ, 4); ld(par + R_P, pp, 3); ld(par + R_W, pw, 3); ld(par + R_V, pv, 3);
+  T off[3] = {T(M.offset[b][0]), T(M.offset[b][1]), T(M.offset[b][2])}, rr[3], wxr[3], p[3], v[3];
+  qrot(pQ, off, rr);
+  cross3(pw, rr, wxr);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { p[k] = pp[k] + rr[k]; v[k] = pv[k] + wxr[k]; }
+  st(rec + R_P, p, 3); st(rec + R_V, v, 3);
+  if (WITH_ZETA) st(rec + R_R, rr, 3);
+  if (M.fixed[b]) {
+    st(rec + R_Q, pQ, 4); st(rec + R_W, pw, 3);
+  } else {
+    T qj[4], wt[3], Q[4], wj[3], w[3];
+    ld(rec + R_QJ, qj, 4); ld(rec + R_WT, wt, 3);
+    qmul(pQ, qj, Q);
+    qnormalize(Q);
+    qrot(Q, wt, wj);
+#pragma unroll
+    for (int k = 0; k < 3; k++) w[k] = pw[k] + wj[k];
+    st(rec + R_Q, Q, 4); st(rec + R_W, w, 3);
+    if (WITH_ZETA) {
+      T z[6];
+      cross3(pw, wj, z); cross3(pw, wxr, z + 3);
+      st(rec + R_ZETA, z, 6);
+    }
+  }
+}
+
+// rigid-body inertia + bias + external / contact / joint-drive terms of one dynamic body -> record
+template <typename T>
+__device__ __forceinline__ void pk_body(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c, T* env, int b, bool ext_on) {
+  const b200_model_t& M = B.m;
+  T* rec = env + b * REC;
+  T Q[4], p[3], w[3], v[3], R[9];
+  ld(rec + R_Q, Q, 4); ld(rec + R_P, p, 3); ld(rec + R_W, w, 3); ld(rec + R_V, v, 3);
+  qmat(Q, R);
+  T A[6], Bm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, C[6] = {0, 0, 0, 0, 0, 0}, bn[3], bf[3], cf[3] = {0, 0, 0};
+  const T ms = T(M.mass[b]);
+  T cl[3] = {T(M.com[b][0]), T(M.com[b][1]), T(M.com[b][2])}, cw[3];
+  mv3(R, cl, cw);
+  {
+    T Ib[6], F[9], RF[9];
+#pragma unroll
+    for (int k = 0; k < 6; k++) Ib[k] = T(M.inertia[b][k]);
+    sym_full(Ib, F);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) RF[i * 3 + j] = R[i * 3] * F[j] + R[i * 3 + 1] * F[3 + j] + R[i * 3 + 2] * F[6 + j];
+    const T c2 = cw[0] * cw[0] + cw[1] * cw[1] + cw[2] * cw[2];
+    A[0] = RF[0] * R[0] + RF[1] * R[1] + RF[2] * R[2] + ms * (c2 - cw[0] * cw[0]);
+    A[1] = RF[3] * R[3] + RF[4] * R[4] + RF[5] * R[5] + ms * (c2 - cw[1] * cw[1]);
+    A[2] = RF[6] * R[6] + RF[7] * R[7] + RF[8] * R[8] + ms * (c2 - cw[2] * cw[2]);
+    A[3] = RF[0] * R[3] + RF[1] * R[4] + RF[2] * R[5] - ms * cw[0] * cw[1];
+    A[4] = RF[0] * R[6] + RF[1] * R[7] + RF[2] * R[8] - ms * cw[0] * cw[2];
+    A[5] = RF[3] * R[6] + RF[4] * R[7] + RF[5] * R[8] - ms * cw[1] * cw[2];
+  }
+  Bm[1] = -ms * cw[2]; Bm[2] = ms * cw[1];
+  Bm[3] = ms * cw[2]; Bm[5] = -ms * cw[0];
+  Bm[6] = -ms * cw[1]; Bm[7] = ms * cw[0];
+  C[0] = C[1] = C[2] = ms;
+  {
+    T Iw[3], t1[3], t2[3];
+    sym_mv(A, w, Iw);
+    cross3(w, Iw, bn);
+    cross3(w, cw, t1);
+    cross3(w, t1, t2);
+    bn[0] -= ms * cw[1] * c.gz;
+    bn[1] += ms * cw[0] * c.gz;
+    bf[0] = ms * t2[0]; bf[1] = ms * t2[1]; bf[2] = ms * t2[2] - ms * c.gz;
+  }
+  const T* ext = env + ENV_EXT;
+  if (c.has_ball && c.racket_body >= 0 && b == M.parent[c.racket_body]) {  // reaction of the last racket impact on the wrist
+    T rF[3] = {ext[6], ext[7], ext[8]}, dx[3] = {ext[9] - p[0], ext[10] - p[1], ext[11] - p[2]}, t[3];
+    cross3(dx, rF, t);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { bn[k] -= t[k]; bf[k] -= rF[k]; }
+  }
+  if (b == 0 && ext_on) {
+    T eF[3] = {ext[0], ext[1], ext[2]}, cxF[3];
+    cross3(cw, eF, cxF);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { bn[k] -= ext[3 + k] + cxF[k]; bf[k] -= eF[k]; }
+  }
+  const int nv = M.nverts[b];
+  if (nv > 0 && p[2] - T(M.radius[b]) < T(0)) {
+    const float* vb = verts + (size_t)b * M.vmax * 3;
+    const T kimp = c.h * c.cn + c.h * c.h * c.kn;
+    for (int k = 0; k < nv; k++) {
+      T vl[3] = {T(vb[3 * k]), T(vb[3 * k + 1]), T(vb[3 * k + 2])};
+      T rz = R[6] * vl[0] + R[7] * vl[1] + R[8] * vl[2];
+      T pen = -(p[2] + rz);
+      if (!(pen > T(0))) continue;
+      T rx = R[0] * vl[0] + R[1] * vl[1] + R[2] * vl[2];
+      T ry = R[3] * vl[0] + R[4] * vl[1] + R[5] * vl[2];
+      T ux = v[0] + w[1] * rz - w[2] * ry;
+      T uy = v[1] + w[2] * rx - w[0] * rz;
+      T uz = v[2] + w[0] * ry - w[1] * rx;
+      T fn0 = c.kn * pen - c.cn * uz;
+      if (!(fn0 > T(0))) continue;
+      T ut = sqrt_(ux * ux + uy * uy);
+      T ct = c.mu * fn0 * rcp_(ut > c.vs ? ut : c.vs);
+      T hct = c.h * ct;
+      A[0] += kimp * ry * ry + hct * rz * rz;
+      A[1] += kimp * rx * rx + hct * rz * rz;
+      A[2] += hct * (ry * ry + rx * rx);
+      A[3] += -kimp * ry * rx;
+      A[4] += -hct * rz * rx;
+      A[5] += -hct * rz * ry;
+      Bm[2] += kimp * ry;
+      Bm[5] += -kimp * rx;
+      Bm[3] += hct * rz;
+      Bm[6] += -hct * ry;
+      Bm[1] += -hct * rz;
+      Bm[7] += hct * rx;
+      C[0] += hct; C[1] += hct; C[2] += kimp;
+      T fx = -ct * ux, fy = -ct * uy;
+      bn[0] -= ry * fn0 - rz * fy;
+      bn[1] -= -rx * fn0 + rz * fx;
+      bn[2] -= -ry * fx + rx * fy;
+      bf[0] -= fx; bf[1] -= fy; bf[2] -= fn0;
+      cf[0] += fx; cf[1] += fy; cf[2] += fn0;
+    }
+  }
+  st(rec + R_A, A, 6); st(rec + R_BM, Bm, 9); st(rec + R_C, C, 6); st(rec + R_BN, bn, 3); st(rec + R_BF, bf, 3); st(rec + R_CF, cf, 3);
+  if (b > 0) {
+    const int d0 = M.dof_of_body[b];
+    T qj[4], wt[3], pd[3], q[3], tau[3], e[3], u[3], E[6];
+    ld(rec + R_QJ, qj, 4); ld(rec + R_WT, wt, 3); ld(rec + R_PD, pd, 3);
+    qlog(qj, q);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      T kp = T(M.kp[d0 + k]), kd = T(M.kd[d0 + k]);
+      e[k] = T(M.armature[d0 + k]) + c.h * kd + c.h * c.h * kp;
+      tau[k] = kp * (pd[k] - q[k] - c.h * wt[k]) - kd * wt[k];
+      T lo = T(M.lim_lo[d0 + k]), hi = T(M.lim_hi[d0 + k]);
+      if (q[k] < lo) { tau[k] += c.limk * (lo - q[k] - c.h * wt[k]) - c.limc * wt[k]; e[k] += c.h * c.limc + c.h * c.h * c.limk; }
+      else if (q[k] > hi) { tau[k] += c.limk * (hi - q[k] - c.h * wt[k]) - c.limc * wt[k]; e[k] += c.h * c.limc + c.h * c.h * c.limk; }
+    }
+    mv3(R, tau, u);
+    E[0] = R[0] * R[0] * e[0] + R[1] * R[1] * e[1] + R[2] * R[2] * e[2];
+    E[1] = R[3] * R[3] * e[0] + R[4] * R[4] * e[1] + R[5] * R[5] * e[2];
+    E[2] = R[6] * R[6] * e[0] + R[7] * R[7] * e[1] + R[8] * R[8] * e[2];
+    E[3] = R[0] * R[3] * e[0] + R[1] * R[4] * e[1] + R[2] * R[5] * e[2];
+    E[4] = R[0] * R[6] * e[0] + R[1] * R[7] * e[1] + R[2] * R[8] * e[2];
+    E[5] = R[3] * R[6] * e[0] + R[4] * R[7] * e[1] + R[5] * R[8] * e[2];
+    st(rec + R_E, E, 6); st(rec + R_U, u, 3);
+  }
+}
+
+// backward step of one dynamic non-root body: D^-1, u, articulated inertia/bias shifted to the parent origin -> out[27]
+template <typename T>
+__device__ __forceinline__ void pk_backward(T* env, int b, T* out) {
+  T* rec = env + b * REC;
+  T A[6], Bm[9], C[6], bn[3], bf[3], E[6], u[3], r[3], zeta[6];
+  ld(rec + R_A, A, 6); ld(rec + R_BM, Bm, 9); ld(rec + R_C, C, 6); ld(rec + R_BN, bn, 3); ld(rec + R_BF, bf, 3);
+  ld(rec + R_E, E, 6); ld(rec + R_U, u, 3); ld(rec + R_R, r, 3); ld(rec + R_ZETA, zeta, 6);
+  T D[6], Dinv[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) D[k] = A[k] + E[k];
+  sym_inv(D, Dinv);
+  u[0] -= bn[0]; u[1] -= bn[1]; u[2] -= bn[2];
+  st(rec + R_E, Dinv, 6); st(rec + R_U, u, 3);
+  T Af[9], Df[9];
+  sym_full(A, Af);
+  sym_full(Dinv, Df);
+  T G[9], K[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      G[i * 3 + j] = Df[i * 3] * Af[j] + Df[i * 3 + 1] * Af[3 + j] + Df[i * 3 + 2] * Af[6 + j];
+      K[i * 3 + j] = Df[i * 3] * Bm[j] + Df[i * 3 + 1] * Bm[3 + j] + Df[i * 3 + 2] * Bm[6 + j];
+    }
+  T aA[6], aB[9], aC[6];
+  aA[0] = A[0] - (Af[0] * G[0] + Af[1] * G[3] + Af[2] * G[6]);
+  aA[1] = A[1] - (Af[3] * G[1] + Af[4] * G[4] + Af[5] * G[7]);
+  aA[2] = A[2] - (Af[6] * G[2] + Af[7] * G[5] + Af[8] * G[8]);
+  aA[3] = A[3] - (Af[0] * G[1] + Af[1] * G[4] + Af[2] * G[7]);
+  aA[4] = A[4] - (Af[0] * G[2] + Af[1] * G[5] + Af[2] * G[8]);
+  aA[5] = A[5] - (Af[3] * G[2] + Af[4] * G[5] + Af[5] * G[8]);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) aB[i * 3 + j] = Bm[i * 3 + j] - (Af[i * 3] * K[j] + Af[i * 3 + 1] * K[3 + j] + Af[i * 3 + 2] * K[6 + j]);
+  aC[0] = C[0] - (Bm[0] * K[0] + Bm[3] * K[3] + Bm[6] * K[6]);
+  aC[1] = C[1] - (Bm[1] * K[1] + Bm[4] * K[4] + Bm[7] * K[7]);
+  aC[2] = C[2] - (Bm[2] * K[2] + Bm[5] * K[5] + Bm[8] * K[8]);
+  aC[3] = C[3] - (Bm[0] * K[1] + Bm[3] * K[4] + Bm[6] * K[7]);
+  aC[4] = C[4] - (Bm[0] * K[2] + Bm[3] * K[5] + Bm[6] * K[8]);
+  aC[5] = C[5] - (Bm[1] * K[2] + Bm[4] * K[5] + Bm[7] * K[8]);
+  T s[3], an[3], af[3], t1[3], t2[3], As[3], Bts[3];
+  sym_mv(Dinv, u, s);
+  sym_mv(aA, zeta, t1);
+  mv3(aB, zeta + 3, t2);
+  sym_mv(A, s, As);
+#pragma unroll
+  for (int k = 0; k < 3; k++) an[k] = bn[k] + t1[k] + t2[k] + As[k];
+  mtv3(aB, zeta, t1);
+  sym_mv(aC, zeta + 3, t2);
+  mtv3(Bm, s, Bts);
+#pragma unroll
+  for (int k = 0; k < 3; k++) af[k] = bf[k] + t1[k] + t2[k] + Bts[k];
+  T Cf[9], Bp[9];
+  sym_full(aC, Cf);
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    T col[3] = {Cf[j], Cf[3 + j], Cf[6 + j]}, x[3];
+    cross3(r, col, x);
+    Bp[j] = aB[j] + x[0]; Bp[3 + j] = aB[3 + j] + x[1]; Bp[6 + j] = aB[6 + j] + x[2];
+  }
+  T P1[9], P2[9];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    T x[3];
+    cross3(r, Bp + 3 * j, x);
+    P1[j] = x[0]; P1[3 + j] = x[1]; P1[6 + j] = x[2];
+    cross3(r, aB + 3 * j, x);
+    P2[j] = x[0]; P2[3 + j] = x[1]; P2[6 + j] = x[2];
+  }
+  out[0] = aA[0] + P1[0] + P2[0];
+  out[1] = aA[1] + P1[4] + P2[4];
+  out[2] = aA[2] + P1[8] + P2[8];
+  out[3] = aA[3] + P1[1] + P2[3];
+  out[4] = aA[4] + P1[2] + P2[6];
+  out[5] = aA[5] + P1[5] + P2[7];
+#pragma unroll
+  for (int k = 0; k < 9; k++) out[6 + k] = Bp[k];
+#pragma unroll
+  for (int k = 0; k < 6; k++) out[15 + k] = aC[k];
+  T rxf[3];
+  cross3(r, af, rxf);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { out[21 + k] = an[k] + rxf[k]; out[24 + k] = af[k]; }
+}
+
+template <typename T> __device__ __forceinline__ void pk_root(const PhysCfg<T>& c, T* env) {
+  T* rec = env;
+  T A[6], Bm[9], C[6], bn[3], bf[3], acc[6];
+  ld(rec + R_A, A, 6); ld(rec + R_BM, Bm, 9); ld(rec + R_C, C, 6); ld(rec + R_BN, bn, 3); ld(rec + R_BF, bf, 3);
+  T Ci[6], Cif[9], BC[9], S[6], Si[6], rhs[3], t[3];
+  sym_inv(C, Ci);
+  sym_full(Ci, Cif);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) BC[i * 3 + j] = Bm[i * 3] * Cif[j] + Bm[i * 3 + 1] * Cif[3 + j] + Bm[i * 3 + 2] * Cif[6 + j];
+  S[0] = A[0] - (BC[0] * Bm[0] + BC[1] * Bm[1] + BC[2] * Bm[2]);
+  S[1] = A[1] - (BC[3] * Bm[3] + BC[4] * Bm[4] + BC[5] * Bm[5]);
+  S[2] = A[2] - (BC[6] * Bm[6] + BC[7] * Bm[7] + BC[8] * Bm[8]);
+  S[3] = A[3] - (BC[0] * Bm[3] + BC[1] * Bm[4] + BC[2] * Bm[5]);
+  S[4] = A[4] - (BC[0] * Bm[6] + BC[1] * Bm[7] + BC[2] * Bm[8]);
+  S[5] = A[5] - (BC[3] * Bm[6] + BC[4] * Bm[7] + BC[5] * Bm[8]);
+  sym_inv(S, Si);
+  mv3(BC, bf, t);
+#pragma unroll
+  for (int k = 0; k < 3; k++) rhs[k] = -bn[k] + t[k];
+  sym_mv(Si, rhs, acc);
+  mtv3(Bm, acc, t);
+#pragma unroll
+  for (int k = 0; k < 3; k++) t[k] = -bf[k] - t[k];
+  sym_mv(Ci, t, acc + 3);
+  st(rec + R_ACC, acc, 6);
+}
+
+// forward step of one dynamic non-root body: accelerations, integrate the joint state
+template <typename T>
+__device__ __forceinline__ void pk_forward(const b200_model_t& M, const PhysCfg<T>& c, T* env, int b) {
+  T* rec = env + b * REC;
+  const T* par = env + M.parent[b] * REC;
+  T pa[6], A[6], Bm[9], Dinv[6], u[3], r[3], zeta[6], Q[4], wt[3], qj[4];
+  ld(par + R_ACC, pa, 6);
+  ld(rec + R_A, A, 6); ld(rec + R_BM, Bm, 9); ld(rec + R_E, Dinv, 6); ld(rec + R_U, u, 3); ld(rec + R_R, r, 3); ld(rec + R_ZETA, zeta, 6);
+  ld(rec + R_Q, Q, 4); ld(rec + R_WT, wt, 3); ld(rec + R_QJ, qj, 4);
+  T axr[3], Ap[6], t1[3], t2[3], t[3], gam[3], wd[3], acc[6];
+  cross3(pa, r, axr);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { Ap[k] = pa[k] + zeta[k]; Ap[3 + k] = pa[3 + k] + axr[k] + zeta[3 + k]; }
+  sym_mv(A, Ap, t1);
+  mv3(Bm, Ap + 3, t2);
+#pragma unroll
+  for (int k = 0; k < 3; k++) t[k] = u[k] - t1[k] - t2[k];
+  sym_mv(Dinv, t, gam);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { acc[k] = Ap[k] + gam[k]; acc[3 + k] = Ap[3 + k]; }
+  st(rec + R_ACC, acc, 6);
+  T cq[4] = {-Q[0], -Q[1], -Q[2], Q[3]};
+  qrot(cq, gam, wd);  // R^T gam
+#pragma unroll
+  for (int k = 0; k < 3; k++) wt[k] = (wt[k] + c.h * wd[k]) * c.damp;
+  T n2 = wt[0] * wt[0] + wt[1] * wt[1] + wt[2] * wt[2];
+  if (n2 > c.wmax * c.wmax) { T sc = c.wmax * rsqrt_(n2); wt[0] *= sc; wt[1] *= sc; wt[2] *= sc; }
+  T hv[3] = {c.h * wt[0], c.h * wt[1], c.h * wt[2]}, dq[4], qn[4];
+  qexp_small(hv, dq);
+  qmul(qj, dq, qn);
+  qnormalize(qn);
+  st(rec + R_WT, wt, 3); st(rec + R_QJ, qn, 4);
+}
+
+template <typename T> __device__ __forceinline__ void pk_root_integrate(const PhysCfg<T>& c, T* env) {
+  T* rec = env;
+  T acc[6], Q[4], p[3], w[3], v[3];
+  ld(rec + R_ACC, acc, 6); ld(rec + R_Q, Q, 4); ld(rec + R_P, p, 3); ld(rec + R_W, w, 3); ld(rec + R_V, v, 3);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { w[k] = (w[k] + c.h * acc[k]) * c.damp; v[k] += c.h * acc[3 + k]; }
+  T n2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  if (n2 > c.wmax * c.wmax) { T sc = c.wmax * rsqrt_(n2); w[0] *= sc; w[1] *= sc; w[2] *= sc; }
+  T hv[3] = {c.h * w[0], c.h * w[1], c.h * w[2]}, dq[4], qn[4];
+#pragma unroll
+  for (int k = 0; k < 3; k++) p[k] += c.h * v[k];
+  qexp_small(hv, dq);
+  qmul(dq, Q, qn);
+  qnormalize(qn);
+  st(rec + R_Q, qn, 4); st(rec + R_P, p, 3); st(rec + R_W, w, 3); st(rec + R_V, v, 3);
+}
+
+// One control step for the warp's EPW envs.  wrec: the warp's records; valid: this lane's env exists.
+// The ball of env g is carried by lane (g, BALL_SLOT) in registers.
+#define BALL_SLOT 7
+template <typename T>
+__device__ __forceinline__ void control_step_packed(const DevBlob& B, const float* verts, const PhysCfg<T>& c, T* wrec, int lane, bool valid,
+                                                    Ball<T>& ball, bool cta_sync) {
+  const b200_model_t& M = B.m;
+  const int g = lane >> 3, s = lane & 7;
+  T* env = wrec + g * ENV_STRIDE;
+  const int nb = M.nb;
+  for (int sim = 0; sim < c.cfi; sim++) {
+    if (c.has_ball && valid && s == BALL_SLOT) {
+      ball_aero<T>(ball.v, ball.w, c.spin_scale, ball.fa);
+      const T thr = c.substeps > 2 ? c.bR * T(6) : c.bR * T(4);
+      if (!ball.has_bounce && ball.p[2] <= thr) {
+        ball.has_bounce = 1; ball.bounce_now = 1;
+        ball.bpos[0] = ball.p[0]; ball.bpos[1] = ball.p[1]; ball.bpos[2] = ball.p[2];
+      }
+    }
+    for (int sub = 0; sub < c.substeps; sub++) {
+      if (cta_sync) __syncthreads();
+      // 1. kinematics, root -> leaves
+      for (int d = 1; d <= M.max_depth; d++) {
+        const int b = valid ? B.t.lvl_all[d][s] : -1;
+        if (b >= 0) pk_fk<T, true>(M, env, b);
+        __syncwarp();
+      }
+      // 2. per-body inertia / bias / contacts / joint drive
+      for (int rr = 0; rr * SLOTS < nb; rr++) {
+        const int b = rr * SLOTS + s;
+        if (valid && b < nb && !M.fixed[b]) pk_body<T>(B, verts, c, env, b, sim == 0);
+      }
+      __syncwarp();
+      // 3. articulated inertia, leaves -> root
+      for (int d = M.max_depth; d >= 1; d--) {
+        const int b = valid ? B.t.lvl_dyn[d][s] : -1;
+        T out[27];
+        if (b >= 0) pk_backward<T>(env, b, out);
+        const int rounds = B.t.maxch[d - 1];
+        for (int cr = 0; cr < rounds; cr++) {
+          if (b >= 0 && B.t.child_rank[b] == cr) {
+            T* pr = env + M.parent[b] * REC + R_A;
+#pragma unroll
+            for (int k = 0; k < 27; k++) pr[k] += out[k];
+          }
+          __syncwarp();
+        }
+      }
+      // 4. root acceleration
+      if (valid && s == 0) pk_root<T>(c, env);
+      __syncwarp();
+      // 5. accelerations root -> leaves, integrate the joints
+      for (int d = 1; d <= M.max_depth; d++) {
+        const int b = valid ? B.t.lvl_dyn[d][s] : -1;
+        if (b >= 0) pk_forward<T>(M, c, env, b);
+        __syncwarp();
+      }
+      // 6. ball (uses the racket's start-of-substep pose/velocity, still in its record), then the root
+      if (c.has_ball && valid && s == BALL_SLOT) {
+        T rQ[4] = {0, 0, 0, 1}, rp[3] = {0, 0, 0}, rv[3] = {0, 0, 0}, rw[3] = {0, 0, 0};
+        const bool has_racket = c.racket_body >= 0;
+        if (has_racket) {
+          const T* rr = env + c.racket_body * REC;
+          ld(rr + R_Q, rQ, 4); ld(rr + R_P, rp, 3); ld(rr + R_V, rv, 3); ld(rr + R_W, rw, 3);
+        }
+        ball_substep<T>(c, ball, has_racket, rQ, rp, rv, rw);
+        T* ext = env + ENV_EXT;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ext[6 + k] = ball.rF[k]; ext[9 + k] = ball.rX[k]; }
+      }
+      if (valid && s == 0) pk_root_integrate<T>(c, env);
+      __syncwarp();
+    }
+  }
+  for (int d = 1; d <= M.max_depth; d++) {
+    const int b = valid ? B.t.lvl_all[d][s] : -1;
+    if (b >= 0) pk_fk<T, false>(M, env, b);
+    __syncwarp();
+  }
+}
