@@ -28,7 +28,8 @@
 #define WARPS_PER_CTA 8  // A/B on B200 (profiles/r1_notes.md): 8 warps x 2 CTAs/SM, barrier per substep
 #endif
 #ifndef STEP_SYNC
-#define STEP_SYNC 1  // 1: CTA barrier at every substep boundary keeps the warps of a CTA on the same code (I-cache sharing)
+#define STEP_SYNC 0  // (packed kernel A/B: 434 us without any barrier, 416 with this one, 391 with POST_SYNC only)
+// legacy note: 1: CTA barrier at every substep boundary keeps the warps of a CTA on the same code (I-cache sharing)
 #endif
 #define SCRATCH_FLOATS 320
 #define MAX_CHILD 4
@@ -954,7 +955,13 @@ __device__ __forceinline__ void store_targets(const b200_buffers_t& bf, const b2
 #pragma unroll
     for (int k = 0; k < 4; k++) bf.t_root_rot[e * 4 + k] = s.rb_rot[k];
   }
-  for (int k = lane; k < nd; k += 32) bf.t_dof_vel[e * nd + k] = ml.dvs[s.f0 * nd + k];
+  {
+    float dv[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const int k = lane + 32 * i; dv[i] = k < nd ? ml.dvs[s.f0 * nd + k] : 0.f; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const int k = lane + 32 * i; if (k < nd) bf.t_dof_vel[e * nd + k] = dv[i]; }
+  }
 }
 
 // raw-state observation row (humanoid_smpl_im.py:653-668, obs_names :198)
@@ -997,12 +1004,40 @@ __device__ __forceinline__ void step_prologue(const b200_buffers_t& bf, const b2
   const float* ds = bf.dof_state + e * nd * 2;
   const float* ac = actions + e * na;
   const bool was_reset = bf.reset_buf[e] == 1;
-  if (lane < 13) scr[lane] = rs[lane];
-  for (int k = lane; k < nd * 2; k += 32) scr[16 + k] = ds[k];
-  for (int k = lane; k < na; k += 32) {
-    float a = (was_reset && cfg.task_mode == 0) ? 0.0f : ac[k];  // actions[self.reset_buf == 1] = 0   (:126, embodied_pose only)
-    scr[16 + 2 * nd + k] = a;
-    bf.actions_used[e * na + k] = a;
+  // all loads of the env's rows are issued before the first dependent store (memory-level parallelism: one latency, not ten)
+  {
+    const int nbl = ml.num_lib_bodies;
+    float r0 = 0.f, d[6], a[3], c0[3], c1[3], c2[3], c3[4];
+    if (lane < 13) r0 = rs[lane];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { const int k = lane + 32 * i; d[i] = k < nd * 2 ? ds[k] : 0.f; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const int k = lane + 32 * i; a[i] = k < na ? ac[k] : 0.f; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const int k = lane + 32 * i; c0[i] = k < nd ? bf.t_dof_pos[e * nd + k] : 0.f; c1[i] = k < nd ? bf.t_dof_vel[e * nd + k] : 0.f; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const int k = lane + 32 * i; c2[i] = k < nbl * 3 ? bf.t_rb_pos[e * nbl * 3 + k] : 0.f; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const int k = lane + 32 * i; c3[i] = k < nbl * 4 ? bf.t_rb_rot[e * nbl * 4 + k] : 0.f; }
+    if (lane < 13) scr[lane] = r0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) { const int k = lane + 32 * i; if (k < nd * 2) scr[16 + k] = d[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const int k = lane + 32 * i;
+      if (k < na) {
+        const float av = (was_reset && cfg.task_mode == 0) ? 0.0f : a[i];  // actions[self.reset_buf == 1] = 0   (:126, embodied_pose only)
+        scr[16 + 2 * nd + k] = av;
+        bf.actions_used[e * na + k] = av;
+      }
+    }
+    // previous targets <- current targets (:626-636); the reward in the epilogue uses them (:677-680)
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const int k = lane + 32 * i; if (k < nd) { bf.p_dof_pos[e * nd + k] = c0[i]; bf.p_dof_vel[e * nd + k] = c1[i]; } }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const int k = lane + 32 * i; if (k < nbl * 3) bf.p_rb_pos[e * nbl * 3 + k] = c2[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const int k = lane + 32 * i; if (k < nbl * 4) bf.p_rb_rot[e * nbl * 4 + k] = c3[i]; }
   }
   __syncwarp();
 
@@ -1049,13 +1084,6 @@ __device__ __forceinline__ void step_prologue(const b200_buffers_t& bf, const b2
     }
     ref_quat_rotate(hq, f, extF);
     ref_quat_rotate(hq, t, extT);
-  }
-  // previous targets <- current targets (:626-636); the reward below uses them (:677-680)
-  {
-    const int nbl = ml.num_lib_bodies;
-    for (int k = lane; k < nd; k += 32) { bf.p_dof_pos[e * nd + k] = bf.t_dof_pos[e * nd + k]; bf.p_dof_vel[e * nd + k] = bf.t_dof_vel[e * nd + k]; }
-    for (int k = lane; k < nbl * 3; k += 32) bf.p_rb_pos[e * nbl * 3 + k] = bf.t_rb_pos[e * nbl * 3 + k];
-    for (int k = lane; k < nbl * 4; k += 32) bf.p_rb_rot[e * nbl * 4 + k] = bf.t_rb_rot[e * nbl * 4 + k];
   }
   __syncwarp();  // the reward below reads p_* rows written by other lanes of this warp
 
@@ -1292,7 +1320,10 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* scr = scratch_all + warp * PK_SCRATCH;
   float* wrec = scratch_all + PK_WARPS * PK_SCRATCH + (size_t)warp * EPW * ENV_STRIDE;
-  const b200_cfg_t& cfg = *gcfg;
+  __shared__ b200_cfg_t s_cfg;  // constants in shared memory: no global (long-scoreboard) reloads inside the substep loop
+  for (int k = threadIdx.x; k < (int)(sizeof(b200_cfg_t) / 4); k += blockDim.x) reinterpret_cast<uint32_t*>(&s_cfg)[k] = reinterpret_cast<const uint32_t*>(gcfg)[k];
+  __syncthreads();
+  const b200_cfg_t& cfg = s_cfg;
   const LaneConst lc = lane_const(M, lane);
   const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
   const int g = lane >> 3, s = lane & 7;
