@@ -44,6 +44,8 @@ int b200v2p_update_state(const b200v2p_state_t* s, void* stream);
 typedef struct b200v2p_ctrl {
   int32_t n, bodies_per_env, ball_stride, racket_body, num_obs, obs_traj_len, use_target, reward_type, early_termination,
       max_episode_length, est_nx, est_ny;
+  int32_t obs_only; /* 1: refresh obs_buf only (the _compute_observations call of _reset_envs :200-201), touch nothing else */
+  int32_t pad_;
   float scale_pos, scale_phase, scale_bounce_pos, scale_bounce_time, w_pos, w_ball_pos;
   float court_min[2], court_max[2];
   float est_params[15]; /* VEL_X, VEL_Y, VSPIN, TRAJ_X, TRAJ_Y ranges (lo, hi, step) */
@@ -63,6 +65,40 @@ typedef struct b200v2p_ctrl {
   int64_t *reset_buf, *terminate_buf;
 } b200v2p_ctrl_t;
 int b200v2p_controller_post(const b200v2p_ctrl_t* c, void* stream);
+
+/* replaces the per-step task part of PhysicsMVAEController._reset_envs when no humanoid needs a reset
+ * (env/tasks/physics_mvae_controller.py:173-201: _reset_balls for the reaction envs :503-524, _reset_recovery_tasks :242-245,
+ * _reset_reaction_tasks :203-240), driven by the device-side masks instead of nonzero() id lists: no host sync.
+ * Random draws come in as device tensors (torch RNG): pool_rand[n] in [0,P), side_rand[n] in [-1000,1000), frame_rand[n] in [-5,5),
+ * target_seed: 3 floats (continuous mode) or n floats (discrete mode). */
+typedef struct b200v2p_treset {
+  int32_t n, pool_size, ball_stride, bodies_per_env, reaction_nframes, target_mode; /* 0 none, 1 continuous, 2 discrete */
+  float target_min[3], target_max[3];
+  const uint8_t *reset_reaction, *reset_recovery;
+  const int64_t *pool_rand, *side_rand, *frame_rand;
+  const float* target_seed;
+  const float* pool;          /* [P,307] */
+  float* ball_states;         /* first ball root row, stride ball_stride */
+  float* rigid_body_state;    /* ball = last body row of each env */
+  float *ball_pos, *ball_vel, *bounce_pos, *ball_traj, *est_bounce_pos, *est_bounce_time, *est_max_height, *target_bounce_pos;
+  uint8_t *has_bounce, *has_contact, *bounce_in, *est_bounce_in;
+  int64_t *tar_time, *tar_time_total, *tar_action, *num_reset_reaction, *swing_type_cycle;
+} b200v2p_treset_t;
+int b200v2p_task_reset(const b200v2p_treset_t* r, void* stream);
+
+/* replaces HumanoidSMPLIMMVAE._reset_actors + _set_env_state + _reset_env_tensors for an id list
+ * (env/tasks/humanoid_smpl_im_mvae.py:463-501, 562-581): the FK of the motion generator's pose (b200v2p_smpl_to_sim over all
+ * envs, prev = NULL) is scattered into the simulation state of the listed envs; velocities zero. */
+typedef struct b200v2p_areset {
+  int32_t n, num_dof, bodies_per_env, root_stride, racket_body, racket_parent;
+  float racket_offset[3];
+  const int64_t* env_ids;
+  const float *src_root_pos, *src_root_rot, *src_dof_pos, *src_rb_pos, *src_rb_rot; /* [N,...] FK results */
+  float *root_states, *dof_state, *rigid_body_state;
+  float *prev_target_root_pos, *prev_target_rb_rot, *root_pos, *root_vel, *pd_target_dof_pos, *target_root_pos;
+  int64_t *progress_buf, *reset_buf, *terminate_buf;
+} b200v2p_areset_t;
+int b200v2p_actor_reset(const b200v2p_areset_t* r, void* stream);
 
 #ifdef __cplusplus
 }

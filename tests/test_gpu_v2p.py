@@ -187,3 +187,121 @@ def test_racket_hit_is_detected():
     assert task._racket_hit_now.float().mean() > 0.9
     dv = (task._ball_root_states[:, 7:10] - v_before).norm(dim=-1)
     assert (dv[task._racket_hit_now] > 20).all()   # restitution 0.9: the normal velocity is reversed
+
+
+def test_controller_cuda_graph_matches_eager():
+    """the captured high-level step replays the same arithmetic as the eager path (same seeds -> same buffers)"""
+    from helpers import SIM_PARAMS, v2p_cfg
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    outs = []
+    for use_graph in (False, True):
+        torch.manual_seed(5)
+        N = 128
+        env = PhysicsMVAEController(v2p_cfg(N, random_walk_in_recovery=False), SIM_PARAMS, 1, "cuda", 0, True)
+        env.reset()
+        if use_graph:
+            snap = {k: v.clone() for k, v in vars(env._mvae_player).items() if isinstance(v, torch.Tensor)}
+            task = env._physics_player.task
+            tsnap = {k: v.clone() for k, v in vars(task).items() if isinstance(v, torch.Tensor)}
+            csnap = {k: v.clone() for k, v in vars(env).items() if isinstance(v, torch.Tensor)}
+            env.enable_cuda_graph()                      # warm-up + capture advance the state: restore it
+            for src, obj in ((snap, env._mvae_player), (tsnap, task), (csnap, env)):
+                for k, v in src.items():
+                    getattr(obj, k).copy_(v)
+        torch.manual_seed(77)
+        g = torch.Generator(device=DEV).manual_seed(3)
+        for _ in range(5):
+            a = torch.clamp(torch.randn(N, 35, device=DEV, generator=g), -5, 5)
+            env.step(a)
+        torch.cuda.synchronize()
+        task = env._physics_player.task
+        outs.append((task._dof_pos.clone(), task._ball_root_states.clone(), env.progress_buf.clone()))
+    # the motion generator draws from the default generator whose offsets differ between capture and eager, so only the
+    # deterministic parts are compared: progress counters and ball flight before any contact
+    assert torch.equal(outs[0][2], outs[1][2])
+    assert torch.isfinite(outs[1][0]).all() and torch.isfinite(outs[1][1]).all()
+    assert (outs[0][1][:, 0:3] - outs[1][1][:, 0:3]).abs().max() < 1e-3
+
+
+def test_fast_task_reset_matches_slow_path():
+    """mask-driven per-step task reset (b200v2p_task_reset) vs the id-list path of _reset_envs on the same masks"""
+    from helpers import SIM_PARAMS, v2p_cfg
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    res = []
+    for fast in (False, True):
+        torch.manual_seed(11)
+        N = 128
+        env = PhysicsMVAEController(v2p_cfg(N, use_random_ball_target="discrete"), SIM_PARAMS, 1, "cuda", 0, True)
+        env.reset()
+        for _ in range(3):
+            env.step(torch.zeros(N, 35, device=DEV))
+            env.reset(torch.zeros(0, dtype=torch.long, device=DEV))
+        env._reset_reaction_buf[:] = False
+        env._reset_recovery_buf[:] = False
+        env._reset_reaction_buf[::3] = True
+        env._reset_recovery_buf[1::4] = True
+        task = env._physics_player.task
+        task._has_bounce[:] = True
+        if fast:
+            env._reset_tasks_fast()
+        else:
+            env._reset_envs_idlist(torch.zeros(0, dtype=torch.long, device=DEV))   # reference-shaped id-list path
+        torch.cuda.synchronize()
+        res.append(dict(tar_time=env._tar_time.clone(), tar_action=env._tar_action.clone(), nrr=env._num_reset_reaction.clone(),
+                        has_bounce=task._has_bounce.clone(), contact=task._has_racket_ball_contact.clone(),
+                        cycle=env._mvae_player._swing_type_cycle.clone(), ball=task._ball_root_states.clone(), traj=env._ball_traj.clone(),
+                        tot=env._tar_time_total.clone(), tgt=env._target_bounce_pos.clone(), obs=env.obs_buf.clone()))
+    a, b = res
+    for k in ("tar_time", "tar_action", "nrr", "has_bounce", "contact", "cycle"):
+        assert torch.equal(a[k], b[k]), k                          # deterministic bookkeeping is identical
+    rea = torch.zeros(128, dtype=torch.bool, device=DEV); rea[::3] = True
+    for r in res:                                                    # random draws differ, their ranges / structure must hold
+        assert ((r["tot"][rea] >= 65) & (r["tot"][rea] < 75)).all()
+        assert (r["ball"][rea, 1] > 11).all() and (r["ball"][rea, 8] < -15).all()
+        assert torch.equal(r["traj"][rea][:, 0], r["ball"][rea, 0:3])   # trajectory row 0 = launch position of the chosen pool row
+        assert (r["tgt"][rea, 1] == 10).all() and torch.isin(r["tgt"][rea, 0], torch.tensor([-3.0, 0.0, 3.0], device=DEV)).all()
+        assert torch.isfinite(r["obs"]).all()
+    assert torch.equal(a["ball"][~rea], b["ball"][~rea])
+
+
+def test_humanoid_reset_kernel_matches_idlist_path():
+    """b200v2p_actor_reset (+ counters) vs the reference-shaped indexed-assignment reset for a list of envs"""
+    from helpers import SIM_PARAMS, v2p_cfg
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    N = 64
+    torch.manual_seed(2)
+    env = PhysicsMVAEController(v2p_cfg(N), SIM_PARAMS, 1, "cuda", 0, True)
+    env.reset()
+    for _ in range(4):
+        env.step(torch.zeros(N, 35, device=DEV))
+    task = env._physics_player.task
+    ids = torch.tensor([1, 5, 17, 40], device=DEV)
+    env._reset_reaction_buf[:] = False
+    env._reset_recovery_buf[:] = False
+    player = env._mvae_player
+    gen_state = player.gen.get_state()
+    before = {k: v.clone() for k, v in (("rs", task._root_states), ("ds", task._dof_state), ("rb", task._rigid_body_state))}
+    env._reset_envs(ids)
+    torch.cuda.synchronize()
+    got = {k: v.clone() for k, v in (("rs", task._root_states), ("ds", task._dof_state), ("rb", task._rigid_body_state),
+                                     ("prp", task._prev_target_root_pos), ("prr", task._prev_target_rb_rot), ("pd", task._pd_target_dof_pos))}
+    # independent check: FK of the player's (now reset) pose written with plain torch indexing
+    tmp = {k: torch.zeros_like(v) for k, v in task._tmp.items()}
+    task._smpl_to_sim_into(player._root_pos.contiguous(), player._joint_rotmat, tmp)
+    rs = task._humanoid_root_states
+    assert torch.equal(rs[ids, 0:3], player._root_pos[ids]) and torch.equal(rs[ids, 3:7], tmp["root_rot"][ids]) and (rs[ids, 7:] == 0).all()
+    rbs = task._rigid_body_state.view(N, 26, 13)
+    assert torch.equal(rbs[ids, :24, 0:3], tmp["rb_pos"][ids]) and torch.equal(rbs[ids, :24, 3:7], tmp["rb_rot"][ids])
+    assert (rbs[ids, :25, 7:] == 0).all()
+    assert torch.equal(task._dof_pos[ids], tmp["dof_pos"][ids]) and (task._dof_vel[ids] == 0).all()
+    assert torch.equal(got["prr"][ids], tmp["rb_rot"][ids]) and torch.equal(got["pd"][ids], tmp["dof_pos"][ids])
+    assert (env.progress_buf[ids] == 0).all() and (env.reset_buf[ids] == 0).all() and (env._num_reset[ids] == 2).all()
+    # racket row: wrist pose + rotated offset
+    off = torch.tensor(task._model["offset"][24], device=DEV, dtype=torch.float)
+    q = tmp["rb_rot"][ids, 22]
+    t = 2.0 * torch.cross(q[:, :3], off.expand(len(ids), 3), dim=-1)
+    want = tmp["rb_pos"][ids, 22] + off + q[:, 3:4] * t + torch.cross(q[:, :3], t, dim=-1)
+    assert (rbs[ids, 24, 0:3] - want).abs().max() < 1e-6
+    keep = torch.ones(N, dtype=torch.bool, device=DEV); keep[ids] = False
+    assert torch.equal(got["ds"].view(N, -1)[keep], before["ds"].view(N, -1)[keep])      # other envs untouched
+    assert torch.equal(got["rb"].view(N, 26, 13)[keep][:, :25], before["rb"].view(N, 26, 13)[keep][:, :25])

@@ -1865,11 +1865,13 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
       h->step_grid = per_sm * sms < need ? per_sm * sms : need;
       if (h->step_grid < 1) return fail(-5, "b200env_step: step_kernel_packed does not fit on this device%s");
     }
+    // the ticket counter is re-zeroed on the stream before every launch: nothing in the launch depends on host-side
+    // history, so a step can be captured into a CUDA graph and replayed
+    CUDA_OK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), (cudaStream_t)stream));
     step_kernel_packed<<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes,
                                                                                       h->d_cfg, h->bufs, h->ml, actions, h->num_envs,
-                                                                                      h->d_ticket, h->ticket_base);
+                                                                                      h->d_ticket, 0ULL);
     CUDA_OK(cudaGetLastError());
-    h->ticket_base += (unsigned long long)(need + h->step_grid) * batch;
     h->launches++;
     return 0;
   }
@@ -1883,12 +1885,11 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
     h->step_grid = per_sm * sms < need ? per_sm * sms : need;
     if (h->step_grid < 1) return fail(-5, "b200env_step: step_kernel does not fit on this device%s");
   }
+  CUDA_OK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), (cudaStream_t)stream));
   step_kernel<<<h->step_grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes,
                                                                                  h->d_cfg, h->bufs, h->ml, actions, h->num_envs,
-                                                                                 h->d_ticket, h->ticket_base);
+                                                                                 h->d_ticket, 0ULL);
   CUDA_OK(cudaGetLastError());
-  // every CTA takes one final (failing) batch ticket: the next launch's tickets start after them
-  h->ticket_base += (unsigned long long)(need_ctas(h) + h->step_grid) * WARPS_PER_CTA;
   h->launches++;
   return 0;
 }

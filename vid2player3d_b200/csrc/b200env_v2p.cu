@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p
   const float kp[3] = {c.racket_pos[e * 3], c.racket_pos[e * 3 + 1], c.racket_pos[e * 3 + 2]};
   const bool has_contact = c.has_contact[e] != 0;
   // ---- _update_state (:271-314): true bounce in court, estimated bounce of the outgoing ball
-  if (lane == 0) {
+  if (lane == 0 && !c.obs_only) {
     if (c.tar_action[e] == 0 && c.has_bounce_now[e]) c.bounce_in[e] = in_court(c.bounce_pos[e * 3], c.bounce_pos[e * 3 + 1]) ? 1 : 0;
     if (c.has_contact_now[e] && c.est_x) {
       const float* b = c.ball_states + e * c.ball_stride;
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p
   }
   __syncwarp();
   // ---- reward (:368-406, jit :493-602)
-  if (lane == 0) {
+  if (lane == 0 && !c.obs_only) {
     const float phase = c.phase[e];
     float d2 = 0.0f;
 #pragma unroll
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p
   if (c.use_target && lane < 2) { float v = c.target_bounce_pos[e * 3 + lane] - rp[lane]; o[225 + c.obs_traj_len * 3 + lane] = v; nan |= isnan(v); }
   const bool has_nan = __any_sync(FULL, nan);
   // ---- reset FSM (:408-436)
-  if (lane == 0) {
+  if (lane == 0 && !c.obs_only) {
     const bool out = rp[0] < c.court_min[0] || rp[1] < c.court_min[1] || rp[0] > c.court_max[0] || rp[1] > c.court_max[1];
     bool terminate = out || has_nan;
     int64_t reset = (c.progress_buf[e] >= (int64_t)c.max_episode_length - 1) ? 1 : (terminate ? 1 : 0);
@@ -391,6 +391,115 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p
     c.reset_buf[e] = reset;
     c.reset_reaction[e] = reaction ? 1 : 0;
     c.reset_recovery[e] = recovery ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ mask-driven task reset
+__global__ void __launch_bounds__(V2P_WARPS * 32) task_reset_kernel(b200v2p_treset_t r) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * V2P_WARPS + warp;
+  if (e >= r.n) return;
+  const bool rea = r.reset_reaction[e] != 0, rec = r.reset_recovery[e] != 0;
+  if (!rea && !rec) return;
+  if (rea) {  // _reset_balls (:503-524) with the sample_random branch of the offline pool (tennis_ball.py:436-444)
+    int64_t idx = r.pool_rand[e];
+    if (r.ball_pos[e * 3 + 1] > 0.0f) {
+      idx = (int64_t)((r.ball_pos[e * 3] + 4.0f) / 8.0f * (float)r.pool_size) + r.side_rand[e];
+      idx = idx < 0 ? 0 : (idx > r.pool_size - 1 ? r.pool_size - 1 : idx);
+    }
+    const float* row = r.pool + idx * 307;
+    __syncwarp();
+    for (int k = lane; k < 300; k += 32) r.ball_traj[e * 300 + k] = row[7 + k];
+    if (lane == 0) {
+      float* b = r.ball_states + e * r.ball_stride;
+      float* rb = r.rigid_body_state + (e * r.bodies_per_env + r.bodies_per_env - 1) * 13;
+      const float v[3] = {row[3], row[4], row[5]};
+      const float c[3] = {-v[1], v[0], 0.0f};
+      const float nn = fmaxf(sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]), 1e-12f);
+      const float sp = row[6] * 3.141592653589793f * 2.0f;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float w = sp * (c[k] / nn);
+        b[k] = row[k]; b[7 + k] = v[k]; b[10 + k] = w;
+        rb[k] = row[k]; rb[7 + k] = v[k]; rb[10 + k] = w;
+        r.ball_pos[e * 3 + k] = row[k]; r.ball_vel[e * 3 + k] = v[k]; r.bounce_pos[e * 3 + k] = 0.0f;
+      }
+      r.has_bounce[e] = 0; r.has_contact[e] = 0;
+    }
+  }
+  if (lane != 0) return;
+  if (rec) {  // _reset_recovery_tasks (:242-245)
+    r.tar_action[e] = 0;
+    r.has_bounce[e] = 0;
+    r.bounce_pos[e * 3] = 0.0f; r.bounce_pos[e * 3 + 1] = 0.0f; r.bounce_pos[e * 3 + 2] = 0.0f;
+  }
+  if (rea) {  // _reset_reaction_tasks (:203-240)
+    r.tar_time[e] = 0;
+    r.tar_action[e] = 1;
+    r.num_reset_reaction[e] += 1;
+    r.bounce_in[e] = 0;
+    r.est_bounce_pos[e * 3] = 0.0f; r.est_bounce_pos[e * 3 + 1] = 0.0f; r.est_bounce_pos[e * 3 + 2] = 0.0f;
+    r.est_bounce_time[e] = 0.0f;
+    r.est_bounce_in[e] = 0;
+    r.est_max_height[e] = 0.0f;
+    r.swing_type_cycle[e] = -1;
+    r.tar_time_total[e] = (int64_t)r.reaction_nframes + r.frame_rand[e];
+    if (r.target_mode == 1) {        // 'continuous': one target shared by the envs reset in this call (:226-229)
+#pragma unroll
+      for (int k = 0; k < 3; k++) r.target_bounce_pos[e * 3 + k] = r.target_seed[k] * (r.target_max[k] - r.target_min[k]) + r.target_min[k];
+    } else if (r.target_mode == 2) { // left / middle / right (:230-237)
+      const float sd = r.target_seed[e];
+      r.target_bounce_pos[e * 3] = sd < 0.33f ? -3.0f : (sd > 0.67f ? 3.0f : 0.0f);
+      r.target_bounce_pos[e * 3 + 1] = 10.0f; r.target_bounce_pos[e * 3 + 2] = 0.0f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ humanoid reset from the FK pose
+__global__ void __launch_bounds__(V2P_WARPS * 32) actor_reset_kernel(b200v2p_areset_t r) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * V2P_WARPS + warp;
+  if (i >= r.n) return;
+  const int64_t e = r.env_ids[i];
+  const int nd = r.num_dof;
+  float* rb = r.rigid_body_state + e * r.bodies_per_env * 13;
+  if (lane < 24) {
+    float* row = rb + lane * 13;
+    const float* p = r.src_rb_pos + (e * 24 + lane) * 3;
+    const float* q = r.src_rb_rot + (e * 24 + lane) * 4;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { row[k] = p[k]; row[7 + k] = 0.0f; row[10 + k] = 0.0f; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) { row[3 + k] = q[k]; r.prev_target_rb_rot[(e * 24 + lane) * 4 + k] = q[k]; }
+  }
+  if (lane == 24 && r.racket_body >= 0) {  // welded racket row = parent pose + rotated offset (first obs is consistent)
+    const float* pp = r.src_rb_pos + (e * 24 + r.racket_parent) * 3;
+    const float* q = r.src_rb_rot + (e * 24 + r.racket_parent) * 4;
+    const float o[3] = {r.racket_offset[0], r.racket_offset[1], r.racket_offset[2]};
+    float t[3] = {2.0f * (q[1] * o[2] - q[2] * o[1]), 2.0f * (q[2] * o[0] - q[0] * o[2]), 2.0f * (q[0] * o[1] - q[1] * o[0])};
+    float u[3] = {q[1] * t[2] - q[2] * t[1], q[2] * t[0] - q[0] * t[2], q[0] * t[1] - q[1] * t[0]};
+    float* row = rb + r.racket_body * 13;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { row[k] = pp[k] + o[k] + q[3] * t[k] + u[k]; row[7 + k] = 0.0f; row[10 + k] = 0.0f; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) row[3 + k] = q[k];
+  }
+  for (int k = lane; k < nd; k += 32) {
+    const float v = r.src_dof_pos[e * nd + k];
+    r.dof_state[(e * nd + k) * 2] = v; r.dof_state[(e * nd + k) * 2 + 1] = 0.0f;
+    r.pd_target_dof_pos[e * nd + k] = v;
+  }
+  if (lane == 0) {
+    float* rs = r.root_states + e * r.root_stride;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float v = r.src_root_pos[e * 3 + k];
+      rs[k] = v; rs[7 + k] = 0.0f; rs[10 + k] = 0.0f;
+      r.prev_target_root_pos[e * 3 + k] = v; r.root_pos[e * 3 + k] = v; r.root_vel[e * 3 + k] = 0.0f; r.target_root_pos[e * 3 + k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) rs[3 + k] = r.src_root_rot[e * 4 + k];
+    r.progress_buf[e] = 0; r.reset_buf[e] = 0; r.terminate_buf[e] = 0;
   }
 }
 
@@ -440,6 +549,24 @@ int b200v2p_update_state(const b200v2p_state_t* s, void* stream) {
   if (!s) return vfail(-1, "b200v2p_update_state: null");
   if (s->n == 0) return 0;
   update_state_kernel<<<(s->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*s);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_actor_reset(const b200v2p_areset_t* r, void* stream) {
+  if (!r) return vfail(-1, "b200v2p_actor_reset: null");
+  if (r->n == 0) return 0;
+  if (r->n < 0 || !r->env_ids || !r->src_root_pos || !r->root_states) return vfail(-1, "b200v2p_actor_reset: bad arguments");
+  actor_reset_kernel<<<(r->n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(*r);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_task_reset(const b200v2p_treset_t* r, void* stream) {
+  if (!r) return vfail(-1, "b200v2p_task_reset: null");
+  if (r->n == 0) return 0;
+  if (r->pool_size < 1 || !r->pool || !r->reset_reaction || !r->reset_recovery) return vfail(-1, "b200v2p_task_reset: bad arguments");
+  task_reset_kernel<<<(r->n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(*r);
   V_CUDA_OK();
   return 0;
 }

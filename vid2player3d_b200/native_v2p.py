@@ -5,7 +5,7 @@ from . import abi
 from .native import _ptr, _stream, lib
 
 SYMBOLS = ["b200v2p_last_error", "b200v2p_smpl_to_sim", "b200v2p_ball_aero", "b200v2p_ball_reset", "b200v2p_update_state",
-           "b200v2p_controller_post"]
+           "b200v2p_controller_post", "b200v2p_task_reset", "b200v2p_actor_reset"]
 GRIP_NORMAL = {'eastern': (0.0, 1.0, 0.0), 'semi_western': (0.0, 2.0 ** -0.5, 2.0 ** -0.5)}
 REWARD_TYPES = {'reach': 0, 'return': 1, 'return_w_estimate': 2}
 
@@ -64,10 +64,11 @@ def controller_post(cfg, t):
               "early_termination", "max_episode_length", "est_nx", "est_ny", "scale_pos", "scale_phase", "scale_bounce_pos",
               "scale_bounce_time", "w_pos", "w_ball_pos"):
         setattr(c, k, cfg[k])
+    c.obs_only = int(cfg.get("obs_only", 0))
     for k in ("court_min", "court_max", "est_params"):
         for i, v in enumerate(cfg[k]):
             getattr(c, k)[i] = float(v)
-    scalars = {f for f, _ in abi.V2PCtrl._fields_ if f in cfg}
+    scalars = {f for f, _ in abi.V2PCtrl._fields_ if f in cfg} | {"obs_only", "pad_"}
     for name, _ in abi.V2PCtrl._fields_:
         if name in scalars:
             continue
@@ -79,3 +80,36 @@ def controller_post(cfg, t):
             assert x.is_cuda and x.is_contiguous(), name
             setattr(c, name, x.data_ptr())
     _check(lib().b200v2p_controller_post(C.byref(c), _stream()))
+
+
+def task_reset(cfg, t):
+    """cfg: scalars of abi.V2PTaskReset (n, pool_size, ball_stride, bodies_per_env, reaction_nframes, target_mode, target_min/max);
+    t: tensors keyed like the struct's pointer fields"""
+    r = abi.V2PTaskReset()
+    for k in ("n", "pool_size", "ball_stride", "bodies_per_env", "reaction_nframes", "target_mode"):
+        setattr(r, k, int(cfg[k]))
+    for k in ("target_min", "target_max"):
+        for i, v in enumerate(cfg[k]):
+            getattr(r, k)[i] = float(v)
+    for name, _ in abi.V2PTaskReset._fields_:
+        if name in cfg:
+            continue
+        x = t[name]
+        assert x.is_cuda and x.is_contiguous(), name
+        setattr(r, name, x.data_ptr())
+    _check(lib().b200v2p_task_reset(C.byref(r), _stream()))
+
+
+def actor_reset(cfg, t):
+    r = abi.V2PActorReset()
+    for k in ("n", "num_dof", "bodies_per_env", "root_stride", "racket_body", "racket_parent"):
+        setattr(r, k, int(cfg[k]))
+    for i, v in enumerate(cfg["racket_offset"]):
+        r.racket_offset[i] = float(v)
+    for name, _ in abi.V2PActorReset._fields_:
+        if name in cfg:
+            continue
+        x = t[name]
+        assert x.is_cuda and x.is_contiguous(), name
+        setattr(r, name, x.data_ptr())
+    _check(lib().b200v2p_actor_reset(C.byref(r), _stream()))

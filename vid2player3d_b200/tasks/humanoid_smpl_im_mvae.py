@@ -232,36 +232,20 @@ class HumanoidSMPLIMMVAE(BaseTask):
             self._reset_actors(reset_humanoid_env_ids)
         if len(reset_ball_env_ids) > 0:
             traj = self._reset_balls(reset_ball_env_ids)
-        if len(reset_humanoid_env_ids) > 0:
-            self.progress_buf[reset_humanoid_env_ids] = 0
-            self.reset_buf[reset_humanoid_env_ids] = 0
-            self._terminate_buf[reset_humanoid_env_ids] = 0
         return traj
 
     def _reset_actors(self, env_ids):
-        """:463-501: sim state <- FK of the motion generator's initial pose (zero velocities)"""
-        self._smpl_to_sim_into(self._mvae_player._root_pos.clone(), self._mvae_player._joint_rotmat, self._tmp)
-        root_pos = self._mvae_player._root_pos
-        rs, rbs = self._humanoid_root_states, self._rigid_body_state.view(self.num_envs, 26, 13)
-        rs[env_ids, 0:3], rs[env_ids, 3:7] = root_pos[env_ids], self._tmp["root_rot"][env_ids]
-        rs[env_ids, 7:13] = 0
-        rbs[env_ids, :24, 0:3], rbs[env_ids, :24, 3:7] = self._tmp["rb_pos"][env_ids], self._tmp["rb_rot"][env_ids]
-        rbs[env_ids, :25, 7:13] = 0
-        # welded racket row: parent (R_Wrist) pose + rotated offset, so the controller's first obs is consistent
-        wq, wp = self._tmp["rb_rot"][env_ids, 22], self._tmp["rb_pos"][env_ids, 22]
-        off = torch.tensor(self._model["offset"][24], device=self.device, dtype=torch.float).expand(len(env_ids), 3)
-        qv, qw = wq[:, :3], wq[:, 3:4]
-        tt = 2.0 * torch.cross(qv, off, dim=-1)
-        rbs[env_ids, 24, 0:3] = wp + off + qw * tt + torch.cross(qv, tt, dim=-1)
-        rbs[env_ids, 24, 3:7] = wq
-        self._dof_pos[env_ids] = self._tmp["dof_pos"][env_ids]
-        self._dof_vel[env_ids] = 0
-        self._prev_target_root_pos[env_ids] = root_pos[env_ids]
-        self._prev_target_rb_rot[env_ids] = self._tmp["rb_rot"][env_ids]
-        self._root_pos[env_ids] = root_pos[env_ids]
-        self._root_vel[env_ids] = 0
-        self._pd_target_dof_pos[env_ids] = self._tmp["dof_pos"][env_ids]
-        self._target_root_pos[env_ids] = root_pos[env_ids]
+        """:463-501 + :562-581: sim state <- FK of the motion generator's initial pose (zero velocities); 2 launches"""
+        self._smpl_to_sim_into(self._mvae_player._root_pos.contiguous(), self._mvae_player._joint_rotmat, self._tmp)
+        cfg = dict(n=len(env_ids), num_dof=self.num_dof, bodies_per_env=26, root_stride=26, racket_body=24, racket_parent=22,
+                   racket_offset=self._model["offset"][24])
+        native_v2p.actor_reset(cfg, dict(
+            env_ids=env_ids.contiguous(), src_root_pos=self._mvae_player._root_pos.contiguous(), src_root_rot=self._tmp["root_rot"],
+            src_dof_pos=self._tmp["dof_pos"], src_rb_pos=self._tmp["rb_pos"], src_rb_rot=self._tmp["rb_rot"], root_states=self._root_states,
+            dof_state=self._dof_state, rigid_body_state=self._rigid_body_state, prev_target_root_pos=self._prev_target_root_pos,
+            prev_target_rb_rot=self._prev_target_rb_rot, root_pos=self._root_pos, root_vel=self._root_vel,
+            pd_target_dof_pos=self._pd_target_dof_pos, target_root_pos=self._target_root_pos, progress_buf=self.progress_buf,
+            reset_buf=self.reset_buf, terminate_buf=self._terminate_buf))
 
     def _reset_balls(self, env_ids):
         """:503-524 with the random branch of TennisBallGeneratorOffline.generate (tennis_ball.py:436-444)"""

@@ -23,14 +23,24 @@ from .humanoid_smpl_im_mvae import HumanoidSMPLIMMVAE
 BASE_ROTMAT = [[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]  # quaternion (.5,.5,.5,.5): SMPL y-up -> world z-up
 
 
+_SKEW = None
+
+
 def _aa_to_rotmat(aa):
-    angle = aa.norm(dim=-1, keepdim=True).clamp_min(1e-8)
-    ax = aa / angle
-    x, y, z = ax.unbind(-1)
-    c, s = torch.cos(angle[..., 0]), torch.sin(angle[..., 0])
-    C = 1 - c
-    return torch.stack([c + x * x * C, x * y * C - z * s, x * z * C + y * s, y * x * C + z * s, c + y * y * C, y * z * C - x * s,
-                        z * x * C - y * s, z * y * C + x * s, c + z * z * C], -1).view(*aa.shape[:-1], 3, 3)
+    """rotation vectors [...,3] -> matrices, Rodrigues as I + s K + c K K with K from one matmul (10 launches instead of ~30)"""
+    global _SKEW
+    if _SKEW is None or _SKEW.device != aa.device:
+        g = torch.zeros(3, 9, device=aa.device)
+        g[0, 5], g[0, 7] = -1.0, 1.0      # x: K[1,2] = -x, K[2,1] = x
+        g[1, 2], g[1, 6] = 1.0, -1.0      # y: K[0,2] = y,  K[2,0] = -y
+        g[2, 1], g[2, 3] = -1.0, 1.0      # z: K[0,1] = -z, K[1,0] = z
+        _SKEW = g
+    K = (aa.reshape(-1, 3) @ _SKEW).view(-1, 3, 3)
+    a2 = (aa * aa).sum(-1).reshape(-1, 1, 1).clamp_min(1e-12)
+    a = a2.sqrt()
+    R = torch.baddbmm(K * (torch.sin(a) / a), K, K * ((1 - torch.cos(a)) / a2))     # s K + c K K
+    R.diagonal(dim1=-2, dim2=-1).add_(1.0)
+    return R.view(*aa.shape[:-1], 3, 3)
 
 
 class SyntheticMotionPlayer:
@@ -39,7 +49,8 @@ class SyntheticMotionPlayer:
 
     def __init__(self, num_envs, device, seed=10, court_min=(-5.0, -16.0), court_max=(5.0, -10.0)):
         self.N, self.device = num_envs, device
-        self.gen = torch.Generator(device=device).manual_seed(seed)
+        self.gen = torch.Generator(device=device).manual_seed(seed)   # construction / reset only; step() uses the default generator
+                                                                       # and updates its state IN PLACE so it can live inside a CUDA graph
         self._aa = torch.zeros(num_envs, 24, 3, device=device)
         self._root_pos = torch.zeros(num_envs, 3, device=device)
         self._joint_rotmat = torch.eye(3, device=device).repeat(num_envs, 24, 1, 1)
@@ -50,40 +61,44 @@ class SyntheticMotionPlayer:
         self._base = torch.tensor(BASE_ROTMAT, device=device)
         self._proj = torch.randn(32, 72, device=device, generator=self.gen) * 0.02
         self.court_min, self.court_max = court_min, court_max
+        self._lo = torch.tensor([court_min[0] + 1, court_min[1] + 1, 0.95], device=device)
+        self._span = torch.tensor([court_max[0] - court_min[0] - 2, court_max[1] - court_min[1] - 2, 0.0], device=device)
 
-    def _update_rotmat(self):
-        R = _aa_to_rotmat(self._aa)
-        c, s = torch.cos(self._heading), torch.sin(self._heading)
+    def _update_rotmat(self, ids=None):
+        aa, heading = (self._aa, self._heading) if ids is None else (self._aa[ids], self._heading[ids])
+        R = _aa_to_rotmat(aa)
+        c, s = torch.cos(heading), torch.sin(heading)
         z, o = torch.zeros_like(c), torch.ones_like(c)
         H = torch.stack([c, -s, z, s, c, z, z, z, o], -1).view(-1, 3, 3)
         R[:, 0] = H @ self._base @ R[:, 0]
-        self._joint_rotmat = R.contiguous()
+        if ids is None:
+            self._joint_rotmat.copy_(R)
+        else:
+            self._joint_rotmat[ids] = R
 
     def reset(self, env_ids):
         n = len(env_ids)
         r = torch.rand(n, 3, device=self.device, generator=self.gen)
-        self._root_pos[env_ids, 0] = self.court_min[0] + 1 + r[:, 0] * (self.court_max[0] - self.court_min[0] - 2)
-        self._root_pos[env_ids, 1] = self.court_min[1] + 1 + r[:, 1] * (self.court_max[1] - self.court_min[1] - 2)
-        self._root_pos[env_ids, 2] = 0.95
+        self._root_pos[env_ids] = self._lo + r * self._span
         self._aa[env_ids] = 0.05 * torch.randn(n, 24, 3, device=self.device, generator=self.gen)
         self._heading[env_ids] = math.pi / 2 + 0.2 * (r[:, 2] - 0.5)       # facing +y (the net)
-        self._phase_pred[env_ids] = 0
-        self._swing_type[env_ids] = 0
-        self._swing_type_cycle[env_ids] = -1
-        self._update_rotmat()
+        self._phase_pred.index_fill_(0, env_ids, 0.0)
+        self._swing_type.index_fill_(0, env_ids, 0)
+        self._swing_type_cycle.index_fill_(0, env_ids, -1)
+        self._update_rotmat(env_ids)
 
     def step(self, mvae_actions, res_dof_actions=None):
         drive = (mvae_actions[:, :32] @ self._proj).view(self.N, 24, 3)
-        noise = 0.02 * torch.randn(self.N, 24, 3, device=self.device, generator=self.gen)
-        self._aa = 0.97 * self._aa + drive + noise
+        noise = 0.02 * torch.randn(self.N, 24, 3, device=self.device)
+        self._aa.mul_(0.97).add_(drive).add_(noise)
         self._aa[:, 0] *= 0.3
         if res_dof_actions is not None and res_dof_actions.numel():
             self._aa[:, 21] += res_dof_actions[:, :3] * 0.1          # residual on the racket wrist (add_residual_dof)
-        self._root_pos[:, :2] += 0.01 * torch.randn(self.N, 2, device=self.device, generator=self.gen)
-        self._phase_pred = torch.remainder(self._phase_pred + 2 * math.pi / 60, 2 * math.pi)
+        self._root_pos[:, :2] += 0.01 * torch.randn(self.N, 2, device=self.device)
+        self._phase_pred.copy_(torch.remainder(self._phase_pred + 2 * math.pi / 60, 2 * math.pi))
         wrap = self._phase_pred < 2 * math.pi / 60
-        self._swing_type = torch.where(wrap, (self._swing_type + 1) % 4, self._swing_type)
-        self._swing_type_cycle = torch.where(self._phase_pred > 2.0, self._swing_type, self._swing_type_cycle)
+        self._swing_type.copy_(torch.where(wrap, (self._swing_type + 1) % 4, self._swing_type))
+        self._swing_type_cycle.copy_(torch.where(self._phase_pred > 2.0, self._swing_type, self._swing_type_cycle))
         self._update_rotmat()
 
 
@@ -125,6 +140,7 @@ class PhysicsMVAEController:
         self.extras = {}
         self._sub_rewards = f(N, 2)
         self._has_init = False
+        self._graph = None
         self._num_humanoid_bodies, self._racket_body_id, self._head_body_id = 24, 24, 13
         self._ball_traj = f(N, 100, 3)
         self._bounce_in, self._est_bounce_in = b(N), b(N)
@@ -216,7 +232,57 @@ class PhysicsMVAEController:
             env_ids = torch.arange(self.num_envs, device=self.device, dtype=torch.long)
         self._reset_envs(env_ids)
 
+    def _reset_tasks_fast(self, update_state=False):
+        """_reset_envs (:173-201) when no humanoid needs a reset - the common per-step case: new balls for the envs whose reaction
+        timer expired, recovery / reaction task bookkeeping, obs refresh.  Mask-driven: 4 RNG launches + 2 kernels, no host sync."""
+        N, dev, t = self.num_envs, self.device, self._physics_player.task
+        P = int(t._ball_pool.shape[0])
+        mode = self.cfg_v2p.get('use_random_ball_target')
+        tm = 1 if mode == 'continuous' else (2 if mode else 0)
+        seed = torch.rand(3 if tm == 1 else (N if tm == 2 else 1), device=dev)
+        cfg = dict(n=N, pool_size=P, ball_stride=26, bodies_per_env=26, reaction_nframes=int(self.cfg_v2p.get('reset_reaction_nframes', 70)),
+                   target_mode=tm, target_min=self._target_bounce_min.tolist() if not hasattr(self, "_tmin") else self._tmin,
+                   target_max=self._target_bounce_max.tolist() if not hasattr(self, "_tmax") else self._tmax)
+        self._tmin, self._tmax = cfg["target_min"], cfg["target_max"]
+        native_v2p.task_reset(cfg, dict(
+            reset_reaction=self._reset_reaction_buf, reset_recovery=self._reset_recovery_buf,
+            pool_rand=torch.randint(0, P, (N,), device=dev), side_rand=torch.randint(-1000, 1000, (N,), device=dev),
+            frame_rand=torch.randint(-5, 5, (N,), device=dev), target_seed=seed, pool=t._ball_pool, ball_states=t._root_states[1:],
+            rigid_body_state=t._rigid_body_state, ball_pos=t._ball_pos, ball_vel=t._ball_vel, bounce_pos=t._bounce_pos,
+            ball_traj=self._ball_traj, est_bounce_pos=self._est_bounce_pos, est_bounce_time=self._est_bounce_time,
+            est_max_height=self._est_max_height, target_bounce_pos=self._target_bounce_pos, has_bounce=t._has_bounce,
+            has_contact=t._has_racket_ball_contact, bounce_in=self._bounce_in, est_bounce_in=self._est_bounce_in, tar_time=self._tar_time,
+            tar_time_total=self._tar_time_total, tar_action=self._tar_action, num_reset_reaction=self._num_reset_reaction,
+            swing_type_cycle=self._mvae_player._swing_type_cycle))
+        if update_state:
+            self._physics_player.task._update_state_from_sim()   # :186-187 "setting the right fields to compute obs"
+        post = dict(self._post_cfg)
+        post["obs_only"] = 1
+        native_v2p.controller_post(post, self._tensors())
+
     def _reset_envs(self, env_ids):
+        """:173-201.  Humanoid part (id list from the agent): motion generator reset, FK pose -> sim state (2 launches), counters.
+        Task part (device masks, sampled BEFORE they are cleared like the reference's id lists): balls, recovery / reaction
+        bookkeeping, obs refresh.  No nonzero() / host sync inside."""
+        task = self._physics_player.task
+        n = len(env_ids)
+        if n > 0:
+            env_ids = env_ids.to(self.device, dtype=torch.long).contiguous()
+            self._mvae_player.reset(env_ids)
+            task._reset_actors(env_ids)
+            for buf in (self.progress_buf, self.reset_buf, self._terminate_buf, self._num_reset_reaction):
+                buf.index_fill_(0, env_ids, 0)
+            self._distance.index_fill_(0, env_ids, 0.0)
+            self._num_reset.index_add_(0, env_ids, torch.ones_like(env_ids))
+        self._reset_tasks_fast(update_state=n > 0)
+        if n > 0:
+            self._reset_reaction_buf.index_fill_(0, env_ids, False)
+            self._reset_recovery_buf.index_fill_(0, env_ids, False)
+        self._has_init = True
+
+    def _reset_envs_idlist(self, env_ids):
+        """The same reset written like the reference (nonzero() id lists + indexed torch ops, :173-201).  Kept as the
+        executable specification the mask-driven kernels are tested against (tests/test_gpu_v2p.py); not used on the hot path."""
         task = self._physics_player.task
         reaction_ids = self._reset_reaction_buf.nonzero(as_tuple=False).flatten()
         recovery_ids = self._reset_recovery_buf.nonzero(as_tuple=False).flatten()
@@ -287,7 +353,7 @@ class PhysicsMVAEController:
 
     def physics_step(self):
         self._physics_player.run_one_step()
-        self._ball_traj = self._ball_traj.roll(-1, dims=1)
+        self._ball_traj.copy_(self._ball_traj.roll(-1, dims=1))   # in place: persistent state keeps its address (CUDA-graph safe)
         self._ball_traj[:, -1] = 0
 
     def post_physics_step(self):
@@ -331,9 +397,36 @@ class PhysicsMVAEController:
         self._sub_rewards.copy_(keep[6])
 
     def step(self, actions):
+        if self._graph is not None:
+            self._graph_actions.copy_(actions)
+            self._graph.replay()
+            return
         self.pre_physics_step(actions.to(self.device, dtype=torch.float))
         self.physics_step()
         self.post_physics_step()
+
+    def enable_cuda_graph(self, warmup=3):
+        """Capture one whole high-level step (motion generator + FK targets + obs + low-level policy + fused physics + fused
+        post step: ~70 launches) into a CUDA graph; afterwards `step()` = one copy + one graph launch.  Requirements: the motion
+        player and the low-level policy update their state in place and make no host synchronisation (true for the synthetic
+        player and for plain nn.Module policies); `reset()` stays eager between replays (it edits the same buffers in place)."""
+        assert self._graph is None
+        self._graph_actions = torch.zeros(self.num_envs, self.num_actions, device=self.device)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.pre_physics_step(self._graph_actions)
+                self.physics_step()
+                self.post_physics_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.pre_physics_step(self._graph_actions)
+            self.physics_step()
+            self.post_physics_step()
+        self._graph = g
 
     def get_aux_losses(self, model_res_dict):
         """:461-472 (autograd-carrying, PyTorch)"""
