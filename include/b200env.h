@@ -173,7 +173,8 @@ int b200env_motion_state(b200env_handle h, const int64_t* motion_ids, const floa
                          float* dof_vel, float* key_pos, float* rb_pos, float* rb_rot, void* stream);
 
 /* replaces compute_humanoid_observations_imitation (humanoid_smpl_im.py:773-850 ==
- * models/im_network_builder.py:262-338): obs [n,1+..=734 for 24 bodies]. */
+ * models/im_network_builder.py:262-338): obs [n,1+..=734 for 24 bodies].  Bit 1 of `local_root_obs` selects the
+ * 'joint_pos' variant compute_humanoid_observations_imitation_jpos (:853-915, 513 wide). */
 int b200env_obs_imitation(b200env_handle h, int32_t n, const float* body_pos, const float* body_rot,
                           const float* target_pos, const float* target_rot, const float* dof_pos, const float* dof_vel,
                           const float* target_dof_pos, const float* body_vel, const float* body_ang_vel,

@@ -17,6 +17,12 @@ int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rot
                         const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
                         float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, void* stream);
 
+/* replaces the fix_head_orientation block of _set_target_motion_state (env/tasks/humanoid_smpl_im_mvae.py:605-634):
+ * rb_pos/rb_rot [n,24,*] = FK of the uncorrected pose (MuJoCo order, head_body = 13); joint_rotmat [n,24,3,3] (SMPL order) is
+ * corrected in place at SMPL joints Head (15) and Neck (12). */
+int b200v2p_fix_head(int32_t n, const float* rb_pos, const float* rb_rot, int32_t head_body, const float* ball_pos, const float* root_pos,
+                     float* joint_rotmat, void* stream);
+
 /* replaces apply_external_force_to_ball (env/tasks/humanoid_smpl_im_mvae.py:711-739): drag + Magnus lift, bounce flag */
 int b200v2p_ball_aero(int32_t n, const float* ball_states, int32_t stride, uint8_t* has_bounce, uint8_t* has_bounce_now, float* bounce_pos,
                       float* force, int32_t substeps, float spin_scale, void* stream);

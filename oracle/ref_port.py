@@ -218,6 +218,20 @@ def compute_humanoid_observations_imitation(body_pos, body_rot, target_pos, targ
                            target_rel_body_rot_obs, motion_bodies), axis=-1)
 
 
+def compute_humanoid_observations_imitation_jpos(body_pos, body_rot, target_pos, target_rot, dof_pos, dof_vel,
+                                                 target_dof_pos, body_vel, body_ang_vel, motion_bodies,
+                                                 local_root_obs=True, root_height_obs=True):
+    """env/tasks/humanoid_smpl_im.py:853-915 (obs_type 'joint_pos'): the same features without the rotation / dof targets"""
+    full = compute_humanoid_observations_imitation(body_pos, body_rot, target_pos, target_rot, dof_pos, dof_vel, target_dof_pos,
+                                                   body_vel, body_ang_vel, motion_bodies, local_root_obs, root_height_obs)
+    B, D = body_pos.shape[1], dof_pos.shape[1]
+    o = 1 + (B - 1) * 3 + B * 6 + B * 6 + D          # end of dof_vel
+    rel_h = full[:, o:o + 1]
+    rel_2d = full[:, o + 7:o + 9]
+    rel_body = full[:, o + 11 + D:o + 11 + D + B * 3]
+    return np.concatenate([full[:, :o], rel_h, rel_2d, rel_body, motion_bodies], axis=-1)
+
+
 def compute_humanoid_obs_raw(body_pos, body_rot, dof_pos, dof_vel, body_vel, body_ang_vel, motion_bodies):
     """env/tasks/humanoid_smpl_im.py:653-668 with obs_names of :198 -> obs_buf[N,461]."""
     N = body_pos.shape[0]

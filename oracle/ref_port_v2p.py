@@ -302,3 +302,44 @@ def controller_reset(root_pos, court_min, court_max, obs_has_nan, progress, max_
     recovery = recovery & ~terminate
     reaction = reaction | reset.astype(bool)
     return reset, terminate_buf, reaction, recovery
+
+
+# --------------------------------------------------------------------------- a13b: head look-at correction
+def angle_axis_to_rotation_matrix(aa, eps=1e-6):
+    """utils/konia_transform.py:250-334"""
+    f = aa.dtype.type
+    theta2 = np.sum(aa * aa, -1, keepdims=True)
+    theta = np.sqrt(np.maximum(theta2, f(eps)))
+    w = aa / (theta + f(eps))
+    wx, wy, wz = w[..., 0:1], w[..., 1:2], w[..., 2:3]
+    c, s_ = np.cos(theta), np.sin(theta)
+    one = f(1.0)
+    normal = np.concatenate([c + wx * wx * (one - c), wx * wy * (one - c) - wz * s_, wy * s_ + wx * wz * (one - c),
+                             wz * s_ + wx * wy * (one - c), c + wy * wy * (one - c), -wx * s_ + wy * wz * (one - c),
+                             -wy * s_ + wx * wz * (one - c), wx * s_ + wy * wz * (one - c), c + wz * wz * (one - c)], -1)
+    rx, ry, rz = aa[..., 0:1], aa[..., 1:2], aa[..., 2:3]
+    k1 = np.ones_like(rx)
+    taylor = np.concatenate([k1, -rz, ry, rz, k1, -rx, -ry, rx, k1], -1)
+    return np.where(theta2 > eps, normal, taylor).reshape(aa.shape[:-1] + (3, 3))
+
+
+def fix_head_orientation(joint_rotmat, head_rot_xyzw, head_pos, ball_pos, root_pos, head=15, neck=12):
+    """env/tasks/humanoid_smpl_im_mvae.py:605-634: returns the joint rotations with Head / Neck yawed half-way each towards
+    the ball (no correction when the ball is behind the player or wider than 4 m)."""
+    f = joint_rotmat.dtype.type
+    m = quaternion_to_rotation_matrix_wxyz(head_rot_xyzw[:, [3, 0, 1, 2]])
+    look = m @ np.array([0, 0, 1], joint_rotmat.dtype)
+    look = look[:, :2] / np.maximum(np.linalg.norm(look[:, :2], axis=-1, keepdims=True), f(1e-12))
+    hb = ball_pos[:, :2] - head_pos[:, :2]
+    hb = hb / np.maximum(np.linalg.norm(hb, axis=-1, keepdims=True), f(1e-12))
+    d = np.arctan2(hb[:, 1], hb[:, 0]) - np.arctan2(look[:, 1], look[:, 0])
+    d = np.where(d > math.pi, d - f(math.pi * 2), d)
+    d = np.where(d < -math.pi, d + f(math.pi * 2), d)
+    miss = (ball_pos[:, 1] < root_pos[:, 1] - 0.5) | (np.abs(ball_pos[:, 0]) > 4)
+    d = np.where(miss, f(0), d).astype(joint_rotmat.dtype)
+    jr = rotation_matrix_to_angle_axis(joint_rotmat[:, [head, neck]])
+    jr[:, 0, 1] += d / 2
+    jr[:, 1, 1] += d / 2
+    out = joint_rotmat.copy()
+    out[:, [head, neck]] = angle_axis_to_rotation_matrix(jr)
+    return out

@@ -90,7 +90,8 @@ def obs_imitation():
     obs = H.compute_humanoid_observations_imitation(*inp.values(), True, True)
     obs_nl = H.compute_humanoid_observations_imitation(*inp.values(), False, False)
     obs64 = H.compute_humanoid_observations_imitation(*[x.double() for x in inp.values()], True, True)
-    npz("obs_imitation.npz", **inp, obs=obs, obs_nolocal_noheight=obs_nl, obs_f64=obs64)
+    obs_jpos = H.compute_humanoid_observations_imitation_jpos(*inp.values(), True, True)
+    npz("obs_imitation.npz", **inp, obs=obs, obs_nolocal_noheight=obs_nl, obs_f64=obs64, obs_jpos=obs_jpos)
 
 
 def dof_reward_reset():

@@ -313,7 +313,44 @@ def controller():
     npz("v2p_controller.npz", **rec)
 
 
+def fix_head():
+    """_set_target_motion_state with fix_head_orientation (:600-661): head / neck yaw correction towards the ball"""
+    g = torch.Generator().manual_seed(25)
+    N = 48
+    t = FakePlayer()
+    t.device = 'cpu'
+    t.num_envs = N
+    t.dt = 2 * (1.0 / 60.0)
+    t.cfg_v2p = {'fix_head_orientation': True}
+    t._head_body_id = 13
+    t._build_mujoco_smpl_transform()
+    rest = rest_joints_smpl_order()
+    t._smpl = SimpleNamespace(joint_pos_bind=rest.unsqueeze(0).repeat(N, 1, 1), parents=torch.tensor(SMPL_PARENTS))
+    aa = 0.4 * torch.randn(N, 24, 3, generator=g)
+    aa[:, 0] = torch.tensor([1.2092, 1.2092, 1.2092]) + 0.1 * torch.randn(N, 3, generator=g)   # ~ the z-up base rotation
+    aa[0, 15] = 0
+    aa[0, 12] = 0
+    rm = angle_axis_to_rotation_matrix(aa.view(-1, 3)).view(N, 24, 3, 3)
+    t._mvae_player = SimpleNamespace(_root_pos=torch.randn(N, 3, generator=g) * torch.tensor([2.0, 2.0, 0.1]) + torch.tensor([0.0, -13.0, 0.95]),
+                                     _joint_rotmat=rm.clone())
+    t._ball_pos = torch.randn(N, 3, generator=g) * torch.tensor([3.0, 8.0, 0.5]) + torch.tensor([0.0, -2.0, 1.0])
+    t._ball_pos[1, 0] = 4.5                       # |x| > 4: miss -> no correction
+    t._ball_pos[2, 1] = -20.0                     # behind the player: miss
+    t._root_pos = t._mvae_player._root_pos + 0.05 * torch.randn(N, 3, generator=g)
+    t._prev_target_root_pos = t._mvae_player._root_pos - 0.02
+    o = t._smpl_to_sim(t._mvae_player._root_pos.clone(), rm)
+    t._prev_target_rb_rot = torch.nn.functional.normalize(o[7] + 0.02 * torch.randn(N, 24, 4, generator=g), dim=-1)
+    t._set_target_motion_state()
+    npz("v2p_fix_head.npz", rest=rest, parents=np.array(SMPL_PARENTS), smpl_2_mujoco=np.array(t._smpl_2_mujoco), dt=np.array(t.dt),
+        rotmat_in=rm, player_root_pos=t._mvae_player._root_pos, ball_pos=t._ball_pos, root_pos=t._root_pos,
+        prev_target_root_pos=t._prev_target_root_pos, prev_target_rb_rot=t._prev_target_rb_rot,
+        rotmat_out=t._mvae_player._joint_rotmat, target_root_rot=t._target_root_rot, target_dof_pos=t._target_dof_pos,
+        target_dof_vel=t._target_dof_vel, target_rb_pos=t._target_rb_pos, target_rb_rot=t._target_rb_rot,
+        target_root_vel=t._target_root_vel)
+
+
 if __name__ == "__main__":
+    fix_head()
     smpl_to_sim()
     ball()
     update_state()

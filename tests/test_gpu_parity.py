@@ -169,6 +169,9 @@ def test_obs_imitation_golden(small_lib):
     np.testing.assert_allclose(obs.cpu().numpy(), g["obs"], rtol=0, atol=1e-5)
     obs = task.compute_imitation_obs(*args, False, False)
     np.testing.assert_allclose(obs.cpu().numpy(), g["obs_nolocal_noheight"], rtol=0, atol=1e-5)
+    jp = task.compute_imitation_obs(*args, True, True, obs_type='joint_pos')   # :853-915
+    assert jp.shape[1] == 513
+    np.testing.assert_allclose(jp.cpu().numpy(), g["obs_jpos"], rtol=0, atol=1e-5)
 
 
 def snapshot(task):

@@ -305,3 +305,23 @@ def test_humanoid_reset_kernel_matches_idlist_path():
     keep = torch.ones(N, dtype=torch.bool, device=DEV); keep[ids] = False
     assert torch.equal(got["ds"].view(N, -1)[keep], before["ds"].view(N, -1)[keep])      # other envs untouched
     assert torch.equal(got["rb"].view(N, 26, 13)[keep][:, :25], before["rb"].view(N, 26, 13)[keep][:, :25])
+
+
+def test_fix_head_golden():
+    from vid2player3d_b200 import native_v2p as V
+    g = golden("v2p_fix_head.npz")
+    n = g["rotmat_in"].shape[0]
+    mk = lambda: dict(root_rot=torch.zeros(n, 4, device=DEV), dof_pos=torch.zeros(n, 69, device=DEV), root_vel=torch.zeros(n, 3, device=DEV),  # noqa: E731
+                      root_ang_vel=torch.zeros(n, 3, device=DEV), dof_vel=torch.zeros(n, 69, device=DEV),
+                      rb_pos=torch.zeros(n, 24, 3, device=DEV), rb_rot=torch.zeros(n, 24, 4, device=DEV))
+    rest, par, s2m = T(g["rest"]), T(g["parents"], torch.int32), T(g["smpl_2_mujoco"], torch.int32)
+    rm = T(g["rotmat_in"])
+    a = mk()
+    V.smpl_to_sim(T(g["player_root_pos"]), rm, rest, par, s2m, float(g["dt"]), a)
+    V.fix_head(a["rb_pos"], a["rb_rot"], T(g["ball_pos"]), T(g["root_pos"]), rm)
+    close(rm, g["rotmat_out"], 2e-6)
+    b = mk()
+    V.smpl_to_sim(T(g["player_root_pos"]), rm, rest, par, s2m, float(g["dt"]), b, prev_root_pos=T(g["prev_target_root_pos"]),
+                  prev_rb_rot=T(g["prev_target_rb_rot"]))
+    close(b["dof_pos"], g["target_dof_pos"], 2e-5); close(b["rb_pos"], g["target_rb_pos"], 2e-5); close(b["rb_rot"], g["target_rb_rot"], 2e-5)
+    close(b["dof_vel"], g["target_dof_vel"], 2e-3)

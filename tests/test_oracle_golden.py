@@ -47,6 +47,8 @@ def test_obs_imitation():
                            "body_vel", "body_ang_vel", "motion_bodies")]
     close(R.compute_humanoid_observations_imitation(*args, True, True), g["obs"], 1e-5)
     close(R.compute_humanoid_observations_imitation(*args, False, False), g["obs_nolocal_noheight"], 1e-5)
+    close(R.compute_humanoid_observations_imitation_jpos(*args, True, True), g["obs_jpos"], 1e-5)
+    assert g["obs_jpos"].shape[1] == 513
     a64 = [a.astype(np.float64) for a in args]
     close(R.compute_humanoid_observations_imitation(*a64, True, True), g["obs_f64"], 1e-12)
     # float32 reference vs float64 oracle: the tolerance the CUDA kernel is held to

@@ -86,3 +86,15 @@ def test_controller_obs_rewards_estimator_reset():
     assert np.array_equal(reset, g["reset"]) and np.array_equal(term, g["terminate"])
     assert np.array_equal(rea, g["reset_reaction"]) and np.array_equal(rec, g["reset_recovery"])
     assert 0 < reset.sum() < len(reset)
+
+
+def test_fix_head_orientation():
+    g = golden("v2p_fix_head.npz")
+    a = V.smpl_to_sim(g["player_root_pos"], g["rotmat_in"], g["rest"], g["parents"], g["smpl_2_mujoco"], float(g["dt"]))
+    out = V.fix_head_orientation(g["rotmat_in"], a[7][:, 13], a[6][:, 13], g["ball_pos"], g["root_pos"])
+    close(out, g["rotmat_out"], 2e-6)
+    assert np.abs(out - g["rotmat_in"]).max() > 0.05          # a correction happened ...
+    assert np.array_equal(out[1], g["rotmat_in"][1]) or np.abs(out[1] - g["rotmat_in"][1]).max() < 2e-6   # ... except for the "miss" rows
+    b = V.smpl_to_sim(g["player_root_pos"], out, g["rest"], g["parents"], g["smpl_2_mujoco"], float(g["dt"]),
+                      prev_root_pos=g["prev_target_root_pos"], prev_rb_rot=g["prev_target_rb_rot"])
+    close(b[2], g["target_dof_pos"], 2e-5); close(b[6], g["target_rb_pos"], 2e-5); close(b[7], g["target_rb_rot"], 2e-5)

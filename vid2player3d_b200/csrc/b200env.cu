@@ -1565,11 +1565,13 @@ obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restri
                      const float* __restrict__ target_pos, const float* __restrict__ target_rot, const float* __restrict__ dof_pos,
                      const float* __restrict__ dof_vel, const float* __restrict__ target_dof_pos, const float* __restrict__ body_vel,
                      const float* __restrict__ body_ang_vel, const float* __restrict__ motion_bodies, int local_root_obs,
-                     int root_height_obs, float* __restrict__ obs) {
+                     int root_height_obs, float* __restrict__ obs, int jpos) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
   if (e >= n) return;
-  const int W = 1 + (nb - 1) * 3 + nb * 6 + nb * 3 + nb * 3 + nd + 1 + 6 + 2 + 2 + nd + nb * 3 + nb * 6 + shape_dim;
+  // jpos = compute_humanoid_observations_imitation_jpos (:853-915): no rotation / heading / dof targets
+  const int W = jpos ? 1 + (nb - 1) * 3 + nb * 6 + nb * 3 + nb * 3 + nd + 1 + 2 + nb * 3 + shape_dim
+                     : 1 + (nb - 1) * 3 + nb * 6 + nb * 3 + nb * 3 + nd + 1 + 6 + 2 + 2 + nd + nb * 3 + nb * 6 + shape_dim;
   float* o = obs + e * W;
   const bool act = lane < nb;
   float p[3] = {0, 0, 0}, q[4] = {0, 0, 0, 1}, v[3] = {0, 0, 0}, w[3] = {0, 0, 0}, tp[3] = {0, 0, 0}, tq[4] = {0, 0, 0, 1};
@@ -1624,22 +1626,32 @@ obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restri
   off += nb * 6;
   for (int k = lane; k < nd; k += 32) o[off + k] = dof_vel[e * nd + k];
   off += nd;
-  if (lane == 0) {
-    o[off] = rp[2] - trp[2];
-    float cj[4] = {-root_rot[0], -root_rot[1], -root_rot[2], root_rot[3]}, rel[4], tn[6];
-    qmul(t_root_rot, cj, rel);
-    ref_tan_norm(rel, tn);
+  if (jpos) {
+    if (lane == 0) {
+      o[off] = rp[2] - trp[2];
+      float d[3] = {trp[0] - rp[0], trp[1] - rp[1], trp[2] - rp[2]}, l[3];
+      ref_quat_rotate(hq, d, l);
+      o[off + 1] = l[0]; o[off + 2] = l[1];
+    }
+    off += 3;
+  } else {
+    if (lane == 0) {
+      o[off] = rp[2] - trp[2];
+      float cj[4] = {-root_rot[0], -root_rot[1], -root_rot[2], root_rot[3]}, rel[4], tn[6];
+      qmul(t_root_rot, cj, rel);
+      ref_tan_norm(rel, tn);
 #pragma unroll
-    for (int k = 0; k < 6; k++) o[off + 1 + k] = tn[k];
-    float d[3] = {trp[0] - rp[0], trp[1] - rp[1], trp[2] - rp[2]}, l[3];
-    ref_quat_rotate(hq, d, l);
-    o[off + 7] = l[0]; o[off + 8] = l[1];
-    const float dh = t_heading - heading;
-    o[off + 9] = cosf(dh); o[off + 10] = sinf(dh);
+      for (int k = 0; k < 6; k++) o[off + 1 + k] = tn[k];
+      float d[3] = {trp[0] - rp[0], trp[1] - rp[1], trp[2] - rp[2]}, l[3];
+      ref_quat_rotate(hq, d, l);
+      o[off + 7] = l[0]; o[off + 8] = l[1];
+      const float dh = t_heading - heading;
+      o[off + 9] = cosf(dh); o[off + 10] = sinf(dh);
+    }
+    off += 11;
+    for (int k = lane; k < nd; k += 32) o[off + k] = target_dof_pos[e * nd + k] - dof_pos[e * nd + k];
+    off += nd;
   }
-  off += 11;
-  for (int k = lane; k < nd; k += 32) o[off + k] = target_dof_pos[e * nd + k] - dof_pos[e * nd + k];
-  off += nd;
   if (act) {
     float d[3] = {tp[0] - p[0], tp[1] - p[1], tp[2] - p[2]}, l[3];
     ref_quat_rotate(hq, d, l);
@@ -1647,14 +1659,16 @@ obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restri
     for (int k = 0; k < 3; k++) o[off + lane * 3 + k] = l[k];
   }
   off += nb * 3;
-  if (act) {
-    float cj[4] = {-q[0], -q[1], -q[2], q[3]}, rel[4], tn[6];
-    qmul(cj, tq, rel);
-    ref_tan_norm(rel, tn);
+  if (!jpos) {
+    if (act) {
+      float cj[4] = {-q[0], -q[1], -q[2], q[3]}, rel[4], tn[6];
+      qmul(cj, tq, rel);
+      ref_tan_norm(rel, tn);
 #pragma unroll
-    for (int k = 0; k < 6; k++) o[off + lane * 6 + k] = tn[k];
+      for (int k = 0; k < 6; k++) o[off + lane * 6 + k] = tn[k];
+    }
+    off += nb * 6;
   }
-  off += nb * 6;
   if (lane < shape_dim) o[off + lane] = motion_bodies[e * shape_dim + lane];
 }
 
@@ -1939,8 +1953,8 @@ int b200env_obs_imitation(b200env_handle h, int32_t n, const float* body_pos, co
   const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
   obs_imitation_kernel<<<grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(n, nbl, h->model.nd, h->cfg.shape_dim, body_pos, body_rot,
                                                                               target_pos, target_rot, dof_pos, dof_vel, target_dof_pos,
-                                                                              body_vel, body_ang_vel, motion_bodies, local_root_obs,
-                                                                              root_height_obs, obs);
+                                                                              body_vel, body_ang_vel, motion_bodies, local_root_obs & 1,
+                                                                              root_height_obs, obs, (local_root_obs >> 1) & 1);
   CUDA_OK(cudaGetLastError());
   h->launches++;
   return 0;

@@ -188,6 +188,56 @@ smpl_to_sim_kernel(int n, const float* __restrict__ root_pos, const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------ a13b: head look-at correction
+// angle_axis_to_rotation_matrix (konia_transform.py:250-334)
+__device__ __forceinline__ void aa_to_rotmat(const float* aa, float* m) {
+  const float theta2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  if (theta2 > 1e-6f) {
+    const float theta = sqrtf(fmaxf(theta2, 1e-6f));
+    const float wx = aa[0] / (theta + 1e-6f), wy = aa[1] / (theta + 1e-6f), wz = aa[2] / (theta + 1e-6f);
+    const float c = cosf(theta), s = sinf(theta), k = 1.0f - c;
+    m[0] = c + wx * wx * k; m[1] = wx * wy * k - wz * s; m[2] = wy * s + wx * wz * k;
+    m[3] = wz * s + wx * wy * k; m[4] = c + wy * wy * k; m[5] = -wx * s + wy * wz * k;
+    m[6] = -wy * s + wx * wz * k; m[7] = wx * s + wy * wz * k; m[8] = c + wz * wz * k;
+  } else {
+    m[0] = 1.0f; m[1] = -aa[2]; m[2] = aa[1]; m[3] = aa[2]; m[4] = 1.0f; m[5] = -aa[0]; m[6] = -aa[1]; m[7] = aa[0]; m[8] = 1.0f;
+  }
+}
+__global__ void fix_head_kernel(int n, const float* __restrict__ rb_pos, const float* __restrict__ rb_rot, int head_body,
+                                const float* __restrict__ ball_pos, const float* __restrict__ root_pos, float* joint_rotmat) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float* hq = rb_rot + (e * 24 + head_body) * 4;
+  const float qw[4] = {hq[3], hq[0], hq[1], hq[2]};
+  float m[9];
+  quat_wxyz_to_rotmat(qw, m);
+  float lx = m[2], ly = m[5];   // head_rotmat @ (0,0,1), xy part
+  float ln = fmaxf(sqrtf(lx * lx + ly * ly), 1e-12f);
+  lx /= ln; ly /= ln;
+  float bx = ball_pos[e * 3] - rb_pos[(e * 24 + head_body) * 3], by = ball_pos[e * 3 + 1] - rb_pos[(e * 24 + head_body) * 3 + 1];
+  float bn = fmaxf(sqrtf(bx * bx + by * by), 1e-12f);
+  bx /= bn; by /= bn;
+  float d = atan2f(by, bx) - atan2f(ly, lx);
+  if (d > 3.14159265358979323846f) d -= 6.283185307179586f;
+  if (d < -3.14159265358979323846f) d += 6.283185307179586f;
+  const bool miss = (ball_pos[e * 3 + 1] < root_pos[e * 3 + 1] - 0.5f) || (fabsf(ball_pos[e * 3]) > 4.0f);
+  if (miss) d = 0.0f;
+  const int joints[2] = {15, 12};  // SMPLPose.Head, SMPLPose.Neck
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    float* R = joint_rotmat + (e * 24 + joints[j]) * 9;
+    float Rl[9], q[4], aa[3], o[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rl[k] = R[k];
+    rotmat_to_quat_wxyz(Rl, q);
+    quat_wxyz_to_angle_axis(q, aa);
+    aa[1] += d / 2.0f;
+    aa_to_rotmat(aa, o);
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = o[k];
+  }
+}
+
 // ------------------------------------------------------------------------------------------ a10: ball aerodynamics
 #define BALL_R 0.032f
 #define BALL_KF 0.0019462794807519486f  // rho*pi*R^2/2, rho = 1.21 (tennis_ball.py:17-22)
@@ -519,6 +569,16 @@ int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rot
   smpl_to_sim_kernel<<<(n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(
       n, root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, prev_root_pos, prev_rb_rot, root_rot, dof_pos, root_vel, root_ang_vel,
       dof_vel, rb_pos, rb_rot);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_fix_head(int32_t n, const float* rb_pos, const float* rb_rot, int32_t head_body, const float* ball_pos, const float* root_pos,
+                     float* joint_rotmat, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !rb_pos || !rb_rot || !ball_pos || !root_pos || !joint_rotmat || head_body < 0 || head_body > 23)
+    return vfail(-1, "b200v2p_fix_head: bad arguments");
+  fix_head_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, rb_pos, rb_rot, head_body, ball_pos, root_pos, joint_rotmat);
   V_CUDA_OK();
   return 0;
 }

@@ -114,12 +114,12 @@ class Env:
                                           *[_ptr(out.get(k)) for k in names], _stream()))
 
     def obs_imitation(self, body_pos, body_rot, target_pos, target_rot, dof_pos, dof_vel, target_dof_pos, body_vel,
-                      body_ang_vel, motion_bodies, local_root_obs, root_height_obs, obs):
+                      body_ang_vel, motion_bodies, local_root_obs, root_height_obs, obs, jpos=False):
         n = int(body_pos.shape[0])
         _check(lib().b200env_obs_imitation(self._h, C.c_int32(n), _ptr(body_pos), _ptr(body_rot), _ptr(target_pos),
                                            _ptr(target_rot), _ptr(dof_pos), _ptr(dof_vel), _ptr(target_dof_pos),
                                            _ptr(body_vel), _ptr(body_ang_vel), _ptr(motion_bodies),
-                                           C.c_int32(int(local_root_obs)), C.c_int32(int(root_height_obs)), _ptr(obs),
+                                           C.c_int32(int(bool(local_root_obs)) | (2 if jpos else 0)), C.c_int32(int(root_height_obs)), _ptr(obs),
                                            _stream()))
 
     def physics_only(self, root, dof_pos, dof_vel, pd_tar, ext_wrench, rb_out, contact_out, n_steps=1, ball=None, ball_hits=None):

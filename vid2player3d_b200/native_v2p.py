@@ -5,7 +5,7 @@ from . import abi
 from .native import _ptr, _stream, lib
 
 SYMBOLS = ["b200v2p_last_error", "b200v2p_smpl_to_sim", "b200v2p_ball_aero", "b200v2p_ball_reset", "b200v2p_update_state",
-           "b200v2p_controller_post", "b200v2p_task_reset", "b200v2p_actor_reset"]
+           "b200v2p_controller_post", "b200v2p_task_reset", "b200v2p_actor_reset", "b200v2p_fix_head"]
 GRIP_NORMAL = {'eastern': (0.0, 1.0, 0.0), 'semi_western': (0.0, 2.0 ** -0.5, 2.0 ** -0.5)}
 REWARD_TYPES = {'reach': 0, 'return': 1, 'return_w_estimate': 2}
 
@@ -28,6 +28,11 @@ def smpl_to_sim(root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, out, p
     _check(lib().b200v2p_smpl_to_sim(C.c_int32(n), _c(root_pos), _c(joint_rotmat), _c(rest), _c(parents), _c(smpl_2_mujoco), C.c_float(dt),
                                      _c(prev_root_pos), _c(prev_rb_rot), _c(out["root_rot"]), _c(out["dof_pos"]), _c(out["root_vel"]),
                                      _c(out["root_ang_vel"]), _c(out["dof_vel"]), _c(out["rb_pos"]), _c(out["rb_rot"]), _stream()))
+
+
+def fix_head(rb_pos, rb_rot, ball_pos, root_pos, joint_rotmat, head_body=13):
+    _check(lib().b200v2p_fix_head(C.c_int32(int(rb_pos.shape[0])), _c(rb_pos), _c(rb_rot), C.c_int32(head_body), _c(ball_pos), _c(root_pos),
+                                  _c(joint_rotmat), _stream()))
 
 
 def ball_aero(ball_states, has_bounce, has_bounce_now, bounce_pos, force, substeps, spin_scale, stride=None):

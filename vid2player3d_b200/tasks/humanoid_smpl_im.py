@@ -333,16 +333,20 @@ class HumanoidSMPLIM(BaseTask):
                 self.model.a2c_network.forward_context(self.context_feat, self.context_mask)
 
     def compute_imitation_obs(self, body_pos, body_rot, target_pos, target_rot, dof_pos, dof_vel, target_dof_pos,
-                              body_vel, body_ang_vel, motion_bodies, local_root_obs=True, root_height_obs=True):
+                              body_vel, body_ang_vel, motion_bodies, local_root_obs=True, root_height_obs=True,
+                              obs_type='full'):
         """compute_humanoid_observations_imitation (:773-850 == models/im_network_builder.py:262-338) as one
-        kernel; what the embodied_pose network calls on the raw 461-d obs + context."""
+        kernel; what the embodied_pose network calls on the raw 461-d obs + context.  obs_type 'joint_pos' is
+        compute_humanoid_observations_imitation_jpos (:853-915)."""
         n, nb = body_pos.shape[0], body_pos.shape[1]
         c = lambda x: x.contiguous().float()  # noqa: E731
-        obs = torch.empty(n, 1 + (nb - 1) * 3 + nb * 6 + nb * 6 + self.num_dof + 11 + self.num_dof + nb * 9 +
-                          motion_bodies.shape[-1], device=self.device)
+        jpos = obs_type == 'joint_pos'
+        width = 1 + (nb - 1) * 3 + nb * 6 + nb * 6 + self.num_dof + motion_bodies.shape[-1]
+        width += (3 + nb * 3) if jpos else (11 + self.num_dof + nb * 9)
+        obs = torch.empty(n, width, device=self.device)
         self._env.obs_imitation(c(body_pos), c(body_rot), c(target_pos), c(target_rot), c(dof_pos), c(dof_vel),
                                 c(target_dof_pos), c(body_vel), c(body_ang_vel), c(motion_bodies), local_root_obs,
-                                root_height_obs, obs)
+                                root_height_obs, obs, jpos=jpos)
         return obs
 
     def get_aux_losses(self, model_res_dict):

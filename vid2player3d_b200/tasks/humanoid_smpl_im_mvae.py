@@ -39,8 +39,6 @@ class HumanoidSMPLIMMVAE(BaseTask):
         self.max_episode_length = env["episodeLength"]
         self._local_root_obs = env.get("localRootObs", True)
         self._root_height_obs = env.get("rootHeightObs", True)
-        if self.cfg_v2p.get("fix_head_orientation"):
-            raise NotImplementedError("fix_head_orientation (humanoid_smpl_im_mvae.py:605-634) is not on the kernel path yet")
         if self.cfg_v2p.get("dual_mode"):
             raise NotImplementedError("dual mode (humanoid_smpl_im_mvae_dual.py) is a later row (DESIGN.md 8)")
         self._num_humanoid_bodies = 24
@@ -184,6 +182,10 @@ class HumanoidSMPLIMMVAE(BaseTask):
             root += self._controller._res_root_actions
         out = dict(root_rot=self._target_root_rot, dof_pos=self._target_dof_pos, root_vel=self._target_root_vel,
                    root_ang_vel=self._target_root_ang_vel, dof_vel=self._target_dof_vel, rb_pos=self._target_rb_pos, rb_rot=self._target_rb_rot)
+        if self.cfg_v2p.get('fix_head_orientation'):    # :605-634: FK of the raw pose, yaw Head/Neck towards the ball (in place)
+            self._smpl_to_sim_into(root, self._mvae_player._joint_rotmat, self._tmp)
+            native_v2p.fix_head(self._tmp["rb_pos"], self._tmp["rb_rot"], self._ball_pos, self._root_pos, self._mvae_player._joint_rotmat,
+                                head_body=self._head_body_id)
         prev_rot = self._prev_target_rb_rot.clone()     # the kernel overwrites rb_rot rows it also reads as "previous"
         self._smpl_to_sim_into(root, self._mvae_player._joint_rotmat, out, self._prev_target_root_pos, prev_rot)
         self._target_root_pos.copy_(root)

@@ -191,7 +191,7 @@ class PhysicsMVAEController:
                             residual_force_scale=phys.get("residual_force_scale", 31.85), is_train=self._is_train,
                             asset=dict(assetFileName=phys.get("assetFileName", "smpl_mesh_humanoid_federer.xml")),
                             plane=dict(staticFriction=1.0, dynamicFriction=1.0, restitution=phys.get("plane_restitution", 0.0)),
-                            vid2player={k: v for k, v in self.cfg_v2p.items() if k != 'fix_head_orientation'},
+                            vid2player=dict(self.cfg_v2p),
                             keyBodies=[], contactBodies=[]),
                 "sim": {"substeps": phys.get("substeps", 2)}, "b200_physics": self.cfg.get("b200_physics", {})}
         task = HumanoidSMPLIMMVAE(pcfg, self._sim_params, self._physics_engine, "cuda", self.device_id, True)
