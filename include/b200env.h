@@ -27,7 +27,7 @@ extern "C" {
 #define B200_MAX_BODIES 32
 #define B200_MAX_DOF 96
 #define B200_MAX_KEY 8
-#define B200_ABI_VERSION 2
+#define B200_ABI_VERSION 3
 
 /* Per-asset constant block produced by vid2player3d_b200/model_compiler.py from the MJCF/STL
  * assets (replaces gym.load_asset + create_actor + set_actor_dof_properties:
@@ -190,6 +190,11 @@ int b200env_obs_imitation(b200env_handle h, int32_t n, const float* body_pos, co
 int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_steps, void* root, void* dof_pos,
                          void* dof_vel, const void* pd_tar, const void* ext_wrench, void* rb_out, void* contact_out,
                          void* ball, int32_t* ball_hits, void* stream);
+
+/* Heterogeneous assets per env (dual mode: env 2k = player 0's asset, env 2k+1 = player 1's,
+ * vid2player/env/tasks/humanoid_smpl_im_mvae.py:270-275 `motion_ids[1::2] = 1`): one handle per asset, all bound to the SAME
+ * tensors; handle-local env i of b200env_step is row env_first + env_stride * i.  num_envs at create = envs of the slice. */
+int b200env_set_env_slice(b200env_handle h, int32_t env_first, int32_t env_stride);
 
 /* number of kernels launched by this handle so far (bench.py "gpu_launches") */
 int64_t b200env_launch_count(b200env_handle h);

@@ -11,10 +11,11 @@ extern "C" {
 const char* b200v2p_last_error(void);
 
 /* replaces HumanoidSMPLIMMVAE._smpl_to_sim + _forward_kinematics (env/tasks/humanoid_smpl_im_mvae.py:897-946, utils/hybrik.py:597-652):
- * joint_rotmat [n,24,3,3] and rest [24,3] in SMPL joint order; outputs in MuJoCo body order (smpl_2_mujoco);
+ * joint_rotmat [n,24,3,3] and rest [num_rest,24,3] in SMPL joint order (env e uses shape e % num_rest: 1 = one player,
+ * 2 = dual mode's alternating players, n = a shape per env); outputs in MuJoCo body order (smpl_2_mujoco);
  * prev_* NULL -> zero velocities. */
-int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rotmat, const float* rest, const int32_t* parents,
-                        const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
+int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rotmat, const float* rest, int32_t num_rest,
+                        const int32_t* parents, const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
                         float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, void* stream);
 
 /* replaces the fix_head_orientation block of _set_target_motion_state (env/tasks/humanoid_smpl_im_mvae.py:605-634):
@@ -36,6 +37,9 @@ int b200v2p_ball_reset(int32_t n, const int64_t* env_ids, const int64_t* pool_in
 typedef struct b200v2p_state {
   int32_t n, bodies_per_env, ball_stride, root_stride, racket_body, wrist_body;
   float grip_normal[3];
+  /* dual_mode 'different' (:839-842, :79-84): odd envs use the second player's grip / racket bodies when dual != 0 */
+  int32_t dual, racket_body2, wrist_body2;
+  float grip_normal2[3];
   const float* rigid_body_state; /* [n, bodies_per_env, 13] */
   const float* root_states;      /* humanoid root row per env, stride root_stride floats */
   const float* ball_states;      /* ball root row per env, stride ball_stride floats */
@@ -51,7 +55,8 @@ typedef struct b200v2p_ctrl {
   int32_t n, bodies_per_env, ball_stride, racket_body, num_obs, obs_traj_len, use_target, reward_type, early_termination,
       max_episode_length, est_nx, est_ny;
   int32_t obs_only; /* 1: refresh obs_buf only (the _compute_observations call of _reset_envs :200-201), touch nothing else */
-  int32_t pad_;
+  int32_t dual;     /* 1: reset FSM of PhysicsMVAEControllerDual._compute_reset (env/tasks/physics_mvae_controller_dual.py:92-120):
+                       envs (2k, 2k+1) are opponents; reset_buf is only ever SET, terminate_buf is not written */
   float scale_pos, scale_phase, scale_bounce_pos, scale_bounce_time, w_pos, w_ball_pos;
   float court_min[2], court_max[2];
   float est_params[15]; /* VEL_X, VEL_Y, VSPIN, TRAJ_X, TRAJ_Y ranges (lo, hi, step) */
@@ -71,6 +76,14 @@ typedef struct b200v2p_ctrl {
   int64_t *reset_buf, *terminate_buf;
 } b200v2p_ctrl_t;
 int b200v2p_controller_post(const b200v2p_ctrl_t* c, void* stream);
+
+/* replaces TennisBallInEstimator.estimate (utils/tennis_ball_in_estimator.py:22-81), the table lookup of
+ * HumanoidSMPLIMMVAEDual._reset_balls (env/tasks/humanoid_smpl_im_mvae_dual.py:63-72): for query i the ball row
+ * ball_states + contact_ids[i]*stride (the ball the opponent just hit) is snapped to the table grid; outputs the incoming
+ * trajectory in the receiver's frame traj[n,50,3] and the snapped in / out ball states [n,13].  The caller scatters them
+ * (states[ball_ids] = in, then states[contact_ids] = out).  table [rows,50,2]; params = HEIGHT, VEL_X, VEL_Y, VSPIN (lo,hi,step). */
+int b200v2p_ball_in_estimate(int32_t n, const int64_t* contact_ids, const float* ball_states, int32_t stride, const float* table,
+                             int64_t table_rows, const double* params, float* traj, float* states_in, float* states_out, void* stream);
 
 /* replaces the per-step task part of PhysicsMVAEController._reset_envs when no humanoid needs a reset
  * (env/tasks/physics_mvae_controller.py:173-201: _reset_balls for the reaction envs :503-524, _reset_recovery_tasks :242-245,
@@ -98,6 +111,8 @@ int b200v2p_task_reset(const b200v2p_treset_t* r, void* stream);
 typedef struct b200v2p_areset {
   int32_t n, num_dof, bodies_per_env, root_stride, racket_body, racket_parent;
   float racket_offset[3];
+  int32_t dual;             /* 1: odd envs use racket_offset2 (second player's asset) */
+  float racket_offset2[3];
   const int64_t* env_ids;
   const float *src_root_pos, *src_root_rot, *src_dof_pos, *src_rb_pos, *src_rb_rot; /* [N,...] FK results */
   float *root_states, *dof_state, *rigid_body_state;

@@ -343,3 +343,99 @@ def fix_head_orientation(joint_rotmat, head_rot_xyzw, head_pos, ball_pos, root_p
     out = joint_rotmat.copy()
     out[:, [head, neck]] = angle_axis_to_rotation_matrix(jr)
     return out
+
+
+# --------------------------------------------------------------------------- dual mode
+def get_opponent_env_ids(env_ids):
+    """utils/common.py:111-115: partner ids, SORTED (so aligned with a sorted id list unless both envs of a pair are in it)"""
+    env_ids = np.asarray(env_ids)
+    if len(env_ids) == 0:
+        return env_ids
+    even = env_ids % 2 == 0
+    return np.sort(np.concatenate([env_ids[even] + 1, env_ids[~even] - 1]))
+
+
+def in_estimator_index(height, vel_x, vel_y, vspin, params):
+    """utils/tennis_ball_in_estimator.py:22-49: params rows = HEIGHT, VEL_X, VEL_Y, VSPIN ranges (lo, hi, step).
+    float32 tensor arithmetic with python scalars folded in one at a time, torch.round = half-to-even; the row index is the
+    float32 sum truncated by .long()."""
+    f = np.float32
+    H, VX, VY, VS = [tuple(float(x) for x in r) for r in np.asarray(params, np.float64)]
+    cl = lambda v, r: np.clip(v.astype(f), f(r[0]), f(r[1] - r[2]))  # noqa: E731
+    height, vel_x, vel_y, vspin = cl(height, H), cl(vel_x, VX), cl(vel_y, VY), cl(vspin, VS)
+    dim = [(r[1] - r[0]) / r[2] for r in (H, VX, VY, VS)]
+    rnd = lambda v, r: np.rint((v - f(r[0])) / f(r[2])).astype(f)  # noqa: E731
+    rh, rx, ry, rs = rnd(height, H), rnd(vel_x, VX), rnd(vel_y, VY), rnd(vspin, VS)
+    index = rh * f(dim[1]) * f(dim[2]) * f(dim[3]) + rx * f(dim[2]) * f(dim[3]) + ry * f(dim[3]) + rs
+    snap = lambda r_, r: r_ * f(r[2]) + f(r[0])  # noqa: E731
+    return index.astype(np.int64), (snap(rh, H), snap(rx, VX), snap(ry, VY), snap(rs, VS))
+
+
+def in_estimator_estimate(ball_states, table, params):
+    """TennisBallInEstimator.estimate (utils/tennis_ball_in_estimator.py:51-81): snap the outgoing ball to the table grid,
+    return the incoming trajectory in the receiver's frame (xy mirrored) and the snapped in / out ball states."""
+    f = np.float32
+    bs = ball_states.astype(f)
+    vel_x = np.sqrt((bs[:, 7:9] ** 2).sum(-1, dtype=f)).astype(f)
+    d = bs[:, 7:9] / vel_x[:, None]
+    vspin = (np.sqrt((bs[:, 10:13] ** 2).sum(-1, dtype=f)).astype(f) / f(math.pi * 2)).astype(f)
+    idx, (height, vx, vy, vs) = in_estimator_index(bs[:, 2], vel_x, bs[:, 9], vspin, params)
+    traj = table[idx].astype(f)
+    tt = np.concatenate([traj[:, :, :1] * d[:, None, :] + bs[:, None, :2], traj[:, :, 1:]], axis=-1)
+    tt[:, :, :2] *= f(-1)
+
+    def omega(v):
+        c = np.cross(v, np.array([0, 0, -1], f)).astype(f)
+        nn = np.maximum(np.sqrt((c * c).sum(-1, keepdims=True, dtype=f)), f(1e-12))
+        return (vs[:, None] * f(math.pi) * f(2)) * (c / nn)      # vspin * pi * 2 * normalize(.)
+    s_in = bs.copy()
+    s_in[:, :2] *= f(-1)
+    s_in[:, 2] = height
+    s_in[:, 7:9] = -vx[:, None] * d
+    s_in[:, 9] = vy
+    s_in[:, 10:13] = omega(s_in[:, 7:10])
+    s_out = s_in.copy()
+    s_out[:, :2] *= f(-1)
+    s_out[:, 7:9] *= f(-1)
+    s_out[:, 10:13] = omega(s_out[:, 7:10])
+    return tt, s_in, s_out
+
+
+def dual_reset_balls(ball_states, racket_pos, recovery_ids, ball_ids, rand3, table, params):
+    """HumanoidSMPLIMMVAEDual._reset_balls (env/tasks/humanoid_smpl_im_mvae_dual.py:52-80).  rand3 [3,len(recovery_ids)] = the three
+    torch.rand draws (vx, vy, vz of the serve) in call order.  Returns traj and the updated copy of ball_states; the flag / view
+    updates (:74-78) are listed in the returned dict."""
+    f = np.float32
+    bs = ball_states.astype(f).copy()
+    if len(recovery_ids) > 0:
+        bs[recovery_ids, :3] = racket_pos[recovery_ids]
+        bs[recovery_ids, 10:13] = np.array([-40, 0, 0], f)
+        bs[recovery_ids, 7] = rand3[0].astype(f) * f(4) + f(-2)
+        bs[recovery_ids, 8] = rand3[1].astype(f) * f(4) + f(28)
+        bs[recovery_ids, 9] = rand3[2].astype(f) * f(3) + f(5)
+    contact = get_opponent_env_ids(ball_ids)
+    traj, s_in, s_out = in_estimator_estimate(bs[contact], table, params)
+    bs[ball_ids] = s_in
+    bs[contact] = s_out
+    return traj, bs, dict(ball_pos=bs[ball_ids, 0:3], ball_vel=bs[ball_ids, 7:10])
+
+
+def dual_controller_reset(tar_action, has_contact, has_bounce, ball_pos, root_pos, root_vel, bounce_in, distance, reset_buf):
+    """PhysicsMVAEControllerDual._compute_reset (env/tasks/physics_mvae_controller_dual.py:92-120) + _compute_stats"""
+    in_recovery = tar_action == 0
+    miss_ball = ball_pos[:, 1] < root_pos[:, 1] - np.float32(1)
+    twice = has_bounce & (ball_pos[:, 2] < np.float32(0.05))
+    recovery = (tar_action == 1) & (has_contact | miss_ball | twice)
+    distance = distance + np.sqrt((root_vel[:, :2] ** 2).sum(-1))
+    reaction = np.zeros_like(recovery)
+    reaction[::2] = recovery[1::2]
+    reaction[1::2] = recovery[::2]
+    terminate = (recovery & ~has_contact) | (in_recovery & has_bounce & ~bounce_in)
+    reset = reset_buf.copy()
+    if terminate.sum() > 0:
+        terminate[::2] |= terminate[1::2]
+        terminate[1::2] |= terminate[::2]
+        reset[terminate] = 1
+        reaction[terminate] = False
+        recovery[terminate] = False
+    return reset, reaction, recovery, distance

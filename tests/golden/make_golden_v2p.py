@@ -5,6 +5,9 @@ through fake `self` objects.  Run in the build container only:  python tests/gol
   v2p_smpl_to_sim.npz   _smpl_to_sim / _forward_kinematics (:897-946) incl. finite-difference velocities   (a13)
   v2p_ball.npz          apply_external_force_to_ball (:711-739), _reset_balls (:503-524) + offline pool sampler (a10, a17)
   v2p_update_state.npz  _update_state_from_sim (:799-860)                                                   (a11, a12)
+  v2p_dual.npz          dual mode: TennisBallInEstimator.estimate (utils/tennis_ball_in_estimator.py:22-81),
+                        HumanoidSMPLIMMVAEDual._reset_balls (humanoid_smpl_im_mvae_dual.py:52-80),
+                        PhysicsMVAEControllerDual._compute_reset (physics_mvae_controller_dual.py:92-120)
   v2p_controller.npz    actor/task obs (:333-360), rewards (:493-602), check_out_of_court, _update_state + estimator
                         (:271-314, tennis_ball_out_estimator.py:164-205), _compute_reset (:408-436)          (a14-a16)
 """
@@ -349,7 +352,125 @@ def fix_head():
         target_root_vel=t._target_root_vel)
 
 
+class SmallInParams:
+    VEL_X_RANGE = (25, 26, 0.25)
+    VEL_Y_RANGE = (5, 6, 0.5)
+    VSPIN_RANGE = (5, 7, 0.5)
+    HEIGHT_RANGE = (0.5, 1.0, 0.1)
+
+
+def dual():
+    from env.tasks import humanoid_smpl_im_mvae_dual as MD
+    from env.tasks import physics_mvae_controller_dual as CD
+    from utils import tennis_ball_in_estimator as EI
+    g = torch.Generator().manual_seed(26)
+    rec = {}
+    # ---- in-estimator on a small synthetic grid (one set on the full-size parameter grid's index math as well)
+    est = EI.TennisBallInEstimator.__new__(EI.TennisBallInEstimator)
+    est.params = SmallInParams
+    rng = np.random.default_rng(5)
+    nrow = 5 * 4 * 2 * 4
+    tab = np.zeros((nrow, 50, 2), np.float32)
+    tab[..., 0] = np.cumsum(rng.uniform(0.3, 0.5, (nrow, 50)), axis=1)
+    tab[..., 1] = rng.uniform(0.05, 2.0, (nrow, 50))
+    est._ball_traj = torch.from_numpy(tab)
+    n = 96
+    bs = torch.zeros(n, 13)
+    bs[:, 0:3] = torch.randn(n, 3, generator=g) * torch.tensor([2.0, 2.0, 0.4]) + torch.tensor([0.0, -11.0, 0.8])
+    bs[:, 3:7] = rq(g, n)
+    bs[:, 7] = torch.randn(n, generator=g) * 4
+    bs[:, 8] = torch.rand(n, generator=g) * 3 + 24
+    bs[:, 9] = torch.rand(n, generator=g) * 2 + 4.5
+    bs[:, 10:13] = torch.randn(n, 3, generator=g) * 25
+    bs[0, 2], bs[1, 2] = 0.2, 3.0                       # clamped heights
+    orig = torch.Tensor.get_device
+    torch.Tensor.get_device = lambda self: torch.device('cpu')
+    try:
+        traj, s_in, s_out = est.estimate(bs.clone())
+        idx, snapped = est.get_ball_traj_index(bs[:, 2], bs[:, 7:9].norm(dim=-1), bs[:, 9], bs[:, 10:13].norm(dim=1) / (np.pi * 2))
+        # index math on the shipped (full-size) parameter grid
+        est_full = EI.TennisBallInEstimator.__new__(EI.TennisBallInEstimator)
+        est_full.params = EI.traj_in_params
+        h = torch.rand(4096, generator=g) * 2.0 + 0.3
+        vx = torch.rand(4096, generator=g) * 6 + 24.5
+        vy = torch.rand(4096, generator=g) * 4 + 4.5
+        vs = torch.rand(4096, generator=g) * 6 + 4.5
+        idx_full, snapped_full = est_full.get_ball_traj_index(h, vx, vy, vs)
+    finally:
+        torch.Tensor.get_device = orig
+    P = SmallInParams
+    rec.update(in_table=tab, in_params=np.array([P.HEIGHT_RANGE, P.VEL_X_RANGE, P.VEL_Y_RANGE, P.VSPIN_RANGE], np.float64),
+               in_params_full=np.array([EI.traj_in_params.HEIGHT_RANGE, EI.traj_in_params.VEL_X_RANGE, EI.traj_in_params.VEL_Y_RANGE,
+                                        EI.traj_in_params.VSPIN_RANGE], np.float64),
+               in_states=bs, in_traj=traj, in_states_in=s_in, in_states_out=s_out, in_index=idx,
+               full_h=h, full_vx=vx, full_vy=vy, full_vs=vs, full_index=idx_full, full_snapped=torch.stack(snapped_full, dim=-1))
+
+    # ---- HumanoidSMPLIMMVAEDual._reset_balls through the real method on a fake self
+    class FakeDual(MD.HumanoidSMPLIMMVAEDual):
+        def __init__(self):
+            pass
+    N = 32
+    t = FakeDual()
+    t.device = 'cpu'
+    t.cfg_v2p = {}
+    t._ball_in_estimator = est
+    t._ball_root_states = torch.zeros(N, 13)
+    t._ball_root_states[:, 0:3] = torch.randn(N, 3, generator=g) * torch.tensor([2.0, 2.0, 0.3]) + torch.tensor([0.0, -11.0, 0.8])
+    t._ball_root_states[:, 6] = 1
+    t._ball_root_states[:, 7] = torch.randn(N, generator=g) * 3
+    t._ball_root_states[:, 8] = torch.rand(N, generator=g) * 2 + 24.5
+    t._ball_root_states[:, 9] = torch.rand(N, generator=g) * 1.5 + 4.8
+    t._ball_root_states[:, 10:13] = torch.randn(N, 3, generator=g) * 25
+    t._mvae_player = SimpleNamespace(_racket_pos=torch.randn(N, 3, generator=g) * 0.5 + torch.tensor([0.3, -11.5, 1.0]))
+    t._has_bounce = torch.ones(N, dtype=torch.bool)
+    t._bounce_pos = torch.ones(N, 3)
+    t._has_racket_ball_contact = torch.ones(N, dtype=torch.bool)
+    t._ball_pos = torch.zeros(N, 3)
+    t._ball_vel = torch.zeros(N, 3)
+    rec["rb_states_before"] = t._ball_root_states.clone()
+    rec["rb_racket_pos"] = t._mvae_player._racket_pos.clone()
+    serve_recovery = torch.tensor([1, 5, 8])            # serving players (their opponents react): envs 0, 4, 9 receive
+    ball_ids = torch.tensor([0, 4, 9, 12, 17, 30])       # reaction envs that get a new incoming ball
+    torch.manual_seed(77)
+    rec["rb_rand"] = torch.stack([torch.rand(3), torch.rand(3), torch.rand(3)])   # the three torch.rand(num_envs) draws, in order
+    torch.manual_seed(77)
+    torch.Tensor.get_device = lambda self: torch.device('cpu')
+    try:
+        traj2 = t._reset_balls(serve_recovery, ball_ids)
+    finally:
+        torch.Tensor.get_device = orig
+    rec.update(rb_recovery_ids=serve_recovery, rb_ball_ids=ball_ids, rb_traj=traj2, rb_states_after=t._ball_root_states.clone(),
+               rb_has_bounce=t._has_bounce, rb_bounce_pos=t._bounce_pos, rb_has_contact=t._has_racket_ball_contact, rb_ball_pos=t._ball_pos,
+               rb_ball_vel=t._ball_vel)
+
+    # ---- PhysicsMVAEControllerDual._compute_reset
+    class FakeCtlDual(CD.PhysicsMVAEControllerDual):
+        def __init__(self):
+            pass
+    N = 128
+    c = FakeCtlDual()
+    player = SimpleNamespace(_has_racket_ball_contact=torch.rand(N, generator=g) < 0.3, _has_bounce=torch.rand(N, generator=g) < 0.5)
+    c._physics_player = SimpleNamespace(task=player)
+    c._tar_action = torch.randint(0, 2, (N,), generator=g)
+    c._ball_pos = torch.randn(N, 3, generator=g) * torch.tensor([3.0, 6.0, 0.1]) + torch.tensor([0.0, -9.0, 0.1])
+    c._root_pos = torch.randn(N, 3, generator=g) * torch.tensor([2.0, 2.0, 0.05]) + torch.tensor([0.0, -12.0, 0.9])
+    c._root_vel = torch.randn(N, 3, generator=g)
+    c._bounce_in = torch.rand(N, generator=g) < 0.6
+    c._distance = torch.rand(N, generator=g)
+    c.reset_buf = (torch.rand(N, generator=g) < 0.05).long()
+    c._reset_reaction_buf = torch.rand(N, generator=g) < 0.5
+    c._reset_recovery_buf = torch.rand(N, generator=g) < 0.5
+    for k in ("_tar_action", "_ball_pos", "_root_pos", "_root_vel", "_bounce_in", "_distance", "reset_buf"):
+        rec["cr" + k] = getattr(c, k).clone()
+    rec["cr_has_contact"], rec["cr_has_bounce"] = player._has_racket_ball_contact, player._has_bounce
+    c._compute_reset()
+    rec.update(cr_out_reset=c.reset_buf, cr_out_reaction=c._reset_reaction_buf, cr_out_recovery=c._reset_recovery_buf,
+               cr_out_distance=c._distance)
+    npz("v2p_dual.npz", **rec)
+
+
 if __name__ == "__main__":
+    dual()
     fix_head()
     smpl_to_sim()
     ball()

@@ -39,3 +39,14 @@ def v2p_cfg(num_envs, substeps=6, reward_type="return_w_estimate", early_termina
                physics=dict(assetFileName="smpl_mesh_humanoid_federer.xml", substeps=substeps, residual_force_scale=31.85, plane_restitution=0.5),
                vid2player=v2p)
     return dict(name="PhysicsMVAEController", env=env, seed=10)
+
+
+def v2p_dual_cfg(num_envs, assets=("smpl_mesh_humanoid_federer.xml", "smpl_mesh_humanoid_djokovic.xml"), players=("federer", "djokovic"),
+                 **v2p_over):
+    """mirrors vid2player/cfg/controller/federer_djokovic.yaml (two right-handed players, eastern grips)"""
+    cfg = v2p_cfg(num_envs, use_random_ball_target=True, dual_mode="different", player=list(players), grip=["eastern", "eastern"],
+                  righthand=[True, True], fix_head_orientation=True, **v2p_over)
+    cfg["name"] = "PhysicsMVAEControllerDual"
+    cfg["env"]["physics"]["assetFileName"] = list(assets)
+    cfg["env"]["physics"]["name"] = "HumanoidSMPLIMMVAEDual"
+    return cfg

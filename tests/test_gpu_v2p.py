@@ -325,3 +325,150 @@ def test_fix_head_golden():
                   prev_rb_rot=T(g["prev_target_rb_rot"]))
     close(b["dof_pos"], g["target_dof_pos"], 2e-5); close(b["rb_pos"], g["target_rb_pos"], 2e-5); close(b["rb_rot"], g["target_rb_rot"], 2e-5)
     close(b["dof_vel"], g["target_dof_vel"], 2e-3)
+
+
+# ------------------------------------------------------------------------------------------ dual mode (config 5)
+def test_ball_in_estimate_golden():
+    """b200v2p_ball_in_estimate vs TennisBallInEstimator.estimate run by the reference (tests/golden/v2p_dual.npz)"""
+    from vid2player3d_b200 import native_v2p as V
+    g = golden("v2p_dual.npz")
+    bs = T(g["in_states"])
+    n = bs.shape[0]
+    ids = torch.arange(n, device=DEV)
+    traj, s_in, s_out = torch.zeros(n, 50, 3, device=DEV), torch.zeros(n, 13, device=DEV), torch.zeros(n, 13, device=DEV)
+    V.ball_in_estimate(ids, bs, 13, T(g["in_table"]), g["in_params"], traj, s_in, s_out)
+    close(traj, g["in_traj"], 1e-5)
+    close(s_in, g["in_states_in"], 2e-5)
+    close(s_out, g["in_states_out"], 2e-5)
+    # index math on the shipped 15 x 50 x 30 x 50 grid: query a table whose row r holds r (split in two float-exact halves)
+    rows = 15 * 50 * 30 * 50
+    tab = torch.zeros(rows, 50, 2, device=DEV)
+    r = torch.arange(rows, device=DEV)
+    tab[:, 0, 0], tab[:, 0, 1] = (r // 1024).float(), (r % 1024).float()
+    m = g["full_h"].shape[0]
+    q = torch.zeros(m, 13, device=DEV)
+    q[:, 2], q[:, 8], q[:, 9], q[:, 10] = T(g["full_h"]), T(g["full_vx"]), T(g["full_vy"]), T(g["full_vs"]) * (2 * np.pi)
+    traj, s_in, s_out = torch.zeros(m, 50, 3, device=DEV), torch.zeros(m, 13, device=DEV), torch.zeros(m, 13, device=DEV)
+    V.ball_in_estimate(torch.arange(m, device=DEV), q, 13, tab, g["in_params_full"], traj, s_in, s_out)
+    got = (-traj[:, 0, 1]).round().long() * 1024 + traj[:, 0, 2].round().long()      # o[1] = -(d * dy + y) with dy = 1, y = 0
+    same = (got.cpu().numpy() == g["full_index"])
+    assert same.mean() > 0.995, same.mean()          # vspin = |omega| / 2pi re-derived on the device: a rounding flip at a cell edge is legal
+    snapped = np.stack([s_in[:, 2].cpu().numpy(), -s_in[:, 8].cpu().numpy(), s_in[:, 9].cpu().numpy()], -1)
+    assert (np.abs(snapped - g["full_snapped"][:, :3]) < 1e-5).mean() > 0.995
+
+
+def _dual_env(N, **over):
+    from helpers import SIM_PARAMS, v2p_dual_cfg
+    from vid2player3d_b200.tasks import PhysicsMVAEControllerDual
+    return PhysicsMVAEControllerDual(v2p_dual_cfg(N, **over), SIM_PARAMS, 1, "cuda", 0, True)
+
+
+def test_dual_reset_balls_golden(monkeypatch):
+    """HumanoidSMPLIMMVAEDual._reset_balls vs the reference method (serve + hand-over through the table, mixed parities)"""
+    g = golden("v2p_dual.npz")
+    env = _dual_env(32, ball_in_table=(g["in_table"], g["in_params"]))
+    task = env._physics_player.task
+    task._ball_root_states[:] = T(g["rb_states_before"])
+    env._mvae_player._racket_pos[:] = T(g["rb_racket_pos"])
+    task._has_bounce[:], task._has_racket_ball_contact[:] = True, True
+    task._bounce_pos[:] = 1.0
+    task._ball_pos[:], task._ball_vel[:] = 0.0, 0.0
+    draws = [T(x) for x in g["rb_rand"]]
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: draws.pop(0))
+    traj = task._reset_balls(T(g["rb_recovery_ids"]), T(g["rb_ball_ids"]))
+    monkeypatch.undo()
+    close(traj, g["rb_traj"], 1e-5)
+    close(task._ball_root_states, g["rb_states_after"], 2e-5)
+    close(task._ball_pos, g["rb_ball_pos"], 2e-6)
+    close(task._ball_vel, g["rb_ball_vel"], 2e-5)
+    close(task._bounce_pos, g["rb_bounce_pos"], 0)
+    assert np.array_equal(task._has_bounce.cpu().numpy(), g["rb_has_bounce"])
+    assert np.array_equal(task._has_racket_ball_contact.cpu().numpy(), g["rb_has_contact"])
+    rbs = task._rigid_body_state.view(32, 26, 13)
+    touched = np.concatenate([g["rb_ball_ids"], g["rb_ball_ids"] ^ 1])
+    close(rbs[touched, 25, 0:3], g["rb_states_after"][touched, 0:3], 2e-5)           # the simulator-side ball rows follow
+
+
+def test_dual_compute_reset_golden():
+    """the dual reset FSM of the fused post-step kernel vs PhysicsMVAEControllerDual._compute_reset run by the reference"""
+    g = golden("v2p_dual.npz")
+    N = 128
+    env = _dual_env(N)
+    env.reset()
+    task = env._physics_player.task
+    env._tar_action[:] = T(g["cr_tar_action"])
+    task._ball_pos[:], task._root_pos[:], task._root_vel[:] = T(g["cr_ball_pos"]), T(g["cr_root_pos"]), T(g["cr_root_vel"])
+    env._bounce_in[:], env._distance[:], env.reset_buf[:] = T(g["cr_bounce_in"]), T(g["cr_distance"]), T(g["crreset_buf"])
+    task._has_racket_ball_contact[:], task._has_bounce[:] = T(g["cr_has_contact"]), T(g["cr_has_bounce"])
+    task._has_bounce_now[:] = False
+    term_before = env._terminate_buf.clone()
+    env._compute_post()
+    assert np.array_equal(env.reset_buf.cpu().numpy(), g["cr_out_reset"])
+    assert np.array_equal(env._reset_reaction_buf.cpu().numpy(), g["cr_out_reaction"])
+    assert np.array_equal(env._reset_recovery_buf.cpu().numpy(), g["cr_out_recovery"])
+    close(env._distance, g["cr_out_distance"], 1e-6)
+    assert torch.equal(env._terminate_buf, term_before)              # the dual FSM never writes _terminate_buf
+
+
+def test_env_slices_match_single_asset():
+    """two handles over the even / odd rows with the SAME asset must reproduce the single-handle step bit for bit"""
+    from helpers import SIM_PARAMS, v2p_cfg
+    from vid2player3d_b200.tasks import HumanoidSMPLIMMVAE
+    N = 66                                             # 33 envs per slice: ragged last batch in both kernels
+    outs = []
+    for assets in ("smpl_mesh_humanoid_federer.xml", ["smpl_mesh_humanoid_federer.xml"] * 2):
+        c = v2p_cfg(N)
+        pcfg = {"env": dict(numEnvs=N, episodeLength=300, residual_force_scale=31.85, is_train=True, asset=dict(assetFileName=assets),
+                            plane=dict(staticFriction=1.0, dynamicFriction=1.0, restitution=0.5), vid2player=c["env"]["vid2player"],
+                            keyBodies=[], contactBodies=[]), "sim": {"substeps": 6}}
+        t = HumanoidSMPLIMMVAE(pcfg, SIM_PARAMS, 1, "cuda", 0, True)
+        gen = torch.Generator(device=DEV).manual_seed(5)
+        t._dof_pos[:] = 0.2 * torch.randn(N, 69, device=DEV, generator=gen)
+        t._humanoid_root_states[:, 2] = 0.95
+        t._ball_root_states[:, 0:3] = torch.tensor([0.0, -8.0, 1.0], device=DEV) + torch.randn(N, 3, device=DEV, generator=gen) * 0.1
+        t._ball_root_states[:, 7:10] = torch.tensor([0.0, -20.0, 1.0], device=DEV)
+        t._target_dof_pos[:] = t._dof_pos
+        t.reset_buf[:] = 0
+        for _ in range(3):
+            t.step(0.3 * torch.randn(N, t.num_actions, device=DEV, generator=gen))
+        torch.cuda.synchronize()
+        outs.append([x.clone() for x in (t._root_states, t._dof_state, t._rigid_body_state, t.obs_buf, t._racket_pos, t._ball_pos)])
+        assert len(t._envs) == (1 if isinstance(assets, str) else 2)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_dual_end_to_end():
+    """config-5 style rollout: federer vs djokovic in paired envs, agent loop with pair resets, ball hand-over through the table"""
+    torch.manual_seed(0)
+    N = 128
+    env = _dual_env(N)
+    assert env.num_obs == 257 and env.num_actions == 35
+    task = env._physics_player.task
+    assert len(task._envs) == 2 and task._rest_t.shape == (2, 24, 3) and not torch.equal(task._rest_t[0], task._rest_t[1])
+    assert not torch.equal(task._reset_ref_motion_bodies[0], task._reset_ref_motion_bodies[1])
+    env.reset()
+    torch.cuda.synchronize()
+    assert torch.isfinite(env.obs_buf).all()
+    # serve from the near player: even envs react to a ball coming from y > 0, their partners serve and recover
+    assert (env._tar_action[::2] == 1).all() and (env._tar_action[1::2] == 0).all()
+    bs = task._ball_root_states
+    close(bs[::2, 0:2], (-bs[1::2, 0:2]).cpu().numpy(), 1e-6)                 # one ball, seen from both courts
+    close(bs[::2, 7:9], (-bs[1::2, 7:9]).cpu().numpy(), 1e-5)
+    close(bs[::2, 2], bs[1::2, 2].cpu().numpy(), 0)
+    handovers, resets = 0, 0
+    for step in range(260):
+        env.step(torch.clamp(torch.randn(N, 35, device=DEV), -5, 5))
+        done = env.reset_buf.nonzero(as_tuple=False).flatten()
+        assert len(done) % 2 == 0 and torch.equal(done[::2] + 1, done[1::2])   # opponents terminate together
+        before = env._num_reset_reaction.clone()
+        resets += len(done)
+        env.reset(done)
+        handovers += int(((env._num_reset_reaction - before) > 0).sum()) - len(done) // 2
+    torch.cuda.synchronize()
+    assert torch.isfinite(env.obs_buf).all() and torch.isfinite(env.rew_buf).all() and torch.isfinite(task._rigid_body_state).all()
+    assert resets > 0                                                        # missed balls ended rallies (pairs reset together)
+    assert (task._rigid_body_rot.norm(dim=-1) - 1).abs().max() < 1e-4
+    assert (task._ball_pos[:, 2] >= 0.0319).all()
+    # the two assets are really different bodies: federer and djokovic settle at different pelvis heights / masses
+    assert abs(float(task._models[0]["mass"].sum()) - float(task._models[1]["mass"].sum())) > 0.1

@@ -38,11 +38,14 @@ def test_struct_layouts_match_header(tmp_path):
             abi.Cfg.key_body.offset]
     assert got == want
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s/include/b200env_v2p.h"\n'
-                   'int main(){printf("%%zu %%zu %%zu %%zu\\n",sizeof(b200v2p_state_t),sizeof(b200v2p_ctrl_t),'
-                   'offsetof(b200v2p_state_t,root_pos),offsetof(b200v2p_ctrl_t,est_x));}' % ROOT)
+                   'int main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",sizeof(b200v2p_state_t),sizeof(b200v2p_ctrl_t),'
+                   'offsetof(b200v2p_state_t,root_pos),offsetof(b200v2p_ctrl_t,est_x),sizeof(b200v2p_treset_t),sizeof(b200v2p_areset_t),'
+                   'offsetof(b200v2p_treset_t,swing_type_cycle),offsetof(b200v2p_areset_t,terminate_buf));}' % ROOT)
     subprocess.check_call(["gcc", str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    assert got == [C.sizeof(abi.V2PState), C.sizeof(abi.V2PCtrl), abi.V2PState.root_pos.offset, abi.V2PCtrl.est_x.offset]
+    assert got == [C.sizeof(abi.V2PState), C.sizeof(abi.V2PCtrl), abi.V2PState.root_pos.offset, abi.V2PCtrl.est_x.offset,
+                   C.sizeof(abi.V2PTaskReset), C.sizeof(abi.V2PActorReset), abi.V2PTaskReset.swing_type_cycle.offset,
+                   abi.V2PActorReset.terminate_buf.offset]
 
 
 def test_no_gpu_means_loud_failure():

@@ -98,3 +98,38 @@ def test_fix_head_orientation():
     b = V.smpl_to_sim(g["player_root_pos"], out, g["rest"], g["parents"], g["smpl_2_mujoco"], float(g["dt"]),
                       prev_root_pos=g["prev_target_root_pos"], prev_rb_rot=g["prev_target_rb_rot"])
     close(b[2], g["target_dof_pos"], 2e-5); close(b[6], g["target_rb_pos"], 2e-5); close(b[7], g["target_rb_rot"], 2e-5)
+
+
+def test_dual_golden():
+    """dual mode: in-estimator (index math on the small AND the shipped grid), _reset_balls, _compute_reset vs the reference"""
+    g = golden("v2p_dual.npz")
+    idx, snapped = V.in_estimator_index(g["full_h"], g["full_vx"], g["full_vy"], g["full_vs"], g["in_params_full"])
+    assert np.array_equal(idx, g["full_index"])
+    np.testing.assert_array_equal(np.stack(snapped, -1), g["full_snapped"])
+    bs = g["in_states"]
+    vspin = np.sqrt((bs[:, 10:13] ** 2).sum(-1)) / np.float32(2 * np.pi)
+    idx, _ = V.in_estimator_index(bs[:, 2], np.sqrt((bs[:, 7:9] ** 2).sum(-1)), bs[:, 9], vspin, g["in_params"])
+    assert np.array_equal(idx, g["in_index"])
+    traj, s_in, s_out = V.in_estimator_estimate(bs, g["in_table"], g["in_params"])
+    np.testing.assert_allclose(traj, g["in_traj"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(s_in, g["in_states_in"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(s_out, g["in_states_out"], rtol=0, atol=2e-5)
+    # _reset_balls (mixed parities in the id list)
+    traj, after, extra = V.dual_reset_balls(g["rb_states_before"], g["rb_racket_pos"], g["rb_recovery_ids"], g["rb_ball_ids"], g["rb_rand"],
+                                            g["in_table"], g["in_params"])
+    np.testing.assert_allclose(traj, g["rb_traj"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(after, g["rb_states_after"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(extra["ball_pos"], g["rb_ball_pos"][g["rb_ball_ids"]], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(extra["ball_vel"], g["rb_ball_vel"][g["rb_ball_ids"]], rtol=0, atol=2e-5)
+    ids = g["rb_ball_ids"]
+    assert not g["rb_has_bounce"][ids].any() and not g["rb_has_contact"][ids].any() and not g["rb_bounce_pos"][ids].any()
+    rest = np.setdiff1d(np.arange(32), ids)
+    assert g["rb_has_bounce"][rest].all() and g["rb_has_contact"][rest].all()
+    # _compute_reset
+    reset, reaction, recovery, dist = V.dual_controller_reset(g["cr_tar_action"], g["cr_has_contact"], g["cr_has_bounce"], g["cr_ball_pos"],
+                                                              g["cr_root_pos"], g["cr_root_vel"], g["cr_bounce_in"], g["cr_distance"],
+                                                              g["crreset_buf"])
+    assert np.array_equal(reset, g["cr_out_reset"]) and np.array_equal(reaction, g["cr_out_reaction"])
+    assert np.array_equal(recovery, g["cr_out_recovery"])
+    np.testing.assert_allclose(dist, g["cr_out_distance"], rtol=0, atol=1e-6)
+    assert g["cr_out_reset"].sum() > g["crreset_buf"].sum() and g["cr_out_reaction"].any() and g["cr_out_recovery"].any()

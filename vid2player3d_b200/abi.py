@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 MAX_BODIES, MAX_DOF, MAX_KEY = 32, 96, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Model(C.Structure):
@@ -175,6 +175,7 @@ class V2PState(C.Structure):
     _fields_ = [
         ("n", C.c_int32), ("bodies_per_env", C.c_int32), ("ball_stride", C.c_int32), ("root_stride", C.c_int32),
         ("racket_body", C.c_int32), ("wrist_body", C.c_int32), ("grip_normal", C.c_float * 3),
+        ("dual", C.c_int32), ("racket_body2", C.c_int32), ("wrist_body2", C.c_int32), ("grip_normal2", C.c_float * 3),
         ("rigid_body_state", C.c_void_p), ("root_states", C.c_void_p), ("ball_states", C.c_void_p),
         ("has_contact", C.c_void_p), ("has_contact_now", C.c_void_p),
         ("root_pos", C.c_void_p), ("root_vel", C.c_void_p), ("racket_pos", C.c_void_p), ("racket_vel", C.c_void_p),
@@ -187,7 +188,7 @@ class V2PCtrl(C.Structure):
         ("n", C.c_int32), ("bodies_per_env", C.c_int32), ("ball_stride", C.c_int32), ("racket_body", C.c_int32),
         ("num_obs", C.c_int32), ("obs_traj_len", C.c_int32), ("use_target", C.c_int32), ("reward_type", C.c_int32),
         ("early_termination", C.c_int32), ("max_episode_length", C.c_int32), ("est_nx", C.c_int32), ("est_ny", C.c_int32),
-        ("obs_only", C.c_int32), ("pad_", C.c_int32),
+        ("obs_only", C.c_int32), ("dual", C.c_int32),
         ("scale_pos", C.c_float), ("scale_phase", C.c_float), ("scale_bounce_pos", C.c_float), ("scale_bounce_time", C.c_float),
         ("w_pos", C.c_float), ("w_ball_pos", C.c_float),
         ("court_min", C.c_float * 2), ("court_max", C.c_float * 2), ("est_params", C.c_float * 15),
@@ -225,6 +226,7 @@ class V2PActorReset(C.Structure):
     _fields_ = [
         ("n", C.c_int32), ("num_dof", C.c_int32), ("bodies_per_env", C.c_int32), ("root_stride", C.c_int32),
         ("racket_body", C.c_int32), ("racket_parent", C.c_int32), ("racket_offset", C.c_float * 3),
+        ("dual", C.c_int32), ("racket_offset2", C.c_float * 3),
         ("env_ids", C.c_void_p),
         ("src_root_pos", C.c_void_p), ("src_root_rot", C.c_void_p), ("src_dof_pos", C.c_void_p), ("src_rb_pos", C.c_void_p),
         ("src_rb_rot", C.c_void_p),

@@ -110,3 +110,31 @@ def synthetic_out_tables(params=None, spin_scale=5.0):
     arr = np.array([p["VEL_X"], p["VEL_Y"], p["VSPIN"], p["TRAJ_X"], p["TRAJ_Y"]], np.float64)
     _TABLE_CACHE[key] = (out_x.astype(np.float32), out_y.astype(np.float32), arr)
     return _TABLE_CACHE[key]
+
+
+IN_PARAMS = dict(HEIGHT=(0.5, 2.0, 0.1), VEL_X=(25.0, 30.0, 0.1), VEL_Y=(5.0, 8.0, 0.1), VSPIN=(5.0, 10.0, 0.1))   # traj_in_params
+IN_PARAMS_COARSE = dict(HEIGHT=(0.5, 2.0, 0.25), VEL_X=(25.0, 30.0, 0.5), VEL_Y=(5.0, 8.0, 0.5), VSPIN=(5.0, 10.0, 1.0))
+
+
+def synthetic_in_table(params=None, spin_scale=5.0):
+    """Incoming-ball table of dual mode in the reference's file format (utils/tennis_ball_in_estimator.py:82-140):
+    rows over (height, horizontal speed, vertical speed, spin) in C order, each 50 frames @ 30 Hz of (distance along the hit
+    direction, height) for a ball launched straight out from (0, 0, height).  Returns (table [rows,50,2] f32, params [4,3] f64).
+    Default = a coarse grid (2 520 rows); pass IN_PARAMS for the shipped 1 125 000-row grid (~450 MB)."""
+    p = dict(IN_PARAMS_COARSE)
+    p.update(params or {})
+    key = ("in", repr(sorted(p.items())), float(spin_scale))
+    if key in _TABLE_CACHE:
+        return _TABLE_CACHE[key]
+    axes = [np.arange(*p[k]) for k in ("HEIGHT", "VEL_X", "VEL_Y", "VSPIN")]
+    hh, vx, vz, vs = [a.ravel() for a in np.meshgrid(*axes, indexing="ij")]
+    rows = len(hh)
+    out = np.zeros((rows, 50, 2), np.float32)
+    for s in range(0, rows, 200000):
+        e = min(rows, s + 200000)
+        pos = np.stack([np.zeros(e - s), np.zeros(e - s), hh[s:e]], -1)
+        vel = np.stack([np.zeros(e - s), vx[s:e], vz[s:e]], -1)
+        out[s:e] = integrate(pos, vel, vs[s:e], n_frames=50, spin_scale=spin_scale)[:, :, 1:]
+    arr = np.array([p["HEIGHT"], p["VEL_X"], p["VEL_Y"], p["VSPIN"]], np.float64)
+    _TABLE_CACHE[key] = (out, arr)
+    return _TABLE_CACHE[key]

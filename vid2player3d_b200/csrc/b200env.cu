@@ -73,6 +73,7 @@ struct b200env {
   b200_cfg_t* d_cfg;
   unsigned long long* d_ticket;
   unsigned long long ticket_base;
+  int env_first = 0, env_stride = 1;   // b200env_set_env_slice: local env i = row env_first + env_stride * i of the bound tensors
   int step_grid;
   int packed;        // 1: 4-envs-per-warp kernels (packed.cuh); 0: lane-per-body kernels.  env B200ENV_KERNEL=lane|packed
   int packed_ok;     // tree fits the packed layout (<= 8 bodies per depth, <= 25 bodies)
@@ -1233,7 +1234,7 @@ __device__ __forceinline__ void step_epilogue(const b200_buffers_t& bf, const b2
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, STEP_MIN_CTAS)
 step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
             b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs, unsigned long long* __restrict__ ticket,
-            unsigned long long base) {
+            int env_first, int env_stride) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t mbar;
   load_blob(smem, gblob, blob_bytes, &mbar);
@@ -1252,13 +1253,13 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
  for (;;) {
   // one ticket per CTA = a batch of WARPS_PER_CTA consecutive envs (CTA-uniform control flow -> barriers are legal)
   __syncthreads();
-  if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)WARPS_PER_CTA) - base;
+  if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)WARPS_PER_CTA);
   __syncthreads();
   const int64_t e0 = (int64_t)s_tk;
   if (e0 >= num_envs) break;
   const bool full_batch = e0 + WARPS_PER_CTA <= num_envs;
-  const int64_t e = e0 + warp;
-  if (!full_batch && e >= num_envs) continue;  // ragged last batch: no CTA barriers below (full_batch is CTA-uniform)
+  if (!full_batch && e0 + warp >= num_envs) continue;  // ragged last batch: no CTA barriers below (full_batch is CTA-uniform)
+  const int64_t e = env_first + (int64_t)env_stride * (e0 + warp);  // row of this env in the bound tensors (env slice)
 
   Lane<float> L;
   float pdtar[3], extF[3], extT[3], cf[3];
@@ -1309,7 +1310,7 @@ template <typename T> __device__ __forceinline__ void pk_load_state(const T* env
 __global__ void __launch_bounds__(PK_WARPS * 32, 1)
 step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
                    b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs, unsigned long long* __restrict__ ticket,
-                   unsigned long long base) {
+                   int env_first, int env_stride) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t mbar;
   load_blob(smem, gblob, blob_bytes, &mbar);
@@ -1332,7 +1333,7 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
   __shared__ unsigned long long s_tk;
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)BATCH) - base;
+    if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)BATCH);
     __syncthreads();
     const int64_t e0 = (int64_t)s_tk;
     if (e0 >= num_envs) break;
@@ -1341,8 +1342,8 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     if (!full_batch && eb >= num_envs) continue;
 
     for (int k = 0; k < EPW; k++) {
-      const int64_t e = eb + k;
-      if (e >= num_envs) break;
+      if (eb + k >= num_envs) break;
+      const int64_t e = env_first + (int64_t)env_stride * (eb + k);  // row in the bound tensors (env slice)
       Lane<float> L;
       float pdtar[3], extF[3], extT[3];
       Ball<float> dummy;
@@ -1353,15 +1354,16 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     const bool valid = eb + g < num_envs;
     Ball<float> ball;
     ball_clear(ball);
-    if (cfg.has_ball && valid && s == BALL_SLOT) ball_load(bf, eb + g, ball);
+    const int64_t erow_g = env_first + (int64_t)env_stride * (eb + g);
+    if (cfg.has_ball && valid && s == BALL_SLOT) ball_load(bf, erow_g, ball);
     control_step_packed<float>(B, verts, pc, wrec, lane, valid, ball, STEP_SYNC && full_batch);
 #if POST_SYNC
     if (full_batch) __syncthreads();
 #endif
-    if (cfg.has_ball && valid && s == BALL_SLOT) ball_writeback(bf, eb + g, ball);
+    if (cfg.has_ball && valid && s == BALL_SLOT) ball_writeback(bf, erow_g, ball);
     for (int k = 0; k < EPW; k++) {
-      const int64_t e = eb + k;
-      if (e >= num_envs) break;
+      if (eb + k >= num_envs) break;
+      const int64_t e = env_first + (int64_t)env_stride * (eb + k);
       Lane<float> L;
       float cf[3];
       pk_load_state<float>(wrec + k * ENV_STRIDE, lc, lane, L, cf);
@@ -1767,6 +1769,7 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   CUDA_OK(cudaSetDevice(device));
   b200env* h = new b200env();
   memset(h, 0, sizeof(*h));
+  h->env_stride = 1;
   h->device = device;
   h->num_envs = num_envs;
   h->model = *model;
@@ -1884,7 +1887,7 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
     CUDA_OK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), (cudaStream_t)stream));
     step_kernel_packed<<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes,
                                                                                       h->d_cfg, h->bufs, h->ml, actions, h->num_envs,
-                                                                                      h->d_ticket, 0ULL);
+                                                                                      h->d_ticket, h->env_first, h->env_stride);
     CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -1902,7 +1905,7 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
   CUDA_OK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), (cudaStream_t)stream));
   step_kernel<<<h->step_grid, WARPS_PER_CTA * 32, smem, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes,
                                                                                  h->d_cfg, h->bufs, h->ml, actions, h->num_envs,
-                                                                                 h->d_ticket, 0ULL);
+                                                                                 h->d_ticket, h->env_first, h->env_stride);
   CUDA_OK(cudaGetLastError());
   h->launches++;
   return 0;
@@ -2010,5 +2013,13 @@ int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_st
 }
 
 int64_t b200env_launch_count(b200env_handle h) { return h ? h->launches : 0; }
+
+int b200env_set_env_slice(b200env_handle h, int32_t env_first, int32_t env_stride) {
+  if (!h) return fail(-1, "b200env_set_env_slice: null handle%s");
+  if (env_first < 0 || env_stride < 1) return fail(-2, "b200env_set_env_slice: env_first >= 0 and env_stride >= 1 required%s");
+  h->env_first = env_first;
+  h->env_stride = env_stride;
+  return 0;
+}
 
 }  // extern "C"

@@ -86,13 +86,14 @@ __device__ __forceinline__ void qmul_xyzw(const float* a, const float* b, float*
 
 // ------------------------------------------------------------------------------------------ a13: SMPL FK targets
 __global__ void __launch_bounds__(V2P_WARPS * 32)
-smpl_to_sim_kernel(int n, const float* __restrict__ root_pos, const float* __restrict__ rotmat, const float* __restrict__ rest,
-                   const int32_t* __restrict__ parents, const int32_t* __restrict__ smpl_2_mujoco, float dt,
+smpl_to_sim_kernel(int n, const float* __restrict__ root_pos, const float* __restrict__ rotmat, const float* __restrict__ rest_all,
+                   int num_rest, const int32_t* __restrict__ parents, const int32_t* __restrict__ smpl_2_mujoco, float dt,
                    const float* __restrict__ prev_root_pos, const float* __restrict__ prev_rb_rot, float* root_rot, float* dof_pos,
                    float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * V2P_WARPS + warp;
   if (e >= n) return;
+  const float* rest = rest_all + (e % num_rest) * 72;   // per-shape rest joints: env e has shape e % num_rest (dual: players alternate)
   const bool act = lane < 24;
   const int j = act ? lane : 0;
   const int par = parents[j] < 0 ? 0 : parents[j];
@@ -306,7 +307,10 @@ __global__ void update_state_kernel(b200v2p_state_t s) {
   const bool now = !s.has_contact[e] && (ball[8] > 0.0f) && ((ball[8] - s.ball_vel[e * 3 + 1]) > 10.0f);
   s.has_contact_now[e] = now ? 1 : 0;
   if (now) s.has_contact[e] = 1;
-  const float* wq = rb + s.wrist_body * 13 + 3;
+  const bool second = s.dual && (e & 1);
+  const int wrist_body = second ? s.wrist_body2 : s.wrist_body, racket_body = second ? s.racket_body2 : s.racket_body;
+  const float* grip = second ? s.grip_normal2 : s.grip_normal;
+  const float* wq = rb + wrist_body * 13 + 3;
   const float qw[4] = {wq[3], wq[0], wq[1], wq[2]};
   float m[9];
   quat_wxyz_to_rotmat(qw, m);
@@ -314,9 +318,9 @@ __global__ void update_state_kernel(b200v2p_state_t s) {
   for (int k = 0; k < 3; k++) {
     s.root_pos[e * 3 + k] = rb[k];
     s.root_vel[e * 3 + k] = s.root_states[e * s.root_stride + 7 + k];
-    s.racket_pos[e * 3 + k] = rb[s.racket_body * 13 + k];
-    s.racket_vel[e * 3 + k] = rb[s.racket_body * 13 + 7 + k];
-    s.racket_normal[e * 3 + k] = m[k * 3] * s.grip_normal[0] + m[k * 3 + 1] * s.grip_normal[1] + m[k * 3 + 2] * s.grip_normal[2];
+    s.racket_pos[e * 3 + k] = rb[racket_body * 13 + k];
+    s.racket_vel[e * 3 + k] = rb[racket_body * 13 + 7 + k];
+    s.racket_normal[e * 3 + k] = m[k * 3] * grip[0] + m[k * 3 + 1] * grip[1] + m[k * 3 + 2] * grip[2];
     s.ball_pos[e * 3 + k] = ball[k];
     s.ball_vel[e * 3 + k] = ball[7 + k];
   }
@@ -422,8 +426,28 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p
   for (int k = lane; k < c.obs_traj_len * 3; k += 32) { float v = c.ball_traj[e * 300 + k] - rk[k % 3]; o[225 + k] = v; nan |= isnan(v); }
   if (c.use_target && lane < 2) { float v = c.target_bounce_pos[e * 3 + lane] - rp[lane]; o[225 + c.obs_traj_len * 3 + lane] = v; nan |= isnan(v); }
   const bool has_nan = __any_sync(FULL, nan);
+  // ---- dual reset FSM (physics_mvae_controller_dual.py:92-120): the opponent's flags are recomputed from its inputs (no exchange)
+  if (lane == 0 && !c.obs_only && c.dual) {
+    const int64_t p = e ^ 1;
+    bool rec[2], term[2];
+    for (int w = 0; w < 2; w++) {
+      const int64_t i = w ? p : e;
+      const bool ta1 = c.tar_action[i] == 1, ta0 = c.tar_action[i] == 0, hc = c.has_contact[i] != 0, hb = c.has_bounce[i] != 0;
+      // bounce_in AFTER this step's _update_state: recomputed when it is being rewritten (by this or the partner's warp)
+      const bool bin = (ta0 && c.has_bounce_now[i]) ? in_court(c.bounce_pos[i * 3], c.bounce_pos[i * 3 + 1]) : (c.bounce_in[i] != 0);
+      const bool miss_ball = c.ball_pos[i * 3 + 1] < c.root_pos[i * 3 + 1] - 1.0f;
+      const bool twice = hb && c.ball_pos[i * 3 + 2] < 0.05f;
+      rec[w] = ta1 && (hc || miss_ball || twice);
+      term[w] = (rec[w] && !hc) || (ta0 && hb && !bin);
+    }
+    c.distance[e] += sqrtf(c.root_vel[e * 3] * c.root_vel[e * 3] + c.root_vel[e * 3 + 1] * c.root_vel[e * 3 + 1]);  // _compute_stats
+    bool reaction = rec[1], recovery = rec[0];     // "recovery also marks the reaction of their opponent"
+    if (term[0] || term[1]) { c.reset_buf[e] = 1; reaction = false; recovery = false; }
+    c.reset_reaction[e] = reaction ? 1 : 0;
+    c.reset_recovery[e] = recovery ? 1 : 0;
+  }
   // ---- reset FSM (:408-436)
-  if (lane == 0 && !c.obs_only) {
+  if (lane == 0 && !c.obs_only && !c.dual) {
     const bool out = rp[0] < c.court_min[0] || rp[1] < c.court_min[1] || rp[0] > c.court_max[0] || rp[1] > c.court_max[1];
     bool terminate = out || has_nan;
     int64_t reset = (c.progress_buf[e] >= (int64_t)c.max_episode_length - 1) ? 1 : (terminate ? 1 : 0);
@@ -441,6 +465,60 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p
     c.reset_buf[e] = reset;
     c.reset_reaction[e] = reaction ? 1 : 0;
     c.reset_recovery[e] = recovery ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ dual mode: incoming-ball table
+struct InParams { float lo[4], hi_m_step[4], step[4], d1, d2, d3; };   // HEIGHT, VEL_X, VEL_Y, VSPIN
+__device__ __forceinline__ float in_round(float v, const InParams& P, int k) {   // clamp, (v - lo) / step, round half-even (:27-45)
+  v = fminf(fmaxf(v, P.lo[k]), P.hi_m_step[k]);
+  return rintf(__fdiv_rn(__fsub_rn(v, P.lo[k]), P.step[k]));
+}
+__global__ void __launch_bounds__(V2P_WARPS * 32) ball_in_estimate_kernel(int n, const int64_t* __restrict__ contact_ids,
+                                                                          const float* __restrict__ ball_states, int stride,
+                                                                          const float* __restrict__ table, int64_t rows, InParams P,
+                                                                          float* __restrict__ traj, float* __restrict__ s_in,
+                                                                          float* __restrict__ s_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * V2P_WARPS + warp;
+  if (i >= n) return;
+  const float* b = ball_states + contact_ids[i] * stride;
+  const float vel_x = sqrtf(__fadd_rn(__fmul_rn(b[7], b[7]), __fmul_rn(b[8], b[8])));
+  const float dx = __fdiv_rn(b[7], vel_x), dy = __fdiv_rn(b[8], vel_x);
+  const float vspin = __fdiv_rn(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(b[10], b[10]), __fmul_rn(b[11], b[11])), __fmul_rn(b[12], b[12]))),
+                                6.283185307179586f);
+  const float rh = in_round(b[2], P, 0), rx = in_round(vel_x, P, 1), ry = in_round(b[9], P, 2), rs = in_round(vspin, P, 3);
+  // float32 index sum, truncated like .long() (:38-41)
+  const float fi = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(__fmul_rn(rh, P.d1), P.d2), P.d3), __fmul_rn(__fmul_rn(rx, P.d2), P.d3)),
+                                       __fmul_rn(ry, P.d3)), rs);
+  int64_t row = (int64_t)fi;
+  row = row < 0 ? 0 : (row >= rows ? rows - 1 : row);   // the reference would raise on an out-of-range row; clamp instead of faulting
+  const float* t = table + row * 100;
+  for (int k = lane; k < 50; k += 32) {   // traj_trans (:63-65): distance along the hit direction -> xy, mirrored for the receiver
+    const float d = t[k * 2], z = t[k * 2 + 1];
+    float* o = traj + (i * 50 + k) * 3;
+    o[0] = -__fadd_rn(__fmul_rn(d, dx), b[0]);
+    o[1] = -__fadd_rn(__fmul_rn(d, dy), b[1]);
+    o[2] = z;
+  }
+  if (lane == 0) {
+    const float height = __fadd_rn(__fmul_rn(rh, P.step[0]), P.lo[0]), vx = __fadd_rn(__fmul_rn(rx, P.step[1]), P.lo[1]);
+    const float vy = __fadd_rn(__fmul_rn(ry, P.step[2]), P.lo[2]), vs = __fadd_rn(__fmul_rn(rs, P.step[3]), P.lo[3]);
+    float* si = s_in + i * 13;
+    float* so = s_out + i * 13;
+    const float vin[2] = {__fmul_rn(-vx, dx), __fmul_rn(-vx, dy)};
+    const float sp = __fmul_rn(__fmul_rn(vs, 3.141592653589793f), 2.0f);
+    // omega = vspin * 2 pi * normalize(v x (0,0,-1)) = (-v_y, v_x, 0) / |.|
+    const float nn = fmaxf(sqrtf(__fadd_rn(__fmul_rn(vin[1], vin[1]), __fmul_rn(vin[0], vin[0]))), 1e-12f);
+    const float wi[3] = {__fmul_rn(sp, __fdiv_rn(-vin[1], nn)), __fmul_rn(sp, __fdiv_rn(vin[0], nn)), 0.0f};
+    si[0] = -b[0]; si[1] = -b[1]; si[2] = height;
+    so[0] = b[0];  so[1] = b[1];  so[2] = height;
+#pragma unroll
+    for (int k = 3; k < 7; k++) { si[k] = b[k]; so[k] = b[k]; }
+    si[7] = vin[0]; si[8] = vin[1]; si[9] = vy;
+    so[7] = -vin[0]; so[8] = -vin[1]; so[9] = vy;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { si[10 + k] = wi[k]; so[10 + k] = k < 2 ? -wi[k] : 0.0f; }
   }
 }
 
@@ -525,7 +603,8 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) actor_reset_kernel(b200v2p_are
   if (lane == 24 && r.racket_body >= 0) {  // welded racket row = parent pose + rotated offset (first obs is consistent)
     const float* pp = r.src_rb_pos + (e * 24 + r.racket_parent) * 3;
     const float* q = r.src_rb_rot + (e * 24 + r.racket_parent) * 4;
-    const float o[3] = {r.racket_offset[0], r.racket_offset[1], r.racket_offset[2]};
+    const float* ro = (r.dual && (e & 1)) ? r.racket_offset2 : r.racket_offset;
+    const float o[3] = {ro[0], ro[1], ro[2]};
     float t[3] = {2.0f * (q[1] * o[2] - q[2] * o[1]), 2.0f * (q[2] * o[0] - q[0] * o[2]), 2.0f * (q[0] * o[1] - q[1] * o[0])};
     float u[3] = {q[1] * t[2] - q[2] * t[1], q[2] * t[0] - q[0] * t[2], q[0] * t[1] - q[1] * t[0]};
     float* row = rb + r.racket_body * 13;
@@ -558,16 +637,17 @@ extern "C" {
 
 const char* b200v2p_last_error(void) { return g_verr; }
 
-int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rotmat, const float* rest, const int32_t* parents,
-                        const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
+int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rotmat, const float* rest, int32_t num_rest,
+                        const int32_t* parents, const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
                         float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || !root_pos || !joint_rotmat || !rest || !parents || !smpl_2_mujoco || !root_rot || !dof_pos || !root_vel || !root_ang_vel ||
       !dof_vel || !rb_pos || !rb_rot)
     return vfail(-1, "b200v2p_smpl_to_sim: bad arguments");
   if (!(dt > 0)) return vfail(-2, "b200v2p_smpl_to_sim: dt must be positive");
+  if (num_rest < 1) return vfail(-2, "b200v2p_smpl_to_sim: num_rest must be >= 1");
   smpl_to_sim_kernel<<<(n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      n, root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, prev_root_pos, prev_rb_rot, root_rot, dof_pos, root_vel, root_ang_vel,
+      n, root_pos, joint_rotmat, rest, num_rest, parents, smpl_2_mujoco, dt, prev_root_pos, prev_rb_rot, root_rot, dof_pos, root_vel, root_ang_vel,
       dof_vel, rb_pos, rb_rot);
   V_CUDA_OK();
   return 0;
@@ -601,6 +681,25 @@ int b200v2p_ball_reset(int32_t n, const int64_t* env_ids, const int64_t* pool_in
     return vfail(-1, "b200v2p_ball_reset: bad arguments");
   ball_reset_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(n, env_ids, pool_index, pool, ball_states, stride, ball_pos, ball_vel, has_bounce,
                                                         bounce_pos, has_contact, traj);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_ball_in_estimate(int32_t n, const int64_t* contact_ids, const float* ball_states, int32_t stride, const float* table,
+                             int64_t table_rows, const double* params, float* traj, float* states_in, float* states_out, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !contact_ids || !ball_states || !table || table_rows < 1 || !params || !traj || !states_in || !states_out)
+    return vfail(-1, "b200v2p_ball_in_estimate: bad arguments");
+  InParams P;
+  double dim[4];
+  for (int k = 0; k < 4; k++) {   // python-double arithmetic of the reference, then the float32 cast torch applies to scalars
+    const double lo = params[k * 3], hi = params[k * 3 + 1], st = params[k * 3 + 2];
+    P.lo[k] = (float)lo; P.hi_m_step[k] = (float)(hi - st); P.step[k] = (float)st;
+    dim[k] = (hi - lo) / st;
+  }
+  P.d1 = (float)dim[1]; P.d2 = (float)dim[2]; P.d3 = (float)dim[3];
+  ball_in_estimate_kernel<<<(n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      n, contact_ids, ball_states, stride, table, table_rows, P, traj, states_in, states_out);
   V_CUDA_OK();
   return 0;
 }

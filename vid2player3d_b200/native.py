@@ -13,7 +13,7 @@ _lib = None
 
 SYMBOLS = ["b200env_abi_version", "b200env_last_error", "b200env_create", "b200env_destroy", "b200env_bind",
            "b200env_set_motion_lib", "b200env_step", "b200env_reset", "b200env_motion_state", "b200env_obs_imitation",
-           "b200env_physics_only", "b200env_launch_count"]
+           "b200env_physics_only", "b200env_launch_count", "b200env_set_env_slice"]
 
 
 def lib():
@@ -96,6 +96,10 @@ class Env:
         v.total_frames = t["gts"].shape[0]
         self._keep.append(t)
         _check(lib().b200env_set_motion_lib(self._h, C.byref(v)))
+
+    def set_env_slice(self, first, stride):
+        """this handle steps rows first, first+stride, ... of the bound tensors (one handle per asset in dual mode)"""
+        _check(lib().b200env_set_env_slice(self._h, C.c_int32(int(first)), C.c_int32(int(stride))))
 
     def step(self, actions):
         assert actions.is_cuda and actions.is_contiguous() and actions.dtype.is_floating_point

@@ -4,7 +4,7 @@ import ctypes as C
 from . import abi
 from .native import _ptr, _stream, lib
 
-SYMBOLS = ["b200v2p_last_error", "b200v2p_smpl_to_sim", "b200v2p_ball_aero", "b200v2p_ball_reset", "b200v2p_update_state",
+SYMBOLS = ["b200v2p_last_error", "b200v2p_smpl_to_sim", "b200v2p_ball_aero", "b200v2p_ball_reset", "b200v2p_ball_in_estimate", "b200v2p_update_state",
            "b200v2p_controller_post", "b200v2p_task_reset", "b200v2p_actor_reset", "b200v2p_fix_head"]
 GRIP_NORMAL = {'eastern': (0.0, 1.0, 0.0), 'semi_western': (0.0, 2.0 ** -0.5, 2.0 ** -0.5)}
 REWARD_TYPES = {'reach': 0, 'return': 1, 'return_w_estimate': 2}
@@ -25,7 +25,9 @@ def _c(t):
 def smpl_to_sim(root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, out, prev_root_pos=None, prev_rb_rot=None):
     """out: dict with root_rot[n,4] dof_pos[n,69] root_vel[n,3] root_ang_vel[n,3] dof_vel[n,69] rb_pos[n,24,3] rb_rot[n,24,4]"""
     n = int(root_pos.shape[0])
-    _check(lib().b200v2p_smpl_to_sim(C.c_int32(n), _c(root_pos), _c(joint_rotmat), _c(rest), _c(parents), _c(smpl_2_mujoco), C.c_float(dt),
+    num_rest = 1 if rest.dim() == 2 else int(rest.shape[0])      # rest [24,3] or [S,24,3]: env e uses shape e % S
+    assert rest.is_contiguous() and rest.shape[-2:] == (24, 3)
+    _check(lib().b200v2p_smpl_to_sim(C.c_int32(n), _c(root_pos), _c(joint_rotmat), _c(rest), C.c_int32(num_rest), _c(parents), _c(smpl_2_mujoco), C.c_float(dt),
                                      _c(prev_root_pos), _c(prev_rb_rot), _c(out["root_rot"]), _c(out["dof_pos"]), _c(out["root_vel"]),
                                      _c(out["root_ang_vel"]), _c(out["dof_vel"]), _c(out["rb_pos"]), _c(out["rb_rot"]), _stream()))
 
@@ -50,16 +52,36 @@ def ball_reset(env_ids, pool_index, pool, ball_states, ball_pos, ball_vel, has_b
 
 def update_state(n, bodies_per_env, rigid_body_state, root_states, root_stride, ball_states, ball_stride, t, grip='eastern',
                  racket_body=24, wrist_body=22):
+    """grip / racket_body / wrist_body may be 2-sequences (dual_mode 'different': even envs, odd envs)"""
     s = abi.V2PState()
-    s.n, s.bodies_per_env, s.ball_stride, s.root_stride, s.racket_body, s.wrist_body = n, bodies_per_env, ball_stride, root_stride, racket_body, wrist_body
-    for i, v in enumerate(GRIP_NORMAL[grip]):
-        s.grip_normal[i] = v
+    pair = lambda v: (v[0], v[1], 1) if isinstance(v, (list, tuple)) else (v, v, 0)  # noqa: E731
+    g0, g1, d0 = pair(grip)
+    r0, r1, d1 = pair(racket_body)
+    w0, w1, d2 = pair(wrist_body)
+    s.n, s.bodies_per_env, s.ball_stride, s.root_stride, s.racket_body, s.wrist_body = n, bodies_per_env, ball_stride, root_stride, r0, w0
+    s.dual, s.racket_body2, s.wrist_body2 = int(bool(d0 or d1 or d2)), r1, w1
+    for i in range(3):
+        s.grip_normal[i] = GRIP_NORMAL[g0][i]
+        s.grip_normal2[i] = GRIP_NORMAL[g1][i]
     s.rigid_body_state, s.root_states, s.ball_states = rigid_body_state.data_ptr(), root_states.data_ptr(), ball_states.data_ptr()
     for k in ("has_contact", "has_contact_now", "root_pos", "root_vel", "racket_pos", "racket_vel", "racket_normal", "ball_pos", "ball_vel",
               "ball_vspin"):
         assert t[k].is_cuda and t[k].is_contiguous(), k
         setattr(s, k, t[k].data_ptr())
     _check(lib().b200v2p_update_state(C.byref(s), _stream()))
+
+
+def ball_in_estimate(contact_ids, ball_states, stride, table, params, traj, states_in, states_out):
+    """TennisBallInEstimator.estimate for the balls of envs `contact_ids`; params [4,3] float64 (HEIGHT, VEL_X, VEL_Y, VSPIN)"""
+    import numpy as np
+    n = int(contact_ids.shape[0])
+    p = np.ascontiguousarray(np.asarray(params, np.float64).reshape(12))
+    for x in (contact_ids, table, traj, states_in, states_out):
+        assert x.is_cuda and x.is_contiguous()
+    assert table.shape[1:] == (50, 2) and traj.shape == (n, 50, 3) and states_in.shape == (n, 13) and states_out.shape == (n, 13)
+    _check(lib().b200v2p_ball_in_estimate(C.c_int32(n), _ptr(contact_ids), _ptr(ball_states), C.c_int32(stride), _ptr(table),
+                                          C.c_int64(int(table.shape[0])), p.ctypes.data_as(C.c_void_p), _ptr(traj), _ptr(states_in),
+                                          _ptr(states_out), _stream()))
 
 
 def controller_post(cfg, t):
@@ -70,10 +92,11 @@ def controller_post(cfg, t):
               "scale_bounce_time", "w_pos", "w_ball_pos"):
         setattr(c, k, cfg[k])
     c.obs_only = int(cfg.get("obs_only", 0))
+    c.dual = int(cfg.get("dual", 0))
     for k in ("court_min", "court_max", "est_params"):
         for i, v in enumerate(cfg[k]):
             getattr(c, k)[i] = float(v)
-    scalars = {f for f, _ in abi.V2PCtrl._fields_ if f in cfg} | {"obs_only", "pad_"}
+    scalars = {f for f, _ in abi.V2PCtrl._fields_ if f in cfg} | {"obs_only", "dual"}
     for name, _ in abi.V2PCtrl._fields_:
         if name in scalars:
             continue
@@ -111,8 +134,12 @@ def actor_reset(cfg, t):
         setattr(r, k, int(cfg[k]))
     for i, v in enumerate(cfg["racket_offset"]):
         r.racket_offset[i] = float(v)
+    if cfg.get("racket_offset2") is not None:
+        r.dual = 1
+        for i, v in enumerate(cfg["racket_offset2"]):
+            r.racket_offset2[i] = float(v)
     for name, _ in abi.V2PActorReset._fields_:
-        if name in cfg:
+        if name in cfg or name in ("dual", "racket_offset2"):
             continue
         x = t[name]
         assert x.is_cuda and x.is_contiguous(), name

@@ -39,19 +39,25 @@ class HumanoidSMPLIMMVAE(BaseTask):
         self.max_episode_length = env["episodeLength"]
         self._local_root_obs = env.get("localRootObs", True)
         self._root_height_obs = env.get("rootHeightObs", True)
-        if self.cfg_v2p.get("dual_mode"):
-            raise NotImplementedError("dual mode (humanoid_smpl_im_mvae_dual.py) is a later row (DESIGN.md 8)")
         self._num_humanoid_bodies = 24
         self._racket_body_id = self._racket_body_id_true = 24
         self._racket_hand_body_id, self._racket_wrist_body_id, self._free_hand_body_id, self._head_body_id = 23, 22, 18, 13
         cfg["device_type"], cfg["device_id"], cfg["headless"] = device_type, device_id, True
         self.device = "cuda:" + str(device_id)
 
-        name = os.path.splitext(os.path.basename(env["asset"]["assetFileName"]))[0]
-        self._model = model_compiler.load_compiled(name)
+        # one asset, or one per player in dual_mode 'different' (:260-275: env 2k -> asset 0, env 2k+1 -> asset 1)
+        files = env["asset"]["assetFileName"]
+        files = list(files) if isinstance(files, (list, tuple)) else [files]
+        self._models = [model_compiler.load_compiled(os.path.splitext(os.path.basename(f))[0]) for f in files]
+        self._model = self._models[0]
         self.body_names = [str(x) for x in self._model["body_names"]]
         self.num_bodies = len(self.body_names)          # 25 = humanoid + Racket (the ball is a separate actor)
-        assert self.num_bodies == 25 and self.body_names[-1] == "Racket"
+        for m in self._models:
+            if [str(x) for x in m["body_names"]] != self.body_names or self.num_bodies != 25 or self.body_names[-1] != "Racket":
+                raise NotImplementedError("left-handed assets (Racket on L_Hand, `righthand: False`, :74-84 / :197-206) need the "
+                                          "rigid-body row permutation _humanoid_body_ids_lefthand; not built (DESIGN.md 8)")
+        if env["numEnvs"] % len(self._models):
+            raise ValueError("numEnvs must be a multiple of the number of assets")
         self.num_dof = self._num_dof = len(self._model["kp"])
         self._num_actions = self.num_dof + (6 if self.residual_force_scale > 0 else 0)
         self._dof_offsets = list(range(0, self.num_dof + 1, 3))
@@ -80,9 +86,6 @@ class HumanoidSMPLIMMVAE(BaseTask):
 
     def create_sim(self):
         env = self.cfg["env"]
-        mass = float(self._model["mass"].sum())
-        pd_scale = mass / env.get("default_humanoid_mass", 90.0)
-        self._model_struct, self._verts = abi.pack_model(self._model, pd_scale * self.kp_scale, pd_scale * self.kd_scale)
         v2p = self.cfg_v2p
         ball = dict(spin_scale=v2p.get("spin_scale", 1.0))
         rest = v2p.get("restitution", 0.9)
@@ -97,7 +100,18 @@ class HumanoidSMPLIMMVAE(BaseTask):
             max_episode_length=self.max_episode_length, enable_early_termination=False, contact_bodies=tuple(env.get("contactBodies", ())),
             key_bodies=tuple(env.get("keyBodies", ())), friction_mu=env.get("plane", {}).get("dynamicFriction", 1.0),
             task_mode=1, pd_mode=1, ball=ball, **self.cfg.get("b200_physics", {}))
-        self._env = native.Env(self._model_struct, self._verts, self._cfg_struct, self.num_envs, self.device_id)
+        # one handle per asset; handle k steps rows k, k+K, ... of the shared tensors (b200env_set_env_slice)
+        self._envs, K = [], len(self._models)
+        for k, m in enumerate(self._models):
+            pd_scale = float(m["mass"].sum()) / env.get("default_humanoid_mass", 90.0)      # :381-389 kp, kd *= mass / 90
+            ms, verts = abi.pack_model(m, pd_scale * self.kp_scale, pd_scale * self.kd_scale)
+            if k == 0:
+                self._model_struct, self._verts = ms, verts
+            h = native.Env(ms, verts, self._cfg_struct, self.num_envs // K, self.device_id)
+            if K > 1:
+                h.set_env_slice(k, K)
+            self._envs.append(h)
+        self._env = self._envs[0]
 
     def _setup_tensors(self):
         """:135-189 - Isaac layouts: 2 actors / env (humanoid, ball), 26 rigid bodies / env (25 + ball)"""
@@ -134,6 +148,14 @@ class HumanoidSMPLIMMVAE(BaseTask):
         self._pd_target_dof_pos = f(N, D)
         self.actions = f(N, self._num_actions)
         self._reset_ref_motion_bodies = f(N, 11)
+        self._reset_ref_motion_bodies[:, 0] = 1          # gender male (:254-260)
+        beta = self.cfg_v2p.get('smpl_beta')
+        if beta is not None:
+            if self.cfg_v2p.get('dual_mode') == 'different':
+                self._reset_ref_motion_bodies[::2, 1:11] = torch.tensor(beta[0], device=dev, dtype=torch.float)
+                self._reset_ref_motion_bodies[1::2, 1:11] = torch.tensor(beta[1], device=dev, dtype=torch.float)
+            else:
+                self._reset_ref_motion_bodies[:, 1:11] = torch.tensor(beta, device=dev, dtype=torch.float).view(-1)[:10]
         self._sub_rewards4, self._key_dummy = f(N, 4), f(N, max(1, self._cfg_struct.num_key), 3)
         self._zero_ids = torch.zeros(N, device=dev, dtype=torch.long)
         self._zero_t = f(N)
@@ -147,25 +169,29 @@ class HumanoidSMPLIMMVAE(BaseTask):
                  p_dof_vel=self._prev_target_dof_vel, p_rb_pos=self._prev_target_rb_pos, p_rb_rot=self._prev_target_rb_rot,
                  pd_targets=self._pd_target_dof_pos, actions_used=self.actions, has_bounce=self._has_bounce,
                  has_bounce_now=self._has_bounce_now, bounce_pos=self._bounce_pos, racket_hit_now=self._racket_hit_now)
-        self._env.bind(t, actors_per_env=2, bodies_per_env=26, num_obs=self.num_obs)
-        # SMPL kinematic constants for the FK targets (rest joints of the shipped skeleton, SMPL joint order)
-        pos = np.zeros((24, 3))
-        for i in range(24):
-            pos[i] = self._model["offset"][i] + (pos[self._model["parent"][i]] if self._model["parent"][i] >= 0 else 0)
-        rest = np.stack([pos[self.body_names.index(n)] for n in SMPL_NAMES]).astype(np.float32)
-        self._smpl = SimpleNamespace(joint_pos_bind=torch.tensor(rest, device=dev).unsqueeze(0).repeat(N, 1, 1),
-                                     parents=torch.tensor(SMPL_PARENTS, device=dev))
-        self._rest_t = torch.tensor(rest, device=dev).contiguous()
+        for h in self._envs:
+            h.bind(t, actors_per_env=2, bodies_per_env=26, num_obs=self.num_obs)
+        # SMPL kinematic constants for the FK targets (rest joints of the shipped skeletons, SMPL joint order), one per asset
+        rests = []
+        for m in self._models:
+            pos = np.zeros((24, 3))
+            for i in range(24):
+                pos[i] = m["offset"][i] + (pos[m["parent"][i]] if m["parent"][i] >= 0 else 0)
+            rests.append(np.stack([pos[self.body_names.index(n)] for n in SMPL_NAMES]).astype(np.float32))
+        K = len(rests)
+        self._rest_t = torch.tensor(np.stack(rests), device=dev).contiguous()            # [K,24,3]: env e uses shape e % K
+        self._smpl = SimpleNamespace(joint_pos_bind=self._rest_t.repeat(N // K, 1, 1), parents=torch.tensor(SMPL_PARENTS, device=dev))
         self._parents_t = torch.tensor(SMPL_PARENTS, device=dev, dtype=torch.int32)
         self._s2m_t = torch.tensor(self._smpl_2_mujoco, device=dev, dtype=torch.int32)
         self._tmp = dict(root_rot=f(N, 4), dof_pos=f(N, D), root_vel=f(N, 3), root_ang_vel=f(N, 3), dof_vel=f(N, D), rb_pos=f(N, 24, 3),
                          rb_rot=f(N, 24, 4))
-        # incoming-ball pool (TennisBallGeneratorOffline, utils/tennis_ball.py:422-456)
-        pool = self.cfg_v2p.get("ball_pool", None)
-        if pool is None:
-            path = self.cfg_v2p.get("ball_traj_file")
-            pool = np.load(path) if path and os.path.exists(path) else ball_data.synthetic_pool(2048, seed=10, spin_scale=self.cfg_v2p.get("spin_scale", 1.0))
-        self._ball_pool = torch.tensor(np.asarray(pool, np.float32), device=dev).contiguous()
+        # incoming-ball pool (TennisBallGeneratorOffline, utils/tennis_ball.py:422-456); dual mode has the in-estimator instead (:126-130)
+        if not self.cfg_v2p.get('dual_mode', False):
+            pool = self.cfg_v2p.get("ball_pool", None)
+            if pool is None:
+                path = self.cfg_v2p.get("ball_traj_file")
+                pool = np.load(path) if path and os.path.exists(path) else ball_data.synthetic_pool(2048, seed=10, spin_scale=self.cfg_v2p.get("spin_scale", 1.0))
+            self._ball_pool = torch.tensor(np.asarray(pool, np.float32), device=dev).contiguous()
         self._ball_traj_buf = f(N, 100, 3)
         self.extras["terminate"] = self._terminate_buf
 
@@ -206,7 +232,9 @@ class HumanoidSMPLIMMVAE(BaseTask):
     def step(self, actions):
         self._prev_target_root_pos.copy_(self._target_root_pos)          # _save_prev_target_motion_state (:741-750)
         self._has_racket_ball_contact_now.zero_()                        # pre_physics_step :689
-        self._env.step(actions.to(self.device, dtype=torch.float).contiguous())
+        actions = actions.to(self.device, dtype=torch.float).contiguous()
+        for h in self._envs:          # one launch per asset (dual: even envs, then odd envs)
+            h.step(actions)
         self._update_state_from_sim()
 
     def _update_state_from_sim(self):
@@ -220,12 +248,16 @@ class HumanoidSMPLIMMVAE(BaseTask):
             self._has_racket_ball_contact |= now
             keep = self._has_racket_ball_contact.clone()
             native_v2p.update_state(self.num_envs, 26, self._rigid_body_state, self._root_states, 26, self._root_states[1:], 26, t,
-                                    grip=self.cfg_v2p.get('grip', 'eastern'))
+                                    grip=self._grip())
             self._has_racket_ball_contact.copy_(keep)
             self._has_racket_ball_contact_now.copy_(now)
         else:
             native_v2p.update_state(self.num_envs, 26, self._rigid_body_state, self._root_states, 26, self._root_states[1:], 26, t,
-                                    grip=self.cfg_v2p.get('grip', 'eastern'))
+                                    grip=self._grip())
+
+    def _grip(self):
+        g = self.cfg_v2p.get('grip', 'eastern')            # a pair in dual_mode 'different' (:839-842)
+        return list(g) if isinstance(g, (list, tuple)) else g
 
     # ------------------------------------------------------------------ reset (:447-524, 562-581)
     def reset(self, reset_humanoid_env_ids, reset_ball_env_ids):
@@ -240,7 +272,8 @@ class HumanoidSMPLIMMVAE(BaseTask):
         """:463-501 + :562-581: sim state <- FK of the motion generator's initial pose (zero velocities); 2 launches"""
         self._smpl_to_sim_into(self._mvae_player._root_pos.contiguous(), self._mvae_player._joint_rotmat, self._tmp)
         cfg = dict(n=len(env_ids), num_dof=self.num_dof, bodies_per_env=26, root_stride=26, racket_body=24, racket_parent=22,
-                   racket_offset=self._model["offset"][24])
+                   racket_offset=self._model["offset"][24],
+                   racket_offset2=self._models[1]["offset"][24] if len(self._models) == 2 else None)
         native_v2p.actor_reset(cfg, dict(
             env_ids=env_ids.contiguous(), src_root_pos=self._mvae_player._root_pos.contiguous(), src_root_rot=self._tmp["root_rot"],
             src_dof_pos=self._tmp["dof_pos"], src_rb_pos=self._tmp["rb_pos"], src_rb_rot=self._tmp["rb_rot"], root_states=self._root_states,
@@ -266,3 +299,69 @@ class HumanoidSMPLIMMVAE(BaseTask):
 
     def render_vis(self, init=False):
         return
+
+
+class HumanoidSMPLIMMVAEDual(HumanoidSMPLIMMVAE):
+    """vid2player/env/tasks/humanoid_smpl_im_mvae_dual.py: envs (2k, 2k+1) are the two players of one rally, each in its own
+    court frame; a ball hit in one env re-enters the partner env mirrored, snapped to the incoming-ball table."""
+
+    def __init__(self, cfg, sim_params, physics_engine, device_type, device_id, headless):
+        super().__init__(cfg=cfg, sim_params=sim_params, physics_engine=physics_engine, device_type=device_type, device_id=device_id,
+                         headless=headless)
+        if self.num_envs % 2:
+            raise ValueError("dual mode needs an even number of envs (opponents are envs 2k and 2k+1)")
+        tab = self.cfg_v2p.get('ball_in_table', None)          # (table [rows,50,2], params [4,3]); utils/tennis_ball_in_estimator.py
+        if tab is None:
+            path = self.cfg_v2p.get('ball_traj_file')
+            if path and os.path.exists(path):
+                tab = (np.load(path), np.array([ball_data.IN_PARAMS[k] for k in ("HEIGHT", "VEL_X", "VEL_Y", "VSPIN")], np.float64))
+            else:
+                tab = ball_data.synthetic_in_table(spin_scale=self.cfg_v2p.get('spin_scale', 1.0))
+        self._in_table = torch.tensor(np.asarray(tab[0], np.float32), device=self.device).contiguous()
+        self._in_params = np.asarray(tab[1], np.float64)
+
+    def reset(self, reset_actor_reaction_env_ids, reset_ball_env_ids):
+        return self._reset_envs(reset_actor_reaction_env_ids, reset_ball_env_ids)
+
+    def _reset_envs(self, reset_actor_reaction_env_ids, reset_ball_env_ids):
+        """:34-50"""
+        from ..torch_ops import get_opponent_env_ids
+        reset_actor_recovery_env_ids = get_opponent_env_ids(reset_actor_reaction_env_ids)
+        reset_actor_env_ids = torch.cat([reset_actor_reaction_env_ids, reset_actor_recovery_env_ids])
+        traj = None
+        if len(reset_actor_env_ids) > 0:
+            self._reset_actors(reset_actor_env_ids)
+        if len(reset_ball_env_ids) > 0:
+            traj = self._reset_balls(reset_actor_recovery_env_ids, reset_ball_env_ids)
+        return traj
+
+    def _reset_balls(self, reset_actor_recovery_env_ids, reset_ball_env_ids):
+        """:52-80: serve = the ball at the server's racket with a random velocity; then every env in `reset_ball_env_ids` receives
+        the ball its opponent just hit (b200v2p_ball_in_estimate), and the opponent's own ball is snapped to the same grid point."""
+        from ..torch_ops import get_opponent_env_ids
+        bs, dev = self._ball_root_states, self.device
+        if len(reset_actor_recovery_env_ids) > 0:
+            ids, n = reset_actor_recovery_env_ids, len(reset_actor_recovery_env_ids)
+            bs[ids, :3] = self._mvae_player._racket_pos[ids]
+            bs[ids, 10:13] = torch.tensor([-40.0, 0.0, 0.0], device=dev)
+            bs[ids, 7] = torch.rand(n, device=dev) * 4 + -2
+            bs[ids, 8] = torch.rand(n, device=dev) * 4 + 28
+            bs[ids, 9] = torch.rand(n, device=dev) * 3 + 5
+        contact_env_ids = get_opponent_env_ids(reset_ball_env_ids)
+        n = len(reset_ball_env_ids)
+        traj = torch.empty(n, 50, 3, device=dev)
+        s_in, s_out = torch.empty(n, 13, device=dev), torch.empty(n, 13, device=dev)
+        native_v2p.ball_in_estimate(contact_env_ids.contiguous(), self._root_states[1:], 26, self._in_table, self._in_params, traj, s_in, s_out)
+        bs[reset_ball_env_ids] = s_in
+        bs[contact_env_ids] = s_out
+        self._has_bounce[reset_ball_env_ids] = False
+        self._bounce_pos[reset_ball_env_ids] = 0
+        self._has_racket_ball_contact[reset_ball_env_ids] = False
+        self._ball_pos[reset_ball_env_ids] = bs[reset_ball_env_ids, 0:3]
+        self._ball_vel[reset_ball_env_ids] = bs[reset_ball_env_ids, 7:10]
+        # the simulator-side copy of the ball rows (_reset_env_tensors :562-572 pushes the root states of both ball actors)
+        both = torch.cat([contact_env_ids, reset_ball_env_ids])
+        rbs = self._rigid_body_state.view(self.num_envs, 26, 13)
+        rbs[both, 25, 0:3] = bs[both, 0:3]
+        rbs[both, 25, 7:13] = bs[both, 7:13]
+        return traj

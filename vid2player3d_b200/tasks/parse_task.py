@@ -1,10 +1,11 @@
 """parse_task mirror (embodied_pose/utils/parse_task.py:19-42): same signature and error behaviour."""
 from .humanoid_smpl_im import HumanoidSMPLIM
-from .humanoid_smpl_im_mvae import HumanoidSMPLIMMVAE
-from .physics_mvae_controller import PhysicsMVAEController
+from .humanoid_smpl_im_mvae import HumanoidSMPLIMMVAE, HumanoidSMPLIMMVAEDual
+from .physics_mvae_controller import PhysicsMVAEController, PhysicsMVAEControllerDual
 from .vec_task import VecTaskPythonWrapper
 
-TASKS = {"HumanoidSMPLIM": HumanoidSMPLIM, "HumanoidSMPLIMMVAE": HumanoidSMPLIMMVAE, "PhysicsMVAEController": PhysicsMVAEController}
+TASKS = {"HumanoidSMPLIM": HumanoidSMPLIM, "HumanoidSMPLIMMVAE": HumanoidSMPLIMMVAE, "HumanoidSMPLIMMVAEDual": HumanoidSMPLIMMVAEDual,
+         "PhysicsMVAEController": PhysicsMVAEController, "PhysicsMVAEControllerDual": PhysicsMVAEControllerDual}
 
 
 def warn_task_name():

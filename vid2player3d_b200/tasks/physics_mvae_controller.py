@@ -18,7 +18,16 @@ import numpy as np
 import torch
 
 from .. import ball as ball_data, native_v2p
-from .humanoid_smpl_im_mvae import HumanoidSMPLIMMVAE
+from ..torch_ops import get_opponent_env_ids
+from .humanoid_smpl_im_mvae import HumanoidSMPLIMMVAE, HumanoidSMPLIMMVAEDual
+
+# SMPL shape coefficients of the three players (vid2player/env/tasks/physics_mvae_controller.py:119-125); they reach the
+# low-level policy through the last 10 entries of the 734-d observation
+SMPL_BETA = {
+    'djokovic': [-0.9807, 1.4050, -0.4144, 1.4028, -1.3299, 2.0045, -1.3108, 0.7475, -0.0924, -0.3262],
+    'federer': [-0.6303, 1.1747, -0.3463, 1.0915, -1.0501, 1.7888, -1.1762, 0.6059, 0.2589, -0.4568],
+    'nadal': [-0.6278, 1.2620, -0.3143, 0.8561, -0.8136, 1.3917, -0.9902, 0.5112, 0.2334, -0.4266],
+}
 
 BASE_ROTMAT = [[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]  # quaternion (.5,.5,.5,.5): SMPL y-up -> world z-up
 
@@ -58,6 +67,8 @@ class SyntheticMotionPlayer:
         self._swing_type = torch.zeros(num_envs, device=device, dtype=torch.long)
         self._swing_type_cycle = -torch.ones(num_envs, device=device, dtype=torch.long)
         self._heading = torch.zeros(num_envs, device=device)
+        self._racket_pos = torch.zeros(num_envs, 3, device=device)        # kinematic racket position (serve toss point in dual mode)
+        self._racket_off = torch.tensor([0.35, 0.25, 0.25], device=device)
         self._base = torch.tensor(BASE_ROTMAT, device=device)
         self._proj = torch.randn(32, 72, device=device, generator=self.gen) * 0.02
         self.court_min, self.court_max = court_min, court_max
@@ -85,7 +96,14 @@ class SyntheticMotionPlayer:
         self._phase_pred.index_fill_(0, env_ids, 0.0)
         self._swing_type.index_fill_(0, env_ids, 0)
         self._swing_type_cycle.index_fill_(0, env_ids, -1)
+        self._racket_pos[env_ids] = self._root_pos[env_ids] + self._racket_off
         self._update_rotmat(env_ids)
+
+    def reset_dual(self, reset_reaction_env_ids, reset_recovery_env_ids):
+        """players/mvae_player.py:167-182: both players of the listed pairs restart (ready pose / serve pose in the reference)"""
+        self.reset(torch.cat([reset_reaction_env_ids, reset_recovery_env_ids]).sort().values)
+        self._swing_type.index_fill_(0, reset_reaction_env_ids, -1)
+        self._swing_type.index_fill_(0, reset_recovery_env_ids, -1)
 
     def step(self, mvae_actions, res_dof_actions=None):
         drive = (mvae_actions[:, :32] @ self._proj).view(self.N, 24, 3)
@@ -95,6 +113,7 @@ class SyntheticMotionPlayer:
         if res_dof_actions is not None and res_dof_actions.numel():
             self._aa[:, 21] += res_dof_actions[:, :3] * 0.1          # residual on the racket wrist (add_residual_dof)
         self._root_pos[:, :2] += 0.01 * torch.randn(self.N, 2, device=self.device)
+        self._racket_pos.copy_(self._root_pos + self._racket_off)
         self._phase_pred.copy_(torch.remainder(self._phase_pred + 2 * math.pi / 60, 2 * math.pi))
         wrap = self._phase_pred < 2 * math.pi / 60
         self._swing_type.copy_(torch.where(wrap, (self._swing_type + 1) % 4, self._swing_type))
@@ -127,6 +146,10 @@ class PhysicsMVAEController:
         self.num_obs = env["numObservations"] = self._num_actor_obs + self._num_task_obs
         self.num_actions = env["numActions"] = self._num_actions
         self.num_states = env.get("numStates", 0)
+        if self.cfg_v2p.get('dual_mode') == 'different':          # :127-135
+            self.cfg_v2p['smpl_beta'] = [SMPL_BETA[p] for p in self.cfg_v2p['player']]
+        else:
+            self.cfg_v2p['smpl_beta'] = SMPL_BETA.get(self.cfg_v2p.get('player'), [0.0] * 10)
         self.create_sim()
         dev = self.device
         f = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float)  # noqa: E731
@@ -181,7 +204,7 @@ class PhysicsMVAEController:
             scale_pos=float(scales.get('pos', 5.0)), scale_phase=float(scales.get('phase', 10.0)),
             scale_bounce_pos=float(scales.get('bounce_pos', 0.05)), scale_bounce_time=float(scales.get('bounce_time', 0.1)),
             w_pos=float(weights.get('pos', 1.0 if rtype == 'reach' else 0.0)), w_ball_pos=float(weights.get('ball_pos', 0.0)),
-            court_min=self._court_min.tolist(), court_max=self._court_max.tolist(), est_params=self._est_params)
+            court_min=self._court_min.tolist(), court_max=self._court_max.tolist(), est_params=self._est_params, dual=0)
 
     # ------------------------------------------------------------------ construction (:118-158)
     def create_sim(self):
@@ -194,7 +217,8 @@ class PhysicsMVAEController:
                             vid2player=dict(self.cfg_v2p),
                             keyBodies=[], contactBodies=[]),
                 "sim": {"substeps": phys.get("substeps", 2)}, "b200_physics": self.cfg.get("b200_physics", {})}
-        task = HumanoidSMPLIMMVAE(pcfg, self._sim_params, self._physics_engine, "cuda", self.device_id, True)
+        cls = HumanoidSMPLIMMVAEDual if self.cfg_v2p.get('dual_mode') else HumanoidSMPLIMMVAE
+        task = cls(pcfg, self._sim_params, self._physics_engine, "cuda", self.device_id, True)
         policy = env.get("low_level_policy", None)
         if policy is None:
             zeros = torch.zeros(self.num_envs, task.num_actions, device=self.device)
@@ -443,3 +467,87 @@ class PhysicsMVAEController:
 
     def render_vis(self):
         return
+
+
+class PhysicsMVAEControllerDual(PhysicsMVAEController):
+    """vid2player/env/tasks/physics_mvae_controller_dual.py: two players per rally in paired envs (2k, 2k+1).  The step is the
+    base class's (motion generator, FK targets, obs, policy, physics launch per asset, fused post step) with the dual reset FSM
+    selected in the post-step kernel; the reset below follows the reference's id lists (:27-64)."""
+
+    def __init__(self, cfg, sim_params, physics_engine, device_type, device_id, headless):
+        if cfg["env"]["numEnvs"] % 2:
+            raise ValueError("dual mode needs an even number of envs")
+        cfg["env"]["vid2player"].setdefault('dual_mode', True)
+        super().__init__(cfg=cfg, sim_params=sim_params, physics_engine=physics_engine, device_type=device_type, device_id=device_id,
+                         headless=headless)
+        self._reset_reaction_buf[:] = False
+        self._reset_recovery_buf[:] = False
+        self._post_cfg["dual"] = 1
+
+    def reset(self, env_ids=None):
+        if env_ids is None:
+            if self._has_init:
+                return
+            env_ids = torch.arange(self.num_envs, device=self.device, dtype=torch.long)
+        self._reset_envs(env_ids)
+
+    def _reset_env_tensors(self, env_ids):
+        """physics_mvae_controller.py:203-210"""
+        for buf in (self.progress_buf, self.reset_buf, self._terminate_buf, self._num_reset_reaction):
+            buf[env_ids] = 0
+        self._reset_reaction_buf[env_ids] = False
+        self._reset_recovery_buf[env_ids] = False
+        self._distance[env_ids] = 0
+
+    def _reset_envs(self, env_ids):
+        """:27-64"""
+        task = self._physics_player.task
+        env_ids = env_ids.to(self.device, dtype=torch.long)
+        empty = torch.zeros(0, device=self.device, dtype=torch.long)
+        if len(env_ids) > 0:
+            assert len(env_ids) % 2 == 0, len(env_ids)
+            reaction_actor = env_ids[::2] if self.cfg_v2p.get('serve_from', 'near') == 'near' else env_ids[1::2]
+            recovery_actor = get_opponent_env_ids(reaction_actor)
+            self._reset_reaction_buf[reaction_actor] = True
+            self._reset_recovery_buf[recovery_actor] = True
+        else:
+            reaction_actor = recovery_actor = empty
+        reaction_ids = self._reset_reaction_buf.nonzero(as_tuple=False).flatten()
+        recovery_ids = self._reset_recovery_buf.nonzero(as_tuple=False).flatten()
+        if len(env_ids) > 0:
+            self._mvae_player.reset_dual(reaction_actor, recovery_actor)
+            self._reset_env_tensors(env_ids)
+        if len(reaction_ids) > 0:
+            new_traj = task.reset(reaction_actor, reaction_ids)
+            self._ball_traj[reaction_ids, :new_traj.shape[1]] = new_traj
+            # self._update_state() (:52) re-derives bounce_in from unchanged inputs: nothing to do on the device
+        if len(recovery_ids) > 0:
+            self._reset_recovery_tasks(recovery_ids)
+        if len(reaction_ids) > 0:
+            self._reset_reaction_tasks(reaction_ids)
+            post = dict(self._post_cfg)
+            post["obs_only"] = 1
+            native_v2p.controller_post(post, self._tensors())
+        self._has_init = True
+
+    def _reset_reaction_tasks(self, env_ids):
+        """:66-85"""
+        self._tar_time[env_ids] = 0
+        self._tar_action[env_ids] = 1
+        self._num_reset_reaction[env_ids] += 1
+        self._bounce_in[env_ids] = False
+        if self.cfg_v2p.get('use_random_ball_target'):
+            seed = torch.rand(len(env_ids), device=self.device)
+            x = torch.where(seed < 0.33, -3.0, torch.where(seed > 0.67, 3.0, 0.0))
+            self._target_bounce_pos[env_ids] = torch.stack([x, torch.full_like(x, 10.0), torch.zeros_like(x)], -1)
+        if self.cfg_v2p.get('reward_type') == 'return_w_estimate':
+            self._est_bounce_pos[env_ids] = 0
+            self._est_bounce_time[env_ids] = 0
+            self._est_bounce_in[env_ids] = False
+            self._est_max_height[env_ids] = 0
+
+    def _reset_recovery_tasks(self, env_ids):
+        """:87-90"""
+        self._tar_action[env_ids] = 0
+        self._physics_player.task._has_bounce[env_ids] = False
+        self._physics_player.task._bounce_pos[env_ids] = 0

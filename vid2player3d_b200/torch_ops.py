@@ -14,3 +14,10 @@ def angle_axis_to_rot6d(aa):
                      y * x * C + z * s, c + y * y * C, y * z * C - x * s,
                      z * x * C - y * s, z * y * C + x * s, c + z * z * C], dim=-1).view(*aa.shape[:-1], 3, 3)
     return R[..., :2].transpose(-1, -2).reshape(*aa.shape[:-1], 6)
+
+
+def get_opponent_env_ids(env_ids):
+    """vid2player/utils/common.py:111-115: the paired env of each id (2k <-> 2k+1), sorted"""
+    if len(env_ids) == 0:
+        return env_ids
+    return (env_ids ^ 1).sort().values
