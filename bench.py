@@ -156,6 +156,53 @@ def federer_workload(envs, device_index, steps=96, warmup=16):
             "roofline_frac_hbm": 10900 * envs / (p0.elapsed_time(p1) / 20 * 1e-3) / 1e9 / peaks()[0]}
 
 
+def dual_workload(envs, device_index, steps=96, warmup=16):
+    """BASELINE config 5 (vid2player federer_djokovic dual) on one GPU: `envs` paired envs (envs/2 rallies), two assets stepped by
+    two launches per step (even rows = federer, odd rows = djokovic), dual reset FSM, ball hand-over through the incoming-ball
+    table; synthetic motion generator / zero-residual low-level policy as in config 3."""
+    import torch
+    from helpers import SIM_PARAMS, v2p_dual_cfg
+    from vid2player3d_b200.tasks import PhysicsMVAEControllerDual
+    torch.manual_seed(10)
+    env = PhysicsMVAEControllerDual(v2p_dual_cfg(envs), SIM_PARAMS, 1, "cuda", device_index, True)
+    dev = env.device
+    env.reset()
+    acts = [torch.clamp(torch.randn(envs, env.num_actions, device=dev), -5, 5) for _ in range(8)]
+    stats = {"resets": 0}
+
+    def run(n):
+        for i in range(n):
+            env.step(acts[i % 8])
+            done = env.reset_buf.nonzero(as_tuple=False).flatten()
+            stats["resets"] += len(done)
+            env.reset(done)
+    run(warmup)
+    env.enable_cuda_graph()
+    run(warmup)
+    torch.cuda.synchronize()
+    stats["resets"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    task = env._physics_player.task
+    a75 = torch.zeros(envs, task.num_actions, device=dev)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(20):
+        for h in task._envs:
+            h.step(a75)
+    p1.record()
+    torch.cuda.synchronize()
+    return {"env_steps_per_s": envs * steps / (ms * 1e-3), "ms_per_step": ms / steps, "physics_ms_both_assets": p0.elapsed_time(p1) / 20,
+            "steps": steps, "pair_resets_per_step": stats["resets"] / 2 / steps,
+            "mode": "one CUDA graph per high-level step (2 physics launches) + eager reference-shaped reset (id lists, host sync)",
+            "workload": f"vid2player federer_djokovic dual: {envs} paired envs ({envs // 2} rallies), substeps 6, return_w_estimate, "
+                        "use_random_ball_target, fix_head_orientation, synthetic incoming-ball table / motion generator"}
+
+
 def cpu_reference_arm(model, flat, sample_envs, steps, warmup, seed=7):
     """The CPU restatement of the same env step (oracle/physics_ref.c with OpenMP over envs + oracle/ref_port.py
     numpy obs/reward/reset/MoCap), timed on the host cores on a bounded sample of the workload's envs.
@@ -343,7 +390,7 @@ def main():
                 "api": "VecTaskPythonWrapper.step/reset, pinned host actions in, reward+reset out, host sync every step"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": "step_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "kernel": "step_kernel" if os.environ.get("B200ENV_KERNEL") == "lane" else "step_kernel_packed", "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                      "peak_source": peak_src,
                      "note": "latency / FP32-issue bound along the 9-level kinematic chain, not HBM bound (DESIGN.md 5)"},
     }
@@ -352,6 +399,10 @@ def main():
             out["config"]["federer"] = federer_workload(N, local_rank)
         except Exception as ex:  # secondary measurement must never break the contract line
             out["config"]["federer"] = {"error": repr(ex)[:200]}
+        try:
+            out["config"]["dual"] = dual_workload(N, local_rank)
+        except Exception as ex:
+            out["config"]["dual"] = {"error": repr(ex)[:200]}
     if not args.no_cpu_baseline:
         from oracle import physics_ref
         physics_ref.build()

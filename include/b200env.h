@@ -86,8 +86,10 @@ typedef struct b200_cfg {
   int32_t racket_body; /* body index of the welded Racket (24), -1 = none */
   float ball_mass, ball_inertia, ball_radius, spin_scale;
   float ball_e_ground, ball_mu_ground, ball_e_racket, ball_mu_racket, bounce_threshold_velocity;
-  float racket_head_center[3]; /* racket frame: cylinder fromto="0 0 0 0 0.0425 0" size 0.15 (federer.xml:190) */
+  float racket_head_center[3]; /* HEAD frame (see racket_head_quat): cylinder fromto="0 0 0 0 0.0425 0" size 0.15 (federer.xml:190) */
   float racket_head_halfthick, racket_head_radius;
+  float racket_head_quat[4]; /* xyzw, racket frame -> head frame whose +y is the string-bed normal: identity for the right-handed
+                                assets, 45 deg about x for nadal.xml's cylinder fromto="0 -.015 -.015 0 .015 .015" */
 } b200_cfg_t;
 
 /* Reference MoCap buffer (embodied_pose/utils/motion_lib.py:68-93): flat device arrays. */

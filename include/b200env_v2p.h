@@ -111,8 +111,9 @@ int b200v2p_task_reset(const b200v2p_treset_t* r, void* stream);
 typedef struct b200v2p_areset {
   int32_t n, num_dof, bodies_per_env, root_stride, racket_body, racket_parent;
   float racket_offset[3];
-  int32_t dual;             /* 1: odd envs use racket_offset2 (second player's asset) */
+  int32_t dual;             /* 1: odd envs use racket_offset2 / racket_parent2 (second player's asset) */
   float racket_offset2[3];
+  int32_t racket_parent2, pad_;
   const int64_t* env_ids;
   const float *src_root_pos, *src_root_rot, *src_dof_pos, *src_rb_pos, *src_rb_rot; /* [N,...] FK results */
   float *root_states, *dof_state, *rigid_body_state;

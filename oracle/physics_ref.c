@@ -389,7 +389,9 @@ static void ball_substep_ref(const b200_cfg_t* cfg, real h, ball_t* B, const bod
     for (int k = 0; k < 3; k++) d[k] = B->p[k] - racket->p[k];
     cross(racket->w, d, wxd);
     for (int k = 0; k < 3; k++) vrel[k] = B->v[k] - racket->v[k] - wxd[k];
-    q_rot_inv(racket->Q, d, d0); q_rot_inv(racket->Q, vrel, vr);
+    real hq[4] = {cfg->racket_head_quat[0], cfg->racket_head_quat[1], cfg->racket_head_quat[2], cfg->racket_head_quat[3]}, hQ[4];
+    q_mul(racket->Q, hq, hQ);   /* head frame in the world: the string-bed normal is its +y */
+    q_rot_inv(hQ, d, d0); q_rot_inv(hQ, vrel, vr);
     for (int k = 0; k < 3; k++) d0[k] -= cfg->racket_head_center[k];
     real H = cfg->racket_head_halfthick + R, Rad = cfg->racket_head_radius + R;
     if (fabs(d0[1]) < H) {
@@ -405,7 +407,7 @@ static void ball_substep_ref(const b200_cfg_t* cfg, real h, ball_t* B, const bod
     }
     if (thit >= 0) {
       real ny[3] = {0, nl, 0}, n[3], J[3], xc[3], dx[3], wxx[3], vo[3], vb[3];
-      q_rot(racket->Q, ny, n);
+      q_rot(hQ, ny, n);
       for (int k = 0; k < 3; k++) { xc[k] = B->p[k] + thit * B->v[k] - R * n[k]; dx[k] = xc[k] - racket->p[k]; vb[k] = B->v[k]; }
       cross(racket->w, dx, wxx);
       for (int k = 0; k < 3; k++) vo[k] = racket->v[k] + wxx[k];

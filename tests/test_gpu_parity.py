@@ -323,10 +323,10 @@ def test_missing_arguments_fail_loudly(small_lib):
 
 
 # --------------------------------------------------------------------------------------- ball + racket (vid2player)
-def make_ball_env(n=4, substeps=6):
-    """native env on the federer asset (24 bodies + welded Racket) with the tennis ball enabled"""
+def make_ball_env(n=4, substeps=6, asset="federer"):
+    """native env on a vid2player asset (24 bodies + welded Racket; nadal = left-handed, tilted head) with the tennis ball enabled"""
     from vid2player3d_b200 import abi, model_compiler, native
-    mod = model_compiler.load_compiled("smpl_mesh_humanoid_federer")
+    mod = model_compiler.canonical_racket_last(model_compiler.load_compiled("smpl_mesh_humanoid_" + asset))
     ms, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
     cfg = abi.make_cfg(mod, substeps=substeps, ball={}, task_mode=1, pd_mode=1)
     return mod, ms, verts, cfg, native.Env(ms, verts, cfg, n, 0)
@@ -347,12 +347,12 @@ def ball_scene(mod, ms, verts, cfg, n, seed):
     ball = np.zeros((n, 13)); ball[:, 6] = 1
     from scipy.spatial.transform import Rotation
     for e in range(n):
-        Rr = Rotation.from_quat(rb[e, 24, 3:7]).as_matrix()
+        Rr = Rotation.from_quat(rb[e, 24, 3:7]).as_matrix() @ Rotation.from_quat(list(cfg.racket_head_quat)).as_matrix()   # head frame
         pr, vr = rb[e, 24, 0:3], rb[e, 24, 7:10]
         kind = e % 4
         if kind in (0, 1):
             side = 1.0 if kind == 0 else -1.0
-            off = np.array([rng.uniform(-0.08, 0.08), 0.02125 + side * rng.uniform(0.06, 0.10), rng.uniform(-0.08, 0.08)])
+            off = np.array(list(cfg.racket_head_center)) + np.array([rng.uniform(-0.08, 0.08), side * rng.uniform(0.06, 0.10), rng.uniform(-0.08, 0.08)])
             ball[e, 0:3] = pr + Rr @ off
             ball[e, 7:10] = vr + Rr @ np.array([rng.normal(0, 3), -side * rng.uniform(15, 30), rng.normal(0, 3)])
             ball[e, 10:13] = rng.normal(0, 40, 3)
@@ -367,12 +367,12 @@ def ball_scene(mod, ms, verts, cfg, n, seed):
     return root, q, qd, tar, ext, ball
 
 
-@pytest.mark.parametrize("substeps", [2, 6])
-def test_ball_physics_f64_matches_oracle(substeps):
+@pytest.mark.parametrize("substeps,asset", [(2, "federer"), (6, "federer"), (6, "nadal")])
+def test_ball_physics_f64_matches_oracle(substeps, asset):
     """humanoid + welded racket + ball (aero, swept racket impact with reaction on the wrist, ground bounce):
     double-precision kernel vs float64 restatement, 1 and 3 control steps"""
     from oracle import physics_ref
-    mod, ms, verts, cfg, env = make_ball_env(4, substeps)
+    mod, ms, verts, cfg, env = make_ball_env(4, substeps, asset)
     n = 64
     root, q, qd, tar, ext, ball = ball_scene(mod, ms, verts, cfg, n, 17)
     for steps, tol in ((1, 1e-9), (3, 1e-7)):

@@ -472,3 +472,35 @@ def test_dual_end_to_end():
     assert (task._ball_pos[:, 2] >= 0.0319).all()
     # the two assets are really different bodies: federer and djokovic settle at different pelvis heights / masses
     assert abs(float(task._models[0]["mass"].sum()) - float(task._models[1]["mass"].sum())) > 0.1
+
+
+def test_left_handed_dual_pair():
+    """nadal (left-handed, semi-western) vs federer (right-handed, eastern): per-player wrist / grip / racket head (cfg nadal_federer.yaml)"""
+    from helpers import SIM_PARAMS, v2p_dual_cfg
+    from oracle import ref_port_v2p as V
+    from vid2player3d_b200.tasks import PhysicsMVAEControllerDual
+    torch.manual_seed(1)
+    N = 32
+    cfg = v2p_dual_cfg(N, assets=("smpl_mesh_humanoid_nadal.xml", "smpl_mesh_humanoid_federer.xml"), players=("nadal", "federer"))
+    cfg["env"]["vid2player"].update(grip=["semi_western", "eastern"], righthand=[False, True])
+    env = PhysicsMVAEControllerDual(cfg, SIM_PARAMS, 1, "cuda", 0, True)
+    task = env._physics_player.task
+    assert task._racket_wrist_body_id == [17, 22]
+    env.reset()
+    for _ in range(20):
+        env.step(torch.clamp(torch.randn(N, 35, device=DEV), -5, 5))
+        env.reset(env.reset_buf.nonzero(as_tuple=False).flatten())
+    torch.cuda.synchronize()
+    rbs = task._rigid_body_state.view(N, 26, 13).cpu().numpy()
+    assert np.isfinite(rbs).all()
+    for par, wrist, grip in ((0, 17, 'semi_western'), (1, 22, 'eastern')):
+        o = V.update_state_from_sim(rbs[par::2, :25], task._humanoid_root_states[par::2].cpu().numpy(), task._ball_root_states[par::2].cpu().numpy(),
+                                    task._ball_vel[par::2].cpu().numpy(), task._has_racket_ball_contact[par::2].cpu().numpy(), grip,
+                                    racket_body=24, wrist_body=wrist)
+        close(task._racket_normal[par::2], o["racket_normal"], 2e-6)
+        close(task._racket_pos[par::2], o["racket_pos"], 0)
+    # the welded racket hangs off the left wrist for nadal, off the right wrist for federer (0.5 m along -/+ x of the wrist frame)
+    d_l = np.linalg.norm(rbs[0::2, 24, 0:3] - rbs[0::2, 17, 0:3], axis=1)
+    d_r = np.linalg.norm(rbs[1::2, 24, 0:3] - rbs[1::2, 22, 0:3], axis=1)
+    np.testing.assert_allclose(d_l, 0.5, atol=1e-4)
+    np.testing.assert_allclose(d_r, 0.5, atol=1e-4)

@@ -104,6 +104,26 @@ def test_compiled_models():
         assert w.min() > 0 and w[0] + w[1] >= w[2] * (1 - 1e-9)
 
 
+def test_left_handed_asset_in_canonical_order():
+    """nadal (Racket welded to L_Wrist, body 19) -> right-handed body order; head slab normal = the semi_western grip normal"""
+    from vid2player3d_b200 import abi, model_compiler, native_v2p
+    raw = model_compiler.load_compiled("smpl_mesh_humanoid_nadal")
+    fed = model_compiler.load_compiled("smpl_mesh_humanoid_federer")
+    m = model_compiler.canonical_racket_last(raw)
+    assert [str(x) for x in m["body_names"]] == [str(x) for x in fed["body_names"]]
+    assert int(m["parent"][24]) == 17 and int(fed["parent"][24]) == 22 and int(m["fixed"][24]) == 1
+    assert np.isclose(m["mass"].sum(), raw["mass"].sum()) and np.isclose(m["dyn_mass"].sum(), raw["dyn_mass"].sum())
+    assert np.array_equal(m["dof_of_body"][:24], fed["dof_of_body"][:24])          # DOF order untouched
+    assert model_compiler.canonical_racket_last(fed) is fed
+    h = abi.racket_head_from_prims(m)
+    x, y, z, w = h["racket_head_quat"]
+    normal = np.array([2 * (x * y - z * w), 1 - 2 * (x * x + z * z), 2 * (y * z + x * w)])   # R(q) e_y
+    np.testing.assert_allclose(normal, native_v2p.GRIP_NORMAL['semi_western'], atol=1e-12)
+    np.testing.assert_allclose(abi.racket_head_from_prims(fed)["racket_head_quat"], (0, 0, 0, 1), atol=1e-12)
+    cfg = abi.make_cfg(m, ball={}, task_mode=1, pd_mode=1)
+    assert cfg.racket_body == 24 and abs(cfg.racket_head_halfthick - 0.015 * 2 ** 0.5) < 1e-6
+
+
 def test_model_compiler_reproduces_committed_blob():
     ref = "/root/reference/embodied_pose/data/assets/mjcf/smpl_mesh_humanoid_amass_v1.xml"
     if not os.path.exists(ref):

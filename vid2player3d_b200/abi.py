@@ -40,6 +40,7 @@ class Cfg(C.Structure):
         ("ball_e_ground", C.c_float), ("ball_mu_ground", C.c_float), ("ball_e_racket", C.c_float), ("ball_mu_racket", C.c_float),
         ("bounce_threshold_velocity", C.c_float),
         ("racket_head_center", C.c_float * 3), ("racket_head_halfthick", C.c_float), ("racket_head_radius", C.c_float),
+        ("racket_head_quat", C.c_float * 4),
     ]
 
 
@@ -151,9 +152,12 @@ def make_cfg(model, *, sim_dt=1.0 / 60.0, substeps=2, control_freq_inv=2, gravit
     c.task_mode, c.pd_mode = task_mode, pd_mode
     c.racket_body = names.index("Racket") if "Racket" in names else -1
     c.has_ball = 0
+    _fill(c.racket_head_quat, (0.0, 0.0, 0.0, 1.0))
     if ball is not None:
         b = dict(DEFAULT_BALL)
+        b.update(racket_head_from_prims(model))
         b.update(ball)
+        _fill(c.racket_head_quat, b["racket_head_quat"])
         c.has_ball = 1
         for k in ("ball_mass", "ball_inertia", "ball_radius", "spin_scale", "ball_e_ground", "ball_mu_ground", "ball_e_racket",
                   "ball_mu_racket", "bounce_threshold_velocity", "racket_head_halfthick", "racket_head_radius"):
@@ -162,12 +166,36 @@ def make_cfg(model, *, sim_dt=1.0 / 60.0, substeps=2, control_freq_inv=2, gravit
     return c
 
 
+def racket_head_from_prims(model):
+    """Racket head slab from the asset's geom primitives (model_compiler `prims` rows: body, p0, p1, radius): the head is the
+    widest cylinder of the Racket body; its axis is the string-bed normal.  Returns {} when the model has no Racket."""
+    names = [str(x) for x in model["body_names"]]
+    if "Racket" not in names or "prims" not in model or len(model["prims"]) == 0:
+        return {}
+    rows = [r for r in np.asarray(model["prims"], np.float64) if int(r[0]) == names.index("Racket")]
+    if not rows:
+        return {}
+    r = max(rows, key=lambda x: x[7])
+    p0, p1 = r[1:4], r[4:7]
+    axis = (p1 - p0) / np.linalg.norm(p1 - p0)
+    y = np.array([0.0, 1.0, 0.0])                      # quaternion (xyzw) rotating +y onto the axis
+    v, w = np.cross(y, axis), 1.0 + float(y @ axis)
+    q = np.array([v[0], v[1], v[2], w])
+    q /= np.linalg.norm(q)
+    x, yq, z, w = q
+    R = np.array([[1 - 2 * (yq * yq + z * z), 2 * (x * yq - z * w), 2 * (x * z + yq * w)],
+                  [2 * (x * yq + z * w), 1 - 2 * (x * x + z * z), 2 * (yq * z - x * w)],
+                  [2 * (x * z - yq * w), 2 * (yq * z + x * w), 1 - 2 * (x * x + yq * yq)]])
+    return dict(racket_head_center=tuple(R.T @ (0.5 * (p0 + p1))), racket_head_halfthick=float(0.5 * np.linalg.norm(p1 - p0)),
+                racket_head_radius=float(r[7]), racket_head_quat=tuple(q))
+
+
 # tennis_ball.urdf (r 0.032, m 0.057, I 4e-5); restitution/friction: PhysX "average" combine of the material values the
 # reference sets (humanoid_smpl_im_mvae.py:414-416,436-438: ball & racket 0.9 / 0.2 & 0.8; plane 0.5 / 1.0 from
 # cfg/controller/federer.yaml:14-23); racket head = cylinder fromto "0 0 0 0 0.0425 0" size 0.15 (federer.xml:190)
 DEFAULT_BALL = dict(ball_mass=0.057, ball_inertia=4e-5, ball_radius=0.032, spin_scale=5.0, ball_e_ground=0.7, ball_mu_ground=0.6,
                     ball_e_racket=0.9, ball_mu_racket=0.5, bounce_threshold_velocity=0.2, racket_head_center=(0.0, 0.02125, 0.0),
-                    racket_head_halfthick=0.02125, racket_head_radius=0.15)
+                    racket_head_halfthick=0.02125, racket_head_radius=0.15, racket_head_quat=(0.0, 0.0, 0.0, 1.0))
 
 
 # ---------------------------------------------------------------- include/b200env_v2p.h
@@ -226,7 +254,7 @@ class V2PActorReset(C.Structure):
     _fields_ = [
         ("n", C.c_int32), ("num_dof", C.c_int32), ("bodies_per_env", C.c_int32), ("root_stride", C.c_int32),
         ("racket_body", C.c_int32), ("racket_parent", C.c_int32), ("racket_offset", C.c_float * 3),
-        ("dual", C.c_int32), ("racket_offset2", C.c_float * 3),
+        ("dual", C.c_int32), ("racket_offset2", C.c_float * 3), ("racket_parent2", C.c_int32), ("pad_", C.c_int32),
         ("env_ids", C.c_void_p),
         ("src_root_pos", C.c_void_p), ("src_root_rot", C.c_void_p), ("src_dof_pos", C.c_void_p), ("src_rb_pos", C.c_void_p),
         ("src_rb_rot", C.c_void_p),

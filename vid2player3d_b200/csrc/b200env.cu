@@ -218,7 +218,7 @@ template <typename T> struct PhysCfg {
   int substeps, cfi;
   // tennis ball (vid2player): lane BALL_LANE integrates it next to the humanoid
   int has_ball, racket_body, wrist_body;
-  T bm, bI, bR, spin_scale, eg, mug, er, mur, vth, hc[3], hh, hr;
+  T bm, bI, bR, spin_scale, eg, mug, er, mur, vth, hc[3], hh, hr, hq[4];
 };
 #define BALL_LANE 31
 // ball state held by lane BALL_LANE (float64 restatement: oracle/physics_ref.c::ball_substep)
@@ -243,6 +243,8 @@ template <typename T> __device__ __forceinline__ PhysCfg<T> make_phys_cfg(const 
   p.vth = T(c.bounce_threshold_velocity);
   p.hc[0] = T(c.racket_head_center[0]); p.hc[1] = T(c.racket_head_center[1]); p.hc[2] = T(c.racket_head_center[2]);
   p.hh = T(c.racket_head_halfthick); p.hr = T(c.racket_head_radius);
+#pragma unroll
+  for (int k = 0; k < 4; k++) p.hq[k] = T(c.racket_head_quat[k]);
   return p;
 }
 
@@ -344,7 +346,9 @@ __device__ __forceinline__ void ball_substep(const PhysCfg<T>& c, Ball<T>& B, bo
     T d[3] = {B.p[0] - rp[0], B.p[1] - rp[1], B.p[2] - rp[2]}, wxd[3];
     cross3(rw, d, wxd);
     T vrel_w[3] = {B.v[0] - rv[0] - wxd[0], B.v[1] - rv[1] - wxd[1], B.v[2] - rv[2] - wxd[2]};
-    T cq[4] = {-rQ[0], -rQ[1], -rQ[2], rQ[3]}, d0[3], vr[3];
+    T hQ[4];
+    qmul(rQ, c.hq, hQ);   // head frame in the world (string-bed normal = its +y)
+    T cq[4] = {-hQ[0], -hQ[1], -hQ[2], hQ[3]}, d0[3], vr[3];
     qrot(cq, d, d0);
     qrot(cq, vrel_w, vr);
     d0[0] -= c.hc[0]; d0[1] -= c.hc[1]; d0[2] -= c.hc[2];
@@ -363,7 +367,7 @@ __device__ __forceinline__ void ball_substep(const PhysCfg<T>& c, Ball<T>& B, bo
     if (thit >= T(0)) {
       const T ny[3] = {T(0), nl, T(0)};
       T n[3], J[3], vo[3];
-      qrot(rQ, ny, n);
+      qrot(hQ, ny, n);
       T xc[3] = {B.p[0] + thit * B.v[0] - c.bR * n[0], B.p[1] + thit * B.v[1] - c.bR * n[1], B.p[2] + thit * B.v[2] - c.bR * n[2]};
       T dx[3] = {xc[0] - rp[0], xc[1] - rp[1], xc[2] - rp[2]}, wxx[3];
       cross3(rw, dx, wxx);

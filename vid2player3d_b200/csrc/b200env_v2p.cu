@@ -601,9 +601,11 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) actor_reset_kernel(b200v2p_are
     for (int k = 0; k < 4; k++) { row[3 + k] = q[k]; r.prev_target_rb_rot[(e * 24 + lane) * 4 + k] = q[k]; }
   }
   if (lane == 24 && r.racket_body >= 0) {  // welded racket row = parent pose + rotated offset (first obs is consistent)
-    const float* pp = r.src_rb_pos + (e * 24 + r.racket_parent) * 3;
-    const float* q = r.src_rb_rot + (e * 24 + r.racket_parent) * 4;
-    const float* ro = (r.dual && (e & 1)) ? r.racket_offset2 : r.racket_offset;
+    const bool second = r.dual && (e & 1);
+    const int rpar = second ? r.racket_parent2 : r.racket_parent;
+    const float* pp = r.src_rb_pos + (e * 24 + rpar) * 3;
+    const float* q = r.src_rb_rot + (e * 24 + rpar) * 4;
+    const float* ro = second ? r.racket_offset2 : r.racket_offset;
     const float o[3] = {ro[0], ro[1], ro[2]};
     float t[3] = {2.0f * (q[1] * o[2] - q[2] * o[1]), 2.0f * (q[2] * o[0] - q[0] * o[2]), 2.0f * (q[0] * o[1] - q[1] * o[0])};
     float u[3] = {q[1] * t[2] - q[2] * t[1], q[2] * t[0] - q[0] * t[2], q[0] * t[1] - q[1] * t[0]};

@@ -236,6 +236,34 @@ def load_compiled(name):
     return load(os.path.join(COMPILED_DIR, name + ".npz"))
 
 
+def canonical_racket_last(model):
+    """Left-handed assets (nadal: Racket welded to L_Wrist, body 19) in the right-handed body order [humanoid 0..23, Racket 24].
+    This is the order the reference's consumers see through `_humanoid_body_ids_lefthand`
+    (vid2player/env/tasks/humanoid_smpl_im_mvae.py:67,197-206); here the simulator itself runs in it, so no permuted copy of the
+    rigid-body tensors is needed.  DOF order is untouched (the Racket has no DOF).  No-op when the Racket is already last."""
+    names = [str(x) for x in model["body_names"]]
+    if "Racket" not in names or names[-1] == "Racket":
+        return model
+    nb, r = len(names), names.index("Racket")
+    perm = [i for i in range(nb) if i != r] + [r]          # new index -> old index
+    inv = {old: new for new, old in enumerate(perm)}
+    out = dict(model)
+    for k, v in model.items():
+        v = np.asarray(v)
+        if k in ("parent", "dof_body_ids"):
+            continue
+        if v.ndim >= 1 and v.shape[0] == nb and k not in ("kp", "kd", "armature", "limits", "dof_names", "prims"):
+            out[k] = v[perm]
+    out["parent"] = np.array([inv[int(p)] if p >= 0 else -1 for p in np.asarray(model["parent"])[perm]], np.int32)
+    out["dof_body_ids"] = np.array([inv[int(b)] for b in model["dof_body_ids"]], np.int32)
+    if "prims" in model and len(model["prims"]):
+        pr = np.array(model["prims"], np.float64)
+        pr[:, 0] = [inv[int(b)] for b in pr[:, 0]]
+        out["prims"] = pr
+    assert all(out["parent"][i] < i for i in range(nb))     # parents still precede their children
+    return out
+
+
 if __name__ == "__main__":
     import sys
     ref = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"

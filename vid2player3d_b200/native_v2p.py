@@ -136,10 +136,11 @@ def actor_reset(cfg, t):
         r.racket_offset[i] = float(v)
     if cfg.get("racket_offset2") is not None:
         r.dual = 1
+        r.racket_parent2 = int(cfg.get("racket_parent2", cfg["racket_parent"]))
         for i, v in enumerate(cfg["racket_offset2"]):
             r.racket_offset2[i] = float(v)
     for name, _ in abi.V2PActorReset._fields_:
-        if name in cfg or name in ("dual", "racket_offset2"):
+        if name in cfg or name in ("dual", "racket_offset2", "racket_parent2", "pad_"):
             continue
         x = t[name]
         assert x.is_cuda and x.is_contiguous(), name

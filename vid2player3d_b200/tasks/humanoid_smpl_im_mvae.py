@@ -48,14 +48,23 @@ class HumanoidSMPLIMMVAE(BaseTask):
         # one asset, or one per player in dual_mode 'different' (:260-275: env 2k -> asset 0, env 2k+1 -> asset 1)
         files = env["asset"]["assetFileName"]
         files = list(files) if isinstance(files, (list, tuple)) else [files]
-        self._models = [model_compiler.load_compiled(os.path.splitext(os.path.basename(f))[0]) for f in files]
+        # left-handed assets are brought into the right-handed body order (Racket last), see model_compiler.canonical_racket_last
+        self._models = [model_compiler.canonical_racket_last(model_compiler.load_compiled(os.path.splitext(os.path.basename(f))[0]))
+                        for f in files]
         self._model = self._models[0]
         self.body_names = [str(x) for x in self._model["body_names"]]
         self.num_bodies = len(self.body_names)          # 25 = humanoid + Racket (the ball is a separate actor)
         for m in self._models:
             if [str(x) for x in m["body_names"]] != self.body_names or self.num_bodies != 25 or self.body_names[-1] != "Racket":
-                raise NotImplementedError("left-handed assets (Racket on L_Hand, `righthand: False`, :74-84 / :197-206) need the "
-                                          "rigid-body row permutation _humanoid_body_ids_lefthand; not built (DESIGN.md 8)")
+                raise ValueError("vid2player assets must be the 24-body SMPL humanoid + a welded Racket")
+        # per-player racket wrist (:68-84): R_Wrist 22, or L_Wrist 17 for a left-handed player; the racket's parent in the asset
+        self._racket_parents = [int(m["parent"][24]) for m in self._models]
+        rh = self.cfg_v2p.get('righthand', True)
+        rh = list(rh) if isinstance(rh, (list, tuple)) else [rh] * len(self._models)
+        for k, (r, par) in enumerate(zip(rh, self._racket_parents)):
+            if par != (22 if r else 17):
+                raise ValueError(f"asset {files[k]} has its racket on body {par}, which contradicts righthand={r}")
+        self._racket_wrist_body_id = self._racket_parents[0] if len(set(self._racket_parents)) == 1 else list(self._racket_parents)
         if env["numEnvs"] % len(self._models):
             raise ValueError("numEnvs must be a multiple of the number of assets")
         self.num_dof = self._num_dof = len(self._model["kp"])
@@ -94,12 +103,13 @@ class HumanoidSMPLIMMVAE(BaseTask):
         ball["ball_e_ground"] = 0.5 * (rest + plane_rest)                        # PhysX average combine
         ball["ball_mu_racket"] = 0.5 * (v2p.get("racket_friction", 0.8) + v2p.get("ball_friction", 0.2))
         ball["ball_mu_ground"] = 0.5 * (env.get("plane", {}).get("dynamicFriction", 1.0) + v2p.get("ball_friction", 0.2))
-        self._cfg_struct = abi.make_cfg(
-            self._model, sim_dt=self.sim_dt, substeps=self.sim_substeps, control_freq_inv=env.get("controlFrequencyInv", 2),
+        mk_cfg = lambda model: abi.make_cfg(  # noqa: E731
+            model, sim_dt=self.sim_dt, substeps=self.sim_substeps, control_freq_inv=env.get("controlFrequencyInv", 2),
             pd_tar_lim=0.5 * np.pi, res_force_scale=self.residual_force_scale, res_torque_scale=self.residual_torque_scale,
             max_episode_length=self.max_episode_length, enable_early_termination=False, contact_bodies=tuple(env.get("contactBodies", ())),
             key_bodies=tuple(env.get("keyBodies", ())), friction_mu=env.get("plane", {}).get("dynamicFriction", 1.0),
             task_mode=1, pd_mode=1, ball=ball, **self.cfg.get("b200_physics", {}))
+        self._cfg_struct = mk_cfg(self._model)
         # one handle per asset; handle k steps rows k, k+K, ... of the shared tensors (b200env_set_env_slice)
         self._envs, K = [], len(self._models)
         for k, m in enumerate(self._models):
@@ -107,7 +117,7 @@ class HumanoidSMPLIMMVAE(BaseTask):
             ms, verts = abi.pack_model(m, pd_scale * self.kp_scale, pd_scale * self.kd_scale)
             if k == 0:
                 self._model_struct, self._verts = ms, verts
-            h = native.Env(ms, verts, self._cfg_struct, self.num_envs // K, self.device_id)
+            h = native.Env(ms, verts, mk_cfg(m), self.num_envs // K, self.device_id)      # racket head geometry is per asset
             if K > 1:
                 h.set_env_slice(k, K)
             self._envs.append(h)
@@ -248,12 +258,12 @@ class HumanoidSMPLIMMVAE(BaseTask):
             self._has_racket_ball_contact |= now
             keep = self._has_racket_ball_contact.clone()
             native_v2p.update_state(self.num_envs, 26, self._rigid_body_state, self._root_states, 26, self._root_states[1:], 26, t,
-                                    grip=self._grip())
+                                    grip=self._grip(), wrist_body=self._racket_wrist_body_id)
             self._has_racket_ball_contact.copy_(keep)
             self._has_racket_ball_contact_now.copy_(now)
         else:
             native_v2p.update_state(self.num_envs, 26, self._rigid_body_state, self._root_states, 26, self._root_states[1:], 26, t,
-                                    grip=self._grip())
+                                    grip=self._grip(), wrist_body=self._racket_wrist_body_id)
 
     def _grip(self):
         g = self.cfg_v2p.get('grip', 'eastern')            # a pair in dual_mode 'different' (:839-842)
@@ -271,9 +281,10 @@ class HumanoidSMPLIMMVAE(BaseTask):
     def _reset_actors(self, env_ids):
         """:463-501 + :562-581: sim state <- FK of the motion generator's initial pose (zero velocities); 2 launches"""
         self._smpl_to_sim_into(self._mvae_player._root_pos.contiguous(), self._mvae_player._joint_rotmat, self._tmp)
-        cfg = dict(n=len(env_ids), num_dof=self.num_dof, bodies_per_env=26, root_stride=26, racket_body=24, racket_parent=22,
-                   racket_offset=self._model["offset"][24],
-                   racket_offset2=self._models[1]["offset"][24] if len(self._models) == 2 else None)
+        cfg = dict(n=len(env_ids), num_dof=self.num_dof, bodies_per_env=26, root_stride=26, racket_body=24,
+                   racket_parent=self._racket_parents[0], racket_offset=self._model["offset"][24],
+                   racket_offset2=self._models[1]["offset"][24] if len(self._models) == 2 else None,
+                   racket_parent2=self._racket_parents[-1])
         native_v2p.actor_reset(cfg, dict(
             env_ids=env_ids.contiguous(), src_root_pos=self._mvae_player._root_pos.contiguous(), src_root_rot=self._tmp["root_rot"],
             src_dof_pos=self._tmp["dof_pos"], src_rb_pos=self._tmp["rb_pos"], src_rb_rot=self._tmp["rb_rot"], root_states=self._root_states,
