@@ -3,6 +3,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -188,3 +189,26 @@ def test_vec_task_and_parse_task_surface():
         class A:  # noqa: D401
             task = "Nope"; device_id = 0; rl_device = "cpu"; physics_engine = 1; device = "cuda"; headless = True
         pt(A, {"env": {}}, {}, None)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/embodied_pose"), reason="reference checkout not present (GPU box)")
+def test_reference_config_module_runs_on_the_shim():
+    """Level B of the boundary: the reference's own utils/config.py (get_args / load_cfg / parse_sim_params)
+    imports and runs UNCHANGED against vid2player3d_b200/shim/isaacgym, in a subprocess so sys.modules stays clean."""
+    code = r'''
+import sys
+sys.path.insert(0, "%s/vid2player3d_b200/shim"); sys.path.insert(0, "/root/reference/embodied_pose")
+sys.argv = ["run.py", "--cfg", "amass_im", "--headless", "--num_envs", "64"]
+from isaacgym import gymapi
+from utils.config import get_args, load_cfg, parse_sim_params
+import os; os.chdir("/root/reference")
+args = get_args()
+cfg, cfg_train = load_cfg(args)
+sp = parse_sim_params(args, cfg, cfg_train)
+assert abs(sp.dt - 1.0 / 60.0) < 1e-9 and sp.substeps == cfg["sim"]["substeps"] == 2, (sp.dt, sp.substeps)
+assert sp.physx.num_position_iterations == 4 and sp.physx.contact_offset == 0.02, (sp.physx.num_position_iterations,)
+assert cfg["env"]["numEnvs"] == 64 and cfg["name"] == "HumanoidSMPLIM"
+print("OK", args.task, sp.up_axis == gymapi.UP_AXIS_Z)
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
