@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/b200env.h"
 
 #define FULL 0xffffffffu
@@ -55,7 +57,7 @@ struct DevTree {
 struct DevBlob {
   b200_model_t m;
   DevTree t;
-  // float verts[nb][vmax][3] follows
+  // float verts[nb][3][vmax] follows (SoA per body: x | y | z, see contact_hull)
 };
 static_assert(sizeof(b200_model_t) % 16 == 0, "model block must be a 16-byte multiple for the bulk copy");
 static_assert(sizeof(DevBlob) % 16 == 0, "blob header must be a 16-byte multiple");
@@ -220,6 +222,9 @@ template <typename T> struct PhysCfg {
   int has_ball, racket_body, wrist_body;
   T bm, bI, bR, spin_scale, eg, mug, er, mur, vth, hc[3], hh, hr, hq[4];
 };
+#ifndef ABL
+#define ABL 0   // tools/ablate.sh: 1 no physics, 2 epilogue = state write-back only, 3 no reward block, 4 no MoCap sample / targets, 5 no obs
+#endif
 #define BALL_LANE 31
 // ball state held by lane BALL_LANE (float64 restatement: oracle/physics_ref.c::ball_substep)
 template <typename T> struct Ball {
@@ -397,6 +402,72 @@ __device__ __forceinline__ void ball_substep(const PhysCfg<T>& c, Ball<T>& B, bo
 }
 
 // One substep of length h (float64 restatement: oracle/physics_ref.c::substep).
+// Ground contact of one body's convex-hull vertices against z = 0, implicit in the velocity.
+// vb: the body's vertices in the blob, SoA  x[vmax] | y[vmax] | z[vmax]  (vmax % 4 == 0, 16-byte aligned, padding = 0).
+// Pass 1 tests four vertices per iteration (3 LDS.128, independent FMAs) and records the penetrating ones in a bit mask;
+// pass 2 visits only those, in ascending vertex order - the accumulation order (and therefore every bit of the result)
+// is the same as a plain loop over k.  With most vertices above the ground the serial per-vertex test was ~40 % of the
+// physics time of fallen humanoids (tools/ablate.sh).
+template <typename T>
+__device__ __forceinline__ void contact_hull(const float* __restrict__ vb, int vmax, int nv, const PhysCfg<T>& c, const T* R, const T* p,
+                                             const T* v, const T* w, T* A, T* Bm, T* C, T* bn, T* bf, T* cf) {
+  unsigned long long mask = 0ull;
+  const T pz = p[2];
+  for (int k0 = 0; k0 < nv; k0 += 4) {
+    const float4 X = *reinterpret_cast<const float4*>(vb + k0);
+    const float4 Y = *reinterpret_cast<const float4*>(vb + vmax + k0);
+    const float4 Z = *reinterpret_cast<const float4*>(vb + 2 * vmax + k0);
+    const T r0 = R[6] * T(X.x) + R[7] * T(Y.x) + R[8] * T(Z.x);
+    const T r1 = R[6] * T(X.y) + R[7] * T(Y.y) + R[8] * T(Z.y);
+    const T r2 = R[6] * T(X.z) + R[7] * T(Y.z) + R[8] * T(Z.z);
+    const T r3 = R[6] * T(X.w) + R[7] * T(Y.w) + R[8] * T(Z.w);
+    const unsigned m = ((-(pz + r0) > T(0)) ? 1u : 0u) | ((-(pz + r1) > T(0)) ? 2u : 0u) | ((-(pz + r2) > T(0)) ? 4u : 0u) |
+                       ((-(pz + r3) > T(0)) ? 8u : 0u);
+    mask |= (unsigned long long)m << k0;
+  }
+  if (nv < 64) mask &= (1ull << nv) - 1ull;   // padding vertices (zeros) never count
+  const T kimp = c.h * c.cn + c.h * c.h * c.kn;
+  while (mask) {
+    const int k = __ffsll((long long)mask) - 1;
+    mask &= mask - 1ull;
+    const T vl[3] = {T(vb[k]), T(vb[vmax + k]), T(vb[2 * vmax + k])};
+    const T rz = R[6] * vl[0] + R[7] * vl[1] + R[8] * vl[2];
+    const T pen = -(pz + rz);
+    if (!(pen > T(0))) continue;   // (re-tested: the two passes may contract their FMAs differently)
+    const T rx = R[0] * vl[0] + R[1] * vl[1] + R[2] * vl[2];
+    const T ry = R[3] * vl[0] + R[4] * vl[1] + R[5] * vl[2];
+    const T ux = v[0] + w[1] * rz - w[2] * ry;
+    const T uy = v[1] + w[2] * rx - w[0] * rz;
+    const T uz = v[2] + w[0] * ry - w[1] * rx;
+    const T fn0 = c.kn * pen - c.cn * uz;
+    if (!(fn0 > T(0))) continue;
+    const T ut = sqrt_(ux * ux + uy * uy);
+    const T ct = c.mu * fn0 * rcp_(ut > c.vs ? ut : c.vs);
+    const T hct = c.h * ct;
+    // Jn = [(ry, -rx, 0); (0,0,1)], Jx = [(0, rz, -ry); (1,0,0)], Jy = [(-rz, 0, rx); (0,1,0)]
+    A[0] += kimp * ry * ry + hct * rz * rz;
+    A[1] += kimp * rx * rx + hct * rz * rz;
+    A[2] += hct * (ry * ry + rx * rx);
+    A[3] += -kimp * ry * rx;
+    A[4] += -hct * rz * rx;
+    A[5] += -hct * rz * ry;
+    Bm[2] += kimp * ry;   // (Jn_ang)(Jn_lin)^T : column z
+    Bm[5] += -kimp * rx;
+    Bm[3] += hct * rz;    // Jx: ang (0,rz,-ry) x lin ex -> column x
+    Bm[6] += -hct * ry;
+    Bm[1] += -hct * rz;   // Jy: ang (-rz,0,rx) x lin ey -> column y
+    Bm[7] += hct * rx;
+    C[0] += hct; C[1] += hct; C[2] += kimp;
+    // wrench W = Jn fn0 - ct (Jx ux + Jy uy);  b -= W
+    const T fx = -ct * ux, fy = -ct * uy;
+    bn[0] -= ry * fn0 - rz * fy;
+    bn[1] -= -rx * fn0 + rz * fx;
+    bn[2] -= -ry * fx + rx * fy;
+    bf[0] -= fx; bf[1] -= fy; bf[2] -= fn0;
+    cf[0] += fx; cf[1] += fy; cf[2] += fn0;
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void substep(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c,
                                         const LaneConst& lc, int lane, Lane<T>& L, const T* pdtar, bool ext_on,
@@ -474,47 +545,8 @@ __device__ __forceinline__ void substep(const DevBlob& B, const float* __restric
     }
     // ground contact of the hull vertices, implicit in the velocity
     const int nv = M.nverts[lane];
-    if (nv > 0 && L.p[2] - T(M.radius[lane]) < T(0)) {
-      const float* vb = verts + (size_t)lane * M.vmax * 3;
-      const T kimp = c.h * c.cn + c.h * c.h * c.kn;
-      for (int k = 0; k < nv; k++) {
-        T vl[3] = {T(vb[3 * k]), T(vb[3 * k + 1]), T(vb[3 * k + 2])};
-        T rz = R[6] * vl[0] + R[7] * vl[1] + R[8] * vl[2];
-        T pen = -(L.p[2] + rz);
-        if (!(pen > T(0))) continue;
-        T rx = R[0] * vl[0] + R[1] * vl[1] + R[2] * vl[2];
-        T ry = R[3] * vl[0] + R[4] * vl[1] + R[5] * vl[2];
-        T ux = L.v[0] + L.w[1] * rz - L.w[2] * ry;
-        T uy = L.v[1] + L.w[2] * rx - L.w[0] * rz;
-        T uz = L.v[2] + L.w[0] * ry - L.w[1] * rx;
-        T fn0 = c.kn * pen - c.cn * uz;
-        if (!(fn0 > T(0))) continue;
-        T ut = sqrt_(ux * ux + uy * uy);
-        T ct = c.mu * fn0 * rcp_(ut > c.vs ? ut : c.vs);
-        T hct = c.h * ct;
-        // Jn = [(ry, -rx, 0); (0,0,1)], Jx = [(0, rz, -ry); (1,0,0)], Jy = [(-rz, 0, rx); (0,1,0)]
-        A[0] += kimp * ry * ry + hct * rz * rz;
-        A[1] += kimp * rx * rx + hct * rz * rz;
-        A[2] += hct * (ry * ry + rx * rx);
-        A[3] += -kimp * ry * rx;
-        A[4] += -hct * rz * rx;
-        A[5] += -hct * rz * ry;
-        Bm[2] += kimp * ry;   // (Jn_ang)(Jn_lin)^T : column z
-        Bm[5] += -kimp * rx;
-        Bm[3] += hct * rz;    // Jx: ang (0,rz,-ry) x lin ex -> column x
-        Bm[6] += -hct * ry;
-        Bm[1] += -hct * rz;   // Jy: ang (-rz,0,rx) x lin ey -> column y
-        Bm[7] += hct * rx;
-        C[0] += hct; C[1] += hct; C[2] += kimp;
-        // wrench W = Jn fn0 - ct (Jx ux + Jy uy);  b -= W
-        T fx = -ct * ux, fy = -ct * uy;
-        bn[0] -= ry * fn0 - rz * fy;
-        bn[1] -= -rx * fn0 + rz * fx;
-        bn[2] -= -ry * fx + rx * fy;
-        bf[0] -= fx; bf[1] -= fy; bf[2] -= fn0;
-        cf[0] += fx; cf[1] += fy; cf[2] += fn0;
-      }
-    }
+    if (nv > 0 && L.p[2] - T(M.radius[lane]) < T(0))
+      contact_hull<T>(verts + (size_t)lane * M.vmax * 3, M.vmax, nv, c, R, L.p, L.v, L.w, A, Bm, C, bn, bf, cf);
     // joint drive (child frame, exp-map chart): implicit PD + armature + limit springs
     if (lane > 0) {
       T q[3], tau[3], e[3];
@@ -1162,24 +1194,28 @@ __device__ __forceinline__ void step_epilogue(const b200_buffers_t& bf, const b2
     if (lane == 0) bf.progress_buf[e] += 1;  // are produced by post_mvae_step, rewards / resets by the controller
     return;
   }
+  if (ABL == 2) return;
   // ---- post-physics (:398-418)
   const int64_t progress = bf.progress_buf[e] + 1;
   const float ref_t = __fadd_rn(bf.ref_motion_times[e], __fmul_rn((float)cfg.control_freq_inv, cfg.sim_dt));
   const float step_dt = __fmul_rn((float)cfg.control_freq_inv, cfg.sim_dt);
   const int64_t mid = bf.motion_ids[e];
   if (lane == 0) { bf.progress_buf[e] = progress; bf.ref_motion_times[e] = ref_t; }
+  if (ABL != 4) {
   const MotionSample ms = sample_motion(ml, M, mid, __fadd_rn(ref_t, step_dt), lane, cfg.ground_tolerance);
   store_targets(bf, cfg, ml, M, ms, e, lane, lc.dof0);
+  }
 
   // observation
   const int nbl = ml.num_lib_bodies;
   const bool is_body = lane < nbl;
+  if (ABL != 5)
   store_obs_raw(bf.obs_buf + e * bf.num_obs, nbl, nd, cfg.shape_dim, lane, is_body, lc.dof0, L.p, L.Q, L.v, L.w, dq, L.wt,
                 bf.motion_bodies + e * cfg.shape_dim);
 
   // reward against the PREVIOUS targets (compute_humanoid_reward :918-953)
   float s_dof = 0.f, s_vel = 0.f, s_pos = 0.f, s_rot = 0.f;
-  if (is_body) {
+  if (is_body && ABL != 3) {
     if (lc.dof0 >= 0) {
       float tq[3], tv[3];
 #pragma unroll
@@ -1280,7 +1316,9 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
 
 // ------------------------------------------------------------------------------------------
 // packed variant of the fused step: 4 envs per warp in the physics (packed.cuh), lane-per-body prologue / epilogue per env
+#ifndef PK_WARPS
 #define PK_WARPS 7          // 7 warps x 4 envs x 7.2 KB records + 20 KB constants = 227 KB of shared memory: one CTA per SM
+#endif
 #define PK_SCRATCH 232
 template <typename T> __device__ __forceinline__ void pk_store_state(T* env, const LaneConst& lc, int lane, const Lane<T>& L, const T* pd,
                                                                      const T* extF, const T* extT) {
@@ -1332,17 +1370,27 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
   const LaneConst lc = lane_const(M, lane);
   const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
   const int g = lane >> 3, s = lane & 7;
-  constexpr int BATCH = PK_WARPS * EPW;
+  // The CTA's warps form PK_GROUPS independent groups, each pulling its own batches and meeting at its own named barrier:
+  // while one group is in the (memory-latency-bound) prologue / epilogue the other is in the (issue-bound) physics.
+#ifndef PK_GROUPS
+#define PK_GROUPS 1   // 2 measured 1.5 % slower (343 vs 338 us): mixing the phases costs more I-cache than it hides latency
+#endif
+  constexpr int G0 = PK_GROUPS == 1 ? PK_WARPS : (PK_WARPS + 1) / 2;       // warps in group 0
+  const int grp = warp < G0 ? 0 : 1;
+  const int gw0 = grp == 0 ? 0 : G0, gwn = grp == 0 ? G0 : PK_WARPS - G0;     // first warp / number of warps of my group
+  const int BATCH = gwn * EPW;
+  const int gthreads = gwn * 32;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(gthreads) : "memory"); };
 
-  __shared__ unsigned long long s_tk;
+  __shared__ unsigned long long s_tk[2];
   for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)BATCH);
-    __syncthreads();
-    const int64_t e0 = (int64_t)s_tk;
+    group_sync();
+    if ((int)threadIdx.x == gw0 * 32) s_tk[grp] = atomicAdd(ticket, (unsigned long long)BATCH);
+    group_sync();
+    const int64_t e0 = (int64_t)s_tk[grp];
     if (e0 >= num_envs) break;
     const bool full_batch = e0 + BATCH <= num_envs;
-    const int64_t eb = e0 + (int64_t)warp * EPW;
+    const int64_t eb = e0 + (int64_t)(warp - gw0) * EPW;
     if (!full_batch && eb >= num_envs) continue;
 
     for (int k = 0; k < EPW; k++) {
@@ -1360,9 +1408,9 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     ball_clear(ball);
     const int64_t erow_g = env_first + (int64_t)env_stride * (eb + g);
     if (cfg.has_ball && valid && s == BALL_SLOT) ball_load(bf, erow_g, ball);
-    control_step_packed<float>(B, verts, pc, wrec, lane, valid, ball, STEP_SYNC && full_batch);
+    if (ABL != 1) control_step_packed<float>(B, verts, pc, wrec, lane, valid, ball, STEP_SYNC && full_batch);
 #if POST_SYNC
-    if (full_batch) __syncthreads();
+    if (full_batch) group_sync();
 #endif
     if (cfg.has_ball && valid && s == BALL_SLOT) ball_writeback(bf, erow_g, ball);
     for (int k = 0; k < EPW; k++) {
@@ -1764,6 +1812,9 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
     return fail(-2, "b200env_create: model dimensions out of range%s");
   if (model->max_depth >= MAX_LEVELS) return fail(-2, "b200env_create: kinematic tree too deep%s");
   if (model->vmax % 4) return fail(-2, "b200env_create: vmax must be a multiple of 4%s");
+  for (int b = 0; b < model->nb; b++)
+    if (model->nverts[b] < 0 || model->nverts[b] > 64 || model->nverts[b] > model->vmax)
+      return fail(-2, "b200env_create: at most 64 hull vertices per body (contact_hull keeps a 64-bit penetration mask)%s");
   if (num_envs < 1) return fail(-2, "b200env_create: num_envs must be positive%s");
   if (cfg->has_ball && model->nb > BALL_LANE) return fail(-2, "b200env_create: has_ball needs nb <= 31 (lane 31 integrates the ball)%s");
   if (cfg->has_ball && cfg->racket_body >= model->nb) return fail(-2, "b200env_create: racket_body out of range%s");
@@ -1816,7 +1867,13 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   CUDA_OK(cudaMalloc(&h->d_blob, h->blob_bytes));
   CUDA_OK(cudaMemset(h->d_blob, 0, h->blob_bytes));
   CUDA_OK(cudaMemcpy(h->d_blob, &hb, sizeof(hb), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy((char*)h->d_blob + sizeof(DevBlob), verts, vbytes, cudaMemcpyHostToDevice));
+  {  // AoS [nb][vmax][3] (ABI) -> SoA [nb][3][vmax] (what contact_hull reads with 128-bit loads)
+    std::vector<float> soa((size_t)model->nb * model->vmax * 3, 0.0f);
+    for (int b = 0; b < model->nb; b++)
+      for (int k = 0; k < model->nverts[b]; k++)
+        for (int a = 0; a < 3; a++) soa[((size_t)b * 3 + a) * model->vmax + k] = verts[((size_t)b * model->vmax + k) * 3 + a];
+    CUDA_OK(cudaMemcpy((char*)h->d_blob + sizeof(DevBlob), soa.data(), vbytes, cudaMemcpyHostToDevice));
+  }
   CUDA_OK(cudaMalloc(&h->d_cfg, sizeof(b200_cfg_t)));
   CUDA_OK(cudaMemcpy(h->d_cfg, cfg, sizeof(b200_cfg_t), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMalloc(&h->d_ticket, sizeof(unsigned long long)));

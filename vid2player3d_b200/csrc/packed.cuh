@@ -122,46 +122,9 @@ __device__ __forceinline__ void pk_body(const DevBlob& B, const float* __restric
 #pragma unroll
     for (int k = 0; k < 3; k++) { bn[k] -= ext[3 + k] + cxF[k]; bf[k] -= eF[k]; }
   }
-  const int nv = M.nverts[b];
-  if (nv > 0 && p[2] - T(M.radius[b]) < T(0)) {
-    const float* vb = verts + (size_t)b * M.vmax * 3;
-    const T kimp = c.h * c.cn + c.h * c.h * c.kn;
-    for (int k = 0; k < nv; k++) {
-      T vl[3] = {T(vb[3 * k]), T(vb[3 * k + 1]), T(vb[3 * k + 2])};
-      T rz = R[6] * vl[0] + R[7] * vl[1] + R[8] * vl[2];
-      T pen = -(p[2] + rz);
-      if (!(pen > T(0))) continue;
-      T rx = R[0] * vl[0] + R[1] * vl[1] + R[2] * vl[2];
-      T ry = R[3] * vl[0] + R[4] * vl[1] + R[5] * vl[2];
-      T ux = v[0] + w[1] * rz - w[2] * ry;
-      T uy = v[1] + w[2] * rx - w[0] * rz;
-      T uz = v[2] + w[0] * ry - w[1] * rx;
-      T fn0 = c.kn * pen - c.cn * uz;
-      if (!(fn0 > T(0))) continue;
-      T ut = sqrt_(ux * ux + uy * uy);
-      T ct = c.mu * fn0 * rcp_(ut > c.vs ? ut : c.vs);
-      T hct = c.h * ct;
-      A[0] += kimp * ry * ry + hct * rz * rz;
-      A[1] += kimp * rx * rx + hct * rz * rz;
-      A[2] += hct * (ry * ry + rx * rx);
-      A[3] += -kimp * ry * rx;
-      A[4] += -hct * rz * rx;
-      A[5] += -hct * rz * ry;
-      Bm[2] += kimp * ry;
-      Bm[5] += -kimp * rx;
-      Bm[3] += hct * rz;
-      Bm[6] += -hct * ry;
-      Bm[1] += -hct * rz;
-      Bm[7] += hct * rx;
-      C[0] += hct; C[1] += hct; C[2] += kimp;
-      T fx = -ct * ux, fy = -ct * uy;
-      bn[0] -= ry * fn0 - rz * fy;
-      bn[1] -= -rx * fn0 + rz * fx;
-      bn[2] -= -ry * fx + rx * fy;
-      bf[0] -= fx; bf[1] -= fy; bf[2] -= fn0;
-      cf[0] += fx; cf[1] += fy; cf[2] += fn0;
-    }
-  }
+  const int nv = ABL == 6 ? 0 : M.nverts[b];
+  if (nv > 0 && p[2] - T(M.radius[b]) < T(0))
+    contact_hull<T>(verts + (size_t)b * M.vmax * 3, M.vmax, nv, c, R, p, v, w, A, Bm, C, bn, bf, cf);
   st(rec + R_A, A, 6); st(rec + R_BM, Bm, 9); st(rec + R_C, C, 6); st(rec + R_BN, bn, 3); st(rec + R_BF, bf, 3); st(rec + R_CF, cf, 3);
   if (b > 0) {
     const int d0 = M.dof_of_body[b];
@@ -364,6 +327,12 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
   const int g = lane >> 3, s = lane & 7;
   T* env = wrec + g * ENV_STRIDE;
   const int nb = M.nb;
+  // kinematics of the start state, root -> leaves; every later FK is fused into the forward pass of the substep before it
+  for (int d = 1; d <= M.max_depth; d++) {
+    const int b = valid ? B.t.lvl_all[d][s] : -1;
+    if (b >= 0) pk_fk<T, true>(M, env, b);
+    __syncwarp();
+  }
   for (int sim = 0; sim < c.cfi; sim++) {
     if (c.has_ball && valid && s == BALL_SLOT) {
       ball_aero<T>(ball.v, ball.w, c.spin_scale, ball.fa);
@@ -375,20 +344,14 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
     }
     for (int sub = 0; sub < c.substeps; sub++) {
       if (cta_sync) __syncthreads();
-      // 1. kinematics, root -> leaves
-      for (int d = 1; d <= M.max_depth; d++) {
-        const int b = valid ? B.t.lvl_all[d][s] : -1;
-        if (b >= 0) pk_fk<T, true>(M, env, b);
-        __syncwarp();
-      }
-      // 2. per-body inertia / bias / contacts / joint drive
-      for (int rr = 0; rr * SLOTS < nb; rr++) {
+      // 1. per-body inertia / bias / contacts / joint drive
+      for (int rr = 0; rr * SLOTS < (ABL == 8 ? 0 : nb); rr++) {
         const int b = rr * SLOTS + s;
         if (valid && b < nb && !M.fixed[b]) pk_body<T>(B, verts, c, env, b, sim == 0);
       }
       __syncwarp();
-      // 3. articulated inertia, leaves -> root
-      for (int d = M.max_depth; d >= 1; d--) {
+      // 2. articulated inertia, leaves -> root
+      for (int d = (ABL == 9 ? 0 : M.max_depth); d >= 1; d--) {
         const int b = valid ? B.t.lvl_dyn[d][s] : -1;
         T out[27];
         if (b >= 0) pk_backward<T>(env, b, out);
@@ -402,16 +365,8 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
           __syncwarp();
         }
       }
-      // 4. root acceleration
-      if (valid && s == 0) pk_root<T>(c, env);
-      __syncwarp();
-      // 5. accelerations root -> leaves, integrate the joints
-      for (int d = 1; d <= M.max_depth; d++) {
-        const int b = valid ? B.t.lvl_dyn[d][s] : -1;
-        if (b >= 0) pk_forward<T>(M, c, env, b);
-        __syncwarp();
-      }
-      // 6. ball (uses the racket's start-of-substep pose/velocity, still in its record), then the root
+      // 3. root acceleration (lane slot 0) next to the ball (slot 7: uses the racket's start-of-substep pose / velocity, which the
+      //    fused pass below is about to overwrite), then the root is integrated
       if (c.has_ball && valid && s == BALL_SLOT) {
         T rQ[4] = {0, 0, 0, 1}, rp[3] = {0, 0, 0}, rv[3] = {0, 0, 0}, rw[3] = {0, 0, 0};
         const bool has_racket = c.racket_body >= 0;
@@ -424,13 +379,18 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
 #pragma unroll
         for (int k = 0; k < 3; k++) { ext[6 + k] = ball.rF[k]; ext[9 + k] = ball.rX[k]; }
       }
-      if (valid && s == 0) pk_root_integrate<T>(c, env);
+      if (valid && s == 0) { pk_root<T>(c, env); pk_root_integrate<T>(c, env); }
       __syncwarp();
+      // 4. root -> leaves: accelerations + joint integration of a body, then at once its kinematics for the next substep
+      //    (its parent's new pose is already in place); welded bodies only have the kinematics
+      for (int d = 1; d <= (ABL == 10 ? 0 : M.max_depth); d++) {
+        const int b = valid ? B.t.lvl_all[d][s] : -1;
+        if (b >= 0) {
+          if (!M.fixed[b]) pk_forward<T>(M, c, env, b);
+          pk_fk<T, true>(M, env, b);
+        }
+        __syncwarp();
+      }
     }
-  }
-  for (int d = 1; d <= M.max_depth; d++) {
-    const int b = valid ? B.t.lvl_all[d][s] : -1;
-    if (b >= 0) pk_fk<T, false>(M, env, b);
-    __syncwarp();
   }
 }
