@@ -193,6 +193,13 @@ int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_st
                          void* dof_vel, const void* pd_tar, const void* ext_wrench, void* rb_out, void* contact_out,
                          void* ball, int32_t* ball_hits, void* stream);
 
+/* replaces HumanoidSMPLIM._init_context (embodied_pose/env/tasks/humanoid_smpl_im.py:530-563): for listed env i and frame
+ * j in [0, num_frames): t = motion_times[i] + dt + (first_frame + j) * dt; writes
+ * context_feat[row, j, :] = rb_pos | rb_rot | dof_pos | rb_pos | dof_pos  ([N, num_frames, 2*(3B+D)+4B] row-major) and
+ * context_mask[row, j] = t <= motion_length + 2 dt, with row = env_ids[i] (or i when env_ids is NULL). */
+int b200env_motion_context(b200env_handle h, const int64_t* env_ids, const int64_t* motion_ids, const float* motion_times, int32_t n,
+                           int32_t num_frames, int32_t first_frame, float dt, float* context_feat, uint8_t* context_mask, void* stream);
+
 /* Heterogeneous assets per env (dual mode: env 2k = player 0's asset, env 2k+1 = player 1's,
  * vid2player/env/tasks/humanoid_smpl_im_mvae.py:270-275 `motion_ids[1::2] = 1`): one handle per asset, all bound to the SAME
  * tensors; handle-local env i of b200env_step is row env_first + env_stride * i.  num_envs at create = envs of the slice. */

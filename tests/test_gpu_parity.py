@@ -418,3 +418,18 @@ def test_ball_physics_f32_vs_oracle():
     np.testing.assert_allclose(bb.cpu().numpy()[same, 0:3], bo[same, 0:3], rtol=0, atol=1e-4)
     np.testing.assert_allclose(bb.cpu().numpy()[same, 7:10], bo[same, 7:10], rtol=0, atol=2e-3)
     np.testing.assert_allclose(qq.cpu().numpy()[same], qo[same], rtol=0, atol=1e-4)
+
+
+def test_motion_context_matches_torch_composition(model, small_lib):
+    """b200env_motion_context (one launch, writes context_feat / context_mask in place) vs the reference-shaped composition
+    (b200env_motion_state over the 48-frame window + torch.cat + indexed assignment, humanoid_smpl_im.py:530-563): bit-identical"""
+    task = make_task(64, small_lib)
+    task.reset()
+    for env_ids in (torch.arange(64, device=task.device), torch.tensor([3, 17, 18, 40, 63], device=task.device)):
+        mids = task._reset_ref_motion_ids[env_ids]
+        times = task.sample_time(mids).contiguous()
+        task._init_context(env_ids, mids, times)
+        feat, mask = task._init_context_torch(env_ids, mids, times)
+        assert torch.equal(task.context_feat[env_ids], feat) and torch.equal(task.context_mask[env_ids], mask)
+        assert feat.shape[1:] == (48, 378) and mask.any() and torch.isfinite(feat).all()
+    assert not task.context_mask.all()        # windows reaching past the end of short motions are masked out

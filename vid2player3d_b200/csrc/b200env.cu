@@ -1613,6 +1613,40 @@ motion_state_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __restr
   if (dof_vel) for (int k = lane; k < nd; k += 32) dof_vel[i * nd + k] = ml.dvs[s.f0 * nd + k];
 }
 
+// _init_context (humanoid_smpl_im.py:530-563): the P-frame MoCap window of each listed env written straight into
+// context_feat[row, j, :] = rb_pos | rb_rot | dof_pos | rb_pos | dof_pos and context_mask[row, j]; warp per (env, frame).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+motion_context_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __restrict__ gcfg, b200_motion_lib_t ml,
+                      const int64_t* __restrict__ env_ids, const int64_t* __restrict__ ids, const float* __restrict__ times, int n, int P,
+                      int first, float dt, float two_dt, float* __restrict__ feat, uint8_t* __restrict__ mask) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+  if (w >= (int64_t)n * P) return;
+  const int64_t i = w / P;
+  const int j = (int)(w - i * P);
+  const b200_model_t& M = gblob->m;
+  const int nd = M.nd, nbl = ml.num_lib_bodies;
+  const int dof0 = lane < M.nb ? M.dof_of_body[lane] : -1;
+  const int64_t mid = ids[i];
+  // torch: (motion_times + dt).unsqueeze(-1) + dt * arange(first, first + P), all float32, op by op
+  const float t = __fadd_rn(__fadd_rn(times[i], dt), __fmul_rn((float)(first + j), dt));
+  const MotionSample s = sample_motion(ml, M, mid, t, lane, gcfg->ground_tolerance);
+  const int64_t row = env_ids ? env_ids[i] : i;
+  const int W = nbl * 3 + nbl * 4 + nd + nbl * 3 + nd;
+  float* o = feat + (row * P + j) * W;
+  if (lane < nbl) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { o[lane * 3 + k] = s.rb_pos[k]; o[nbl * 7 + nd + lane * 3 + k] = s.rb_pos[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[nbl * 3 + lane * 4 + k] = s.rb_rot[k];
+    if (dof0 >= 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) { o[nbl * 7 + dof0 + k] = s.dof[k]; o[nbl * 10 + nd + dof0 + k] = s.dof[k]; }
+    }
+  }
+  if (lane == 0) mask[row * P + j] = t <= __fadd_rn(ml.motion_lengths[mid], two_dt) ? 1 : 0;
+}
+
 // compute_humanoid_observations_imitation (humanoid_smpl_im.py:773-850): warp per env, lane per body
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restrict__ body_pos, const float* __restrict__ body_rot,
@@ -1998,6 +2032,24 @@ int b200env_motion_state(b200env_handle h, const int64_t* motion_ids, const floa
   motion_state_kernel<<<grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->ml, motion_ids,
                                                                              motion_times, n, root_pos, root_rot, dof_pos, root_vel,
                                                                              root_ang_vel, dof_vel, key_pos, rb_pos, rb_rot);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int b200env_motion_context(b200env_handle h, const int64_t* env_ids, const int64_t* motion_ids, const float* motion_times, int32_t n,
+                           int32_t num_frames, int32_t first_frame, float dt, float* context_feat, uint8_t* context_mask, void* stream) {
+  if (!h) return fail(-1, "b200env_motion_context: null handle%s");
+  if (n == 0) return 0;
+  if (!motion_ids || !motion_times || !context_feat || !context_mask || n < 0 || num_frames < 1)
+    return fail(-1, "b200env_motion_context: bad arguments%s");
+  if (!h->has_ml) return fail(-4, "b200env_motion_context: set a motion lib first%s");
+  cudaSetDevice(h->device);
+  const int64_t warps = (int64_t)n * num_frames;
+  const int grid = (int)((warps + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+  motion_context_kernel<<<grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->ml, env_ids, motion_ids,
+                                                                               motion_times, n, num_frames, first_frame, dt,
+                                                                               (float)(2.0 * (double)dt), context_feat, context_mask);
   CUDA_OK(cudaGetLastError());
   h->launches++;
   return 0;

@@ -13,7 +13,7 @@ _lib = None
 
 SYMBOLS = ["b200env_abi_version", "b200env_last_error", "b200env_create", "b200env_destroy", "b200env_bind",
            "b200env_set_motion_lib", "b200env_step", "b200env_reset", "b200env_motion_state", "b200env_obs_imitation",
-           "b200env_physics_only", "b200env_launch_count", "b200env_set_env_slice"]
+           "b200env_physics_only", "b200env_launch_count", "b200env_set_env_slice", "b200env_motion_context"]
 
 
 def lib():
@@ -116,6 +116,13 @@ class Env:
         names = ("root_pos", "root_rot", "dof_pos", "root_vel", "root_ang_vel", "dof_vel", "key_pos", "rb_pos", "rb_rot")
         _check(lib().b200env_motion_state(self._h, _ptr(ids), _ptr(times), C.c_int32(int(ids.shape[0])),
                                           *[_ptr(out.get(k)) for k in names], _stream()))
+
+    def motion_context(self, env_ids, motion_ids, motion_times, num_frames, first_frame, dt, feat, mask):
+        """feat [N, num_frames, W] float32, mask [N, num_frames] bool; rows env_ids (None: rows 0..n-1)"""
+        assert feat.is_cuda and feat.is_contiguous() and mask.is_contiguous() and motion_ids.is_contiguous() and motion_times.is_contiguous()
+        _check(lib().b200env_motion_context(self._h, _ptr(env_ids), _ptr(motion_ids), _ptr(motion_times), C.c_int32(int(motion_ids.shape[0])),
+                                            C.c_int32(int(num_frames)), C.c_int32(int(first_frame)), C.c_float(float(dt)), _ptr(feat),
+                                            _ptr(mask), _stream()))
 
     def obs_imitation(self, body_pos, body_rot, target_pos, target_rot, dof_pos, dof_vel, target_dof_pos, body_vel,
                       body_ang_vel, motion_bodies, local_root_obs, root_height_obs, obs, jpos=False):

@@ -306,6 +306,25 @@ class HumanoidSMPLIM(BaseTask):
         """:530-563: 48-frame MoCap window per env -> context_feat / context_mask (one launch)."""
         n = len(env_ids)
         P = self.context_length + self.context_padding * 2
+        nbl, D = self._num_lib_bodies, self.num_dof
+        if not hasattr(self, "context_feat"):
+            self.context_feat = torch.zeros(self.num_envs, P, 2 * (3 * nbl + D) + 4 * nbl, device=self.device)
+            self.context_mask = torch.zeros(self.num_envs, P, device=self.device, dtype=torch.bool)
+        self._env.motion_context(env_ids.to(self.device, dtype=torch.long).contiguous(), motion_ids.contiguous(), motion_times.contiguous(),
+                                 P, -self.context_padding, self.dt, self.context_feat, self.context_mask)
+        if self.model is not None:
+            if not self.is_env_dim_setup:
+                self.model.a2c_network.setup_env_named_dims(self.obs_names, self.obs_shapes, self.obs_dims,
+                                                            self.context_names, self.context_shapes, self.context_dims)
+                self.is_env_dim_setup = True
+            with torch.no_grad():
+                self.model.a2c_network.forward_context(self.context_feat, self.context_mask)
+
+    def _init_context_torch(self, env_ids, motion_ids, motion_times):
+        """the same window composed with torch ops from b200env_motion_state outputs (written like the reference, :530-563);
+        kept as the executable specification b200env_motion_context is tested against"""
+        n = len(env_ids)
+        P = self.context_length + self.context_padding * 2
         steps = self.dt * torch.arange(-self.context_padding, self.context_length + self.context_padding, device=self.device)
         all_times = ((motion_times + self.dt).unsqueeze(-1) + steps).contiguous()
         all_ids = motion_ids.unsqueeze(-1).expand(n, P).contiguous()
@@ -314,23 +333,8 @@ class HumanoidSMPLIM(BaseTask):
         rb_pos, rb_rot, dof_pos = f(n * P, nbl, 3), f(n * P, nbl, 4), f(n * P, D)
         self._env.motion_state(all_ids.view(-1), all_times.view(-1), dict(rb_pos=rb_pos, rb_rot=rb_rot, dof_pos=dof_pos))
         feat = torch.cat([rb_pos.view(n * P, -1), rb_rot.view(n * P, -1), dof_pos, rb_pos.view(n * P, -1), dof_pos], dim=-1)
-        feat = feat.view(n, P, -1)
         mask = all_times <= (self._ml_t["motion_lengths"][motion_ids] + 2 * self.dt).unsqueeze(-1)
-        if n == self.num_envs:
-            self.context_feat, self.context_mask = feat, mask
-        else:
-            if not hasattr(self, "context_feat"):
-                self.context_feat = torch.zeros(self.num_envs, P, feat.shape[-1], device=self.device)
-                self.context_mask = torch.zeros(self.num_envs, P, device=self.device, dtype=torch.bool)
-            self.context_feat[env_ids] = feat
-            self.context_mask[env_ids] = mask
-        if self.model is not None:
-            if not self.is_env_dim_setup:
-                self.model.a2c_network.setup_env_named_dims(self.obs_names, self.obs_shapes, self.obs_dims,
-                                                            self.context_names, self.context_shapes, self.context_dims)
-                self.is_env_dim_setup = True
-            with torch.no_grad():
-                self.model.a2c_network.forward_context(self.context_feat, self.context_mask)
+        return feat.view(n, P, -1), mask
 
     def compute_imitation_obs(self, body_pos, body_rot, target_pos, target_rot, dof_pos, dof_vel, target_dof_pos,
                               body_vel, body_ang_vel, motion_bodies, local_root_obs=True, root_height_obs=True,
