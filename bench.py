@@ -390,7 +390,9 @@ def main():
                 "api": "VecTaskPythonWrapper.step/reset, pinned host actions in, reward+reset out, host sync every step"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "kernel": "step_kernel" if os.environ.get("B200ENV_KERNEL") == "lane" else "step_kernel_packed", "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "kernel": ("step_kernel" if os.environ.get("B200ENV_KERNEL") == "lane" else
+                                "step_kernel_packed<fused>" if os.environ.get("B200ENV_SPLIT") == "0" else
+                                "one env step = pre_kernel + step_kernel_packed<split> (dominant, ~90 %) + post_kernel"), "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
                      "peak_source": peak_src,
                      "note": "latency / FP32-issue bound along the 9-level kinematic chain, not HBM bound (DESIGN.md 5)"},
     }

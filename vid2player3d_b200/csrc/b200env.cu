@@ -75,6 +75,9 @@ struct b200env {
   b200_cfg_t* d_cfg;
   unsigned long long* d_ticket;
   unsigned long long ticket_base;
+  float* d_ext;                        // [num_envs rows of the bound tensors, 6] residual root wrench between pre_kernel and the physics launch
+  int ext_rows;
+  int split;                           // 1: three launches (pre / physics / post), 0: one fused launch.  env B200ENV_SPLIT=0|1
   int env_first = 0, env_stride = 1;   // b200env_set_env_slice: local env i = row env_first + env_stride * i of the bound tensors
   int step_grid;
   int packed;        // 1: 4-envs-per-warp kernels (packed.cuh); 0: lane-per-body kernels.  env B200ENV_KERNEL=lane|packed
@@ -1157,16 +1160,13 @@ __device__ __forceinline__ void ball_load(const b200_buffers_t& bf, int64_t e, B
   ball.has_bounce = bf.has_bounce[e];
 }
 
-// ---- per-env epilogue (lane = body): write back the state, ball flags, MoCap target, obs, reward, reset
-__device__ __forceinline__ void step_epilogue(const b200_buffers_t& bf, const b200_motion_lib_t& ml, const b200_cfg_t& cfg,
-                                              const b200_model_t& M, const LaneConst& lc, int lane, int64_t e, const Lane<float>& L,
-                                              const float* cf, const Ball<float>& ball, bool ball_in_lane31 = true) {
+// ---- per-env epilogue, part 1 (lane = body): write back the simulation state (what gym.refresh_* exposes); dq = log(qj)
+__device__ __forceinline__ void epilogue_writeback(const b200_buffers_t& bf, const b200_cfg_t& cfg, const b200_model_t& M,
+                                                   const LaneConst& lc, int lane, int64_t e, const Lane<float>& L, const float* cf,
+                                                   float* dq) {
   const int nd = M.nd;
-  const bool was_reset = bf.reset_buf[e] == 1;  // still the pre-step value: reset_buf is only written at the end of this function
-  if (cfg.has_ball && lane == BALL_LANE && ball_in_lane31) ball_writeback(bf, e, ball);
-
+  dq[0] = dq[1] = dq[2] = 0.f;
   // ---- write back the simulation state (what gym.refresh_* exposes)
-  float dq[3] = {0.f, 0.f, 0.f};
   if (lane == 0) {
     float* wrs = bf.root_states + e * bf.actors_per_env * 13;
 #pragma unroll
@@ -1190,11 +1190,16 @@ __device__ __forceinline__ void step_epilogue(const b200_buffers_t& bf, const b2
     cfo[0] = cf[0]; cfo[1] = cf[1]; cfo[2] = cf[2];
   }
 
-  if (cfg.task_mode == 1) {  // vid2player player env: post_physics_step (:785-797) only advances progress; obs / targets
-    if (lane == 0) bf.progress_buf[e] += 1;  // are produced by post_mvae_step, rewards / resets by the controller
-    return;
-  }
-  if (ABL == 2) return;
+  if (cfg.task_mode == 1 && lane == 0) bf.progress_buf[e] += 1;  // vid2player player env: post_physics_step (:785-797) only advances
+}                                                                 // progress; obs / targets come from post_mvae_step, rewards / resets from the controller
+
+// ---- per-env epilogue, part 2 (lane = body; embodied_pose task): MoCap target, obs, reward, reset.  Needs p, Q, v, w, wt of the
+// lane's body and dq - either still in registers (fused kernel) or read back from the state rows (post_kernel).
+__device__ __forceinline__ void epilogue_post(const b200_buffers_t& bf, const b200_motion_lib_t& ml, const b200_cfg_t& cfg,
+                                              const b200_model_t& M, const LaneConst& lc, int lane, int64_t e, const Lane<float>& L,
+                                              const float* dq) {
+  const int nd = M.nd;
+  const bool was_reset = bf.reset_buf[e] == 1;  // still the pre-step value: reset_buf is only written at the end of this function
   // ---- post-physics (:398-418)
   const int64_t progress = bf.progress_buf[e] + 1;
   const float ref_t = __fadd_rn(bf.ref_motion_times[e], __fmul_rn((float)cfg.control_freq_inv, cfg.sim_dt));
@@ -1267,6 +1272,17 @@ __device__ __forceinline__ void step_epilogue(const b200_buffers_t& bf, const b2
   }
 }
 
+// ---- per-env epilogue of the fused kernels
+__device__ __forceinline__ void step_epilogue(const b200_buffers_t& bf, const b200_motion_lib_t& ml, const b200_cfg_t& cfg,
+                                              const b200_model_t& M, const LaneConst& lc, int lane, int64_t e, const Lane<float>& L,
+                                              const float* cf, const Ball<float>& ball, bool ball_in_lane31 = true) {
+  if (cfg.has_ball && lane == BALL_LANE && ball_in_lane31) ball_writeback(bf, e, ball);
+  float dq[3];
+  epilogue_writeback(bf, cfg, M, lc, lane, e, L, cf, dq);
+  if (cfg.task_mode == 1 || ABL == 2) return;
+  epilogue_post(bf, ml, cfg, M, lc, lane, e, L, dq);
+}
+
 // ------------------------------------------------------------------------------------------
 // fused env step:  pre-physics -> substeps -> MoCap target -> obs -> reward -> reset
 // Persistent: the grid is sized to the resident CTA slots; each warp pulls env indices from a global ticket
@@ -1315,6 +1331,89 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
 
 
 // ------------------------------------------------------------------------------------------
+// three-launch form of the env step (b200env_step with h->split): pre_kernel -> step_kernel_packed<true> -> post_kernel.
+// state of env row e as the physics wants it, from the rows the pre_kernel left behind (lane = body)
+__device__ __forceinline__ void load_state_rows(const b200_buffers_t& bf, const b200_model_t& M, const LaneConst& lc, int lane, int64_t e,
+                                                const float* __restrict__ ext_wrench, Lane<float>& L, float* pdtar, float* extF, float* extT) {
+  const int nd = M.nd;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { L.Q[k] = 0.f; L.qj[k] = 0.f; }
+  L.Q[3] = 1.f; L.qj[3] = 1.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { L.p[k] = 0.f; L.w[k] = 0.f; L.v[k] = 0.f; L.wt[k] = 0.f; pdtar[k] = 0.f; extF[k] = 0.f; extT[k] = 0.f; }
+  if (lane == 0) {
+    const float* rs = bf.root_states + e * bf.actors_per_env * 13;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { L.p[k] = rs[k]; L.v[k] = rs[7 + k]; L.w[k] = rs[10 + k]; extF[k] = ext_wrench[e * 6 + k]; extT[k] = ext_wrench[e * 6 + 3 + k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) L.Q[k] = rs[3 + k];
+    qnormalize(L.Q);
+  }
+  if (lc.dyn && lane > 0) {
+    const float* ds = bf.dof_state + (e * nd + lc.dof0) * 2;
+    float q[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { q[k] = ds[2 * k]; L.wt[k] = ds[2 * k + 1]; pdtar[k] = bf.pd_targets[e * nd + lc.dof0 + k]; }
+    qexp(q, L.qj);
+  }
+}
+
+// launch 1: pre_physics_step of every env (zeroed actions of reset envs, PD targets, residual root wrench, previous <- current
+// targets).  Warp per env, lane per body, 8 warps per CTA, no big shared-memory footprint -> full occupancy.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+pre_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf, b200_motion_lib_t ml,
+           const float* __restrict__ actions, int num_envs, int env_first, int env_stride, float* __restrict__ ext_wrench) {
+  __shared__ float s_scr[WARPS_PER_CTA * SCRATCH_FLOATS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+  if (i >= num_envs) return;
+  const int64_t e = env_first + (int64_t)env_stride * i;
+  const b200_model_t& M = gblob->m;
+  const LaneConst lc = lane_const(M, lane);
+  Lane<float> L;
+  float pdtar[3], extF[3], extT[3];
+  Ball<float> dummy;
+  step_prologue(bf, ml, *gcfg, M, lc, lane, s_scr + warp * SCRATCH_FLOATS, actions, e, L, pdtar, extF, extT, dummy);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { ext_wrench[e * 6 + k] = extF[k]; ext_wrench[e * 6 + 3 + k] = extT[k]; }
+  }
+}
+
+// launch 3: post_physics_step of every env (MoCap target, obs, reward, reset) from the state rows launch 2 wrote
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+post_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf, b200_motion_lib_t ml, int num_envs,
+            int env_first, int env_stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+  if (i >= num_envs) return;
+  const int64_t e = env_first + (int64_t)env_stride * i;
+  const b200_model_t& M = gblob->m;
+  const LaneConst lc = lane_const(M, lane);
+  const int nd = M.nd;
+  Lane<float> L;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { L.Q[k] = 0.f; L.qj[k] = 0.f; }
+  L.Q[3] = 1.f; L.qj[3] = 1.f;
+  float dq[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 3; k++) { L.p[k] = 0.f; L.w[k] = 0.f; L.v[k] = 0.f; L.wt[k] = 0.f; }
+  if (lc.active) {
+    const float* rb = bf.rigid_body_state + (e * bf.bodies_per_env + lane) * 13;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { L.p[k] = rb[k]; L.v[k] = rb[7 + k]; L.w[k] = rb[10 + k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) L.Q[k] = rb[3 + k];
+  }
+  if (lc.dyn && lane > 0) {
+    const float* ds = bf.dof_state + (e * nd + lc.dof0) * 2;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { dq[k] = ds[2 * k]; L.wt[k] = ds[2 * k + 1]; }
+  }
+  epilogue_post(bf, ml, *gcfg, M, lc, lane, e, L, dq);
+}
+
+// ------------------------------------------------------------------------------------------
 // packed variant of the fused step: 4 envs per warp in the physics (packed.cuh), lane-per-body prologue / epilogue per env
 #ifndef PK_WARPS
 #define PK_WARPS 7          // 7 warps x 4 envs x 7.2 KB records + 20 KB constants = 227 KB of shared memory: one CTA per SM
@@ -1349,10 +1448,14 @@ template <typename T> __device__ __forceinline__ void pk_load_state(const T* env
   }
 }
 
+// SPLIT = false: the whole env step in this launch.  SPLIT = true: the middle launch of pre_kernel -> this -> post_kernel; here only
+// the state rows / PD targets / residual wrench are read and the state rows written (the once-per-step task logic runs in the two
+// high-occupancy kernels, where its memory latency is covered by 48+ warps per SM instead of the 7 this kernel can hold).
+template <bool SPLIT>
 __global__ void __launch_bounds__(PK_WARPS * 32, 1)
 step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
                    b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs, unsigned long long* __restrict__ ticket,
-                   int env_first, int env_stride) {
+                   int env_first, int env_stride, const float* __restrict__ ext_wrench) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t mbar;
   load_blob(smem, gblob, blob_bytes, &mbar);
@@ -1393,6 +1496,49 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     const int64_t eb = e0 + (int64_t)(warp - gw0) * EPW;
     if (!full_batch && eb >= num_envs) continue;
 
+    if (SPLIT) {
+      // all loads of the warp's EPW envs are issued before the first use (one memory latency instead of EPW)
+      float rq[EPW][3], rw[EPW][3], rp[EPW][3], r1[EPW];   // r1: lane j < 13 holds root_states[e][j], 13 <= j < 19 the residual wrench
+      const int nd = M.nd;
+#pragma unroll
+      for (int k = 0; k < EPW; k++) {
+        const int64_t ek = eb + k < num_envs ? eb + k : (int64_t)num_envs - 1;   // ragged tail: re-read the last env, never stored
+        const int64_t e = env_first + (int64_t)env_stride * ek;
+        if (lc.dyn && lane > 0) {
+          const float* ds = bf.dof_state + (e * nd + lc.dof0) * 2;
+#pragma unroll
+          for (int j = 0; j < 3; j++) { rq[k][j] = ds[2 * j]; rw[k][j] = ds[2 * j + 1]; rp[k][j] = bf.pd_targets[e * nd + lc.dof0 + j]; }
+        }
+        r1[k] = lane < 13 ? bf.root_states[e * bf.actors_per_env * 13 + lane] : (lane < 19 ? ext_wrench[e * 6 + lane - 13] : 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < EPW; k++) {
+        if (eb + k >= num_envs) break;
+        Lane<float> L;
+        float pdtar[3] = {0.f, 0.f, 0.f}, extF[3] = {0.f, 0.f, 0.f}, extT[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; j++) { L.Q[j] = 0.f; L.qj[j] = 0.f; }
+        L.Q[3] = 1.f; L.qj[3] = 1.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { L.p[j] = 0.f; L.w[j] = 0.f; L.v[j] = 0.f; L.wt[j] = 0.f; }
+        float rr[19];
+#pragma unroll
+        for (int j = 0; j < 19; j++) rr[j] = __shfl_sync(FULL, r1[k], j);
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 3; j++) { L.p[j] = rr[j]; L.v[j] = rr[7 + j]; L.w[j] = rr[10 + j]; extF[j] = rr[13 + j]; extT[j] = rr[16 + j]; }
+#pragma unroll
+          for (int j = 0; j < 4; j++) L.Q[j] = rr[3 + j];
+          qnormalize(L.Q);
+        }
+        if (lc.dyn && lane > 0) {
+#pragma unroll
+          for (int j = 0; j < 3; j++) { L.wt[j] = rw[k][j]; pdtar[j] = rp[k][j]; }
+          qexp(rq[k], L.qj);
+        }
+        pk_store_state<float>(wrec + k * ENV_STRIDE, lc, lane, L, pdtar, extF, extT);
+      }
+    } else {
     for (int k = 0; k < EPW; k++) {
       if (eb + k >= num_envs) break;
       const int64_t e = env_first + (int64_t)env_stride * (eb + k);  // row in the bound tensors (env slice)
@@ -1401,6 +1547,7 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
       Ball<float> dummy;
       step_prologue(bf, ml, cfg, M, lc, lane, scr, actions, e, L, pdtar, extF, extT, dummy);
       pk_store_state<float>(wrec + k * ENV_STRIDE, lc, lane, L, pdtar, extF, extT);
+    }
     }
     __syncwarp();
     const bool valid = eb + g < num_envs;
@@ -1419,7 +1566,12 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
       Lane<float> L;
       float cf[3];
       pk_load_state<float>(wrec + k * ENV_STRIDE, lc, lane, L, cf);
-      step_epilogue(bf, ml, cfg, M, lc, lane, e, L, cf, ball, false);
+      if (SPLIT) {
+        float dq[3];
+        epilogue_writeback(bf, cfg, M, lc, lane, e, L, cf, dq);
+      } else {
+        step_epilogue(bf, ml, cfg, M, lc, lane, e, L, cf, ball, false);
+      }
     }
     __syncwarp();
   }
@@ -1896,6 +2048,8 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   }
   const char* kv = getenv("B200ENV_KERNEL");
   h->packed = h->packed_ok && !(kv && strcmp(kv, "lane") == 0);
+  const char* sv = getenv("B200ENV_SPLIT");
+  h->split = h->packed && !(sv && strcmp(sv, "0") == 0);
   const size_t vbytes = (size_t)model->nb * model->vmax * 3 * sizeof(float);
   h->blob_bytes = sizeof(DevBlob) + ((vbytes + 15) & ~(size_t)15);
   CUDA_OK(cudaMalloc(&h->d_blob, h->blob_bytes));
@@ -1922,6 +2076,7 @@ int b200env_destroy(b200env_handle h) {
   cudaFree(h->d_blob);
   cudaFree(h->d_cfg);
   cudaFree(h->d_ticket);
+  cudaFree(h->d_ext);
   delete h;
   return 0;
 }
@@ -1970,9 +2125,10 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
     const int batch = PK_WARPS * EPW;
     const int need = (h->num_envs + batch - 1) / batch;
     if (h->step_grid == 0) {
-      CUDA_OK(cudaFuncSetAttribute(step_kernel_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
       int per_sm = 0, sms = 0;
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed, PK_WARPS * 32, psmem));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<false>, PK_WARPS * 32, psmem));
       CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
       h->step_grid = per_sm * sms < need ? per_sm * sms : need;
       if (h->step_grid < 1) return fail(-5, "b200env_step: step_kernel_packed does not fit on this device%s");
@@ -1980,9 +2136,30 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
     // the ticket counter is re-zeroed on the stream before every launch: nothing in the launch depends on host-side
     // history, so a step can be captured into a CUDA graph and replayed
     CUDA_OK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), (cudaStream_t)stream));
-    step_kernel_packed<<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes,
-                                                                                      h->d_cfg, h->bufs, h->ml, actions, h->num_envs,
-                                                                                      h->d_ticket, h->env_first, h->env_stride);
+    if (h->split) {
+      const int rows = h->env_first + h->env_stride * (h->num_envs - 1) + 1;
+      if (rows > h->ext_rows) {  // first step (or a wider env slice): never inside a graph capture - the bound task warms up first
+        cudaFree(h->d_ext);
+        h->d_ext = nullptr;
+        CUDA_OK(cudaMalloc(&h->d_ext, (size_t)rows * 6 * sizeof(float)));
+        h->ext_rows = rows;
+      }
+      const int io_grid = need_ctas(h);
+      pre_kernel<<<io_grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->bufs, h->ml, actions,
+                                                                           h->num_envs, h->env_first, h->env_stride, h->d_ext);
+      step_kernel_packed<true><<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>(
+          (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->ml, actions, h->num_envs, h->d_ticket, h->env_first,
+          h->env_stride, h->d_ext);
+      if (h->cfg.task_mode == 0)
+        post_kernel<<<io_grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->bufs, h->ml, h->num_envs,
+                                                                              h->env_first, h->env_stride);
+      CUDA_OK(cudaGetLastError());
+      h->launches += h->cfg.task_mode == 0 ? 3 : 2;
+      return 0;
+    }
+    step_kernel_packed<false><<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>(
+        (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->ml, actions, h->num_envs, h->d_ticket, h->env_first,
+        h->env_stride, nullptr);
     CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;
