@@ -16,9 +16,10 @@ def test_library_exports_every_declared_symbol():
     from vid2player3d_b200 import build, native
     lib = build.build()
     from vid2player3d_b200 import native_v2p
-    hdr = open(os.path.join(ROOT, "include", "b200env.h")).read() + open(os.path.join(ROOT, "include", "b200env_v2p.h")).read()
-    declared = sorted(set(re.findall(r"\b(b200(?:env|v2p)_[a-z_0-9]+)\s*\(", hdr)))
-    assert declared == sorted(native.SYMBOLS + native_v2p.SYMBOLS)
+    from vid2player3d_b200 import ball_gen
+    hdr = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("b200env.h", "b200env_v2p.h", "b200ball.h"))
+    declared = sorted(set(re.findall(r"\b(b200(?:env|v2p|ball)_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared == sorted(native.SYMBOLS + native_v2p.SYMBOLS + ball_gen.SYMBOLS)
     L = C.CDLL(lib)  # loads without a GPU; no compute call is made here
     for name in declared:
         assert hasattr(L, name), name

@@ -39,6 +39,9 @@
 #ifndef POST_SYNC
 #define POST_SYNC 1
 #endif
+#ifndef PK_WARP_TICKETS
+#define PK_WARP_TICKETS 0   // packed kernel: 1 = every warp pulls its own groups of EPW envs (no CTA barrier in the loop)
+#endif
 #ifndef STEP_MIN_CTAS
 #define STEP_MIN_CTAS 2
 #endif
@@ -53,6 +56,7 @@ struct DevTree {
   int32_t lvl_all[MAX_LEVELS][PK_SLOTS];      // all bodies of the depth (kinematics), -1 padded
   int32_t lvl_dyn[MAX_LEVELS][PK_SLOTS];      // non-welded bodies of the depth (dynamics), -1 padded
   int32_t child_rank[B200_MAX_BODIES];
+  int32_t rix[B200_MAX_BODIES];               // record index of a body in the packed kernel's shared-memory layout = breadth-first rank
 };
 struct DevBlob {
   b200_model_t m;
@@ -215,6 +219,7 @@ template <typename T> struct Lane {
 };
 struct LaneConst {
   int par, depth, dof0;
+  int rix;           // packed kernels: the body's record index (DevTree::rix); set by the kernel after lane_const()
   bool active, dyn;  // dyn: takes part in the dynamics (not welded)
 };
 
@@ -846,6 +851,7 @@ __device__ __forceinline__ LaneConst lane_const(const b200_model_t& M, int lane)
   lc.depth = lc.active ? M.depth[lane] : -1;
   lc.dof0 = lc.active ? M.dof_of_body[lane] : -1;
   lc.dyn = lc.active && !M.fixed[lane];
+  lc.rix = lane;
   return lc;
 }
 
@@ -1422,9 +1428,23 @@ post_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __restrict__ gc
 template <typename T> __device__ __forceinline__ void pk_store_state(T* env, const LaneConst& lc, int lane, const Lane<T>& L, const T* pd,
                                                                      const T* extF, const T* extT) {
   if (lc.active) {
-    T* rec = env + lane * REC;
-    if (lane == 0) { st(rec + R_Q, L.Q, 4); st(rec + R_P, L.p, 3); st(rec + R_W, L.w, 3); st(rec + R_V, L.v, 3); }
-    else if (lc.dyn) { st(rec + R_QJ, L.qj, 4); st(rec + R_WT, L.wt, 3); st(rec + R_PD, pd, 3); }
+    T* rec = env + lc.rix * REC;
+    if (lane == 0) {
+      T o[13];
+#pragma unroll
+      for (int k = 0; k < 4; k++) o[k] = L.Q[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { o[4 + k] = L.p[k]; o[7 + k] = L.w[k]; o[10 + k] = L.v[k]; }
+      str<R_Q, 13>(rec, o);
+    } else if (lc.dyn) {
+      T o[7];
+#pragma unroll
+      for (int k = 0; k < 4; k++) o[k] = L.qj[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) o[4 + k] = pd[k];
+      str<R_QJ, 7>(rec, o);
+      str<R_WT, 3>(rec, L.wt);
+    }
   }
   if (lane == 0) {
     T* ext = env + ENV_EXT;
@@ -1439,11 +1459,21 @@ template <typename T> __device__ __forceinline__ void pk_load_state(const T* env
 #pragma unroll
   for (int k = 0; k < 3; k++) { L.p[k] = 0; L.w[k] = 0; L.v[k] = 0; L.wt[k] = 0; cf[k] = 0; }
   if (lc.active) {
-    const T* rec = env + lane * REC;
-    ld(rec + R_Q, L.Q, 4); ld(rec + R_P, L.p, 3); ld(rec + R_W, L.w, 3); ld(rec + R_V, L.v, 3);
+    const T* rec = env + lc.rix * REC;
+    T o[16];
+    ldr<R_Q, 16>(rec, o);
+#pragma unroll
+    for (int k = 0; k < 4; k++) L.Q[k] = o[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { L.p[k] = o[4 + k]; L.w[k] = o[7 + k]; L.v[k] = o[10 + k]; }
     if (lc.dyn) {
-      ld(rec + R_CF, cf, 3);
-      if (lane > 0) { ld(rec + R_QJ, L.qj, 4); ld(rec + R_WT, L.wt, 3); }
+      cf[0] = rec[R_CFX];
+      ldr<R_CFY, 2>(rec, cf + 1);
+      if (lane > 0) {
+        ldr<R_QJ, 4>(rec, L.qj);
+#pragma unroll
+        for (int k = 0; k < 3; k++) L.wt[k] = o[13 + k];
+      }
     }
   }
 }
@@ -1464,13 +1494,14 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
   const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
   float* scratch_all = reinterpret_cast<float*>(smem + ((blob_bytes + 15) & ~15u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* scr = scratch_all + warp * PK_SCRATCH;
-  float* wrec = scratch_all + PK_WARPS * PK_SCRATCH + (size_t)warp * EPW * ENV_STRIDE;
+  float* scr = scratch_all + warp * PK_SCRATCH;   // prologue / epilogue scratch of the fused form; the split form has none
+  float* wrec = scratch_all + (SPLIT ? 0 : PK_WARPS * PK_SCRATCH) + (size_t)warp * EPW * ENV_STRIDE;
   __shared__ b200_cfg_t s_cfg;  // constants in shared memory: no global (long-scoreboard) reloads inside the substep loop
   for (int k = threadIdx.x; k < (int)(sizeof(b200_cfg_t) / 4); k += blockDim.x) reinterpret_cast<uint32_t*>(&s_cfg)[k] = reinterpret_cast<const uint32_t*>(gcfg)[k];
   __syncthreads();
   const b200_cfg_t& cfg = s_cfg;
-  const LaneConst lc = lane_const(M, lane);
+  LaneConst lc = lane_const(M, lane);
+  if (lc.active) lc.rix = B.t.rix[lane];
   const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
   const int g = lane >> 3, s = lane & 7;
   // The CTA's warps form PK_GROUPS independent groups, each pulling its own batches and meeting at its own named barrier:
@@ -1487,6 +1518,17 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
 
   __shared__ unsigned long long s_tk[2];
   for (;;) {
+#if PK_WARP_TICKETS
+    // one ticket per WARP = EPW consecutive envs: no CTA barrier anywhere in the loop, a warp whose envs were cheap (no
+    // ground contact) simply comes back for the next group earlier
+    unsigned long long tk = 0;
+    if (lane == 0) tk = atomicAdd(ticket, (unsigned long long)EPW);
+    tk = __shfl_sync(FULL, tk, 0);
+    const int64_t eb = (int64_t)tk;
+    if (eb >= num_envs) break;
+    const bool full_batch = false;
+    (void)s_tk; (void)BATCH; (void)group_sync;
+#else
     group_sync();
     if ((int)threadIdx.x == gw0 * 32) s_tk[grp] = atomicAdd(ticket, (unsigned long long)BATCH);
     group_sync();
@@ -1495,6 +1537,7 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     const bool full_batch = e0 + BATCH <= num_envs;
     const int64_t eb = e0 + (int64_t)(warp - gw0) * EPW;
     if (!full_batch && eb >= num_envs) continue;
+#endif
 
     if (SPLIT) {
       // all loads of the warp's EPW envs are issued before the first use (one memory latency instead of EPW)
@@ -1557,7 +1600,9 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     if (cfg.has_ball && valid && s == BALL_SLOT) ball_load(bf, erow_g, ball);
     if (ABL != 1) control_step_packed<float>(B, verts, pc, wrec, lane, valid, ball, STEP_SYNC && full_batch);
 #if POST_SYNC
-    if (full_batch) group_sync();
+    // fused form only: re-aligns the warps before the long straight-line epilogue (I-cache).  The split form's epilogue is a
+    // state write-back; without the barrier it measured 295.3 vs 298.3 us per 8192-env step (profiles/r1h_ab.log).
+    if (!SPLIT && full_batch) group_sync();
 #endif
     if (cfg.has_ball && valid && s == BALL_SLOT) ball_writeback(bf, erow_g, ball);
     for (int k = 0; k < EPW; k++) {
@@ -1591,7 +1636,8 @@ physics_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, co
   T* wrec = reinterpret_cast<T*>(smem + ((blob_bytes + 15) & ~15u)) + (size_t)warp * EPW * ENV_STRIDE;
   const int64_t eb = ((int64_t)blockIdx.x * WARPS + warp) * EPW;
   if (eb >= n) return;
-  const LaneConst lc = lane_const(M, lane);
+  LaneConst lc = lane_const(M, lane);
+  if (lc.active) lc.rix = B.t.rix[lane];
   const int nb = M.nb, nd = M.nd;
   PhysCfg<T> pc = make_phys_cfg<T>(*gcfg);
   const bool with_ball = pc.has_ball && ballio != nullptr;
@@ -1633,12 +1679,12 @@ physics_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, co
       for (int k = 0; k < EPW; k++) {
         if (eb + k >= n) break;
         if (lc.dyn && lane > 0) {
-          T* rec = wrec + k * ENV_STRIDE + lane * REC;
+          T* rec = wrec + k * ENV_STRIDE + lc.rix * REC;
           T qj[4], q[3];
-          ld(rec + R_QJ, qj, 4);
+          ldr<R_QJ, 4>(rec, qj);
           qlog(qj, q);
           qexp(q, qj);
-          st(rec + R_QJ, qj, 4);
+          str<R_QJ, 4>(rec, qj);
         }
         if (lane == 0) {  // the racket reaction does not carry over a control step in the lane kernel either (ball.rF is per substep)
         }
@@ -2045,6 +2091,10 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
         if (b > 0) hb.t.child_rank[b] = rk[model->parent[b]]++;
       }
     }
+    int next = 0;   // breadth-first record order (packed.cuh: neighbouring lanes of a tree depth -> neighbouring records)
+    for (int d = 0; d < MAX_LEVELS; d++)
+      for (int b = 0; b < model->nb; b++)
+        if (model->depth[b] == d) hb.t.rix[b] = next++;
   }
   const char* kv = getenv("B200ENV_KERNEL");
   h->packed = h->packed_ok && !(kv && strcmp(kv, "lane") == 0);
@@ -2121,14 +2171,16 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
   if (!h->bound || (!h->has_ml && h->cfg.task_mode == 0)) return fail(-4, "b200env_step: bind buffers and a motion lib first%s");
   cudaSetDevice(h->device);
   if (h->packed) {
-    const size_t psmem = ((h->blob_bytes + 15) & ~(size_t)15) + PK_WARPS * PK_SCRATCH * sizeof(float) + (size_t)PK_WARPS * EPW * ENV_STRIDE * sizeof(float);
+    const size_t psmem = ((h->blob_bytes + 15) & ~(size_t)15) + (h->split ? 0 : PK_WARPS * PK_SCRATCH * sizeof(float)) +
+                         (size_t)PK_WARPS * EPW * ENV_STRIDE * sizeof(float);
     const int batch = PK_WARPS * EPW;
     const int need = (h->num_envs + batch - 1) / batch;
     if (h->step_grid == 0) {
       CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
       CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
       int per_sm = 0, sms = 0;
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<false>, PK_WARPS * 32, psmem));
+      if (h->split) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<true>, PK_WARPS * 32, psmem)); }
+      else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<false>, PK_WARPS * 32, psmem)); }
       CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
       h->step_grid = per_sm * sms < need ? per_sm * sms : need;
       if (h->step_grid < 1) return fail(-5, "b200env_step: step_kernel_packed does not fit on this device%s");
@@ -2313,3 +2365,5 @@ int b200env_set_env_slice(b200env_handle h, int32_t env_first, int32_t env_strid
 }
 
 }  // extern "C"
+
+#include "ballgen.cuh"

@@ -1,0 +1,214 @@
+// ballgen.cuh - offline tennis-ball data generators (include/b200ball.h).  Included at the end of b200env.cu:
+// the balls are integrated by the very ball model of the env step kernel (Ball<T>, ball_substep<T> above), so the pool
+// trajectories and the estimator tables are consistent with what the envs simulate.  float64 twin: oracle/ref_port_ballgen.py.
+//
+// One thread per ball.  A trajectory is a serial chain (a sim step needs the previous one), the balls are independent: the
+// launch is sized to fill the machine with resident warps.  Output rows are written by the owning thread as they are produced
+// (12 B per 30 Hz frame, or one table column at a time); the rows of a warp are 480-1200 B apart, the sectors are completed in
+// L2 by the same thread a few iterations later.
+#pragma once
+#include "../../include/b200ball.h"
+
+#define BALLGEN_THREADS 128
+#define NET_HEIGHT_F 1.07  // tennis_ball.py:20
+
+// forces of simulate() (tennis_ball.py:160-183) / simulate_without_bounce (:58-74): drag + Magnus lift like ball_aero(), but the
+// lift direction follows the sign of the LAUNCH spin (vspin := -|w|/2pi for a back-spin launch)
+template <typename T>
+__device__ __forceinline__ void ball_aero_signed(const T* vel, const T* angvel, T launch_vspin, T spin_scale, T* force) {
+  const T KF = T(0.0019462794807519486), CD = T(0.55);
+  const T vs = sqrt_(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+  const T iv = rcp_(vs);
+  const T vn[3] = {vel[0] * iv, vel[1] * iv, vel[2] * iv};
+  const T vt[3] = {-vn[1], vn[0], T(0)};  // vn x (0,0,-1)
+  T vspin = sqrt_(angvel[0] * angvel[0] + angvel[1] * angvel[1] + angvel[2] * angvel[2]) * T(0.15915494309189535);
+  if (!(launch_vspin > T(0))) vspin = -vspin;
+  T cl = rcp_(T(2) + fabs(vs * rcp_(vspin * spin_scale + T(1e-6))));
+  cl = vspin > T(0) ? -cl : cl;
+  const T cx = vt[1] * vn[2] - vt[2] * vn[1], cy = vt[2] * vn[0] - vt[0] * vn[2], cz = vt[0] * vn[1] - vt[1] * vn[0];
+  const T kd = -KF * CD * vs, kl = -KF * cl * vs * vs;
+  force[0] = kd * vel[0] + kl * cx; force[1] = kd * vel[1] + kl * cy; force[2] = kd * vel[2] + kl * cz;
+}
+
+template <typename T> __device__ __forceinline__ PhysCfg<T> ballgen_cfg(const b200ball_sim_t& c) {
+  PhysCfg<T> p;
+  p.h = T(c.sim_dt) / T(c.substeps);
+  p.gz = T(c.gravity_z);
+  p.kn = p.cn = p.mu = p.vs = p.damp = p.wmax = p.limk = p.limc = T(0);
+  p.substeps = c.substeps; p.cfi = c.control_freq_inv;
+  p.has_ball = 1; p.racket_body = -1; p.wrist_body = 0;
+  p.bm = T(c.ball_mass); p.bI = T(c.ball_inertia); p.bR = T(c.ball_radius); p.spin_scale = T(c.spin_scale);
+  p.eg = T(c.e_ground); p.mug = T(c.mu_ground); p.er = T(0); p.mur = T(0); p.vth = T(c.bounce_threshold_velocity);
+  p.hc[0] = p.hc[1] = p.hc[2] = T(0); p.hh = p.hr = T(0);
+  p.hq[0] = p.hq[1] = p.hq[2] = T(0); p.hq[3] = T(1);
+  return p;
+}
+
+// launch state: angular velocity = vspin * 2pi * normalize(v x (0,0,-1))  (tennis_ball.py:134-139)
+template <typename T> __device__ __forceinline__ void ballgen_launch(Ball<T>& B, const T* p, const T* v, T vspin) {
+  ball_clear(B);
+  const T c[3] = {-v[1], v[0], T(0)};
+  T nn = sqrt_(c[0] * c[0] + c[1] * c[1]);
+  nn = nn > T(1e-12) ? nn : T(1e-12);
+  const T s = vspin * T(6.283185307179586) / nn;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { B.p[k] = p[k]; B.v[k] = v[k]; B.w[k] = s * c[k]; }
+}
+
+// ------------------------------------------------------------------------------------------ simulate()  (tennis_ball.py:113-218)
+template <typename T>
+__global__ void __launch_bounds__(BALLGEN_THREADS)
+ball_simulate_kernel(b200ball_sim_t c, int64_t n, const T* __restrict__ lp, const T* __restrict__ lv, const T* __restrict__ ls,
+                     T* __restrict__ traj, T* __restrict__ bounce_pos, int64_t* __restrict__ bounce_idx, uint8_t* __restrict__ pass_net) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const PhysCfg<T> pc = ballgen_cfg<T>(c);
+  Ball<T> B;
+  const T p0[3] = {lp[i * 3], lp[i * 3 + 1], lp[i * 3 + 2]}, v0[3] = {lv[i * 3], lv[i * 3 + 1], lv[i * 3 + 2]};
+  T lvs = ls[i];
+  ballgen_launch(B, p0, v0, lvs);
+  const T thr = c.substeps > 2 ? pc.bR * T(6) : pc.bR * T(4);
+  const int F = c.num_frames, nc = 3 - c.first_comp;
+  bool has_bounce = false, has_pass = false, pass_ok = false;
+  int64_t bidx = F - 1;
+  T bp[3] = {T(0), T(0), T(0)};
+  T* row = traj + i * F * nc;
+  for (int t = 0; t < F; t++) {
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (k >= c.first_comp) row[t * nc + k - c.first_comp] = B.p[k];
+    for (int s = 0; s < c.control_freq_inv; s++) {
+      ball_aero_signed<T>(B.v, B.w, lvs, pc.spin_scale, B.fa);
+      if (!has_pass && B.p[1] < T(0)) { pass_ok = !has_bounce && B.p[2] > T(NET_HEIGHT_F); has_pass = true; }     // :168-170
+      if (!has_bounce && B.p[2] <= thr) {                                                                         // :185-199
+        bp[0] = B.p[0]; bp[1] = B.p[1]; bp[2] = B.p[2];
+        bidx = t; has_bounce = true;
+        if (!(lvs > T(0))) lvs = -lvs;   // "backspin ball changes to topspin after bounce"
+      }
+      for (int sub = 0; sub < c.substeps; sub++) ball_substep<T>(pc, B, false, nullptr, nullptr, nullptr, nullptr);
+    }
+  }
+  bounce_pos[i * 3] = bp[0]; bounce_pos[i * 3 + 1] = bp[1]; bounce_pos[i * 3 + 2] = bp[2];
+  bounce_idx[i] = bidx;
+  pass_net[i] = pass_ok ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------- simulate_without_bounce()  (tennis_ball_out_estimator.py:21-121)
+// The reference stores the whole 60 Hz trajectory and then walks it once per grid value with a monotone sample pointer
+// (:90-110).  Both walks only ever look at two consecutive samples, so here a row is resampled while it is integrated:
+// at sample t every pending grid value whose stop condition holds (`!(t < T-1 && y_t < x)` resp. `!(t < T-1 && -z_t < y)`) is
+// emitted from samples (t-1, t).  t = 0 pairs sample 0 with sample "-1" = the LAST sample (Python index wrap, reachable only
+// by grid values <= 0): those columns are emitted after the loop.
+template <typename T>
+__global__ void __launch_bounds__(BALLGEN_THREADS)
+ball_out_rows_kernel(b200ball_sim_t c, int64_t n, const T* __restrict__ vel_h, const T* __restrict__ vel_v, const T* __restrict__ vspin,
+                     const float* __restrict__ gx, const int32_t* __restrict__ cx, int ngx, int nx, const float* __restrict__ gy,
+                     const int32_t* __restrict__ cy, int ngy, int ny, T* __restrict__ out_x, T* __restrict__ out_y) {
+  extern __shared__ unsigned char bg_smem[];
+  float* sgx = reinterpret_cast<float*>(bg_smem);
+  float* sgy = sgx + ngx;
+  int32_t* scx = reinterpret_cast<int32_t*>(sgy + ngy);
+  int32_t* scy = scx + ngx;
+  for (int k = threadIdx.x; k < ngx; k += blockDim.x) { sgx[k] = gx[k]; scx[k] = cx[k]; }
+  for (int k = threadIdx.x; k < ngy; k += blockDim.x) { sgy[k] = gy[k]; scy[k] = cy[k]; }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const T h = T(c.sim_dt) / T(c.substeps), gz = T(c.gravity_z), im = rcp_(T(c.ball_mass));
+  Ball<T> B;
+  const T p0[3] = {T(0), T(0), T(0)}, v0[3] = {T(0), vel_h[i], vel_v[i]};
+  const T lvs = vspin[i];
+  ballgen_launch(B, p0, v0, lvs);
+  const int Tn = (c.num_frames + 1) * c.control_freq_inv;
+  const T tscale = T(c.control_freq_inv * 30);
+  T* ox = out_x + i * nx;
+  T* oy = out_y + i * ny * 2;
+  int jx = 0, jy = 0, n0x = 0, n0y = 0;
+  T y1 = T(0), z1 = T(0);  // previous sample
+  auto emit_x = [&](int j, T ya, T za, T yb, T zb) {
+    const T x = T(sgx[j]);
+    const T w = (x - ya) / (yb - ya);
+    ox[scx[j]] = za * (T(1) - w) + zb * w;
+  };
+  auto emit_y = [&](int j, T ya, T za, T yb, T zb, int t) {
+    const T y = T(sgy[j]);
+    const T w = (-y - za) / (zb - za);
+    T* o = oy + scy[j] * 2;
+    o[0] = ya * (T(1) - w) + yb * w;
+    o[1] = (T(t - 1) * (T(1) - w) + T(t) * w) / tscale;
+  };
+  for (int t = 0; t < Tn; t++) {
+    const T y2 = B.p[1], z2 = B.p[2];
+    const bool last = t == Tn - 1;
+    while (jx < ngx && (last || !(y2 < T(sgx[jx])))) {
+      if (t == 0) n0x++; else emit_x(jx, y1, z1, y2, z2);
+      jx++;
+    }
+    while (jy < ngy && (last || !(-z2 < T(sgy[jy])))) {
+      if (t == 0) n0y++; else emit_y(jy, y1, z1, y2, z2, t);
+      jy++;
+    }
+    y1 = y2; z1 = z2;
+    if (last) break;
+    ball_aero_signed<T>(B.v, B.w, lvs, T(c.spin_scale), B.fa);
+    for (int sub = 0; sub < c.substeps; sub++) {
+      B.v[0] += h * B.fa[0] * im; B.v[1] += h * B.fa[1] * im; B.v[2] += h * (gz + B.fa[2] * im);
+      B.p[0] += h * B.v[0]; B.p[1] += h * B.v[1]; B.p[2] += h * B.v[2];
+    }
+  }
+  for (int j = 0; j < n0x; j++) emit_x(j, y1, z1, T(0), T(0));        // (sample -1 = last sample, sample 0 = launch point)
+  for (int j = 0; j < n0y; j++) emit_y(j, y1, z1, T(0), T(0), 0);
+}
+
+extern "C" {
+
+static int ballgen_check(const b200ball_sim_t* c, int64_t n, int32_t prec, const char* who) {
+  if (!c) return fail(-1, "%s: null cfg", who);
+  if (n < 0 || prec < 0 || prec > 1) return fail(-2, "%s: n >= 0 and prec in {0,1} required", who);
+  if (c->num_frames < 1 || c->control_freq_inv < 1 || c->substeps < 1 || c->first_comp < 0 || c->first_comp > 2 || !(c->sim_dt > 0.f) ||
+      !(c->ball_mass > 0.f) || !(c->ball_inertia > 0.f) || !(c->ball_radius > 0.f))
+    return fail(-2, "%s: bad simulation parameters", who);
+  return 0;
+}
+
+int b200ball_simulate(const b200ball_sim_t* cfg, int64_t n, int32_t prec, const void* launch_pos, const void* launch_vel,
+                      const void* launch_vspin, void* traj, void* bounce_pos, int64_t* bounce_idx, uint8_t* pass_net, void* stream) {
+  if (int rc = ballgen_check(cfg, n, prec, "b200ball_simulate")) return rc;
+  if (n == 0) return 0;
+  if (!launch_pos || !launch_vel || !launch_vspin || !traj || !bounce_pos || !bounce_idx || !pass_net)
+    return fail(-1, "b200ball_simulate: null argument%s");
+  const unsigned grid = (unsigned)((n + BALLGEN_THREADS - 1) / BALLGEN_THREADS);
+  if (prec == 0)
+    ball_simulate_kernel<float><<<grid, BALLGEN_THREADS, 0, (cudaStream_t)stream>>>(*cfg, n, (const float*)launch_pos, (const float*)launch_vel,
+                                                                                   (const float*)launch_vspin, (float*)traj, (float*)bounce_pos,
+                                                                                   bounce_idx, pass_net);
+  else
+    ball_simulate_kernel<double><<<grid, BALLGEN_THREADS, 0, (cudaStream_t)stream>>>(*cfg, n, (const double*)launch_pos, (const double*)launch_vel,
+                                                                                    (const double*)launch_vspin, (double*)traj, (double*)bounce_pos,
+                                                                                    bounce_idx, pass_net);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int b200ball_out_rows(const b200ball_sim_t* cfg, int64_t n, int32_t prec, const void* vel_h, const void* vel_v, const void* vspin,
+                      const float* grid_x, const int32_t* col_x, int32_t ngx, int32_t nx, const float* grid_y, const int32_t* col_y,
+                      int32_t ngy, int32_t ny, void* out_x, void* out_y, void* stream) {
+  if (int rc = ballgen_check(cfg, n, prec, "b200ball_out_rows")) return rc;
+  if (n == 0) return 0;
+  if (!vel_h || !vel_v || !vspin || !grid_x || !col_x || !grid_y || !col_y || !out_x || !out_y) return fail(-1, "b200ball_out_rows: null argument%s");
+  if (ngx < 0 || ngy < 0 || nx < 1 || ny < 1 || ngx > 4096 || ngy > 4096) return fail(-2, "b200ball_out_rows: grid sizes out of range%s");
+  const unsigned grid = (unsigned)((n + BALLGEN_THREADS - 1) / BALLGEN_THREADS);
+  const size_t smem = (size_t)(ngx + ngy) * (sizeof(float) + sizeof(int32_t));
+  if (prec == 0)
+    ball_out_rows_kernel<float><<<grid, BALLGEN_THREADS, smem, (cudaStream_t)stream>>>(*cfg, n, (const float*)vel_h, (const float*)vel_v,
+                                                                                      (const float*)vspin, grid_x, col_x, ngx, nx, grid_y, col_y, ngy,
+                                                                                      ny, (float*)out_x, (float*)out_y);
+  else
+    ball_out_rows_kernel<double><<<grid, BALLGEN_THREADS, smem, (cudaStream_t)stream>>>(*cfg, n, (const double*)vel_h, (const double*)vel_v,
+                                                                                       (const double*)vspin, grid_x, col_x, ngx, nx, grid_y, col_y,
+                                                                                       ngy, ny, (double*)out_x, (double*)out_y);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -10,58 +10,115 @@
 
 #define EPW 4     // envs per warp
 #define SLOTS 8   // lanes per env
-// record layout (element offsets); REC is odd -> consecutive bodies fall on different banks
+// Record layout (element offsets).  Records are 16-byte aligned (REC % 4 == 0, ENV_STRIDE % 4 == 0) and the fields that are
+// read / written together form runs that start on 4-float boundaries, so that a run moves with LDS.128 / STS.128 instead of one
+// 32-bit access per float (ncu r1g: 21 M of the 97 M warp instructions of a launch were scalar LDS / STS).  Body b lives in
+// record B.t.rix[b] = its rank in breadth-first order: the bodies of one tree depth are handled by neighbouring lanes at the
+// same time, and consecutive records are 18 float4 apart -> different bank groups for the 8 lanes of a quarter-warp phase
+// (the SMPL numbering itself puts siblings 4 bodies apart = the same bank group).
 enum {
-  R_Q = 0, R_P = 4, R_W = 7, R_V = 10,   // world pose / velocity of the body origin
-  R_QJ = 13, R_WT = 17, R_PD = 20,      // joint state + PD target
-  R_R = 23, R_ZETA = 26,                // p - p_parent, velocity-product terms
-  R_A = 32, R_BM = 38, R_C = 47, R_BN = 53, R_BF = 56,  // articulated inertia + bias (27 contiguous); R_BN.. reused as (alpha,a) after the backward pass
-  R_E = 59,                             // E_w, then D^-1
-  R_U = 65, R_CF = 68, REC = 71
+  R_Q = 0, R_P = 4, R_W = 7, R_V = 10, R_WT = 13,          // [0,16)  world pose / velocity of the body origin, joint velocity
+  R_QJ = 16, R_PD = 20, R_CFX = 23,                        // [16,24) joint rotation, PD target, contact force x
+  R_R = 24, R_ZETA = 27, R_U = 33,                         // [24,36) p - p_parent, velocity-product terms, joint-space bias
+  R_A = 36, R_BM = 42, R_C = 51, R_BN = 57, R_BF = 60, R_PAD = 63,  // [36,64) articulated inertia + bias (27 contiguous + 1 pad)
+  R_E = 64,                                                // [64,70) E_w, then D^-1
+  R_CFY = 70, R_CFZ = 71, REC = 72
 };
-#define R_ACC R_BN
-#define ENV_EXT (B200_MAX_BODIES_PK * REC)  // per-env extras: extF[3] extT[3] reactF[3] reactX[3]
+#define R_ACC 56   // (alpha, a) of the body after the backward pass: aliases C[5], bn, bf[0..1] (dead by then); v4 + v2
 #define B200_MAX_BODIES_PK 25
-#define ENV_STRIDE (ENV_EXT + 14)           // odd (1789): the 4 env groups of a warp start on different banks
+#define ENV_EXT (B200_MAX_BODIES_PK * REC)  // per-env extras: extF[3] extT[3] reactF[3] reactX[3]
+#define ENV_STRIDE (ENV_EXT + 12)
+#define RIX(B, b) ((B).t.rix[b])
 
-template <typename T> __device__ __forceinline__ void ld(const T* p, T* r, int n) {
-#pragma unroll
-  for (int k = 0; k < 27; k++) if (k < n) r[k] = p[k];
+// run of N record elements starting at the compile-time offset OFF of a 16-byte aligned record: float -> widest aligned accesses
+template <int OFF, int N, int K> __device__ __forceinline__ void ldr_f(const float* rec, float* r) {
+  if constexpr (K < N) {
+    if constexpr ((OFF + K) % 4 == 0 && N - K >= 4) {
+      const float4 v = *reinterpret_cast<const float4*>(rec + OFF + K);
+      r[K] = v.x; r[K + 1] = v.y; r[K + 2] = v.z; r[K + 3] = v.w;
+      ldr_f<OFF, N, K + 4>(rec, r);
+    } else if constexpr ((OFF + K) % 2 == 0 && N - K >= 2) {
+      const float2 v = *reinterpret_cast<const float2*>(rec + OFF + K);
+      r[K] = v.x; r[K + 1] = v.y;
+      ldr_f<OFF, N, K + 2>(rec, r);
+    } else {
+      r[K] = rec[OFF + K];
+      ldr_f<OFF, N, K + 1>(rec, r);
+    }
+  }
 }
-template <typename T> __device__ __forceinline__ void st(T* p, const T* r, int n) {
+template <int OFF, int N, int K> __device__ __forceinline__ void str_f(float* rec, const float* r) {
+  if constexpr (K < N) {
+    if constexpr ((OFF + K) % 4 == 0 && N - K >= 4) {
+      *reinterpret_cast<float4*>(rec + OFF + K) = make_float4(r[K], r[K + 1], r[K + 2], r[K + 3]);
+      str_f<OFF, N, K + 4>(rec, r);
+    } else if constexpr ((OFF + K) % 2 == 0 && N - K >= 2) {
+      *reinterpret_cast<float2*>(rec + OFF + K) = make_float2(r[K], r[K + 1]);
+      str_f<OFF, N, K + 2>(rec, r);
+    } else {
+      rec[OFF + K] = r[K];
+      str_f<OFF, N, K + 1>(rec, r);
+    }
+  }
+}
+template <int OFF, int N> __device__ __forceinline__ void ldr(const float* rec, float* r) { ldr_f<OFF, N, 0>(rec, r); }
+template <int OFF, int N> __device__ __forceinline__ void str(float* rec, const float* r) { str_f<OFF, N, 0>(rec, r); }
+template <int OFF, int N> __device__ __forceinline__ void ldr(const double* rec, double* r) {
 #pragma unroll
-  for (int k = 0; k < 27; k++) if (k < n) p[k] = r[k];
+  for (int k = 0; k < N; k++) r[k] = rec[OFF + k];
+}
+template <int OFF, int N> __device__ __forceinline__ void str(double* rec, const double* r) {
+#pragma unroll
+  for (int k = 0; k < N; k++) rec[OFF + k] = r[k];
 }
 
-// kinematics of one body from its parent's record
-template <typename T, bool WITH_ZETA>
-__device__ __forceinline__ void pk_fk(const b200_model_t& M, T* env, int b) {
-  T* rec = env + b * REC;
-  const T* par = env + M.parent[b] * REC;
-  T pQ[4], pp[3], pw[3], pv[3];
-  ld(par + R_Q, pQ, 4); ld(par + R_P, pp, 3); ld(par + R_W, pw, 3); ld(par + R_V, pv, 3);
-  T off[3] = {T(M.offset[b][0]), T(M.offset[b][1]), T(M.offset[b][2])}, rr[3], wxr[3], p[3], v[3];
+// kinematics of one body from its parent's record.  JOINT_IN_REGS: the caller (forward pass) just produced the body's joint
+// rotation / velocity and hands them over in registers (they are already in the record, this only saves the reload).
+template <typename T, bool WITH_ZETA, bool JOINT_IN_REGS = false>
+__device__ __forceinline__ void pk_fk(const DevBlob& B, T* env, int b, const T* qj_in = nullptr, const T* wt_in = nullptr) {
+  const b200_model_t& M = B.m;
+  T* rec = env + RIX(B, b) * REC;
+  const T* par = env + RIX(B, M.parent[b]) * REC;
+  T ps[13];  // parent Q[4] p[3] w[3] v[3]
+  ldr<R_Q, 13>(par, ps);
+  const T *pQ = ps, *pp = ps + 4, *pw = ps + 7, *pv = ps + 10;
+  T off[3] = {T(M.offset[b][0]), T(M.offset[b][1]), T(M.offset[b][2])}, rr[3], wxr[3];
+  T o[16];   // own Q[4] p[3] w[3] v[3] wt[3]
   qrot(pQ, off, rr);
   cross3(pw, rr, wxr);
 #pragma unroll
-  for (int k = 0; k < 3; k++) { p[k] = pp[k] + rr[k]; v[k] = pv[k] + wxr[k]; }
-  st(rec + R_P, p, 3); st(rec + R_V, v, 3);
-  if (WITH_ZETA) st(rec + R_R, rr, 3);
+  for (int k = 0; k < 3; k++) { o[4 + k] = pp[k] + rr[k]; o[10 + k] = pv[k] + wxr[k]; }
   if (M.fixed[b]) {
-    st(rec + R_Q, pQ, 4); st(rec + R_W, pw, 3);
-  } else {
-    T qj[4], wt[3], Q[4], wj[3], w[3];
-    ld(rec + R_QJ, qj, 4); ld(rec + R_WT, wt, 3);
-    qmul(pQ, qj, Q);
-    qnormalize(Q);
-    qrot(Q, wt, wj);
 #pragma unroll
-    for (int k = 0; k < 3; k++) w[k] = pw[k] + wj[k];
-    st(rec + R_Q, Q, 4); st(rec + R_W, w, 3);
+    for (int k = 0; k < 4; k++) o[k] = pQ[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[7 + k] = pw[k];
+    str<R_Q, 13>(rec, o);
+    if (WITH_ZETA) str<R_R, 3>(rec, rr);
+  } else {
+    T qj[4], wt[3], wj[3];
+    if (JOINT_IN_REGS) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) qj[k] = qj_in[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) wt[k] = wt_in[k];
+    } else {
+      T t4[4];
+      ldr<R_QJ, 4>(rec, qj);
+      ldr<12, 4>(rec, t4);   // v[2] | wt[3]
+      wt[0] = t4[1]; wt[1] = t4[2]; wt[2] = t4[3];
+    }
+    qmul(pQ, qj, o);
+    qnormalize(o);
+    qrot(o, wt, wj);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { o[7 + k] = pw[k] + wj[k]; o[13 + k] = wt[k]; }
+    str<R_Q, 16>(rec, o);
     if (WITH_ZETA) {
-      T z[6];
-      cross3(pw, wj, z); cross3(pw, wxr, z + 3);
-      st(rec + R_ZETA, z, 6);
+      T rz[9];
+      rz[0] = rr[0]; rz[1] = rr[1]; rz[2] = rr[2];
+      cross3(pw, wj, rz + 3); cross3(pw, wxr, rz + 6);
+      str<R_R, 9>(rec, rz);
     }
   }
 }
@@ -70,11 +127,16 @@ __device__ __forceinline__ void pk_fk(const b200_model_t& M, T* env, int b) {
 template <typename T>
 __device__ __forceinline__ void pk_body(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c, T* env, int b, bool ext_on) {
   const b200_model_t& M = B.m;
-  T* rec = env + b * REC;
-  T Q[4], p[3], w[3], v[3], R[9];
-  ld(rec + R_Q, Q, 4); ld(rec + R_P, p, 3); ld(rec + R_W, w, 3); ld(rec + R_V, v, 3);
+  T* rec = env + RIX(B, b) * REC;
+  T own[16], R[9];   // Q[4] p[3] w[3] v[3] wt[3]
+  ldr<R_Q, 16>(rec, own);
+  const T *Q = own, *p = own + 4, *w = own + 7, *v = own + 10;
   qmat(Q, R);
-  T A[6], Bm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, C[6] = {0, 0, 0, 0, 0, 0}, bn[3], bf[3], cf[3] = {0, 0, 0};
+  T ab[28];          // A[6] Bm[9] C[6] bn[3] bf[3] pad: one run of the record
+  T *A = ab, *Bm = ab + 6, *C = ab + 15, *bn = ab + 21, *bf = ab + 24, cf[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 6; k < 21; k++) ab[k] = T(0);
+  ab[27] = T(0);
   const T ms = T(M.mass[b]);
   T cl[3] = {T(M.com[b][0]), T(M.com[b][1]), T(M.com[b][2])}, cw[3];
   mv3(R, cl, cw);
@@ -125,11 +187,14 @@ __device__ __forceinline__ void pk_body(const DevBlob& B, const float* __restric
   const int nv = ABL == 6 ? 0 : M.nverts[b];
   if (nv > 0 && p[2] - T(M.radius[b]) < T(0))
     contact_hull<T>(verts + (size_t)b * M.vmax * 3, M.vmax, nv, c, R, p, v, w, A, Bm, C, bn, bf, cf);
-  st(rec + R_A, A, 6); st(rec + R_BM, Bm, 9); st(rec + R_C, C, 6); st(rec + R_BN, bn, 3); st(rec + R_BF, bf, 3); st(rec + R_CF, cf, 3);
+  str<R_A, 28>(rec, ab);
+  rec[R_CFX] = cf[0];
+  str<R_CFY, 2>(rec, cf + 1);
   if (b > 0) {
     const int d0 = M.dof_of_body[b];
-    T qj[4], wt[3], pd[3], q[3], tau[3], e[3], u[3], E[6];
-    ld(rec + R_QJ, qj, 4); ld(rec + R_WT, wt, 3); ld(rec + R_PD, pd, 3);
+    T jp[8], q[3], tau[3], e[3], u[3], E[6];   // qj[4] pd[3] (cf x)
+    ldr<R_QJ, 8>(rec, jp);
+    const T *qj = jp, *pd = jp + 4, *wt = own + 13;
     qlog(qj, q);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -147,23 +212,24 @@ __device__ __forceinline__ void pk_body(const DevBlob& B, const float* __restric
     E[3] = R[0] * R[3] * e[0] + R[1] * R[4] * e[1] + R[2] * R[5] * e[2];
     E[4] = R[0] * R[6] * e[0] + R[1] * R[7] * e[1] + R[2] * R[8] * e[2];
     E[5] = R[3] * R[6] * e[0] + R[4] * R[7] * e[1] + R[5] * R[8] * e[2];
-    st(rec + R_E, E, 6); st(rec + R_U, u, 3);
+    str<R_E, 6>(rec, E); str<R_U, 3>(rec, u);
   }
 }
 
 // backward step of one dynamic non-root body: D^-1, u, articulated inertia/bias shifted to the parent origin -> out[27]
 template <typename T>
-__device__ __forceinline__ void pk_backward(T* env, int b, T* out) {
-  T* rec = env + b * REC;
-  T A[6], Bm[9], C[6], bn[3], bf[3], E[6], u[3], r[3], zeta[6];
-  ld(rec + R_A, A, 6); ld(rec + R_BM, Bm, 9); ld(rec + R_C, C, 6); ld(rec + R_BN, bn, 3); ld(rec + R_BF, bf, 3);
-  ld(rec + R_E, E, 6); ld(rec + R_U, u, 3); ld(rec + R_R, r, 3); ld(rec + R_ZETA, zeta, 6);
+__device__ __forceinline__ void pk_backward(const DevBlob& B, T* env, int b, T* out) {
+  T* rec = env + RIX(B, b) * REC;
+  T ab[28], rzu[12], E[6];   // A[6] Bm[9] C[6] bn[3] bf[3] pad | r[3] zeta[6] u[3]
+  ldr<R_A, 28>(rec, ab); ldr<R_R, 12>(rec, rzu); ldr<R_E, 6>(rec, E);
+  const T *A = ab, *Bm = ab + 6, *C = ab + 15, *bn = ab + 21, *bf = ab + 24, *r = rzu, *zeta = rzu + 3;
+  T u[3] = {rzu[9], rzu[10], rzu[11]};
   T D[6], Dinv[6];
 #pragma unroll
   for (int k = 0; k < 6; k++) D[k] = A[k] + E[k];
   sym_inv(D, Dinv);
   u[0] -= bn[0]; u[1] -= bn[1]; u[2] -= bn[2];
-  st(rec + R_E, Dinv, 6); st(rec + R_U, u, 3);
+  str<R_E, 6>(rec, Dinv); str<R_U, 3>(rec, u);
   T Af[9], Df[9];
   sym_full(A, Af);
   sym_full(Dinv, Df);
@@ -235,12 +301,14 @@ __device__ __forceinline__ void pk_backward(T* env, int b, T* out) {
   cross3(r, af, rxf);
 #pragma unroll
   for (int k = 0; k < 3; k++) { out[21 + k] = an[k] + rxf[k]; out[24 + k] = af[k]; }
+  out[27] = T(0);
 }
 
 template <typename T> __device__ __forceinline__ void pk_root(const PhysCfg<T>& c, T* env) {
-  T* rec = env;
-  T A[6], Bm[9], C[6], bn[3], bf[3], acc[6];
-  ld(rec + R_A, A, 6); ld(rec + R_BM, Bm, 9); ld(rec + R_C, C, 6); ld(rec + R_BN, bn, 3); ld(rec + R_BF, bf, 3);
+  T* rec = env;   // the root is record 0
+  T ab[28], acc[6];
+  ldr<R_A, 28>(rec, ab);
+  const T *A = ab, *Bm = ab + 6, *C = ab + 15, *bn = ab + 21, *bf = ab + 24;
   T Ci[6], Cif[9], BC[9], S[6], Si[6], rhs[3], t[3];
   sym_inv(C, Ci);
   sym_full(Ci, Cif);
@@ -263,18 +331,22 @@ template <typename T> __device__ __forceinline__ void pk_root(const PhysCfg<T>& 
 #pragma unroll
   for (int k = 0; k < 3; k++) t[k] = -bf[k] - t[k];
   sym_mv(Ci, t, acc + 3);
-  st(rec + R_ACC, acc, 6);
+  str<R_ACC, 6>(rec, acc);
 }
 
-// forward step of one dynamic non-root body: accelerations, integrate the joint state
+// forward step of one dynamic non-root body: accelerations, integrate the joint state; the new joint rotation / velocity are also
+// returned in registers for the kinematics that follow at once (pk_fk<.., JOINT_IN_REGS>)
 template <typename T>
-__device__ __forceinline__ void pk_forward(const b200_model_t& M, const PhysCfg<T>& c, T* env, int b) {
-  T* rec = env + b * REC;
-  const T* par = env + M.parent[b] * REC;
-  T pa[6], A[6], Bm[9], Dinv[6], u[3], r[3], zeta[6], Q[4], wt[3], qj[4];
-  ld(par + R_ACC, pa, 6);
-  ld(rec + R_A, A, 6); ld(rec + R_BM, Bm, 9); ld(rec + R_E, Dinv, 6); ld(rec + R_U, u, 3); ld(rec + R_R, r, 3); ld(rec + R_ZETA, zeta, 6);
-  ld(rec + R_Q, Q, 4); ld(rec + R_WT, wt, 3); ld(rec + R_QJ, qj, 4);
+__device__ __forceinline__ void pk_forward(const DevBlob& B, const PhysCfg<T>& c, T* env, int b, T* qn, T* wt) {
+  const b200_model_t& M = B.m;
+  T* rec = env + RIX(B, b) * REC;
+  const T* par = env + RIX(B, M.parent[b]) * REC;
+  T pa[6], abm[16], Dinv[6], rzu[12], Q[4], vw[4], qj[4];   // abm: A[6] Bm[9] (C[0]);  rzu: r[3] zeta[6] u[3];  vw: v[2] wt[3]
+  ldr<R_ACC, 6>(par, pa);
+  ldr<R_A, 16>(rec, abm); ldr<R_E, 6>(rec, Dinv); ldr<R_R, 12>(rec, rzu);
+  ldr<R_Q, 4>(rec, Q); ldr<12, 4>(rec, vw); ldr<R_QJ, 4>(rec, qj);
+  const T *A = abm, *Bm = abm + 6, *r = rzu, *zeta = rzu + 3, *u = rzu + 9;
+  wt[0] = vw[1]; wt[1] = vw[2]; wt[2] = vw[3];
   T axr[3], Ap[6], t1[3], t2[3], t[3], gam[3], wd[3], acc[6];
   cross3(pa, r, axr);
 #pragma unroll
@@ -286,24 +358,26 @@ __device__ __forceinline__ void pk_forward(const b200_model_t& M, const PhysCfg<
   sym_mv(Dinv, t, gam);
 #pragma unroll
   for (int k = 0; k < 3; k++) { acc[k] = Ap[k] + gam[k]; acc[3 + k] = Ap[3 + k]; }
-  st(rec + R_ACC, acc, 6);
+  str<R_ACC, 6>(rec, acc);
   T cq[4] = {-Q[0], -Q[1], -Q[2], Q[3]};
   qrot(cq, gam, wd);  // R^T gam
 #pragma unroll
   for (int k = 0; k < 3; k++) wt[k] = (wt[k] + c.h * wd[k]) * c.damp;
   T n2 = wt[0] * wt[0] + wt[1] * wt[1] + wt[2] * wt[2];
   if (n2 > c.wmax * c.wmax) { T sc = c.wmax * rsqrt_(n2); wt[0] *= sc; wt[1] *= sc; wt[2] *= sc; }
-  T hv[3] = {c.h * wt[0], c.h * wt[1], c.h * wt[2]}, dq[4], qn[4];
+  T hv[3] = {c.h * wt[0], c.h * wt[1], c.h * wt[2]}, dq[4];
   qexp_small(hv, dq);
   qmul(qj, dq, qn);
   qnormalize(qn);
-  st(rec + R_WT, wt, 3); st(rec + R_QJ, qn, 4);
+  vw[1] = wt[0]; vw[2] = wt[1]; vw[3] = wt[2];
+  str<12, 4>(rec, vw); str<R_QJ, 4>(rec, qn);
 }
 
 template <typename T> __device__ __forceinline__ void pk_root_integrate(const PhysCfg<T>& c, T* env) {
   T* rec = env;
-  T acc[6], Q[4], p[3], w[3], v[3];
-  ld(rec + R_ACC, acc, 6); ld(rec + R_Q, Q, 4); ld(rec + R_P, p, 3); ld(rec + R_W, w, 3); ld(rec + R_V, v, 3);
+  T acc[6], o[13];   // Q[4] p[3] w[3] v[3]
+  ldr<R_ACC, 6>(rec, acc); ldr<R_Q, 13>(rec, o);
+  T *Q = o, *p = o + 4, *w = o + 7, *v = o + 10;
 #pragma unroll
   for (int k = 0; k < 3; k++) { w[k] = (w[k] + c.h * acc[k]) * c.damp; v[k] += c.h * acc[3 + k]; }
   T n2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
@@ -314,7 +388,9 @@ template <typename T> __device__ __forceinline__ void pk_root_integrate(const Ph
   qexp_small(hv, dq);
   qmul(dq, Q, qn);
   qnormalize(qn);
-  st(rec + R_Q, qn, 4); st(rec + R_P, p, 3); st(rec + R_W, w, 3); st(rec + R_V, v, 3);
+#pragma unroll
+  for (int k = 0; k < 4; k++) Q[k] = qn[k];
+  str<R_Q, 13>(rec, o);
 }
 
 // One control step for the warp's EPW envs.  wrec: the warp's records; valid: this lane's env exists.
@@ -330,7 +406,7 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
   // kinematics of the start state, root -> leaves; every later FK is fused into the forward pass of the substep before it
   for (int d = 1; d <= M.max_depth; d++) {
     const int b = valid ? B.t.lvl_all[d][s] : -1;
-    if (b >= 0) pk_fk<T, true>(M, env, b);
+    if (b >= 0) pk_fk<T, true>(B, env, b);
     __syncwarp();
   }
   for (int sim = 0; sim < c.cfi; sim++) {
@@ -353,14 +429,17 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
       // 2. articulated inertia, leaves -> root
       for (int d = (ABL == 9 ? 0 : M.max_depth); d >= 1; d--) {
         const int b = valid ? B.t.lvl_dyn[d][s] : -1;
-        T out[27];
-        if (b >= 0) pk_backward<T>(env, b, out);
+        T out[28];
+        if (b >= 0) pk_backward<T>(B, env, b, out);
         const int rounds = B.t.maxch[d - 1];
         for (int cr = 0; cr < rounds; cr++) {
           if (b >= 0 && B.t.child_rank[b] == cr) {
-            T* pr = env + M.parent[b] * REC + R_A;
+            T* pr = env + RIX(B, M.parent[b]) * REC;
+            T acc[28];
+            ldr<R_A, 28>(pr, acc);
 #pragma unroll
-            for (int k = 0; k < 27; k++) pr[k] += out[k];
+            for (int k = 0; k < 28; k++) acc[k] += out[k];
+            str<R_A, 28>(pr, acc);
           }
           __syncwarp();
         }
@@ -371,8 +450,13 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
         T rQ[4] = {0, 0, 0, 1}, rp[3] = {0, 0, 0}, rv[3] = {0, 0, 0}, rw[3] = {0, 0, 0};
         const bool has_racket = c.racket_body >= 0;
         if (has_racket) {
-          const T* rr = env + c.racket_body * REC;
-          ld(rr + R_Q, rQ, 4); ld(rr + R_P, rp, 3); ld(rr + R_V, rv, 3); ld(rr + R_W, rw, 3);
+          const T* rr = env + RIX(B, c.racket_body) * REC;
+          T rs[13];
+          ldr<R_Q, 13>(rr, rs);
+#pragma unroll
+          for (int k = 0; k < 4; k++) rQ[k] = rs[k];
+#pragma unroll
+          for (int k = 0; k < 3; k++) { rp[k] = rs[4 + k]; rw[k] = rs[7 + k]; rv[k] = rs[10 + k]; }
         }
         ball_substep<T>(c, ball, has_racket, rQ, rp, rv, rw);
         T* ext = env + ENV_EXT;
@@ -386,8 +470,13 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
       for (int d = 1; d <= (ABL == 10 ? 0 : M.max_depth); d++) {
         const int b = valid ? B.t.lvl_all[d][s] : -1;
         if (b >= 0) {
-          if (!M.fixed[b]) pk_forward<T>(M, c, env, b);
-          pk_fk<T, true>(M, env, b);
+          if (!M.fixed[b]) {
+            T qn[4], wt[3];
+            pk_forward<T>(B, c, env, b, qn, wt);
+            pk_fk<T, true, true>(B, env, b, qn, wt);
+          } else {
+            pk_fk<T, true>(B, env, b);
+          }
         }
         __syncwarp();
       }
