@@ -26,6 +26,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ALGO_BYTES_PER_ENV_STEP = 9792  # SURVEY.md 8(d), embodied_pose configs; derivation in DESIGN.md 5
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE step_kernel_packed<split> launch at 8192 envs, from the `ncu --set full`
+# capture profiles/r1h_step_kernel_packed_ncu.md (7.51 MB read + 512 B written: the state rows the neighbouring launches of a
+# rollout touch stay in the 126 MB L2, so the DRAM traffic is far BELOW the 80.2 MB of algorithmic bytes; pre_kernel adds 18.6 MB,
+# post_kernel 40.3 MB, profiles/r1g ncu).  A constant from the profile, not measured by bench.py.
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 7508992
 HORIZON = 32
 
 
@@ -201,6 +206,43 @@ def dual_workload(envs, device_index, steps=96, warmup=16):
             "mode": "one CUDA graph per high-level step (2 physics launches) + eager reference-shaped reset (id lists, host sync)",
             "workload": f"vid2player federer_djokovic dual: {envs} paired envs ({envs // 2} rallies), substeps 6, return_w_estimate, "
                         "use_random_ball_target, fix_head_orientation, synthetic incoming-ball table / motion generator"}
+
+
+def ball_tables_workload(reps=3):
+    """the reference's offline ball data products at their full sizes, one launch each (tools/perf_ballgen.py has the
+    stand-alone version).  out tables: 8 250 000 rows x (60 + 30 x 2) f32; in table: 1 125 000 rows x 50 x 2 f32."""
+    import torch
+    from vid2player3d_b200 import ball_gen as G
+    dev = "cuda:%d" % torch.cuda.current_device()
+
+    def best_ms(fn):
+        fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return min(ms)
+    vh, vv, vs = G._mesh(G.traj_out_params.VEL_X_RANGE, G.traj_out_params.VEL_Y_RANGE, G.traj_out_params.VSPIN_RANGE, device=dev)
+    n = int(vh.shape[0])
+    ms_out = best_ms(lambda: G.simulate_without_bounce(vh, vv, vs, device=dev))
+    del vh, vv, vs
+    hh, vx, vz, sp = G._mesh(G.traj_in_params.HEIGHT_RANGE, G.traj_in_params.VEL_X_RANGE, G.traj_in_params.VEL_Y_RANGE,
+                             G.traj_in_params.VSPIN_RANGE, device=dev)
+    m = int(hh.shape[0])
+    pos = torch.stack([torch.zeros_like(hh), torch.zeros_like(hh), hh], 1)
+    vel = torch.stack([torch.zeros_like(hh), vx, vz], 1)
+    ms_in = best_ms(lambda: G.simulate(pos, vel, sp, num_frames=50, first_comp=1, device=dev))
+    out_bytes = n * (120 * 4 + 12)
+    return {"out_tables": {"rows": n, "ms": ms_out, "rows_per_s": n / (ms_out * 1e-3), "algorithmic_bytes": out_bytes,
+                           "GBps": out_bytes / 1e9 / (ms_out * 1e-3), "ball_sim_steps_per_s": n * 122 / (ms_out * 1e-3)},
+            "in_table": {"rows": m, "ms": ms_in, "rows_per_s": m / (ms_in * 1e-3), "ball_substeps_per_s": m * 50 * 12 / (ms_in * 1e-3)},
+            "workload": "offline ball data generators (tennis_ball_out_estimator.py:208-258, tennis_ball_in_estimator.py:82-140) at the "
+                        "reference's grid sizes; the reference steps 10 000 balls per Isaac Gym batch from Python"}
 
 
 def cpu_reference_arm(model, flat, sample_envs, steps, warmup, seed=7):
@@ -389,7 +431,7 @@ def main():
                 "d2h_bytes_per_step": N * 4 + N * 8,
                 "api": "VecTaskPythonWrapper.step/reset, pinned host actions in, reward+reset out, host sync every step"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                      "kernel": ("step_kernel" if os.environ.get("B200ENV_KERNEL") == "lane" else
                                 "step_kernel_packed<fused>" if os.environ.get("B200ENV_SPLIT") == "0" else
                                 "one env step = pre_kernel + step_kernel_packed<split> (dominant, ~90 %) + post_kernel"), "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
@@ -405,6 +447,10 @@ def main():
             out["config"]["dual"] = dual_workload(N, local_rank)
         except Exception as ex:
             out["config"]["dual"] = {"error": repr(ex)[:200]}
+        try:
+            out["config"]["ball_tables"] = ball_tables_workload()
+        except Exception as ex:
+            out["config"]["ball_tables"] = {"error": repr(ex)[:200]}
     if not args.no_cpu_baseline:
         from oracle import physics_ref
         physics_ref.build()

@@ -33,14 +33,16 @@ I_BALL = 4e-5                                     # tennis_ball.urdf
 class BallWorld:
     """N free balls over the plane z = 0 (our model; see module docstring).  state[N,13] = pos3 quat4 vel3 angvel3."""
 
-    def __init__(self, n, substeps=6, sim_dt=1.0 / 60.0, e_ground=0.7, mu_ground=0.6, vth=0.2, gravity=-9.81, ground=True):
+    def __init__(self, n, substeps=6, sim_dt=1.0 / 60.0, e_ground=0.7, mu_ground=0.6, vth=0.2, gravity=-9.81, ground=True,
+                 mass=M_BALL, radius=R_BALL, inertia=I_BALL):
         self.n, self.substeps, self.h = n, substeps, sim_dt / substeps
         self.e, self.mu, self.vth, self.g, self.ground = e_ground, mu_ground, vth, gravity, ground
+        self.m, self.R, self.I = mass, radius, inertia
 
     def sim_step(self, state, force):
         """one gym.simulate(): `substeps` substeps with the applied force held constant; float64 arithmetic in place"""
         p, v, w = state[:, 0:3], state[:, 7:10], state[:, 10:13]
-        h, m, R, I = self.h, M_BALL, R_BALL, I_BALL
+        h, m, R, I = self.h, self.m, self.R, self.I
         for _ in range(self.substeps):
             v[:, 0] += h * force[:, 0] / m
             v[:, 1] += h * force[:, 1] / m
@@ -110,7 +112,7 @@ def simulate(launch_pos, launch_vel, launch_vspin, control_freq_inv=2, num_frame
     bounce_pos = np.zeros((n, 3), np.float32)
     bounce_idx = np.zeros(n, np.int64) + num_frames - 1
     has_bounce, has_pass_net, pass_ok = np.zeros(n, bool), np.zeros(n, bool), np.zeros(n, bool)
-    thr = R_BALL * 6 if substeps > 2 else R_BALL * 4
+    thr = world.R * 6 if substeps > 2 else world.R * 4
     for t in range(num_frames):
         traj[:, t] = st[:, 0:3]
         for _ in range(control_freq_inv):
@@ -137,12 +139,12 @@ def torch_arange(lo, hi, step):
 
 
 def simulate_without_bounce(launch_pos, launch_vel, launch_vspin, traj_x_range=(0, 30, 0.5), traj_y_range=(0, 3, 0.1),
-                            control_freq_inv=2, num_frames=60, substeps=6, spin_scale=5, state32=True):
+                            control_freq_inv=2, num_frames=60, substeps=6, spin_scale=5, state32=True, world_kw=None):
     """tennis_ball_out_estimator.py:21-121 -> traj_x[n, NX] (height over launch at horizontal distance x),
     traj_y[n, NY, 2] (distance, time at which the ball has dropped y below the launch height)"""
     dt = np.float32 if state32 else np.float64
     n = len(launch_pos)
-    world = BallWorld(n, substeps=substeps, ground=False)
+    world = BallWorld(n, substeps=substeps, ground=False, **(world_kw or {}))
     st = launch_state(np.asarray(launch_pos), np.asarray(launch_vel), np.asarray(launch_vspin), dt)
     lvspin = np.array(launch_vspin, dt)
     samples = []
@@ -188,6 +190,13 @@ def simulate_without_bounce(launch_pos, launch_vel, launch_vspin, traj_x_range=(
         tt = (t - 1).astype(dt) * (1 - w) + t.astype(dt) * w     # torch: int64 * float32 -> float32
         traj_y[:, j, 1] = tt / (control_freq_inv * 30)
     return traj_x, traj_y
+
+
+def f32_physics():
+    """the parameter block as the C ABI carries it (b200ball_sim_t holds floats): what the kernel's double instantiation integrates"""
+    f = lambda x: float(np.float32(x))  # noqa: E731
+    return dict(sim_dt=f(1.0 / 60.0), e_ground=f(0.7), mu_ground=f(0.6), vth=f(0.2), gravity=f(-9.81), mass=f(M_BALL), radius=f(R_BALL),
+                inertia=f(I_BALL))
 
 
 def launch_grid_out(vel_x=(10, 65, 0.1), vel_y=(-5, 10, 0.1), vspin=(-10, 10, 0.2)):

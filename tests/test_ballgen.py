@@ -58,7 +58,7 @@ def test_simulate_kernel_double_equals_oracle_twin():
     from vid2player3d_b200 import ball_gen
     for substeps, frames in ((6, 100), (2, 60)):
         ref = P.simulate(Z["sim_pos"].astype(np.float64), Z["sim_vel"].astype(np.float64), Z["sim_vspin"].astype(np.float64),
-                         num_frames=frames, substeps=substeps, state32=False)
+                         num_frames=frames, substeps=substeps, state32=False, world_kw=P.f32_physics())
         got = ball_gen.simulate(Z["sim_pos"], Z["sim_vel"], Z["sim_vspin"], num_frames=frames, substeps=substeps, dtype=torch.float64)
         assert np.abs(got[0].cpu().numpy() - ref[0]).max() < 1e-9
         assert np.abs(got[1].cpu().numpy() - ref[1]).max() < 1e-6      # the oracle keeps bounce_pos in float32 like the reference
@@ -87,7 +87,7 @@ def test_out_rows_kernel_vs_oracle_and_golden():
     vh, vv, vs = _out_launch()
     m = len(vs)
     lv = np.stack([np.zeros(m), vh, vv], 1)
-    rx, ry = P.simulate_without_bounce(np.zeros((m, 3)), lv, vs.astype(np.float64), state32=False)
+    rx, ry = P.simulate_without_bounce(np.zeros((m, 3)), lv, vs.astype(np.float64), state32=False, world_kw=P.f32_physics())
     gx, gy = ball_gen.simulate_without_bounce(vh, vv, vs, dtype=torch.float64)
     # the oracle interpolates in the dtype of its trajectory (float64 here) and stores float32 tables
     assert np.abs(gx.cpu().numpy() - rx).max() < 1e-5
@@ -122,10 +122,16 @@ def test_full_size_tables_properties():
     from vid2player3d_b200 import ball_gen
     tx, ty = ball_gen.generate_outgoing_trajectory()
     assert tx.shape == (8250000, 60) and ty.shape == (8250000, 30, 2)
-    assert bool(torch.isfinite(tx).all()) and bool(torch.isfinite(ty).all())
-    assert bool((tx[:, 0] == 0).all()) and bool((ty[:, 0] == 0).all())
-    assert bool((ty[:, 2:, 1] >= ty[:, 1:-1, 1]).all())          # a larger drop is never reached earlier
     vh, vv, vs = P.launch_grid_out()
+    assert bool(torch.isfinite(tx).all()) and bool((tx[:, 0] == 0).all()) and bool((ty[:, 0] == 0).all())
+    # A ball that is still above its launch height after the 2 s of flight has its drop columns EXTRAPOLATED from the last two
+    # samples (the reference does the same, :101-110): meaningless values, non-finite when the two heights coincide (14 of the
+    # 8.25 M rows on B200).  Balls launched flat or downwards come down at once: there every column is an interpolation.
+    down = torch.from_numpy(vv <= 0).to(ty.device)
+    assert bool(torch.isfinite(ty[down]).all())
+    assert bool((ty[down][:, 2:, 1] >= ty[down][:, 1:-1, 1]).all())     # a larger drop is never reached earlier
+    assert bool((ty[down][:, 1:, 0] > 0).all())                         # ... and the ball has moved forward by then
+    assert int((~torch.isfinite(ty)).any(2).any(1).sum()) < 100
     pick = np.arange(0, len(vh), 350003)
     sx, sy = ball_gen.simulate_without_bounce(vh[pick], vv[pick], vs[pick])
     assert torch.equal(sx, tx[pick]) and torch.equal(sy, ty[pick])              # rows do not depend on the batch they were in

@@ -213,3 +213,24 @@ print("OK", args.task, sp.up_axis == gymapi.UP_AXIS_Z)
 ''' % ROOT
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_flat_motion_library_file_roundtrip(tmp_path):
+    """the mmap-able on-disk MoCap format holds exactly the arrays the sampler reads"""
+    from vid2player3d_b200 import model_compiler, motion_lib
+    model = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    flat = motion_lib.synthetic(model, num_motions=5, num_frames=40, seed=3, ragged=True)
+    path = str(tmp_path / "lib.b200ml")
+    flat.save_flat(path)
+    for mm in (True, False):
+        back = motion_lib.FlatMotionLib.load_flat(path, mmap=mm)
+        for k in motion_lib.FlatMotionLib.FIELDS:
+            a, b = getattr(flat, k), getattr(back, k)
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), k
+    assert isinstance(back.gts, np.ndarray) and motion_lib.FlatMotionLib.load_any(path).num_motions() == 5
+    assert os.path.getsize(path) % 64 == 0
+    flat.save(str(tmp_path / "lib.npz"))
+    assert np.array_equal(motion_lib.FlatMotionLib.load_any(str(tmp_path / "lib.npz")).dvs, flat.dvs)
+    (tmp_path / "bad.b200ml").write_bytes(b"not a library" * 4)
+    with pytest.raises(ValueError, match="not a B200ML01"):
+        motion_lib.FlatMotionLib.load_flat(str(tmp_path / "bad.b200ml"))

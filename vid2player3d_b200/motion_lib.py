@@ -12,6 +12,8 @@ SURVEY.md §0.5), so `synthetic()` fabricates a smooth random-walk library on th
 skeleton for tests and benchmarks.  `from_reference()` accepts a loaded reference MotionLib
 object when one is available.
 """
+import os
+
 import numpy as np
 
 BASE_ROT = np.array([0.5, 0.5, 0.5, 0.5])  # SMPL y-up -> z-up base rotation (humanoid_smpl_im.py:766-770)
@@ -86,6 +88,68 @@ class FlatMotionLib:
     def load(cls, path):
         z = np.load(path)
         return cls(**{k: z[k] for k in cls.FIELDS})
+
+    # ---- flat on-disk format: one file, mmap-able, arrays 64-byte aligned in the order the sampler reads them.
+    #   bytes 0-7   magic "B200ML01"      bytes 8-15  little-endian uint64 = length of the JSON header that follows
+    #   header      {"fields": {name: {"dtype": "<f4"|"<i8", "shape": [...], "offset": bytes from file start}}, "num_motions": M}
+    #   payload     the arrays of FIELDS, C order.  Replaces `torch.save(motion_lib)` pickles of Python objects
+    #   (embodied_pose/utils/motion_lib.py:68-93 keeps the same tensors after `_load_motions`).
+    MAGIC = b"B200ML01"
+
+    def save_flat(self, path):
+        import json
+        arrays = {k: np.ascontiguousarray(getattr(self, k)) for k in self.FIELDS}
+        base = 4096                                   # header region: magic + length + JSON, space padded; payload starts here
+        while True:
+            fields, off = {}, base
+            for k, a in arrays.items():
+                fields[k] = {"dtype": a.dtype.str, "shape": list(a.shape), "offset": off}
+                off += (a.nbytes + 63) // 64 * 64
+            hdr = json.dumps({"fields": fields, "num_motions": int(self.num_motions())}).encode()
+            if 16 + len(hdr) <= base:
+                break
+            base *= 2
+        with open(path, "wb") as fh:
+            fh.write(self.MAGIC)
+            fh.write(np.uint64(len(hdr)).tobytes())
+            fh.write(hdr)
+            for k, a in arrays.items():
+                fh.seek(fields[k]["offset"])
+                fh.write(a.tobytes())
+            fh.truncate(off)
+
+    @classmethod
+    def load_flat(cls, path, mmap=True):
+        """mmap=True: the arrays are read-only views of the file (no copy until the upload to the device)."""
+        import json
+        with open(path, "rb") as fh:
+            if fh.read(8) != cls.MAGIC:
+                raise ValueError(f"{path}: not a B200ML01 motion library")
+            n = int(np.frombuffer(fh.read(8), np.uint64)[0])
+            hdr = json.loads(fh.read(n).decode())
+        missing = [k for k in cls.FIELDS if k not in hdr["fields"]]
+        if missing:
+            raise ValueError(f"{path}: missing fields {missing}")
+        kw = {}
+        for k in cls.FIELDS:
+            f = hdr["fields"][k]
+            if mmap:
+                kw[k] = np.memmap(path, dtype=np.dtype(f["dtype"]), mode="r", offset=f["offset"], shape=tuple(f["shape"]))
+            else:
+                kw[k] = np.fromfile(path, dtype=np.dtype(f["dtype"]), count=int(np.prod(f["shape"])), offset=f["offset"]).reshape(f["shape"])
+        return cls(**kw)
+
+    @classmethod
+    def load_any(cls, path):
+        """`.b200ml` flat file, `.npz` archive (save()), or a reference `torch.save(motion_lib)` pickle (`.pth` / `.pt`; needs the
+        reference's `utils.motion_lib` and `poselib` importable, like the reference's own `torch.load` of it)."""
+        ext = os.path.splitext(path)[1].lower()
+        if ext == ".npz":
+            return cls.load(path)
+        if ext in (".pth", ".pt"):
+            import torch
+            return cls.from_reference(torch.load(path, map_location="cpu", weights_only=False))
+        return cls.load_flat(path)
 
     @classmethod
     def from_reference(cls, ml):
