@@ -1,0 +1,143 @@
+// emu_packed.cpp - TEST INFRASTRUCTURE: the packed articulated step (csrc/packed*.cuh) executed on the CPU, one host thread per
+// lane, in float64, behind the same signature as b200env_physics_only.  Lets a new lane mapping of the kernel be checked against
+// the float64 restatement (oracle/physics_ref.c) without a GPU.  Built by tests/emu/build.py (g++ -O1 -pthread -shared).
+#include "cuda_compat.h"
+
+thread_local EmuWarp* emu_warp = nullptr;
+thread_local int emu_lane = 0;
+
+#include "../../vid2player3d_b200/csrc/dyn_common.cuh"
+#ifdef EMU_PACKED3
+#include "../../vid2player3d_b200/csrc/packed3.cuh"
+#else
+#include "../../vid2player3d_b200/csrc/packed.cuh"
+#endif
+
+#include <vector>
+
+namespace {
+struct Job {
+  const DevBlob* B;
+  const float* verts;
+  const b200_cfg_t* cfg;
+  int n, n_steps;
+  double *root, *dof_pos, *dof_vel;
+  const double *pd_tar, *ext;
+  double *rb_out, *contact_out, *ballio;
+  int32_t* hits;
+};
+
+// one warp = the body of physics_kernel_packed<double> (b200env.cu) for envs eb .. eb + EPW - 1
+void lane_main(EmuWarp* w, int lane, const Job* J, int64_t eb, double* wrec) {
+  emu_warp = w;
+  emu_lane = lane;
+  typedef double T;
+  const DevBlob& B = *J->B;
+  const b200_model_t& M = B.m;
+  const int n = J->n, nb = M.nb, nd = M.nd;
+  LaneConst lc = lane_const(M, lane);
+  if (lc.active) lc.rix = B.t.rix[lane];
+  PhysCfg<T> pc = make_phys_cfg<T>(*J->cfg);
+  const bool with_ball = pc.has_ball && J->ballio != nullptr;
+  pc.has_ball = with_ball;
+  const int g = lane / PK_LANES_PER_ENV, s = lane % PK_LANES_PER_ENV;
+  for (int k = 0; k < EPW; k++) {
+    const int64_t e = eb + k;
+    if (e >= n) break;
+    Lane<T> L;
+    for (int j = 0; j < 4; j++) { L.Q[j] = 0; L.qj[j] = 0; }
+    L.Q[3] = 1; L.qj[3] = 1;
+    for (int j = 0; j < 3; j++) { L.p[j] = 0; L.w[j] = 0; L.v[j] = 0; L.wt[j] = 0; }
+    T pdt[3] = {0, 0, 0}, eF[3] = {0, 0, 0}, eT[3] = {0, 0, 0};
+    if (lane == 0) {
+      const T* rs = J->root + e * 13;
+      for (int j = 0; j < 3; j++) { L.p[j] = rs[j]; L.v[j] = rs[7 + j]; L.w[j] = rs[10 + j]; }
+      for (int j = 0; j < 4; j++) L.Q[j] = rs[3 + j];
+      qnormalize(L.Q);
+      if (J->ext) for (int j = 0; j < 3; j++) { eF[j] = J->ext[e * 6 + j]; eT[j] = J->ext[e * 6 + 3 + j]; }
+    }
+    if (lc.dyn && lane > 0) {
+      T q[3];
+      for (int j = 0; j < 3; j++) { q[j] = J->dof_pos[e * nd + lc.dof0 + j]; L.wt[j] = J->dof_vel[e * nd + lc.dof0 + j]; pdt[j] = J->pd_tar[e * nd + lc.dof0 + j]; }
+      qexp(q, L.qj);
+    }
+    pk_store_state<T>(wrec + k * ENV_STRIDE, lc, lane, L, pdt, eF, eT);
+  }
+  __syncwarp();
+  const bool valid = g < EPW && eb + g < n;
+  Ball<T> ball;
+  ball_clear(ball);
+  if (with_ball && valid && s == BALL_SLOT) {
+    const int64_t e = eb + g;
+    for (int j = 0; j < 3; j++) { ball.p[j] = J->ballio[e * 13 + j]; ball.v[j] = J->ballio[e * 13 + 7 + j]; ball.w[j] = J->ballio[e * 13 + 10 + j]; }
+  }
+  for (int st_ = 0; st_ < J->n_steps; st_++) {
+    control_step_packed<T>(B, J->verts, pc, wrec, lane, valid, ball, false);
+    if (st_ + 1 < J->n_steps) {
+      for (int k = 0; k < EPW; k++) {
+        if (eb + k >= n) break;
+        if (lc.dyn && lane > 0) {
+          T* rec = wrec + k * ENV_STRIDE + lc.rix * REC;
+          T qj[4], q[3];
+          ldr<R_QJ, 4>(rec, qj);
+          qlog(qj, q);
+          qexp(q, qj);
+          str<R_QJ, 4>(rec, qj);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int k = 0; k < EPW; k++) {
+    const int64_t e = eb + k;
+    if (e >= n) break;
+    Lane<T> L;
+    T cf[3];
+    pk_load_state<T>(wrec + k * ENV_STRIDE, lc, lane, L, cf);
+    if (lane == 0) {
+      T* rs = J->root + e * 13;
+      for (int j = 0; j < 3; j++) { rs[j] = L.p[j]; rs[7 + j] = L.v[j]; rs[10 + j] = L.w[j]; }
+      for (int j = 0; j < 4; j++) rs[3 + j] = L.Q[j];
+    }
+    if (lc.dyn && lane > 0) {
+      T q[3];
+      qlog(L.qj, q);
+      for (int j = 0; j < 3; j++) { J->dof_pos[e * nd + lc.dof0 + j] = q[j]; J->dof_vel[e * nd + lc.dof0 + j] = L.wt[j]; }
+    }
+    if (lc.active) {
+      T* rb = J->rb_out + (e * nb + lane) * 13;
+      for (int j = 0; j < 3; j++) { rb[j] = L.p[j]; rb[7 + j] = L.v[j]; rb[10 + j] = L.w[j]; }
+      for (int j = 0; j < 4; j++) rb[3 + j] = L.Q[j];
+      if (J->contact_out) for (int j = 0; j < 3; j++) J->contact_out[(e * nb + lane) * 3 + j] = cf[j];
+    }
+  }
+  if (with_ball && valid && s == BALL_SLOT) {
+    const int64_t e = eb + g;
+    for (int j = 0; j < 3; j++) { J->ballio[e * 13 + j] = ball.p[j]; J->ballio[e * 13 + 7 + j] = ball.v[j]; J->ballio[e * 13 + 10 + j] = ball.w[j]; }
+    if (J->hits) J->hits[e] = ball.hits;
+  }
+}
+}  // namespace
+
+extern "C" int emu_packed_physics(const b200_model_t* model, const float* verts, const b200_cfg_t* cfg, int n, int n_steps, double* root,
+                                  double* dof_pos, double* dof_vel, const double* pd_tar, const double* ext, double* rb_out,
+                                  double* contact_out, double* ballio, int32_t* hits) {
+  DevBlob hb;
+  int slots_ok = 1;
+  if (build_dev_blob(model, hb, &slots_ok) != 0 || !slots_ok || model->nb > B200_MAX_BODIES_PK) return -1;
+  std::vector<float> soa((size_t)model->nb * model->vmax * 3 + 16, 0.0f);
+  float* sv = soa.data();
+  while ((uintptr_t)sv % 16) sv++;   // contact_hull reads the vertices with 128-bit loads
+  verts_to_soa(model, verts, sv);
+  Job J{&hb, sv, cfg, n, n_steps, root, dof_pos, dof_vel, pd_tar, ext, rb_out, contact_out, ballio, hits};
+  std::vector<double> rec((size_t)EPW * ENV_STRIDE + 2, 0.0);
+  double* wrec = rec.data();
+  while ((uintptr_t)wrec % 16) wrec++;
+  for (int64_t eb = 0; eb < n; eb += EPW) {
+    EmuWarp w;
+    std::vector<std::thread> th;
+    for (int lane = 0; lane < 32; lane++) th.emplace_back(lane_main, &w, lane, &J, eb, wrec);
+    for (auto& t : th) t.join();
+  }
+  return 0;
+}

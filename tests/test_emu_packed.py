@@ -1,0 +1,93 @@
+"""The packed articulated step executed on the CPU, lane by lane (tests/emu: 32 host threads per warp, __syncwarp = barrier,
+the very device code of csrc/packed*.cuh compiled as host C++, float64) vs the float64 restatement oracle/physics_ref.c.
+Same check as tests/test_gpu_parity.py::test_physics_f64_matches_oracle, but it needs no GPU: a change to the lane mapping of the
+kernel is debugged here first."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+from helpers import rand_quat  # noqa: E402
+
+from oracle import physics_ref  # noqa: E402
+from vid2player3d_b200 import abi, model_compiler  # noqa: E402
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def emu_step(variant, ms, verts, cfg, root, q, qd, tar, ext, n_steps=1, ball=None, hits=None):
+    import build as emu_build
+    lib = C.CDLL(emu_build.build(variant))
+    n = root.shape[0]
+    rb = np.zeros((n, ms.nb, 13))
+    cf = np.zeros((n, ms.nb, 3))
+    rc = lib.emu_packed_physics(C.byref(ms), _p(np.ascontiguousarray(verts, np.float32)), C.byref(cfg), C.c_int(n), C.c_int(n_steps),
+                                _p(root), _p(q), _p(qd), _p(tar), _p(ext), _p(rb), _p(cf), _p(ball), _p(hits))
+    assert rc == 0
+    return rb, cf
+
+
+def states(n, seed, contact):
+    rng = np.random.default_rng(seed)
+    root = np.zeros((n, 13))
+    root[:, 0:2] = rng.uniform(-3, 3, (n, 2))
+    root[:, 2] = rng.uniform(0.7, 1.1, n) if contact else rng.uniform(3, 5, n)
+    root[:, 3:7] = rand_quat(rng, n)
+    root[: n // 2, 3:7] = [0.5, 0.5, 0.5, 0.5]
+    root[:, 7:10] = rng.normal(0, 0.5, (n, 3))
+    root[:, 10:13] = rng.normal(0, 1.0, (n, 3))
+    q = rng.normal(0, 0.3, (n, 69))
+    qd = rng.normal(0, 1.5, (n, 69))
+    return root, q, qd, q + rng.normal(0, 0.2, (n, 69)), rng.normal(0, 30, (n, 6))
+
+
+VARIANTS = ["packed"] + (["packed3"] if os.path.exists(os.path.join(HERE, "..", "vid2player3d_b200", "csrc", "packed3.cuh")) else [])
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("contact", [False, True])
+def test_emulated_packed_step_matches_oracle(variant, contact):
+    mod = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    ms, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    cfg = abi.make_cfg(mod)
+    n = 6                                                        # one full warp of envs + a ragged one
+    root, q, qd, tar, ext = states(n, 11, contact)
+    for steps, tol in ((1, 1e-9), (4, 1e-7)):
+        r1, q1, v1 = root.copy(), q.copy(), qd.copy()
+        rb1, cf1 = emu_step(variant, ms, verts, cfg, r1, q1, v1, tar.copy(), ext.copy(), steps)
+        r2, q2, v2 = root.copy(), q.copy(), qd.copy()
+        rb2, cf2 = physics_ref.control_step(ms, verts, cfg, r2, q2, v2, tar.copy(), ext.copy(), n_steps=steps)
+        for a, b, name, sc in ((r1, r2, "root", 1), (q1, q2, "dof_pos", 1), (v1, v2, "dof_vel", 1), (rb1, rb2, "rb", 1), (cf1, cf2, "contact", 1e3)):
+            np.testing.assert_allclose(a, b, rtol=0, atol=tol * sc, err_msg=f"{variant} {name} steps={steps}")
+    if contact:
+        assert np.abs(cf2).max() > 10.0
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_emulated_packed_step_with_racket_and_ball(variant):
+    mod = model_compiler.canonical_racket_last(model_compiler.load_compiled("smpl_mesh_humanoid_federer"))
+    ms, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    cfg = abi.make_cfg(mod, substeps=6, ball={}, task_mode=1, pd_mode=1)
+    n = 5
+    root, q, qd, tar, ext = states(n, 5, True)
+    rng = np.random.default_rng(2)
+    ball = np.zeros((n, 13))
+    ball[:, 0:3] = root[:, 0:3] + rng.normal(0, 0.6, (n, 3)) + [0, 0.5, 0.3]
+    ball[:, 2] = np.abs(ball[:, 2]) + 0.04
+    ball[:, 7:10] = rng.normal(0, 8, (n, 3))
+    ball[:, 10:13] = rng.normal(0, 40, (n, 3))
+    b1, b2 = ball.copy(), ball.copy()
+    h1, h2 = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    r1, q1, v1 = root.copy(), q.copy(), qd.copy()
+    rb1, _ = emu_step(variant, ms, verts, cfg, r1, q1, v1, tar.copy(), ext.copy(), 2, b1, h1)
+    r2, q2, v2 = root.copy(), q.copy(), qd.copy()
+    rb2, _ = physics_ref.control_step(ms, verts, cfg, r2, q2, v2, tar.copy(), ext.copy(), n_steps=2, ball=b2, hits=h2)
+    np.testing.assert_allclose(b1, b2, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(q1, q2, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(rb1, rb2, rtol=0, atol=1e-5)

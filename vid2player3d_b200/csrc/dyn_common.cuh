@@ -1,0 +1,473 @@
+// dyn_common.cuh - device code shared by every form of the articulated step (b200env.cu: lane-per-body kernel; packed.cuh /
+// packed3.cuh: envs packed into a warp) and by the offline ball generators: constant-block layout, small math, per-lane state,
+// the tennis-ball model, ground contact of a convex hull.  Plain templated C++ with __device__ qualifiers only - it also compiles
+// as host code under tests/emu/cuda_compat.h, which is how the packed kernels are checked lane by lane on the CPU
+// (tests/emu/emu_packed.cpp runs one host thread per lane, __syncwarp() = a barrier).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/b200env.h"
+
+#ifndef FULL
+#define FULL 0xffffffffu
+#endif
+#define MAX_CHILD 4
+#define MAX_LEVELS 16
+// ------------------------------------------------------------------------------------------
+// device-side constant block: header | tree tables | hull vertices   (all 16-byte multiples)
+#define PK_SLOTS 8
+struct DevTree {
+  int32_t child[B200_MAX_BODIES][MAX_CHILD];  // dynamic (non-welded) children, -1 padded
+  int32_t maxch[MAX_LEVELS];                  // max #children over the bodies of each depth
+  // packed (4 envs / warp) variant: the s-th body of every tree depth, and each body's rank among its siblings
+  int32_t lvl_all[MAX_LEVELS][PK_SLOTS];      // all bodies of the depth (kinematics), -1 padded
+  int32_t lvl_dyn[MAX_LEVELS][PK_SLOTS];      // non-welded bodies of the depth (dynamics), -1 padded
+  int32_t child_rank[B200_MAX_BODIES];
+  int32_t rix[B200_MAX_BODIES];               // record index of a body in the packed kernel's shared-memory layout = breadth-first rank
+};
+struct DevBlob {
+  b200_model_t m;
+  DevTree t;
+  // float verts[nb][3][vmax] follows (SoA per body: x | y | z, see contact_hull)
+};
+static_assert(sizeof(b200_model_t) % 16 == 0, "model block must be a 16-byte multiple for the bulk copy");
+static_assert(sizeof(DevBlob) % 16 == 0, "blob header must be a 16-byte multiple");
+
+// host side: tree tables of a model (used by b200env_create and by the CPU lane emulator).  Returns 0, -1 (bodies not in
+// topological order) or -2 (too many children); *slots_ok = 0 when a tree depth has more bodies than the packed kernels have slots.
+static inline int build_dev_blob(const b200_model_t* model, DevBlob& hb, int* slots_ok) {
+  memset(&hb, 0, sizeof(hb));
+  hb.m = *model;
+  *slots_ok = 1;
+  for (int b = 0; b < B200_MAX_BODIES; b++)
+    for (int c = 0; c < MAX_CHILD; c++) hb.t.child[b][c] = -1;
+  int cnt[B200_MAX_BODIES] = {0};
+  for (int b = 1; b < model->nb; b++) {
+    if (model->fixed[b]) continue;
+    int p = model->parent[b];
+    if (p < 0 || p >= b) return -1;
+    if (cnt[p] >= MAX_CHILD) return -2;
+    hb.t.child[p][cnt[p]++] = b;
+  }
+  for (int b = 0; b < model->nb; b++)
+    if (cnt[b] > hb.t.maxch[model->depth[b]]) hb.t.maxch[model->depth[b]] = cnt[b];
+  int na[MAX_LEVELS] = {0}, ndy[MAX_LEVELS] = {0}, rk[B200_MAX_BODIES] = {0};
+  for (int d = 0; d < MAX_LEVELS; d++)
+    for (int k = 0; k < PK_SLOTS; k++) { hb.t.lvl_all[d][k] = -1; hb.t.lvl_dyn[d][k] = -1; }
+  for (int b = 0; b < model->nb; b++) {
+    const int d = model->depth[b];
+    if (na[d] >= PK_SLOTS) { *slots_ok = 0; continue; }
+    hb.t.lvl_all[d][na[d]++] = b;
+    if (!model->fixed[b]) {
+      hb.t.lvl_dyn[d][ndy[d]++] = b;
+      if (b > 0) hb.t.child_rank[b] = rk[model->parent[b]]++;
+    }
+  }
+  int next = 0;   // breadth-first record order (packed.cuh: neighbouring lanes of a tree depth -> neighbouring records)
+  for (int d = 0; d < MAX_LEVELS; d++)
+    for (int b = 0; b < model->nb; b++)
+      if (model->depth[b] == d) hb.t.rix[b] = next++;
+  return 0;
+}
+// hull vertices AoS [nb][vmax][3] (ABI) -> SoA [nb][3][vmax] (what contact_hull reads with 128-bit loads); dst zero-initialised
+static inline void verts_to_soa(const b200_model_t* model, const float* verts, float* soa) {
+  for (int b = 0; b < model->nb; b++)
+    for (int k = 0; k < model->nverts[b]; k++)
+      for (int a = 0; a < 3; a++) soa[((size_t)b * 3 + a) * model->vmax + k] = verts[((size_t)b * model->vmax + k) * 3 + a];
+}
+
+// ------------------------------------------------------------------------------------------
+// small math (templated on float / double)
+template <typename T> __device__ __forceinline__ T shfl(T v, int src) { return __shfl_sync(FULL, v, src); }
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+// fast reciprocal / rsqrt for the float path (MUFU, ~2 ulp); exact for the double (test) path
+__device__ __forceinline__ float rcp_(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
+__device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
+__device__ __forceinline__ float sqrt_(float x) { return x * rsqrtf(fmaxf(x, 1e-37f)); }
+__device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+template <typename T> __device__ __forceinline__ void cross3(const T* a, const T* b, T* o) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+template <typename T> __device__ __forceinline__ void qmul(const T* a, const T* b, T* o) {
+  T x1 = a[0], y1 = a[1], z1 = a[2], w1 = a[3], x2 = b[0], y2 = b[1], z2 = b[2], w2 = b[3];
+  o[0] = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
+  o[1] = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
+  o[2] = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
+  o[3] = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
+}
+template <typename T> __device__ __forceinline__ void qnormalize(T* q) {
+  T n = rsqrt_(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
+}
+// rotate v by unit quaternion q:  v + 2 w (qv x v) + 2 qv x (qv x v)
+template <typename T> __device__ __forceinline__ void qrot(const T* q, const T* v, T* o) {
+  T t[3], u[3];
+  cross3(q, v, t);
+  t[0] *= T(2); t[1] *= T(2); t[2] *= T(2);
+  cross3(q, t, u);
+  o[0] = v[0] + q[3] * t[0] + u[0];
+  o[1] = v[1] + q[3] * t[1] + u[1];
+  o[2] = v[2] + q[3] * t[2] + u[2];
+}
+template <typename T> __device__ __forceinline__ void qmat(const T* q, T* R) {  // row-major 3x3
+  T x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+}
+template <typename T> __device__ __forceinline__ void mv3(const T* R, const T* v, T* o) {
+  T a = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  T b = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  T c = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+template <typename T> __device__ __forceinline__ void mtv3(const T* R, const T* v, T* o) {
+  T a = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+  T b = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+  T c = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+// rotation vector -> quaternion (exact exponential)
+template <typename T> __device__ __forceinline__ void qexp(const T* v, T* q) {
+  T a2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  T a = sqrt(a2), s;
+  if (a < T(1e-6)) s = T(0.5) - a2 / T(48); else s = sin(T(0.5) * a) / a;
+  q[0] = s * v[0]; q[1] = s * v[1]; q[2] = s * v[2]; q[3] = cos(T(0.5) * a);
+}
+// exponential for the per-substep increments (|v| = h*|omega| <= h*max_ang_vel < 1 rad): even-power series,
+// truncation error < 2e-9 for |v| <= 2; the double path keeps sin/cos
+__device__ __forceinline__ void qexp_small(const float* v, float* q) {
+  const float a2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  if (a2 > 4.0f) { qexp(v, q); return; }
+  const float s = 0.5f + a2 * (-1.0f / 48.0f + a2 * (1.0f / 3840.0f + a2 * (-1.0f / 645120.0f + a2 * (1.0f / 185794560.0f))));
+  const float c = 1.0f + a2 * (-0.125f + a2 * (1.0f / 384.0f + a2 * (-1.0f / 46080.0f + a2 * (1.0f / 10321920.0f + a2 * (-1.0f / 3715891200.0f)))));
+  q[0] = s * v[0]; q[1] = s * v[1]; q[2] = s * v[2]; q[3] = c;
+}
+__device__ __forceinline__ void qexp_small(const double* v, double* q) { qexp(v, q); }
+// quaternion -> rotation vector, angle in [0, pi]
+template <typename T> __device__ __forceinline__ void qlog(const T* qi, T* v) {
+  T sg = qi[3] < T(0) ? T(-1) : T(1);
+  T x = sg * qi[0], y = sg * qi[1], z = sg * qi[2], w = sg * qi[3];
+  T s2 = x * x + y * y + z * z;
+  T s = sqrt_(s2), f;
+  if (s < T(1e-6)) f = T(2) + s2 * T(1.0 / 3.0); else f = T(2) * atan2(s, w) * rcp_(s);
+  v[0] = f * x; v[1] = f * y; v[2] = f * z;
+}
+// symmetric 3x3 stored as [xx, yy, zz, xy, xz, yz]
+template <typename T> __device__ __forceinline__ void sym_mv(const T* S, const T* v, T* o) {
+  T a = S[0] * v[0] + S[3] * v[1] + S[4] * v[2];
+  T b = S[3] * v[0] + S[1] * v[1] + S[5] * v[2];
+  T c = S[4] * v[0] + S[5] * v[1] + S[2] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+template <typename T> __device__ __forceinline__ void sym_inv(const T* S, T* O) {
+  T c00 = S[1] * S[2] - S[5] * S[5];
+  T c01 = S[5] * S[4] - S[3] * S[2];
+  T c02 = S[3] * S[5] - S[1] * S[4];
+  T det = S[0] * c00 + S[3] * c01 + S[4] * c02;
+  T id = rcp_(det);
+  O[0] = c00 * id;
+  O[1] = (S[0] * S[2] - S[4] * S[4]) * id;
+  O[2] = (S[0] * S[1] - S[3] * S[3]) * id;
+  O[3] = c01 * id;
+  O[4] = c02 * id;
+  O[5] = (S[3] * S[4] - S[0] * S[5]) * id;
+}
+// full 3x3 (row-major) from symmetric
+template <typename T> __device__ __forceinline__ void sym_full(const T* S, T* F) {
+  F[0] = S[0]; F[1] = S[3]; F[2] = S[4];
+  F[3] = S[3]; F[4] = S[1]; F[5] = S[5];
+  F[6] = S[4]; F[7] = S[5]; F[8] = S[2];
+}
+
+// ------------------------------------------------------------------------------------------
+// per-lane (per-body) state
+template <typename T> struct Lane {
+  T Q[4], p[3], w[3], v[3];  // world pose and velocity of the body origin
+  T qj[4], wt[3];            // joint rotation (child in parent) and joint velocity (child frame)
+};
+struct LaneConst {
+  int par, depth, dof0;
+  int rix;           // packed kernels: the body's record index (DevTree::rix); set by the kernel after lane_const()
+  bool active, dyn;  // dyn: takes part in the dynamics (not welded)
+};
+
+template <typename T> struct PhysCfg {
+  T h, gz, kn, cn, mu, vs, damp, wmax, limk, limc;
+  int substeps, cfi;
+  // tennis ball (vid2player): lane BALL_LANE integrates it next to the humanoid
+  int has_ball, racket_body, wrist_body;
+  T bm, bI, bR, spin_scale, eg, mug, er, mur, vth, hc[3], hh, hr, hq[4];
+};
+#ifndef ABL
+#define ABL 0   // tools/ablate.sh: 1 no physics, 2 epilogue = state write-back only, 3 no reward block, 4 no MoCap sample / targets, 5 no obs
+#endif
+#define BALL_LANE 31
+// ball state held by lane BALL_LANE (float64 restatement: oracle/physics_ref.c::ball_substep)
+template <typename T> struct Ball {
+  T p[3], v[3], w[3];   // position, linear and angular velocity (world)
+  T fa[3];              // aerodynamic force, refreshed once per sim step like the reference (humanoid_smpl_im_mvae.py:752-756)
+  T rF[3], rX[3];       // reaction force on the racket from the last impact (applied to the wrist link next substep) and its point
+  int hits;             // racket impacts so far
+  int has_bounce, bounce_now;
+  T bpos[3];
+};
+template <typename T> __device__ __forceinline__ PhysCfg<T> make_phys_cfg(const b200_cfg_t& c) {
+  PhysCfg<T> p;
+  p.h = T(c.sim_dt) / T(c.substeps);
+  p.gz = T(c.gravity_z); p.kn = T(c.contact_kn); p.cn = T(c.contact_cn); p.mu = T(c.friction_mu);
+  p.vs = T(c.friction_vs); p.damp = T(1) - p.h * T(c.ang_damping); p.wmax = T(c.max_ang_vel);
+  p.limk = T(c.limit_k); p.limc = T(c.limit_c);
+  p.substeps = c.substeps; p.cfi = c.control_freq_inv;
+  p.has_ball = c.has_ball; p.racket_body = c.racket_body; p.wrist_body = 0;
+  p.bm = T(c.ball_mass); p.bI = T(c.ball_inertia); p.bR = T(c.ball_radius); p.spin_scale = T(c.spin_scale);
+  p.eg = T(c.ball_e_ground); p.mug = T(c.ball_mu_ground); p.er = T(c.ball_e_racket); p.mur = T(c.ball_mu_racket);
+  p.vth = T(c.bounce_threshold_velocity);
+  p.hc[0] = T(c.racket_head_center[0]); p.hc[1] = T(c.racket_head_center[1]); p.hc[2] = T(c.racket_head_center[2]);
+  p.hh = T(c.racket_head_halfthick); p.hr = T(c.racket_head_radius);
+#pragma unroll
+  for (int k = 0; k < 4; k++) p.hq[k] = T(c.racket_head_quat[k]);
+  return p;
+}
+
+// forward kinematics, level by level: fills Q,p,w,v (world) of every lane from the root state and
+// the joint state.  Optionally returns r = p - p_parent and the velocity-product terms zeta.
+#ifndef LEVEL_SYNC
+#define LEVEL_SYNC 0  // 1: CTA barrier at every tree level (keeps all warps of the CTA in the same code region: I-cache sharing)
+#endif
+template <typename T, bool WITH_ZETA>
+__device__ __forceinline__ void fk_pass(const b200_model_t& M, const LaneConst& lc, int lane, Lane<T>& L, T* r, T* zeta,
+                                        bool lsync = false) {
+  for (int d = 1; d <= M.max_depth; d++) {
+    if (LEVEL_SYNC && lsync) __syncthreads();
+    T pQ[4], pp[3], pw[3], pv[3];
+#pragma unroll
+    for (int k = 0; k < 4; k++) pQ[k] = shfl(L.Q[k], lc.par);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { pp[k] = shfl(L.p[k], lc.par); pw[k] = shfl(L.w[k], lc.par); pv[k] = shfl(L.v[k], lc.par); }
+    if (lc.active && lc.depth == d) {
+      T off[3] = {T(M.offset[lane][0]), T(M.offset[lane][1]), T(M.offset[lane][2])};
+      T rr[3], wxr[3];
+      qrot(pQ, off, rr);
+      cross3(pw, rr, wxr);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { L.p[k] = pp[k] + rr[k]; L.v[k] = pv[k] + wxr[k]; }
+      if (WITH_ZETA) { r[0] = rr[0]; r[1] = rr[1]; r[2] = rr[2]; }
+      if (!lc.dyn) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) L.Q[k] = pQ[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) L.w[k] = pw[k];
+      } else {
+        qmul(pQ, L.qj, L.Q);
+        qnormalize(L.Q);
+        T wj[3];
+        qrot(L.Q, L.wt, wj);
+#pragma unroll
+        for (int k = 0; k < 3; k++) L.w[k] = pw[k] + wj[k];
+        if (WITH_ZETA) { cross3(pw, wj, zeta); cross3(pw, wxr, zeta + 3); }
+      }
+    }
+  }
+}
+
+
+// drag + Magnus lift on the ball (apply_external_force_to_ball, humanoid_smpl_im_mvae.py:711-739; constants tennis_ball.py:15-37)
+template <typename T> __device__ __forceinline__ void ball_aero(const T* vel, const T* angvel, T spin_scale, T* force) {
+  const T KF = T(0.0019462794807519486), CD = T(0.55);
+  T vs = sqrt_(vel[0] * vel[0] + vel[1] * vel[1] + vel[2] * vel[2]);
+  if (vs == T(0)) vs += T(1);
+  const T iv = rcp_(vs);
+  const T vn[3] = {vel[0] * iv, vel[1] * iv, vel[2] * iv};
+  const T vt[3] = {-vn[1], vn[0], T(0)};  // vn x (0,0,-1)
+  const T vspin = sqrt_(angvel[0] * angvel[0] + angvel[1] * angvel[1] + angvel[2] * angvel[2]) * T(0.15915494309189535);
+  T cl = rcp_(T(2) + fabs(vs * rcp_(vspin * spin_scale + T(1e-6))));
+  cl = vspin > T(0) ? -cl : cl;
+  const T cx = vt[1] * vn[2] - vt[2] * vn[1], cy = vt[2] * vn[0] - vt[0] * vn[2], cz = vt[0] * vn[1] - vt[1] * vn[0];
+  const T kd = -KF * CD * vs, kl = -KF * cl * vs * vs;
+  force[0] = kd * vel[0] + kl * cx; force[1] = kd * vel[1] + kl * cy; force[2] = kd * vel[2] + kl * cz;
+}
+// impulse on a sphere at contact normal n (pointing from the obstacle into the ball), obstacle point velocity vo:
+// restitution e on the normal part, Coulomb friction mu capped at the sticking impulse (spin coupled through I).
+template <typename T>
+__device__ __forceinline__ void ball_impulse(const PhysCfg<T>& c, Ball<T>& B, const T* n, const T* vo, T e, T mu, T* J) {
+  // contact point on the ball: -R n ; u = v + w x (-R n) - vo
+  T rn[3] = {-c.bR * n[0], -c.bR * n[1], -c.bR * n[2]}, wxr[3];
+  cross3(B.w, rn, wxr);
+  T u[3] = {B.v[0] + wxr[0] - vo[0], B.v[1] + wxr[1] - vo[1], B.v[2] + wxr[2] - vo[2]};
+  const T un = u[0] * n[0] + u[1] * n[1] + u[2] * n[2];
+  J[0] = J[1] = J[2] = T(0);
+  if (!(un < T(0))) return;
+  const T jn = (-un > c.vth ? (T(1) + e) : T(1)) * (-un) * c.bm;
+  T ut[3] = {u[0] - un * n[0], u[1] - un * n[1], u[2] - un * n[2]};
+  const T utn = sqrt_(ut[0] * ut[0] + ut[1] * ut[1] + ut[2] * ut[2]);
+  T jt = T(0);
+  if (utn > T(1e-9)) {
+    const T stick = c.bm * utn * rcp_(T(1) + c.bm * c.bR * c.bR * rcp_(c.bI));
+    jt = mu * jn < stick ? mu * jn : stick;
+    const T iu = rcp_(utn);
+    ut[0] *= iu; ut[1] *= iu; ut[2] *= iu;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) J[k] = jn * n[k] - jt * ut[k];
+  T rxJ[3];
+  cross3(rn, J, rxJ);
+  const T im = rcp_(c.bm), iI = rcp_(c.bI);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { B.v[k] += J[k] * im; B.w[k] += rxJ[k] * iI; }
+}
+// one substep of the ball: gravity + aero, swept test against the racket head (a cylinder of half thickness hh and
+// radius hr centred at hc in the racket frame; pose/velocity of the racket at the START of the substep), ground bounce.
+template <typename T>
+__device__ __forceinline__ void ball_substep(const PhysCfg<T>& c, Ball<T>& B, bool has_racket, const T* rQ, const T* rp, const T* rv, const T* rw) {
+  const T im = rcp_(c.bm);
+  B.v[0] += c.h * B.fa[0] * im; B.v[1] += c.h * B.fa[1] * im; B.v[2] += c.h * (c.gz + B.fa[2] * im);
+  B.rF[0] = B.rF[1] = B.rF[2] = T(0);
+  T thit = T(-1), nl = T(0);
+  if (has_racket) {
+    T d[3] = {B.p[0] - rp[0], B.p[1] - rp[1], B.p[2] - rp[2]}, wxd[3];
+    cross3(rw, d, wxd);
+    T vrel_w[3] = {B.v[0] - rv[0] - wxd[0], B.v[1] - rv[1] - wxd[1], B.v[2] - rv[2] - wxd[2]};
+    T hQ[4];
+    qmul(rQ, c.hq, hQ);   // head frame in the world (string-bed normal = its +y)
+    T cq[4] = {-hQ[0], -hQ[1], -hQ[2], hQ[3]}, d0[3], vr[3];
+    qrot(cq, d, d0);
+    qrot(cq, vrel_w, vr);
+    d0[0] -= c.hc[0]; d0[1] -= c.hc[1]; d0[2] -= c.hc[2];
+    const T H = c.hh + c.bR, Rad = c.hr + c.bR;
+    if (fabs(d0[1]) < H) {
+      if (d0[0] * d0[0] + d0[2] * d0[2] < Rad * Rad) { thit = T(0); nl = d0[1] >= T(0) ? T(1) : T(-1); }
+    } else {
+      T t = T(-1);
+      if (d0[1] >= H && vr[1] < T(0)) t = (d0[1] - H) * rcp_(-vr[1]);
+      else if (d0[1] <= -H && vr[1] > T(0)) t = (-H - d0[1]) * rcp_(vr[1]);
+      if (t >= T(0) && t <= c.h) {
+        const T hx = d0[0] + t * vr[0], hz = d0[2] + t * vr[2];
+        if (hx * hx + hz * hz < Rad * Rad) { thit = t; nl = d0[1] >= T(0) ? T(1) : T(-1); }
+      }
+    }
+    if (thit >= T(0)) {
+      const T ny[3] = {T(0), nl, T(0)};
+      T n[3], J[3], vo[3];
+      qrot(hQ, ny, n);
+      T xc[3] = {B.p[0] + thit * B.v[0] - c.bR * n[0], B.p[1] + thit * B.v[1] - c.bR * n[1], B.p[2] + thit * B.v[2] - c.bR * n[2]};
+      T dx[3] = {xc[0] - rp[0], xc[1] - rp[1], xc[2] - rp[2]}, wxx[3];
+      cross3(rw, dx, wxx);
+      vo[0] = rv[0] + wxx[0]; vo[1] = rv[1] + wxx[1]; vo[2] = rv[2] + wxx[2];
+      const T vb[3] = {B.v[0], B.v[1], B.v[2]};
+      ball_impulse(c, B, n, vo, c.er, c.mur, J);
+      if (J[0] != T(0) || J[1] != T(0) || J[2] != T(0)) {
+        const T ih = rcp_(c.h);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { B.rF[k] = -J[k] * ih; B.rX[k] = xc[k]; B.p[k] += thit * vb[k] + (c.h - thit) * B.v[k]; }
+        B.hits++;
+      } else {
+        thit = T(-1);
+      }
+    }
+  }
+  if (thit < T(0)) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) B.p[k] += c.h * B.v[k];
+  }
+  if (B.p[2] < c.bR && B.v[2] < T(0)) {  // ground
+    const T n[3] = {T(0), T(0), T(1)}, vo[3] = {T(0), T(0), T(0)};
+    T J[3];
+    ball_impulse(c, B, n, vo, c.eg, c.mug, J);
+    B.p[2] = c.bR;
+  }
+}
+
+// One substep of length h (float64 restatement: oracle/physics_ref.c::substep).
+// Ground contact of one body's convex-hull vertices against z = 0, implicit in the velocity.
+// vb: the body's vertices in the blob, SoA  x[vmax] | y[vmax] | z[vmax]  (vmax % 4 == 0, 16-byte aligned, padding = 0).
+// Pass 1 tests four vertices per iteration (3 LDS.128, independent FMAs) and records the penetrating ones in a bit mask;
+// pass 2 visits only those, in ascending vertex order - the accumulation order (and therefore every bit of the result)
+// is the same as a plain loop over k.  With most vertices above the ground the serial per-vertex test was ~40 % of the
+// physics time of fallen humanoids (tools/ablate.sh).
+template <typename T>
+__device__ __forceinline__ void contact_hull(const float* __restrict__ vb, int vmax, int nv, const PhysCfg<T>& c, const T* R, const T* p,
+                                             const T* v, const T* w, T* A, T* Bm, T* C, T* bn, T* bf, T* cf) {
+  unsigned long long mask = 0ull;
+  const T pz = p[2];
+  for (int k0 = 0; k0 < nv; k0 += 4) {
+    const float4 X = *reinterpret_cast<const float4*>(vb + k0);
+    const float4 Y = *reinterpret_cast<const float4*>(vb + vmax + k0);
+    const float4 Z = *reinterpret_cast<const float4*>(vb + 2 * vmax + k0);
+    const T r0 = R[6] * T(X.x) + R[7] * T(Y.x) + R[8] * T(Z.x);
+    const T r1 = R[6] * T(X.y) + R[7] * T(Y.y) + R[8] * T(Z.y);
+    const T r2 = R[6] * T(X.z) + R[7] * T(Y.z) + R[8] * T(Z.z);
+    const T r3 = R[6] * T(X.w) + R[7] * T(Y.w) + R[8] * T(Z.w);
+    const unsigned m = ((-(pz + r0) > T(0)) ? 1u : 0u) | ((-(pz + r1) > T(0)) ? 2u : 0u) | ((-(pz + r2) > T(0)) ? 4u : 0u) |
+                       ((-(pz + r3) > T(0)) ? 8u : 0u);
+    mask |= (unsigned long long)m << k0;
+  }
+  if (nv < 64) mask &= (1ull << nv) - 1ull;   // padding vertices (zeros) never count
+  const T kimp = c.h * c.cn + c.h * c.h * c.kn;
+  while (mask) {
+    const int k = __ffsll((long long)mask) - 1;
+    mask &= mask - 1ull;
+    const T vl[3] = {T(vb[k]), T(vb[vmax + k]), T(vb[2 * vmax + k])};
+    const T rz = R[6] * vl[0] + R[7] * vl[1] + R[8] * vl[2];
+    const T pen = -(pz + rz);
+    if (!(pen > T(0))) continue;   // (re-tested: the two passes may contract their FMAs differently)
+    const T rx = R[0] * vl[0] + R[1] * vl[1] + R[2] * vl[2];
+    const T ry = R[3] * vl[0] + R[4] * vl[1] + R[5] * vl[2];
+    const T ux = v[0] + w[1] * rz - w[2] * ry;
+    const T uy = v[1] + w[2] * rx - w[0] * rz;
+    const T uz = v[2] + w[0] * ry - w[1] * rx;
+    const T fn0 = c.kn * pen - c.cn * uz;
+    if (!(fn0 > T(0))) continue;
+    const T ut = sqrt_(ux * ux + uy * uy);
+    const T ct = c.mu * fn0 * rcp_(ut > c.vs ? ut : c.vs);
+    const T hct = c.h * ct;
+    // Jn = [(ry, -rx, 0); (0,0,1)], Jx = [(0, rz, -ry); (1,0,0)], Jy = [(-rz, 0, rx); (0,1,0)]
+    A[0] += kimp * ry * ry + hct * rz * rz;
+    A[1] += kimp * rx * rx + hct * rz * rz;
+    A[2] += hct * (ry * ry + rx * rx);
+    A[3] += -kimp * ry * rx;
+    A[4] += -hct * rz * rx;
+    A[5] += -hct * rz * ry;
+    Bm[2] += kimp * ry;   // (Jn_ang)(Jn_lin)^T : column z
+    Bm[5] += -kimp * rx;
+    Bm[3] += hct * rz;    // Jx: ang (0,rz,-ry) x lin ex -> column x
+    Bm[6] += -hct * ry;
+    Bm[1] += -hct * rz;   // Jy: ang (-rz,0,rx) x lin ey -> column y
+    Bm[7] += hct * rx;
+    C[0] += hct; C[1] += hct; C[2] += kimp;
+    // wrench W = Jn fn0 - ct (Jx ux + Jy uy);  b -= W
+    const T fx = -ct * ux, fy = -ct * uy;
+    bn[0] -= ry * fn0 - rz * fy;
+    bn[1] -= -rx * fn0 + rz * fx;
+    bn[2] -= -ry * fx + rx * fy;
+    bf[0] -= fx; bf[1] -= fy; bf[2] -= fn0;
+    cf[0] += fx; cf[1] += fy; cf[2] += fn0;
+  }
+}
+
+
+template <typename T> __device__ __forceinline__ void ball_clear(Ball<T>& b) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) { b.p[k] = 0; b.v[k] = 0; b.w[k] = 0; b.fa[k] = 0; b.rF[k] = 0; b.rX[k] = 0; b.bpos[k] = 0; }
+  b.hits = 0; b.has_bounce = 0; b.bounce_now = 0;
+}
+
+__device__ __forceinline__ LaneConst lane_const(const b200_model_t& M, int lane) {
+  LaneConst lc;
+  lc.active = lane < M.nb;
+  lc.par = lc.active ? (M.parent[lane] < 0 ? 0 : M.parent[lane]) : 0;
+  lc.depth = lc.active ? M.depth[lane] : -1;
+  lc.dof0 = lc.active ? M.dof_of_body[lane] : -1;
+  lc.dyn = lc.active && !M.fixed[lane];
+  lc.rix = lane;
+  return lc;
+}
+

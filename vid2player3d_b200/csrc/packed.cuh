@@ -10,6 +10,7 @@
 
 #define EPW 4     // envs per warp
 #define SLOTS 8   // lanes per env
+#define PK_LANES_PER_ENV SLOTS
 // Record layout (element offsets).  Records are 16-byte aligned (REC % 4 == 0, ENV_STRIDE % 4 == 0) and the fields that are
 // read / written together form runs that start on 4-float boundaries, so that a run moves with LDS.128 / STS.128 instead of one
 // 32-bit access per float (ncu r1g: 21 M of the 97 M warp instructions of a launch were scalar LDS / STS).  Body b lives in
@@ -479,6 +480,60 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
           }
         }
         __syncwarp();
+      }
+    }
+  }
+}
+
+// state of one env between the lane-per-body prologue / epilogue (lane = body) and the records
+template <typename T> __device__ __forceinline__ void pk_store_state(T* env, const LaneConst& lc, int lane, const Lane<T>& L, const T* pd,
+                                                                     const T* extF, const T* extT) {
+  if (lc.active) {
+    T* rec = env + lc.rix * REC;
+    if (lane == 0) {
+      T o[13];
+#pragma unroll
+      for (int k = 0; k < 4; k++) o[k] = L.Q[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { o[4 + k] = L.p[k]; o[7 + k] = L.w[k]; o[10 + k] = L.v[k]; }
+      str<R_Q, 13>(rec, o);
+    } else if (lc.dyn) {
+      T o[7];
+#pragma unroll
+      for (int k = 0; k < 4; k++) o[k] = L.qj[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) o[4 + k] = pd[k];
+      str<R_QJ, 7>(rec, o);
+      str<R_WT, 3>(rec, L.wt);
+    }
+  }
+  if (lane == 0) {
+    T* ext = env + ENV_EXT;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { ext[k] = extF[k]; ext[3 + k] = extT[k]; ext[6 + k] = T(0); ext[9 + k] = T(0); }
+  }
+}
+template <typename T> __device__ __forceinline__ void pk_load_state(const T* env, const LaneConst& lc, int lane, Lane<T>& L, T* cf) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) { L.Q[k] = 0; L.qj[k] = 0; }
+  L.Q[3] = 1; L.qj[3] = 1;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { L.p[k] = 0; L.w[k] = 0; L.v[k] = 0; L.wt[k] = 0; cf[k] = 0; }
+  if (lc.active) {
+    const T* rec = env + lc.rix * REC;
+    T o[16];
+    ldr<R_Q, 16>(rec, o);
+#pragma unroll
+    for (int k = 0; k < 4; k++) L.Q[k] = o[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { L.p[k] = o[4 + k]; L.w[k] = o[7 + k]; L.v[k] = o[10 + k]; }
+    if (lc.dyn) {
+      cf[0] = rec[R_CFX];
+      ldr<R_CFY, 2>(rec, cf + 1);
+      if (lane > 0) {
+        ldr<R_QJ, 4>(rec, L.qj);
+#pragma unroll
+        for (int k = 0; k < 3; k++) L.wt[k] = o[13 + k];
       }
     }
   }
