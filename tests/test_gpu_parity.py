@@ -433,3 +433,30 @@ def test_motion_context_matches_torch_composition(model, small_lib):
         assert torch.equal(task.context_feat[env_ids], feat) and torch.equal(task.context_mask[env_ids], mask)
         assert feat.shape[1:] == (48, 378) and mask.any() and torch.isfinite(feat).all()
     assert not task.context_mask.all()        # windows reaching past the end of short motions are masked out
+
+
+def test_vec_task_graph_step_equals_eager_step(model, small_lib):
+    """VecTaskPython.enable_cuda_graph: the captured step (clamp -> 3 launches -> clamp) leaves the same buffers as the eager one"""
+    from vid2player3d_b200.tasks import VecTaskPythonWrapper
+    outs = []
+    for use_graph in (False, True):
+        torch.manual_seed(5)
+        task = make_task(96, small_lib)
+        vec = VecTaskPythonWrapper(task, task.device, 5.0, 1.0)
+        g = torch.Generator(device=task.device).manual_seed(9)
+        acts = [torch.rand(96, task.num_actions, device=task.device, generator=g) * 4 - 2 for _ in range(6)]   # beyond the clip range
+        buf = torch.zeros_like(acts[0])
+        if use_graph:
+            assert vec.enable_cuda_graph(buf) is buf      # its warm-up steps the envs: enable before the reset that starts a rollout
+        vec.reset()
+        rec = []
+        for i, a in enumerate(acts):
+            buf.copy_(a)
+            obs, rew, reset, extras = vec.step(buf if i % 2 == 0 else a)     # the static buffer and a foreign tensor
+            rec.append((obs.clone(), rew.clone(), reset.clone(), extras["terminate"].clone()))
+            if i == 3:
+                vec.reset(torch.arange(0, 96, 3, device=task.device))
+        outs.append(rec)
+    for (o1, r1, d1, t1), (o2, r2, d2, t2) in zip(*outs):
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(t1, t2)
+    assert float(outs[0][-1][0].abs().max()) <= 5.0
