@@ -57,6 +57,8 @@ typedef struct b200v2p_ctrl {
   int32_t obs_only; /* 1: refresh obs_buf only (the _compute_observations call of _reset_envs :200-201), touch nothing else */
   int32_t dual;     /* 1: reset FSM of PhysicsMVAEControllerDual._compute_reset (env/tasks/physics_mvae_controller_dual.py:92-120):
                        envs (2k, 2k+1) are opponents; reset_buf is only ever SET, terminate_buf is not written */
+  int32_t use_history; /* cfg use_history_ball_obs (:348-351): the task observation is the HISTORY of ball positions (ball_obs)
+                          instead of the future trajectory window (ball_traj) */
   float scale_pos, scale_phase, scale_bounce_pos, scale_bounce_time, w_pos, w_ball_pos;
   float court_min[2], court_max[2];
   float est_params[15]; /* VEL_X, VEL_Y, VSPIN, TRAJ_X, TRAJ_Y ranges (lo, hi, step) */
@@ -74,6 +76,9 @@ typedef struct b200v2p_ctrl {
   float *est_bounce_pos, *est_bounce_time, *est_max_height, *distance;
   float *obs_buf, *rew_buf, *sub_rewards; /* sub_rewards [n,2] */
   int64_t *reset_buf, *terminate_buf;
+  float* ball_obs; /* [n, obs_traj_len, 3] _ball_obs (:65): rolled by one and appended with ball_pos at every observation (:345-346);
+                      in obs_only mode only for the envs whose reset masks are set (the reference refreshes those ids only).
+                      NULL = not kept (then use_history must be 0) */
 } b200v2p_ctrl_t;
 int b200v2p_controller_post(const b200v2p_ctrl_t* c, void* stream);
 
@@ -102,6 +107,8 @@ typedef struct b200v2p_treset {
   float *ball_pos, *ball_vel, *bounce_pos, *ball_traj, *est_bounce_pos, *est_bounce_time, *est_max_height, *target_bounce_pos;
   uint8_t *has_bounce, *has_contact, *bounce_in, *est_bounce_in;
   int64_t *tar_time, *tar_time_total, *tar_action, *num_reset_reaction, *swing_type_cycle;
+  float* ball_obs;       /* use_history_ball_obs (:213-214): rows of the reaction envs <- the new ball position repeated; NULL = off */
+  int32_t obs_traj_len, pad_;
 } b200v2p_treset_t;
 int b200v2p_task_reset(const b200v2p_treset_t* r, void* stream);
 

@@ -182,12 +182,30 @@ def update_state_from_sim(rbs, root_states, ball_states, prev_ball_vel, contact,
 
 
 # --------------------------------------------------------------------------- a14: high-level observation
-def controller_obs(rbs25, root_pos, root_vel, racket_normal, ball_traj, target_bounce_pos, obs_len, use_target=True):
-    """_compute_actor_obs (physics_mvae_controller.py:333-342) + _compute_task_obs (:344-360, future-trajectory variant)"""
+def roll_ball_obs(ball_obs, ball_pos, ids=None):
+    """_compute_task_obs :345-346 on the rows `ids` (None = all): the history shifts by one, the current ball position is appended"""
+    ids = np.arange(len(ball_obs)) if ids is None else np.asarray(ids)
+    out = ball_obs.copy()
+    out[ids] = np.roll(ball_obs[ids], -1, axis=1)
+    out[ids, -1] = ball_pos[ids]
+    return out
+
+
+def reset_ball_obs(ball_obs, ball_pos, ids):
+    """_reset_reaction_tasks :213-214 (use_history_ball_obs): the rows of the reaction envs <- the ball position repeated"""
+    out = ball_obs.copy()
+    out[np.asarray(ids)] = ball_pos[np.asarray(ids)][:, None, :]
+    return out
+
+
+def controller_obs(rbs25, root_pos, root_vel, racket_normal, ball_traj, target_bounce_pos, obs_len, use_target=True, ball_obs=None):
+    """_compute_actor_obs (physics_mvae_controller.py:333-342) + _compute_task_obs (:344-360); ball_obs (already rolled) selects the
+    use_history_ball_obs variant (:348-349), else the future-trajectory window"""
     N = rbs25.shape[0]
     actor = np.concatenate([root_pos, root_vel, (rbs25[:, 1:, 0:3] - root_pos[:, None]).reshape(N, 72),
                             quat_to_rot6d(rbs25[:, :24, 3:7].reshape(-1, 4)).reshape(N, 144), racket_normal], -1)
-    task = (ball_traj[:, :obs_len] - rbs25[:, 24, 0:3][:, None]).reshape(N, -1)
+    src = ball_traj[:, :obs_len] if ball_obs is None else ball_obs
+    task = (src - rbs25[:, 24, 0:3][:, None]).reshape(N, -1)
     if use_target:
         task = np.concatenate([task, target_bounce_pos[:, :2] - root_pos[:, :2]], -1)
     return np.concatenate([actor, task], -1)

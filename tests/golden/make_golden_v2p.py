@@ -313,6 +313,26 @@ def controller():
     rec.update(reset=c.reset_buf.clone(), terminate=c._terminate_buf.clone(), reset_reaction=c._reset_reaction_buf.clone(),
                reset_recovery=c._reset_recovery_buf.clone(), distance=c._distance.clone(),
                out_of_court=C.check_out_of_court(c._root_pos, c._court_min, c._court_max))
+    # ---- use_history_ball_obs (:213-214, :345-351): a reaction reset fills the history with the ball position, every observation
+    # rolls it by one and appends the current position; _compute_observations(ids) touches the listed rows only
+    c.cfg_v2p['use_history_ball_obs'] = True
+    c.cfg_v2p['reset_reaction_nframes'] = 70
+    c._num_reset_reaction = torch.zeros(N, dtype=torch.long)
+    c._mvae_player._swing_type_cycle = c._mvae_player._swing_type_cycle.clone()   # `rec` holds the recorded tensor itself
+    hist = dict(hist_in=c._ball_obs.clone(), hist_ball_pos0=player._ball_pos.clone())
+    ids = torch.tensor([1, 5, 9, 33])
+    c._reset_reaction_tasks(ids)
+    hist.update(hist_reset_ids=ids, hist_after_reset=c._ball_obs.clone(), hist_target_bounce_pos=c._target_bounce_pos.clone())
+    part = torch.tensor([0, 1, 2, 40, 41])
+    c._compute_observations(part)
+    hist.update(hist_part_ids=part, hist_after_partial=c._ball_obs.clone(), hist_obs_partial=c.obs_buf.clone())
+    for k in range(2):
+        player._ball_pos += 0.1 * (k + 1) * torch.randn(N, 3, generator=g)     # in place: the controller's _ball_pos is this tensor
+        c._compute_observations()
+        hist[f"hist_ball_pos{k + 1}"] = player._ball_pos.clone()
+        hist[f"hist_after_full{k + 1}"] = c._ball_obs.clone()
+        hist[f"hist_obs_full{k + 1}"] = c.obs_buf.clone()
+    rec.update(hist)
     npz("v2p_controller.npz", **rec)
 
 

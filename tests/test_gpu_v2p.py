@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from conftest import golden
+from helpers import SIM_PARAMS, v2p_cfg
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -122,6 +123,90 @@ def test_controller_post_golden(rtype):
             got = t[k].cpu().numpy()
             want = g[gk]
             assert np.array_equal(got.astype(np.int64), want.astype(np.int64)), k
+
+
+def test_controller_post_history_ball_obs():
+    """use_history_ball_obs through the fused post kernel: obs_only refresh of the masked rows, then two full steps (golden)"""
+    from vid2player3d_b200 import native_v2p as V
+    g = golden("v2p_controller.npz")
+    N = g["rbs"].shape[0]
+    z = lambda *s, dt=torch.float32: torch.zeros(*s, device=DEV, dtype=dt)  # noqa: E731
+    obs = T(g["hist_obs_partial"]).clone()
+    obs[torch.isnan(obs)] = 0
+    part = torch.tensor(g["hist_part_ids"], device=DEV)
+    rea, rec = z(N, dt=torch.bool), z(N, dt=torch.bool)
+    rea[part[:3]] = True
+    rec[part[3:]] = True
+    ball_pos = T(g["hist_ball_pos0"]).clone()
+    hist = T(g["hist_after_reset"]).clone()
+    t = dict(rigid_body_state=T(g["rbs"]), ball_states=T(g["ball_states"]), root_pos=T(g["p_root_pos"]), root_vel=T(g["p_root_vel"]),
+             racket_pos=T(g["p_racket_pos"]), racket_normal=T(g["p_racket_normal"]), ball_pos=ball_pos,
+             has_contact=T(g["p_has_racket_ball_contact"]), has_contact_now=T(g["p_has_racket_ball_contact_now"]),
+             has_bounce=T(g["p_has_bounce"]), has_bounce_now=T(g["p_has_bounce_now"]), bounce_pos=T(g["p_bounce_pos"]),
+             ball_traj=T(g["ball_traj"]), target_bounce_pos=T(g["hist_target_bounce_pos"]), phase=T(g["phase"]), swing_type=T(g["swing_type"]),
+             swing_type_cycle=T(g["swing_type_cycle"]), tar_action=T(g["tar_action"]), tar_time=T(g["tar_time"]),
+             tar_time_total=T(g["tar_time_total"]), progress_buf=T(g["progress"]), est_x=T(g["est_x"]), est_y=T(g["est_y"]),
+             bounce_in=z(N, dt=torch.bool), est_bounce_in=z(N, dt=torch.bool), reset_reaction=rea, reset_recovery=rec,
+             est_bounce_pos=z(N, 3), est_bounce_time=z(N), est_max_height=z(N), distance=z(N), obs_buf=obs, rew_buf=z(N), sub_rewards=z(N, 2),
+             reset_buf=z(N, dt=torch.long), terminate_buf=z(N, dt=torch.long), ball_obs=hist)
+    cfg = dict(n=N, bodies_per_env=25, ball_stride=13, racket_body=24, num_obs=257, obs_traj_len=10, use_target=1,
+               reward_type=V.REWARD_TYPES["return_w_estimate"], early_termination=1, max_episode_length=300, est_nx=60, est_ny=30, scale_pos=5.0,
+               scale_phase=10.0, scale_bounce_pos=0.05, scale_bounce_time=0.1, w_pos=0.5, w_ball_pos=0.5,
+               court_min=g["court_min"], court_max=g["court_max"], est_params=g["est_params"].reshape(-1), use_history=1, obs_only=1)
+    V.controller_post(cfg, t)          # the refresh of _reset_envs: only the rows whose reset masks are set
+    torch.cuda.synchronize()
+    assert np.array_equal(hist.cpu().numpy(), g["hist_after_partial"])
+    close(obs[part], g["hist_obs_partial"][g["hist_part_ids"]], 2e-6)
+    cfg["obs_only"] = 0
+    for k in (1, 2):
+        ball_pos.copy_(T(g[f"hist_ball_pos{k}"]))
+        V.controller_post(cfg, t)
+        torch.cuda.synchronize()
+        assert np.array_equal(hist.cpu().numpy(), g[f"hist_after_full{k}"])
+        close(obs, g[f"hist_obs_full{k}"], 2e-6)
+    with pytest.raises(RuntimeError, match="use_history needs"):
+        V.controller_post(cfg, dict(t, ball_obs=None))
+
+
+def test_controller_history_mode_end_to_end():
+    """PhysicsMVAEController with use_history_ball_obs: after the first reset the whole history is the launch position, afterwards its
+    last row is the current ball position and the task observation is (history - racket position)"""
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    torch.manual_seed(3)
+    env = PhysicsMVAEController(v2p_cfg(64, use_history_ball_obs=True), SIM_PARAMS, 1, "cuda", 0, True)
+    env.reset()
+    task = env._physics_player.task
+    L = env._obs_ball_traj_length
+    assert torch.equal(env._ball_obs, task._ball_pos[:, None, :].expand(-1, L, -1))
+    prev = env._ball_obs.clone()
+    for i in range(3):
+        env.step(torch.clamp(torch.randn(64, env.num_actions, device=env.device), -5, 5))
+        keep = ~(env._reset_reaction_buf | env._reset_recovery_buf)
+        assert torch.equal(env._ball_obs[:, -1], task._ball_pos)
+        assert torch.equal(env._ball_obs[:, :-1], prev[:, 1:])
+        want = (env._ball_obs - task._rigid_body_state.view(64, 26, 13)[:, 24, 0:3][:, None]).reshape(64, -1)
+        assert torch.allclose(env.obs_buf[:, 225:225 + 3 * L], want, atol=1e-6)
+        env.reset(env.reset_buf.nonzero(as_tuple=False).flatten())
+        prev = env._ball_obs.clone()
+        assert keep.any()
+
+
+def test_test_time_joint_rot_export():
+    """is_train False (humanoid_smpl_im_mvae.py:814-820): _joint_rot = root angle-axis | dof_pos in SMPL joint order"""
+    from scipy.spatial.transform import Rotation
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    cfg = v2p_cfg(16)
+    cfg["env"]["is_train"] = False
+    env = PhysicsMVAEController(cfg, SIM_PARAMS, 1, "cuda", 0, True)
+    env.reset()
+    env.step(torch.zeros(16, env.num_actions, device=env.device))
+    task = env._physics_player.task
+    jr = env._joint_rot.cpu().numpy()
+    dof = task._dof_pos.cpu().numpy().reshape(16, 23, 3)
+    root = Rotation.from_quat(task._rigid_body_rot[:, 0].cpu().numpy()).as_rotvec()
+    mj_pose = np.concatenate([root[:, None], dof], 1)                     # mujoco body order (Pelvis first)
+    assert np.abs(jr - mj_pose[:, task._mujoco_2_smpl]).max() < 1e-5
+    assert np.abs(jr[:, 0] - root).max() < 1e-5                           # Pelvis is joint 0 in both orders
 
 
 def test_controller_end_to_end():

@@ -234,3 +234,18 @@ def test_flat_motion_library_file_roundtrip(tmp_path):
     (tmp_path / "bad.b200ml").write_bytes(b"not a library" * 4)
     with pytest.raises(ValueError, match="not a B200ML01"):
         motion_lib.FlatMotionLib.load_flat(str(tmp_path / "bad.b200ml"))
+
+
+def test_quaternion_to_angle_axis_matches_scipy():
+    """torch_ops.quaternion_wxyz_to_angle_axis (the ceres formula of konia_transform.py:558-628, test-time `_joint_rot` export)"""
+    from scipy.spatial.transform import Rotation
+    from vid2player3d_b200.torch_ops import quaternion_wxyz_to_angle_axis
+    rng = np.random.default_rng(0)
+    q = rng.normal(size=(256, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[0] = [1, 0, 0, 0]
+    got = quaternion_wxyz_to_angle_axis(torch.tensor(q)).numpy()
+    want = Rotation.from_quat(q[:, [1, 2, 3, 0]]).as_rotvec()
+    # q and -q are the same rotation: the formula keeps the angle in (-pi, pi] like the reference
+    assert np.abs(got - want).max() < 1e-9
+    assert np.all(got[0] == 0)

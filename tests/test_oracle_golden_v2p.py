@@ -133,3 +133,22 @@ def test_dual_golden():
     assert np.array_equal(recovery, g["cr_out_recovery"])
     np.testing.assert_allclose(dist, g["cr_out_distance"], rtol=0, atol=1e-6)
     assert g["cr_out_reset"].sum() > g["crreset_buf"].sum() and g["cr_out_reaction"].any() and g["cr_out_recovery"].any()
+
+
+def test_history_ball_obs_variant():
+    """use_history_ball_obs (physics_mvae_controller.py:213-214, 345-351): fill on a reaction reset, roll + append at every
+    observation, partial refresh touches the listed rows only"""
+    g = golden("v2p_controller.npz")
+    assert np.array_equal(g["hist_in"], g["ball_obs_after"])
+    h = V.reset_ball_obs(g["hist_in"], g["hist_ball_pos0"], g["hist_reset_ids"])
+    assert np.array_equal(h, g["hist_after_reset"])
+    part = g["hist_part_ids"]
+    h = V.roll_ball_obs(h, g["hist_ball_pos0"], part)
+    assert np.array_equal(h, g["hist_after_partial"])
+    args = (g["rbs"], g["p_root_pos"], g["p_root_vel"], g["p_racket_normal"], g["ball_traj"], g["hist_target_bounce_pos"], 10)
+    close(V.controller_obs(*args, ball_obs=h)[part], g["hist_obs_partial"][part], 2e-6)
+    for k in (1, 2):
+        h = V.roll_ball_obs(h, g[f"hist_ball_pos{k}"])
+        assert np.array_equal(h, g[f"hist_after_full{k}"])
+        close(V.controller_obs(*args, ball_obs=h), g[f"hist_obs_full{k}"], 2e-6)
+

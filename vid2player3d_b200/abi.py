@@ -216,7 +216,7 @@ class V2PCtrl(C.Structure):
         ("n", C.c_int32), ("bodies_per_env", C.c_int32), ("ball_stride", C.c_int32), ("racket_body", C.c_int32),
         ("num_obs", C.c_int32), ("obs_traj_len", C.c_int32), ("use_target", C.c_int32), ("reward_type", C.c_int32),
         ("early_termination", C.c_int32), ("max_episode_length", C.c_int32), ("est_nx", C.c_int32), ("est_ny", C.c_int32),
-        ("obs_only", C.c_int32), ("dual", C.c_int32),
+        ("obs_only", C.c_int32), ("dual", C.c_int32), ("use_history", C.c_int32),
         ("scale_pos", C.c_float), ("scale_phase", C.c_float), ("scale_bounce_pos", C.c_float), ("scale_bounce_time", C.c_float),
         ("w_pos", C.c_float), ("w_ball_pos", C.c_float),
         ("court_min", C.c_float * 2), ("court_max", C.c_float * 2), ("est_params", C.c_float * 15),
@@ -231,7 +231,7 @@ class V2PCtrl(C.Structure):
         ("bounce_in", C.c_void_p), ("est_bounce_in", C.c_void_p), ("reset_reaction", C.c_void_p), ("reset_recovery", C.c_void_p),
         ("est_bounce_pos", C.c_void_p), ("est_bounce_time", C.c_void_p), ("est_max_height", C.c_void_p), ("distance", C.c_void_p),
         ("obs_buf", C.c_void_p), ("rew_buf", C.c_void_p), ("sub_rewards", C.c_void_p),
-        ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p),
+        ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p), ("ball_obs", C.c_void_p),
     ]
 
 
@@ -246,7 +246,7 @@ class V2PTaskReset(C.Structure):
         ("est_bounce_pos", C.c_void_p), ("est_bounce_time", C.c_void_p), ("est_max_height", C.c_void_p), ("target_bounce_pos", C.c_void_p),
         ("has_bounce", C.c_void_p), ("has_contact", C.c_void_p), ("bounce_in", C.c_void_p), ("est_bounce_in", C.c_void_p),
         ("tar_time", C.c_void_p), ("tar_time_total", C.c_void_p), ("tar_action", C.c_void_p), ("num_reset_reaction", C.c_void_p),
-        ("swing_type_cycle", C.c_void_p),
+        ("swing_type_cycle", C.c_void_p), ("ball_obs", C.c_void_p), ("obs_traj_len", C.c_int32), ("pad_", C.c_int32),
     ]
 
 

@@ -423,7 +423,28 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p
     for (int k = 0; k < 6; k++) nan |= isnan(r6[k]);
   }
   const float* rk = rb + c.racket_body * 13;
-  for (int k = lane; k < c.obs_traj_len * 3; k += 32) { float v = c.ball_traj[e * 300 + k] - rk[k % 3]; o[225 + k] = v; nan |= isnan(v); }
+  const int L3 = c.obs_traj_len * 3;
+  if (c.ball_obs) {   // _compute_task_obs :345-346: _ball_obs <- roll(-1) with the current ball position appended (kept in every mode)
+    float* hst = c.ball_obs + e * L3;
+    const bool touch = !c.obs_only || c.reset_reaction[e] || (!c.dual && c.reset_recovery[e]);   // obs_only: the reference refreshes
+    if (touch) {                                                                                // the reset ids only (:200-201; dual :64-66)
+      float tmp[10];   // L3 <= 300 -> at most 10 values per lane: read everything, then write (in-place shift inside the warp)
+#pragma unroll
+      for (int i = 0; i < 10; i++) {
+        const int k = lane + 32 * i;
+        tmp[i] = k < L3 - 3 ? hst[k + 3] : (k < L3 ? c.ball_pos[e * 3 + k - (L3 - 3)] : 0.0f);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 10; i++) {
+        const int k = lane + 32 * i;
+        if (k < L3) hst[k] = tmp[i];
+      }
+      __syncwarp();
+    }
+  }
+  const float* src = c.use_history ? c.ball_obs + e * L3 : c.ball_traj + e * 300;
+  for (int k = lane; k < L3; k += 32) { float v = src[k] - rk[k % 3]; o[225 + k] = v; nan |= isnan(v); }
   if (c.use_target && lane < 2) { float v = c.target_bounce_pos[e * 3 + lane] - rp[lane]; o[225 + c.obs_traj_len * 3 + lane] = v; nan |= isnan(v); }
   const bool has_nan = __any_sync(FULL, nan);
   // ---- dual reset FSM (physics_mvae_controller_dual.py:92-120): the opponent's flags are recomputed from its inputs (no exchange)
@@ -537,7 +558,11 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) task_reset_kernel(b200v2p_tres
     }
     const float* row = r.pool + idx * 307;
     __syncwarp();
-    for (int k = lane; k < 300; k += 32) r.ball_traj[e * 300 + k] = row[7 + k];
+    if (r.ball_obs) {   // use_history_ball_obs: _ball_traj is left alone (:187-188), _ball_obs <- the launch position repeated (:213-214)
+      for (int k = lane; k < r.obs_traj_len * 3; k += 32) r.ball_obs[e * r.obs_traj_len * 3 + k] = row[k % 3];
+    } else {
+      for (int k = lane; k < 300; k += 32) r.ball_traj[e * 300 + k] = row[7 + k];
+    }
     if (lane == 0) {
       float* b = r.ball_states + e * r.ball_stride;
       float* rb = r.rigid_body_state + (e * r.bodies_per_env + r.bodies_per_env - 1) * 13;
@@ -738,6 +763,7 @@ int b200v2p_controller_post(const b200v2p_ctrl_t* c, void* stream) {
   if (c->obs_traj_len < 0 || c->obs_traj_len > 100 || c->num_obs < 225 + 3 * c->obs_traj_len + (c->use_target ? 2 : 0))
     return vfail(-2, "b200v2p_controller_post: observation width / trajectory length mismatch");
   if (c->reward_type < 0 || c->reward_type > 2) return vfail(-2, "b200v2p_controller_post: reward_type must be 0 (reach), 1 (return) or 2 (return_w_estimate)");
+  if (c->use_history && !c->ball_obs) return vfail(-2, "b200v2p_controller_post: use_history needs the ball_obs buffer");
   controller_post_kernel<<<(c->n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(*c);
   V_CUDA_OK();
   return 0;

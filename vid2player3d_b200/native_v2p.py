@@ -93,16 +93,17 @@ def controller_post(cfg, t):
         setattr(c, k, cfg[k])
     c.obs_only = int(cfg.get("obs_only", 0))
     c.dual = int(cfg.get("dual", 0))
+    c.use_history = int(cfg.get("use_history", 0))
     for k in ("court_min", "court_max", "est_params"):
         for i, v in enumerate(cfg[k]):
             getattr(c, k)[i] = float(v)
-    scalars = {f for f, _ in abi.V2PCtrl._fields_ if f in cfg} | {"obs_only", "dual"}
+    scalars = {f for f, _ in abi.V2PCtrl._fields_ if f in cfg} | {"obs_only", "dual", "use_history"}
     for name, _ in abi.V2PCtrl._fields_:
         if name in scalars:
             continue
         x = t.get(name)
         if x is None:
-            assert name in ("est_x", "est_y"), name
+            assert name in ("est_x", "est_y", "ball_obs"), name
             setattr(c, name, None)
         else:
             assert x.is_cuda and x.is_contiguous(), name
@@ -119,10 +120,15 @@ def task_reset(cfg, t):
     for k in ("target_min", "target_max"):
         for i, v in enumerate(cfg[k]):
             getattr(r, k)[i] = float(v)
+    r.obs_traj_len = int(cfg.get("obs_traj_len", 0))
     for name, _ in abi.V2PTaskReset._fields_:
-        if name in cfg:
+        if name in cfg or name in ("obs_traj_len", "pad_"):
             continue
-        x = t[name]
+        x = t.get(name)
+        if x is None:
+            assert name == "ball_obs", name
+            setattr(r, name, None)
+            continue
         assert x.is_cuda and x.is_contiguous(), name
         setattr(r, name, x.data_ptr())
     _check(lib().b200v2p_task_reset(C.byref(r), _stream()))

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from .. import abi, ball as ball_data, model_compiler, native, native_v2p
+from ..torch_ops import quaternion_wxyz_to_angle_axis
 from .base_task import BaseTask
 
 SMPL_NAMES = ["Pelvis", "L_Hip", "R_Hip", "Torso", "L_Knee", "R_Knee", "Spine", "L_Ankle", "R_Ankle", "Chest", "L_Toe", "R_Toe",
@@ -139,6 +140,8 @@ class HumanoidSMPLIMMVAE(BaseTask):
         self._rigid_body_state[:, 6] = 1.0
         rbs = self._rigid_body_state.view(N, 26, 13)
         self._rigid_body_pos, self._rigid_body_rot = rbs[:, :25, 0:3], rbs[:, :25, 3:7]
+        if not self._is_train:   # :113-116 test-time export of the simulated pose (SMPL joint order)
+            self._joint_rot = torch.zeros((self.num_envs, 24, 3), device=self.device, dtype=torch.float32)
         self._rigid_body_vel, self._rigid_body_ang_vel = rbs[:, :25, 7:10], rbs[:, :25, 10:13]
         self._contact_force_tensor = f(N * 26, 3)
         self._contact_forces = self._contact_force_tensor.view(N, 26, 3)
@@ -264,6 +267,11 @@ class HumanoidSMPLIMMVAE(BaseTask):
         else:
             native_v2p.update_state(self.num_envs, 26, self._rigid_body_state, self._root_states, 26, self._root_states[1:], 26, t,
                                     grip=self._grip(), wrist_body=self._racket_wrist_body_id)
+        if not self._is_train:
+            # :814-820 test-time export of the simulated pose as SMPL joint rotations (root angle-axis | dof_pos, SMPL joint order)
+            root_rot = quaternion_wxyz_to_angle_axis(self._rigid_body_rot[:, 0][..., [3, 0, 1, 2]])
+            self._joint_rot[:] = torch.cat((root_rot.reshape(self.num_envs, 1, 3), self._dof_pos.reshape(self.num_envs, -1, 3)),
+                                           dim=1)[:, self._mujoco_2_smpl]
 
     def _grip(self):
         g = self.cfg_v2p.get('grip', 'eastern')            # a pair in dual_mode 'different' (:839-842)

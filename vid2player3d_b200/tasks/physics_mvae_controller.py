@@ -166,6 +166,8 @@ class PhysicsMVAEController:
         self._graph = None
         self._num_humanoid_bodies, self._racket_body_id, self._head_body_id = 24, 24, 13
         self._ball_traj = f(N, 100, 3)
+        self._ball_obs = f(N, self._obs_ball_traj_length, 3)            # :65 history of ball positions (rolled at every observation)
+        self._use_history = bool(self.cfg_v2p.get('use_history_ball_obs', False))
         self._bounce_in, self._est_bounce_in = b(N), b(N)
         self._est_bounce_pos, self._est_bounce_time, self._est_max_height = f(N, 3), f(N), f(N)
         self._court_min = torch.tensor(self.cfg_v2p.get('court_min', [-5, -16]), device=dev, dtype=torch.float)
@@ -204,7 +206,8 @@ class PhysicsMVAEController:
             scale_pos=float(scales.get('pos', 5.0)), scale_phase=float(scales.get('phase', 10.0)),
             scale_bounce_pos=float(scales.get('bounce_pos', 0.05)), scale_bounce_time=float(scales.get('bounce_time', 0.1)),
             w_pos=float(weights.get('pos', 1.0 if rtype == 'reach' else 0.0)), w_ball_pos=float(weights.get('ball_pos', 0.0)),
-            court_min=self._court_min.tolist(), court_max=self._court_max.tolist(), est_params=self._est_params, dual=0)
+            court_min=self._court_min.tolist(), court_max=self._court_max.tolist(), est_params=self._est_params, dual=0,
+            use_history=int(self._use_history))
 
     # ------------------------------------------------------------------ construction (:118-158)
     def create_sim(self):
@@ -265,7 +268,7 @@ class PhysicsMVAEController:
         tm = 1 if mode == 'continuous' else (2 if mode else 0)
         seed = torch.rand(3 if tm == 1 else (N if tm == 2 else 1), device=dev)
         cfg = dict(n=N, pool_size=P, ball_stride=26, bodies_per_env=26, reaction_nframes=int(self.cfg_v2p.get('reset_reaction_nframes', 70)),
-                   target_mode=tm, target_min=self._target_bounce_min.tolist() if not hasattr(self, "_tmin") else self._tmin,
+                   obs_traj_len=self._obs_ball_traj_length, target_mode=tm, target_min=self._target_bounce_min.tolist() if not hasattr(self, "_tmin") else self._tmin,
                    target_max=self._target_bounce_max.tolist() if not hasattr(self, "_tmax") else self._tmax)
         self._tmin, self._tmax = cfg["target_min"], cfg["target_max"]
         native_v2p.task_reset(cfg, dict(
@@ -277,7 +280,7 @@ class PhysicsMVAEController:
             est_max_height=self._est_max_height, target_bounce_pos=self._target_bounce_pos, has_bounce=t._has_bounce,
             has_contact=t._has_racket_ball_contact, bounce_in=self._bounce_in, est_bounce_in=self._est_bounce_in, tar_time=self._tar_time,
             tar_time_total=self._tar_time_total, tar_action=self._tar_action, num_reset_reaction=self._num_reset_reaction,
-            swing_type_cycle=self._mvae_player._swing_type_cycle))
+            swing_type_cycle=self._mvae_player._swing_type_cycle, ball_obs=self._ball_obs if self._use_history else None))
         if update_state:
             self._physics_player.task._update_state_from_sim()   # :186-187 "setting the right fields to compute obs"
         post = dict(self._post_cfg)
@@ -323,7 +326,7 @@ class PhysicsMVAEController:
             self._num_reset[env_ids] += 1
         if len(env_ids) > 0 or len(reaction_ids) > 0:
             traj = task.reset(env_ids, reaction_ids)
-            if traj is not None:
+            if traj is not None and not self._use_history:      # :187-188
                 self._ball_traj[reaction_ids] = traj
         if len(env_ids) > 0:
             task._update_state_from_sim()
@@ -339,6 +342,8 @@ class PhysicsMVAEController:
 
     def _reset_reaction_tasks(self, env_ids):
         """:203-240"""
+        if self._use_history:                                   # :213-214
+            self._ball_obs[env_ids] = self._physics_player.task._ball_pos[env_ids].view(-1, 1, 3).repeat(1, self._obs_ball_traj_length, 1)
         self._tar_time[env_ids] = 0
         self._tar_action[env_ids] = 1
         self._num_reset_reaction[env_ids] += 1
@@ -399,7 +404,8 @@ class PhysicsMVAEController:
                     est_x=self._est_x, est_y=self._est_y, bounce_in=self._bounce_in, est_bounce_in=self._est_bounce_in,
                     reset_reaction=self._reset_reaction_buf, reset_recovery=self._reset_recovery_buf, est_bounce_pos=self._est_bounce_pos,
                     est_bounce_time=self._est_bounce_time, est_max_height=self._est_max_height, distance=self._distance, obs_buf=self.obs_buf,
-                    rew_buf=self.rew_buf, sub_rewards=self._sub_rewards, reset_buf=self.reset_buf, terminate_buf=self._terminate_buf)
+                    rew_buf=self.rew_buf, sub_rewards=self._sub_rewards, reset_buf=self.reset_buf, terminate_buf=self._terminate_buf,
+                    ball_obs=self._ball_obs)
 
     def _compute_post(self):
         """_update_state + _compute_reward + _compute_observations + _compute_reset as ONE launch (:271-436)"""
@@ -409,6 +415,8 @@ class PhysicsMVAEController:
         self._root_pos, self._root_vel, self._racket_pos, self._racket_vel, self._racket_normal = t._root_pos, t._root_vel, t._racket_pos, t._racket_vel, t._racket_normal
         self._ball_pos, self._ball_vel, self._ball_vspin = t._ball_pos, t._ball_vel, t._ball_vspin
         self._phase_pred = self._mvae_player._phase_pred
+        if not self._is_train:
+            self._joint_rot = t._joint_rot          # :274-275
 
     def _compute_observations(self, env_ids=None):
         """used on reset: the observation rows are refreshed by the same kernel (reward / reset flags of a reset env are rewritten
@@ -519,7 +527,8 @@ class PhysicsMVAEControllerDual(PhysicsMVAEController):
             self._reset_env_tensors(env_ids)
         if len(reaction_ids) > 0:
             new_traj = task.reset(reaction_actor, reaction_ids)
-            self._ball_traj[reaction_ids, :new_traj.shape[1]] = new_traj
+            if not self._use_history:
+                self._ball_traj[reaction_ids, :new_traj.shape[1]] = new_traj
             # self._update_state() (:52) re-derives bounce_in from unchanged inputs: nothing to do on the device
         if len(recovery_ids) > 0:
             self._reset_recovery_tasks(recovery_ids)
@@ -532,6 +541,8 @@ class PhysicsMVAEControllerDual(PhysicsMVAEController):
 
     def _reset_reaction_tasks(self, env_ids):
         """:66-85"""
+        if self._use_history:                                   # :69-70
+            self._ball_obs[env_ids] = self._physics_player.task._ball_pos[env_ids].view(-1, 1, 3).repeat(1, self._obs_ball_traj_length, 1)
         self._tar_time[env_ids] = 0
         self._tar_action[env_ids] = 1
         self._num_reset_reaction[env_ids] += 1
