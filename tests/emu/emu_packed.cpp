@@ -9,8 +9,16 @@ thread_local int emu_lane = 0;
 #include "../../vid2player3d_b200/csrc/dyn_common.cuh"
 #ifdef EMU_PACKED3
 #include "../../vid2player3d_b200/csrc/packed3.cuh"
+#define EMU_EPW EPW3
+#define EMU_LPE LPE3
+#define EMU_BALL_SLOT BALL_SLOT3
+#define EMU_STEP control_step_packed3
 #else
 #include "../../vid2player3d_b200/csrc/packed.cuh"
+#define EMU_EPW EPW
+#define EMU_LPE PK_LANES_PER_ENV
+#define EMU_BALL_SLOT BALL_SLOT
+#define EMU_STEP control_step_packed
 #endif
 
 #include <vector>
@@ -40,8 +48,8 @@ void lane_main(EmuWarp* w, int lane, const Job* J, int64_t eb, double* wrec) {
   PhysCfg<T> pc = make_phys_cfg<T>(*J->cfg);
   const bool with_ball = pc.has_ball && J->ballio != nullptr;
   pc.has_ball = with_ball;
-  const int g = lane / PK_LANES_PER_ENV, s = lane % PK_LANES_PER_ENV;
-  for (int k = 0; k < EPW; k++) {
+  const int g = lane / EMU_LPE, s = lane % EMU_LPE;
+  for (int k = 0; k < EMU_EPW; k++) {
     const int64_t e = eb + k;
     if (e >= n) break;
     Lane<T> L;
@@ -64,17 +72,17 @@ void lane_main(EmuWarp* w, int lane, const Job* J, int64_t eb, double* wrec) {
     pk_store_state<T>(wrec + k * ENV_STRIDE, lc, lane, L, pdt, eF, eT);
   }
   __syncwarp();
-  const bool valid = g < EPW && eb + g < n;
+  const bool valid = g < EMU_EPW && eb + g < n;
   Ball<T> ball;
   ball_clear(ball);
-  if (with_ball && valid && s == BALL_SLOT) {
+  if (with_ball && valid && s == EMU_BALL_SLOT) {
     const int64_t e = eb + g;
     for (int j = 0; j < 3; j++) { ball.p[j] = J->ballio[e * 13 + j]; ball.v[j] = J->ballio[e * 13 + 7 + j]; ball.w[j] = J->ballio[e * 13 + 10 + j]; }
   }
   for (int st_ = 0; st_ < J->n_steps; st_++) {
-    control_step_packed<T>(B, J->verts, pc, wrec, lane, valid, ball, false);
+    EMU_STEP<T>(B, J->verts, pc, wrec, lane, valid, ball, false);
     if (st_ + 1 < J->n_steps) {
-      for (int k = 0; k < EPW; k++) {
+      for (int k = 0; k < EMU_EPW; k++) {
         if (eb + k >= n) break;
         if (lc.dyn && lane > 0) {
           T* rec = wrec + k * ENV_STRIDE + lc.rix * REC;
@@ -88,7 +96,7 @@ void lane_main(EmuWarp* w, int lane, const Job* J, int64_t eb, double* wrec) {
       __syncwarp();
     }
   }
-  for (int k = 0; k < EPW; k++) {
+  for (int k = 0; k < EMU_EPW; k++) {
     const int64_t e = eb + k;
     if (e >= n) break;
     Lane<T> L;
@@ -111,7 +119,7 @@ void lane_main(EmuWarp* w, int lane, const Job* J, int64_t eb, double* wrec) {
       if (J->contact_out) for (int j = 0; j < 3; j++) J->contact_out[(e * nb + lane) * 3 + j] = cf[j];
     }
   }
-  if (with_ball && valid && s == BALL_SLOT) {
+  if (with_ball && valid && s == EMU_BALL_SLOT) {
     const int64_t e = eb + g;
     for (int j = 0; j < 3; j++) { J->ballio[e * 13 + j] = ball.p[j]; J->ballio[e * 13 + 7 + j] = ball.v[j]; J->ballio[e * 13 + 10 + j] = ball.w[j]; }
     if (J->hits) J->hits[e] = ball.hits;
@@ -130,10 +138,10 @@ extern "C" int emu_packed_physics(const b200_model_t* model, const float* verts,
   while ((uintptr_t)sv % 16) sv++;   // contact_hull reads the vertices with 128-bit loads
   verts_to_soa(model, verts, sv);
   Job J{&hb, sv, cfg, n, n_steps, root, dof_pos, dof_vel, pd_tar, ext, rb_out, contact_out, ballio, hits};
-  std::vector<double> rec((size_t)EPW * ENV_STRIDE + 2, 0.0);
+  std::vector<double> rec((size_t)EMU_EPW * ENV_STRIDE + 2, 0.0);
   double* wrec = rec.data();
   while ((uintptr_t)wrec % 16) wrec++;
-  for (int64_t eb = 0; eb < n; eb += EPW) {
+  for (int64_t eb = 0; eb < n; eb += EMU_EPW) {
     EmuWarp w;
     std::vector<std::thread> th;
     for (int lane = 0; lane < 32; lane++) th.emplace_back(lane_main, &w, lane, &J, eb, wrec);

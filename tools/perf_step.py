@@ -23,5 +23,5 @@ for i in range(K):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); task.step(acts[i % 8]); e1.record(); torch.cuda.synchronize()
     tot += e0.elapsed_time(e1)
-print(f"{os.environ.get('B200ENV_LIB','default')}: step_kernel avg {tot / K * 1e3:.1f} us -> {N * K / tot / 1e3:.2f} M env-steps/s "
+print(f"{os.environ.get('B200ENV_LIB','default')} kernel={os.environ.get('B200ENV_KERNEL','packed')}: step_kernel avg {tot / K * 1e3:.1f} us -> {N * K / tot / 1e3:.2f} M env-steps/s "
       f"(rew mean {float(task.rew_buf.mean()):.4f}, resets {int(task.reset_buf.sum())})")

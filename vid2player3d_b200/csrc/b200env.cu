@@ -60,6 +60,7 @@ struct b200env {
   unsigned long long ticket_base;
   float* d_ext;                        // [num_envs rows of the bound tensors, 6] residual root wrench between pre_kernel and the physics launch
   int ext_rows;
+  int packed3;                         // 1: the physics launch is step_kernel_packed3 (B200ENV_KERNEL=packed3)
   int split;                           // 1: three launches (pre / physics / post), 0: one fused launch.  env B200ENV_SPLIT=0|1
   int env_first = 0, env_stride = 1;   // b200env_set_env_slice: local env i = row env_first + env_stride * i of the bound tensors
   int step_grid;
@@ -413,6 +414,7 @@ __device__ __forceinline__ void control_step(const DevBlob& B, const float* vert
 }
 
 #include "packed.cuh"
+#include "packed3.cuh"
 
 // ------------------------------------------------------------------------------------------
 // TMA bulk load of the constant block into shared memory (one elected thread issues it)
@@ -1158,6 +1160,105 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// packed3 form of the middle launch (pre_kernel -> this -> post_kernel): 2 envs per warp, 14 warps per CTA (csrc/packed3.cuh).
+// Same shared-memory footprint and the same 28 envs per CTA batch as step_kernel_packed<split>; twice the warps.
+#ifndef PK3_WARPS
+#define PK3_WARPS 14
+#endif
+__global__ void __launch_bounds__(PK3_WARPS * 32, 1)
+step_kernel_packed3(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
+                    int num_envs, unsigned long long* __restrict__ ticket, int env_first, int env_stride,
+                    const float* __restrict__ ext_wrench) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  load_blob(smem, gblob, blob_bytes, &mbar);
+  const DevBlob& B = *reinterpret_cast<const DevBlob*>(smem);
+  const b200_model_t& M = B.m;
+  const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* wrec = reinterpret_cast<float*>(smem + ((blob_bytes + 15) & ~15u)) + (size_t)warp * EPW3 * ENV_STRIDE;
+  __shared__ b200_cfg_t s_cfg;
+  for (int k = threadIdx.x; k < (int)(sizeof(b200_cfg_t) / 4); k += blockDim.x) reinterpret_cast<uint32_t*>(&s_cfg)[k] = reinterpret_cast<const uint32_t*>(gcfg)[k];
+  __syncthreads();
+  const b200_cfg_t& cfg = s_cfg;
+  LaneConst lc = lane_const(M, lane);
+  if (lc.active) lc.rix = B.t.rix[lane];
+  const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
+  const int g = lane >> 4, u = lane & 15;
+  constexpr int BATCH = PK3_WARPS * EPW3;
+  __shared__ unsigned long long s_tk;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)BATCH);
+    __syncthreads();
+    const int64_t e0 = (int64_t)s_tk;
+    if (e0 >= num_envs) break;
+    const int64_t eb = e0 + (int64_t)warp * EPW3;
+    if (eb >= num_envs) continue;
+    {
+      // all loads of the warp's envs are issued before the first use
+      float rq[EPW3][3], rw[EPW3][3], rp[EPW3][3], r1[EPW3];
+      const int nd = M.nd;
+#pragma unroll
+      for (int k = 0; k < EPW3; k++) {
+        const int64_t ek = eb + k < num_envs ? eb + k : (int64_t)num_envs - 1;
+        const int64_t e = env_first + (int64_t)env_stride * ek;
+        if (lc.dyn && lane > 0) {
+          const float* ds = bf.dof_state + (e * nd + lc.dof0) * 2;
+#pragma unroll
+          for (int j = 0; j < 3; j++) { rq[k][j] = ds[2 * j]; rw[k][j] = ds[2 * j + 1]; rp[k][j] = bf.pd_targets[e * nd + lc.dof0 + j]; }
+        }
+        r1[k] = lane < 13 ? bf.root_states[e * bf.actors_per_env * 13 + lane] : (lane < 19 ? ext_wrench[e * 6 + lane - 13] : 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < EPW3; k++) {
+        if (eb + k >= num_envs) break;
+        Lane<float> L;
+        float pdtar[3] = {0.f, 0.f, 0.f}, extF[3] = {0.f, 0.f, 0.f}, extT[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; j++) { L.Q[j] = 0.f; L.qj[j] = 0.f; }
+        L.Q[3] = 1.f; L.qj[3] = 1.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { L.p[j] = 0.f; L.w[j] = 0.f; L.v[j] = 0.f; L.wt[j] = 0.f; }
+        float rr[19];
+#pragma unroll
+        for (int j = 0; j < 19; j++) rr[j] = __shfl_sync(FULL, r1[k], j);
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 3; j++) { L.p[j] = rr[j]; L.v[j] = rr[7 + j]; L.w[j] = rr[10 + j]; extF[j] = rr[13 + j]; extT[j] = rr[16 + j]; }
+#pragma unroll
+          for (int j = 0; j < 4; j++) L.Q[j] = rr[3 + j];
+          qnormalize(L.Q);
+        }
+        if (lc.dyn && lane > 0) {
+#pragma unroll
+          for (int j = 0; j < 3; j++) { L.wt[j] = rw[k][j]; pdtar[j] = rp[k][j]; }
+          qexp(rq[k], L.qj);
+        }
+        pk_store_state<float>(wrec + k * ENV_STRIDE, lc, lane, L, pdtar, extF, extT);
+      }
+    }
+    __syncwarp();
+    const bool valid = eb + g < num_envs;
+    Ball<float> ball;
+    ball_clear(ball);
+    const int64_t erow_g = env_first + (int64_t)env_stride * (valid ? eb + g : eb);
+    if (cfg.has_ball && valid && u == BALL_SLOT3) ball_load(bf, erow_g, ball);
+    control_step_packed3<float>(B, verts, pc, wrec, lane, valid, ball, false);
+    if (cfg.has_ball && valid && u == BALL_SLOT3) ball_writeback(bf, erow_g, ball);
+    for (int k = 0; k < EPW3; k++) {
+      if (eb + k >= num_envs) break;
+      const int64_t e = env_first + (int64_t)env_stride * (eb + k);
+      Lane<float> L;
+      float cf[3], dq[3];
+      pk_load_state<float>(wrec + k * ENV_STRIDE, lc, lane, L, cf);
+      epilogue_writeback(bf, cfg, M, lc, lane, e, L, cf, dq);
+    }
+    __syncwarp();
+  }
+}
+
 template <typename T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 physics_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, int n, int n_steps,
@@ -1608,6 +1709,11 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   h->packed = h->packed_ok && !(kv && strcmp(kv, "lane") == 0);
   const char* sv = getenv("B200ENV_SPLIT");
   h->split = h->packed && !(sv && strcmp(sv, "0") == 0);
+  // packed3 (2 envs per warp, 3 lanes per body in the backward pass; csrc/packed3.cuh): needs the split form and at most 5 bodies
+  // per tree depth.  B200ENV_KERNEL=packed3 selects it (A/B against the 4-envs-per-warp kernel, profiles/).
+  int wide = 0;
+  for (int d = 0; d < MAX_LEVELS; d++) if (hb.t.lvl_all[d][SLOTS3] >= 0) wide = 1;
+  h->packed3 = h->split && !wide && kv && strcmp(kv, "packed3") == 0;
   const size_t vbytes = (size_t)model->nb * model->vmax * 3 * sizeof(float);
   h->blob_bytes = sizeof(DevBlob) + ((vbytes + 15) & ~(size_t)15);
   CUDA_OK(cudaMalloc(&h->d_blob, h->blob_bytes));
@@ -1685,7 +1791,10 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
       CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
       CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
       int per_sm = 0, sms = 0;
-      if (h->split) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<true>, PK_WARPS * 32, psmem)); }
+      if (h->packed3) {
+        CUDA_OK(cudaFuncSetAttribute(step_kernel_packed3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed3, PK3_WARPS * 32, psmem));
+      } else if (h->split) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<true>, PK_WARPS * 32, psmem)); }
       else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<false>, PK_WARPS * 32, psmem)); }
       CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
       h->step_grid = per_sm * sms < need ? per_sm * sms : need;
@@ -1705,9 +1814,13 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
       const int io_grid = need_ctas(h);
       pre_kernel<<<io_grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->bufs, h->ml, actions,
                                                                            h->num_envs, h->env_first, h->env_stride, h->d_ext);
-      step_kernel_packed<true><<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>(
-          (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->ml, actions, h->num_envs, h->d_ticket, h->env_first,
-          h->env_stride, h->d_ext);
+      if (h->packed3)
+        step_kernel_packed3<<<h->step_grid, PK3_WARPS * 32, psmem, (cudaStream_t)stream>>>(
+            (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->num_envs, h->d_ticket, h->env_first, h->env_stride, h->d_ext);
+      else
+        step_kernel_packed<true><<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>(
+            (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->ml, actions, h->num_envs, h->d_ticket, h->env_first,
+            h->env_stride, h->d_ext);
       if (h->cfg.task_mode == 0)
         post_kernel<<<io_grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->bufs, h->ml, h->num_envs,
                                                                               h->env_first, h->env_stride);
