@@ -289,6 +289,16 @@ def cpu_reference_arm(model, flat, sample_envs, steps, warmup, seed=7):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line, the JSON: anything a library prints there meanwhile (NCCL prints its version banner on
+    # stdout at init) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -296,6 +306,8 @@ def main():
     workload = (f"embodied_pose amass_im: {args.envs} envs/GPU, SMPL humanoid 24 bodies/69 dof, synthetic MoCap 64x300 frames, "
                 f"random policy, reset(all) every {HORIZON} steps")
 
+    if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(cores)   # torchrun's default of 1 would cripple the CPU restatement (OpenMP over envs)
     if args.impl == "reference":
         if rank != 0:
             return
@@ -307,7 +319,7 @@ def main():
         steps, warm = min(args.steps, 40), min(args.warmup, 3)
         v, ms_step = cpu_reference_arm(model, flat, args.cpu_sample_envs, steps, warm)
         sample = f"{args.cpu_sample_envs} of {args.envs} envs x {steps} steps, OpenMP over envs + numpy"
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 physics / f32 task logic", "data": "synthetic",
@@ -315,7 +327,7 @@ def main():
                        "pipeline cannot be installed here (closed binary, py3.8) - stand-in, labelled as such"},
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        })
         return
 
     import torch
@@ -462,13 +474,13 @@ def main():
             out["config"]["ball_tables"] = ball_tables_workload()
         except Exception as ex:
             out["config"]["ball_tables"] = {"error": repr(ex)[:200]}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # contract: the CPU baseline is timed at N = 1 only
         from oracle import physics_ref
         physics_ref.build()
         v, _ = cpu_reference_arm(model, flat, args.cpu_sample_envs, 24, 2)
         out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                "sample": f"{args.cpu_sample_envs} of {N} envs x 24 steps (OpenMP physics restatement + numpy task logic)"}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
