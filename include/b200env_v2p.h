@@ -126,6 +126,8 @@ typedef struct b200v2p_areset {
   float *root_states, *dof_state, *rigid_body_state;
   float *prev_target_root_pos, *prev_target_rb_rot, *root_pos, *root_vel, *pd_target_dof_pos, *target_root_pos;
   int64_t *progress_buf, *reset_buf, *terminate_buf;
+  const uint8_t* mask;      /* optional [N]: row env_ids[i] is reset only when mask[env_ids[i]] != 0 (mask-driven form: env_ids =
+                               0..N-1, n = N; no id list has to be built on the host, the launch can live in a CUDA graph) */
 } b200v2p_areset_t;
 int b200v2p_actor_reset(const b200v2p_areset_t* r, void* stream);
 

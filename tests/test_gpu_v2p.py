@@ -209,6 +209,49 @@ def test_test_time_joint_rot_export():
     assert np.abs(jr[:, 0] - root).max() < 1e-5                           # Pelvis is joint 0 in both orders
 
 
+def test_masked_actor_reset_equals_id_list_reset_and_reset_graph_runs():
+    """mask-driven humanoid reset (b200v2p_areset_t.mask, CUDA-graph safe) == the id-list one; the controller's reset graph keeps
+    the reset contract: listed envs restart (progress 0, sim state = FK of the motion generator's pose), the others are untouched"""
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    envs = []
+    for _ in range(2):
+        torch.manual_seed(11)
+        e = PhysicsMVAEController(v2p_cfg(48), SIM_PARAMS, 1, "cuda", 0, True)
+        e.reset()
+        for i in range(3):
+            e.step(torch.zeros(48, e.num_actions, device=e.device))
+        envs.append(e)
+    a, b = envs
+    ids = torch.tensor([0, 5, 6, 31, 47], device=DEV)
+    mask = torch.zeros(48, dtype=torch.bool, device=DEV)
+    mask[ids] = True
+    ta, tb = a._physics_player.task, b._physics_player.task
+    ta._reset_actors(ids)
+    tb._reset_actors_masked(mask)
+    torch.cuda.synchronize()
+    for name in ("_root_states", "_dof_state", "_rigid_body_state", "_prev_target_root_pos", "_prev_target_rb_rot", "_root_pos", "_root_vel",
+                 "_pd_target_dof_pos", "_target_root_pos", "progress_buf", "reset_buf", "_terminate_buf"):
+        assert torch.equal(getattr(ta, name), getattr(tb, name)), name
+    # the reset graph
+    b.enable_cuda_graph()
+    for i in range(4):
+        b.step(torch.clamp(torch.randn(48, b.num_actions, device=DEV), -5, 5))
+        done = b.reset_buf.nonzero(as_tuple=False).flatten()
+        keep = torch.ones(48, dtype=torch.bool, device=DEV)
+        keep[done] = False
+        before = tb._dof_state.view(48, -1).clone()
+        prog = b.progress_buf.clone()
+        b.reset(done)
+        torch.cuda.synchronize()
+        assert torch.equal(tb._dof_state.view(48, -1)[keep], before[keep])                 # untouched envs
+        assert bool((b.progress_buf[done] == 0).all()) and torch.equal(b.progress_buf[keep], prog[keep])
+        assert bool((b.reset_buf[done] == 0).all()) and bool(torch.isfinite(b.obs_buf).all())
+        if len(done):
+            want = tb._tmp["dof_pos"][done]                                                # FK of the (re-drawn) generator pose
+            assert torch.allclose(tb._dof_state.view(48, -1, 2)[done, :, 0], want) and bool((tb._dof_state.view(48, -1, 2)[done, :, 1] == 0).all())
+    assert b._reset_graph is not None
+
+
 def test_controller_end_to_end():
     """config-3 style rollout (synthetic motion generator, zero-residual low-level policy): 150 high-level steps"""
     from helpers import SIM_PARAMS, v2p_cfg

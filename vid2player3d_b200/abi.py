@@ -261,5 +261,5 @@ class V2PActorReset(C.Structure):
         ("root_states", C.c_void_p), ("dof_state", C.c_void_p), ("rigid_body_state", C.c_void_p),
         ("prev_target_root_pos", C.c_void_p), ("prev_target_rb_rot", C.c_void_p), ("root_pos", C.c_void_p), ("root_vel", C.c_void_p),
         ("pd_target_dof_pos", C.c_void_p), ("target_root_pos", C.c_void_p),
-        ("progress_buf", C.c_void_p), ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p),
+        ("progress_buf", C.c_void_p), ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p), ("mask", C.c_void_p),
     ]

@@ -614,6 +614,7 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) actor_reset_kernel(b200v2p_are
   const int i = blockIdx.x * V2P_WARPS + warp;
   if (i >= r.n) return;
   const int64_t e = r.env_ids[i];
+  if (r.mask && !r.mask[e]) return;
   const int nd = r.num_dof;
   float* rb = r.rigid_body_state + e * r.bodies_per_env * 13;
   if (lane < 24) {

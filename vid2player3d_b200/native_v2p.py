@@ -148,7 +148,11 @@ def actor_reset(cfg, t):
     for name, _ in abi.V2PActorReset._fields_:
         if name in cfg or name in ("dual", "racket_offset2", "racket_parent2", "pad_"):
             continue
-        x = t[name]
+        x = t.get(name)
+        if x is None:
+            assert name == "mask", name
+            setattr(r, name, None)
+            continue
         assert x.is_cuda and x.is_contiguous(), name
         setattr(r, name, x.data_ptr())
     _check(lib().b200v2p_actor_reset(C.byref(r), _stream()))

@@ -301,6 +301,23 @@ class HumanoidSMPLIMMVAE(BaseTask):
             pd_target_dof_pos=self._pd_target_dof_pos, target_root_pos=self._target_root_pos, progress_buf=self.progress_buf,
             reset_buf=self.reset_buf, terminate_buf=self._terminate_buf))
 
+    def _reset_actors_masked(self, mask):
+        """_reset_actors for the envs whose mask is set: same two launches over all rows, no id list (CUDA-graph safe)"""
+        if not hasattr(self, "_all_ids"):
+            self._all_ids = torch.arange(self.num_envs, device=self.device, dtype=torch.long)
+        self._smpl_to_sim_into(self._mvae_player._root_pos.contiguous(), self._mvae_player._joint_rotmat, self._tmp)
+        cfg = dict(n=self.num_envs, num_dof=self.num_dof, bodies_per_env=26, root_stride=26, racket_body=24,
+                   racket_parent=self._racket_parents[0], racket_offset=self._model["offset"][24],
+                   racket_offset2=self._models[1]["offset"][24] if len(self._models) == 2 else None,
+                   racket_parent2=self._racket_parents[-1])
+        native_v2p.actor_reset(cfg, dict(
+            env_ids=self._all_ids, mask=mask, src_root_pos=self._mvae_player._root_pos.contiguous(), src_root_rot=self._tmp["root_rot"],
+            src_dof_pos=self._tmp["dof_pos"], src_rb_pos=self._tmp["rb_pos"], src_rb_rot=self._tmp["rb_rot"], root_states=self._root_states,
+            dof_state=self._dof_state, rigid_body_state=self._rigid_body_state, prev_target_root_pos=self._prev_target_root_pos,
+            prev_target_rb_rot=self._prev_target_rb_rot, root_pos=self._root_pos, root_vel=self._root_vel,
+            pd_target_dof_pos=self._pd_target_dof_pos, target_root_pos=self._target_root_pos, progress_buf=self.progress_buf,
+            reset_buf=self.reset_buf, terminate_buf=self._terminate_buf))
+
     def _reset_balls(self, env_ids):
         """:503-524 with the random branch of TennisBallGeneratorOffline.generate (tennis_ball.py:436-444)"""
         P = self._ball_pool.shape[0]

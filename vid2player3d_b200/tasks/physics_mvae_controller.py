@@ -99,6 +99,20 @@ class SyntheticMotionPlayer:
         self._racket_pos[env_ids] = self._root_pos[env_ids] + self._racket_off
         self._update_rotmat(env_ids)
 
+    def reset_masked(self, mask):
+        """reset() for the envs whose mask is set, written as full-width in-place ops (no id list, default generator): it can be
+        captured into a CUDA graph together with the rest of a mask-driven env reset"""
+        N, m1, m3 = self.N, mask, mask[:, None]
+        r = torch.rand(N, 3, device=self.device)
+        self._root_pos.copy_(torch.where(m3, self._lo + r * self._span, self._root_pos))
+        self._aa.copy_(torch.where(mask[:, None, None], 0.05 * torch.randn(N, 24, 3, device=self.device), self._aa))
+        self._heading.copy_(torch.where(m1, math.pi / 2 + 0.2 * (r[:, 2] - 0.5), self._heading))
+        self._phase_pred.masked_fill_(m1, 0.0)
+        self._swing_type.masked_fill_(m1, 0)
+        self._swing_type_cycle.masked_fill_(m1, -1)
+        self._racket_pos.copy_(torch.where(m3, self._root_pos + self._racket_off, self._racket_pos))
+        self._update_rotmat()          # all rows: the rotation matrices are a pure function of (_aa, _heading)
+
     def reset_dual(self, reset_reaction_env_ids, reset_recovery_env_ids):
         """players/mvae_player.py:167-182: both players of the listed pairs restart (ready pose / serve pose in the reference)"""
         self.reset(torch.cat([reset_reaction_env_ids, reset_recovery_env_ids]).sort().values)
@@ -257,6 +271,14 @@ class PhysicsMVAEController:
             if self._has_init and self.num_envs > 1:
                 return
             env_ids = torch.arange(self.num_envs, device=self.device, dtype=torch.long)
+        if getattr(self, "_reset_graph", None) is not None:
+            # graph mode: the id list only fills a mask (2 launches), everything else is one graph replay
+            self._reset_mask.zero_()
+            if len(env_ids) > 0:
+                self._reset_mask.index_fill_(0, env_ids.to(self.device, dtype=torch.long), True)
+            self._reset_graph.replay()
+            self._has_init = True
+            return
         self._reset_envs(env_ids)
 
     def _reset_tasks_fast(self, update_state=False):
@@ -305,6 +327,21 @@ class PhysicsMVAEController:
         if n > 0:
             self._reset_reaction_buf.index_fill_(0, env_ids, False)
             self._reset_recovery_buf.index_fill_(0, env_ids, False)
+        self._has_init = True
+
+    def _reset_envs_masked(self, mask):
+        """_reset_envs (:173-201) driven by a device mask of the humanoids to reset instead of an id list: full-width in-place ops
+        and mask-aware kernels only, no host synchronisation - `enable_cuda_graph` captures it as the reset graph."""
+        task = self._physics_player.task
+        self._mvae_player.reset_masked(mask)
+        task._reset_actors_masked(mask)
+        for buf in (self.progress_buf, self.reset_buf, self._terminate_buf, self._num_reset_reaction):
+            buf.masked_fill_(mask, 0)
+        self._distance.masked_fill_(mask, 0.0)
+        self._num_reset.add_(mask.to(torch.long))
+        self._reset_tasks_fast(update_state=True)
+        self._reset_reaction_buf.masked_fill_(mask, False)
+        self._reset_recovery_buf.masked_fill_(mask, False)
         self._has_init = True
 
     def _reset_envs_idlist(self, env_ids):
@@ -459,6 +496,17 @@ class PhysicsMVAEController:
             self.physics_step()
             self.post_physics_step()
         self._graph = g
+        if type(self)._reset_envs is PhysicsMVAEController._reset_envs and hasattr(self._mvae_player, "reset_masked"):
+            # second graph: the whole env reset, mask-driven (single-player controller with a graph-safe motion player)
+            self._reset_mask = torch.zeros(self.num_envs, device=self.device, dtype=torch.bool)
+            with torch.cuda.stream(s):
+                self._reset_envs_masked(self._reset_mask)          # warm-up with an all-false humanoid mask: only the task masks act
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            rg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(rg):
+                self._reset_envs_masked(self._reset_mask)
+            self._reset_graph = rg
 
     def get_aux_losses(self, model_res_dict):
         """:461-472 (autograd-carrying, PyTorch)"""
