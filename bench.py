@@ -116,7 +116,9 @@ def federer_workload(envs, device_index, steps=96, warmup=16):
     from helpers import SIM_PARAMS, v2p_cfg
     from vid2player3d_b200.tasks import PhysicsMVAEController
     torch.manual_seed(10)
-    env = PhysicsMVAEController(v2p_cfg(envs), SIM_PARAMS, 1, "cuda", device_index, True)
+    cfg = v2p_cfg(envs)
+    cfg["env"]["motion_player"] = "stream"      # resident kinematic target stream in place of the unreleased MVAE
+    env = PhysicsMVAEController(cfg, SIM_PARAMS, 1, "cuda", device_index, True)
     dev = env.device
     env.reset()
     acts = [torch.clamp(torch.randn(envs, env.num_actions, device=dev), -5, 5) for _ in range(8)]
@@ -153,11 +155,11 @@ def federer_workload(envs, device_index, steps=96, warmup=16):
     p1.record()
     torch.cuda.synchronize()
     return {"env_steps_per_s": envs * steps / (ms * 1e-3), "ms_per_step": ms / steps, "physics_kernel_ms": p0.elapsed_time(p1) / 20,
-            "mode": "one CUDA graph per high-level step + eager reset(done ids) with a host sync every step",
+            "mode": "one CUDA graph per high-level step + reset(done ids) = nonzero() host sync, mask fill, one reset-graph replay",
             "env_steps_per_s_eager": envs * steps / (ms_eager * 1e-3),
             "steps": steps, "step_kernel_launches_outside_graph": task._env.launch_count - l0 - 20,
             "workload": f"vid2player federer single: {envs} envs, humanoid+racket+ball, substeps 6 (12 per step), return_w_estimate, "
-                        "synthetic motion generator + zero-residual low-level policy (MVAE / policy checkpoints unreleased)",
+                        "resident kinematic target stream (48 frames in HBM) + zero-residual low-level policy (MVAE / policy checkpoints unreleased)",
             "roofline_frac_hbm": 10900 * envs / (p0.elapsed_time(p1) / 20 * 1e-3) / 1e9 / peaks()[0]}
 
 
@@ -169,7 +171,9 @@ def dual_workload(envs, device_index, steps=96, warmup=16):
     from helpers import SIM_PARAMS, v2p_dual_cfg
     from vid2player3d_b200.tasks import PhysicsMVAEControllerDual
     torch.manual_seed(10)
-    env = PhysicsMVAEControllerDual(v2p_dual_cfg(envs), SIM_PARAMS, 1, "cuda", device_index, True)
+    cfg = v2p_dual_cfg(envs)
+    cfg["env"]["motion_player"] = "stream"
+    env = PhysicsMVAEControllerDual(cfg, SIM_PARAMS, 1, "cuda", device_index, True)
     dev = env.device
     env.reset()
     acts = [torch.clamp(torch.randn(envs, env.num_actions, device=dev), -5, 5) for _ in range(8)]
@@ -205,7 +209,7 @@ def dual_workload(envs, device_index, steps=96, warmup=16):
             "steps": steps, "pair_resets_per_step": stats["resets"] / 2 / steps,
             "mode": "one CUDA graph per high-level step (2 physics launches) + eager reference-shaped reset (id lists, host sync)",
             "workload": f"vid2player federer_djokovic dual: {envs} paired envs ({envs // 2} rallies), substeps 6, return_w_estimate, "
-                        "use_random_ball_target, fix_head_orientation, synthetic incoming-ball table / motion generator"}
+                        "use_random_ball_target, fix_head_orientation, synthetic incoming-ball table, resident kinematic target stream"}
 
 
 def ball_tables_workload(reps=3):

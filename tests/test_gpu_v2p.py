@@ -252,6 +252,36 @@ def test_masked_actor_reset_equals_id_list_reset_and_reset_graph_runs():
     assert b._reset_graph is not None
 
 
+def test_stream_motion_player_in_step_and_reset_graphs():
+    """StreamMotionPlayer (resident target stream): a step is a gather of frame (t + offset) % K, a reset re-draws offsets; the
+    controller's step graph and reset graph replay it"""
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    from vid2player3d_b200.tasks.physics_mvae_controller import StreamMotionPlayer
+    cfg = v2p_cfg(40)
+    cfg["env"]["motion_player"] = "stream"
+    torch.manual_seed(2)
+    env = PhysicsMVAEController(cfg, SIM_PARAMS, 1, "cuda", 0, True)
+    p = env._mvae_player
+    assert isinstance(p, StreamMotionPlayer)
+    ring = p._ring["_joint_rotmat"].view(p.K, 40, 24, 3, 3)
+    env.reset()
+    env.enable_cuda_graph()
+    for i in range(5):
+        t0, off0 = int(p._t), p._off.clone()
+        env.step(torch.zeros(40, env.num_actions, device=DEV))
+        assert int(p._t) == t0 + 1
+        want = ring[(t0 + 1 + off0) % p.K, torch.arange(40, device=DEV)]
+        assert torch.equal(p._joint_rotmat, want)
+        done = torch.tensor([1, 7, 20], device=DEV) if i == 2 else env.reset_buf.nonzero(as_tuple=False).flatten()
+        env.reset(done)
+        keep = torch.ones(40, dtype=torch.bool, device=DEV)
+        keep[done] = False
+        assert torch.equal(p._off[keep], off0[keep])
+        assert bool(torch.isfinite(env.obs_buf).all())
+    det = torch.linalg.det(p._joint_rotmat.reshape(-1, 3, 3))
+    assert float((det - 1).abs().max()) < 1e-4
+
+
 def test_controller_end_to_end():
     """config-3 style rollout (synthetic motion generator, zero-residual low-level policy): 150 high-level steps"""
     from helpers import SIM_PARAMS, v2p_cfg

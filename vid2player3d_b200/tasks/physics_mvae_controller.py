@@ -135,6 +135,55 @@ class SyntheticMotionPlayer:
         self._update_rotmat()
 
 
+class StreamMotionPlayer:
+    """The "synthetic kinematic target stream" of SURVEY.md 8d (config 3): K frames of the SyntheticMotionPlayer's random walk are
+    generated ONCE and kept in HBM (joint rotation matrices [K, N, 24, 3, 3] = 7 MB per frame at 8192 envs); a step gathers frame
+    (t + offset[env]) % K of every env into the fixed buffers the FK kernel reads (one gather per field, no per-step math), a reset
+    re-draws the env's offset.  Same fields and methods as SyntheticMotionPlayer; everything is in place and sync-free, so step and
+    masked reset live in CUDA graphs.  The latent action does not steer the stream (throughput stand-in; the MVAE network is out of
+    the kernel path).  The stream is not periodic: an env's targets jump once every K steps."""
+
+    FIELDS = ("_joint_rotmat", "_root_pos", "_racket_pos", "_phase_pred", "_swing_type", "_swing_type_cycle")
+
+    def __init__(self, num_envs, device, seed=10, frames=48, court_min=(-5.0, -16.0), court_max=(5.0, -10.0)):
+        src = SyntheticMotionPlayer(num_envs, device, seed=seed, court_min=court_min, court_max=court_max)
+        self.N, self.K, self.device = num_envs, frames, device
+        gen = torch.Generator(device=device).manual_seed(seed + 1)
+        src.reset(torch.arange(num_envs, device=device))
+        rings = {f: [] for f in self.FIELDS}
+        for _ in range(frames):
+            src.step(torch.clamp(torch.randn(num_envs, 32, device=device, generator=gen), -5, 5))
+            for f in self.FIELDS:
+                rings[f].append(getattr(src, f).clone())
+        self._ring = {f: torch.stack(v, 0).reshape(frames * num_envs, *v[0].shape[1:]).contiguous() for f, v in rings.items()}
+        for f in self.FIELDS:                                   # the live buffers the env reads (fixed addresses)
+            setattr(self, f, rings[f][0].clone())
+        self._t = torch.zeros((), device=device, dtype=torch.long)
+        self._off = torch.randint(0, frames, (num_envs,), device=device, generator=gen)
+        self._env = torch.arange(num_envs, device=device)
+        self._gather()
+
+    def _gather(self):
+        idx = torch.remainder(self._t + self._off, self.K) * self.N + self._env
+        for f in self.FIELDS:
+            torch.index_select(self._ring[f], 0, idx, out=getattr(self, f))
+
+    def step(self, mvae_actions, res_dof_actions=None):
+        self._t.add_(1)
+        self._gather()
+
+    def reset(self, env_ids):
+        self._off[env_ids] = torch.randint(0, self.K, (len(env_ids),), device=self.device)
+        self._gather()
+
+    def reset_masked(self, mask):
+        self._off.copy_(torch.where(mask, torch.randint(0, self.K, (self.N,), device=self.device), self._off))
+        self._gather()
+
+    def reset_dual(self, reset_reaction_env_ids, reset_recovery_env_ids):
+        self.reset(torch.cat([reset_reaction_env_ids, reset_recovery_env_ids]).sort().values)
+
+
 class PhysicsMVAEController:
     def __init__(self, cfg, sim_params, physics_engine, device_type, device_id, headless):
         self.cfg = cfg
@@ -249,6 +298,9 @@ class PhysicsMVAEController:
             task.step(torch.clamp(action, -1.0, 1.0))
         self._physics_player = SimpleNamespace(task=task, run_one_step=run_one_step)
         player = env.get("motion_player", None)
+        if player == "stream":       # resident target stream: the bench's choice
+            player = StreamMotionPlayer(self.num_envs, self.device, seed=self.cfg.get("seed", 10),
+                                        court_min=self.cfg_v2p.get('court_min', [-5, -16]), court_max=self.cfg_v2p.get('court_max', [5, -10]))
         if player is None:
             player = SyntheticMotionPlayer(self.num_envs, self.device, seed=self.cfg.get("seed", 10),
                                            court_min=self.cfg_v2p.get('court_min', [-5, -16]), court_max=self.cfg_v2p.get('court_max', [5, -10]))
