@@ -207,7 +207,7 @@ def dual_workload(envs, device_index, steps=96, warmup=16):
     torch.cuda.synchronize()
     return {"env_steps_per_s": envs * steps / (ms * 1e-3), "ms_per_step": ms / steps, "physics_ms_both_assets": p0.elapsed_time(p1) / 20,
             "steps": steps, "pair_resets_per_step": stats["resets"] / 2 / steps,
-            "mode": "one CUDA graph per high-level step (2 physics launches) + eager reference-shaped reset (id lists, host sync)",
+            "mode": "one CUDA graph per high-level step (2 physics launches) + reset(done ids) = nonzero() host sync, mask fill, one reset-graph replay",
             "workload": f"vid2player federer_djokovic dual: {envs} paired envs ({envs // 2} rallies), substeps 6, return_w_estimate, "
                         "use_random_ball_target, fix_head_orientation, synthetic incoming-ball table, resident kinematic target stream"}
 

@@ -282,6 +282,59 @@ def test_stream_motion_player_in_step_and_reset_graphs():
     assert float((det - 1).abs().max()) < 1e-4
 
 
+def test_dual_masked_reset_matches_id_list_reset_on_deterministic_fields():
+    """PhysicsMVAEControllerDual: the mask-driven reset (reset graph) against the reference-shaped id-list reset from the same state -
+    everything that does not depend on a random draw must agree"""
+    from helpers import v2p_dual_cfg
+    from vid2player3d_b200.tasks import PhysicsMVAEControllerDual
+    envs = []
+    for _ in range(2):
+        torch.manual_seed(21)
+        cfg = v2p_dual_cfg(32)
+        cfg["env"]["motion_player"] = "stream"
+        e = PhysicsMVAEControllerDual(cfg, SIM_PARAMS, 1, "cuda", 0, True)
+        e.reset()
+        for i in range(4):
+            e.step(torch.zeros(32, e.num_actions, device=DEV))
+        envs.append(e)
+    a, b = envs
+    ta, tb = a._physics_player.task, b._physics_player.task
+    assert torch.equal(ta._root_states, tb._root_states) and torch.equal(a._reset_reaction_buf, b._reset_reaction_buf)
+    ids = torch.tensor([4, 5, 18, 19], device=DEV)                      # two rallies restart; other envs may carry task resets
+    mask = torch.zeros(32, dtype=torch.bool, device=DEV)
+    mask[ids] = True
+    b._mvae_player._off.copy_(a._mvae_player._off)
+    a._reset_envs(ids)
+    b._mvae_player._off.copy_(a._mvae_player._off)                       # the stream offsets are random draws: align them first ...
+    b._mvae_player._gather()
+    off = b._mvae_player._off.clone()
+    b._reset_envs_masked(mask)
+    b._mvae_player._off.copy_(off)                                       # ... and keep them aligned
+    torch.cuda.synchronize()
+    for name in ("progress_buf", "reset_buf", "_terminate_buf", "_reset_reaction_buf", "_reset_recovery_buf", "_tar_time", "_tar_action",
+                 "_num_reset_reaction", "_bounce_in", "_distance"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    for name in ("_has_bounce", "_bounce_pos", "_has_racket_ball_contact"):
+        assert torch.equal(getattr(ta, name), getattr(tb, name)), name
+    servers = ids[1::2]                                                  # serve_from near: the even env receives, the odd one serves
+    sv, sa = tb._ball_root_states[servers], ta._ball_root_states[servers]
+    assert bool(torch.isfinite(sv).all()) and torch.equal(sv[:, 10:13], sa[:, 10:13])     # served spin; the velocity is a random draw,
+    assert bool((sv[:, 8] > 20).all())                                                    # snapped to the table grid: flies to the far side
+    untouched = torch.ones(32, dtype=torch.bool, device=DEV)
+    untouched[ids] = False
+    untouched &= ~(a._num_reset_reaction > 0)
+    assert torch.equal(ta._dof_state.view(32, -1)[untouched], tb._dof_state.view(32, -1)[untouched])
+    assert bool(torch.isfinite(b.obs_buf).all()) and bool(torch.isfinite(tb._root_states).all())
+    # and the graphs run
+    b.enable_cuda_graph()
+    for i in range(3):
+        b.step(torch.clamp(torch.randn(32, b.num_actions, device=DEV), -5, 5))
+        done = b.reset_buf.nonzero(as_tuple=False).flatten()
+        b.reset(done)
+        assert bool((b.reset_buf[done] == 0).all()) and bool(torch.isfinite(b.obs_buf).all())
+    assert b._reset_graph is not None
+
+
 def test_controller_end_to_end():
     """config-3 style rollout (synthetic motion generator, zero-residual low-level policy): 150 high-level steps"""
     from helpers import SIM_PARAMS, v2p_cfg

@@ -371,6 +371,38 @@ class HumanoidSMPLIMMVAEDual(HumanoidSMPLIMMVAE):
             traj = self._reset_balls(reset_actor_recovery_env_ids, reset_ball_env_ids)
         return traj
 
+    def _reset_balls_masked(self, serve_mask, recv_mask, opp):
+        """_reset_balls (:52-80) with masks instead of id lists (CUDA-graph safe): `serve_mask` = the recovery actors (servers),
+        `recv_mask` = the envs that receive a new incoming ball, `opp` = arange(N) ^ 1.  Same order of effects as the id-list form."""
+        bs, dev, N = self._ball_root_states, self.device, self.num_envs
+        m = serve_mask[:, None]
+        bs[:, 0:3] = torch.where(m, self._mvae_player._racket_pos, bs[:, 0:3])
+        if not hasattr(self, "_serve_spin"):
+            self._serve_spin = torch.tensor([-40.0, 0.0, 0.0], device=dev)    # created outside any graph capture (first, eager call)
+        bs[:, 10:13] = torch.where(m, self._serve_spin, bs[:, 10:13])
+        v = torch.stack([torch.rand(N, device=dev) * 4 + -2, torch.rand(N, device=dev) * 4 + 28, torch.rand(N, device=dev) * 3 + 5], -1)
+        bs[:, 7:10] = torch.where(m, v, bs[:, 7:10])
+        if not hasattr(self, "_in_buf"):
+            self._in_buf = (torch.empty(N, 50, 3, device=dev), torch.empty(N, 13, device=dev), torch.empty(N, 13, device=dev))
+        traj, s_in, s_out = self._in_buf
+        # every env as a receiver of the ball of its opponent; only the rows of recv_mask are used
+        native_v2p.ball_in_estimate(opp, self._root_states[1:], 26, self._in_table, self._in_params, traj, s_in, s_out)
+        r = recv_mask[:, None]
+        hit = recv_mask[opp][:, None]                      # envs whose ball was just handed over (contact_env_ids)
+        new = torch.where(r, s_in, bs)
+        new = torch.where(hit, s_out[opp], new)            # the hitter's own ball, snapped to the same grid point (written second)
+        bs.copy_(new)
+        self._has_bounce.masked_fill_(recv_mask, False)
+        self._bounce_pos.masked_fill_(r, 0.0)
+        self._has_racket_ball_contact.masked_fill_(recv_mask, False)
+        self._ball_pos.copy_(torch.where(r, bs[:, 0:3], self._ball_pos))
+        self._ball_vel.copy_(torch.where(r, bs[:, 7:10], self._ball_vel))
+        both = r | hit
+        rbs = self._rigid_body_state.view(N, 26, 13)
+        rbs[:, 25, 0:3] = torch.where(both, bs[:, 0:3], rbs[:, 25, 0:3])
+        rbs[:, 25, 7:13] = torch.where(both, bs[:, 7:13], rbs[:, 25, 7:13])
+        return traj
+
     def _reset_balls(self, reset_actor_recovery_env_ids, reset_ball_env_ids):
         """:52-80: serve = the ball at the server's racket with a random velocity; then every env in `reset_ball_env_ids` receives
         the ball its opponent just hit (b200v2p_ball_in_estimate), and the opponent's own ball is snapped to the same grid point."""

@@ -323,15 +323,19 @@ class PhysicsMVAEController:
             if self._has_init and self.num_envs > 1:
                 return
             env_ids = torch.arange(self.num_envs, device=self.device, dtype=torch.long)
-        if getattr(self, "_reset_graph", None) is not None:
-            # graph mode: the id list only fills a mask (2 launches), everything else is one graph replay
-            self._reset_mask.zero_()
-            if len(env_ids) > 0:
-                self._reset_mask.index_fill_(0, env_ids.to(self.device, dtype=torch.long), True)
-            self._reset_graph.replay()
-            self._has_init = True
-            return
-        self._reset_envs(env_ids)
+        if not self._reset_via_graph(env_ids):
+            self._reset_envs(env_ids)
+
+    def _reset_via_graph(self, env_ids):
+        """graph mode (enable_cuda_graph): the id list only fills a mask (2 launches), everything else is one replay of the reset graph"""
+        if getattr(self, "_reset_graph", None) is None:
+            return False
+        self._reset_mask.zero_()
+        if len(env_ids) > 0:
+            self._reset_mask.index_fill_(0, env_ids.to(self.device, dtype=torch.long), True)
+        self._reset_graph.replay()
+        self._has_init = True
+        return True
 
     def _reset_tasks_fast(self, update_state=False):
         """_reset_envs (:173-201) when no humanoid needs a reset - the common per-step case: new balls for the envs whose reaction
@@ -548,8 +552,8 @@ class PhysicsMVAEController:
             self.physics_step()
             self.post_physics_step()
         self._graph = g
-        if type(self)._reset_envs is PhysicsMVAEController._reset_envs and hasattr(self._mvae_player, "reset_masked"):
-            # second graph: the whole env reset, mask-driven (single-player controller with a graph-safe motion player)
+        if hasattr(self._mvae_player, "reset_masked"):
+            # second graph: the whole env reset, mask-driven (needs a graph-safe motion player)
             self._reset_mask = torch.zeros(self.num_envs, device=self.device, dtype=torch.bool)
             with torch.cuda.stream(s):
                 self._reset_envs_masked(self._reset_mask)          # warm-up with an all-false humanoid mask: only the task masks act
@@ -597,7 +601,57 @@ class PhysicsMVAEControllerDual(PhysicsMVAEController):
             if self._has_init:
                 return
             env_ids = torch.arange(self.num_envs, device=self.device, dtype=torch.long)
-        self._reset_envs(env_ids)
+        if not self._reset_via_graph(env_ids):
+            self._reset_envs(env_ids)
+
+    def _reset_envs_masked(self, mask):
+        """_reset_envs (:27-64) driven by a device mask of the humanoids to reset (both players of a pair set) instead of id lists:
+        full-width in-place ops and mask-aware kernels, no host synchronisation (captured as the reset graph).  Same order of
+        effects as the id-list form below: serve, then the ball hand-over through the incoming-ball table, then the task fields."""
+        task, N, dev = self._physics_player.task, self.num_envs, self.device
+        if not hasattr(self, "_near"):
+            ar = torch.arange(N, device=dev)
+            self._near = (ar % 2) == (0 if self.cfg_v2p.get('serve_from', 'near') == 'near' else 1)
+            self._opp = (ar ^ 1).contiguous()
+        reaction_actor, recovery_actor = mask & self._near, mask & ~self._near
+        self._reset_reaction_buf.logical_or_(reaction_actor)
+        self._reset_recovery_buf.logical_or_(recovery_actor)
+        R, Cm = self._reset_reaction_buf.clone(), self._reset_recovery_buf.clone()     # the id lists of the reference, as masks
+        self._mvae_player.reset_masked(mask)
+        if hasattr(self._mvae_player, "_swing_type"):
+            self._mvae_player._swing_type.masked_fill_(mask, -1)                       # reset_dual
+        for buf in (self.progress_buf, self.reset_buf, self._terminate_buf, self._num_reset_reaction):      # _reset_env_tensors
+            buf.masked_fill_(mask, 0)
+        self._reset_reaction_buf.masked_fill_(mask, False)
+        self._reset_recovery_buf.masked_fill_(mask, False)
+        self._distance.masked_fill_(mask, 0.0)
+        task._reset_actors_masked(mask)                                                # task.reset: the pairs' humanoids ...
+        traj = task._reset_balls_masked(recovery_actor, R, self._opp)                  # ... serve + hand-over for the reaction envs
+        if not self._use_history:
+            self._ball_traj[:, :traj.shape[1]] = torch.where(R[:, None, None], traj, self._ball_traj[:, :traj.shape[1]])
+        self._tar_action.masked_fill_(Cm, 0)                                           # _reset_recovery_tasks
+        task._has_bounce.masked_fill_(Cm, False)
+        task._bounce_pos.masked_fill_(Cm[:, None], 0.0)
+        if self._use_history:                                                          # _reset_reaction_tasks
+            self._ball_obs.copy_(torch.where(R[:, None, None], task._ball_pos[:, None, :].expand(-1, self._obs_ball_traj_length, -1), self._ball_obs))
+        self._tar_time.masked_fill_(R, 0)
+        self._tar_action.masked_fill_(R, 1)
+        self._num_reset_reaction.add_(R.to(torch.long))
+        self._bounce_in.masked_fill_(R, False)
+        if self.cfg_v2p.get('use_random_ball_target'):
+            seed = torch.rand(N, device=dev)
+            x = torch.where(seed < 0.33, -3.0, torch.where(seed > 0.67, 3.0, 0.0))
+            tgt = torch.stack([x, torch.full_like(x, 10.0), torch.zeros_like(x)], -1)
+            self._target_bounce_pos.copy_(torch.where(R[:, None], tgt, self._target_bounce_pos))
+        if self.cfg_v2p.get('reward_type') == 'return_w_estimate':
+            self._est_bounce_pos.masked_fill_(R[:, None], 0.0)
+            self._est_bounce_time.masked_fill_(R, 0.0)
+            self._est_bounce_in.masked_fill_(R, False)
+            self._est_max_height.masked_fill_(R, 0.0)
+        post = dict(self._post_cfg)
+        post["obs_only"] = 1
+        native_v2p.controller_post(post, self._tensors())
+        self._has_init = True
 
     def _reset_env_tensors(self, env_ids):
         """physics_mvae_controller.py:203-210"""
