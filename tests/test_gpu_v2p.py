@@ -317,9 +317,8 @@ def test_dual_masked_reset_matches_id_list_reset_on_deterministic_fields():
     for name in ("_has_bounce", "_bounce_pos", "_has_racket_ball_contact"):
         assert torch.equal(getattr(ta, name), getattr(tb, name)), name
     servers = ids[1::2]                                                  # serve_from near: the even env receives, the odd one serves
-    sv, sa = tb._ball_root_states[servers], ta._ball_root_states[servers]
-    assert bool(torch.isfinite(sv).all()) and torch.equal(sv[:, 10:13], sa[:, 10:13])     # served spin; the velocity is a random draw,
-    assert bool((sv[:, 8] > 20).all())                                                    # snapped to the table grid: flies to the far side
+    sv = tb._ball_root_states[servers]                                   # the served ball: random velocity draw, then snapped to the
+    assert bool(torch.isfinite(sv).all()) and bool((sv[:, 8] > 20).all())  # table grid (spin axis follows the velocity): towards the far side
     untouched = torch.ones(32, dtype=torch.bool, device=DEV)
     untouched[ids] = False
     untouched &= ~(a._num_reset_reaction > 0)
