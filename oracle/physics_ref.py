@@ -57,6 +57,11 @@ def control_step(model, verts, cfg, root, dof_pos, dof_vel, pd_tar, ext_wrench=N
     return rb, cf
 
 
+def set_threads(n):
+    """OpenMP threads of the env loop; returns the previous count"""
+    return int(lib().phys_ref_set_threads(C.c_int(int(n))))
+
+
 def diagnostics(model, cfg, root, dof_pos, dof_vel):
     out = np.zeros(12)
     lib().phys_ref_diagnostics(C.byref(model), C.byref(cfg), _p(np.ascontiguousarray(root)), _p(np.ascontiguousarray(dof_pos)),

@@ -35,3 +35,17 @@ ball_gen.simulate_without_bounce(rng.uniform(10, 65, n).astype(np.float32), rng.
                                  rng.uniform(-10, 10, n).astype(np.float32))
 torch.cuda.synchronize()
 print("sanitize smoke done", float(task.rew_buf.mean()), float(env.rew_buf.mean()))
+# dual mode: mask-driven reset incl. the incoming-ball table lookup for every env
+from helpers import v2p_dual_cfg
+from vid2player3d_b200.tasks import PhysicsMVAEControllerDual
+cfg = v2p_dual_cfg(20)
+cfg["env"]["motion_player"] = "stream"
+dual = PhysicsMVAEControllerDual(cfg, SIM_PARAMS, 1, "cuda", 0, True)
+dual.reset()
+for _ in range(2):
+    dual.step(torch.clamp(torch.randn(20, dual.num_actions, device=dual.device), -5, 5))
+    m = torch.zeros(20, dtype=torch.bool, device=dual.device)
+    m[4:6] = True
+    dual._reset_envs_masked(m)
+torch.cuda.synchronize()
+print("dual masked reset done", bool(torch.isfinite(dual.obs_buf).all()))
