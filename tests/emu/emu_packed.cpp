@@ -24,22 +24,21 @@ thread_local int emu_lane = 0;
 #include <vector>
 
 namespace {
-struct Job {
+template <typename T> struct Job {
   const DevBlob* B;
   const float* verts;
   const b200_cfg_t* cfg;
   int n, n_steps;
-  double *root, *dof_pos, *dof_vel;
-  const double *pd_tar, *ext;
-  double *rb_out, *contact_out, *ballio;
+  T *root, *dof_pos, *dof_vel;
+  const T *pd_tar, *ext;
+  T *rb_out, *contact_out, *ballio;
   int32_t* hits;
 };
 
 // one warp = the body of physics_kernel_packed<double> (b200env.cu) for envs eb .. eb + EPW - 1
-void lane_main(EmuWarp* w, int lane, const Job* J, int64_t eb, double* wrec) {
+template <typename T> void lane_main(EmuWarp* w, int lane, const Job<T>* J, int64_t eb, T* wrec) {
   emu_warp = w;
   emu_lane = lane;
-  typedef double T;
   const DevBlob& B = *J->B;
   const b200_model_t& M = B.m;
   const int n = J->n, nb = M.nb, nd = M.nd;
@@ -127,9 +126,9 @@ void lane_main(EmuWarp* w, int lane, const Job* J, int64_t eb, double* wrec) {
 }
 }  // namespace
 
-extern "C" int emu_packed_physics(const b200_model_t* model, const float* verts, const b200_cfg_t* cfg, int n, int n_steps, double* root,
-                                  double* dof_pos, double* dof_vel, const double* pd_tar, const double* ext, double* rb_out,
-                                  double* contact_out, double* ballio, int32_t* hits) {
+template <typename T>
+static int run(const b200_model_t* model, const float* verts, const b200_cfg_t* cfg, int n, int n_steps, T* root, T* dof_pos, T* dof_vel,
+               const T* pd_tar, const T* ext, T* rb_out, T* contact_out, T* ballio, int32_t* hits) {
   DevBlob hb;
   int slots_ok = 1;
   if (build_dev_blob(model, hb, &slots_ok) != 0 || !slots_ok || model->nb > B200_MAX_BODIES_PK) return -1;
@@ -137,15 +136,28 @@ extern "C" int emu_packed_physics(const b200_model_t* model, const float* verts,
   float* sv = soa.data();
   while ((uintptr_t)sv % 16) sv++;   // contact_hull reads the vertices with 128-bit loads
   verts_to_soa(model, verts, sv);
-  Job J{&hb, sv, cfg, n, n_steps, root, dof_pos, dof_vel, pd_tar, ext, rb_out, contact_out, ballio, hits};
-  std::vector<double> rec((size_t)EMU_EPW * ENV_STRIDE + 2, 0.0);
-  double* wrec = rec.data();
-  while ((uintptr_t)wrec % 16) wrec++;
+  Job<T> J{&hb, sv, cfg, n, n_steps, root, dof_pos, dof_vel, pd_tar, ext, rb_out, contact_out, ballio, hits};
+  std::vector<T> rec((size_t)EMU_EPW * ENV_STRIDE + 8, T(0));
+  T* wrec = rec.data();
+  while ((uintptr_t)wrec % 16) wrec++;   // the records are read with 128-bit accesses on the float path
   for (int64_t eb = 0; eb < n; eb += EMU_EPW) {
     EmuWarp w;
     std::vector<std::thread> th;
-    for (int lane = 0; lane < 32; lane++) th.emplace_back(lane_main, &w, lane, &J, eb, wrec);
+    for (int lane = 0; lane < 32; lane++) th.emplace_back(lane_main<T>, &w, lane, &J, eb, wrec);
     for (auto& t : th) t.join();
   }
   return 0;
+}
+
+// float64: the parity instantiation (vs oracle/physics_ref.c to round-off); float32: the arithmetic the product kernel runs
+// (host libm instead of the MUFU approximations of rcp_ / rsqrt_)
+extern "C" int emu_packed_physics(const b200_model_t* model, const float* verts, const b200_cfg_t* cfg, int n, int n_steps, double* root,
+                                  double* dof_pos, double* dof_vel, const double* pd_tar, const double* ext, double* rb_out,
+                                  double* contact_out, double* ballio, int32_t* hits) {
+  return run<double>(model, verts, cfg, n, n_steps, root, dof_pos, dof_vel, pd_tar, ext, rb_out, contact_out, ballio, hits);
+}
+extern "C" int emu_packed_physics_f32(const b200_model_t* model, const float* verts, const b200_cfg_t* cfg, int n, int n_steps, float* root,
+                                      float* dof_pos, float* dof_vel, const float* pd_tar, const float* ext, float* rb_out,
+                                      float* contact_out, float* ballio, int32_t* hits) {
+  return run<float>(model, verts, cfg, n, n_steps, root, dof_pos, dof_vel, pd_tar, ext, rb_out, contact_out, ballio, hits);
 }

@@ -91,3 +91,34 @@ def test_emulated_packed_step_with_racket_and_ball(variant):
     np.testing.assert_allclose(b1, b2, rtol=0, atol=1e-7)
     np.testing.assert_allclose(q1, q2, rtol=0, atol=1e-7)
     np.testing.assert_allclose(rb1, rb2, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_emulated_float32_path_config1_drop(variant):
+    """BASELINE config 1 on the CPU: one humanoid in the default pose (identity root at z = 0.89), zero action, 20 control steps incl.
+    the ground impact - the kernel's float32 arithmetic (128-bit record accesses, float device functions) vs the float64 restatement.
+    The GPU twin (tests/test_gpu_parity.py::test_physics_f32_config1_drop) runs 60 steps with the MUFU reciprocals."""
+    import build as emu_build
+    mod = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    ms, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    cfg = abi.make_cfg(mod)
+    n, steps = 3, 20
+    root = np.zeros((n, 13))
+    root[:, 2], root[:, 6] = 0.89, 1.0
+    root[1, 0:2] = [0.4, -0.3]
+    root[2, 2] = 0.95
+    q, qd = np.zeros((n, 69)), np.zeros((n, 69))
+    tar, ext = np.zeros((n, 69)), np.zeros((n, 6))
+    r64, q64, v64 = root.copy(), q.copy(), qd.copy()
+    physics_ref.control_step(ms, verts, cfg, r64, q64, v64, tar.copy(), ext.copy(), n_steps=steps)
+    f = lambda a: np.ascontiguousarray(a, np.float32)  # noqa: E731
+    r32, q32, v32, t32, e32 = f(root), f(q), f(qd), f(tar), f(ext)
+    rb, cf = np.zeros((n, ms.nb, 13), np.float32), np.zeros((n, ms.nb, 3), np.float32)
+    lib = C.CDLL(emu_build.build(variant))
+    rc = lib.emu_packed_physics_f32(C.byref(ms), _p(np.ascontiguousarray(verts, np.float32)), C.byref(cfg), C.c_int(n), C.c_int(steps), _p(r32),
+                                    _p(q32), _p(v32), _p(t32), _p(e32), _p(rb), _p(cf), None, None)
+    assert rc == 0
+    assert np.abs(q32 - q64).max() < 1e-4 and np.abs(v32 - v64).max() < 1e-3          # north_star: joint q within 1e-4
+    assert np.abs(r32[:, :7] - r64[:, :7]).max() < 1e-4
+    assert r64[0, 2] < 0.885 and np.abs(cf).max() > 1.0                               # it fell and touched the ground
+
