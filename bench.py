@@ -391,11 +391,20 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = task._env.launch_count
+    try:
+        task._env.set_kernel_timing(True)       # CUDA event pair around the physics launch of every step, on the launching stream
+    except Exception:
+        pass
     t_wall = time.perf_counter()
     evs = run(K, True)
     barrier()
     wall = time.perf_counter() - t_wall
     launches = task._env.launch_count - launches0
+    try:
+        phys_ms, phys_n = task._env.kernel_ms()
+        task._env.set_kernel_timing(False)
+    except Exception:
+        phys_ms, phys_n = 0.0, 0
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b, _ in evs]
     total_ms = sum(step_ms)
@@ -477,7 +486,11 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                      "kernel": ("step_kernel" if os.environ.get("B200ENV_KERNEL") == "lane" else
                                 "step_kernel_packed<fused>" if os.environ.get("B200ENV_SPLIT") == "0" else
-                                "one env step = pre_kernel + step_kernel_packed<split> (dominant, ~90 %) + post_kernel"), "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                                "one env step = pre_kernel + step_kernel_packed<split> (dominant, ~75 %) + post_kernel"), "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "dominant_kernel": {"name": "step_kernel_packed<split>", "ms": phys_ms, "launches_timed": phys_n,
+                                         "algorithmic_bytes_per_env": 3044, "GBps": (3044 * N / (phys_ms * 1e-3) / 1e9) if phys_ms > 0 else None,
+                                         "note": "CUDA event pair around this launch inside b200env_step (b200env_set_kernel_timing); its share of "
+                                                 "the step's algorithmic bytes: state rows + PD targets + wrench in, state / rigid-body / contact rows out"},
                      "peak_source": peak_src,
                      "note": "latency / FP32-issue bound along the 9-level kinematic chain, not HBM bound (DESIGN.md 5)"},
     }

@@ -208,6 +208,13 @@ int b200env_set_env_slice(b200env_handle h, int32_t env_first, int32_t env_strid
 /* number of kernels launched by this handle so far (bench.py "gpu_launches") */
 int64_t b200env_launch_count(b200env_handle h);
 
+/* Measurement aid (bench.py `roofline.kernel_ms`): with timing on, b200env_step records a CUDA event pair around the physics launch
+ * (step_kernel_packed / step_kernel_packed3 / the fused kernel) on the launching stream.  b200env_kernel_ms synchronises the recorded
+ * events, returns the mean duration in ms of the launches since the last call (or since timing was switched on) in *mean_ms and their
+ * number in *count, and clears the record.  At most 4096 launches are kept between two reads; not for use inside a CUDA graph capture. */
+int b200env_set_kernel_timing(b200env_handle h, int32_t on);
+int b200env_kernel_ms(b200env_handle h, double* mean_ms, int32_t* count);
+
 #ifdef __cplusplus
 }
 #endif

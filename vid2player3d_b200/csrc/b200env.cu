@@ -67,6 +67,8 @@ struct b200env {
   int packed;        // 1: 4-envs-per-warp kernels (packed.cuh); 0: lane-per-body kernels.  env B200ENV_KERNEL=lane|packed
   int packed_ok;     // tree fits the packed layout (<= 8 bodies per depth, <= 25 bodies)
   int64_t launches;
+  int timing;                          // b200env_set_kernel_timing: event pairs around the physics launch
+  std::vector<cudaEvent_t>* tev;       // recorded (start, stop) pairs
 };
 
 static thread_local char g_err[512] = "";
@@ -1739,6 +1741,7 @@ int b200env_destroy(b200env_handle h) {
   cudaFree(h->d_cfg);
   cudaFree(h->d_ticket);
   cudaFree(h->d_ext);
+  if (h->tev) { for (cudaEvent_t e : *h->tev) cudaEventDestroy(e); delete h->tev; }
   delete h;
   return 0;
 }
@@ -1814,6 +1817,11 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
       const int io_grid = need_ctas(h);
       pre_kernel<<<io_grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->bufs, h->ml, actions,
                                                                            h->num_envs, h->env_first, h->env_stride, h->d_ext);
+      cudaEvent_t tv0 = nullptr, tv1 = nullptr;
+      if (h->timing && h->tev && h->tev->size() < 8192) {
+        if (cudaEventCreate(&tv0) == cudaSuccess && cudaEventCreate(&tv1) == cudaSuccess) cudaEventRecord(tv0, (cudaStream_t)stream);
+        else tv0 = tv1 = nullptr;
+      }
       if (h->packed3)
         step_kernel_packed3<<<h->step_grid, PK3_WARPS * 32, psmem, (cudaStream_t)stream>>>(
             (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->num_envs, h->d_ticket, h->env_first, h->env_stride, h->d_ext);
@@ -1821,6 +1829,7 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
         step_kernel_packed<true><<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>(
             (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->ml, actions, h->num_envs, h->d_ticket, h->env_first,
             h->env_stride, h->d_ext);
+      if (tv0) { cudaEventRecord(tv1, (cudaStream_t)stream); h->tev->push_back(tv0); h->tev->push_back(tv1); }
       if (h->cfg.task_mode == 0)
         post_kernel<<<io_grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->bufs, h->ml, h->num_envs,
                                                                               h->env_first, h->env_stride);
@@ -1974,6 +1983,35 @@ int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_st
 }
 
 int64_t b200env_launch_count(b200env_handle h) { return h ? h->launches : 0; }
+
+int b200env_set_kernel_timing(b200env_handle h, int32_t on) {
+  if (!h) return fail(-1, "b200env_set_kernel_timing: null handle%s");
+  if (!h->tev) h->tev = new std::vector<cudaEvent_t>();
+  for (cudaEvent_t e : *h->tev) cudaEventDestroy(e);
+  h->tev->clear();
+  h->timing = on ? 1 : 0;
+  return 0;
+}
+
+int b200env_kernel_ms(b200env_handle h, double* mean_ms, int32_t* count) {
+  if (!h || !mean_ms || !count) return fail(-1, "b200env_kernel_ms: null argument%s");
+  *mean_ms = 0.0;
+  *count = 0;
+  if (!h->tev || h->tev->empty()) return 0;
+  cudaSetDevice(h->device);
+  double sum = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < h->tev->size(); i += 2) {
+    float ms = 0.f;
+    if (cudaEventSynchronize((*h->tev)[i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, (*h->tev)[i], (*h->tev)[i + 1]) == cudaSuccess) { sum += ms; n++; }
+  }
+  for (cudaEvent_t e : *h->tev) cudaEventDestroy(e);
+  h->tev->clear();
+  cudaGetLastError();
+  if (n) *mean_ms = sum / n;
+  *count = n;
+  return 0;
+}
 
 int b200env_set_env_slice(b200env_handle h, int32_t env_first, int32_t env_stride) {
   if (!h) return fail(-1, "b200env_set_env_slice: null handle%s");

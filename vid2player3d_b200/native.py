@@ -13,7 +13,8 @@ _lib = None
 
 SYMBOLS = ["b200env_abi_version", "b200env_last_error", "b200env_create", "b200env_destroy", "b200env_bind",
            "b200env_set_motion_lib", "b200env_step", "b200env_reset", "b200env_motion_state", "b200env_obs_imitation",
-           "b200env_physics_only", "b200env_launch_count", "b200env_set_env_slice", "b200env_motion_context"]
+           "b200env_physics_only", "b200env_launch_count", "b200env_set_env_slice", "b200env_motion_context", "b200env_set_kernel_timing",
+           "b200env_kernel_ms"]
 
 
 def lib():
@@ -145,3 +146,13 @@ class Env:
     @property
     def launch_count(self):
         return int(lib().b200env_launch_count(self._h))
+
+    def set_kernel_timing(self, on=True):
+        """event pairs around the physics launch of every step (measurement aid, include/b200env.h)"""
+        _check(lib().b200env_set_kernel_timing(self._h, C.c_int32(1 if on else 0)))
+
+    def kernel_ms(self):
+        """(mean ms, count) of the physics launches since the last call"""
+        ms, n = C.c_double(0.0), C.c_int32(0)
+        _check(lib().b200env_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
