@@ -27,7 +27,7 @@ extern "C" {
 #define B200_MAX_BODIES 32
 #define B200_MAX_DOF 96
 #define B200_MAX_KEY 8
-#define B200_ABI_VERSION 3
+#define B200_ABI_VERSION 4
 
 /* Per-asset constant block produced by vid2player3d_b200/model_compiler.py from the MJCF/STL
  * assets (replaces gym.load_asset + create_actor + set_actor_dof_properties:
@@ -90,6 +90,13 @@ typedef struct b200_cfg {
   float racket_head_halfthick, racket_head_radius;
   float racket_head_quat[4]; /* xyzw, racket frame -> head frame whose +y is the string-bed normal: identity for the right-handed
                                 assets, 45 deg about x for nadal.xml's cylinder fromto="0 -.015 -.015 0 .015 .015" */
+  /* --- optional: the other contacts of the ball (in the reference the ball collides with every shape of the env: collision filter 0,
+   * humanoid_smpl_im_mvae.py:436-442).  Default off.  Bodies: every convex-hull vertex is a sphere of a per-body radius (half the mean
+   * vertex spacing); handle: the cylinder fromto="0.5 0 0 0.15 0 0" size 0.016 of the Racket body as a capsule.  The deepest contact of
+   * a substep gets the impulse (restitution / Coulomb friction like the string bed); the obstacle is kinematic (no reaction on it). */
+  int32_t ball_body_contact;
+  float ball_e_body, ball_mu_body; /* PhysX "average" of the ball (0.9 / 0.2) and a default shape (0 / 1): 0.45, 0.6 */
+  float racket_handle[7];          /* racket frame: p0[3], p1[3], radius; radius 0 = no handle */
 } b200_cfg_t;
 
 /* Reference MoCap buffer (embodied_pose/utils/motion_lib.py:68-93): flat device arrays. */

@@ -426,6 +426,91 @@ static void ball_substep_ref(const b200_cfg_t* cfg, real h, ball_t* B, const bod
   }
 }
 
+/* ball-body contact (b200_cfg_t::ball_body_contact): per-body radius of the spheres that stand for the hull vertices - the same float
+ * arithmetic as csrc/dyn_common.cuh::hull_vertex_radius */
+static void hull_vertex_radius_ref(const b200_model_t* model, const float* verts, float* vrho) {
+  for (int b = 0; b < B200_MAX_BODIES; b++) vrho[b] = 0.0f;
+  for (int b = 0; b < model->nb; b++) {
+    const int nv = model->nverts[b];
+    if (nv < 2) continue;
+    const float* v = verts + (size_t)b * model->vmax * 3;
+    double sum = 0.0;
+    for (int i = 0; i < nv; i++) {
+      double best = 1e30;
+      for (int j = 0; j < nv; j++) {
+        if (j == i) continue;
+        const double dx = (double)v[i * 3] - v[j * 3], dy = (double)v[i * 3 + 1] - v[j * 3 + 1], dz = (double)v[i * 3 + 2] - v[j * 3 + 2];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 > 1e-12 && d2 < best) best = d2;
+      }
+      sum += sqrt(best);
+    }
+    double r = 0.5 * sum / nv;
+    r = r < 0.005 ? 0.005 : (r > 0.05 ? 0.05 : r);
+    vrho[b] = (float)r;
+  }
+}
+
+/* float64 restatement of csrc/packed.cuh::pk_ball_contacts_extra: the ball against the bodies (hull vertices as spheres) and the racket
+ * handle (capsule), poses of the start of the substep, deepest contact only, kinematic obstacle */
+static void ball_contacts_extra_ref(const b200_model_t* m, const float* verts, const b200_cfg_t* cfg, const float* vrho, const body_t* B,
+                                    ball_t* ball) {
+  real R = cfg->ball_radius;
+  {
+    real dx = ball->p[0] - B[0].p[0], dy = ball->p[1] - B[0].p[1], dz = ball->p[2] - B[0].p[2];
+    if (dx * dx + dy * dy + dz * dz > 2.25) return;
+  }
+  real best = 0, bn[3] = {0, 0, 1}, bvo[3] = {0, 0, 0}, be = cfg->ball_e_body, bmu = cfg->ball_mu_body;
+  for (int b = 0; b < m->nb; b++) {
+    const int handle = b == cfg->racket_body && cfg->racket_handle[6] > 0;
+    const int nv = m->nverts[b];
+    if (nv == 0 && !handle) continue;
+    const body_t* bd = &B[b];
+    real d[3] = {ball->p[0] - bd->p[0], ball->p[1] - bd->p[1], ball->p[2] - bd->p[2]};
+    real d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    real reach = handle ? (real)0.6 : (real)m->radius[b] + (real)vrho[b] + R;
+    if (d2 > reach * reach) continue;
+    real dl[3], el[3] = {0, 0, 0}, dist = 0, rad = 0;
+    q_rot_inv(bd->Q, d, dl);
+    if (handle) {
+      const float* hd = cfg->racket_handle;
+      real a[3] = {(real)hd[3] - hd[0], (real)hd[4] - hd[1], (real)hd[5] - hd[2]};
+      real q0[3] = {dl[0] - hd[0], dl[1] - hd[1], dl[2] - hd[2]};
+      real t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) / (a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      t = t < 0 ? 0 : (t > 1 ? 1 : t);
+      for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
+      dist = sqrt(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
+      rad = hd[6];
+    } else {
+      const float* vb = verts + (size_t)b * m->vmax * 3;
+      real m2 = 1e30;
+      for (int k = 0; k < nv; k++) {
+        real ex = dl[0] - vb[k * 3], ey = dl[1] - vb[k * 3 + 1], ez = dl[2] - vb[k * 3 + 2];
+        real e2 = ex * ex + ey * ey + ez * ez;
+        if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+      }
+      dist = sqrt(m2);
+      rad = vrho[b];
+    }
+    real pen = R + rad - dist;
+    if (pen > best && dist > 1e-9) {
+      best = pen;
+      real nl[3] = {el[0] / dist, el[1] / dist, el[2] / dist};
+      q_rot(bd->Q, nl, bn);
+      real x[3] = {d[0] - R * bn[0], d[1] - R * bn[1], d[2] - R * bn[2]}, wxx[3];
+      cross(bd->w, x, wxx);
+      for (int k = 0; k < 3; k++) bvo[k] = bd->v[k] + wxx[k];
+      be = handle ? cfg->ball_e_racket : cfg->ball_e_body;
+      bmu = handle ? cfg->ball_mu_racket : cfg->ball_mu_body;
+    }
+  }
+  if (best > 0) {
+    real J[3];
+    ball_impulse_ref(cfg, ball, bn, bvo, be, bmu, J);
+    for (int k = 0; k < 3; k++) ball->p[k] += best * bn[k];
+  }
+}
+
 /* One control step (control_freq_inv sim steps x substeps) for n envs.  Same I/O contract as
  * b200env_physics_only(prec=1) in include/b200env.h.  Returns 0, or -(env+1) on a failed solve. */
 int phys_ref_control_step_ball(const b200_model_t* m, const float* verts, const b200_cfg_t* cfg, int n, double* root,
@@ -434,6 +519,8 @@ int phys_ref_control_step_ball(const b200_model_t* m, const float* verts, const 
   int nb = m->nb, nd = m->nd, fail = 0;
   real h = (real)cfg->sim_dt / cfg->substeps;
   const int with_ball = cfg->has_ball && ballio != 0;
+  float vrho[B200_MAX_BODIES];
+  hull_vertex_radius_ref(m, verts, vrho);
 #pragma omp parallel for schedule(static)
   for (int e = 0; e < n; e++) {
     body_t B[B200_MAX_BODIES];
@@ -463,9 +550,18 @@ int phys_ref_control_step_ball(const b200_model_t* m, const float* verts, const 
       }
       for (int k = 0; k < cfg->substeps && !err; k++) {
         real react[6] = {ball.rF[0], ball.rF[1], ball.rF[2], ball.rX[0], ball.rX[1], ball.rX[2]};
+        const body_t root0 = B[0];   /* substep() integrates the root in place; the other bodies keep their start-of-substep pose */
         err = substep(m, verts, cfg, h, B, pd_tar + (size_t)e * nd, (s == 0 && ext_wrench) ? ext_wrench + (size_t)e * 6 : 0, cf,
                       with_ball ? react : 0);
-        if (with_ball && !err) ball_substep_ref(cfg, h, &ball, cfg->racket_body >= 0 ? &B[cfg->racket_body] : 0);
+        if (with_ball && !err) {
+          ball_substep_ref(cfg, h, &ball, cfg->racket_body >= 0 ? &B[cfg->racket_body] : 0);
+          if (cfg->ball_body_contact) {   /* every body at its start-of-substep pose, like the kernel's records at that point */
+            const body_t root1 = B[0];
+            B[0] = root0;
+            ball_contacts_extra_ref(m, verts, cfg, vrho, B, &ball);
+            B[0] = root1;
+          }
+        }
       }
     }
     if (err) {

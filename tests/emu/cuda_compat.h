@@ -5,6 +5,7 @@
 // Nothing here is used by the product path.
 #pragma once
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <string.h>
 

@@ -132,6 +132,7 @@ static int run(const b200_model_t* model, const float* verts, const b200_cfg_t* 
   DevBlob hb;
   int slots_ok = 1;
   if (build_dev_blob(model, hb, &slots_ok) != 0 || !slots_ok || model->nb > B200_MAX_BODIES_PK) return -1;
+  hull_vertex_radius(model, verts, hb.t.vrho);
   std::vector<float> soa((size_t)model->nb * model->vmax * 3 + 16, 0.0f);
   float* sv = soa.data();
   while ((uintptr_t)sv % 16) sv++;   // contact_hull reads the vertices with 128-bit loads

@@ -122,3 +122,57 @@ def test_emulated_float32_path_config1_drop(variant):
     assert np.abs(r32[:, :7] - r64[:, :7]).max() < 1e-4
     assert r64[0, 2] < 0.885 and np.abs(cf).max() > 1.0                               # it fell and touched the ground
 
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_emulated_ball_body_and_handle_contacts(variant):
+    """optional ball contacts (b200_cfg_t::ball_body_contact): balls thrown at the torso, at a forearm and at the racket handle of
+    flying humanoids - lane emulation of the kernel code vs the float64 restatement, and the contacts really happen"""
+    mod = model_compiler.canonical_racket_last(model_compiler.load_compiled("smpl_mesh_humanoid_federer"))
+    ms, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    cfg_on = abi.make_cfg(mod, substeps=6, ball={"ball_body_contact": 1}, task_mode=1, pd_mode=1)
+    cfg_off = abi.make_cfg(mod, substeps=6, ball={}, task_mode=1, pd_mode=1)
+    assert cfg_on.racket_handle[6] > 0 and cfg_off.ball_body_contact == 0
+    names = [str(x) for x in mod["body_names"]]
+    n = 6
+    root, q, qd, tar, ext = states(n, 21, False)
+    root[:, 2] = 2.0
+    qd *= 0.2
+    # body poses at the start (a control step of ~0 length through the oracle)
+    tiny = abi.Cfg.from_buffer_copy(cfg_off)
+    tiny.sim_dt = 1e-12
+    rb, _ = physics_ref.control_step(ms, verts, tiny, root.copy(), q.copy(), qd.copy(), tar.copy(), None)
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(3)
+    ball = np.zeros((n, 13))
+    targets = ["Torso", "Chest", "L_Elbow", "R_Knee", "HANDLE", "HANDLE"]
+    for e, tname in enumerate(targets):
+        if tname == "HANDLE":
+            b = names.index("Racket")
+            Rr = Rotation.from_quat(rb[e, b, 3:7]).as_matrix()
+            hd = np.array(list(cfg_on.racket_handle))
+            tgt = rb[e, b, 0:3] + Rr @ (0.5 * (hd[0:3] + hd[3:6]))
+            direction = Rr @ np.array([0.0, 0.0, 1.0])                   # across the handle, in the plane of the string bed
+        else:
+            b = names.index(tname)
+            Rb = Rotation.from_quat(rb[e, b, 3:7]).as_matrix()
+            tgt = rb[e, b, 0:3] + Rb @ np.asarray(mod["com"][b])
+            direction = rng.normal(size=3)
+            direction /= np.linalg.norm(direction)
+        ball[e, 0:3] = tgt + 0.12 * direction
+        ball[e, 7:10] = rb[e, b, 7:10] - 12.0 * direction                  # 12 m/s towards the target: 3.3 cm per substep
+        ball[e, 10:13] = rng.normal(0, 20, 3)
+    outs = {}
+    for name, cfg in (("on", cfg_on), ("off", cfg_off)):
+        b1, b2 = ball.copy(), ball.copy()
+        h1, h2 = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        r1, q1, v1 = root.copy(), q.copy(), qd.copy()
+        emu_step(variant, ms, verts, cfg, r1, q1, v1, tar.copy(), ext.copy(), 1, b1, h1)
+        r2, q2, v2 = root.copy(), q.copy(), qd.copy()
+        physics_ref.control_step(ms, verts, cfg, r2, q2, v2, tar.copy(), ext.copy(), n_steps=1, ball=b2, hits=h2)
+        np.testing.assert_allclose(b1, b2, rtol=0, atol=1e-8, err_msg=name)
+        np.testing.assert_allclose(q1, q2, rtol=0, atol=1e-9, err_msg=name)
+        outs[name] = b2
+    dv = np.linalg.norm(outs["on"][:, 7:10] - outs["off"][:, 7:10], axis=1)
+    assert (dv > 3.0).sum() >= 5, dv                                        # the ball bounced off the bodies / the handle
+    assert np.isfinite(outs["on"]).all()

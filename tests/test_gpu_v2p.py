@@ -714,3 +714,46 @@ def test_left_handed_dual_pair():
     d_r = np.linalg.norm(rbs[1::2, 24, 0:3] - rbs[1::2, 22, 0:3], axis=1)
     np.testing.assert_allclose(d_l, 0.5, atol=1e-4)
     np.testing.assert_allclose(d_r, 0.5, atol=1e-4)
+
+
+def test_ball_body_contact_option_on_gpu():
+    """b200_cfg_t::ball_body_contact through the product path (float32 kernels): balls thrown at the torso bounce off it when the
+    option is on and fly through when it is off; double kernel == float64 restatement with the option on"""
+    from oracle import physics_ref
+    from vid2player3d_b200 import abi, model_compiler, native
+    mod = model_compiler.canonical_racket_last(model_compiler.load_compiled("smpl_mesh_humanoid_federer"))
+    ms, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    names = [str(x) for x in mod["body_names"]]
+    n = 32
+    rng = np.random.default_rng(8)
+    root = np.zeros((n, 13)); root[:, 2] = 2.0; root[:, 3:7] = [0.5, 0.5, 0.5, 0.5]
+    q, qd = rng.normal(0, 0.2, (n, 69)), np.zeros((n, 69))
+    tar, ext = q.copy(), np.zeros((n, 6))
+    tiny = abi.Cfg.from_buffer_copy(abi.make_cfg(mod, substeps=6, ball={}, task_mode=1, pd_mode=1))
+    tiny.sim_dt = 1e-12
+    rb, _ = physics_ref.control_step(ms, verts, tiny, root.copy(), q.copy(), qd.copy(), tar.copy(), None)
+    b = names.index("Chest")
+    ball = np.zeros((n, 13))
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    ball[:, 0:3] = rb[:, b, 0:3] + 0.25 * d
+    ball[:, 7:10] = -15.0 * d
+    res = {}
+    for on in (0, 1):
+        cfg = abi.make_cfg(mod, substeps=6, ball={"ball_body_contact": on}, task_mode=1, pd_mode=1)
+        env = native.Env(ms, verts, cfg, 4, 0)
+        for dt, prec_tol in ((torch.float32, None), (torch.float64, 1e-8)):
+            t = lambda a: torch.tensor(a, dtype=dt, device=DEV).contiguous()  # noqa: E731
+            r, qq, vv, tt, ee, bb = t(root), t(q), t(qd), t(tar), t(ext), t(ball)
+            rbo, cf = torch.zeros(n, 25, 13, dtype=dt, device=DEV), torch.zeros(n, 25, 3, dtype=dt, device=DEV)
+            hits = torch.zeros(n, dtype=torch.int32, device=DEV)
+            env.physics_only(r, qq, vv, tt, ee, rbo, cf, n_steps=2, ball=bb, ball_hits=hits)
+            torch.cuda.synchronize()
+            if prec_tol is not None:
+                ro, qo, vo, bo = root.copy(), q.copy(), qd.copy(), ball.copy()
+                physics_ref.control_step(ms, verts, cfg, ro, qo, vo, tar.copy(), ext.copy(), n_steps=2, ball=bo, hits=np.zeros(n, np.int32))
+                np.testing.assert_allclose(bb.cpu().numpy(), bo, rtol=0, atol=prec_tol)
+            else:
+                res[on] = bb.cpu().numpy()
+    along_on, along_off = (res[1][:, 7:10] * d).sum(1), (res[0][:, 7:10] * d).sum(1)     # velocity along the approach axis (-15 at launch)
+    assert (along_off < -13).all()                          # option off: the ball flies through the body
+    assert (along_on > -8).mean() >= 0.9                    # option on: stopped / thrown back by the chest (float64 oracle: -4 .. +6)

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 MAX_BODIES, MAX_DOF, MAX_KEY = 32, 96, 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Model(C.Structure):
@@ -41,6 +41,7 @@ class Cfg(C.Structure):
         ("bounce_threshold_velocity", C.c_float),
         ("racket_head_center", C.c_float * 3), ("racket_head_halfthick", C.c_float), ("racket_head_radius", C.c_float),
         ("racket_head_quat", C.c_float * 4),
+        ("ball_body_contact", C.c_int32), ("ball_e_body", C.c_float), ("ball_mu_body", C.c_float), ("racket_handle", C.c_float * 7),
     ]
 
 
@@ -163,7 +164,26 @@ def make_cfg(model, *, sim_dt=1.0 / 60.0, substeps=2, control_freq_inv=2, gravit
                   "ball_mu_racket", "bounce_threshold_velocity", "racket_head_halfthick", "racket_head_radius"):
             setattr(c, k, b[k])
         _fill(c.racket_head_center, b["racket_head_center"])
+        # optional ball contacts with the bodies / the racket handle (include/b200env.h; default off)
+        c.ball_body_contact = int(bool(b.get("ball_body_contact", 0)))
+        c.ball_e_body, c.ball_mu_body = float(b.get("ball_e_body", 0.45)), float(b.get("ball_mu_body", 0.6))
+        _fill(c.racket_handle, racket_handle_from_prims(model))
     return c
+
+
+def racket_handle_from_prims(model):
+    """the thin cylinder of the Racket body (the grip, e.g. federer.xml fromto="0.5 0 0 0.15 0 0" size 0.016) as p0, p1, radius;
+    zeros when the asset has none"""
+    names = [str(x) for x in model["body_names"]]
+    if "Racket" not in names or len(model["prims"]) == 0:
+        return [0.0] * 7
+    rows = [r for r in np.asarray(model["prims"]) if int(r[0]) == names.index("Racket")]
+    if not rows:
+        return [0.0] * 7
+    r = min(rows, key=lambda x: x[7])            # the head slab is the wide one (radius 0.15), the handle the thin one
+    if r[7] > 0.05:
+        return [0.0] * 7
+    return [float(x) for x in r[1:8]]
 
 
 def racket_head_from_prims(model):

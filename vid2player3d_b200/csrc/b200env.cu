@@ -1707,6 +1707,7 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   if (trc == -1) { delete h; return fail(-2, "b200env_create: bodies must be in topological order%s"); }
   if (trc == -2) { delete h; return fail(-2, "b200env_create: too many children per body%s"); }
   h->packed_ok = model->nb <= B200_MAX_BODIES_PK && slots_ok;
+  hull_vertex_radius(model, verts, hb.t.vrho);
   const char* kv = getenv("B200ENV_KERNEL");
   h->packed = h->packed_ok && !(kv && strcmp(kv, "lane") == 0);
   const char* sv = getenv("B200ENV_SPLIT");
@@ -1716,6 +1717,10 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   int wide = 0;
   for (int d = 0; d < MAX_LEVELS; d++) if (hb.t.lvl_all[d][SLOTS3] >= 0) wide = 1;
   h->packed3 = h->split && !wide && kv && strcmp(kv, "packed3") == 0;
+  if (cfg->has_ball && cfg->ball_body_contact && !h->packed) {
+    delete h;
+    return fail(-2, "b200env_create: ball_body_contact needs the packed kernels (the lane-per-body kernel does not have it)%s");
+  }
   const size_t vbytes = (size_t)model->nb * model->vmax * 3 * sizeof(float);
   h->blob_bytes = sizeof(DevBlob) + ((vbytes + 15) & ~(size_t)15);
   CUDA_OK(cudaMalloc(&h->d_blob, h->blob_bytes));

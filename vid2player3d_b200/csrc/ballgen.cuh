@@ -42,6 +42,8 @@ template <typename T> __device__ __forceinline__ PhysCfg<T> ballgen_cfg(const b2
   p.eg = T(c.e_ground); p.mug = T(c.mu_ground); p.er = T(0); p.mur = T(0); p.vth = T(c.bounce_threshold_velocity);
   p.hc[0] = p.hc[1] = p.hc[2] = T(0); p.hh = p.hr = T(0);
   p.hq[0] = p.hq[1] = p.hq[2] = T(0); p.hq[3] = T(1);
+  p.ball_body = 0; p.eb = p.mub = T(0);
+  for (int k = 0; k < 7; k++) p.hdl[k] = T(0);
   return p;
 }
 

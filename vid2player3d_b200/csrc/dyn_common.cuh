@@ -4,6 +4,7 @@
 // as host code under tests/emu/cuda_compat.h, which is how the packed kernels are checked lane by lane on the CPU
 // (tests/emu/emu_packed.cpp runs one host thread per lane, __syncwarp() = a barrier).
 #pragma once
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -25,6 +26,7 @@ struct DevTree {
   int32_t lvl_dyn[MAX_LEVELS][PK_SLOTS];      // non-welded bodies of the depth (dynamics), -1 padded
   int32_t child_rank[B200_MAX_BODIES];
   int32_t rix[B200_MAX_BODIES];               // record index of a body in the packed kernel's shared-memory layout = breadth-first rank
+  float vrho[B200_MAX_BODIES];                // ball-body contact: radius of the sphere every hull vertex of the body stands for (hull_vertex_radius)
 };
 struct DevBlob {
   b200_model_t m;
@@ -69,6 +71,30 @@ static inline int build_dev_blob(const b200_model_t* model, DevBlob& hb, int* sl
     for (int b = 0; b < model->nb; b++)
       if (model->depth[b] == d) hb.t.rix[b] = next++;
   return 0;
+}
+// ball-body contact (b200_cfg_t::ball_body_contact): a body's hull is stood in for by spheres on its vertices; radius = half the mean
+// distance of a vertex to its nearest neighbour, kept within [5 mm, 5 cm].  Same function (same float arithmetic) in oracle/physics_ref.c.
+static inline void hull_vertex_radius(const b200_model_t* model, const float* verts, float* vrho) {
+  for (int b = 0; b < B200_MAX_BODIES; b++) vrho[b] = 0.0f;
+  for (int b = 0; b < model->nb; b++) {
+    const int nv = model->nverts[b];
+    if (nv < 2) continue;
+    const float* v = verts + (size_t)b * model->vmax * 3;
+    double sum = 0.0;
+    for (int i = 0; i < nv; i++) {
+      double best = 1e30;
+      for (int j = 0; j < nv; j++) {
+        if (j == i) continue;
+        const double dx = (double)v[i * 3] - v[j * 3], dy = (double)v[i * 3 + 1] - v[j * 3 + 1], dz = (double)v[i * 3 + 2] - v[j * 3 + 2];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 > 1e-12 && d2 < best) best = d2;
+      }
+      sum += sqrt(best);
+    }
+    double r = 0.5 * sum / nv;
+    r = r < 0.005 ? 0.005 : (r > 0.05 ? 0.05 : r);
+    vrho[b] = (float)r;
+  }
 }
 // hull vertices AoS [nb][vmax][3] (ABI) -> SoA [nb][3][vmax] (what contact_hull reads with 128-bit loads); dst zero-initialised
 static inline void verts_to_soa(const b200_model_t* model, const float* verts, float* soa) {
@@ -206,6 +232,8 @@ template <typename T> struct PhysCfg {
   // tennis ball (vid2player): lane BALL_LANE integrates it next to the humanoid
   int has_ball, racket_body, wrist_body;
   T bm, bI, bR, spin_scale, eg, mug, er, mur, vth, hc[3], hh, hr, hq[4];
+  int ball_body;        // optional ball contacts with the bodies / the racket handle (b200_cfg_t::ball_body_contact)
+  T eb, mub, hdl[7];    // their restitution / friction; handle capsule p0[3] p1[3] radius in the racket frame
 };
 #ifndef ABL
 #define ABL 0   // tools/ablate.sh: 1 no physics, 2 epilogue = state write-back only, 3 no reward block, 4 no MoCap sample / targets, 5 no obs
@@ -235,6 +263,10 @@ template <typename T> __device__ __forceinline__ PhysCfg<T> make_phys_cfg(const 
   p.hh = T(c.racket_head_halfthick); p.hr = T(c.racket_head_radius);
 #pragma unroll
   for (int k = 0; k < 4; k++) p.hq[k] = T(c.racket_head_quat[k]);
+  p.ball_body = c.has_ball && c.ball_body_contact;
+  p.eb = T(c.ball_e_body); p.mub = T(c.ball_mu_body);
+#pragma unroll
+  for (int k = 0; k < 7; k++) p.hdl[k] = T(c.racket_handle[k]);
   return p;
 }
 

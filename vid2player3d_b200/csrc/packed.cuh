@@ -394,6 +394,79 @@ template <typename T> __device__ __forceinline__ void pk_root_integrate(const Ph
   str<R_Q, 13>(rec, o);
 }
 
+// Optional contacts of the ball with the humanoid's bodies and the racket handle (b200_cfg_t::ball_body_contact; float64 restatement:
+// oracle/physics_ref.c::ball_contacts_extra_ref).  Runs on the ball's lane right after ball_substep, against the poses / velocities the
+// bodies had at the start of the substep (what the records hold at that point, like the string-bed test).  A body's hull = spheres of
+// radius vrho[b] on its vertices, the handle = a capsule; the DEEPEST contact of the substep gets the impulse and the ball is moved out
+// of it.  The obstacle is kinematic: no reaction on the humanoid (57 g ball).
+template <typename T>
+__device__ __forceinline__ void pk_ball_contacts_extra(const DevBlob& B, const float* verts, const PhysCfg<T>& c, const T* env, Ball<T>& ball) {
+  const b200_model_t& M = B.m;
+  {
+    T rp[3];
+    ldr<R_P, 3>(env, rp);   // the root is record 0
+    const T dx = ball.p[0] - rp[0], dy = ball.p[1] - rp[1], dz = ball.p[2] - rp[2];
+    if (dx * dx + dy * dy + dz * dz > T(2.25)) return;   // nothing of the player within 1.5 m of the pelvis
+  }
+  T best = T(0), bn[3] = {T(0), T(0), T(1)}, bvo[3] = {T(0), T(0), T(0)}, be = c.eb, bmu = c.mub;
+  for (int b = 0; b < M.nb; b++) {
+    const bool handle = b == c.racket_body && c.hdl[6] > T(0);
+    const int nv = M.nverts[b];
+    if (nv == 0 && !handle) continue;
+    T s[13];   // Q[4] p[3] w[3] v[3]
+    ldr<R_Q, 13>(env + RIX(B, b) * REC, s);
+    const T *Q = s, *p = s + 4, *w = s + 7, *v = s + 10;
+    const T d[3] = {ball.p[0] - p[0], ball.p[1] - p[1], ball.p[2] - p[2]};
+    const T d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    const T reach = handle ? T(0.6) : T(M.radius[b]) + T(B.t.vrho[b]) + c.bR;
+    if (d2 > reach * reach) continue;
+    const T cq[4] = {-Q[0], -Q[1], -Q[2], Q[3]};
+    T dl[3], el[3] = {T(0), T(0), T(0)}, dist = T(0), rad = T(0);
+    qrot(cq, d, dl);   // ball centre in the body frame
+    if (handle) {
+      const T a[3] = {c.hdl[3] - c.hdl[0], c.hdl[4] - c.hdl[1], c.hdl[5] - c.hdl[2]};
+      const T q0[3] = {dl[0] - c.hdl[0], dl[1] - c.hdl[1], dl[2] - c.hdl[2]};
+      T t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) * rcp_(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t);
+#pragma unroll
+      for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
+      dist = sqrt_(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
+      rad = c.hdl[6];
+    } else {
+      const float* vb = verts + (size_t)b * M.vmax * 3;
+      T m2 = T(1e30);
+      for (int k = 0; k < nv; k++) {
+        const T ex = dl[0] - T(vb[k]), ey = dl[1] - T(vb[M.vmax + k]), ez = dl[2] - T(vb[2 * M.vmax + k]);
+        const T e2 = ex * ex + ey * ey + ez * ez;
+        if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+      }
+      dist = sqrt_(m2);
+      rad = T(B.t.vrho[b]);
+    }
+    const T pen = c.bR + rad - dist;
+    if (pen > best && dist > T(1e-9)) {
+      best = pen;
+      const T id = rcp_(dist);
+      const T nl[3] = {el[0] * id, el[1] * id, el[2] * id};
+      qrot(Q, nl, bn);
+      // velocity of the obstacle at the contact point x = c - R n
+      const T x[3] = {d[0] - c.bR * bn[0], d[1] - c.bR * bn[1], d[2] - c.bR * bn[2]};
+      T wxx[3];
+      cross3(w, x, wxx);
+#pragma unroll
+      for (int k = 0; k < 3; k++) bvo[k] = v[k] + wxx[k];
+      be = handle ? c.er : c.eb;
+      bmu = handle ? c.mur : c.mub;
+    }
+  }
+  if (best > T(0)) {
+    T J[3];
+    ball_impulse(c, ball, bn, bvo, be, bmu, J);
+#pragma unroll
+    for (int k = 0; k < 3; k++) ball.p[k] += best * bn[k];
+  }
+}
+
 // One control step for the warp's EPW envs.  wrec: the warp's records; valid: this lane's env exists.
 // The ball of env g is carried by lane (g, BALL_SLOT) in registers.
 #define BALL_SLOT 7
@@ -460,11 +533,14 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
           for (int k = 0; k < 3; k++) { rp[k] = rs[4 + k]; rw[k] = rs[7 + k]; rv[k] = rs[10 + k]; }
         }
         ball_substep<T>(c, ball, has_racket, rQ, rp, rv, rw);
+        if (c.ball_body) pk_ball_contacts_extra<T>(B, verts, c, env, ball);
         T* ext = env + ENV_EXT;
 #pragma unroll
         for (int k = 0; k < 3; k++) { ext[6 + k] = ball.rF[k]; ext[9 + k] = ball.rX[k]; }
       }
-      if (valid && s == 0) { pk_root<T>(c, env); pk_root_integrate<T>(c, env); }
+      if (valid && s == 0) pk_root<T>(c, env);
+      if (c.ball_body) __syncwarp();   // the extra ball contacts read the root's pose: integrate it only after the ball lane is done
+      if (valid && s == 0) pk_root_integrate<T>(c, env);
       __syncwarp();
       // 4. root -> leaves: accelerations + joint integration of a body, then at once its kinematics for the next substep
       //    (its parent's new pose is already in place); welded bodies only have the kinematics

@@ -172,11 +172,14 @@ __device__ __forceinline__ void control_step_packed3(const DevBlob& B, const flo
           for (int k = 0; k < 3; k++) { rp[k] = rs[4 + k]; rw[k] = rs[7 + k]; rv[k] = rs[10 + k]; }
         }
         ball_substep<T>(c, ball, has_racket, rQ, rp, rv, rw);
+        if (c.ball_body) pk_ball_contacts_extra<T>(B, verts, c, env, ball);
         T* ext = env + ENV_EXT;
 #pragma unroll
         for (int k = 0; k < 3; k++) { ext[6 + k] = ball.rF[k]; ext[9 + k] = ball.rX[k]; }
       }
-      if (valid && u == 0) { pk_root<T>(c, env); pk_root_integrate<T>(c, env); }
+      if (valid && u == 0) pk_root<T>(c, env);
+      if (c.ball_body) __syncwarp();   // the extra ball contacts read the root's pose: integrate it only after the ball lane is done
+      if (valid && u == 0) pk_root_integrate<T>(c, env);
       __syncwarp();
       // 4. root -> leaves: accelerations + joint integration of a body, then at once its kinematics for the next substep
       for (int d = 1; d <= M.max_depth; d++) {

@@ -104,6 +104,12 @@ class HumanoidSMPLIMMVAE(BaseTask):
         ball["ball_e_ground"] = 0.5 * (rest + plane_rest)                        # PhysX average combine
         ball["ball_mu_racket"] = 0.5 * (v2p.get("racket_friction", 0.8) + v2p.get("ball_friction", 0.2))
         ball["ball_mu_ground"] = 0.5 * (env.get("plane", {}).get("dynamicFriction", 1.0) + v2p.get("ball_friction", 0.2))
+        # optional (B200 addition, default off): the ball also collides with the humanoid's bodies and the racket handle, as it does in
+        # the reference's PhysX scene (ball collision filter 0, :436-442); include/b200env.h `ball_body_contact`
+        if v2p.get("ball_body_contact", False):
+            ball["ball_body_contact"] = 1
+            ball["ball_e_body"] = 0.5 * rest                                      # body shapes: default material (restitution 0, friction 1)
+            ball["ball_mu_body"] = 0.5 * (1.0 + v2p.get("ball_friction", 0.2))
         mk_cfg = lambda model: abi.make_cfg(  # noqa: E731
             model, sim_dt=self.sim_dt, substeps=self.sim_substeps, control_freq_inv=env.get("controlFrequencyInv", 2),
             pd_tar_lim=0.5 * np.pi, res_force_scale=self.residual_force_scale, res_torque_scale=self.residual_torque_scale,
