@@ -1,0 +1,52 @@
+"""B200ENV_SORT=1: the physics launch hands the envs out by ground-contact load (sort_count_kernel / sort_perm_kernel in
+csrc/b200env.cu).  Envs are independent, so the hand-out order must not change a single bit of any env's result.
+(File name: last in the suite on purpose - the option is off by default and was added after the last GPU slot of round 1.)"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import SIM_PARAMS, im_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _rollout(sort):
+    from vid2player3d_b200 import model_compiler, motion_lib
+    from vid2player3d_b200.tasks import HumanoidSMPLIM
+    model = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    flat = motion_lib.synthetic(model, num_motions=4, num_frames=80, seed=5)
+    old = os.environ.pop("B200ENV_SORT", None)
+    if sort:
+        os.environ["B200ENV_SORT"] = "1"
+    try:
+        torch.manual_seed(12)
+        task = HumanoidSMPLIM(im_cfg(150, flat), SIM_PARAMS, 1, "cuda", 0, True)     # 150: ragged last warp and batch
+    finally:
+        os.environ.pop("B200ENV_SORT", None)
+        if old is not None:
+            os.environ["B200ENV_SORT"] = old
+    task.reset()
+    g = torch.Generator(device=task.device).manual_seed(3)
+    out = []
+    for i in range(40):                                   # long enough for most humanoids to fall: contact loads differ widely
+        a = torch.rand(150, task.num_actions, device=task.device, generator=g) * 2 - 1
+        task.step(a)
+        if i == 25:
+            task.reset(torch.arange(0, 150, 7, device=task.device))
+        if i % 8 == 7 or i == 39:
+            out.append((task.obs_buf.clone(), task.rew_buf.clone(), task.reset_buf.clone(), task._rigid_body_state.clone(),
+                        task._dof_state.clone(), task._contact_forces.clone() if hasattr(task, "_contact_forces") else task.rew_buf.clone()))
+    return out, task
+
+
+def test_sorted_hand_out_is_bit_identical():
+    ref, t0 = _rollout(False)
+    got, t1 = _rollout(True)
+    for a, b in zip(ref, got):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    fallen = float((t1._rigid_body_state.view(150, -1, 13)[:, 0, 2] < 0.5).float().mean())
+    assert fallen > 0.3                                   # the workload really has contact-heavy envs
+    assert t1._env.launch_count > t0._env.launch_count    # the two sort launches ran

@@ -60,6 +60,9 @@ struct b200env {
   unsigned long long ticket_base;
   float* d_ext;                        // [num_envs rows of the bound tensors, 6] residual root wrench between pre_kernel and the physics launch
   int ext_rows;
+  int sort;                            // 1: envs handed out by contact load (B200ENV_SORT=1; split form, 4-envs-per-warp kernel)
+  int32_t *d_bin, *d_perm;             // [num_envs]
+  uint32_t *d_pos, *d_cnt;             // [num_envs], [SORT_BINS]
   int packed3;                         // 1: the physics launch is step_kernel_packed3 (B200ENV_KERNEL=packed3)
   int split;                           // 1: three launches (pre / physics / post), 0: one fused launch.  env B200ENV_SPLIT=0|1
   int env_first = 0, env_stride = 1;   // b200env_set_env_slice: local env i = row env_first + env_stride * i of the bound tensors
@@ -1025,7 +1028,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(PK_WARPS * 32, 1)
 step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
                    b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs, unsigned long long* __restrict__ ticket,
-                   int env_first, int env_stride, const float* __restrict__ ext_wrench) {
+                   int env_first, int env_stride, const float* __restrict__ ext_wrench, const int32_t* __restrict__ perm) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ __align__(8) uint64_t mbar;
   load_blob(smem, gblob, blob_bytes, &mbar);
@@ -1044,6 +1047,9 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
   if (lc.active) lc.rix = B.t.rix[lane];
   const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
   const int g = lane >> 3, s = lane & 7;
+  // hand-out order of the envs: identity, or (B200ENV_SORT=1) the permutation sort_perm_kernel built from the contact load, so that
+  // the envs of a warp / of a CTA batch have similar ground-contact work (tools/contact_imbalance.py)
+  auto row = [&](int64_t i) -> int64_t { return env_first + (int64_t)env_stride * (perm ? (int64_t)perm[i] : i); };
   // The CTA's warps form PK_GROUPS independent groups, each pulling its own batches and meeting at its own named barrier:
   // while one group is in the (memory-latency-bound) prologue / epilogue the other is in the (issue-bound) physics.
 #ifndef PK_GROUPS
@@ -1086,7 +1092,7 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
 #pragma unroll
       for (int k = 0; k < EPW; k++) {
         const int64_t ek = eb + k < num_envs ? eb + k : (int64_t)num_envs - 1;   // ragged tail: re-read the last env, never stored
-        const int64_t e = env_first + (int64_t)env_stride * ek;
+        const int64_t e = row(ek);
         if (lc.dyn && lane > 0) {
           const float* ds = bf.dof_state + (e * nd + lc.dof0) * 2;
 #pragma unroll
@@ -1136,7 +1142,7 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     const bool valid = eb + g < num_envs;
     Ball<float> ball;
     ball_clear(ball);
-    const int64_t erow_g = env_first + (int64_t)env_stride * (eb + g);
+    const int64_t erow_g = SPLIT ? row(valid ? eb + g : eb) : env_first + (int64_t)env_stride * (eb + g);
     if (cfg.has_ball && valid && s == BALL_SLOT) ball_load(bf, erow_g, ball);
     if (ABL != 1) control_step_packed<float>(B, verts, pc, wrec, lane, valid, ball, STEP_SYNC && full_batch);
 #if POST_SYNC
@@ -1147,7 +1153,7 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     if (cfg.has_ball && valid && s == BALL_SLOT) ball_writeback(bf, erow_g, ball);
     for (int k = 0; k < EPW; k++) {
       if (eb + k >= num_envs) break;
-      const int64_t e = env_first + (int64_t)env_stride * (eb + k);
+      const int64_t e = SPLIT ? row(eb + k) : env_first + (int64_t)env_stride * (eb + k);
       Lane<float> L;
       float cf[3];
       pk_load_state<float>(wrec + k * ENV_STRIDE, lc, lane, L, cf);
@@ -1160,6 +1166,53 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     }
     __syncwarp();
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// hand-out order by contact load (B200ENV_SORT=1, split form).  The per-vertex loop of contact_hull runs on the body's lane; a warp
+// executes, per body round, as many iterations as its slowest lane, and a CTA batch waits for its slowest warp: with fallen humanoids
+// handed out in env order the slowest warp of a batch has ~75 % more vertex iterations than the average one, sorted by load ~10 %
+// (tools/contact_imbalance.py).  sort_count_kernel: serial vertex iterations of every env from the rigid-body rows (the state the
+// step starts from) -> 16 bins, position inside the bin by atomicAdd (the order inside a bin does not matter: envs are independent,
+// every env's result is bit-identical whatever the order).  sort_perm_kernel: heaviest bin first.
+#define SORT_BINS 16
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+sort_count_kernel(const DevBlob* __restrict__ gblob, b200_buffers_t bf, int num_envs, int env_first, int env_stride, int32_t* __restrict__ bin,
+                  uint32_t* __restrict__ pos, uint32_t* __restrict__ cnt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
+  if (i >= num_envs) return;
+  const int64_t e = env_first + (int64_t)env_stride * i;
+  const b200_model_t& M = gblob->m;
+  const float* verts = reinterpret_cast<const float*>(gblob + 1);   // SoA [nb][3][vmax] behind the header
+  int c = 0;
+  if (lane < M.nb && M.nverts[lane] > 0 && !M.fixed[lane]) {
+    const float* rb = bf.rigid_body_state + (e * bf.bodies_per_env + lane) * 13;
+    const float pz = rb[2];
+    if (pz - M.radius[lane] < 0.f) {
+      const float x = rb[3], y = rb[4], z = rb[5], w = rb[6];
+      const float r6 = 2.f * (x * z - y * w), r7 = 2.f * (y * z + x * w), r8 = 1.f - 2.f * (x * x + y * y);   // z row of the rotation
+      const float* vb = verts + (size_t)lane * M.vmax * 3;
+      for (int k = 0; k < M.nverts[lane]; k++) c += (pz + r6 * vb[k] + r7 * vb[M.vmax + k] + r8 * vb[2 * M.vmax + k]) < 0.f;
+    }
+  }
+  // lanes 8r .. 8r+7 = the bodies of round r of the packed body pass: max per round, then the sum of the rounds
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) c = max(c, __shfl_xor_sync(FULL, c, o));
+  const int serial = __shfl_sync(FULL, c, 0) + __shfl_sync(FULL, c, 8) + __shfl_sync(FULL, c, 16) + __shfl_sync(FULL, c, 24);
+  if (lane == 0) {
+    const int b = min(serial / 3, SORT_BINS - 1);
+    bin[i] = b;
+    pos[i] = atomicAdd(&cnt[b], 1u);
+  }
+}
+__global__ void sort_perm_kernel(int num_envs, const int32_t* __restrict__ bin, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ cnt,
+                                 int32_t* __restrict__ perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_envs) return;
+  uint32_t off = 0;
+  for (int b = SORT_BINS - 1; b > bin[i]; b--) off += cnt[b];   // heaviest bin first
+  perm[off + pos[i]] = i;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1717,6 +1770,8 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   int wide = 0;
   for (int d = 0; d < MAX_LEVELS; d++) if (hb.t.lvl_all[d][SLOTS3] >= 0) wide = 1;
   h->packed3 = h->split && !wide && kv && strcmp(kv, "packed3") == 0;
+  const char* so = getenv("B200ENV_SORT");
+  h->sort = h->split && !h->packed3 && so && strcmp(so, "1") == 0;
   if (cfg->has_ball && cfg->ball_body_contact && !h->packed) {
     delete h;
     return fail(-2, "b200env_create: ball_body_contact needs the packed kernels (the lane-per-body kernel does not have it)%s");
@@ -1733,6 +1788,12 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   }
   CUDA_OK(cudaMalloc(&h->d_cfg, sizeof(b200_cfg_t)));
   CUDA_OK(cudaMemcpy(h->d_cfg, cfg, sizeof(b200_cfg_t), cudaMemcpyHostToDevice));
+  if (h->sort) {
+    CUDA_OK(cudaMalloc(&h->d_bin, sizeof(int32_t) * num_envs));
+    CUDA_OK(cudaMalloc(&h->d_perm, sizeof(int32_t) * num_envs));
+    CUDA_OK(cudaMalloc(&h->d_pos, sizeof(uint32_t) * num_envs));
+    CUDA_OK(cudaMalloc(&h->d_cnt, sizeof(uint32_t) * SORT_BINS));
+  }
   CUDA_OK(cudaMalloc(&h->d_ticket, sizeof(unsigned long long)));
   CUDA_OK(cudaMemset(h->d_ticket, 0, sizeof(unsigned long long)));
   *out = h;
@@ -1746,6 +1807,7 @@ int b200env_destroy(b200env_handle h) {
   cudaFree(h->d_cfg);
   cudaFree(h->d_ticket);
   cudaFree(h->d_ext);
+  cudaFree(h->d_bin); cudaFree(h->d_perm); cudaFree(h->d_pos); cudaFree(h->d_cnt);
   if (h->tev) { for (cudaEvent_t e : *h->tev) cudaEventDestroy(e); delete h->tev; }
   delete h;
   return 0;
@@ -1820,6 +1882,13 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
         h->ext_rows = rows;
       }
       const int io_grid = need_ctas(h);
+      if (h->sort) {
+        CUDA_OK(cudaMemsetAsync(h->d_cnt, 0, sizeof(uint32_t) * SORT_BINS, (cudaStream_t)stream));
+        sort_count_kernel<<<io_grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->bufs, h->num_envs, h->env_first,
+                                                                                    h->env_stride, h->d_bin, h->d_pos, h->d_cnt);
+        sort_perm_kernel<<<(h->num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->num_envs, h->d_bin, h->d_pos, h->d_cnt, h->d_perm);
+        h->launches += 2;
+      }
       pre_kernel<<<io_grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->bufs, h->ml, actions,
                                                                            h->num_envs, h->env_first, h->env_stride, h->d_ext);
       cudaEvent_t tv0 = nullptr, tv1 = nullptr;
@@ -1833,7 +1902,7 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
       else
         step_kernel_packed<true><<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>(
             (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->ml, actions, h->num_envs, h->d_ticket, h->env_first,
-            h->env_stride, h->d_ext);
+            h->env_stride, h->d_ext, h->sort ? h->d_perm : nullptr);
       if (tv0) { cudaEventRecord(tv1, (cudaStream_t)stream); h->tev->push_back(tv0); h->tev->push_back(tv1); }
       if (h->cfg.task_mode == 0)
         post_kernel<<<io_grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->bufs, h->ml, h->num_envs,
@@ -1844,7 +1913,7 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
     }
     step_kernel_packed<false><<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>(
         (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->ml, actions, h->num_envs, h->d_ticket, h->env_first,
-        h->env_stride, nullptr);
+        h->env_stride, nullptr, nullptr);
     CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;
