@@ -95,14 +95,14 @@ def test_emulated_packed_step_with_racket_and_ball(variant):
 
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_emulated_float32_path_config1_drop(variant):
-    """BASELINE config 1 on the CPU: one humanoid in the default pose (identity root at z = 0.89), zero action, 20 control steps incl.
+    """BASELINE config 1 on the CPU: one humanoid in the default pose (identity root at z = 0.89), zero action, 60 control steps incl.
     the ground impact - the kernel's float32 arithmetic (128-bit record accesses, float device functions) vs the float64 restatement.
-    The GPU twin (tests/test_gpu_parity.py::test_physics_f32_config1_drop) runs 60 steps with the MUFU reciprocals."""
+    The GPU twin (tests/test_gpu_parity.py::test_physics_f32_config1_drop) runs the same 60 steps with the MUFU reciprocals."""
     import build as emu_build
     mod = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
     ms, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
     cfg = abi.make_cfg(mod)
-    n, steps = 3, 20
+    n, steps = 3, 60
     root = np.zeros((n, 13))
     root[:, 2], root[:, 6] = 0.89, 1.0
     root[1, 0:2] = [0.4, -0.3]
