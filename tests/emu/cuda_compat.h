@@ -56,6 +56,14 @@ template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
   return r;
 }
 template <typename T> static inline T __shfl_xor_sync(unsigned m, T v, int x) { return __shfl_sync(m, v, emu_lane ^ x); }
+static inline unsigned __ballot_sync(unsigned, int p) {
+  emu_warp->pred[emu_lane] = p;
+  emu_warp->barrier();
+  unsigned r = 0;
+  for (int k = 0; k < 32; k++) r |= (emu_warp->pred[k] ? 1u : 0u) << k;
+  emu_warp->barrier();
+  return r;
+}
 static inline int __any_sync(unsigned, int p) {
   emu_warp->pred[emu_lane] = p;
   emu_warp->barrier();

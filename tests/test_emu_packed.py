@@ -176,3 +176,40 @@ def test_emulated_ball_body_and_handle_contacts(variant):
     dv = np.linalg.norm(outs["on"][:, 7:10] - outs["off"][:, 7:10], axis=1)
     assert (dv > 3.0).sum() >= 5, dv                                        # the ball bounced off the bodies / the handle
     assert np.isfinite(outs["on"]).all()
+
+
+def test_compacted_contact_phase_is_bit_identical():
+    """-DPK_CONTACT_COMPACT=1 (pk_contact_phase: bodies in contact compacted per env group, one lane per body) must reproduce the
+    in-place form bit for bit - float64 and float32 - on humanoids in natural ground contact over several control steps"""
+    import build as emu_build
+    mod = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    ms, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    cfg = abi.make_cfg(mod)
+    n = 9
+    root, q, qd, tar, ext = states(n, 31, True)
+    ext[:] = 0
+    root[:, 3:7] = [0.5, 0.5, 0.5, 0.5]
+    rng = np.random.default_rng(2)
+    for _ in range(35):                                           # let them fall: the restatement brings them to the ground
+        tar = np.clip(rng.uniform(-1, 1, (n, 69)), q - 0.5 * np.pi, q + 0.5 * np.pi)
+        physics_ref.control_step(ms, verts, cfg, root, q, qd, tar, None)
+    assert (root[:, 2] < 0.5).sum() >= 6                          # lying humanoids: many bodies in contact, uneven vertex counts
+    res = {}
+    for tag, flags in (("plain", ()), ("compact", ("-DPK_CONTACT_COMPACT=1",))):
+        lib = C.CDLL(emu_build.build("packed", flags))
+        r, qq, vv = root.copy(), q.copy(), qd.copy()
+        rb, cf = np.zeros((n, ms.nb, 13)), np.zeros((n, ms.nb, 3))
+        assert lib.emu_packed_physics(C.byref(ms), _p(np.ascontiguousarray(verts, np.float32)), C.byref(cfg), C.c_int(n), C.c_int(3), _p(r), _p(qq),
+                                      _p(vv), _p(tar.copy()), _p(ext.copy()), _p(rb), _p(cf), None, None) == 0
+        f = lambda a: np.ascontiguousarray(a, np.float32)  # noqa: E731
+        r32, q32, v32 = f(root), f(q), f(qd)
+        rb32, cf32 = np.zeros((n, ms.nb, 13), np.float32), np.zeros((n, ms.nb, 3), np.float32)
+        assert lib.emu_packed_physics_f32(C.byref(ms), _p(np.ascontiguousarray(verts, np.float32)), C.byref(cfg), C.c_int(n), C.c_int(3), _p(r32),
+                                          _p(q32), _p(v32), _p(f(tar)), _p(f(ext)), _p(rb32), _p(cf32), None, None) == 0
+        res[tag] = (r, qq, vv, rb, cf, r32, q32, v32, rb32, cf32)
+    for a, b in zip(res["plain"], res["compact"]):
+        assert np.array_equal(a, b)
+    assert (np.abs(res["plain"][4]).sum(-1) > 0).sum() >= 8       # bodies really were in contact (the last substep's contact forces)
+    r2, q2, v2 = root.copy(), q.copy(), qd.copy()
+    physics_ref.control_step(ms, verts, cfg, r2, q2, v2, tar.copy(), ext.copy(), n_steps=3)
+    np.testing.assert_allclose(res["compact"][1], q2, rtol=0, atol=1e-7)

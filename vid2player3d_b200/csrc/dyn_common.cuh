@@ -425,9 +425,9 @@ __device__ __forceinline__ void ball_substep(const PhysCfg<T>& c, Ball<T>& B, bo
 // pass 2 visits only those, in ascending vertex order - the accumulation order (and therefore every bit of the result)
 // is the same as a plain loop over k.  With most vertices above the ground the serial per-vertex test was ~40 % of the
 // physics time of fallen humanoids (tools/ablate.sh).
+// pass 1: 64-bit mask of the hull vertices below the ground plane (four vertices per iteration)
 template <typename T>
-__device__ __forceinline__ void contact_hull(const float* __restrict__ vb, int vmax, int nv, const PhysCfg<T>& c, const T* R, const T* p,
-                                             const T* v, const T* w, T* A, T* Bm, T* C, T* bn, T* bf, T* cf) {
+__device__ __forceinline__ unsigned long long contact_mask(const float* __restrict__ vb, int vmax, int nv, const T* R, const T* p) {
   unsigned long long mask = 0ull;
   const T pz = p[2];
   for (int k0 = 0; k0 < nv; k0 += 4) {
@@ -443,6 +443,13 @@ __device__ __forceinline__ void contact_hull(const float* __restrict__ vb, int v
     mask |= (unsigned long long)m << k0;
   }
   if (nv < 64) mask &= (1ull << nv) - 1ull;   // padding vertices (zeros) never count
+  return mask;
+}
+// pass 2: the penetrating vertices, in ascending vertex order, added to the body's inertia / bias / contact force
+template <typename T>
+__device__ __forceinline__ void contact_apply(const float* __restrict__ vb, int vmax, unsigned long long mask, const PhysCfg<T>& c, const T* R,
+                                              const T* p, const T* v, const T* w, T* A, T* Bm, T* C, T* bn, T* bf, T* cf) {
+  const T pz = p[2];
   const T kimp = c.h * c.cn + c.h * c.h * c.kn;
   while (mask) {
     const int k = __ffsll((long long)mask) - 1;
@@ -483,6 +490,11 @@ __device__ __forceinline__ void contact_hull(const float* __restrict__ vb, int v
     bf[0] -= fx; bf[1] -= fy; bf[2] -= fn0;
     cf[0] += fx; cf[1] += fy; cf[2] += fn0;
   }
+}
+template <typename T>
+__device__ __forceinline__ void contact_hull(const float* __restrict__ vb, int vmax, int nv, const PhysCfg<T>& c, const T* R, const T* p,
+                                             const T* v, const T* w, T* A, T* Bm, T* C, T* bn, T* bf, T* cf) {
+  contact_apply<T>(vb, vmax, contact_mask<T>(vb, vmax, nv, R, p), c, R, p, v, w, A, Bm, C, bn, bf, cf);
 }
 
 

@@ -8,6 +8,9 @@
 // shared-memory read (no shuffles).  The arithmetic is the same as substep<T>() - same model, same oracle.
 #pragma once
 
+#ifndef PK_CONTACT_COMPACT
+#define PK_CONTACT_COMPACT 0   // 1: per-vertex ground contact as a compacted phase of its own (pk_contact_phase); A/B, off until measured
+#endif
 #define EPW 4     // envs per warp
 #define SLOTS 8   // lanes per env
 #define PK_LANES_PER_ENV SLOTS
@@ -125,7 +128,15 @@ __device__ __forceinline__ void pk_fk(const DevBlob& B, T* env, int b, const T* 
 }
 
 // rigid-body inertia + bias + external / contact / joint-drive terms of one dynamic body -> record
-template <typename T>
+// DEFER_CONTACT (PK_CONTACT_COMPACT): only the penetration mask of the hull is computed here and left in the record (in the two
+// slots of the contact force y/z - bit patterns, 0 = no contact = a zero force); pk_contact_phase adds the vertices afterwards.
+template <typename T> __device__ __forceinline__ T pk_bits_to_slot(uint32_t x);
+template <> __device__ __forceinline__ float pk_bits_to_slot<float>(uint32_t x) { float f; memcpy(&f, &x, 4); return f; }
+template <> __device__ __forceinline__ double pk_bits_to_slot<double>(uint32_t x) { return (double)x; }
+__device__ __forceinline__ uint32_t pk_slot_to_bits(float f) { uint32_t x; memcpy(&x, &f, 4); return x; }
+__device__ __forceinline__ uint32_t pk_slot_to_bits(double d) { return (uint32_t)d; }
+
+template <typename T, bool DEFER_CONTACT = false>
 __device__ __forceinline__ void pk_body(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c, T* env, int b, bool ext_on) {
   const b200_model_t& M = B.m;
   T* rec = env + RIX(B, b) * REC;
@@ -186,8 +197,14 @@ __device__ __forceinline__ void pk_body(const DevBlob& B, const float* __restric
     for (int k = 0; k < 3; k++) { bn[k] -= ext[3 + k] + cxF[k]; bf[k] -= eF[k]; }
   }
   const int nv = ABL == 6 ? 0 : M.nverts[b];
-  if (nv > 0 && p[2] - T(M.radius[b]) < T(0))
+  if (DEFER_CONTACT) {
+    unsigned long long mask = 0ull;
+    if (nv > 0 && p[2] - T(M.radius[b]) < T(0)) mask = contact_mask<T>(verts + (size_t)b * M.vmax * 3, M.vmax, nv, R, p);
+    cf[1] = pk_bits_to_slot<T>((uint32_t)mask);
+    cf[2] = pk_bits_to_slot<T>((uint32_t)(mask >> 32));
+  } else if (nv > 0 && p[2] - T(M.radius[b]) < T(0)) {
     contact_hull<T>(verts + (size_t)b * M.vmax * 3, M.vmax, nv, c, R, p, v, w, A, Bm, C, bn, bf, cf);
+  }
   str<R_A, 28>(rec, ab);
   rec[R_CFX] = cf[0];
   str<R_CFY, 2>(rec, cf + 1);
@@ -394,6 +411,57 @@ template <typename T> __device__ __forceinline__ void pk_root_integrate(const Ph
   str<R_Q, 13>(rec, o);
 }
 
+// PK_CONTACT_COMPACT: the per-vertex part of the ground contact as its own phase.  In the body pass a lane's bodies sit in three
+// rounds and every round costs the warp as many vertex iterations as its busiest lane (tools/contact_imbalance.py: 32 serial
+// iterations per substep with 7 % of the lanes busy for fallen humanoids, on 2.8 bodies in contact per env).  Here the bodies whose
+// penetration mask is non-zero are compacted per env group (ballot + n-th set bit) and handed to the 8 lanes of the group: all
+// bodies in contact of an env go in ONE round (two if there are more than 8).  Each body is still summed by one lane in ascending
+// vertex order onto the values the body pass stored, so every result is bit-identical to the in-place form.
+__device__ __forceinline__ int pk_nth_set_bit(uint32_t w, int n) {   // position of the n-th (0-based) set bit of w; w has more than n bits set
+#if defined(__CUDA_ARCH__)
+  return __fns(w, 0, n + 1);
+#else
+  for (int k = 0; k < 32; k++) if ((w >> k) & 1u) { if (n == 0) return k; n--; }
+  return -1;
+#endif
+}
+template <typename T>
+__device__ __forceinline__ void pk_contact_phase(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c, T* env, int lane, bool valid) {
+  const b200_model_t& M = B.m;
+  const int g = lane >> 3, s = lane & 7, nb = M.nb;
+  // which of my bodies (rounds 0..2 of the body pass) have penetrating vertices
+  uint32_t word = 0;   // bit rr*8 + slot over the 8 lanes of my env group
+  for (int rr = 0; rr * SLOTS < nb; rr++) {
+    const int b = rr * SLOTS + s;
+    bool hit = false;
+    if (valid && b < nb && !M.fixed[b]) {
+      const T* rec = env + RIX(B, b) * REC;
+      hit = (pk_slot_to_bits(rec[R_CFY]) | pk_slot_to_bits(rec[R_CFZ])) != 0u;
+    }
+    const uint32_t bal = __ballot_sync(FULL, hit);
+    word |= ((bal >> (g * 8)) & 0xFFu) << (rr * 8);
+  }
+  int n = 0;
+  for (uint32_t w = word; w; w &= w - 1) n++;
+  for (int t0 = 0; __any_sync(FULL, t0 < n); t0 += 8) {
+    const int idx = t0 + s;
+    if (idx < n) {
+      const int b = pk_nth_set_bit(word, idx);        // = rr*8 + slot = the body index
+      T* rec = env + RIX(B, b) * REC;
+      T own[13], R[9], ab[28], cf[3];
+      ldr<R_Q, 13>(rec, own);
+      ldr<R_A, 28>(rec, ab);
+      const unsigned long long mask = (unsigned long long)pk_slot_to_bits(rec[R_CFY]) | ((unsigned long long)pk_slot_to_bits(rec[R_CFZ]) << 32);
+      cf[0] = rec[R_CFX]; cf[1] = T(0); cf[2] = T(0);
+      qmat(own, R);
+      contact_apply<T>(verts + (size_t)b * M.vmax * 3, M.vmax, mask, c, R, own + 4, own + 10, own + 7, ab, ab + 6, ab + 15, ab + 21, ab + 24, cf);
+      str<R_A, 28>(rec, ab);
+      rec[R_CFX] = cf[0];
+      str<R_CFY, 2>(rec, cf + 1);
+    }
+  }
+}
+
 // Optional contacts of the ball with the humanoid's bodies and the racket handle (b200_cfg_t::ball_body_contact; float64 restatement:
 // oracle/physics_ref.c::ball_contacts_extra_ref).  Runs on the ball's lane right after ball_substep, against the poses / velocities the
 // bodies had at the start of the substep (what the records hold at that point, like the string-bed test).  A body's hull = spheres of
@@ -497,9 +565,13 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
       // 1. per-body inertia / bias / contacts / joint drive
       for (int rr = 0; rr * SLOTS < (ABL == 8 ? 0 : nb); rr++) {
         const int b = rr * SLOTS + s;
-        if (valid && b < nb && !M.fixed[b]) pk_body<T>(B, verts, c, env, b, sim == 0);
+        if (valid && b < nb && !M.fixed[b]) pk_body<T, PK_CONTACT_COMPACT != 0>(B, verts, c, env, b, sim == 0);
       }
       __syncwarp();
+#if PK_CONTACT_COMPACT
+      pk_contact_phase<T>(B, verts, c, env, lane, valid);
+      __syncwarp();
+#endif
       // 2. articulated inertia, leaves -> root
       for (int d = (ABL == 9 ? 0 : M.max_depth); d >= 1; d--) {
         const int b = valid ? B.t.lvl_dyn[d][s] : -1;
