@@ -31,6 +31,10 @@ ALGO_BYTES_PER_ENV_STEP = 9792  # SURVEY.md 8(d), embodied_pose configs; derivat
 # rollout touch stay in the 126 MB L2, so the DRAM traffic is far BELOW the 80.2 MB of algorithmic bytes; pre_kernel adds 18.6 MB,
 # post_kernel 40.3 MB, profiles/r1g ncu).  A constant from the profile, not measured by bench.py.
 NCU_TRAFFIC_BYTES_PER_LAUNCH = 7508992
+# FP32 work of one env step (SURVEY.md 8d asks for achieved FP32 FLOP/s next to the HBM figure): from the executed-instruction mix of
+# the physics launch in the ncu source page of capture G (97.4 M warp instructions x 13.4 active lanes; 25.4 % FFMA = 2 flop, 18.0 % FMUL,
+# 13.4 % FADD) = 1.07 GFLOP per 8192-env launch = 131 kFLOP per env step (pre / post launches add ~4 %); a constant from the profile.
+FP32_FLOP_PER_ENV_STEP = 131.0e3
 HORIZON = 32
 
 
@@ -492,6 +496,8 @@ def main():
                                          "note": "CUDA event pair around this launch inside b200env_step (b200env_set_kernel_timing); its share of "
                                                  "the step's algorithmic bytes: state rows + PD targets + wrench in, state / rigid-body / contact rows out"},
                      "peak_source": peak_src,
+                     "fp32": {"flop_per_env_step": FP32_FLOP_PER_ENV_STEP, "achieved_tflops": FP32_FLOP_PER_ENV_STEP * N / (kernel_ms * 1e-3) / 1e12,
+                              "note": "from the ncu instruction mix (profiles/r1h_step_kernel_packed_ncu.md); B200 non-tensor FP32 peak ~75 TFLOP/s"},
                      "note": "latency / FP32-issue bound along the 9-level kinematic chain, not HBM bound (DESIGN.md 5)"},
     }
     if not args.no_federer and world == 1:
