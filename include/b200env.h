@@ -27,7 +27,7 @@ extern "C" {
 #define B200_MAX_BODIES 32
 #define B200_MAX_DOF 96
 #define B200_MAX_KEY 8
-#define B200_ABI_VERSION 4
+#define B200_ABI_VERSION 5
 
 /* Per-asset constant block produced by vid2player3d_b200/model_compiler.py from the MJCF/STL
  * assets (replaces gym.load_asset + create_actor + set_actor_dof_properties:
@@ -142,6 +142,8 @@ typedef struct b200_buffers {
   float *p_dof_pos, *p_dof_vel, *p_rb_pos, *p_rb_rot;
   float* pd_targets;       /* [N, nd] last PD targets (set_dof_position_target_tensor argument) */
   float* actions_used;     /* [N, num_actions] actions after zeroing reset envs (self.actions) */
+  int32_t num_actions;     /* row width of `actions` / `actions_used`: nd + 6 with a residual root wrench (res_force_scale > 0,
+                              humanoid_smpl_im.py:111-112), nd without (the 6 residual columns are then neither read nor written) */
   /* vid2player player env only (may be NULL when cfg.has_ball == 0); bool tensors, 1 byte each */
   uint8_t* has_bounce;       /* [N] _has_bounce */
   uint8_t* has_bounce_now;   /* [N] _has_bounce_now (cleared at the start of every step, :688) */
@@ -166,7 +168,7 @@ int b200env_set_motion_lib(b200env_handle h, const b200_motion_lib_t* ml);
 
 /* replaces BaseTask.step = pre_physics_step + _physics_step + post_physics_step
  * (base_task.py:147-165; humanoid_smpl_im.py:125-157,398-418): ONE fused launch.
- * actions: [N, nd+6] device. */
+ * actions: [N, b200_buffers_t::num_actions] device. */
 int b200env_step(b200env_handle h, const float* actions, void* stream);
 
 /* replaces HumanoidSMPLIM._reset_envs for ref-state init (humanoid_smpl_im.py:442-450,489-528,

@@ -334,6 +334,30 @@ def get_motion_state(ml, motion_ids, motion_times, adjust_height=True, ground_to
 
 
 # --------------------------------------------------------------------------- pre-physics actuation
+def init_context(ml, motion_ids, motion_times, dt, context_length=32, context_padding=8, mask_body_ids=None):
+    """HumanoidSMPLIM._init_context + _transform_target 'mask_joints' (embodied_pose/env/tasks/humanoid_smpl_im.py:530-592):
+    the window of context_length + 2 padding MoCap frames starting at t + dt - padding dt ->
+    feat [n, P, body_pos | body_rot | dof_pos | body_pos_gt | dof_pos_gt (| joint_conf)], mask [n, P] = t_j <= length + 2 dt."""
+    dt = np.float32(dt)
+    n, P = len(motion_ids), context_length + 2 * context_padding
+    steps = dt * np.arange(-context_padding, context_length + context_padding).astype(np.float32)
+    all_t = ((motion_times.astype(np.float32) + dt)[:, None] + steps[None, :]).astype(np.float32)
+    all_ids = np.repeat(np.asarray(motion_ids)[:, None], P, 1)
+    st = get_motion_state(ml, all_ids.reshape(-1), all_t.reshape(-1))
+    dof_pos, rb_pos, rb_rot = st[2], st[7], st[8]
+    body_pos = rb_pos.copy()
+    parts = [None, rb_rot.reshape(n * P, -1), dof_pos, rb_pos.reshape(n * P, -1), dof_pos]
+    if mask_body_ids is not None:
+        conf = np.ones(rb_pos.shape[:2], np.float32)
+        conf[:, list(mask_body_ids)] = 0.0
+        body_pos = body_pos * conf[..., None]
+        parts.append(conf)
+    parts[0] = body_pos.reshape(n * P, -1)
+    feat = np.concatenate(parts, -1).astype(np.float32).reshape(n, P, -1)
+    mask = all_t <= (ml["motion_lengths"][motion_ids].astype(np.float32) + np.float32(2) * dt)[:, None]
+    return feat, mask
+
+
 def pre_physics(actions, reset_buf, dof_pos, root_body_rot, num_dof, pd_tar_lim, res_force_scale, res_torque_scale):
     """env/tasks/humanoid_smpl_im.py:125-157 + :391-396.
     Returns (actions_used, pd_tar[N,D], force[N,3], torque[N,3]) - the wrench is for body 0, ENV_SPACE."""

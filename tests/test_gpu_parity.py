@@ -460,3 +460,65 @@ def test_vec_task_graph_step_equals_eager_step(model, small_lib):
     for (o1, r1, d1, t1), (o2, r2, d2, t2) in zip(*outs):
         assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(t1, t2)
     assert float(outs[0][-1][0].abs().max()) <= 5.0
+
+
+def test_no_residual_wrench_action_width(model, small_lib):
+    """residual_force_scale = 0 (the code's own default, humanoid_smpl_im.py:39,111): the action rows are nd = 69 wide.  The step
+    must use that stride (a hard-coded nd + 6 read misaligned rows and wrote past the tensors) and give exactly what the
+    75-wide task gives with zero residual columns."""
+    N = 96
+    torch.manual_seed(11)
+    ta = make_task(N, small_lib)
+    torch.manual_seed(11)
+    tb = make_task(N, small_lib, residual_force_scale=0.0)
+    assert ta.num_actions == 75 and tb.num_actions == 69 and tuple(tb.actions.shape) == (N, 69)
+    torch.manual_seed(12)
+    ta.reset()
+    torch.manual_seed(12)
+    tb.reset()
+    assert torch.equal(ta._dof_pos, tb._dof_pos)
+    g = torch.Generator(device=ta.device).manual_seed(3)
+    for _ in range(4):
+        a = torch.rand(N, 69, device=ta.device, generator=g) * 2 - 1
+        ta.step(torch.cat([a, torch.zeros(N, 6, device=ta.device)], 1))
+        tb.step(a)
+        torch.cuda.synchronize()
+        assert torch.equal(tb.actions, ta.actions[:, :69])
+        for name in ("_dof_pos", "_dof_vel", "obs_buf", "rew_buf", "reset_buf", "_pd_target_dof_pos"):
+            assert torch.equal(getattr(ta, name), getattr(tb, name)), name
+    with pytest.raises(ValueError):
+        tb.step(torch.zeros(N, 75, device=tb.device))
+
+
+def test_init_context_golden():
+    """b200env_motion_context (+ the torch `_transform_target`) vs the fixture produced by the reference's own `_init_context` /
+    `_transform_target` run on a fake self (tests/golden/make_golden_context.py; humanoid_smpl_im.py:530-592)."""
+    from vid2player3d_b200 import motion_lib
+    g = golden("init_context.npz")
+    flat = motion_lib.FlatMotionLib(**{k[4:]: g[k] for k in g if k.startswith("lib_")})
+    n = len(g["plain_ids"])
+    for case, over in (("plain", {}), ("mask", {"transform_specs": {"mask_joints": {"joints": [str(j) for j in g["mask_joints"]]}}})):
+        task = make_task(n, flat, **over)
+        dev = task.device
+        ids, times = torch.tensor(g[f"{case}_ids"], device=dev), torch.tensor(g[f"{case}_times"], device=dev)
+        task._reset_ref_motion_ids[:] = ids
+        task._init_context(torch.arange(n, device=dev), ids, times)
+        torch.cuda.synchronize()
+        assert tuple(task.context_feat.shape) == g[f"{case}_feat"].shape
+        np.testing.assert_allclose(task.context_feat.cpu().numpy(), g[f"{case}_feat"], rtol=0, atol=1e-5, err_msg=case)
+        assert np.array_equal(task.context_mask.cpu().numpy(), g[f"{case}_mask"]), case
+        assert task.context_names[-1] == ("joint_conf" if over else "dof_pos_gt")
+    # the two random transforms: invariants of :573-590 (confidence in [0, 1], dropped joints zeroed in body_pos only, root kept by
+    # mask_random_joints, ground-truth columns untouched)
+    specs = {"noisy_joints": {"noise_std": 0.05, "prob": 0.5, "conf_std": 0.05, "min_conf": 0.2}, "mask_random_joints": {"prob": 0.3}}
+    task = make_task(n, flat, transform_specs=specs)
+    ids, times = torch.tensor(g["plain_ids"], device=task.device), torch.tensor(g["plain_times"], device=task.device)
+    torch.manual_seed(0)
+    task._init_context(torch.arange(n, device=task.device), ids, times)
+    f = task.context_feat.cpu().numpy()
+    conf, bp, gt = f[..., 378:], f[..., :72].reshape(n, 48, 24, 3), g["plain_feat"]
+    assert conf.min() >= 0.0 and conf.max() <= 1.0 and (conf == 0).mean() > 0.2 and (conf == 1).mean() > 0.1
+    assert np.all(bp[conf == 0] == 0.0)
+    np.testing.assert_allclose(f[..., 72:378], gt[..., 72:], rtol=0, atol=1e-5)
+    clean = conf == 1.0
+    np.testing.assert_allclose(bp[clean], gt[..., :72].reshape(n, 48, 24, 3)[clean], rtol=0, atol=1e-5)

@@ -110,3 +110,21 @@ def test_im_step_state_machine():
         close(o.t_key_pos, g[f"target_key_pos_{s}"], 2e-5)
         saw_reset = int(o.reset_buf.sum())
     assert saw_reset >= 3  # sticky flag + fall + episode end all exercised
+
+
+def test_init_context():
+    """oracle init_context vs the reference's own _init_context / _transform_target run on a fake self (make_golden_context.py)"""
+    g = golden("init_context.npz")
+    ml = lib_from(g)
+    dt = np.float32(2) * np.float32(1 / 60)
+    feat, mask = R.init_context(ml, g["plain_ids"], g["plain_times"], dt)
+    assert feat.shape == g["plain_feat"].shape == (16, 48, 378)
+    close(feat, g["plain_feat"], 1e-5)
+    assert np.array_equal(mask, g["plain_mask"]) and mask.any() and not mask.all()
+    names = ['Pelvis', 'L_Hip', 'L_Knee', 'L_Ankle', 'L_Toe', 'R_Hip', 'R_Knee', 'R_Ankle', 'R_Toe', 'Torso', 'Spine', 'Chest', 'Neck', 'Head',
+             'L_Thorax', 'L_Shoulder', 'L_Elbow', 'L_Wrist', 'L_Hand', 'R_Thorax', 'R_Shoulder', 'R_Elbow', 'R_Wrist', 'R_Hand']
+    ids = [names.index(str(j)) for j in g["mask_joints"]]
+    feat, mask = R.init_context(ml, g["mask_ids"], g["mask_times"], dt, mask_body_ids=ids)
+    assert feat.shape == g["mask_feat"].shape == (16, 48, 402)
+    close(feat, g["mask_feat"], 1e-5)
+    assert np.array_equal(mask, g["mask_mask"])

@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 
 MAX_BODIES, MAX_DOF, MAX_KEY = 32, 96, 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Model(C.Structure):
@@ -67,7 +67,7 @@ class Buffers(C.Structure):
         ("t_root_ang_vel", C.c_void_p), ("t_dof_vel", C.c_void_p), ("t_key_pos", C.c_void_p), ("t_rb_pos", C.c_void_p),
         ("t_rb_rot", C.c_void_p),
         ("p_dof_pos", C.c_void_p), ("p_dof_vel", C.c_void_p), ("p_rb_pos", C.c_void_p), ("p_rb_rot", C.c_void_p),
-        ("pd_targets", C.c_void_p), ("actions_used", C.c_void_p),
+        ("pd_targets", C.c_void_p), ("actions_used", C.c_void_p), ("num_actions", C.c_int32),
         ("has_bounce", C.c_void_p), ("has_bounce_now", C.c_void_p), ("bounce_pos", C.c_void_p), ("racket_hit_now", C.c_void_p),
     ]
 

@@ -638,7 +638,7 @@ __device__ __forceinline__ void step_prologue(const b200_buffers_t& bf, const b2
                                               const b200_model_t& M, const LaneConst& lc, int lane, float* scr,
                                               const float* __restrict__ actions, int64_t e, Lane<float>& L, float* pdtar, float* extF,
                                               float* extT, Ball<float>& ball) {
-  const int nd = M.nd, na = nd + 6;
+  const int nd = M.nd, na = bf.num_actions;   // row width of the action tensors: nd, or nd + 6 with the residual root wrench
   __syncwarp();  // scratch reuse when called back to back
   // ---- load state rows (coalesced) into the warp's scratch
   const float* rs = bf.root_states + e * bf.actors_per_env * 13;
@@ -903,7 +903,7 @@ step_kernel(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_c
   float* scr = scratch_all + warp * SCRATCH_FLOATS;
   const b200_cfg_t& cfg = *gcfg;
   const LaneConst lc = lane_const(M, lane);
-  const int nd = M.nd, na = nd + 6;
+  const int nd = M.nd;
   const PhysCfg<float> pc = make_phys_cfg<float>(cfg);
 
  __shared__ unsigned long long s_tk;
@@ -1828,6 +1828,10 @@ int b200env_bind(b200env_handle h, const b200_buffers_t* bufs) {
     if (!bufs->has_bounce || !bufs->has_bounce_now || !bufs->bounce_pos || !bufs->racket_hit_now) return fail(-1, "b200env_bind: ball flag buffers are null%s");
   }
   if (((uintptr_t)bufs->t_rb_rot | (uintptr_t)bufs->p_rb_rot) & 15) return fail(-2, "b200env_bind: quaternion rows must be 16-byte aligned%s");
+  if (bufs->num_actions != h->model.nd && bufs->num_actions != h->model.nd + 6)
+    return fail(-2, "b200env_bind: num_actions must be nd (no residual wrench) or nd + 6%s");
+  if (h->cfg.res_force_scale > 0.f && bufs->num_actions != h->model.nd + 6)
+    return fail(-2, "b200env_bind: res_force_scale > 0 needs num_actions = nd + 6 (force + torque columns)%s");
   h->bufs = *bufs;
   h->bound = true;
   return 0;

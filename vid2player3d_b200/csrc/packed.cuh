@@ -9,7 +9,8 @@
 #pragma once
 
 #ifndef PK_CONTACT_COMPACT
-#define PK_CONTACT_COMPACT 0   // 1: per-vertex ground contact as a compacted phase of its own (pk_contact_phase); A/B, off until measured
+#define PK_CONTACT_COMPACT 1   // 1: per-vertex ground contact as a compacted phase of its own (pk_contact_phase); bit-identical, 291.9 -> 283.8 us
+                               // per 8192-env step on B200 (profiles/r2a_ab.md); 0 keeps the in-place form for A/B
 #endif
 #define EPW 4     // envs per warp
 #define SLOTS 8   // lanes per env

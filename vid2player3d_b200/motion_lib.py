@@ -140,16 +140,49 @@ class FlatMotionLib:
         return cls(**kw)
 
     @classmethod
-    def load_any(cls, path):
-        """`.b200ml` flat file, `.npz` archive (save()), or a reference `torch.save(motion_lib)` pickle (`.pth` / `.pt`; needs the
-        reference's `utils.motion_lib` and `poselib` importable, like the reference's own `torch.load` of it)."""
+    def load_any(cls, path, motion_file_range=None):
+        """What the reference's `motion_file` may name (embodied_pose/env/tasks/humanoid_smpl_im.py:420-440) plus our own formats:
+        a `.b200ml` flat file, an `.npz` archive (save()), a reference `torch.save(motion_lib)` pickle (`.pth` / `.pt`; needs the
+        reference's `utils.motion_lib` and `poselib` importable, like the reference's own `torch.load` of it), or a DIRECTORY of such
+        files: sorted, sliced by `motion_file_range` = [first, last) and merged like `merge_multiple_motion_libs` (:101-118)."""
+        path = os.fspath(path)
+        if os.path.isdir(path):
+            files = []
+            for pat in ("*.pth", "*.pt", "*.b200ml", "*.npz"):
+                files = sorted(f for f in (os.path.join(path, n) for n in os.listdir(path)) if f.endswith(pat[1:]))
+                if files:
+                    break                         # the reference globs *.pth; a directory of our own formats works the same way
+            if motion_file_range is not None:
+                files = files[motion_file_range[0]:motion_file_range[1]]
+            if not files:
+                raise FileNotFoundError(f"{path}: no motion library files (*.pth, *.pt, *.b200ml, *.npz) in the directory / range")
+            return cls.merge([cls.load_any(f) for f in files])
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
         ext = os.path.splitext(path)[1].lower()
         if ext == ".npz":
             return cls.load(path)
         if ext in (".pth", ".pt"):
             import torch
             return cls.from_reference(torch.load(path, map_location="cpu", weights_only=False))
-        return cls.load_flat(path)
+        with open(path, "rb") as fh:
+            if fh.read(8) == cls.MAGIC:
+                return cls.load_flat(path)
+        raise ValueError(f"{path}: unknown motion library format (expected .b200ml, .npz, or a reference .pth / .pt pickle)")
+
+    @classmethod
+    def merge(cls, libs):
+        """Concatenation of motion libraries (the reference's `merge_multiple_motion_libs`, motion_lib.py:101-118): per-frame arrays and
+        per-motion tables are concatenated, the frame offsets of every motion are rebuilt (`generate_length_starts`)."""
+        libs = list(libs)
+        if len(libs) == 1:
+            return libs[0]
+        if len({(l.gts.shape[1], l.dvs.shape[1], l.motion_bodies.shape[1]) for l in libs}) != 1:
+            raise ValueError("motion libraries with different skeletons / shape widths cannot be merged")
+        kw = {k: np.concatenate([np.asarray(getattr(l, k)) for l in libs], 0) for k in cls.FIELDS if k != "length_starts"}
+        nf = kw["num_frames"].astype(np.int64)
+        kw["length_starts"] = np.concatenate([[0], np.cumsum(nf)[:-1]]).astype(np.int64)
+        return cls(**kw)
 
     @classmethod
     def from_reference(cls, ml):

@@ -75,7 +75,7 @@ class Env:
     def bind(self, tensors, actors_per_env, bodies_per_env, num_obs):
         b = abi.Buffers()
         for name, _ in abi.Buffers._fields_:
-            if name in ("actors_per_env", "bodies_per_env", "num_obs"):
+            if name in ("actors_per_env", "bodies_per_env", "num_obs", "num_actions"):
                 continue
             if name in ("has_bounce", "has_bounce_now", "bounce_pos", "racket_hit_now") and name not in tensors:
                 continue  # ball flag buffers: only for the vid2player player env
@@ -83,6 +83,8 @@ class Env:
             assert t.is_cuda and t.is_contiguous(), name
             setattr(b, name, t.data_ptr())
         b.actors_per_env, b.bodies_per_env, b.num_obs = actors_per_env, bodies_per_env, num_obs
+        b.num_actions = self.num_actions = int(tensors["actions_used"].shape[-1])   # row width of `actions` in step()
+        self.num_envs_bound = int(tensors["actions_used"].shape[0])   # rows of the bound tensors (>= num_envs with an env slice)
         self._keep.append(tensors)
         _check(lib().b200env_bind(self._h, C.byref(b)))
 
@@ -103,7 +105,10 @@ class Env:
         _check(lib().b200env_set_env_slice(self._h, C.c_int32(int(first)), C.c_int32(int(stride))))
 
     def step(self, actions):
-        assert actions.is_cuda and actions.is_contiguous() and actions.dtype.is_floating_point
+        if not (actions.is_cuda and actions.is_contiguous() and actions.dtype.is_floating_point):
+            raise ValueError("actions must be a contiguous floating-point CUDA tensor")
+        if tuple(actions.shape) != (self.num_envs_bound, self.num_actions):
+            raise ValueError(f"actions must be [{self.num_envs_bound}, {self.num_actions}], got {tuple(actions.shape)}")
         _check(lib().b200env_step(self._h, _ptr(actions), _stream()))
 
     def reset(self, env_ids, motion_times):

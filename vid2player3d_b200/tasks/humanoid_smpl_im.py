@@ -80,14 +80,17 @@ class HumanoidSMPLIM(BaseTask):
 
     # ------------------------------------------------------------------ construction
     def _load_motion(self, motion_file):
-        """humanoid_smpl_im.py:420-440.  Accepts a FlatMotionLib, an .npz written by FlatMotionLib.save,
-        or a loaded reference MotionLib object."""
+        """humanoid_smpl_im.py:420-440.  Accepts a FlatMotionLib, a path - `.b200ml` flat file, `.npz`, a reference
+        `torch.save(motion_lib)` `.pth`, or a directory of them sliced by cfg.env.motion_file_range and merged - or a loaded
+        reference MotionLib object."""
         if isinstance(motion_file, FlatMotionLib):
             flat = motion_file
         elif isinstance(motion_file, (str, os.PathLike)):
-            flat = FlatMotionLib.load(motion_file)
-        else:
+            flat = FlatMotionLib.load_any(motion_file, self.cfg["env"].get("motion_file_range", None))
+        elif all(hasattr(motion_file, k) for k in ("gts", "grs", "lrs", "_motion_lengths")):
             flat = FlatMotionLib.from_reference(motion_file)
+        else:
+            raise TypeError(f"motion_lib / motion_file: expected a FlatMotionLib, a path or a reference MotionLib, got {type(motion_file)}")
         self._motion_lib = flat
         dev = self.device
         self._ml_t = {k: torch.from_numpy(getattr(flat, k)).to(dev).contiguous() for k in FlatMotionLib.FIELDS}
@@ -119,6 +122,9 @@ class HumanoidSMPLIM(BaseTask):
         self.obs_shapes = [shape_dict[x] for x in self.obs_names]
         self.obs_dims = [int(np.prod(x)) for x in self.obs_shapes]
         self.context_names = ['body_pos', 'body_rot', 'dof_pos', 'body_pos_gt', 'dof_pos_gt']
+        self._transform_specs = self.cfg['env'].get('transform_specs', None)
+        if 'transform_specs' in self.cfg['env']:             # :202-204
+            self.context_names.append('joint_conf')
         self.context_shapes = [shape_dict[x] for x in self.context_names]
         self.context_dims = [int(np.prod(x)) for x in self.context_shapes]
         self.is_env_dim_setup = False
@@ -307,11 +313,17 @@ class HumanoidSMPLIM(BaseTask):
         n = len(env_ids)
         P = self.context_length + self.context_padding * 2
         nbl, D = self._num_lib_bodies, self.num_dof
+        W = 2 * (3 * nbl + D) + 4 * nbl
+        with_conf = 'joint_conf' in self.context_names
         if not hasattr(self, "context_feat"):
-            self.context_feat = torch.zeros(self.num_envs, P, 2 * (3 * nbl + D) + 4 * nbl, device=self.device)
+            self.context_feat = torch.zeros(self.num_envs, P, W + (nbl if with_conf else 0), device=self.device)
             self.context_mask = torch.zeros(self.num_envs, P, device=self.device, dtype=torch.bool)
-        self._env.motion_context(env_ids.to(self.device, dtype=torch.long).contiguous(), motion_ids.contiguous(), motion_times.contiguous(),
-                                 P, -self.context_padding, self.dt, self.context_feat, self.context_mask)
+            self._context_raw = torch.zeros(self.num_envs, P, W, device=self.device) if with_conf else self.context_feat
+        env_ids = env_ids.to(self.device, dtype=torch.long).contiguous()
+        self._env.motion_context(env_ids, motion_ids.contiguous(), motion_times.contiguous(),
+                                 P, -self.context_padding, self.dt, self._context_raw, self.context_mask)
+        if with_conf:
+            self.context_feat[env_ids] = self._transform_target(self._context_raw[env_ids])
         if self.model is not None:
             if not self.is_env_dim_setup:
                 self.model.a2c_network.setup_env_named_dims(self.obs_names, self.obs_shapes, self.obs_dims,
@@ -319,6 +331,39 @@ class HumanoidSMPLIM(BaseTask):
                 self.is_env_dim_setup = True
             with torch.no_grad():
                 self.model.a2c_network.forward_context(self.context_feat, self.context_mask)
+
+    def _transform_target(self, raw):
+        """:565-592 on the rows of the window the kernel just wrote ([n, P, body_pos | body_rot | dof_pos | body_pos_gt | dof_pos_gt]):
+        `mask_joints` / `noisy_joints` / `mask_random_joints` edit body_pos and produce joint_conf, appended as the last nbl columns.
+        Reset-time only (cold path), plain torch on the device; the normal CDF is 0.5 erfc(-x / sqrt 2) instead of the reference's
+        round trip through scipy on the CPU."""
+        nbl = self._num_lib_bodies
+        n, P, _ = raw.shape
+        body_pos = raw[..., :3 * nbl].reshape(n, P, nbl, 3).clone()
+        conf = torch.ones(n, P, nbl, device=raw.device)
+        for transform, specs in (self._transform_specs or {}).items():
+            if transform == 'mask_joints':
+                idx = [self.body_names.index(j) for j in specs['joints']]
+                conf[..., idx] = 0.0
+                body_pos = body_pos * conf.unsqueeze(-1)
+            elif transform == 'noisy_joints':
+                noise_std = torch.full_like(conf, float(specs['noise_std']))
+                noise_std[torch.bernoulli(torch.full_like(conf, float(specs['prob']))) == 0.0] = 0.0
+                noise = torch.randn_like(body_pos) * noise_std.unsqueeze(-1)
+                noise_norm = noise.norm(dim=-1) / (np.sqrt(3) * specs['conf_std'])
+                conf = torch.erfc(noise_norm / np.sqrt(2.0))            # (1 - cdf(x)) * 2
+                body_pos = body_pos + noise
+                occluded = conf < specs['min_conf']
+                conf[occluded] = 0.0
+                body_pos[occluded] = 0.0
+            elif transform == 'mask_random_joints':
+                drop = torch.bernoulli(torch.full_like(conf, float(specs['prob']))) == 1.0
+                drop[..., 0] = False
+                conf[drop] = 0.0
+                body_pos[drop] = 0.0
+            else:
+                raise NotImplementedError(f"transform_specs: unknown transform {transform!r}")
+        return torch.cat([body_pos.reshape(n, P, -1), raw[..., 3 * nbl:], conf], dim=-1)
 
     def _init_context_torch(self, env_ids, motion_ids, motion_times):
         """the same window composed with torch ops from b200env_motion_state outputs (written like the reference, :530-563);
