@@ -278,3 +278,27 @@ def test_stream_motion_player_logic_on_cpu():
     assert torch.equal(p._joint_rotmat, ring[(int(p._t) + p._off) % 6, env])
     det = torch.linalg.det(p._joint_rotmat.reshape(-1, 3, 3))
     assert float((det - 1).abs().max()) < 1e-4
+
+
+def test_nn_library_exports_and_layout(tmp_path):
+    """libb200nn.so (include/b200nn.h): loads without a GPU, exports every declared symbol, descriptor layout == ctypes mirror,
+    and refuses to build a layer without a CUDA device (no fallback)."""
+    from vid2player3d_b200 import build, nn
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "b200nn.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200nn_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared == sorted(nn.SYMBOLS)
+    L = nn.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s/include/b200nn.h"\n'
+                   'int main(){printf("%%zu %%zu %%zu\\n",sizeof(b200nn_linear_desc_t),offsetof(b200nn_linear_desc_t,out),'
+                   'offsetof(b200nn_linear_desc_t,k_padded));}' % ROOT)
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [C.sizeof(nn.LinearDesc), nn.LinearDesc.out.offset, nn.LinearDesc.k_padded.offset]
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA device only"):
+            nn.Linear(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(8, 64), torch.zeros(8), torch.zeros(128, 64, dtype=torch.bfloat16), 4)
