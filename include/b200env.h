@@ -192,6 +192,17 @@ int b200env_obs_imitation(b200env_handle h, int32_t n, const float* body_pos, co
                           const float* motion_bodies, int32_t local_root_obs, int32_t root_height_obs, float* obs,
                           void* stream);
 
+/* The same observation computed straight from the Isaac-layout state rows the env owns - rigid_body_state [n, bodies_per_env, 13]
+ * (pos 0:3, rot 3:7, vel 7:10, ang vel 10:13; the first `humanoid bodies` rows of every env are used) and dof_state [n, nd, 2] -
+ * instead of six contiguous gathers of them (what the reference's slicing + cat amounts to, humanoid_smpl_im_mvae.py:862-895).
+ * obs_bf16 (may be NULL): additionally writes the policy's first-layer operand row, bf16(clamp((obs - mean) * rstd, -clamp, clamp)),
+ * [n, ld_bf16] (RunningMeanStd + the +-5 clamp of ImitatorPlayer.run_one_step, vid2player/players/im_player.py:187-190; mean /
+ * rstd NULL = no normalisation), so that the network forward (include/b200nn.h) starts without a cast launch. */
+int b200env_obs_imitation_rows(b200env_handle h, int32_t n, const float* rigid_body_state, int32_t bodies_per_env, const float* dof_state,
+                               const float* target_pos, const float* target_rot, const float* target_dof_pos, const float* motion_bodies,
+                               int32_t local_root_obs, int32_t root_height_obs, float* obs, void* obs_bf16, int32_t ld_bf16, const float* mean,
+                               const float* rstd, float clamp, void* stream);
+
 /* Physics-only control step on caller-provided arrays, float (prec=0) or double (prec=1):
  * the same device code as b200env_step's physics, exposed so tests can compare it with the
  * float64 CPU restatement (oracle/physics_ref.c).  root [n,13], dof_pos/dof_vel/pd_tar [n,nd],

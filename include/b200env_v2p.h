@@ -13,10 +13,13 @@ const char* b200v2p_last_error(void);
 /* replaces HumanoidSMPLIMMVAE._smpl_to_sim + _forward_kinematics (env/tasks/humanoid_smpl_im_mvae.py:897-946, utils/hybrik.py:597-652):
  * joint_rotmat [n,24,3,3] and rest [num_rest,24,3] in SMPL joint order (env e uses shape e % num_rest: 1 = one player,
  * 2 = dual mode's alternating players, n = a shape per env); outputs in MuJoCo body order (smpl_2_mujoco);
- * prev_* NULL -> zero velocities. */
+ * prev_* NULL -> zero velocities.  prev_root_pos_update / target_root_pos_out (either may be NULL): after the finite difference the
+ * root position of this call is stored there - `_save_prev_target_motion_state` (:741-750) and `self._target_root_pos = root_pos`
+ * (:655) folded into the launch; prev_root_pos_update may be the same buffer as prev_root_pos. */
 int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rotmat, const float* rest, int32_t num_rest,
                         const int32_t* parents, const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
-                        float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, void* stream);
+                        float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, float* prev_root_pos_update,
+                        float* target_root_pos_out, void* stream);
 
 /* replaces the fix_head_orientation block of _set_target_motion_state (env/tasks/humanoid_smpl_im_mvae.py:605-634):
  * rb_pos/rb_rot [n,24,*] = FK of the uncorrected pose (MuJoCo order, head_body = 13); joint_rotmat [n,24,3,3] (SMPL order) is
@@ -59,6 +62,8 @@ typedef struct b200v2p_ctrl {
                        envs (2k, 2k+1) are opponents; reset_buf is only ever SET, terminate_buf is not written */
   int32_t use_history; /* cfg use_history_ball_obs (:348-351): the task observation is the HISTORY of ball positions (ball_obs)
                           instead of the future trajectory window (ball_traj) */
+  int32_t advance;     /* 1 (ignored with obs_only): first do the tail of physics_step and the head of post_physics_step (:364-366,
+                          :441-444) - ball_traj <- roll(-1) with a zero last frame, tar_time += 1, progress_buf += 1 - then the rest */
   float scale_pos, scale_phase, scale_bounce_pos, scale_bounce_time, w_pos, w_ball_pos;
   float court_min[2], court_max[2];
   float est_params[15]; /* VEL_X, VEL_Y, VSPIN, TRAJ_X, TRAJ_Y ranges (lo, hi, step) */
@@ -67,10 +72,13 @@ typedef struct b200v2p_ctrl {
   const float *root_pos, *root_vel, *racket_pos, *racket_normal, *ball_pos;
   const uint8_t *has_contact, *has_contact_now, *has_bounce, *has_bounce_now;
   const float* bounce_pos;
-  const float* ball_traj; /* [n,100,3] */
+  float* ball_traj; /* [n,100,3]; written only with advance = 1 */
   const float* target_bounce_pos;
   const float* phase;
-  const int64_t *swing_type, *swing_type_cycle, *tar_action, *tar_time, *tar_time_total, *progress_buf;
+  const int64_t *swing_type, *swing_type_cycle, *tar_action;
+  int64_t* tar_time;            /* written only with advance = 1 */
+  const int64_t* tar_time_total;
+  int64_t* progress_buf;        /* written only with advance = 1 */
   const float *est_x, *est_y; /* estimator tables [rows, est_nx], [rows, est_ny, 2]; NULL = no estimator (dual mode) */
   uint8_t *bounce_in, *est_bounce_in, *reset_reaction, *reset_recovery;
   float *est_bounce_pos, *est_bounce_time, *est_max_height, *distance;
@@ -81,6 +89,43 @@ typedef struct b200v2p_ctrl {
                       NULL = not kept (then use_history must be 0) */
 } b200v2p_ctrl_t;
 int b200v2p_controller_post(const b200v2p_ctrl_t* c, void* stream);
+
+/* replaces the action handling of PhysicsMVAEController.pre_physics_step (env/tasks/physics_mvae_controller.py:247-262) that precedes
+ * the motion generator: mvae_actions = actions[:, :num_latent] * vae_action_scale, replaced by clamp(N(0,1), -5, 5) where
+ * tar_action == 0 when random_walk_in_recovery; res_dof_actions = actions[:, num_latent : num_latent + num_res_dof] *
+ * residual_dof_scale.  The normal deviates are counter-based (seed, *step_counter, element), *step_counter is advanced by the launch
+ * (done_counter: one zero-initialised uint32 of scratch), so that a captured step replays with fresh numbers. */
+typedef struct b200v2p_prestep {
+  int32_t n, num_actions, num_latent, num_res_dof, random_walk_in_recovery;
+  float vae_action_scale, residual_dof_scale;
+  uint64_t seed;
+  const float* actions;        /* [n, num_actions] */
+  const int64_t* tar_action;   /* [n] */
+  int64_t* step_counter;       /* [1] */
+  uint32_t* done_counter;      /* [1] scratch, zero between launches */
+  float* mvae_actions;         /* [n, num_latent] */
+  float* res_dof_actions;      /* [n, num_res_dof] or NULL */
+} b200v2p_prestep_t;
+int b200v2p_pre_step(const b200v2p_prestep_t* p, void* stream);
+
+/* The resident kinematic target stream that stands in for the unreleased MVAE motion generator: `frames`
+ * frames of every field for all n envs are kept in HBM ([frames * n, ...], frame-major); env e reads frame (clock + advance +
+ * offset[e]) % frames into the live buffers MVAEPlayer exposes (players/mvae_player.py: _joint_rotmat [n,24,3,3], _root_pos,
+ * _racket_pos [n,3], _phase_pred [n], _swing_type, _swing_type_cycle [n] int64).  advance = 1: a step (the clock moves on), 0: re-read
+ * after a reset changed offsets. */
+typedef struct b200v2p_stream {
+  int32_t n, frames, advance, pad_;
+  int64_t* clock;              /* [1] */
+  uint32_t* done_counter;      /* [1] scratch, zero between launches */
+  const int64_t* offset;       /* [n] */
+  const float* ring_rotmat;    float* rotmat;
+  const float* ring_root_pos;  float* root_pos;
+  const float* ring_racket_pos; float* racket_pos;
+  const float* ring_phase;     float* phase;
+  const int64_t* ring_swing_type; int64_t* swing_type;
+  const int64_t* ring_swing_type_cycle; int64_t* swing_type_cycle;
+} b200v2p_stream_t;
+int b200v2p_stream_gather(const b200v2p_stream_t* s, void* stream);
 
 /* replaces TennisBallInEstimator.estimate (utils/tennis_ball_in_estimator.py:22-81), the table lookup of
  * HumanoidSMPLIMMVAEDual._reset_balls (env/tasks/humanoid_smpl_im_mvae_dual.py:63-72): for query i the ball row

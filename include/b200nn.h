@@ -47,6 +47,7 @@ typedef struct b200nn_linear_desc {
   int32_t num_experts;/* 1 (plain linear layer) or 2..6 (mixture of experts) */
   int32_t act;        /* B200NN_ACT_* */
   int32_t out_bf16;   /* 1: bf16 output (feeds the next layer), 0: float output */
+  float out_min, out_max; /* clamp applied after the activation (im_player.py:198 clamps the action to +-1); out_min >= out_max: none */
 } b200nn_linear_desc_t;
 
 int b200nn_abi_version(void);
@@ -63,6 +64,11 @@ int b200nn_linear_run(b200nn_linear_handle h, void* stream);
  * bf16 operand.  Columns [cols, ld_dst) of dst are left untouched (zero from the allocation). */
 int b200nn_cast_rows(const float* src, int32_t ld_src, void* dst_bf16, int32_t ld_dst, int32_t rows, int32_t cols, const float* mean,
                      const float* rstd, float lo, float hi, void* stream);
+
+/* the same cast of one float block into up to three bf16 buffers of the same leading dimension (dst2 / dst3 may be NULL): the latent z
+ * is the first block of all three MixedDecoder layer inputs (`torch.cat((z, layer_out), dim=1)`, model.py:247) */
+int b200nn_cast_rows3(const float* src, int32_t ld_src, void* dst_bf16, void* dst2_bf16, void* dst3_bf16, int32_t ld_dst, int32_t rows,
+                      int32_t cols, void* stream);
 
 /* coef[r, :] = softmax( h[r, :k] W^T + b ) over num_experts outputs: last layer of the MixedDecoder gate (model.py:226-235) */
 int b200nn_gate_softmax(const void* h_bf16, int32_t ldh, int32_t k, const float* w, const float* b, int32_t num_experts, float* coef,

@@ -22,17 +22,27 @@ def _worker(rank, world, port, q):
     r, lr, w = D.init("gloo")
     assert (r, w) == (rank, world)
     torch.manual_seed(0)
-    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
-    D.broadcast_parameters(net.parameters())
+    torch.manual_seed(rank)        # different initial weights / buffers per rank: the broadcast must make them equal
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.BatchNorm1d(16), torch.nn.ReLU(), torch.nn.Linear(16, 3))
+    net[1].running_mean.fill_(float(rank + 1))     # a buffer (stands for the RunningMeanStd statistics)
+    D.broadcast_parameters(net)
+    assert float(net[1].running_mean[0]) == 1.0, "buffers are broadcast with the parameters"
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
     red = D.GradAllReducer(net.parameters())
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(red.params, red.views))
     torch.manual_seed(100 + rank)  # rank-specific minibatch
     x, y = torch.randn(32, 8), torch.randn(32, 3)
     loss = ((net(x) - y) ** 2).mean()
     loss.backward()
     local = [p.grad.clone() for p in net.parameters()]
     red.synchronize()
+    synced = [p.grad.clone().numpy() for p in net.parameters()]
+    opt.step()
+    D.broadcast_optimizer_state(opt)
+    red.zero_grad()
+    assert all(float(p.grad.abs().max()) == 0.0 for p in net.parameters())
     kl = D.average_value(torch.tensor(float(rank + 1)))
-    q.put((rank, [g.numpy() for g in local], [p.grad.clone().numpy() for p in net.parameters()], float(kl),
+    q.put((rank, [g.numpy() for g in local], synced, float(kl),
            list(D.shard_envs(16, rank, world, pair=True)), D.rank_seed(7, rank)))
     dist.destroy_process_group()
 

@@ -236,7 +236,7 @@ class V2PCtrl(C.Structure):
         ("n", C.c_int32), ("bodies_per_env", C.c_int32), ("ball_stride", C.c_int32), ("racket_body", C.c_int32),
         ("num_obs", C.c_int32), ("obs_traj_len", C.c_int32), ("use_target", C.c_int32), ("reward_type", C.c_int32),
         ("early_termination", C.c_int32), ("max_episode_length", C.c_int32), ("est_nx", C.c_int32), ("est_ny", C.c_int32),
-        ("obs_only", C.c_int32), ("dual", C.c_int32), ("use_history", C.c_int32),
+        ("obs_only", C.c_int32), ("dual", C.c_int32), ("use_history", C.c_int32), ("advance", C.c_int32),
         ("scale_pos", C.c_float), ("scale_phase", C.c_float), ("scale_bounce_pos", C.c_float), ("scale_bounce_time", C.c_float),
         ("w_pos", C.c_float), ("w_ball_pos", C.c_float),
         ("court_min", C.c_float * 2), ("court_max", C.c_float * 2), ("est_params", C.c_float * 15),
@@ -252,6 +252,25 @@ class V2PCtrl(C.Structure):
         ("est_bounce_pos", C.c_void_p), ("est_bounce_time", C.c_void_p), ("est_max_height", C.c_void_p), ("distance", C.c_void_p),
         ("obs_buf", C.c_void_p), ("rew_buf", C.c_void_p), ("sub_rewards", C.c_void_p),
         ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p), ("ball_obs", C.c_void_p),
+    ]
+
+
+class V2PPreStep(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("num_actions", C.c_int32), ("num_latent", C.c_int32), ("num_res_dof", C.c_int32),
+        ("random_walk_in_recovery", C.c_int32), ("vae_action_scale", C.c_float), ("residual_dof_scale", C.c_float), ("seed", C.c_uint64),
+        ("actions", C.c_void_p), ("tar_action", C.c_void_p), ("step_counter", C.c_void_p), ("done_counter", C.c_void_p),
+        ("mvae_actions", C.c_void_p), ("res_dof_actions", C.c_void_p),
+    ]
+
+
+class V2PStream(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("frames", C.c_int32), ("advance", C.c_int32), ("pad_", C.c_int32),
+        ("clock", C.c_void_p), ("done_counter", C.c_void_p), ("offset", C.c_void_p),
+        ("ring_rotmat", C.c_void_p), ("rotmat", C.c_void_p), ("ring_root_pos", C.c_void_p), ("root_pos", C.c_void_p),
+        ("ring_racket_pos", C.c_void_p), ("racket_pos", C.c_void_p), ("ring_phase", C.c_void_p), ("phase", C.c_void_p),
+        ("ring_swing_type", C.c_void_p), ("swing_type", C.c_void_p), ("ring_swing_type_cycle", C.c_void_p), ("swing_type_cycle", C.c_void_p),
     ]
 
 

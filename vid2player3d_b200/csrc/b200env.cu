@@ -15,6 +15,7 @@
 //   MotionLib.get_motion_state         utils/motion_lib.py:164-266, 427-436, 460-488
 //   obs / reward / reset               env/tasks/humanoid_smpl_im.py:653-668, 773-850, 918-987
 //   quaternion helpers                 utils/torch_utils.py:70-243
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -1538,27 +1539,43 @@ motion_context_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __res
 }
 
 // compute_humanoid_observations_imitation (humanoid_smpl_im.py:773-850): warp per env, lane per body
+// element strides of the state arrays of obs_imitation_kernel: contiguous [n, nb, 3] / [n, nb, 4] / [n, nd] copies (legacy entry) or the
+// Isaac-layout rows themselves (rigid_body_state [n, bodies_per_env, 13], dof_state [n, nd, 2]) - no gather copies
+struct ObsStrides { int p_row, p_elem, q_row, q_elem, d_row, d_elem; };
+struct ObsBf16 { __nv_bfloat16* out; int ld; const float* mean; const float* rstd; float clamp; };
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restrict__ body_pos, const float* __restrict__ body_rot,
                      const float* __restrict__ target_pos, const float* __restrict__ target_rot, const float* __restrict__ dof_pos,
                      const float* __restrict__ dof_vel, const float* __restrict__ target_dof_pos, const float* __restrict__ body_vel,
                      const float* __restrict__ body_ang_vel, const float* __restrict__ motion_bodies, int local_root_obs,
-                     int root_height_obs, float* __restrict__ obs, int jpos) {
+                     int root_height_obs, float* __restrict__ obs, int jpos, ObsStrides st, ObsBf16 ob) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
   if (e >= n) return;
   // jpos = compute_humanoid_observations_imitation_jpos (:853-915): no rotation / heading / dof targets
   const int W = jpos ? 1 + (nb - 1) * 3 + nb * 6 + nb * 3 + nb * 3 + nd + 1 + 2 + nb * 3 + shape_dim
                      : 1 + (nb - 1) * 3 + nb * 6 + nb * 3 + nb * 3 + nd + 1 + 6 + 2 + 2 + nd + nb * 3 + nb * 6 + shape_dim;
-  float* o = obs + e * W;
+  // every value goes through put(): the float row the reference returns and, when asked for, the bf16 operand row of the policy's
+  // first layer = clamp((x - mean) * rstd, -clamp, clamp) (RunningMeanStd + the +-5 clamp of im_player.py:187-190) in the same launch
+  float* orow = obs + e * W;
+  __nv_bfloat16* brow = ob.out ? ob.out + e * (int64_t)ob.ld : nullptr;
+  auto put = [&](int idx, float val) {
+    orow[idx] = val;
+    if (brow) {
+      float x = val;
+      if (ob.mean) x = (x - __ldg(ob.mean + idx)) * __ldg(ob.rstd + idx);
+      brow[idx] = __float2bfloat16_rn(fminf(fmaxf(x, -ob.clamp), ob.clamp));
+    }
+  };
   const bool act = lane < nb;
   float p[3] = {0, 0, 0}, q[4] = {0, 0, 0, 1}, v[3] = {0, 0, 0}, w[3] = {0, 0, 0}, tp[3] = {0, 0, 0}, tq[4] = {0, 0, 0, 1};
   if (act) {
     const int64_t i3 = (e * nb + lane) * 3, i4 = (e * nb + lane) * 4;
+    const int64_t s3 = e * st.p_row + (int64_t)lane * st.p_elem, s4 = e * st.q_row + (int64_t)lane * st.q_elem;   // state arrays: own strides
 #pragma unroll
-    for (int k = 0; k < 3; k++) { p[k] = body_pos[i3 + k]; v[k] = body_vel[i3 + k]; w[k] = body_ang_vel[i3 + k]; tp[k] = target_pos[i3 + k]; }
+    for (int k = 0; k < 3; k++) { p[k] = body_pos[s3 + k]; v[k] = body_vel[s3 + k]; w[k] = body_ang_vel[s3 + k]; tp[k] = target_pos[i3 + k]; }
 #pragma unroll
-    for (int k = 0; k < 4; k++) { q[k] = body_rot[i4 + k]; tq[k] = target_rot[i4 + k]; }
+    for (int k = 0; k < 4; k++) { q[k] = body_rot[s4 + k]; tq[k] = target_rot[i4 + k]; }
   }
   float rp[3], rq[4], trp[3], trq[4];
 #pragma unroll
@@ -1572,14 +1589,14 @@ obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restri
   ref_remove_base_rot(trq, t_root_rot);
   const float t_heading = ref_calc_heading(t_root_rot);
   int off = 0;
-  if (lane == 0) o[0] = root_height_obs ? rp[2] : 0.f;
+  if (lane == 0) put(0, root_height_obs ? rp[2] : 0.f);
   off = 1;
   if (act) {
     float d[3] = {p[0] - rp[0], p[1] - rp[1], p[2] - rp[2]}, l[3];
     ref_quat_rotate(hq, d, l);
     if (lane > 0) {
 #pragma unroll
-      for (int k = 0; k < 3; k++) o[off + (lane - 1) * 3 + k] = l[k];
+      for (int k = 0; k < 3; k++) put(off + (lane - 1) * 3 + k, l[k]);
     }
   }
   off += (nb - 1) * 3;
@@ -1589,52 +1606,52 @@ obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restri
     ref_tan_norm(lq, tn);
     if (lane == 0 && local_root_obs) ref_tan_norm(root_rot, tn);  // quirk kept (:806-809)
 #pragma unroll
-    for (int k = 0; k < 6; k++) o[off + lane * 6 + k] = tn[k];
+    for (int k = 0; k < 6; k++) put(off + lane * 6 + k, tn[k]);
   }
   off += nb * 6;
   if (act) {
     float l[3];
     ref_quat_rotate(hq, v, l);
 #pragma unroll
-    for (int k = 0; k < 3; k++) o[off + lane * 3 + k] = l[k];
+    for (int k = 0; k < 3; k++) put(off + lane * 3 + k, l[k]);
     ref_quat_rotate(hq, w, l);
 #pragma unroll
-    for (int k = 0; k < 3; k++) o[off + nb * 3 + lane * 3 + k] = l[k];
+    for (int k = 0; k < 3; k++) put(off + nb * 3 + lane * 3 + k, l[k]);
   }
   off += nb * 6;
-  for (int k = lane; k < nd; k += 32) o[off + k] = dof_vel[e * nd + k];
+  for (int k = lane; k < nd; k += 32) put(off + k, dof_vel[e * st.d_row + (int64_t)k * st.d_elem]);
   off += nd;
   if (jpos) {
     if (lane == 0) {
-      o[off] = rp[2] - trp[2];
+      put(off, rp[2] - trp[2]);
       float d[3] = {trp[0] - rp[0], trp[1] - rp[1], trp[2] - rp[2]}, l[3];
       ref_quat_rotate(hq, d, l);
-      o[off + 1] = l[0]; o[off + 2] = l[1];
+      put(off + 1, l[0]); put(off + 2, l[1]);
     }
     off += 3;
   } else {
     if (lane == 0) {
-      o[off] = rp[2] - trp[2];
+      put(off, rp[2] - trp[2]);
       float cj[4] = {-root_rot[0], -root_rot[1], -root_rot[2], root_rot[3]}, rel[4], tn[6];
       qmul(t_root_rot, cj, rel);
       ref_tan_norm(rel, tn);
 #pragma unroll
-      for (int k = 0; k < 6; k++) o[off + 1 + k] = tn[k];
+      for (int k = 0; k < 6; k++) put(off + 1 + k, tn[k]);
       float d[3] = {trp[0] - rp[0], trp[1] - rp[1], trp[2] - rp[2]}, l[3];
       ref_quat_rotate(hq, d, l);
-      o[off + 7] = l[0]; o[off + 8] = l[1];
+      put(off + 7, l[0]); put(off + 8, l[1]);
       const float dh = t_heading - heading;
-      o[off + 9] = cosf(dh); o[off + 10] = sinf(dh);
+      put(off + 9, cosf(dh)); put(off + 10, sinf(dh));
     }
     off += 11;
-    for (int k = lane; k < nd; k += 32) o[off + k] = target_dof_pos[e * nd + k] - dof_pos[e * nd + k];
+    for (int k = lane; k < nd; k += 32) put(off + k, target_dof_pos[e * st.d_row + (int64_t)k * st.d_elem] - dof_pos[e * st.d_row + (int64_t)k * st.d_elem]);
     off += nd;
   }
   if (act) {
     float d[3] = {tp[0] - p[0], tp[1] - p[1], tp[2] - p[2]}, l[3];
     ref_quat_rotate(hq, d, l);
 #pragma unroll
-    for (int k = 0; k < 3; k++) o[off + lane * 3 + k] = l[k];
+    for (int k = 0; k < 3; k++) put(off + lane * 3 + k, l[k]);
   }
   off += nb * 3;
   if (!jpos) {
@@ -1643,11 +1660,11 @@ obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restri
       qmul(cj, tq, rel);
       ref_tan_norm(rel, tn);
 #pragma unroll
-      for (int k = 0; k < 6; k++) o[off + lane * 6 + k] = tn[k];
+      for (int k = 0; k < 6; k++) put(off + lane * 6 + k, tn[k]);
     }
     off += nb * 6;
   }
-  if (lane < shape_dim) o[off + lane] = motion_bodies[e * shape_dim + lane];
+  if (lane < shape_dim) put(off + lane, motion_bodies[e * shape_dim + lane]);
 }
 
 // physics-only entry used by the parity tests (float or double)
@@ -2005,7 +2022,32 @@ int b200env_obs_imitation(b200env_handle h, int32_t n, const float* body_pos, co
   obs_imitation_kernel<<<grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(n, nbl, h->model.nd, h->cfg.shape_dim, body_pos, body_rot,
                                                                               target_pos, target_rot, dof_pos, dof_vel, target_dof_pos,
                                                                               body_vel, body_ang_vel, motion_bodies, local_root_obs & 1,
-                                                                              root_height_obs, obs, (local_root_obs >> 1) & 1);
+                                                                              root_height_obs, obs, (local_root_obs >> 1) & 1,
+                                                                              ObsStrides{nbl * 3, 3, nbl * 4, 4, h->model.nd, 1}, ObsBf16{nullptr, 0, nullptr, nullptr, 0.f});
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int b200env_obs_imitation_rows(b200env_handle h, int32_t n, const float* rigid_body_state, int32_t bodies_per_env, const float* dof_state,
+                               const float* target_pos, const float* target_rot, const float* target_dof_pos, const float* motion_bodies,
+                               int32_t local_root_obs, int32_t root_height_obs, float* obs, void* obs_bf16, int32_t ld_bf16, const float* mean,
+                               const float* rstd, float clamp, void* stream) {
+  if (!h || !rigid_body_state || !dof_state || !target_pos || !target_rot || !target_dof_pos || !motion_bodies || !obs)
+    return fail(-1, "b200env_obs_imitation_rows: null argument%s");
+  if (n <= 0) return fail(-2, "b200env_obs_imitation_rows: n must be positive%s");
+  const int nbl = h->has_ml ? h->ml.num_lib_bodies : (h->model.fixed[h->model.nb - 1] ? h->model.nb - 1 : h->model.nb);
+  if (bodies_per_env < nbl) return fail(-2, "b200env_obs_imitation_rows: bodies_per_env smaller than the humanoid%s");
+  if ((mean == nullptr) != (rstd == nullptr)) return fail(-2, "b200env_obs_imitation_rows: mean and rstd go together%s");
+  if (obs_bf16 && !(clamp > 0.f)) return fail(-2, "b200env_obs_imitation_rows: the bf16 row needs a positive clamp%s");
+  cudaSetDevice(h->device);
+  const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const int nd = h->model.nd;
+  obs_imitation_kernel<<<grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+      n, nbl, nd, h->cfg.shape_dim, rigid_body_state, rigid_body_state + 3, target_pos, target_rot, dof_state, dof_state + 1, target_dof_pos,
+      rigid_body_state + 7, rigid_body_state + 10, motion_bodies, local_root_obs & 1, root_height_obs, obs, (local_root_obs >> 1) & 1,
+      ObsStrides{bodies_per_env * 13, 13, bodies_per_env * 13, 13, nd * 2, 2},
+      ObsBf16{reinterpret_cast<__nv_bfloat16*>(obs_bf16), ld_bf16, mean, rstd, clamp});
   CUDA_OK(cudaGetLastError());
   h->launches++;
   return 0;

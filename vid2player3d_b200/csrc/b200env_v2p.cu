@@ -88,8 +88,9 @@ __device__ __forceinline__ void qmul_xyzw(const float* a, const float* b, float*
 __global__ void __launch_bounds__(V2P_WARPS * 32)
 smpl_to_sim_kernel(int n, const float* __restrict__ root_pos, const float* __restrict__ rotmat, const float* __restrict__ rest_all,
                    int num_rest, const int32_t* __restrict__ parents, const int32_t* __restrict__ smpl_2_mujoco, float dt,
-                   const float* __restrict__ prev_root_pos, const float* __restrict__ prev_rb_rot, float* root_rot, float* dof_pos,
-                   float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot) {
+                   const float* prev_root_pos, const float* __restrict__ prev_rb_rot, float* root_rot, float* dof_pos,
+                   float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, float* prev_root_pos_update,
+                   float* target_root_pos_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * V2P_WARPS + warp;
   if (e >= n) return;
@@ -184,6 +185,16 @@ smpl_to_sim_kernel(int n, const float* __restrict__ root_pos, const float* __res
       } else {
 #pragma unroll
         for (int k = 0; k < 3; k++) dof_vel[e * 69 + (mj - 1) * 3 + k] = 0.0f;
+      }
+    }
+    // _save_prev_target_motion_state (:741-750) / `self._target_root_pos = root_pos` folded in: the lane that just read the previous
+    // root position stores the current one (prev_root_pos_update may alias prev_root_pos)
+    if (mj == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const float r = root_pos[e * 3 + k];
+        if (prev_root_pos_update) prev_root_pos_update[e * 3 + k] = r;
+        if (target_root_pos_out) target_root_pos_out[e * 3 + k] = r;
       }
     }
   }
@@ -338,6 +349,25 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p
   const int64_t e = (int64_t)blockIdx.x * V2P_WARPS + warp;
   if (e >= c.n) return;
   const float* rb = c.rigid_body_state + e * c.bodies_per_env * 13;
+  if (c.advance && !c.obs_only) {
+    // tail of physics_step (:364-366) + head of post_physics_step (:441-444) folded in: the future-trajectory window moves on by one
+    // frame (roll(-1), last frame zeroed), the reaction timer and the episode progress count one step.  In place inside the warp.
+    float* tr = c.ball_traj + e * 300;
+    float tmp[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      const int k = lane + 32 * i;
+      tmp[i] = k < 297 ? tr[k + 3] : 0.0f;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      const int k = lane + 32 * i;
+      if (k < 300) tr[k] = tmp[i];
+    }
+    if (lane == 0) { c.tar_time[e] += 1; c.progress_buf[e] += 1; }
+    __syncwarp();
+  }
   const float rp[3] = {c.root_pos[e * 3], c.root_pos[e * 3 + 1], c.root_pos[e * 3 + 2]};
   const float bp[3] = {c.ball_pos[e * 3], c.ball_pos[e * 3 + 1], c.ball_pos[e * 3 + 2]};
   const float kp[3] = {c.racket_pos[e * 3], c.racket_pos[e * 3 + 1], c.racket_pos[e * 3 + 2]};
@@ -660,6 +690,74 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) actor_reset_kernel(b200v2p_are
   }
 }
 
+// ------------------------------------------------------------------------------------------ high-level pre_physics_step
+// PhysicsMVAEController.pre_physics_step (:247-262) before the motion generator runs: the latent part of the action scaled by
+// vae_action_scale, replaced by clamp(N(0,1), -5, 5) for the envs in recovery (random_walk_in_recovery), the residual-dof part scaled
+// by residual_dof_scale.  The normal deviates come from a counter-based generator (splitmix64 of seed, step counter, element index +
+// Box-Muller) so that the step needs no separate RNG launch; the step counter lives on the device and is advanced by the last
+// block to finish, which keeps the launch replayable inside a CUDA graph.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ float counter_normal(uint64_t seed, uint64_t step, uint64_t idx) {
+  const uint64_t h = splitmix64(splitmix64(seed ^ (step * 0xD1B54A32D192ED03ull)) + idx);
+  const float u1 = ((uint32_t)(h >> 40) + 1u) * (1.0f / 16777217.0f);     // (0, 1)
+  const float u2 = (uint32_t)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+}
+__device__ __forceinline__ void last_block_advance(int64_t* counter, unsigned int* done, int64_t inc) {
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) { counter[0] += inc; *done = 0u; __threadfence(); }
+}
+__global__ void pre_step_kernel(b200v2p_prestep_t p) {
+  const int W = p.num_latent + p.num_res_dof;
+  const int64_t step = p.step_counter[0];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)p.n * W) {
+    const int64_t e = i / W;
+    const int k = (int)(i - e * W);
+    const float a = p.actions[e * p.num_actions + k];
+    if (k < p.num_latent) {
+      float v = a * p.vae_action_scale;
+      if (p.random_walk_in_recovery && p.tar_action[e] == 0) v = fminf(fmaxf(counter_normal(p.seed, (uint64_t)step, (uint64_t)i), -5.0f), 5.0f);
+      p.mvae_actions[e * p.num_latent + k] = v;
+    } else {
+      p.res_dof_actions[e * p.num_res_dof + (k - p.num_latent)] = a * p.residual_dof_scale;
+    }
+  }
+  last_block_advance(p.step_counter, p.done_counter, 1);
+}
+
+// ------------------------------------------------------------------------------------------ resident kinematic target stream
+// StreamMotionPlayer (tasks/physics_mvae_controller.py; SURVEY.md 8d "synthetic kinematic target stream"): env e reads frame
+// (t + off[e]) % K of the ring kept in HBM into the live buffers the FK kernel and the controller read.  One launch instead of six
+// index_selects and the index arithmetic; `advance` = 1 moves the stream clock on by one frame first (step), 0 re-reads (reset).
+__global__ void __launch_bounds__(V2P_WARPS * 32) stream_gather_kernel(b200v2p_stream_t s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * V2P_WARPS + warp;
+  const int64_t t = s.clock[0] + s.advance;
+  if (e < s.n) {
+    int64_t f = (t + s.offset[e]) % s.frames;
+    if (f < 0) f += s.frames;
+    const int64_t row = f * s.n + e;
+    const float4* src = reinterpret_cast<const float4*>(s.ring_rotmat + row * 216);
+    float4* dst = reinterpret_cast<float4*>(s.rotmat + e * 216);
+    for (int k = lane; k < 54; k += 32) dst[k] = src[k];
+    if (lane < 3) { s.root_pos[e * 3 + lane] = s.ring_root_pos[row * 3 + lane]; s.racket_pos[e * 3 + lane] = s.ring_racket_pos[row * 3 + lane]; }
+    if (lane == 3) s.phase[e] = s.ring_phase[row];
+    if (lane == 4) s.swing_type[e] = s.ring_swing_type[row];
+    if (lane == 5) s.swing_type_cycle[e] = s.ring_swing_type_cycle[row];
+  }
+  if (s.advance) last_block_advance(s.clock, s.done_counter, s.advance);
+}
+
 // ------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -667,7 +765,8 @@ const char* b200v2p_last_error(void) { return g_verr; }
 
 int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rotmat, const float* rest, int32_t num_rest,
                         const int32_t* parents, const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
-                        float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, void* stream) {
+                        float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, float* prev_root_pos_update,
+                        float* target_root_pos_out, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || !root_pos || !joint_rotmat || !rest || !parents || !smpl_2_mujoco || !root_rot || !dof_pos || !root_vel || !root_ang_vel ||
       !dof_vel || !rb_pos || !rb_rot)
@@ -676,7 +775,7 @@ int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rot
   if (num_rest < 1) return vfail(-2, "b200v2p_smpl_to_sim: num_rest must be >= 1");
   smpl_to_sim_kernel<<<(n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(
       n, root_pos, joint_rotmat, rest, num_rest, parents, smpl_2_mujoco, dt, prev_root_pos, prev_rb_rot, root_rot, dof_pos, root_vel, root_ang_vel,
-      dof_vel, rb_pos, rb_rot);
+      dof_vel, rb_pos, rb_rot, prev_root_pos_update, target_root_pos_out);
   V_CUDA_OK();
   return 0;
 }
@@ -754,6 +853,31 @@ int b200v2p_task_reset(const b200v2p_treset_t* r, void* stream) {
   if (r->n == 0) return 0;
   if (r->pool_size < 1 || !r->pool || !r->reset_reaction || !r->reset_recovery) return vfail(-1, "b200v2p_task_reset: bad arguments");
   task_reset_kernel<<<(r->n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(*r);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_pre_step(const b200v2p_prestep_t* p, void* stream) {
+  if (!p) return vfail(-1, "b200v2p_pre_step: null");
+  if (p->n == 0) return 0;
+  if (p->n < 0 || !p->actions || !p->mvae_actions || !p->step_counter || !p->done_counter || p->num_latent < 1 || p->num_res_dof < 0 ||
+      p->num_actions < p->num_latent + p->num_res_dof || (p->num_res_dof > 0 && !p->res_dof_actions) || (p->random_walk_in_recovery && !p->tar_action))
+    return vfail(-1, "b200v2p_pre_step: bad arguments");
+  const int64_t total = (int64_t)p->n * (p->num_latent + p->num_res_dof);
+  pre_step_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_stream_gather(const b200v2p_stream_t* s, void* stream) {
+  if (!s) return vfail(-1, "b200v2p_stream_gather: null");
+  if (s->n == 0) return 0;
+  if (s->n < 0 || s->frames < 1 || !s->clock || !s->done_counter || !s->offset || !s->ring_rotmat || !s->rotmat || !s->ring_root_pos || !s->root_pos ||
+      !s->ring_racket_pos || !s->racket_pos || !s->ring_phase || !s->phase || !s->ring_swing_type || !s->swing_type || !s->ring_swing_type_cycle ||
+      !s->swing_type_cycle || s->advance < 0)
+    return vfail(-1, "b200v2p_stream_gather: bad arguments");
+  if (((uintptr_t)s->ring_rotmat | (uintptr_t)s->rotmat) & 15) return vfail(-2, "b200v2p_stream_gather: rotation matrices must be 16-byte aligned");
+  stream_gather_kernel<<<(s->n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(*s);
   V_CUDA_OK();
   return 0;
 }

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/b200nn.h"
 
@@ -68,10 +69,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 4000000000LL) {
-      printf("b200nn: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) __trap();   // surfaces as a launch failure on the host
   }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -114,17 +112,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
+// TMEM -> registers: the warp's 32 lanes x 16 (32) consecutive columns, one row per thread.  The load is asynchronous: several are
+// issued back to back and ONE tcgen05.wait::ld covers them (the round trip is ~0.5 us when every load is waited for on its own).
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == B200NN_ACT_RELU) return fmaxf(x, 0.f);
@@ -132,12 +139,33 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+
+#ifndef B200NN_PROBE
+#define B200NN_PROBE 0
+#endif
+#if B200NN_PROBE
+__device__ unsigned long long g_probe[16];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PROBE(i) do { if (blockIdx.x == 0 && blockIdx.y == 0) g_probe[i] = gtime(); } while (0)
+__device__ unsigned long long g_cta[4096][2];
+#define PROBE_CTA(k) do { const int c_ = blockIdx.y * gridDim.x + blockIdx.x; if (c_ < 4096) g_cta[c_][k] = gtime(); } while (0)
+#else
+#define PROBE_CTA(k) do { } while (0)
+#define PROBE(i) do { } while (0)
+#endif
+
 struct LinearParams {
   const float* bias;
   const float* coef;
   void* out;
   int ldo, out_col0, rows, n, n_padded, k_padded, act, out_bf16;
+  float out_min, out_max;
 };
+
+__device__ __forceinline__ float finish(float x, const LinearParams& p) {
+  x = apply_act(x, p.act);
+  return p.out_min < p.out_max ? fminf(fmaxf(x, p.out_min), p.out_max) : x;
+}
 
 __host__ __device__ constexpr int tmem_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
@@ -180,12 +208,14 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* sbias = reinterpret_cast<float*>(tmem_holder + 4);        // [E][BN] bias of this tile's columns
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BN;
   const int nkb = p.k_padded / BLOCK_K;
 
+  if (threadIdx.x == 0) { PROBE(0); PROBE_CTA(0); }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -201,9 +231,16 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) PROBE(1);
+  // Programmatic dependent launch: the next layer's CTAs may be scheduled as soon as ours have all started (they take the SM
+  // slots our last wave leaves free, run their set-up and park at griddepcontrol.wait), and everything ABOVE this line ran
+  // while the previous layer was still finishing.  Below it, every read of data a previous kernel produced (the A operand, the
+  // blend coefficients) comes after griddepcontrol.wait = previous grid complete and visible.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {   // ---------------- TMA producer
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int kb = 0; kb < nkb; kb++) {
         const int s = kb % STAGES;
         mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
@@ -211,13 +248,16 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         mbar_expect_tx(&full[s], STAGE_BYTES);
         tma_load_2d(sa, &tmA, kb * BLOCK_K, m0, &full[s]);
         tma_load_3d(sa + A_STAGE_BYTES, &tmW, kb * BLOCK_K, n0, 0, &full[s]);
+        if (kb == 0) PROBE(2);
       }
+      PROBE(3);
     }
   } else if (warp == 1) {
     if (lane == 0) {   // ---------------- MMA issuer (one thread)
       for (int kb = 0; kb < nkb; kb++) {
         const int s = kb % STAGES;
         mbar_wait(&full[s], (kb / STAGES) & 1);
+        if (kb == 0) PROBE(4);
         tcgen05_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES), b_addr = a_addr + A_STAGE_BYTES;
 #pragma unroll
@@ -233,38 +273,66 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         umma_commit(&empty[s]);      // the stage is free again once these MMAs have read it
       }
       umma_commit(tmem_full);        // accumulators complete
+      PROBE(5);
     }
     __syncwarp();
   } else {
     // ---------------- epilogue: warp w may touch TMEM lanes 32 (w % 4) .. +31 = rows m0 + 32 (w % 4) + lane
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
+    // everything that does not depend on the accumulators happens BEFORE the wait: the tile's bias goes to shared memory, the
+    // row's blend coefficients to registers
+    for (int i = (int)threadIdx.x - 64; i < ACC; i += 128) sbias[i] = __ldg(p.bias + (size_t)(i / BN) * p.n_padded + n0 + (i % BN));
     float coef[E];
+    if (E > 1) asm volatile("griddepcontrol.wait;" ::: "memory");    // the coefficients come from the gate kernel before us
 #pragma unroll
     for (int e = 0; e < E; e++) coef[e] = (E == 1) ? 1.f : (row < p.rows ? p.coef[(size_t)row * E + e] : 0.f);
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 epilogue warps only
     mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 64) PROBE(6);
     tcgen05_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    if constexpr (E == 1) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float y[16];
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        if (n0 + c0 >= p.n) break;                   // padding columns of the last tile: nothing to store
+        uint32_t r[64];
+        tmem_ld32_issue(trow + c0, r);
+        tmem_ld32_issue(trow + c0 + 32, r + 32);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; i++) y[i] = 0.f;
+        for (int j = 0; j < 4; j++) {
+          float y[16];
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        float v[16];
-        tmem_ld16(trow + e * BN + c0, v);
-        const float* b = p.bias + (size_t)e * p.n_padded + n0 + c0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) y[i] = fmaf(coef[e], v[i] + __ldg(b + i), y[i]);
+          for (int i = 0; i < 16; i++) y[i] = finish(__uint_as_float(r[16 * j + i]) + sbias[c0 + 16 * j + i], p);
+          if (row < p.rows) store16(p, row, n0 + c0 + 16 * j, y);
+        }
       }
+    } else {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        if (n0 + c0 >= p.n) break;
+        uint32_t r[E][16];
 #pragma unroll
-      for (int i = 0; i < 16; i++) y[i] = apply_act(y[i], p.act);
-      if (row < p.rows) store16(p, row, n0 + c0, y);
+        for (int e = 0; e < E; e++) tmem_ld16_issue(trow + e * BN + c0, r[e]);     // E loads in flight, one wait
+        tmem_ld_wait();
+        float y[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) y[i] = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; e++)
+#pragma unroll
+          for (int i = 0; i < 16; i++) y[i] = fmaf(coef[e], __uint_as_float(r[e][i]) + sbias[e * BN + c0 + i], y[i]);
+#pragma unroll
+        for (int i = 0; i < 16; i++) y[i] = finish(y[i], p);
+        if (row < p.rows) store16(p, row, n0 + c0, y);
+      }
     }
+    if (threadIdx.x == 64) { PROBE(7); PROBE_CTA(1); }
     tcgen05_fence_before();
   }
   __syncthreads();
+  if (threadIdx.x == 0) PROBE(8);
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -272,15 +340,22 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------------------------------ small SIMT kernels
-__global__ void cast_rows_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst, int rows, int cols,
-                                 const float* __restrict__ mean, const float* __restrict__ rstd, float lo, float hi) {
-  const int64_t total = (int64_t)rows * cols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cols), c = (int)(i % cols);
-    float x = src[(size_t)r * ld_src + c];
-    if (mean) x = (x - mean[c]) * rstd[c];
-    x = fminf(fmaxf(x, lo), hi);
-    dst[(size_t)r * ld_dst + c] = __float2bfloat16_rn(x);
+// rows strided by the grid, columns by the block: coalesced, no integer division; up to three destinations of the same leading
+// dimension get the same values (the latent block of the three MixedDecoder layer inputs)
+__global__ void cast_rows_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst2,
+                                 __nv_bfloat16* __restrict__ dst3, int ld_dst, int rows, int cols, const float* __restrict__ mean,
+                                 const float* __restrict__ rstd, float lo, float hi) {
+  for (int r = blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += gridDim.x * blockDim.y) {
+    const float* s = src + (size_t)r * ld_src;
+    const size_t o = (size_t)r * ld_dst;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+      float x = s[c];
+      if (mean) x = (x - __ldg(mean + c)) * __ldg(rstd + c);
+      const __nv_bfloat16 v = __float2bfloat16_rn(fminf(fmaxf(x, lo), hi));
+      dst[o + c] = v;
+      if (dst2) dst2[o + c] = v;
+      if (dst3) dst3[o + c] = v;
+    }
   }
 }
 
@@ -325,7 +400,7 @@ encode_tiled_fn get_encode() {
   return fn;
 }
 
-template <int E, int BN, int STAGES> constexpr int smem_bytes() { return STAGES * (A_STAGE_BYTES + E * BN * BLOCK_K * 2) + 1024 + 256; }
+template <int E, int BN, int STAGES> constexpr int smem_bytes() { return STAGES * (A_STAGE_BYTES + E * BN * BLOCK_K * 2) + 1024 + 256 + E * BN * 4; }
 
 }  // namespace
 
@@ -333,7 +408,7 @@ struct b200nn_linear {
   b200nn_linear_desc_t d;
   CUtensorMap tmA, tmW;
   LinearParams p;
-  int device, bn;
+  int device, bn, pdl;
   dim3 grid;
 };
 
@@ -343,8 +418,17 @@ template <int E, int BN, int STAGES> static int launch(const b200nn_linear* h, c
     CUDA_OK(cudaFuncSetAttribute(linear_kernel<E, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<E, BN, STAGES>()));
     attr_set[h->device & 15] = true;
   }
-  linear_kernel<E, BN, STAGES><<<h->grid, NUM_THREADS, smem_bytes<E, BN, STAGES>(), st>>>(h->tmA, h->tmW, h->p);
-  CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = h->grid;
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes<E, BN, STAGES>();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, linear_kernel<E, BN, STAGES>, h->tmA, h->tmW, h->p));
   return 0;
 }
 
@@ -373,6 +457,10 @@ int b200nn_linear_create(const b200nn_linear_desc_t* d, int32_t device, b200nn_l
   h->d = *d;
   h->device = device;
   h->bn = bn;
+  {
+    const char* e = getenv("B200NN_PDL");    // A/B switch: B200NN_PDL=0 launches the layers without programmatic dependent launch
+    h->pdl = !(e && e[0] == '0');
+  }
   const int rows_padded = (d->rows + BLOCK_M - 1) / BLOCK_M * BLOCK_M;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->k_padded, (cuuint64_t)rows_padded};
@@ -390,7 +478,7 @@ int b200nn_linear_create(const b200nn_linear_desc_t* d, int32_t device, b200nn_l
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete h; snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled(W) failed: %d", (int)r); return -3; }
   }
-  h->p = LinearParams{d->bias, d->coef, d->out, d->ldo, d->out_col0, d->rows, d->n, d->n_padded, d->k_padded, d->act, d->out_bf16};
+  h->p = LinearParams{d->bias, d->coef, d->out, d->ldo, d->out_col0, d->rows, d->n, d->n_padded, d->k_padded, d->act, d->out_bf16, d->out_min, d->out_max};
   h->grid = dim3(rows_padded / BLOCK_M, (d->n + bn - 1) / bn, 1);
   *out = h;
   return 0;
@@ -415,15 +503,32 @@ int b200nn_linear_run(b200nn_linear_handle h, void* stream) {
   return fail(-2, "b200nn_linear_run: unsupported expert count");
 }
 
-int b200nn_cast_rows(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, int32_t rows, int32_t cols, const float* mean, const float* rstd,
-                     float lo, float hi, void* stream) {
+#if B200NN_PROBE
+int b200nn_probe_read_ctas(unsigned long long* out, int n) { return cudaMemcpyFromSymbol(out, g_cta, sizeof(unsigned long long) * 2 * n) == cudaSuccess ? 0 : -1; }
+int b200nn_probe_read(unsigned long long* out16) { return cudaMemcpyFromSymbol(out16, g_probe, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -1; }
+#endif
+
+static int cast_launch(const float* src, int32_t ld_src, void* dst, void* dst2, void* dst3, int32_t ld_dst, int32_t rows, int32_t cols,
+                       const float* mean, const float* rstd, float lo, float hi, void* stream) {
   if (!src || !dst || rows < 1 || cols < 1 || cols > ld_src || cols > ld_dst) return fail(-2, "b200nn_cast_rows: bad argument");
   if ((mean == nullptr) != (rstd == nullptr)) return fail(-2, "b200nn_cast_rows: mean and rstd go together");
-  const int64_t total = (int64_t)rows * cols;
-  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  cast_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols, mean, rstd, lo, hi);
+  const int tx = cols >= 256 ? 256 : (cols >= 128 ? 128 : (cols >= 64 ? 64 : 32));
+  const dim3 block(tx, 256 / tx, 1);
+  const int want = (rows + (int)block.y - 1) / (int)block.y;
+  const int blocks = want < 148 * 16 ? want : 148 * 16;
+  cast_rows_kernel<<<blocks, block, 0, (cudaStream_t)stream>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<__nv_bfloat16*>(dst2),
+                                                             reinterpret_cast<__nv_bfloat16*>(dst3), ld_dst, rows, cols, mean, rstd, lo, hi);
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int b200nn_cast_rows(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, int32_t rows, int32_t cols, const float* mean, const float* rstd,
+                     float lo, float hi, void* stream) {
+  return cast_launch(src, ld_src, dst, nullptr, nullptr, ld_dst, rows, cols, mean, rstd, lo, hi, stream);
+}
+
+int b200nn_cast_rows3(const float* src, int32_t ld_src, void* dst, void* dst2, void* dst3, int32_t ld_dst, int32_t rows, int32_t cols, void* stream) {
+  return cast_launch(src, ld_src, dst, dst2, dst3, ld_dst, rows, cols, nullptr, nullptr, -3.0e38f, 3.0e38f, stream);
 }
 
 int b200nn_gate_softmax(const void* h, int32_t ldh, int32_t k, const float* w, const float* b, int32_t E, float* coef, int32_t rows, void* stream) {

@@ -14,7 +14,7 @@ _lib = None
 SYMBOLS = ["b200env_abi_version", "b200env_last_error", "b200env_create", "b200env_destroy", "b200env_bind",
            "b200env_set_motion_lib", "b200env_step", "b200env_reset", "b200env_motion_state", "b200env_obs_imitation",
            "b200env_physics_only", "b200env_launch_count", "b200env_set_env_slice", "b200env_motion_context", "b200env_set_kernel_timing",
-           "b200env_kernel_ms"]
+           "b200env_kernel_ms", "b200env_obs_imitation_rows"]
 
 
 def lib():
@@ -138,6 +138,16 @@ class Env:
                                            _ptr(body_vel), _ptr(body_ang_vel), _ptr(motion_bodies),
                                            C.c_int32(int(bool(local_root_obs)) | (2 if jpos else 0)), C.c_int32(int(root_height_obs)), _ptr(obs),
                                            _stream()))
+
+    def obs_imitation_rows(self, n, rigid_body_state, bodies_per_env, dof_state, target_pos, target_rot, target_dof_pos, motion_bodies,
+                           local_root_obs, root_height_obs, obs, obs_bf16=None, mean=None, rstd=None, clamp=5.0):
+        """the 734-d observation straight from the state rows (no gathers); obs_bf16: padded bf16 operand buffer of the policy's
+        first layer, written in the same launch (normalised by mean / rstd when given, clamped to +-clamp)"""
+        _check(lib().b200env_obs_imitation_rows(self._h, C.c_int32(int(n)), _ptr(rigid_body_state), C.c_int32(int(bodies_per_env)), _ptr(dof_state),
+                                                _ptr(target_pos), _ptr(target_rot), _ptr(target_dof_pos), _ptr(motion_bodies),
+                                                C.c_int32(int(bool(local_root_obs))), C.c_int32(int(root_height_obs)), _ptr(obs), _ptr(obs_bf16),
+                                                C.c_int32(int(obs_bf16.shape[1]) if obs_bf16 is not None else 0), _ptr(mean), _ptr(rstd),
+                                                C.c_float(float(clamp)), _stream()))
 
     def physics_only(self, root, dof_pos, dof_vel, pd_tar, ext_wrench, rb_out, contact_out, n_steps=1, ball=None, ball_hits=None):
         import torch

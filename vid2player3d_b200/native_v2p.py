@@ -5,7 +5,7 @@ from . import abi
 from .native import _ptr, _stream, lib
 
 SYMBOLS = ["b200v2p_last_error", "b200v2p_smpl_to_sim", "b200v2p_ball_aero", "b200v2p_ball_reset", "b200v2p_ball_in_estimate", "b200v2p_update_state",
-           "b200v2p_controller_post", "b200v2p_task_reset", "b200v2p_actor_reset", "b200v2p_fix_head"]
+           "b200v2p_controller_post", "b200v2p_task_reset", "b200v2p_actor_reset", "b200v2p_fix_head", "b200v2p_pre_step", "b200v2p_stream_gather"]
 GRIP_NORMAL = {'eastern': (0.0, 1.0, 0.0), 'semi_western': (0.0, 2.0 ** -0.5, 2.0 ** -0.5)}
 REWARD_TYPES = {'reach': 0, 'return': 1, 'return_w_estimate': 2}
 
@@ -22,14 +22,17 @@ def _c(t):
     return _ptr(t)
 
 
-def smpl_to_sim(root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, out, prev_root_pos=None, prev_rb_rot=None):
-    """out: dict with root_rot[n,4] dof_pos[n,69] root_vel[n,3] root_ang_vel[n,3] dof_vel[n,69] rb_pos[n,24,3] rb_rot[n,24,4]"""
+def smpl_to_sim(root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, out, prev_root_pos=None, prev_rb_rot=None, prev_root_pos_update=None,
+                target_root_pos_out=None):
+    """out: dict with root_rot[n,4] dof_pos[n,69] root_vel[n,3] root_ang_vel[n,3] dof_vel[n,69] rb_pos[n,24,3] rb_rot[n,24,4];
+    prev_root_pos_update / target_root_pos_out: the root position of this call is also stored there (may alias prev_root_pos)"""
     n = int(root_pos.shape[0])
     num_rest = 1 if rest.dim() == 2 else int(rest.shape[0])      # rest [24,3] or [S,24,3]: env e uses shape e % S
     assert rest.is_contiguous() and rest.shape[-2:] == (24, 3)
     _check(lib().b200v2p_smpl_to_sim(C.c_int32(n), _c(root_pos), _c(joint_rotmat), _c(rest), C.c_int32(num_rest), _c(parents), _c(smpl_2_mujoco), C.c_float(dt),
                                      _c(prev_root_pos), _c(prev_rb_rot), _c(out["root_rot"]), _c(out["dof_pos"]), _c(out["root_vel"]),
-                                     _c(out["root_ang_vel"]), _c(out["dof_vel"]), _c(out["rb_pos"]), _c(out["rb_rot"]), _stream()))
+                                     _c(out["root_ang_vel"]), _c(out["dof_vel"]), _c(out["rb_pos"]), _c(out["rb_rot"]), _c(prev_root_pos_update),
+                                     _c(target_root_pos_out), _stream()))
 
 
 def fix_head(rb_pos, rb_rot, ball_pos, root_pos, joint_rotmat, head_body=13):
@@ -94,10 +97,11 @@ def controller_post(cfg, t):
     c.obs_only = int(cfg.get("obs_only", 0))
     c.dual = int(cfg.get("dual", 0))
     c.use_history = int(cfg.get("use_history", 0))
+    c.advance = int(cfg.get("advance", 0))
     for k in ("court_min", "court_max", "est_params"):
         for i, v in enumerate(cfg[k]):
             getattr(c, k)[i] = float(v)
-    scalars = {f for f, _ in abi.V2PCtrl._fields_ if f in cfg} | {"obs_only", "dual", "use_history"}
+    scalars = {f for f, _ in abi.V2PCtrl._fields_ if f in cfg} | {"obs_only", "dual", "use_history", "advance"}
     for name, _ in abi.V2PCtrl._fields_:
         if name in scalars:
             continue
@@ -156,3 +160,28 @@ def actor_reset(cfg, t):
         assert x.is_cuda and x.is_contiguous(), name
         setattr(r, name, x.data_ptr())
     _check(lib().b200v2p_actor_reset(C.byref(r), _stream()))
+
+
+def pre_step(cfg, t):
+    """cfg: n, num_actions, num_latent, num_res_dof, random_walk_in_recovery, vae_action_scale, residual_dof_scale, seed;
+    t: actions, tar_action, step_counter (int64 [1]), done_counter (int32 [1]), mvae_actions, res_dof_actions (or None)"""
+    p = abi.V2PPreStep()
+    for k in ("n", "num_actions", "num_latent", "num_res_dof", "random_walk_in_recovery", "seed"):
+        setattr(p, k, int(cfg[k]))
+    p.vae_action_scale, p.residual_dof_scale = float(cfg["vae_action_scale"]), float(cfg["residual_dof_scale"])
+    for k in ("actions", "tar_action", "step_counter", "done_counter", "mvae_actions", "res_dof_actions"):
+        x = t.get(k)
+        assert x is None or (x.is_cuda and x.is_contiguous()), k
+        setattr(p, k, x.data_ptr() if x is not None else None)
+    _check(lib().b200v2p_pre_step(C.byref(p), _stream()))
+
+
+def stream_gather(n, frames, advance, t):
+    """t: clock (int64 [1]), done_counter (int32 [1]), offset [n] int64, ring_* / live buffers of include/b200env_v2p.h b200v2p_stream_t"""
+    s = abi.V2PStream()
+    s.n, s.frames, s.advance = int(n), int(frames), int(advance)
+    for name, _ in abi.V2PStream._fields_[4:]:
+        x = t[name]
+        assert x.is_cuda and x.is_contiguous(), name
+        setattr(s, name, x.data_ptr())
+    _check(lib().b200v2p_stream_gather(C.byref(s), _stream()))

@@ -22,14 +22,15 @@ ACT = {None: 0, "none": 0, "relu": 1, "elu": 2}
 _lib = None
 
 SYMBOLS = ["b200nn_abi_version", "b200nn_last_error", "b200nn_linear_create", "b200nn_linear_destroy", "b200nn_linear_run",
-           "b200nn_cast_rows", "b200nn_gate_softmax"]
+           "b200nn_cast_rows", "b200nn_cast_rows3", "b200nn_gate_softmax"]
 ABI_VERSION = 1
 
 
 class LinearDesc(C.Structure):
     _fields_ = [("a", C.c_void_p), ("lda", C.c_int32), ("w", C.c_void_p), ("ldw", C.c_int32), ("bias", C.c_void_p), ("coef", C.c_void_p),
                 ("out", C.c_void_p), ("ldo", C.c_int32), ("out_col0", C.c_int32), ("rows", C.c_int32), ("n", C.c_int32),
-                ("n_padded", C.c_int32), ("k_padded", C.c_int32), ("num_experts", C.c_int32), ("act", C.c_int32), ("out_bf16", C.c_int32)]
+                ("n_padded", C.c_int32), ("k_padded", C.c_int32), ("num_experts", C.c_int32), ("act", C.c_int32), ("out_bf16", C.c_int32),
+                ("out_min", C.c_float), ("out_max", C.c_float)]
 
 
 def lib():
@@ -73,7 +74,7 @@ class Linear:
     """out[:, col0:col0+N] = act(sum_e coef[:, e] (a W_e^T + b_e)); one launch.  weight [E, N, K] or [N, K] float (torch layout:
     out x in), bias [E, N] or [N]; `a` / `out` are buffers from padded_bf16 (out may also be a float [rows, N] tensor)."""
 
-    def __init__(self, a, weight, bias, out, rows, act=None, coef=None, out_col0=0):
+    def __init__(self, a, weight, bias, out, rows, act=None, coef=None, out_col0=0, out_clamp=None):
         dev = a.device
         if dev.type != "cuda":
             raise RuntimeError("b200nn runs on a CUDA device only (no CPU fallback)")
@@ -97,7 +98,8 @@ class Linear:
             assert coef is not None and coef.dtype == torch.float32 and coef.is_contiguous() and tuple(coef.shape) == (rows, E)
         d = LinearDesc(a=a.data_ptr(), lda=a.shape[1], w=self.w.data_ptr(), ldw=self.k_padded, bias=self.b.data_ptr(),
                        coef=coef.data_ptr() if coef is not None else None, out=out.data_ptr(), ldo=out.shape[1], out_col0=out_col0,
-                       rows=rows, n=N, n_padded=self.n_padded, k_padded=self.k_padded, num_experts=E, act=ACT[act], out_bf16=int(out_bf16))
+                       rows=rows, n=N, n_padded=self.n_padded, k_padded=self.k_padded, num_experts=E, act=ACT[act], out_bf16=int(out_bf16),
+                       out_min=out_clamp[0] if out_clamp else 0.0, out_max=out_clamp[1] if out_clamp else 0.0)
         self._h = C.c_void_p()
         _check(lib().b200nn_linear_create(C.byref(d), C.c_int32(dev.index or 0), C.byref(self._h)))
         self.flops = 2.0 * rows * N * K * E
@@ -125,13 +127,15 @@ def cast_rows(src, dst, cols, mean=None, rstd=None, lo=-3.0e38, hi=3.0e38):
 class PolicyMLP:
     """mu = W4 relu(W3 relu(W2 relu(W1 x + b1) + b2) + b3) + b4 with x = clamp((obs - mean) / sqrt(var + eps), -5, 5)
     (im_network_builder.py:191-230 `actor_mlp` + `mu`, RunningMeanStd; im_player.py:187-202).  `layers` = [(weight [out, in],
-    bias [out]), ...] in torch nn.Linear layout; the last layer has no activation."""
+    bias [out]), ...] in torch nn.Linear layout; the last layer has no activation.  clamp_actions = 1.0 folds
+    ImitatorPlayer's `torch.clamp(action, -1, 1)` (im_player.py:198) into the last layer's epilogue."""
 
-    def __init__(self, layers, num_envs, device, obs_mean=None, obs_var=None, eps=1e-5, clamp_obs=5.0, activation="relu"):
+    def __init__(self, layers, num_envs, device, obs_mean=None, obs_var=None, eps=1e-5, clamp_obs=5.0, activation="relu", clamp_actions=None):
         self.rows, self.device = num_envs, torch.device(device)
         self.in_dim = layers[0][0].shape[1]
         self.out_dim = layers[-1][0].shape[0]
         self.clamp_obs = float(clamp_obs)
+        self.clamp_actions = clamp_actions
         self.mean = obs_mean.to(self.device, torch.float32).contiguous() if obs_mean is not None else None
         self.rstd = (1.0 / torch.sqrt(obs_var.to(self.device, torch.float32) + eps)).contiguous() if obs_var is not None else None
         if (self.mean is None) != (self.rstd is None):
@@ -142,7 +146,8 @@ class PolicyMLP:
         for i, (w, b) in enumerate(layers):
             last = i == len(layers) - 1
             o = self.out if last else padded_bf16(num_envs, w.shape[0], self.device)
-            self.layers.append(Linear(a, w, b, o, num_envs, act=None if last else activation))
+            self.layers.append(Linear(a, w, b, o, num_envs, act=None if last else activation,
+                                      out_clamp=(-clamp_actions, clamp_actions) if (last and clamp_actions) else None))
             a = o
         self.flops = sum(l.flops for l in self.layers)
         self.launches_per_forward = 1 + len(self.layers)
@@ -155,6 +160,13 @@ class PolicyMLP:
         return self.out
 
     __call__ = forward
+
+    def forward_prepared(self):
+        """the layers only: the normalised / clamped bf16 observation row is already in `self.x` (b200env_obs_imitation_rows writes it
+        in the launch that computes the observation)"""
+        for l in self.layers:
+            l.run()
+        return self.out
 
     @classmethod
     def random(cls, num_envs, device, in_dim=734, units=(1024, 1024, 512), out_dim=75, seed=0, out_gain=0.1, **kw):
@@ -203,14 +215,16 @@ class MixedDecoder:
         self.l2 = Linear(self.x1, t(weights[1]), biases[1], self.x2, num_envs, act="elu", coef=self.coef, out_col0=latent_size)
         self.l3 = Linear(self.x2, t(weights[2]), biases[2], self.out, num_envs, act=None, coef=self.coef)
         self.flops = sum(l.flops for l in (self.gate1, self.gate2, self.l1, self.l2, self.l3))
-        self.launches_per_forward = 3 + 2 + 1 + 3
+        self.launches_per_forward = 1 + 1 + 2 + 1 + 3
 
-    def forward(self, z, c):
-        """z float [rows, latent], c float [rows, cond] -> float [rows, out_dim] (static buffer)"""
-        L = self.L
-        for buf in (self.x0, self.x1, self.x2):       # the latent is the first block of every layer's input
-            cast_rows(z, buf, L)
-        _cast_cols(c, self.x0, L, self.cond)
+    def forward(self, z, c=None, c_clamp=None):
+        """z float [rows, latent], c float [rows, >= cond] -> float [rows, out_dim] (static buffer).  c = None: the condition block
+        already sits in the first layer's operand buffer (`set_condition`, or the autoregressive `feed_back`)."""
+        assert z.dtype == torch.float32 and z.stride(-1) == 1
+        _check(lib().b200nn_cast_rows3(C.c_void_p(z.data_ptr()), C.c_int32(z.stride(0)), C.c_void_p(self.x0.data_ptr()), C.c_void_p(self.x1.data_ptr()),
+                                       C.c_void_p(self.x2.data_ptr()), C.c_int32(self.x0.shape[1]), C.c_int32(self.rows), C.c_int32(self.L), _stream()))
+        if c is not None:
+            self.set_condition(c, c_clamp)
         self.gate1.run()
         self.gate2.run()
         _check(lib().b200nn_gate_softmax(C.c_void_p(self.g2.data_ptr()), C.c_int32(self.g2.shape[1]), C.c_int32(self.gw.shape[1]),
@@ -222,6 +236,16 @@ class MixedDecoder:
         return self.out
 
     __call__ = forward
+
+    def set_condition(self, c, clamp=None):
+        """condition block of the first layer's operand <- bf16(clamp(c[:, :cond]))"""
+        lo, hi = (-clamp, clamp) if clamp else (-3.0e38, 3.0e38)
+        _cast_cols(c, self.x0, self.L, self.cond, lo, hi)
+
+    def feed_back(self, clamp=3.0):
+        """autoregression of MVAEPlayer (players/mvae_player.py:201-204): the predicted frame becomes the next condition - one cast
+        launch from the output buffer straight into the operand buffer (kept inside the normalised range)"""
+        self.set_condition(self.out, clamp)
 
     @classmethod
     def random(cls, num_envs, device, frame_size=288, latent_size=32, hidden_size=256, num_experts=6, out_extra=2, seed=0):
@@ -242,9 +266,9 @@ class MixedDecoder:
         return cls(ws, bs, gate, num_envs, device, latent_size)
 
 
-def _cast_cols(src, dst, col0, cols):
-    """dst[:, col0:col0+cols] = bf16(src[:, :cols]) through the strided view (col0 elements into each row of dst)"""
+def _cast_cols(src, dst, col0, cols, lo=-3.0e38, hi=3.0e38):
+    """dst[:rows, col0:col0+cols] = bf16(clamp(src[:, :cols])) through the strided view (col0 elements into each row of dst)"""
     assert src.dtype == torch.float32 and src.stride(-1) == 1
     view_ptr = dst.data_ptr() + col0 * 2
     _check(lib().b200nn_cast_rows(C.c_void_p(src.data_ptr()), C.c_int32(src.stride(0)), C.c_void_p(view_ptr), C.c_int32(dst.shape[1]),
-                                  C.c_int32(src.shape[0]), C.c_int32(cols), None, None, C.c_float(-3.0e38), C.c_float(3.0e38), _stream()))
+                                  C.c_int32(src.shape[0]), C.c_int32(cols), None, None, C.c_float(lo), C.c_float(hi), _stream()))

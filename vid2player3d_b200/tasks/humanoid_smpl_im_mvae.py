@@ -80,6 +80,8 @@ class HumanoidSMPLIMMVAE(BaseTask):
         self._terminate_buf = torch.ones(self.num_envs, device=self.device, dtype=torch.long)
         self._mvae_player = None
         self._controller = None
+        self._obs_operand = None
+        self._fast_targets = not self.cfg_v2p.get('fix_head_orientation') and not self.cfg_v2p.get('add_residual_root')
         self._setup_tensors()
 
     def _build_mujoco_smpl_transform(self):
@@ -222,11 +224,18 @@ class HumanoidSMPLIMMVAE(BaseTask):
     def _set_target_motion_state(self):
         """:600-661 (fix_head_orientation off): targets = FK of the motion generator's pose, velocities by finite difference
         against the previous targets."""
+        out = dict(root_rot=self._target_root_rot, dof_pos=self._target_dof_pos, root_vel=self._target_root_vel,
+                   root_ang_vel=self._target_root_ang_vel, dof_vel=self._target_dof_vel, rb_pos=self._target_rb_pos, rb_rot=self._target_rb_rot)
+        if self._fast_targets:
+            # ONE launch: FK + finite differences against the previous targets (p_rb_rot is a buffer of its own, so no clone), and the
+            # kernel itself stores this call's root position as the new "previous" / target root position
+            native_v2p.smpl_to_sim(self._mvae_player._root_pos, self._mvae_player._joint_rotmat, self._rest_t, self._parents_t, self._s2m_t,
+                                   self.dt, out, prev_root_pos=self._prev_target_root_pos, prev_rb_rot=self._prev_target_rb_rot,
+                                   prev_root_pos_update=self._prev_target_root_pos, target_root_pos_out=self._target_root_pos)
+            return
         root = self._mvae_player._root_pos.clone()
         if self.cfg_v2p.get('add_residual_root') and self._controller is not None:
             root += self._controller._res_root_actions
-        out = dict(root_rot=self._target_root_rot, dof_pos=self._target_dof_pos, root_vel=self._target_root_vel,
-                   root_ang_vel=self._target_root_ang_vel, dof_vel=self._target_dof_vel, rb_pos=self._target_rb_pos, rb_rot=self._target_rb_rot)
         if self.cfg_v2p.get('fix_head_orientation'):    # :605-634: FK of the raw pose, yaw Head/Neck towards the ball (in place)
             self._smpl_to_sim_into(root, self._mvae_player._joint_rotmat, self._tmp)
             native_v2p.fix_head(self._tmp["rb_pos"], self._tmp["rb_rot"], self._ball_pos, self._root_pos, self._mvae_player._joint_rotmat,
@@ -237,11 +246,11 @@ class HumanoidSMPLIMMVAE(BaseTask):
 
     def _compute_observations(self):
         """:862-895 -> compute_humanoid_observations_imitation (:1046-1132) into obs_buf"""
-        rbs = self._rigid_body_state.view(self.num_envs, 26, 13)
-        c = lambda x: x.contiguous()  # noqa: E731
-        self._env.obs_imitation(c(rbs[:, :24, 0:3]), c(rbs[:, :24, 3:7]), self._target_rb_pos, self._target_rb_rot, c(self._dof_pos),
-                                c(self._dof_vel), self._target_dof_pos, c(rbs[:, :24, 7:10]), c(rbs[:, :24, 10:13]),
-                                self._reset_ref_motion_bodies, self._local_root_obs, self._root_height_obs, self.obs_buf)
+        op = self._obs_operand          # (bf16 operand buffer, mean, rstd, clamp) of a b200nn policy, or None
+        self._env.obs_imitation_rows(self.num_envs, self._rigid_body_state, 26, self._dof_state, self._target_rb_pos, self._target_rb_rot,
+                                     self._target_dof_pos, self._reset_ref_motion_bodies, self._local_root_obs, self._root_height_obs, self.obs_buf,
+                                     obs_bf16=op[0] if op else None, mean=op[1] if op else None, rstd=op[2] if op else None,
+                                     clamp=op[3] if op else 5.0)
 
     def post_mvae_step(self):
         self._set_target_motion_state()
@@ -249,8 +258,9 @@ class HumanoidSMPLIMMVAE(BaseTask):
 
     # ------------------------------------------------------------------ step (BaseTask.step :147-165 with :663-797)
     def step(self, actions):
-        self._prev_target_root_pos.copy_(self._target_root_pos)          # _save_prev_target_motion_state (:741-750)
-        self._has_racket_ball_contact_now.zero_()                        # pre_physics_step :689
+        if not self._fast_targets:
+            self._prev_target_root_pos.copy_(self._target_root_pos)      # _save_prev_target_motion_state (:741-750); else inside smpl_to_sim
+        # pre_physics_step :689 zeroes _has_racket_ball_contact_now here; _update_state_from_sim below rewrites every row of it
         actions = actions.to(self.device, dtype=torch.float).contiguous()
         for h in self._envs:          # one launch per asset (dual: even envs, then odd envs)
             h.step(actions)

@@ -158,19 +158,22 @@ class StreamMotionPlayer:
         self._ring = {f: torch.stack(v, 0).reshape(frames * num_envs, *v[0].shape[1:]).contiguous() for f, v in rings.items()}
         for f in self.FIELDS:                                   # the live buffers the env reads (fixed addresses)
             setattr(self, f, rings[f][0].clone())
-        self._t = torch.zeros((), device=device, dtype=torch.long)
+        self._t = torch.zeros(1, device=device, dtype=torch.long)
+        self._done = torch.zeros(1, device=device, dtype=torch.int32)      # scratch of the launch (last-block counter)
         self._off = torch.randint(0, frames, (num_envs,), device=device, generator=gen)
-        self._env = torch.arange(num_envs, device=device)
+        self._gt = dict(clock=self._t, done_counter=self._done, offset=self._off, ring_rotmat=self._ring["_joint_rotmat"], rotmat=self._joint_rotmat,
+                        ring_root_pos=self._ring["_root_pos"], root_pos=self._root_pos, ring_racket_pos=self._ring["_racket_pos"],
+                        racket_pos=self._racket_pos, ring_phase=self._ring["_phase_pred"], phase=self._phase_pred,
+                        ring_swing_type=self._ring["_swing_type"], swing_type=self._swing_type,
+                        ring_swing_type_cycle=self._ring["_swing_type_cycle"], swing_type_cycle=self._swing_type_cycle)
         self._gather()
 
-    def _gather(self):
-        idx = torch.remainder(self._t + self._off, self.K) * self.N + self._env
-        for f in self.FIELDS:
-            torch.index_select(self._ring[f], 0, idx, out=getattr(self, f))
+    def _gather(self, advance=0):
+        """one launch (b200v2p_stream_gather): frame (t + advance + off[e]) % K of every field -> the live buffers; advance moves the clock"""
+        native_v2p.stream_gather(self.N, self.K, advance, self._gt)
 
     def step(self, mvae_actions, res_dof_actions=None):
-        self._t.add_(1)
-        self._gather()
+        self._gather(advance=1)
 
     def reset(self, env_ids):
         self._off[env_ids] = torch.randint(0, self.K, (len(env_ids),), device=self.device)
@@ -182,6 +185,42 @@ class StreamMotionPlayer:
 
     def reset_dual(self, reset_reaction_env_ids, reset_recovery_env_ids):
         self.reset(torch.cat([reset_reaction_env_ids, reset_recovery_env_ids]).sort().values)
+
+
+class DecoderStreamPlayer(StreamMotionPlayer):
+    """StreamMotionPlayer + the MVAE decoder forward of MVAEPlayer.step (vid2player/players/mvae_player.py:184-199) executed every
+    step with parameters of the reference's shapes (random: the trained checkpoints are unreleased, README.md:13): the 32-d latent
+    action and the 288-d condition go through `nn.MixedDecoder` (gate + three mixture-of-experts layers, tcgen05 GEMMs,
+    include/b200nn.h), the predicted frame becomes the next condition like `_update_mvae_state` (:201-204, autoregressive, kept in
+    the normalised range), the two extra outputs are the phase prediction (`_phase_decoded`).  The kinematic TARGETS still come from
+    the resident stream - a random-weight decoder produces noise poses - so this measures the decoder where it runs (inside the
+    step graph, on the live action) without letting it steer the humanoid."""
+
+    def __init__(self, num_envs, device, seed=10, **kw):
+        super().__init__(num_envs, device, seed=seed, **kw)
+        from .. import nn
+        self.decoder = nn.MixedDecoder.random(num_envs, device, seed=seed)
+        g = torch.Generator(device=device).manual_seed(seed + 2)
+        self._init_data = torch.randn(num_envs, self.decoder.cond, device=device, generator=g).clamp_(-3, 3)   # :160 `_init_data`
+        self.decoder.set_condition(self._init_data)
+        # the condition state lives in the decoder's bf16 operand buffer (columns latent .. latent + cond of its first layer input)
+        self._cond_view = self.decoder.x0[:num_envs, self.decoder.L:self.decoder.L + self.decoder.cond]
+        self._init_bf16 = self._init_data.to(torch.bfloat16)
+        self._phase_decoded = torch.zeros(num_envs, device=device)
+
+    def reset(self, env_ids):
+        super().reset(env_ids)
+        self._cond_view[env_ids] = self._init_bf16[env_ids]           # :162-166 condition of a reset env = its initial frame
+
+    def reset_masked(self, mask):
+        super().reset_masked(mask)
+        self._cond_view.copy_(torch.where(mask[:, None], self._init_bf16, self._cond_view))
+
+    def step(self, mvae_actions, res_dof_actions=None):
+        super().step(mvae_actions, res_dof_actions)
+        out = self.decoder(mvae_actions)           # condition = the previous prediction, already in the operand buffer
+        self.decoder.feed_back(clamp=3.0)          # :201-204 the predicted frame is the next condition
+        torch.atan2(out[:, -2], out[:, -1], out=self._phase_decoded)
 
 
 class PhysicsMVAEController:
@@ -271,6 +310,17 @@ class PhysicsMVAEController:
             w_pos=float(weights.get('pos', 1.0 if rtype == 'reach' else 0.0)), w_ball_pos=float(weights.get('ball_pos', 0.0)),
             court_min=self._court_min.tolist(), court_max=self._court_max.tolist(), est_params=self._est_params, dual=0,
             use_history=int(self._use_history))
+        # fused step glue (B200): action handling of pre_physics_step as one launch; trajectory roll + step counters inside the post launch
+        self._fused_pre = bool(self.cfg.get("b200_fused_glue", True)) and not self.cfg_v2p.get('add_residual_root')
+        self._fused_post = bool(self.cfg.get("b200_fused_glue", True))
+        self._mvae_actions = f(N, self._num_mvae_action)
+        self._res_dof_actions = f(N, max(self._num_res_dof_action, 1)) if self._num_res_dof_action else torch.empty(0, device=dev)
+        self._rng_step = torch.zeros(1, device=dev, dtype=torch.long)
+        self._rng_done = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._pre_cfg = dict(n=N, num_actions=self._num_actions, num_latent=self._num_mvae_action, num_res_dof=self._num_res_dof_action,
+                             random_walk_in_recovery=int(bool(self.cfg_v2p.get('random_walk_in_recovery', False))),
+                             vae_action_scale=float(self.cfg_v2p.get('vae_action_scale', 1.0)),
+                             residual_dof_scale=float(self.cfg_v2p.get('residual_dof_scale', 0.1)), seed=int(self.cfg.get("seed", 10)) * 7919 + 13)
 
     # ------------------------------------------------------------------ construction (:118-158)
     def create_sim(self):
@@ -289,18 +339,30 @@ class PhysicsMVAEController:
         if policy is None:
             zeros = torch.zeros(self.num_envs, task.num_actions, device=self.device)
             policy = lambda obs: zeros  # noqa: E731  (zero residual: PD targets = kinematic targets)
+        elif policy == "b200nn":     # the reference's actor shape (734 -> 1024 -> 1024 -> 512 -> 75, ReLU) with random weights, as
+            from .. import nn        # tcgen05 layers; obs clamp and action clamp of run_one_step are folded into its first / last launch
+            policy = nn.PolicyMLP.random(self.num_envs, self.device, in_dim=task.num_obs, out_dim=task.num_actions,
+                                         seed=self.cfg.get("seed", 10), clamp_obs=5.0, clamp_actions=1.0,
+                                         out_gain=float(env.get("low_level_policy_gain", 0.1)))
         self._low_level_policy = policy
+        fused = getattr(policy, "clamp_obs", None) == 5.0 and getattr(policy, "clamp_actions", None) == 1.0 and hasattr(policy, "forward_prepared")
+        if fused:     # the obs kernel writes the policy's normalised / clamped bf16 operand row itself: no cast launch
+            task._obs_operand = (policy.x, policy.mean, policy.rstd, policy.clamp_obs)
 
         def run_one_step():   # ImitatorPlayer.run_one_step (players/im_player.py:187-202)
-            obs = torch.clamp(task.obs_buf, -5.0, 5.0)
             with torch.no_grad():
-                action = self._low_level_policy(obs)
-            task.step(torch.clamp(action, -1.0, 1.0))
+                if fused:
+                    task.step(self._low_level_policy.forward_prepared())
+                else:
+                    action = self._low_level_policy(torch.clamp(task.obs_buf, -5.0, 5.0))
+                    task.step(torch.clamp(action, -1.0, 1.0))
         self._physics_player = SimpleNamespace(task=task, run_one_step=run_one_step)
         player = env.get("motion_player", None)
-        if player == "stream":       # resident target stream: the bench's choice
-            player = StreamMotionPlayer(self.num_envs, self.device, seed=self.cfg.get("seed", 10),
-                                        court_min=self.cfg_v2p.get('court_min', [-5, -16]), court_max=self.cfg_v2p.get('court_max', [5, -10]))
+        pk = dict(seed=self.cfg.get("seed", 10), court_min=self.cfg_v2p.get('court_min', [-5, -16]), court_max=self.cfg_v2p.get('court_max', [5, -10]))
+        if player == "stream":       # resident target stream
+            player = StreamMotionPlayer(self.num_envs, self.device, **pk)
+        elif player == "stream+decoder":   # + the MVAE mixture-of-experts decoder forward every step (the bench's choice)
+            player = DecoderStreamPlayer(self.num_envs, self.device, **pk)
         if player is None:
             player = SyntheticMotionPlayer(self.num_envs, self.device, seed=self.cfg.get("seed", 10),
                                            court_min=self.cfg_v2p.get('court_min', [-5, -16]), court_max=self.cfg_v2p.get('court_max', [5, -10]))
@@ -336,6 +398,16 @@ class PhysicsMVAEController:
         self._reset_graph.replay()
         self._has_init = True
         return True
+
+    def reset_done(self):
+        """B200 addition: `reset(reset_buf.nonzero())` without the id list - the mask of the finished envs is taken from the device
+        flags and the whole reset is one replay of the reset graph: no host synchronisation between steps.  Needs enable_cuda_graph()."""
+        if getattr(self, "_reset_graph", None) is None:
+            self.reset(self.reset_buf.nonzero(as_tuple=False).flatten())
+            return
+        torch.ne(self.reset_buf, 0, out=self._reset_mask)
+        self._reset_graph.replay()
+        self._has_init = True
 
     def _reset_tasks_fast(self, update_state=False):
         """_reset_envs (:173-201) when no humanoid needs a reset - the common per-step case: new balls for the envs whose reaction
@@ -457,6 +529,15 @@ class PhysicsMVAEController:
 
     # ------------------------------------------------------------------ step (:247-269, 362-366, 441-459)
     def pre_physics_step(self, actions):
+        if self._fused_pre:
+            # one launch: latent scaling, random walk in recovery (counter-based normals), residual-dof scaling (b200v2p_pre_step)
+            self._actions = actions
+            native_v2p.pre_step(self._pre_cfg, dict(actions=actions, tar_action=self._tar_action, step_counter=self._rng_step,
+                                                    done_counter=self._rng_done, mvae_actions=self._mvae_actions,
+                                                    res_dof_actions=self._res_dof_actions if self._num_res_dof_action else None))
+            self._mvae_player.step(self._mvae_actions, self._res_dof_actions)
+            self._physics_player.task.post_mvae_step()
+            return
         self._actions = actions.clone()
         na = self._num_mvae_action
         self._mvae_actions = actions[:, :na].clone() * self.cfg_v2p.get('vae_action_scale', 1.0)
@@ -475,13 +556,15 @@ class PhysicsMVAEController:
 
     def physics_step(self):
         self._physics_player.run_one_step()
-        self._ball_traj.copy_(self._ball_traj.roll(-1, dims=1))   # in place: persistent state keeps its address (CUDA-graph safe)
-        self._ball_traj[:, -1] = 0
+        if not self._fused_post:
+            self._ball_traj.copy_(self._ball_traj.roll(-1, dims=1))   # in place: persistent state keeps its address (CUDA-graph safe)
+            self._ball_traj[:, -1] = 0
 
     def post_physics_step(self):
-        self._tar_time += 1
-        self.progress_buf += 1
-        self._compute_post()
+        if not self._fused_post:
+            self._tar_time += 1
+            self.progress_buf += 1
+        self._compute_post(advance=self._fused_post)
         self.extras["terminate"] = self._terminate_buf
         self.extras["sub_rewards"] = self._sub_rewards
         self.extras["sub_rewards_names"] = self._sub_rewards_names
@@ -500,10 +583,15 @@ class PhysicsMVAEController:
                     rew_buf=self.rew_buf, sub_rewards=self._sub_rewards, reset_buf=self.reset_buf, terminate_buf=self._terminate_buf,
                     ball_obs=self._ball_obs)
 
-    def _compute_post(self):
-        """_update_state + _compute_reward + _compute_observations + _compute_reset as ONE launch (:271-436)"""
+    def _compute_post(self, advance=False):
+        """_update_state + _compute_reward + _compute_observations + _compute_reset as ONE launch (:271-436); advance: the launch first
+        rolls the ball-trajectory window and counts tar_time / progress_buf (tail of physics_step + head of post_physics_step)"""
         self._ball_traj = self._ball_traj.contiguous()
-        native_v2p.controller_post(self._post_cfg, self._tensors())
+        cfg = self._post_cfg
+        if advance:
+            cfg = dict(cfg)
+            cfg["advance"] = 1
+        native_v2p.controller_post(cfg, self._tensors())
         t = self._physics_player.task
         self._root_pos, self._root_vel, self._racket_pos, self._racket_vel, self._racket_normal = t._root_pos, t._root_vel, t._racket_pos, t._racket_vel, t._racket_normal
         self._ball_pos, self._ball_vel, self._ball_vspin = t._ball_pos, t._ball_vel, t._ball_vspin
@@ -526,7 +614,7 @@ class PhysicsMVAEController:
             self._graph_actions.copy_(actions)
             self._graph.replay()
             return
-        self.pre_physics_step(actions.to(self.device, dtype=torch.float))
+        self.pre_physics_step(actions.to(self.device, dtype=torch.float).contiguous())
         self.physics_step()
         self.post_physics_step()
 
