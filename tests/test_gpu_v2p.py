@@ -757,3 +757,85 @@ def test_ball_body_contact_option_on_gpu():
     along_on, along_off = (res[1][:, 7:10] * d).sum(1), (res[0][:, 7:10] * d).sum(1)     # velocity along the approach axis (-15 at launch)
     assert (along_off < -13).all()                          # option off: the ball flies through the body
     assert (along_on > -8).mean() >= 0.9                    # option on: stopped / thrown back by the chest (float64 oracle: -4 .. +6)
+
+
+def test_stream_motion_player_gather():
+    """StreamMotionPlayer (the bench's resident target stream): step = gather of frame (t + offset[env]) % K,
+    resets re-draw offsets of the listed / masked envs only; rotation matrices stay proper (b200v2p_stream_gather)"""
+    from vid2player3d_b200.tasks.physics_mvae_controller import StreamMotionPlayer
+    torch.manual_seed(0)
+    p = StreamMotionPlayer(12, DEV, seed=4, frames=6)
+    ring = p._ring["_joint_rotmat"].view(6, 12, 24, 3, 3)
+    env = torch.arange(12, device=DEV)
+    for k in range(8):                                   # runs past the end of the stream: wraps
+        t0, off = int(p._t), p._off.clone()
+        p.step(torch.zeros(12, 32, device=DEV))
+        assert torch.equal(p._joint_rotmat, ring[(t0 + 1 + off) % 6, env])
+        assert torch.equal(p._root_pos, p._ring["_root_pos"].view(6, 12, 3)[(t0 + 1 + off) % 6, env])
+    off = p._off.clone()
+    ids = torch.tensor([2, 9], device=DEV)
+    p.reset(ids)
+    keep = torch.ones(12, dtype=torch.bool, device=DEV)
+    keep[ids] = False
+    assert torch.equal(p._off[keep], off[keep]) and bool(((p._off >= 0) & (p._off < 6)).all())
+    off = p._off.clone()
+    mask = torch.zeros(12, dtype=torch.bool, device=DEV)
+    mask[[0, 5]] = True
+    p.reset_masked(mask)
+    assert torch.equal(p._off[~mask], off[~mask])
+    assert torch.equal(p._joint_rotmat, ring[(int(p._t) + p._off) % 6, env])
+    det = torch.linalg.det(p._joint_rotmat.reshape(-1, 3, 3))
+    assert float((det - 1).abs().max()) < 1e-4
+
+
+
+
+def test_pre_step_kernel():
+    """b200v2p_pre_step = the action handling of PhysicsMVAEController.pre_physics_step (:247-262): scaling is exact; the envs in
+    recovery get fresh N(0,1) draws clamped to +-5 (statistics), different on every launch (device step counter)"""
+    from vid2player3d_b200 import native_v2p
+    N = 4096
+    g = torch.Generator(device=DEV).manual_seed(2)
+    actions = torch.randn(N, 35, device=DEV, generator=g)
+    tar = (torch.arange(N, device=DEV) % 2).to(torch.long)         # even envs: recovery (tar_action 0)
+    mv, rd = torch.zeros(N, 32, device=DEV), torch.zeros(N, 3, device=DEV)
+    cnt, done = torch.zeros(1, device=DEV, dtype=torch.long), torch.zeros(1, device=DEV, dtype=torch.int32)
+    cfg = dict(n=N, num_actions=35, num_latent=32, num_res_dof=3, random_walk_in_recovery=1, vae_action_scale=1.5, residual_dof_scale=0.4, seed=77)
+    t = dict(actions=actions, tar_action=tar, step_counter=cnt, done_counter=done, mvae_actions=mv, res_dof_actions=rd)
+    native_v2p.pre_step(cfg, t)
+    first = mv.clone()
+    assert int(cnt) == 1 and int(done) == 0
+    assert torch.equal(mv[1::2], actions[1::2, :32] * 1.5) and torch.equal(rd, actions[:, 32:35] * 0.4)
+    r = mv[0::2]
+    assert abs(float(r.mean())) < 0.02 and abs(float(r.std()) - 1.0) < 0.02 and float(r.abs().max()) <= 5.0
+    assert abs(float((r > 1.0).float().mean()) - 0.1587) < 0.01          # normal tail, not uniform
+    native_v2p.pre_step(cfg, t)
+    assert int(cnt) == 2 and not torch.equal(mv[0::2], first[0::2]) and torch.equal(mv[1::2], first[1::2])
+    cfg["random_walk_in_recovery"] = 0
+    native_v2p.pre_step(cfg, t)
+    assert torch.equal(mv, actions[:, :32] * 1.5)
+
+
+def test_obs_imitation_rows_matches_gathered_inputs():
+    """b200env_obs_imitation_rows (state rows in place, + the bf16 operand row) == b200env_obs_imitation on contiguous gathers"""
+    from vid2player3d_b200.tasks import PhysicsMVAEController
+    torch.manual_seed(3)
+    env = PhysicsMVAEController(v2p_cfg(96), SIM_PARAMS, 1, "cuda", 0, True)
+    env.reset()
+    for _ in range(3):
+        env.step(torch.clamp(torch.randn(96, env.num_actions, device=DEV), -5, 5))
+    task = env._physics_player.task
+    rbs = task._rigid_body_state.view(96, 26, 13)
+    c = lambda x: x.contiguous()  # noqa: E731
+    ref = torch.zeros_like(task.obs_buf)
+    task._env.obs_imitation(c(rbs[:, :24, 0:3]), c(rbs[:, :24, 3:7]), task._target_rb_pos, task._target_rb_rot, c(task._dof_pos), c(task._dof_vel),
+                            task._target_dof_pos, c(rbs[:, :24, 7:10]), c(rbs[:, :24, 10:13]), task._reset_ref_motion_bodies, True, True, ref)
+    out = torch.zeros_like(ref)
+    op = torch.zeros(128, 768, device=DEV, dtype=torch.bfloat16)
+    mean, rstd = torch.randn(734, device=DEV) * 0.1, torch.rand(734, device=DEV) + 0.5
+    task._env.obs_imitation_rows(96, task._rigid_body_state, 26, task._dof_state, task._target_rb_pos, task._target_rb_rot, task._target_dof_pos,
+                                 task._reset_ref_motion_bodies, True, True, out, obs_bf16=op, mean=mean, rstd=rstd, clamp=5.0)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    want = torch.clamp((ref - mean) * rstd, -5, 5).to(torch.bfloat16)
+    assert torch.equal(op[:96, :734], want) and float(op[96:].abs().max()) == 0 and float(op[:, 734:].abs().max()) == 0

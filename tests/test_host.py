@@ -251,35 +251,6 @@ def test_quaternion_to_angle_axis_matches_scipy():
     assert np.all(got[0] == 0)
 
 
-def test_stream_motion_player_logic_on_cpu():
-    """StreamMotionPlayer (the bench's resident target stream): step = gather of frame (t + offset[env]) % K,
-    resets re-draw offsets of the listed / masked envs only; rotation matrices stay proper"""
-    from vid2player3d_b200.tasks.physics_mvae_controller import StreamMotionPlayer
-    torch.manual_seed(0)
-    p = StreamMotionPlayer(12, "cpu", seed=4, frames=6)
-    ring = p._ring["_joint_rotmat"].view(6, 12, 24, 3, 3)
-    env = torch.arange(12)
-    for k in range(8):                                   # runs past the end of the stream: wraps
-        t0, off = int(p._t), p._off.clone()
-        p.step(torch.zeros(12, 32))
-        assert torch.equal(p._joint_rotmat, ring[(t0 + 1 + off) % 6, env])
-        assert torch.equal(p._root_pos, p._ring["_root_pos"].view(6, 12, 3)[(t0 + 1 + off) % 6, env])
-    off = p._off.clone()
-    ids = torch.tensor([2, 9])
-    p.reset(ids)
-    keep = torch.ones(12, dtype=torch.bool)
-    keep[ids] = False
-    assert torch.equal(p._off[keep], off[keep]) and bool(((p._off >= 0) & (p._off < 6)).all())
-    off = p._off.clone()
-    mask = torch.zeros(12, dtype=torch.bool)
-    mask[[0, 5]] = True
-    p.reset_masked(mask)
-    assert torch.equal(p._off[~mask], off[~mask])
-    assert torch.equal(p._joint_rotmat, ring[(int(p._t) + p._off) % 6, env])
-    det = torch.linalg.det(p._joint_rotmat.reshape(-1, 3, 3))
-    assert float((det - 1).abs().max()) < 1e-4
-
-
 def test_nn_library_exports_and_layout(tmp_path):
     """libb200nn.so (include/b200nn.h): loads without a GPU, exports every declared symbol, descriptor layout == ctypes mirror,
     and refuses to build a layer without a CUDA device (no fallback)."""
