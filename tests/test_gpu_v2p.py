@@ -836,6 +836,7 @@ def test_obs_imitation_rows_matches_gathered_inputs():
     task._env.obs_imitation_rows(96, task._rigid_body_state, 26, task._dof_state, task._target_rb_pos, task._target_rb_rot, task._target_dof_pos,
                                  task._reset_ref_motion_bodies, True, True, out, obs_bf16=op, mean=mean, rstd=rstd, clamp=5.0)
     torch.cuda.synchronize()
-    assert torch.equal(out, ref)
+    d = (out - ref).abs()
+    assert torch.equal(out, ref), (float(d.max()), d.nonzero()[:8].tolist(), out[d > 0][:4].tolist(), ref[d > 0][:4].tolist())
     want = torch.clamp((ref - mean) * rstd, -5, 5).to(torch.bfloat16)
     assert torch.equal(op[:96, :734], want) and float(op[96:].abs().max()) == 0 and float(op[:, 734:].abs().max()) == 0

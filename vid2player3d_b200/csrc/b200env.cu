@@ -1644,7 +1644,7 @@ obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restri
       put(off + 9, cosf(dh)); put(off + 10, sinf(dh));
     }
     off += 11;
-    for (int k = lane; k < nd; k += 32) put(off + k, target_dof_pos[e * st.d_row + (int64_t)k * st.d_elem] - dof_pos[e * st.d_row + (int64_t)k * st.d_elem]);
+    for (int k = lane; k < nd; k += 32) put(off + k, target_dof_pos[e * nd + k] - dof_pos[e * st.d_row + (int64_t)k * st.d_elem]);
     off += nd;
   }
   if (act) {
