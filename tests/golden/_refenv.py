@@ -15,7 +15,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 
 # absent third-party packages of the reference: any `import pkg.sub.mod` resolves to a MagicMock
 MOCK_TOP = {"imageio", "gym", "mujoco_py", "lxml", "stl", "smpl_visualizer", "pyvista", "vtk", "vtkmodules", "cv2",
-            "tensorboardX", "rl_games", "scenepic", "horovod", "wandb"}
+            "tensorboardX", "rl_games", "scenepic", "horovod", "wandb", "glfw", "OpenGL", "mujoco", "chumpy", "smplx", "pyrender", "trimesh", "open3d", "ffmpeg", "mediapy"}
 
 
 class _MockFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
