@@ -100,7 +100,7 @@ print(json.dumps({"touched": sorted(t.touched), "steps": t.d["steps"], "obs_max"
     missing = [n for n in out["touched"] if n not in provided]
     assert not missing, f"the reference's callers touch task attributes the B200 task does not define: {missing}"
     assert out["obs_max"] <= 5.0 and out["n_agents"] == 1 and out["info_keys"] == ["action_space", "observation_space"]
-    assert out["steps"][0] == ["reset", None] and out["steps"][-1] == ["reset", 2] and out["steps"][1] == [6, 75]
+    assert out["steps"][0] == ["reset", None] and out["steps"][-1] == ["reset", 2] and out["steps"].count([6, 75]) == 3
 
 
 @needs_ref
