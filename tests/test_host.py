@@ -286,3 +286,57 @@ def test_v2p_glue_struct_layouts(tmp_path):
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert got == [C.sizeof(abi.V2PPreStep), abi.V2PPreStep.actions.offset, C.sizeof(abi.V2PStream), abi.V2PStream.ring_phase.offset,
                    abi.V2PCtrl.advance.offset]
+
+
+def test_motion_lib_formats_directory_and_merge(tmp_path):
+    """motion_file handling of HumanoidSMPLIM._load_motion (reference humanoid_smpl_im.py:420-440): .npz / .b200ml files, a directory
+    of them with motion_file_range, merge = concatenation with rebuilt frame offsets; unknown formats fail loudly"""
+    from vid2player3d_b200 import model_compiler, motion_lib as ML
+    model = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    libs = [ML.synthetic(model, num_motions=m, num_frames=20, seed=s, ragged=True) for m, s in ((2, 1), (3, 2), (1, 3))]
+    d = tmp_path / "libs"
+    d.mkdir()
+    for i, l in enumerate(libs):
+        l.save_flat(str(d / f"part{i}.b200ml"))
+    libs[0].save(str(tmp_path / "one.npz"))
+    a = ML.FlatMotionLib.load_any(str(tmp_path / "one.npz"))
+    assert np.array_equal(a.gts, libs[0].gts)
+    merged = ML.FlatMotionLib.load_any(str(d))
+    assert merged.num_motions() == 6 and merged.gts.shape[0] == sum(l.gts.shape[0] for l in libs)
+    assert np.array_equal(merged.length_starts, np.concatenate([[0], np.cumsum(merged.num_frames)[:-1]]))
+    assert np.array_equal(merged.gts[libs[0].gts.shape[0]:libs[0].gts.shape[0] + libs[1].gts.shape[0]], libs[1].gts)
+    part = ML.FlatMotionLib.load_any(str(d), motion_file_range=[1, 3])
+    assert part.num_motions() == 4 and np.array_equal(part.motion_lengths, np.concatenate([libs[1].motion_lengths, libs[2].motion_lengths]))
+    bad = tmp_path / "x.bin"
+    bad.write_bytes(b"not a motion library")
+    with pytest.raises(ValueError, match="unknown motion library format"):
+        ML.FlatMotionLib.load_any(str(bad))
+    with pytest.raises(FileNotFoundError):
+        ML.FlatMotionLib.load_any(str(tmp_path / "missing.pth"))
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(FileNotFoundError):
+        ML.FlatMotionLib.load_any(str(empty))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/embodied_pose"), reason="reference checkout not present (GPU box)")
+def test_from_reference_motion_lib_pickle(tmp_path):
+    """a reference `torch.save(motion_lib)` pickle (what every reference yaml's motion_file names) loads through
+    FlatMotionLib.load_any / from_reference; run in a subprocess with the reference importable, like the reference's own torch.load"""
+    code = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%(root)r, "tests", "golden")); sys.path.insert(0, %(root)r)
+import numpy as np, torch
+import make_golden as G                     # builds a reference MotionLib object from a synthetic flat library
+from vid2player3d_b200.motion_lib import FlatMotionLib
+model, flat, key = G.small_lib()
+ml = G.make_ref_motion_lib(flat, key, model["dof_body_ids"])
+path = os.path.join(%(tmp)r, "lib.pth")
+torch.save(ml, path)
+back = FlatMotionLib.load_any(path)
+for k in FlatMotionLib.FIELDS:
+    assert np.array_equal(np.asarray(getattr(back, k)), np.asarray(getattr(flat, k))), k
+print("ok")
+''' % {"root": ROOT, "tmp": str(tmp_path)}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-1500:] + r.stderr[-2500:]

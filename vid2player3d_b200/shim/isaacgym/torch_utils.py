@@ -4,7 +4,7 @@ Convention: quaternions are xyzw, Hamilton product.  These are the published
 definitions of Isaac Gym's python/isaacgym/torch_utils.py (un-vendored dependency of the
 reference).  They are cross-checked against the reference's own
 poselib/poselib/core/rotation3d.py (quat_mul :15, quat_conjugate :60,
-quat_from_angle_axis :125, quat_rotate :208) in tests/test_shim.py.
+quat_from_angle_axis :125, quat_rotate :208) in tests/test_host.py::test_shim_quaternion_helpers_match_poselib_conventions.
 """
 import numpy as np
 import torch
