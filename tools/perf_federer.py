@@ -1,47 +1,55 @@
-"""Phase timing of the vid2player federer high-level step (not the bench contract)."""
-import os, sys, time
+"""Where the config-3 step goes, from graph replays (warm, in-graph timing - ncu launch lists are cold and serialised):
+python tools/perf_federer.py [envs]"""
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT)
 import torch
-from helpers import SIM_PARAMS, v2p_cfg
-from vid2player3d_b200.tasks import PhysicsMVAEController
+import bench
+
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-torch.manual_seed(10)
-env = PhysicsMVAEController(v2p_cfg(N), SIM_PARAMS, 1, "cuda", 0, True)
-env.reset()
-acts = [torch.clamp(torch.randn(N, 35, device=env.device), -5, 5) for _ in range(8)]
-empty = torch.zeros(0, dtype=torch.long, device=env.device)
-def timed(fn, n=50):
-    torch.cuda.synchronize(); t0 = time.perf_counter()
+env = bench.federer_env(N, 0)
+dev = env.device
+task = env._physics_player.task
+acts = [torch.clamp(torch.randn(N, env.num_actions, device=dev), -5, 5) for _ in range(8)]
+for i in range(4):
+    env.step(acts[i % 8]); env.reset(env.reset_buf.nonzero(as_tuple=False).flatten())
+env.enable_cuda_graph()
+
+
+def timed(fn, reps=200):
+    for _ in range(10):
+        fn()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(n): fn(i)
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n, (time.perf_counter() - t0) / n * 1e3
-for i in range(10): env.step(acts[i % 8]); env.reset(empty)
-task = env._physics_player.task
-print("phase: gpu-ms (event) / wall-ms")
-print("pre_physics_step  ", timed(lambda i: env.pre_physics_step(acts[i % 8])))
-print("  mvae_player.step", timed(lambda i: env._mvae_player.step(acts[i % 8][:, :32], acts[i % 8][:, 32:35])))
-print("  post_mvae_step  ", timed(lambda i: task.post_mvae_step()))
-print("physics_step      ", timed(lambda i: env.physics_step()))
-print("  task.step       ", timed(lambda i: task.step(torch.zeros(N, 75, device=env.device))))
-print("  native step only", timed(lambda i: task._env.step(torch.zeros(N, 75, device=env.device))))
-print("post_physics_step ", timed(lambda i: env.post_physics_step()))
-print("reset fast path   ", timed(lambda i: env.reset(empty)))
-print("nonzero sync      ", timed(lambda i: env.reset_buf.nonzero().flatten()))
-print("full step+reset   ", timed(lambda i: (env.step(acts[i % 8]), env.reset(env.reset_buf.nonzero().flatten()))))
-env.enable_cuda_graph()
-print("graph step only   ", timed(lambda i: env.step(acts[i % 8])))
-print("graph step+reset  ", timed(lambda i: (env.step(acts[i % 8]), env.reset(env.reset_buf.nonzero().flatten()))))
-print("resets pending:", int(env.reset_buf.sum()), "reaction", int(env._reset_reaction_buf.sum()))
-ids = torch.tensor([3, 77, 500, 4000, 8000], device=env.device)
-player = env._mvae_player
-print("--- reset pieces with 5 humanoid ids")
-print("player.reset      ", timed(lambda i: player.reset(ids)))
-print("task._reset_actors", timed(lambda i: task._reset_actors(ids)))
-print("  smpl_to_sim all ", timed(lambda i: task._smpl_to_sim_into(player._root_pos.contiguous(), player._joint_rotmat, task._tmp)))
-print("tasks_fast(update)", timed(lambda i: env._reset_tasks_fast(update_state=True)))
-print("  update_state    ", timed(lambda i: task._update_state_from_sim()))
-print("_reset_envs(ids)  ", timed(lambda i: env._reset_envs(ids)))
-print("nonzero           ", timed(lambda i: env.reset_buf.nonzero().flatten()))
+    for i in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+def graph_of(fn):
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g.replay
+
+
+print(f"step + reset_done      : {timed(lambda: (env.step(acts[0]), env.reset_done())):.1f} us")
+print(f"step graph alone       : {timed(lambda: env.step(acts[0])):.1f} us")
+print(f"reset graph alone      : {timed(env.reset_done):.1f} us")
+a75 = torch.zeros(N, task.num_actions, device=dev)
+print(f"physics (3 launches)   : {timed(graph_of(lambda: task._env.step(a75))):.1f} us")
+print(f"policy 4 layers        : {timed(graph_of(env._low_level_policy.forward_prepared)):.1f} us")
+p = env._mvae_player
+print(f"decoder + feedback     : {timed(graph_of(lambda: (p.decoder(env._mvae_actions), p.decoder.feed_back(3.0)))):.1f} us")
+print(f"stream gather          : {timed(graph_of(lambda: p._gather(1))):.1f} us")
+print(f"targets FK + obs       : {timed(graph_of(task.post_mvae_step)):.1f} us")
+print(f"update_state           : {timed(graph_of(task._update_state_from_sim)):.1f} us")
+print(f"controller post        : {timed(graph_of(lambda: env._compute_post(advance=True))):.1f} us")
+print(f"empty graph replay     : {timed(graph_of(lambda: env._rng_done.zero_())):.1f} us")

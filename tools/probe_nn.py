@@ -18,9 +18,17 @@ for (M, K, N) in ((8192, 64, 64), (8192, 512, 75), (8192, 1024, 1024), (128, 64,
     nn.lib().b200nn_probe_read(buf)
     t = list(buf)[:9]
     nc = (nn.padded_rows(M) // 128) * ((N + 127) // 128)
-    cb = (C.c_ulonglong * (2 * nc))()
+    cb = (C.c_ulonglong * (8 * nc))()
     nn.lib().b200nn_probe_read_ctas(cb, C.c_int(nc))
-    st, en = list(cb)[0::2], list(cb)[1::2]
+    v = list(cb)
+    st = v[0::8]
     t00 = min(st)
-    print(f"   {nc} CTAs: starts span {(max(st) - t00) / 1e3:.2f} us, epilogue ends: min {(min(en) - t00) / 1e3:.2f} median {(sorted(en)[nc // 2] - t00) / 1e3:.2f} max {(max(en) - t00) / 1e3:.2f} us")
+    ends = [[v[8 * c + k] for c in range(nc)] for k in range(1, 6)]
+    print(f"   {nc} CTAs: starts span {(max(st) - t00) / 1e3:.2f} us; epilogue warp ends (max over CTAs) " +
+          " ".join(f"{(max(e) - t00) / 1e3:.2f}" for e in ends[:4]) + f" us; dealloc done max {(max(ends[4]) - t00) / 1e3:.2f} us")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(20): lin.run()
+    e1.record(); torch.cuda.synchronize()
+    print(f"   back-to-back launches: {e0.elapsed_time(e1) / 20 * 1e3:.2f} us per launch")
     print(f"M={M} K={K} N={N}: " + ", ".join(f"{n} +{(x - t[0]) / 1e3:.2f}us" for n, x in zip(names, t)))

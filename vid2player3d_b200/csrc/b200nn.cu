@@ -82,6 +82,9 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -145,9 +148,9 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 #endif
 #if B200NN_PROBE
 __device__ unsigned long long g_probe[16];
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory"); return t; }
 #define PROBE(i) do { if (blockIdx.x == 0 && blockIdx.y == 0) g_probe[i] = gtime(); } while (0)
-__device__ unsigned long long g_cta[4096][2];
+__device__ unsigned long long g_cta[4096][8];
 #define PROBE_CTA(k) do { const int c_ = blockIdx.y * gridDim.x + blockIdx.x; if (c_ < 4096) g_cta[c_][k] = gtime(); } while (0)
 #else
 #define PROBE_CTA(k) do { } while (0)
@@ -195,7 +198,8 @@ __device__ __forceinline__ void store16(const LinearParams& p, int row, int col,
 
 template <int E, int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const LinearParams p) {
+linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
+              const LinearParams p) {
   constexpr int ACC = E * BN;                          // accumulator columns in TMEM
   constexpr int B_STAGE_BYTES = ACC * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
@@ -219,6 +223,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -292,6 +297,12 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (threadIdx.x == 64) PROBE(6);
     tcgen05_fence_after();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    // bf16 outputs leave through shared memory and ONE TMA store per warp and 64-column half: the warp's 32 rows x 128 bytes are
+    // staged in the (now idle) pipeline stage 0 in the 128-byte swizzle the tensor map expects - thread = row, 16-byte chunk j of
+    // the row at ((j ^ (row & 7)) << 4): conflict-free per quarter warp - and written to global memory as whole 128-byte lines
+    // (the direct form wrote 16-byte pieces of 32 different lines per instruction: ~5 us per tile against ~1.5 us now).
+    uint8_t* stage_out = smem + (size_t)q * 4096;           // + half * 16384
+    const int rsw = lane & 7;
     if constexpr (E == 1) {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 64) {
@@ -300,13 +311,39 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tmem_ld32_issue(trow + c0, r);
         tmem_ld32_issue(trow + c0 + 32, r + 32);
         tmem_ld_wait();
+        if (p.out_bf16) {
+          uint8_t* dst = stage_out + (c0 >> 6) * 16384 + lane * 128;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          float y[16];
+          for (int j = 0; j < 8; j++) {
+            uint32_t w[4];
 #pragma unroll
-          for (int i = 0; i < 16; i++) y[i] = finish(__uint_as_float(r[16 * j + i]) + sbias[c0 + 16 * j + i], p);
-          if (row < p.rows) store16(p, row, n0 + c0 + 16 * j, y);
+            for (int i = 0; i < 4; i++) {
+              const float a = finish(__uint_as_float(r[8 * j + 2 * i]) + sbias[c0 + 8 * j + 2 * i], p);
+              const float b = finish(__uint_as_float(r[8 * j + 2 * i + 1]) + sbias[c0 + 8 * j + 2 * i + 1], p);
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst + ((j ^ rsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            float y[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) y[i] = finish(__uint_as_float(r[16 * j + i]) + sbias[c0 + 16 * j + i], p);
+            if (row < p.rows) store16(p, row, n0 + c0 + 16 * j, y);
+          }
         }
+      }
+      if (p.out_bf16) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && m0 + q * 32 < p.rows) {
+          for (int c0 = 0; c0 < BN && n0 + c0 < p.n; c0 += 64) tma_store_2d(&tmO, stage_out + (c0 >> 6) * 16384, p.out_col0 + n0 + c0, m0 + q * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
       }
     } else {
 #pragma unroll 1
@@ -325,10 +362,35 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int i = 0; i < 16; i++) y[i] = fmaf(coef[e], __uint_as_float(r[e][i]) + sbias[e * BN + c0 + i], y[i]);
 #pragma unroll
         for (int i = 0; i < 16; i++) y[i] = finish(y[i], p);
-        if (row < p.rows) store16(p, row, n0 + c0, y);
+        if (p.out_bf16) {
+          uint8_t* dst = stage_out + lane * 128;
+#pragma unroll
+          for (int jj = 0; jj < 2; jj++) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(y[8 * jj + 2 * i], y[8 * jj + 2 * i + 1]);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst + ((((c0 >> 3) + jj) ^ rsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else if (row < p.rows) {
+          store16(p, row, n0 + c0, y);
+        }
+      }
+      if (p.out_bf16) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && m0 + q * 32 < p.rows) {
+          tma_store_2d(&tmO, stage_out, p.out_col0 + n0, m0 + q * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
       }
     }
-    if (threadIdx.x == 64) { PROBE(7); PROBE_CTA(1); }
+    if (threadIdx.x == 64) PROBE(7);
+    if (lane == 0) PROBE_CTA(1 + q);
     tcgen05_fence_before();
   }
   __syncthreads();
@@ -336,6 +398,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (lane == 0) PROBE_CTA(5);
   }
 }
 
@@ -406,7 +469,7 @@ template <int E, int BN, int STAGES> constexpr int smem_bytes() { return STAGES 
 
 struct b200nn_linear {
   b200nn_linear_desc_t d;
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmO;
   LinearParams p;
   int device, bn, pdl;
   dim3 grid;
@@ -428,7 +491,7 @@ template <int E, int BN, int STAGES> static int launch(const b200nn_linear* h, c
   attr[0].val.programmaticStreamSerializationAllowed = h->pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CUDA_OK(cudaLaunchKernelEx(&cfg, linear_kernel<E, BN, STAGES>, h->tmA, h->tmW, h->p));
+  CUDA_OK(cudaLaunchKernelEx(&cfg, linear_kernel<E, BN, STAGES>, h->tmA, h->tmW, h->tmO, h->p));
   return 0;
 }
 
@@ -478,6 +541,16 @@ int b200nn_linear_create(const b200nn_linear_desc_t* d, int32_t device, b200nn_l
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete h; snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled(W) failed: %d", (int)r); return -3; }
   }
+  if (d->out_bf16) {   // output tile store: 64 columns x 32 rows per TMA store, clipped at the real extent of the block that is written
+    cuuint64_t dims[2] = {(cuuint64_t)(d->out_col0 + d->n), (cuuint64_t)d->rows};
+    cuuint64_t strides[1] = {(cuuint64_t)d->ldo * 2};
+    cuuint32_t box[2] = {64, 32}, es[2] = {1, 1};
+    CUresult r = enc(&h->tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete h; snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled(out) failed: %d", (int)r); return -3; }
+  } else {
+    h->tmO = h->tmA;   // unused by the float-output epilogue
+  }
   h->p = LinearParams{d->bias, d->coef, d->out, d->ldo, d->out_col0, d->rows, d->n, d->n_padded, d->k_padded, d->act, d->out_bf16, d->out_min, d->out_max};
   h->grid = dim3(rows_padded / BLOCK_M, (d->n + bn - 1) / bn, 1);
   *out = h;
@@ -504,7 +577,7 @@ int b200nn_linear_run(b200nn_linear_handle h, void* stream) {
 }
 
 #if B200NN_PROBE
-int b200nn_probe_read_ctas(unsigned long long* out, int n) { return cudaMemcpyFromSymbol(out, g_cta, sizeof(unsigned long long) * 2 * n) == cudaSuccess ? 0 : -1; }
+int b200nn_probe_read_ctas(unsigned long long* out, int n) { return cudaMemcpyFromSymbol(out, g_cta, sizeof(unsigned long long) * 8 * n) == cudaSuccess ? 0 : -1; }
 int b200nn_probe_read(unsigned long long* out16) { return cudaMemcpyFromSymbol(out16, g_probe, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -1; }
 #endif
 
