@@ -467,6 +467,14 @@ template <int E, int BN, int STAGES> constexpr int smem_bytes() { return STAGES 
 
 }  // namespace
 
+// A/B switch (B200NN_CARVEOUT=1): every kernel of this library asks for the same L1 / shared-memory split (all shared), so that
+// neighbouring launches never re-partition the SMs' L1.  Measured on B200 (profiles/r2j_nn.md): no gain for the policy (91.6 vs 91.8 us),
+// a loss for the decoder chain (118.9 vs 110.7 us: the small cast / gate kernels like their L1) - off by default.
+template <class K> static void prefer_max_shared(K kernel) {
+  static const bool on = getenv("B200NN_CARVEOUT") && getenv("B200NN_CARVEOUT")[0] == '1';
+  if (on) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 struct b200nn_linear {
   b200nn_linear_desc_t d;
   CUtensorMap tmA, tmW, tmO;
@@ -479,6 +487,7 @@ template <int E, int BN, int STAGES> static int launch(const b200nn_linear* h, c
   static bool attr_set[16] = {};
   if (!attr_set[h->device & 15]) {
     CUDA_OK(cudaFuncSetAttribute(linear_kernel<E, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<E, BN, STAGES>()));
+    prefer_max_shared(linear_kernel<E, BN, STAGES>);
     attr_set[h->device & 15] = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -589,6 +598,8 @@ static int cast_launch(const float* src, int32_t ld_src, void* dst, void* dst2, 
   const dim3 block(tx, 256 / tx, 1);
   const int want = (rows + (int)block.y - 1) / (int)block.y;
   const int blocks = want < 148 * 16 ? want : 148 * 16;
+  static bool once = (prefer_max_shared(cast_rows_kernel), true);
+  (void)once;
   cast_rows_kernel<<<blocks, block, 0, (cudaStream_t)stream>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<__nv_bfloat16*>(dst2),
                                                              reinterpret_cast<__nv_bfloat16*>(dst3), ld_dst, rows, cols, mean, rstd, lo, hi);
   CUDA_OK(cudaGetLastError());
@@ -606,6 +617,8 @@ int b200nn_cast_rows3(const float* src, int32_t ld_src, void* dst, void* dst2, v
 
 int b200nn_gate_softmax(const void* h, int32_t ldh, int32_t k, const float* w, const float* b, int32_t E, float* coef, int32_t rows, void* stream) {
   if (!h || !w || !b || !coef || E < 1 || E > 8 || rows < 1 || k < 1 || k > ldh) return fail(-2, "b200nn_gate_softmax: bad argument");
+  static bool once = (prefer_max_shared(gate_softmax_kernel), true);
+  (void)once;
   gate_softmax_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(h), ldh, k, w, b, E, coef, rows);
   CUDA_OK(cudaGetLastError());
   return 0;
