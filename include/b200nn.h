@@ -14,7 +14,7 @@
  * One `linear` object = one launch: out[:, col0 : col0 + N] = act( sum_e coef[:, e] * (A W_e^T + bias_e) ).
  * All pointers are DEVICE pointers; operands are bf16 (K contiguous), accumulation fp32, bias / coef fp32.
  * Shapes are padded by the caller (the Python binding does it): rows of A / out to a multiple of 128, K and the leading
- * dimensions to a multiple of 64 elements with zero padding, rows of W_e to a multiple of the output tile (128, or 64 when E > 1).
+ * dimensions to a multiple of 64 elements with zero padding, rows of W_e to a multiple of the output tile (128, or 32 when E > 1).
  * Functions return 0 on success; b200nn_last_error() describes the last failure.  No allocation and no host sync in `run`.
  */
 #ifndef B200NN_H
@@ -42,7 +42,7 @@ typedef struct b200nn_linear_desc {
   int32_t out_col0;   /* first output column (the MVAE layers write behind the latent: col0 = 32); bf16 output: multiple of 8 */
   int32_t rows;       /* M: envs */
   int32_t n;          /* N: output features actually stored (<= n_padded) */
-  int32_t n_padded;   /* rows of W per expert, multiple of the tile (128, or 64 when num_experts > 1) */
+  int32_t n_padded;   /* rows of W per expert, multiple of the tile (128, or 32 when num_experts > 1) */
   int32_t k_padded;   /* K: multiple of 64; A[:, K:k_padded] and W[:, K:k_padded] must be zero */
   int32_t num_experts;/* 1 (plain linear layer) or 2..6 (mixture of experts) */
   int32_t act;        /* B200NN_ACT_* */

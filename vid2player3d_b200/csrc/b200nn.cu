@@ -41,6 +41,15 @@ static int fail(int code, const char* msg) {
 // ------------------------------------------------------------------------------------------ device helpers (PTX)
 namespace {
 
+// mixture-of-experts layers: output tile = MOE_BN columns x E experts.  32 (x 6 experts = 192 accumulator columns, 40 KB per stage,
+// two CTAs per SM so that one tile's blend epilogue runs under the other's main loop) measured against 64 (384 columns, 64 KB per
+// stage, one CTA per SM) in profiles/r2j_nn.md; -DMOE_BN=64 -DMOE_STAGES=3 rebuilds the wide form.
+#ifndef MOE_BN
+#define MOE_BN 32
+#endif
+#ifndef MOE_STAGES
+#define MOE_STAGES 2
+#endif
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                        // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
@@ -192,12 +201,20 @@ __device__ __forceinline__ void store16(const LinearParams& p, int row, int col,
     }
   } else {
     float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + p.out_col0 + col;
-    for (int i = 0; i < 16 && col + i < p.n; i++) o[i] = y[i];
+    if (col + 16 <= p.n && ((uintptr_t)o & 15) == 0) {          // widest store the row's alignment allows
+#pragma unroll
+      for (int i = 0; i < 4; i++) reinterpret_cast<float4*>(o)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    } else if (col + 16 <= p.n && ((uintptr_t)o & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) reinterpret_cast<float2*>(o)[i] = make_float2(y[2 * i], y[2 * i + 1]);
+    } else {
+      for (int i = 0; i < 16 && col + i < p.n; i++) o[i] = y[i];
+    }
   }
 }
 
 template <int E, int BN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
               const LinearParams p) {
   constexpr int ACC = E * BN;                          // accumulator columns in TMEM
@@ -362,7 +379,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int i = 0; i < 16; i++) y[i] = fmaf(coef[e], __uint_as_float(r[e][i]) + sbias[e * BN + c0 + i], y[i]);
 #pragma unroll
         for (int i = 0; i < 16; i++) y[i] = finish(y[i], p);
-        if (p.out_bf16) {
+        if (BN == 64 && p.out_bf16) {
           uint8_t* dst = stage_out + lane * 128;
 #pragma unroll
           for (int jj = 0; jj < 2; jj++) {
@@ -375,10 +392,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             *reinterpret_cast<uint4*>(dst + ((((c0 >> 3) + jj) ^ rsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         } else if (row < p.rows) {
-          store16(p, row, n0 + c0, y);
+          store16(p, row, n0 + c0, y);      // 32-column tiles: 64 contiguous bytes per row from registers
         }
       }
-      if (p.out_bf16) {
+      if (BN == 64 && p.out_bf16) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0 && m0 + q * 32 < p.rows) {
@@ -515,7 +532,7 @@ int b200nn_linear_create(const b200nn_linear_desc_t* d, int32_t device, b200nn_l
   const int E = d->num_experts;
   if (E < 1 || E > 6) return fail(-2, "b200nn_linear_create: num_experts must be 1..6");
   if (E > 1 && !d->coef) return fail(-1, "b200nn_linear_create: mixture layer needs the coefficient tensor");
-  const int bn = E == 1 ? 128 : 64;
+  const int bn = E == 1 ? 128 : MOE_BN;
   if (d->k_padded < BLOCK_K || d->k_padded % BLOCK_K || d->lda % BLOCK_K || d->ldw % BLOCK_K || d->lda < d->k_padded || d->ldw < d->k_padded)
     return fail(-2, "b200nn_linear_create: K and the leading dimensions must be padded to multiples of 64");
   if (d->n_padded < bn || d->n_padded % bn || d->n < 1 || d->n > d->n_padded) return fail(-2, "b200nn_linear_create: n_padded must be a multiple of the output tile");
@@ -576,11 +593,11 @@ int b200nn_linear_run(b200nn_linear_handle h, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   switch (h->d.num_experts) {
     case 1: return launch<1, 128, 3>(h, st);
-    case 2: return launch<2, 64, 4>(h, st);
-    case 3: return launch<3, 64, 4>(h, st);
-    case 4: return launch<4, 64, 4>(h, st);
-    case 5: return launch<5, 64, 3>(h, st);
-    case 6: return launch<6, 64, 3>(h, st);
+    case 2: return launch<2, MOE_BN, 3>(h, st);
+    case 3: return launch<3, MOE_BN, 3>(h, st);
+    case 4: return launch<4, MOE_BN, 3>(h, st);
+    case 5: return launch<5, MOE_BN, MOE_STAGES>(h, st);
+    case 6: return launch<6, MOE_BN, MOE_STAGES>(h, st);
   }
   return fail(-2, "b200nn_linear_run: unsupported expert count");
 }

@@ -83,7 +83,7 @@ class Linear:
         if w.dim() == 2:
             w, b = w[None], b[None]
         E, N, K = w.shape
-        bn = 128 if E == 1 else 64
+        bn = 128 if E == 1 else 32
         self.n_padded, self.k_padded = _up(N, bn), _up(K, 64)
         assert a.dtype == torch.bfloat16 and a.is_contiguous() and a.shape[1] >= self.k_padded and a.shape[0] >= padded_rows(rows)
         self.w = torch.zeros(E, self.n_padded, self.k_padded, device=dev, dtype=torch.bfloat16)
