@@ -1541,6 +1541,7 @@ motion_context_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __res
 // compute_humanoid_observations_imitation (humanoid_smpl_im.py:773-850): warp per env, lane per body
 // element strides of the state arrays of obs_imitation_kernel: contiguous [n, nb, 3] / [n, nb, 4] / [n, nd] copies (legacy entry) or the
 // Isaac-layout rows themselves (rigid_body_state [n, bodies_per_env, 13], dof_state [n, nd, 2]) - no gather copies
+#define OBS_ROW_MAX 768   // widest observation row: 734 (24 bodies, 69 dof, shape 11)
 struct ObsStrides { int p_row, p_elem, q_row, q_elem, d_row, d_elem; };
 struct ObsBf16 { __nv_bfloat16* out; int ld; const float* mean; const float* rstd; float clamp; };
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
@@ -1555,18 +1556,14 @@ obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restri
   // jpos = compute_humanoid_observations_imitation_jpos (:853-915): no rotation / heading / dof targets
   const int W = jpos ? 1 + (nb - 1) * 3 + nb * 6 + nb * 3 + nb * 3 + nd + 1 + 2 + nb * 3 + shape_dim
                      : 1 + (nb - 1) * 3 + nb * 6 + nb * 3 + nb * 3 + nd + 1 + 6 + 2 + 2 + nd + nb * 3 + nb * 6 + shape_dim;
-  // every value goes through put(): the float row the reference returns and, when asked for, the bf16 operand row of the policy's
-  // first layer = clamp((x - mean) * rstd, -clamp, clamp) (RunningMeanStd + the +-5 clamp of im_player.py:187-190) in the same launch
-  float* orow = obs + e * W;
-  __nv_bfloat16* brow = ob.out ? ob.out + e * (int64_t)ob.ld : nullptr;
-  auto put = [&](int idx, float val) {
-    orow[idx] = val;
-    if (brow) {
-      float x = val;
-      if (ob.mean) x = (x - __ldg(ob.mean + idx)) * __ldg(ob.rstd + idx);
-      brow[idx] = __float2bfloat16_rn(fminf(fmaxf(x, -ob.clamp), ob.clamp));
-    }
-  };
+  // every value goes through put() into the warp's row in shared memory; the row leaves at the end as coalesced 8-byte stores
+  // (the per-lane pieces - 3 / 6 values per body - are 12 / 24 bytes apart: written straight to global memory they made the launch
+  // ~30 us for 36 MB) - the float row the reference returns and, when asked for, the bf16 operand row of the policy's first layer =
+  // clamp((x - mean) * rstd, -clamp, clamp) (RunningMeanStd + the +-5 clamp of im_player.py:187-190) from the same values
+  __shared__ __align__(16) float s_obs[WARPS_PER_CTA][OBS_ROW_MAX];
+  if (W > OBS_ROW_MAX) return;            // cannot happen with the 24-body SMPL humanoid (W = 734 / 513); the host entry points check nb
+  float* srow = s_obs[warp];
+  auto put = [&](int idx, float val) { srow[idx] = val; };
   const bool act = lane < nb;
   float p[3] = {0, 0, 0}, q[4] = {0, 0, 0, 1}, v[3] = {0, 0, 0}, w[3] = {0, 0, 0}, tp[3] = {0, 0, 0}, tq[4] = {0, 0, 0, 1};
   if (act) {
@@ -1665,6 +1662,27 @@ obs_imitation_kernel(int n, int nb, int nd, int shape_dim, const float* __restri
     off += nb * 6;
   }
   if (lane < shape_dim) put(off + lane, motion_bodies[e * shape_dim + lane]);
+  __syncwarp();
+  float* orow = obs + e * W;
+  if ((((uintptr_t)orow) & 7) == 0 && (W & 1) == 0) {
+    for (int k = lane; k < W / 2; k += 32) reinterpret_cast<float2*>(orow)[k] = reinterpret_cast<const float2*>(srow)[k];
+  } else {
+    for (int k = lane; k < W; k += 32) orow[k] = srow[k];
+  }
+  if (ob.out) {
+    __nv_bfloat16* brow = ob.out + e * (int64_t)ob.ld;
+    for (int k = 2 * lane; k < W; k += 64) {
+      float x0 = srow[k], x1 = k + 1 < W ? srow[k + 1] : 0.f;
+      if (ob.mean) {
+        x0 = (x0 - __ldg(ob.mean + k)) * __ldg(ob.rstd + k);
+        if (k + 1 < W) x1 = (x1 - __ldg(ob.mean + k + 1)) * __ldg(ob.rstd + k + 1);
+      }
+      x0 = fminf(fmaxf(x0, -ob.clamp), ob.clamp);
+      x1 = fminf(fmaxf(x1, -ob.clamp), ob.clamp);
+      if (k + 1 < W) *reinterpret_cast<__nv_bfloat162*>(brow + k) = __floats2bfloat162_rn(x0, x1);   // ld is a multiple of 64: 4-byte aligned
+      else brow[k] = __float2bfloat16_rn(x0);
+    }
+  }
 }
 
 // physics-only entry used by the parity tests (float or double)
