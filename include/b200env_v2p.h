@@ -15,11 +15,12 @@ const char* b200v2p_last_error(void);
  * 2 = dual mode's alternating players, n = a shape per env); outputs in MuJoCo body order (smpl_2_mujoco);
  * prev_* NULL -> zero velocities.  prev_root_pos_update / target_root_pos_out (either may be NULL): after the finite difference the
  * root position of this call is stored there - `_save_prev_target_motion_state` (:741-750) and `self._target_root_pos = root_pos`
- * (:655) folded into the launch; prev_root_pos_update may be the same buffer as prev_root_pos. */
+ * (:655) folded into the launch; prev_root_pos_update may be the same buffer as prev_root_pos.  only_mask (may be NULL): bool [n], the
+ * envs whose entry is 0 are skipped (mask-driven reset: FK of the envs being reset only). */
 int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rotmat, const float* rest, int32_t num_rest,
                         const int32_t* parents, const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
                         float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, float* prev_root_pos_update,
-                        float* target_root_pos_out, void* stream);
+                        float* target_root_pos_out, const uint8_t* only_mask, void* stream);
 
 /* replaces the fix_head_orientation block of _set_target_motion_state (env/tasks/humanoid_smpl_im_mvae.py:605-634):
  * rb_pos/rb_rot [n,24,*] = FK of the uncorrected pose (MuJoCo order, head_body = 13); joint_rotmat [n,24,3,3] (SMPL order) is
@@ -48,6 +49,7 @@ typedef struct b200v2p_state {
   const float* ball_states;      /* ball root row per env, stride ball_stride floats */
   uint8_t *has_contact, *has_contact_now;
   float *root_pos, *root_vel, *racket_pos, *racket_vel, *racket_normal, *ball_pos, *ball_vel, *ball_vspin;
+  const uint8_t* only_mask;      /* NULL, or bool [n]: refresh the envs whose entry is set only (reset path) */
 } b200v2p_state_t;
 int b200v2p_update_state(const b200v2p_state_t* s, void* stream);
 
@@ -87,6 +89,9 @@ typedef struct b200v2p_ctrl {
   float* ball_obs; /* [n, obs_traj_len, 3] _ball_obs (:65): rolled by one and appended with ball_pos at every observation (:345-346);
                       in obs_only mode only for the envs whose reset masks are set (the reference refreshes those ids only).
                       NULL = not kept (then use_history must be 0) */
+  const uint8_t* touch_mask; /* NULL, or bool [n] with obs_only: the humanoids just reset.  Rows of envs that are neither in it nor flagged
+                                reset_reaction / reset_recovery are still current and skipped; the task flags of the envs in it are cleared
+                                at the end (tail of _reset_envs, :176-177) */
 } b200v2p_ctrl_t;
 int b200v2p_controller_post(const b200v2p_ctrl_t* c, void* stream);
 
@@ -108,6 +113,11 @@ typedef struct b200v2p_prestep {
 } b200v2p_prestep_t;
 int b200v2p_pre_step(const b200v2p_prestep_t* p, void* stream);
 
+/* the controller's own bookkeeping of a humanoid reset (env/tasks/physics_mvae_controller.py:176-181, 203-210) for the envs whose mask
+ * is set: progress / reset / terminate / num_reset_reaction <- 0, distance <- 0, num_reset += 1 */
+int b200v2p_ctrl_reset(int32_t n, const uint8_t* mask, int64_t* progress_buf, int64_t* reset_buf, int64_t* terminate_buf, int64_t* num_reset_reaction,
+                       float* distance, int64_t* num_reset, void* stream);
+
 /* The resident kinematic target stream that stands in for the unreleased MVAE motion generator: `frames`
  * frames of every field for all n envs are kept in HBM ([frames * n, ...], frame-major); env e reads frame (clock + advance +
  * offset[e]) % frames into the live buffers MVAEPlayer exposes (players/mvae_player.py: _joint_rotmat [n,24,3,3], _root_pos,
@@ -117,7 +127,10 @@ typedef struct b200v2p_stream {
   int32_t n, frames, advance, pad_;
   int64_t* clock;              /* [1] */
   uint32_t* done_counter;      /* [1] scratch, zero between launches */
-  const int64_t* offset;       /* [n] */
+  int64_t* offset;             /* [n] */
+  const uint8_t* reseed_mask;  /* NULL, or bool [n] (reset): the envs whose entry is set draw a new offset (counter-based: seed, clock, env)
+                                  and re-read their frame; the others are left alone */
+  uint64_t seed;
   const float* ring_rotmat;    float* rotmat;
   const float* ring_root_pos;  float* root_pos;
   const float* ring_racket_pos; float* racket_pos;

@@ -65,6 +65,11 @@ int b200nn_linear_run(b200nn_linear_handle h, void* stream);
 int b200nn_cast_rows(const float* src, int32_t ld_src, void* dst_bf16, int32_t ld_dst, int32_t rows, int32_t cols, const float* mean,
                      const float* rstd, float lo, float hi, void* stream);
 
+/* the cast for the rows whose mask entry (bool [rows]) is set only: the condition of the envs being reset <- their initial frame
+ * (MVAEPlayer.reset, players/mvae_player.py:162-166) inside the mask-driven reset graph */
+int b200nn_cast_rows_masked(const float* src, int32_t ld_src, void* dst_bf16, int32_t ld_dst, int32_t rows, int32_t cols, const uint8_t* row_mask,
+                            float lo, float hi, void* stream);
+
 /* the same cast of one float block into up to three bf16 buffers of the same leading dimension (dst2 / dst3 may be NULL): the latent z
  * is the first block of all three MixedDecoder layer inputs (`torch.cat((z, layer_out), dim=1)`, model.py:247) */
 int b200nn_cast_rows3(const float* src, int32_t ld_src, void* dst_bf16, void* dst2_bf16, void* dst3_bf16, int32_t ld_dst, int32_t rows,

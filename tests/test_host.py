@@ -279,13 +279,13 @@ def test_v2p_glue_struct_layouts(tmp_path):
     from vid2player3d_b200 import abi
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s/include/b200env_v2p.h"\n'
-                   'int main(){printf("%%zu %%zu %%zu %%zu %%zu\\n",sizeof(b200v2p_prestep_t),offsetof(b200v2p_prestep_t,actions),'
-                   'sizeof(b200v2p_stream_t),offsetof(b200v2p_stream_t,ring_phase),offsetof(b200v2p_ctrl_t,advance));}' % ROOT)
+                   'int main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu\\n",sizeof(b200v2p_prestep_t),offsetof(b200v2p_prestep_t,actions),'
+                   'sizeof(b200v2p_stream_t),offsetof(b200v2p_stream_t,ring_phase),offsetof(b200v2p_ctrl_t,advance),offsetof(b200v2p_ctrl_t,touch_mask),offsetof(b200v2p_state_t,only_mask));}' % ROOT)
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert got == [C.sizeof(abi.V2PPreStep), abi.V2PPreStep.actions.offset, C.sizeof(abi.V2PStream), abi.V2PStream.ring_phase.offset,
-                   abi.V2PCtrl.advance.offset]
+                   abi.V2PCtrl.advance.offset, abi.V2PCtrl.touch_mask.offset, abi.V2PState.only_mask.offset]
 
 
 def test_motion_lib_formats_directory_and_merge(tmp_path):

@@ -228,6 +228,7 @@ class V2PState(C.Structure):
         ("has_contact", C.c_void_p), ("has_contact_now", C.c_void_p),
         ("root_pos", C.c_void_p), ("root_vel", C.c_void_p), ("racket_pos", C.c_void_p), ("racket_vel", C.c_void_p),
         ("racket_normal", C.c_void_p), ("ball_pos", C.c_void_p), ("ball_vel", C.c_void_p), ("ball_vspin", C.c_void_p),
+        ("only_mask", C.c_void_p),
     ]
 
 
@@ -251,7 +252,7 @@ class V2PCtrl(C.Structure):
         ("bounce_in", C.c_void_p), ("est_bounce_in", C.c_void_p), ("reset_reaction", C.c_void_p), ("reset_recovery", C.c_void_p),
         ("est_bounce_pos", C.c_void_p), ("est_bounce_time", C.c_void_p), ("est_max_height", C.c_void_p), ("distance", C.c_void_p),
         ("obs_buf", C.c_void_p), ("rew_buf", C.c_void_p), ("sub_rewards", C.c_void_p),
-        ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p), ("ball_obs", C.c_void_p),
+        ("reset_buf", C.c_void_p), ("terminate_buf", C.c_void_p), ("ball_obs", C.c_void_p), ("touch_mask", C.c_void_p),
     ]
 
 
@@ -267,7 +268,7 @@ class V2PPreStep(C.Structure):
 class V2PStream(C.Structure):
     _fields_ = [
         ("n", C.c_int32), ("frames", C.c_int32), ("advance", C.c_int32), ("pad_", C.c_int32),
-        ("clock", C.c_void_p), ("done_counter", C.c_void_p), ("offset", C.c_void_p),
+        ("clock", C.c_void_p), ("done_counter", C.c_void_p), ("offset", C.c_void_p), ("reseed_mask", C.c_void_p), ("seed", C.c_uint64),
         ("ring_rotmat", C.c_void_p), ("rotmat", C.c_void_p), ("ring_root_pos", C.c_void_p), ("root_pos", C.c_void_p),
         ("ring_racket_pos", C.c_void_p), ("racket_pos", C.c_void_p), ("ring_phase", C.c_void_p), ("phase", C.c_void_p),
         ("ring_swing_type", C.c_void_p), ("swing_type", C.c_void_p), ("ring_swing_type_cycle", C.c_void_p), ("swing_type_cycle", C.c_void_p),

@@ -90,10 +90,11 @@ smpl_to_sim_kernel(int n, const float* __restrict__ root_pos, const float* __res
                    int num_rest, const int32_t* __restrict__ parents, const int32_t* __restrict__ smpl_2_mujoco, float dt,
                    const float* prev_root_pos, const float* __restrict__ prev_rb_rot, float* root_rot, float* dof_pos,
                    float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, float* prev_root_pos_update,
-                   float* target_root_pos_out) {
+                   float* target_root_pos_out, const uint8_t* __restrict__ only_mask) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * V2P_WARPS + warp;
   if (e >= n) return;
+  if (only_mask && !only_mask[e]) return;      // mask-driven reset: FK of the envs being reset only
   const float* rest = rest_all + (e % num_rest) * 72;   // per-shape rest joints: env e has shape e % num_rest (dual: players alternate)
   const bool act = lane < 24;
   const int j = act ? lane : 0;
@@ -312,6 +313,7 @@ __global__ void ball_reset_kernel(int n, const int64_t* __restrict__ env_ids, co
 __global__ void update_state_kernel(b200v2p_state_t s) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= s.n) return;
+  if (s.only_mask && !s.only_mask[e]) return;     // reset path: the reference refreshes the state views when humanoids were reset (:186-187)
   const float* rb = s.rigid_body_state + e * s.bodies_per_env * 13;
   const float* ball = s.ball_states + e * s.ball_stride;
   // velocity-jump contact detector (substeps > 2): uses the ball velocity of the previous control step (:800-808)
@@ -348,6 +350,8 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * V2P_WARPS + warp;
   if (e >= c.n) return;
+  const bool touched = c.touch_mask && c.touch_mask[e];
+  if (c.obs_only && c.touch_mask && !touched && !c.reset_reaction[e] && !c.reset_recovery[e]) return;   // row still current
   const float* rb = c.rigid_body_state + e * c.bodies_per_env * 13;
   if (c.advance && !c.obs_only) {
     // tail of physics_step (:364-366) + head of post_physics_step (:441-444) folded in: the future-trajectory window moves on by one
@@ -517,6 +521,7 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) controller_post_kernel(b200v2p
     c.reset_reaction[e] = reaction ? 1 : 0;
     c.reset_recovery[e] = recovery ? 1 : 0;
   }
+  if (lane == 0 && c.obs_only && touched) { c.reset_reaction[e] = 0; c.reset_recovery[e] = 0; }   // tail of _reset_envs (:176-177) for the reset humanoids
 }
 
 // ------------------------------------------------------------------------------------------ dual mode: incoming-ball table
@@ -690,6 +695,16 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) actor_reset_kernel(b200v2p_are
   }
 }
 
+// ------------------------------------------------------------------------------------------ controller bookkeeping of a humanoid reset
+// PhysicsMVAEController._reset_envs (:176-181) for the envs whose mask is set: the controller's own progress / reset / terminate
+// counters and statistics, one launch instead of seven masked fills
+__global__ void ctrl_reset_kernel(int n, const uint8_t* __restrict__ mask, int64_t* progress, int64_t* reset_buf, int64_t* terminate,
+                                  int64_t* num_reset_reaction, float* distance, int64_t* num_reset) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n || !mask[e]) return;
+  progress[e] = 0; reset_buf[e] = 0; terminate[e] = 0; num_reset_reaction[e] = 0; distance[e] = 0.0f; num_reset[e] += 1;
+}
+
 // ------------------------------------------------------------------------------------------ high-level pre_physics_step
 // PhysicsMVAEController.pre_physics_step (:247-262) before the motion generator runs: the latent part of the action scaled by
 // vae_action_scale, replaced by clamp(N(0,1), -5, 5) for the envs in recovery (random_walk_in_recovery), the residual-dof part scaled
@@ -743,7 +758,12 @@ __global__ void __launch_bounds__(V2P_WARPS * 32) stream_gather_kernel(b200v2p_s
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * V2P_WARPS + warp;
   const int64_t t = s.clock[0] + s.advance;
-  if (e < s.n) {
+  if (e < s.n && (!s.reseed_mask || s.reseed_mask[e])) {
+    if (s.reseed_mask) {          // reset of the masked envs: a fresh offset into the stream (counter-based draw), others untouched
+      const uint64_t h = splitmix64(splitmix64(s.seed ^ ((uint64_t)t * 0xD1B54A32D192ED03ull)) + (uint64_t)e);
+      if (lane == 0) s.offset[e] = (int64_t)(h % (uint64_t)s.frames);
+      __syncwarp();
+    }
     int64_t f = (t + s.offset[e]) % s.frames;
     if (f < 0) f += s.frames;
     const int64_t row = f * s.n + e;
@@ -766,7 +786,7 @@ const char* b200v2p_last_error(void) { return g_verr; }
 int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rotmat, const float* rest, int32_t num_rest,
                         const int32_t* parents, const int32_t* smpl_2_mujoco, float dt, const float* prev_root_pos, const float* prev_rb_rot, float* root_rot,
                         float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel, float* rb_pos, float* rb_rot, float* prev_root_pos_update,
-                        float* target_root_pos_out, void* stream) {
+                        float* target_root_pos_out, const uint8_t* only_mask, void* stream) {
   if (n == 0) return 0;
   if (n < 0 || !root_pos || !joint_rotmat || !rest || !parents || !smpl_2_mujoco || !root_rot || !dof_pos || !root_vel || !root_ang_vel ||
       !dof_vel || !rb_pos || !rb_rot)
@@ -775,7 +795,7 @@ int b200v2p_smpl_to_sim(int32_t n, const float* root_pos, const float* joint_rot
   if (num_rest < 1) return vfail(-2, "b200v2p_smpl_to_sim: num_rest must be >= 1");
   smpl_to_sim_kernel<<<(n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(
       n, root_pos, joint_rotmat, rest, num_rest, parents, smpl_2_mujoco, dt, prev_root_pos, prev_rb_rot, root_rot, dof_pos, root_vel, root_ang_vel,
-      dof_vel, rb_pos, rb_rot, prev_root_pos_update, target_root_pos_out);
+      dof_vel, rb_pos, rb_rot, prev_root_pos_update, target_root_pos_out, only_mask);
   V_CUDA_OK();
   return 0;
 }
@@ -853,6 +873,16 @@ int b200v2p_task_reset(const b200v2p_treset_t* r, void* stream) {
   if (r->n == 0) return 0;
   if (r->pool_size < 1 || !r->pool || !r->reset_reaction || !r->reset_recovery) return vfail(-1, "b200v2p_task_reset: bad arguments");
   task_reset_kernel<<<(r->n + V2P_WARPS - 1) / V2P_WARPS, V2P_WARPS * 32, 0, (cudaStream_t)stream>>>(*r);
+  V_CUDA_OK();
+  return 0;
+}
+
+int b200v2p_ctrl_reset(int32_t n, const uint8_t* mask, int64_t* progress_buf, int64_t* reset_buf, int64_t* terminate_buf, int64_t* num_reset_reaction,
+                       float* distance, int64_t* num_reset, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !mask || !progress_buf || !reset_buf || !terminate_buf || !num_reset_reaction || !distance || !num_reset)
+    return vfail(-1, "b200v2p_ctrl_reset: bad arguments");
+  ctrl_reset_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, mask, progress_buf, reset_buf, terminate_buf, num_reset_reaction, distance, num_reset);
   V_CUDA_OK();
   return 0;
 }

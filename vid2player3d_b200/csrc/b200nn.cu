@@ -424,8 +424,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // dimension get the same values (the latent block of the three MixedDecoder layer inputs)
 __global__ void cast_rows_kernel(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst2,
                                  __nv_bfloat16* __restrict__ dst3, int ld_dst, int rows, int cols, const float* __restrict__ mean,
-                                 const float* __restrict__ rstd, float lo, float hi) {
+                                 const float* __restrict__ rstd, float lo, float hi, const uint8_t* __restrict__ row_mask) {
   for (int r = blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += gridDim.x * blockDim.y) {
+    if (row_mask && !row_mask[r]) continue;
     const float* s = src + (size_t)r * ld_src;
     const size_t o = (size_t)r * ld_dst;
     for (int c = threadIdx.x; c < cols; c += blockDim.x) {
@@ -608,7 +609,7 @@ int b200nn_probe_read(unsigned long long* out16) { return cudaMemcpyFromSymbol(o
 #endif
 
 static int cast_launch(const float* src, int32_t ld_src, void* dst, void* dst2, void* dst3, int32_t ld_dst, int32_t rows, int32_t cols,
-                       const float* mean, const float* rstd, float lo, float hi, void* stream) {
+                       const float* mean, const float* rstd, float lo, float hi, void* stream, const uint8_t* row_mask = nullptr) {
   if (!src || !dst || rows < 1 || cols < 1 || cols > ld_src || cols > ld_dst) return fail(-2, "b200nn_cast_rows: bad argument");
   if ((mean == nullptr) != (rstd == nullptr)) return fail(-2, "b200nn_cast_rows: mean and rstd go together");
   const int tx = cols >= 256 ? 256 : (cols >= 128 ? 128 : (cols >= 64 ? 64 : 32));
@@ -618,7 +619,7 @@ static int cast_launch(const float* src, int32_t ld_src, void* dst, void* dst2, 
   static bool once = (prefer_max_shared(cast_rows_kernel), true);
   (void)once;
   cast_rows_kernel<<<blocks, block, 0, (cudaStream_t)stream>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), reinterpret_cast<__nv_bfloat16*>(dst2),
-                                                             reinterpret_cast<__nv_bfloat16*>(dst3), ld_dst, rows, cols, mean, rstd, lo, hi);
+                                                             reinterpret_cast<__nv_bfloat16*>(dst3), ld_dst, rows, cols, mean, rstd, lo, hi, row_mask);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -626,6 +627,12 @@ static int cast_launch(const float* src, int32_t ld_src, void* dst, void* dst2, 
 int b200nn_cast_rows(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, int32_t rows, int32_t cols, const float* mean, const float* rstd,
                      float lo, float hi, void* stream) {
   return cast_launch(src, ld_src, dst, nullptr, nullptr, ld_dst, rows, cols, mean, rstd, lo, hi, stream);
+}
+
+int b200nn_cast_rows_masked(const float* src, int32_t ld_src, void* dst, int32_t ld_dst, int32_t rows, int32_t cols, const uint8_t* row_mask,
+                            float lo, float hi, void* stream) {
+  if (!row_mask) return fail(-2, "b200nn_cast_rows_masked: null mask");
+  return cast_launch(src, ld_src, dst, nullptr, nullptr, ld_dst, rows, cols, nullptr, nullptr, lo, hi, stream, row_mask);
 }
 
 int b200nn_cast_rows3(const float* src, int32_t ld_src, void* dst, void* dst2, void* dst3, int32_t ld_dst, int32_t rows, int32_t cols, void* stream) {

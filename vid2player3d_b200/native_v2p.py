@@ -5,7 +5,7 @@ from . import abi
 from .native import _ptr, _stream, lib
 
 SYMBOLS = ["b200v2p_last_error", "b200v2p_smpl_to_sim", "b200v2p_ball_aero", "b200v2p_ball_reset", "b200v2p_ball_in_estimate", "b200v2p_update_state",
-           "b200v2p_controller_post", "b200v2p_task_reset", "b200v2p_actor_reset", "b200v2p_fix_head", "b200v2p_pre_step", "b200v2p_stream_gather"]
+           "b200v2p_controller_post", "b200v2p_task_reset", "b200v2p_actor_reset", "b200v2p_fix_head", "b200v2p_pre_step", "b200v2p_stream_gather", "b200v2p_ctrl_reset"]
 GRIP_NORMAL = {'eastern': (0.0, 1.0, 0.0), 'semi_western': (0.0, 2.0 ** -0.5, 2.0 ** -0.5)}
 REWARD_TYPES = {'reach': 0, 'return': 1, 'return_w_estimate': 2}
 
@@ -23,7 +23,7 @@ def _c(t):
 
 
 def smpl_to_sim(root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, out, prev_root_pos=None, prev_rb_rot=None, prev_root_pos_update=None,
-                target_root_pos_out=None):
+                target_root_pos_out=None, only_mask=None):
     """out: dict with root_rot[n,4] dof_pos[n,69] root_vel[n,3] root_ang_vel[n,3] dof_vel[n,69] rb_pos[n,24,3] rb_rot[n,24,4];
     prev_root_pos_update / target_root_pos_out: the root position of this call is also stored there (may alias prev_root_pos)"""
     n = int(root_pos.shape[0])
@@ -32,7 +32,7 @@ def smpl_to_sim(root_pos, joint_rotmat, rest, parents, smpl_2_mujoco, dt, out, p
     _check(lib().b200v2p_smpl_to_sim(C.c_int32(n), _c(root_pos), _c(joint_rotmat), _c(rest), C.c_int32(num_rest), _c(parents), _c(smpl_2_mujoco), C.c_float(dt),
                                      _c(prev_root_pos), _c(prev_rb_rot), _c(out["root_rot"]), _c(out["dof_pos"]), _c(out["root_vel"]),
                                      _c(out["root_ang_vel"]), _c(out["dof_vel"]), _c(out["rb_pos"]), _c(out["rb_rot"]), _c(prev_root_pos_update),
-                                     _c(target_root_pos_out), _stream()))
+                                     _c(target_root_pos_out), _c(only_mask), _stream()))
 
 
 def fix_head(rb_pos, rb_rot, ball_pos, root_pos, joint_rotmat, head_body=13):
@@ -54,7 +54,7 @@ def ball_reset(env_ids, pool_index, pool, ball_states, ball_pos, ball_vel, has_b
 
 
 def update_state(n, bodies_per_env, rigid_body_state, root_states, root_stride, ball_states, ball_stride, t, grip='eastern',
-                 racket_body=24, wrist_body=22):
+                 racket_body=24, wrist_body=22, only_mask=None):
     """grip / racket_body / wrist_body may be 2-sequences (dual_mode 'different': even envs, odd envs)"""
     s = abi.V2PState()
     pair = lambda v: (v[0], v[1], 1) if isinstance(v, (list, tuple)) else (v, v, 0)  # noqa: E731
@@ -71,6 +71,7 @@ def update_state(n, bodies_per_env, rigid_body_state, root_states, root_stride, 
               "ball_vspin"):
         assert t[k].is_cuda and t[k].is_contiguous(), k
         setattr(s, k, t[k].data_ptr())
+    s.only_mask = only_mask.data_ptr() if only_mask is not None else None
     _check(lib().b200v2p_update_state(C.byref(s), _stream()))
 
 
@@ -107,7 +108,7 @@ def controller_post(cfg, t):
             continue
         x = t.get(name)
         if x is None:
-            assert name in ("est_x", "est_y", "ball_obs"), name
+            assert name in ("est_x", "est_y", "ball_obs", "touch_mask"), name
             setattr(c, name, None)
         else:
             assert x.is_cuda and x.is_contiguous(), name
@@ -176,12 +177,24 @@ def pre_step(cfg, t):
     _check(lib().b200v2p_pre_step(C.byref(p), _stream()))
 
 
-def stream_gather(n, frames, advance, t):
-    """t: clock (int64 [1]), done_counter (int32 [1]), offset [n] int64, ring_* / live buffers of include/b200env_v2p.h b200v2p_stream_t"""
+def stream_gather(n, frames, advance, t, reseed_mask=None, seed=0):
+    """t: clock (int64 [1]), done_counter (int32 [1]), offset [n] int64, ring_* / live buffers of include/b200env_v2p.h b200v2p_stream_t;
+    reseed_mask (bool [n]): the masked envs draw a new offset and re-read their frame, the others are left alone"""
     s = abi.V2PStream()
     s.n, s.frames, s.advance = int(n), int(frames), int(advance)
+    s.seed = int(seed)
+    s.reseed_mask = reseed_mask.data_ptr() if reseed_mask is not None else None
     for name, _ in abi.V2PStream._fields_[4:]:
+        if name in ("reseed_mask", "seed"):
+            continue
         x = t[name]
         assert x.is_cuda and x.is_contiguous(), name
         setattr(s, name, x.data_ptr())
     _check(lib().b200v2p_stream_gather(C.byref(s), _stream()))
+
+
+def ctrl_reset(mask, progress_buf, reset_buf, terminate_buf, num_reset_reaction, distance, num_reset):
+    for x in (mask, progress_buf, reset_buf, terminate_buf, num_reset_reaction, distance, num_reset):
+        assert x.is_cuda and x.is_contiguous()
+    _check(lib().b200v2p_ctrl_reset(C.c_int32(int(mask.shape[0])), _ptr(mask), _ptr(progress_buf), _ptr(reset_buf), _ptr(terminate_buf),
+                                    _ptr(num_reset_reaction), _ptr(distance), _ptr(num_reset), _stream()))

@@ -22,7 +22,7 @@ ACT = {None: 0, "none": 0, "relu": 1, "elu": 2}
 _lib = None
 
 SYMBOLS = ["b200nn_abi_version", "b200nn_last_error", "b200nn_linear_create", "b200nn_linear_destroy", "b200nn_linear_run",
-           "b200nn_cast_rows", "b200nn_cast_rows3", "b200nn_gate_softmax"]
+           "b200nn_cast_rows", "b200nn_cast_rows3", "b200nn_cast_rows_masked", "b200nn_gate_softmax"]
 ABI_VERSION = 1
 
 
@@ -237,10 +237,10 @@ class MixedDecoder:
 
     __call__ = forward
 
-    def set_condition(self, c, clamp=None):
-        """condition block of the first layer's operand <- bf16(clamp(c[:, :cond]))"""
+    def set_condition(self, c, clamp=None, row_mask=None):
+        """condition block of the first layer's operand <- bf16(clamp(c[:, :cond])); row_mask (bool [rows]): those rows only"""
         lo, hi = (-clamp, clamp) if clamp else (-3.0e38, 3.0e38)
-        _cast_cols(c, self.x0, self.L, self.cond, lo, hi)
+        _cast_cols(c, self.x0, self.L, self.cond, lo, hi, row_mask)
 
     def feed_back(self, clamp=3.0):
         """autoregression of MVAEPlayer (players/mvae_player.py:201-204): the predicted frame becomes the next condition - one cast
@@ -266,9 +266,15 @@ class MixedDecoder:
         return cls(ws, bs, gate, num_envs, device, latent_size)
 
 
-def _cast_cols(src, dst, col0, cols, lo=-3.0e38, hi=3.0e38):
+def _cast_cols(src, dst, col0, cols, lo=-3.0e38, hi=3.0e38, row_mask=None):
     """dst[:rows, col0:col0+cols] = bf16(clamp(src[:, :cols])) through the strided view (col0 elements into each row of dst)"""
     assert src.dtype == torch.float32 and src.stride(-1) == 1
     view_ptr = dst.data_ptr() + col0 * 2
+    if row_mask is not None:
+        assert row_mask.dtype == torch.bool and row_mask.is_contiguous() and row_mask.shape[0] == src.shape[0]
+        _check(lib().b200nn_cast_rows_masked(C.c_void_p(src.data_ptr()), C.c_int32(src.stride(0)), C.c_void_p(view_ptr), C.c_int32(dst.shape[1]),
+                                             C.c_int32(src.shape[0]), C.c_int32(cols), C.c_void_p(row_mask.data_ptr()), C.c_float(lo), C.c_float(hi),
+                                             _stream()))
+        return
     _check(lib().b200nn_cast_rows(C.c_void_p(src.data_ptr()), C.c_int32(src.stride(0)), C.c_void_p(view_ptr), C.c_int32(dst.shape[1]),
                                   C.c_int32(src.shape[0]), C.c_int32(cols), None, None, C.c_float(lo), C.c_float(hi), _stream()))

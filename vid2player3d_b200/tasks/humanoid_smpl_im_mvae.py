@@ -266,8 +266,8 @@ class HumanoidSMPLIMMVAE(BaseTask):
             h.step(actions)
         self._update_state_from_sim()
 
-    def _update_state_from_sim(self):
-        """:799-860"""
+    def _update_state_from_sim(self, only_mask=None):
+        """:799-860; only_mask (bool [N], reset path): refresh the masked envs only"""
         t = dict(has_contact=self._has_racket_ball_contact, has_contact_now=self._has_racket_ball_contact_now, root_pos=self._root_pos,
                  root_vel=self._root_vel, racket_pos=self._racket_pos, racket_vel=self._racket_vel, racket_normal=self._racket_normal,
                  ball_pos=self._ball_pos, ball_vel=self._ball_vel, ball_vspin=self._ball_vspin)
@@ -282,7 +282,7 @@ class HumanoidSMPLIMMVAE(BaseTask):
             self._has_racket_ball_contact_now.copy_(now)
         else:
             native_v2p.update_state(self.num_envs, 26, self._rigid_body_state, self._root_states, 26, self._root_states[1:], 26, t,
-                                    grip=self._grip(), wrist_body=self._racket_wrist_body_id)
+                                    grip=self._grip(), wrist_body=self._racket_wrist_body_id, only_mask=only_mask)
         if not self._is_train:
             # :814-820 test-time export of the simulated pose as SMPL joint rotations (root angle-axis | dof_pos, SMPL joint order)
             root_rot = quaternion_wxyz_to_angle_axis(self._rigid_body_rot[:, 0][..., [3, 0, 1, 2]])
@@ -321,7 +321,8 @@ class HumanoidSMPLIMMVAE(BaseTask):
         """_reset_actors for the envs whose mask is set: same two launches over all rows, no id list (CUDA-graph safe)"""
         if not hasattr(self, "_all_ids"):
             self._all_ids = torch.arange(self.num_envs, device=self.device, dtype=torch.long)
-        self._smpl_to_sim_into(self._mvae_player._root_pos.contiguous(), self._mvae_player._joint_rotmat, self._tmp)
+        native_v2p.smpl_to_sim(self._mvae_player._root_pos.contiguous(), self._mvae_player._joint_rotmat.contiguous(), self._rest_t, self._parents_t,
+                               self._s2m_t, self.dt, self._tmp, only_mask=mask)
         cfg = dict(n=self.num_envs, num_dof=self.num_dof, bodies_per_env=26, root_stride=26, racket_body=24,
                    racket_parent=self._racket_parents[0], racket_offset=self._model["offset"][24],
                    racket_offset2=self._models[1]["offset"][24] if len(self._models) == 2 else None,

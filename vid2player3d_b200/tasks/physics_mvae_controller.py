@@ -159,6 +159,7 @@ class StreamMotionPlayer:
         for f in self.FIELDS:                                   # the live buffers the env reads (fixed addresses)
             setattr(self, f, rings[f][0].clone())
         self._t = torch.zeros(1, device=device, dtype=torch.long)
+        self._seed = int(seed) * 104729 + 7
         self._done = torch.zeros(1, device=device, dtype=torch.int32)      # scratch of the launch (last-block counter)
         self._off = torch.randint(0, frames, (num_envs,), device=device, generator=gen)
         self._gt = dict(clock=self._t, done_counter=self._done, offset=self._off, ring_rotmat=self._ring["_joint_rotmat"], rotmat=self._joint_rotmat,
@@ -168,9 +169,10 @@ class StreamMotionPlayer:
                         ring_swing_type_cycle=self._ring["_swing_type_cycle"], swing_type_cycle=self._swing_type_cycle)
         self._gather()
 
-    def _gather(self, advance=0):
-        """one launch (b200v2p_stream_gather): frame (t + advance + off[e]) % K of every field -> the live buffers; advance moves the clock"""
-        native_v2p.stream_gather(self.N, self.K, advance, self._gt)
+    def _gather(self, advance=0, reseed_mask=None):
+        """one launch (b200v2p_stream_gather): frame (t + advance + off[e]) % K of every field -> the live buffers; advance moves the
+        clock; reseed_mask: those envs draw a new offset first (counter-based) and only they are re-read"""
+        native_v2p.stream_gather(self.N, self.K, advance, self._gt, reseed_mask=reseed_mask, seed=self._seed)
 
     def step(self, mvae_actions, res_dof_actions=None):
         self._gather(advance=1)
@@ -180,8 +182,7 @@ class StreamMotionPlayer:
         self._gather()
 
     def reset_masked(self, mask):
-        self._off.copy_(torch.where(mask, torch.randint(0, self.K, (self.N,), device=self.device), self._off))
-        self._gather()
+        self._gather(reseed_mask=mask)          # one launch: new offsets for the masked envs + their frames
 
     def reset_dual(self, reset_reaction_env_ids, reset_recovery_env_ids):
         self.reset(torch.cat([reset_reaction_env_ids, reset_recovery_env_ids]).sort().values)
@@ -214,7 +215,7 @@ class DecoderStreamPlayer(StreamMotionPlayer):
 
     def reset_masked(self, mask):
         super().reset_masked(mask)
-        self._cond_view.copy_(torch.where(mask[:, None], self._init_bf16, self._cond_view))
+        self.decoder.set_condition(self._init_data, row_mask=mask)      # one launch, masked rows only
 
     def step(self, mvae_actions, res_dof_actions=None):
         super().step(mvae_actions, res_dof_actions)
@@ -409,7 +410,7 @@ class PhysicsMVAEController:
         self._reset_graph.replay()
         self._has_init = True
 
-    def _reset_tasks_fast(self, update_state=False):
+    def _reset_tasks_fast(self, update_state=False, humanoid_mask=None):
         """_reset_envs (:173-201) when no humanoid needs a reset - the common per-step case: new balls for the envs whose reaction
         timer expired, recovery / reaction task bookkeeping, obs refresh.  Mask-driven: 4 RNG launches + 2 kernels, no host sync."""
         N, dev, t = self.num_envs, self.device, self._physics_player.task
@@ -432,10 +433,13 @@ class PhysicsMVAEController:
             tar_time_total=self._tar_time_total, tar_action=self._tar_action, num_reset_reaction=self._num_reset_reaction,
             swing_type_cycle=self._mvae_player._swing_type_cycle, ball_obs=self._ball_obs if self._use_history else None))
         if update_state:
-            self._physics_player.task._update_state_from_sim()   # :186-187 "setting the right fields to compute obs"
+            self._physics_player.task._update_state_from_sim(only_mask=humanoid_mask)   # :186-187 "setting the right fields to compute obs"
         post = dict(self._post_cfg)
         post["obs_only"] = 1
-        native_v2p.controller_post(post, self._tensors())
+        t = self._tensors()
+        if humanoid_mask is not None:
+            t["touch_mask"] = humanoid_mask
+        native_v2p.controller_post(post, t)
 
     def _reset_envs(self, env_ids):
         """:173-201.  Humanoid part (id list from the agent): motion generator reset, FK pose -> sim state (2 launches), counters.
@@ -458,18 +462,14 @@ class PhysicsMVAEController:
         self._has_init = True
 
     def _reset_envs_masked(self, mask):
-        """_reset_envs (:173-201) driven by a device mask of the humanoids to reset instead of an id list: full-width in-place ops
-        and mask-aware kernels only, no host synchronisation - `enable_cuda_graph` captures it as the reset graph."""
+        """_reset_envs (:173-201) driven by a device mask of the humanoids to reset instead of an id list: mask-aware kernels only, no
+        host synchronisation - `enable_cuda_graph` captures it as the reset graph.  Kernels of the humanoid part skip the envs whose
+        mask is clear, so a replay in which nobody finished costs little more than its launches."""
         task = self._physics_player.task
         self._mvae_player.reset_masked(mask)
         task._reset_actors_masked(mask)
-        for buf in (self.progress_buf, self.reset_buf, self._terminate_buf, self._num_reset_reaction):
-            buf.masked_fill_(mask, 0)
-        self._distance.masked_fill_(mask, 0.0)
-        self._num_reset.add_(mask.to(torch.long))
-        self._reset_tasks_fast(update_state=True)
-        self._reset_reaction_buf.masked_fill_(mask, False)
-        self._reset_recovery_buf.masked_fill_(mask, False)
+        native_v2p.ctrl_reset(mask, self.progress_buf, self.reset_buf, self._terminate_buf, self._num_reset_reaction, self._distance, self._num_reset)
+        self._reset_tasks_fast(update_state=True, humanoid_mask=mask)      # also clears the task flags of the reset humanoids at its end
         self._has_init = True
 
     def _reset_envs_idlist(self, env_ids):
