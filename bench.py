@@ -175,22 +175,27 @@ def amass_leg(envs, device_index, rank, K, W, flush):
     ms = timed_steps(step, K, flush)
     phys_ms, _ = task._env.kernel_ms()
     task._env.set_kernel_timing(False)
-    resets = int(task.reset_buf.sum())
-    # standing / tracking workload next to the random policy: zero residual actions = PD targets at the MoCap pose
-    zero = torch.zeros(envs, task.num_actions, device=task.device)
+    resets = int(task._terminate_buf.sum())
+    # standing / tracking workload next to the random policy: the action of embodied_pose IS the PD target (clamp(action, q +- lim),
+    # humanoid_smpl_im.py:391-396), so feeding the current MoCap target pose makes the humanoid track its reference motion
+    track = torch.zeros(envs, task.num_actions, device=task.device)
     task.reset()
-    for i in range(8):
-        task.step(zero)
-    ms_track = timed_steps(lambda i: task.step(zero), min(K, 24), flush)   # within the 32 frames that follow the sampled start times
-    fallen_track = int(task.reset_buf.sum())
+
+    def track_step(i):
+        track[:, :task.num_dof].copy_(task._target_dof_pos)
+        task.step(track)
+    for i in range(4):
+        track_step(i)
+    ms_track = timed_steps(track_step, min(K, 24), flush)   # within the 32 frames that follow the sampled start times
+    fallen_track = int(task._terminate_buf.sum())
     total = sum(ms)
     return {"amass_im_env_steps_per_s": envs * K / (total * 1e-3), "amass_im_ms_per_step": total / K, "amass_im_physics_kernel_ms": phys_ms,
             "amass_im_roofline_frac_hbm": ALGO_BYTES_CFG2 * envs / (total / K * 1e-3) / 1e9 / peaks()[0],
-            "amass_im_envs_flagged_reset_at_end": resets,
+            "amass_im_envs_terminated_at_end": resets,
             "amass_im_tracking_env_steps_per_s": envs * len(ms_track) / (sum(ms_track) * 1e-3),
-            "amass_im_tracking_envs_flagged_reset": fallen_track,
+            "amass_im_tracking_envs_terminated": fallen_track,
             "amass_im_workload": f"embodied_pose amass_im: {envs} envs/GPU, 24 bodies / 69 dof, synthetic MoCap 64x300 frames, dt 1/60 x 2 x substeps 2, "
-                                 f"random policy U(-1,1) with reset(all) every {HORIZON} steps; `tracking` = zero action (PD targets at the MoCap pose)"}
+                                 f"random policy U(-1,1) with reset(all) every {HORIZON} steps; `tracking` = PD targets at the MoCap target pose (standing / tracking humanoids)"}
 
 
 def dual_leg(envs, device_index, rank, K, W, flush):

@@ -8,7 +8,7 @@ thread_local int emu_lane = 0;
 
 #include "../../vid2player3d_b200/csrc/dyn_common.cuh"
 #ifdef EMU_PACKED3
-#include "../../vid2player3d_b200/csrc/packed3.cuh"
+#include "../../tools/variants/packed3.cuh"
 #define EMU_EPW EPW3
 #define EMU_LPE LPE3
 #define EMU_BALL_SLOT BALL_SLOT3

@@ -11,7 +11,7 @@
 // Same records, same model, same oracle; results differ from packed.cuh by rounding only (a symmetric block is assembled from one
 // column per lane).
 #pragma once
-#include "packed.cuh"
+#include "../../vid2player3d_b200/csrc/packed.cuh"
 
 #define EPW3 2        // envs per warp
 #define LPE3 16       // lanes per env

@@ -420,7 +420,14 @@ __device__ __forceinline__ void control_step(const DevBlob& B, const float* vert
 }
 
 #include "packed.cuh"
-#include "packed3.cuh"
+// A/B variants that lost their measurements live outside the product build: -DB200ENV_WITH_PACKED3=1 compiles the
+// 2-envs-per-warp / 3-lanes-per-body kernel of tools/variants/packed3.cuh back in (B200ENV_KERNEL=packed3; 16 % slower, profiles/r1j, r2a)
+#ifndef B200ENV_WITH_PACKED3
+#define B200ENV_WITH_PACKED3 0
+#endif
+#if B200ENV_WITH_PACKED3
+#include "../../tools/variants/packed3.cuh"
+#endif
 
 // ------------------------------------------------------------------------------------------
 // TMA bulk load of the constant block into shared memory (one elected thread issues it)
@@ -1217,6 +1224,7 @@ __global__ void sort_perm_kernel(int num_envs, const int32_t* __restrict__ bin, 
 }
 
 // ------------------------------------------------------------------------------------------
+#if B200ENV_WITH_PACKED3
 // packed3 form of the middle launch (pre_kernel -> this -> post_kernel): 2 envs per warp, 14 warps per CTA (csrc/packed3.cuh).
 // Same shared-memory footprint and the same 28 envs per CTA batch as step_kernel_packed<split>; twice the warps.
 #ifndef PK3_WARPS
@@ -1314,6 +1322,8 @@ step_kernel_packed3(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, cons
     __syncwarp();
   }
 }
+#endif  // B200ENV_WITH_PACKED3
+
 
 template <typename T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
@@ -1802,9 +1812,13 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   h->split = h->packed && !(sv && strcmp(sv, "0") == 0);
   // packed3 (2 envs per warp, 3 lanes per body in the backward pass; csrc/packed3.cuh): needs the split form and at most 5 bodies
   // per tree depth.  B200ENV_KERNEL=packed3 selects it (A/B against the 4-envs-per-warp kernel, profiles/).
+#if B200ENV_WITH_PACKED3
   int wide = 0;
   for (int d = 0; d < MAX_LEVELS; d++) if (hb.t.lvl_all[d][SLOTS3] >= 0) wide = 1;
   h->packed3 = h->split && !wide && kv && strcmp(kv, "packed3") == 0;
+#else
+  h->packed3 = 0;
+#endif
   const char* so = getenv("B200ENV_SORT");
   h->sort = h->split && !h->packed3 && so && strcmp(so, "1") == 0;
   if (cfg->has_ball && cfg->ball_body_contact && !h->packed) {
@@ -1900,10 +1914,13 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
       CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
       CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
       int per_sm = 0, sms = 0;
+#if B200ENV_WITH_PACKED3
       if (h->packed3) {
         CUDA_OK(cudaFuncSetAttribute(step_kernel_packed3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed3, PK3_WARPS * 32, psmem));
-      } else if (h->split) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<true>, PK_WARPS * 32, psmem)); }
+      } else
+#endif
+      if (h->split) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<true>, PK_WARPS * 32, psmem)); }
       else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<false>, PK_WARPS * 32, psmem)); }
       CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
       h->step_grid = per_sm * sms < need ? per_sm * sms : need;
@@ -1935,10 +1952,12 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
         if (cudaEventCreate(&tv0) == cudaSuccess && cudaEventCreate(&tv1) == cudaSuccess) cudaEventRecord(tv0, (cudaStream_t)stream);
         else tv0 = tv1 = nullptr;
       }
+#if B200ENV_WITH_PACKED3
       if (h->packed3)
         step_kernel_packed3<<<h->step_grid, PK3_WARPS * 32, psmem, (cudaStream_t)stream>>>(
             (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->num_envs, h->d_ticket, h->env_first, h->env_stride, h->d_ext);
       else
+#endif
         step_kernel_packed<true><<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>(
             (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->ml, actions, h->num_envs, h->d_ticket, h->env_first,
             h->env_stride, h->d_ext, h->sort ? h->d_perm : nullptr);
