@@ -113,12 +113,12 @@ class ClockSampler:
 
 
 # ================================================================================================ workloads
-def federer_env(envs, device_index, seed=10, policy="b200nn", player="stream+decoder"):
+def federer_env(envs, device_index, seed=10, policy="b200nn", player="stream+decoder", **v2p_over):
     import torch
     from vid2player3d_b200.configs import SIM_PARAMS, v2p_cfg
     from vid2player3d_b200.tasks import PhysicsMVAEController
     torch.manual_seed(seed)
-    cfg = v2p_cfg(envs)
+    cfg = v2p_cfg(envs, **v2p_over)
     cfg["seed"] = seed
     cfg["env"]["motion_player"] = player
     cfg["env"]["low_level_policy"] = policy
@@ -402,7 +402,8 @@ def _cpu_worker(conn, n, seed, threads):
     model = model_compiler.canonical_racket_last(model_compiler.load_compiled("smpl_mesh_humanoid_federer"))
     ms, verts = abi.pack_model(model, float(model["mass"].sum()) / 90.0)
     cfg = abi.make_cfg(model, substeps=6, task_mode=1, pd_mode=1, contact_bodies=(), key_bodies=(), enable_early_termination=False,
-                       ball=dict(spin_scale=5.0, ball_e_racket=0.9, ball_e_ground=0.7, ball_mu_racket=0.5, ball_mu_ground=0.6))
+                       ball=dict(spin_scale=5.0, ball_e_racket=0.9, ball_e_ground=0.7, ball_mu_racket=0.5, ball_mu_ground=0.6, ball_body_contact=1,
+                                 ball_e_body=0.45, ball_mu_body=0.6))
     names = [str(x) for x in model["body_names"]][:24]
     s2m = np.array([SMPL_NAMES.index(q) for q in names])
     rest = np.zeros((24, 3))

@@ -7,7 +7,9 @@ import torch
 import bench
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-env = bench.federer_env(N, 0)
+BB = os.environ.get("BALL_BODY")          # A/B of vid2player.ball_body_contact: BALL_BODY=0 / 1
+env = bench.federer_env(N, 0, **({"ball_body_contact": BB == "1"} if BB is not None else {}))
+print("ball_body_contact:", env._physics_player.task._cfg_struct.ball_body_contact)
 dev = env.device
 task = env._physics_player.task
 acts = [torch.clamp(torch.randn(N, env.num_actions, device=dev), -5, 5) for _ in range(8)]

@@ -13,6 +13,7 @@
                                // per 8192-env step on B200 (profiles/r2a_ab.md); 0 keeps the in-place form for A/B
 #endif
 #define EPW 4     // envs per warp
+#define BALL_SLOT 7   // the ball of env g is carried by lane (g, BALL_SLOT) in registers
 #define SLOTS 8   // lanes per env
 #define PK_LANES_PER_ENV SLOTS
 // Record layout (element offsets).  Records are 16-byte aligned (REC % 4 == 0, ENV_STRIDE % 4 == 0) and the fields that are
@@ -536,9 +537,106 @@ __device__ __forceinline__ void pk_ball_contacts_extra(const DevBlob& B, const f
   }
 }
 
+// The same contacts with the body loop spread over the 8 lanes of the env's group (the serial form on the ball's lane costs the whole
+// warp ~1 000 instructions per substep: +170 us per 8192-env step of config 3, profiles/r2m_ball_body.md).  Every lane of the warp calls
+// this (the shuffles are warp-wide); lane (g, s) tests bodies s, s + 8, s + 16, (24) of env g against the ball its group's lane
+// BALL_SLOT carries, the deepest contact wins (ties: the lower body index, as in the serial loop) and the ball's lane applies it.
+template <typename T>
+__device__ __forceinline__ void pk_ball_contacts_group(const DevBlob& B, const float* verts, const PhysCfg<T>& c, const T* env, int lane, bool valid,
+                                                       Ball<T>& ball) {
+  const b200_model_t& M = B.m;
+  const int s = lane & 7, src = (lane & ~7) | BALL_SLOT;
+  T bp[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) bp[k] = __shfl_sync(FULL, ball.p[k], src);
+  bool near = valid;
+  if (near) {
+    T rp[3];
+    ldr<R_P, 3>(env, rp);   // the root is record 0
+    const T dx = bp[0] - rp[0], dy = bp[1] - rp[1], dz = bp[2] - rp[2];
+    near = dx * dx + dy * dy + dz * dz <= T(2.25);       // nothing of the player beyond 1.5 m of the pelvis
+  }
+  T best = T(0), bn[3] = {T(0), T(0), T(1)}, bvo[3] = {T(0), T(0), T(0)}, be = c.eb, bmu = c.mub;
+  int bbody = 1 << 20;
+  if (near) {
+    for (int b = s; b < M.nb; b += SLOTS) {
+      const bool handle = b == c.racket_body && c.hdl[6] > T(0);
+      const int nv = M.nverts[b];
+      if (nv == 0 && !handle) continue;
+      T st[13];   // Q[4] p[3] w[3] v[3]
+      ldr<R_Q, 13>(env + RIX(B, b) * REC, st);
+      const T *Q = st, *p = st + 4, *w = st + 7, *v = st + 10;
+      const T d[3] = {bp[0] - p[0], bp[1] - p[1], bp[2] - p[2]};
+      const T d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+      const T reach = handle ? T(0.6) : T(M.radius[b]) + T(B.t.vrho[b]) + c.bR;
+      if (d2 > reach * reach) continue;
+      const T cq[4] = {-Q[0], -Q[1], -Q[2], Q[3]};
+      T dl[3], el[3] = {T(0), T(0), T(0)}, dist = T(0), rad = T(0);
+      qrot(cq, d, dl);   // ball centre in the body frame
+      if (handle) {
+        const T a[3] = {c.hdl[3] - c.hdl[0], c.hdl[4] - c.hdl[1], c.hdl[5] - c.hdl[2]};
+        const T q0[3] = {dl[0] - c.hdl[0], dl[1] - c.hdl[1], dl[2] - c.hdl[2]};
+        T t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) * rcp_(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t);
+#pragma unroll
+        for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
+        dist = sqrt_(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
+        rad = c.hdl[6];
+      } else {
+        const float* vb = verts + (size_t)b * M.vmax * 3;
+        T m2 = T(1e30);
+        for (int k = 0; k < nv; k++) {
+          const T ex = dl[0] - T(vb[k]), ey = dl[1] - T(vb[M.vmax + k]), ez = dl[2] - T(vb[2 * M.vmax + k]);
+          const T e2 = ex * ex + ey * ey + ez * ez;
+          if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+        }
+        dist = sqrt_(m2);
+        rad = T(B.t.vrho[b]);
+      }
+      const T pen = c.bR + rad - dist;
+      if (pen > best && dist > T(1e-9)) {
+        best = pen;
+        bbody = b;
+        const T id = rcp_(dist);
+        const T nl[3] = {el[0] * id, el[1] * id, el[2] * id};
+        qrot(Q, nl, bn);
+        const T x[3] = {d[0] - c.bR * bn[0], d[1] - c.bR * bn[1], d[2] - c.bR * bn[2]};   // contact point relative to the body origin
+        T wxx[3];
+        cross3(w, x, wxx);
+#pragma unroll
+        for (int k = 0; k < 3; k++) bvo[k] = v[k] + wxx[k];
+        be = handle ? c.er : c.eb;
+        bmu = handle ? c.mur : c.mub;
+      }
+    }
+  }
+  // deepest contact of the group (butterfly over the 8 lanes; equal depths: the lower body index, like the serial loop); skipped by
+  // the whole warp when no lane found a contact (the common substep)
+  if (!__any_sync(FULL, best > T(0))) return;
+#pragma unroll
+  for (int off = 1; off < SLOTS; off <<= 1) {
+    const T opn = __shfl_xor_sync(FULL, best, off);
+    const int obd = __shfl_xor_sync(FULL, bbody, off);
+    T on[3], ov[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { on[k] = __shfl_xor_sync(FULL, bn[k], off); ov[k] = __shfl_xor_sync(FULL, bvo[k], off); }
+    const T oe = __shfl_xor_sync(FULL, be, off), om = __shfl_xor_sync(FULL, bmu, off);
+    if (opn > best || (opn == best && obd < bbody)) {
+      best = opn; bbody = obd; be = oe; bmu = om;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { bn[k] = on[k]; bvo[k] = ov[k]; }
+    }
+  }
+  if (valid && s == BALL_SLOT && best > T(0)) {
+    T J[3];
+    ball_impulse(c, ball, bn, bvo, be, bmu, J);
+#pragma unroll
+    for (int k = 0; k < 3; k++) ball.p[k] += best * bn[k];
+  }
+}
+
 // One control step for the warp's EPW envs.  wrec: the warp's records; valid: this lane's env exists.
 // The ball of env g is carried by lane (g, BALL_SLOT) in registers.
-#define BALL_SLOT 7
 template <typename T>
 __device__ __forceinline__ void control_step_packed(const DevBlob& B, const float* verts, const PhysCfg<T>& c, T* wrec, int lane, bool valid,
                                                     Ball<T>& ball, bool cta_sync) {
@@ -606,13 +704,13 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
           for (int k = 0; k < 3; k++) { rp[k] = rs[4 + k]; rw[k] = rs[7 + k]; rv[k] = rs[10 + k]; }
         }
         ball_substep<T>(c, ball, has_racket, rQ, rp, rv, rw);
-        if (c.ball_body) pk_ball_contacts_extra<T>(B, verts, c, env, ball);
         T* ext = env + ENV_EXT;
 #pragma unroll
         for (int k = 0; k < 3; k++) { ext[6 + k] = ball.rF[k]; ext[9 + k] = ball.rX[k]; }
       }
+      if (c.ball_body) pk_ball_contacts_group<T>(B, verts, c, env, lane, valid, ball);   // all lanes: the body loop is spread over the group
       if (valid && s == 0) pk_root<T>(c, env);
-      if (c.ball_body) __syncwarp();   // the extra ball contacts read the root's pose: integrate it only after the ball lane is done
+      if (c.ball_body) __syncwarp();   // the extra ball contacts read the root's pose: integrate it only after every lane is done
       if (valid && s == 0) pk_root_integrate<T>(c, env);
       __syncwarp();
       // 4. root -> leaves: accelerations + joint integration of a body, then at once its kinematics for the next substep

@@ -106,9 +106,11 @@ class HumanoidSMPLIMMVAE(BaseTask):
         ball["ball_e_ground"] = 0.5 * (rest + plane_rest)                        # PhysX average combine
         ball["ball_mu_racket"] = 0.5 * (v2p.get("racket_friction", 0.8) + v2p.get("ball_friction", 0.2))
         ball["ball_mu_ground"] = 0.5 * (env.get("plane", {}).get("dynamicFriction", 1.0) + v2p.get("ball_friction", 0.2))
-        # optional (B200 addition, default off): the ball also collides with the humanoid's bodies and the racket handle, as it does in
-        # the reference's PhysX scene (ball collision filter 0, :436-442); include/b200env.h `ball_body_contact`
-        if v2p.get("ball_body_contact", False):
+        # the ball also collides with the humanoid's bodies and the racket handle, as it does in the reference's PhysX scene (ball
+        # collision filter 0, :436-442); include/b200env.h `ball_body_contact`.  On by default since round 2 (the body loop runs on the
+        # 8 lanes of the env's group: +59 us per 8192-env step of config 3 without the any-contact skip, profiles/r2m_ball_body.md);
+        # vid2player.ball_body_contact: False switches it off
+        if v2p.get("ball_body_contact", True):
             ball["ball_body_contact"] = 1
             ball["ball_e_body"] = 0.5 * rest                                      # body shapes: default material (restitution 0, friction 1)
             ball["ball_mu_body"] = 0.5 * (1.0 + v2p.get("ball_friction", 0.2))
