@@ -590,7 +590,7 @@ def main():
         env.reset_done()                                           # reset(finished envs) from the device flags: mask + one graph replay
     for i in range(4):
         step_ids(i)
-    env.enable_cuda_graph()
+    env.enable_cuda_graph(count_nodes=True)
     for i in range(W):
         step_ids(i)
     barrier()
@@ -703,6 +703,7 @@ def main():
     free = lambda: (torch.cuda.synchronize(), torch.cuda.empty_cache())   # noqa: E731
     step_launches = task._env.launch_count - launches0
     graph_nodes = getattr(env, "graph_kernel_nodes", None)
+    reset_nodes = getattr(env, "reset_graph_kernel_nodes", None)
     del env, task
     free()
 
@@ -759,9 +760,12 @@ def main():
                        "taken from the HOST flags every step (strict)", "ms_per_step": e2e_ms / K,
                 "value_pipelined": total_envs * K / (e2e_pipe_ms * 1e-3),
                 "pipelined": "same calls and bytes, action upload of step t+1 on a side stream under step t, flags of step t read while step t+1 runs"},
-        "gpu_launches": int(step_launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "traffic_note": "see profiles/r2*_federer_ncu.md for dram bytes of the physics launch (from a profile, not measured per run)",
+        "gpu_launches": int((graph_nodes + (reset_nodes or 0) + 1) * K) if graph_nodes else int(step_launches),
+        "gpu_launches_note": "kernel nodes of the step graph + the reset graph (+ the mask kernel) x timed steps, counted from the graphs' DOT dumps; "
+                             "our own kernels among them per step: 22 (step graph) + 7 (reset graph)",
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": 8026112,
+                     "traffic_note": "from_profile: dram__bytes_read.sum + dram__bytes_write.sum of ONE step_kernel_packed<split> launch (the dominant "
+                                     "kernel) in the ncu --set full capture profiles/r2i_step_kernel_ncu.md; not measured by this run",
                      "kernel": "one env step = one CUDA graph (motion targets, FK, 734-d obs, decoder + policy GEMMs, physics, post step); dominant launch "
                                "step_kernel_packed<split>", "kernel_ms": ms_step, "algorithmic_bytes_per_env_step": ALGO_BYTES_CFG3,
                      "dominant_kernel": {"name": "step_kernel_packed<split> (12 substeps + ball)", "ms": phys_ms, "launches_timed": 10,
@@ -771,7 +775,7 @@ def main():
                      "note": "latency / issue bound along the kinematic chain x 12 substeps, not HBM bound (DESIGN.md 5); the GEMMs of the step are "
                              "tensor-core work reported in DESIGN.md against the bf16 peak"},
         "value_hot_l2_back_to_back": total_envs * K / (hot_ms * 1e-3), "wall_s_timed_loop": wall, "resets_per_step": resets_per_step,
-        "target_env_steps_per_s_1gpu": 4.0e6, "cuda_graph_kernel_nodes_per_step": graph_nodes,
+        "target_env_steps_per_s_1gpu": 4.0e6, "cuda_graph_kernel_nodes_per_step": graph_nodes, "cuda_graph_kernel_nodes_per_reset": reset_nodes,
     }
     out.update(extra)
     if not args.no_cpu_baseline and world == 1:   # contract: the CPU baseline is timed at N = 1 only, on a bounded sample

@@ -618,7 +618,7 @@ class PhysicsMVAEController:
         self.physics_step()
         self.post_physics_step()
 
-    def enable_cuda_graph(self, warmup=3):
+    def enable_cuda_graph(self, warmup=3, count_nodes=False):
         """Capture one whole high-level step (motion generator + FK targets + obs + low-level policy + fused physics + fused
         post step: ~70 launches) into a CUDA graph; afterwards `step()` = one copy + one graph launch.  Requirements: the motion
         player and the low-level policy update their state in place and make no host synchronisation (true for the synthetic
@@ -635,11 +635,14 @@ class PhysicsMVAEController:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        if count_nodes:
+            g.enable_debug_mode()
         with torch.cuda.graph(g):
             self.pre_physics_step(self._graph_actions)
             self.physics_step()
             self.post_physics_step()
         self._graph = g
+        self.graph_kernel_nodes = self._count_kernel_nodes(g) if count_nodes else None
         if hasattr(self._mvae_player, "reset_masked"):
             # second graph: the whole env reset, mask-driven (needs a graph-safe motion player)
             self._reset_mask = torch.zeros(self.num_envs, device=self.device, dtype=torch.bool)
@@ -648,9 +651,26 @@ class PhysicsMVAEController:
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             rg = torch.cuda.CUDAGraph()
+            if count_nodes:
+                rg.enable_debug_mode()
             with torch.cuda.graph(rg):
                 self._reset_envs_masked(self._reset_mask)
             self._reset_graph = rg
+            self.reset_graph_kernel_nodes = self._count_kernel_nodes(rg) if count_nodes else None
+
+    @staticmethod
+    def _count_kernel_nodes(graph):
+        """kernel nodes of a captured graph, from its DOT dump (measurement aid: bench `gpu_launches`)"""
+        import os
+        import tempfile
+        path = os.path.join(tempfile.gettempdir(), f"b200_graph_{os.getpid()}_{id(graph)}.dot")
+        try:
+            graph.debug_dump(path)
+            txt = open(path).read()
+            os.remove(path)
+            return sum(1 for line in txt.splitlines() if "label=" in line and ("KERNEL" in line.upper() or "kernel" in line)) or None
+        except Exception:
+            return None
 
     def get_aux_losses(self, model_res_dict):
         """:461-472 (autograd-carrying, PyTorch)"""
