@@ -635,14 +635,12 @@ class PhysicsMVAEController:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        if count_nodes:
-            g.enable_debug_mode()
         with torch.cuda.graph(g):
             self.pre_physics_step(self._graph_actions)
             self.physics_step()
             self.post_physics_step()
         self._graph = g
-        self.graph_kernel_nodes = self._count_kernel_nodes(g) if count_nodes else None
+        self.graph_kernel_nodes = self.reset_graph_kernel_nodes = None
         if hasattr(self._mvae_player, "reset_masked"):
             # second graph: the whole env reset, mask-driven (needs a graph-safe motion player)
             self._reset_mask = torch.zeros(self.num_envs, device=self.device, dtype=torch.bool)
@@ -651,24 +649,33 @@ class PhysicsMVAEController:
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             rg = torch.cuda.CUDAGraph()
-            if count_nodes:
-                rg.enable_debug_mode()
             with torch.cuda.graph(rg):
                 self._reset_envs_masked(self._reset_mask)
             self._reset_graph = rg
-            self.reset_graph_kernel_nodes = self._count_kernel_nodes(rg) if count_nodes else None
+        if count_nodes:      # measurement aid (bench `gpu_launches`): the same launch sequences run eagerly once under the CUDA profiler
+            def step_once():
+                self.pre_physics_step(self._graph_actions)
+                self.physics_step()
+                self.post_physics_step()
+            self.graph_kernel_nodes = self._count_kernels(step_once)
+            if getattr(self, "_reset_graph", None) is not None:
+                self._reset_mask.zero_()
+                self.reset_graph_kernel_nodes = self._count_kernels(lambda: self._reset_envs_masked(self._reset_mask))
 
     @staticmethod
-    def _count_kernel_nodes(graph):
-        """kernel nodes of a captured graph, from its DOT dump (measurement aid: bench `gpu_launches`)"""
-        import os
-        import tempfile
-        path = os.path.join(tempfile.gettempdir(), f"b200_graph_{os.getpid()}_{id(graph)}.dot")
+    def _count_kernels(fn):
+        """number of kernels `fn` launches (CUPTI through torch.profiler; memcpy / memset activities are not counted)"""
         try:
-            graph.debug_dump(path)
-            txt = open(path).read()
-            os.remove(path)
-            return sum(1 for line in txt.splitlines() if "label=" in line and ("KERNEL" in line.upper() or "kernel" in line)) or None
+            from torch.profiler import ProfilerActivity, profile
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                fn()
+                torch.cuda.synchronize()
+            n = 0
+            for e in prof.events():
+                if str(getattr(e, "device_type", "")).endswith("CUDA") and not any(t in e.name for t in ("Memcpy", "Memset", "memcpy", "memset")):
+                    n += 1
+            return n or None
         except Exception:
             return None
 
