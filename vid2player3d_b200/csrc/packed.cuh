@@ -12,6 +12,9 @@
 #define PK_CONTACT_COMPACT 1   // 1: per-vertex ground contact as a compacted phase of its own (pk_contact_phase); bit-identical, 291.9 -> 283.8 us
                                // per 8192-env step on B200 (profiles/r2a_ab.md); 0 keeps the in-place form for A/B
 #endif
+#ifndef PK_SYNC_EVERY
+#define PK_SYNC_EVERY 1   // CTA barrier every n-th substep (keeps the CTA's warps on the same instruction-cache lines); A/B in profiles/r2n
+#endif
 #define EPW 4     // envs per warp
 #define BALL_SLOT 7   // the ball of env g is carried by lane (g, BALL_SLOT) in registers
 #define SLOTS 8   // lanes per env
@@ -660,7 +663,7 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
       }
     }
     for (int sub = 0; sub < c.substeps; sub++) {
-      if (cta_sync) __syncthreads();
+      if (cta_sync && (PK_SYNC_EVERY == 1 || (sub % PK_SYNC_EVERY) == 0)) __syncthreads();
       // 1. per-body inertia / bias / contacts / joint drive
       for (int rr = 0; rr * SLOTS < (ABL == 8 ? 0 : nb); rr++) {
         const int b = rr * SLOTS + s;
