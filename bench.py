@@ -94,6 +94,18 @@ class ClockSampler:
                 return
             time.sleep(self.period)
 
+    def sample_now(self):
+        """one sample from the calling thread (the timed loop calls it between two launches: the GPU is busy with the previous step,
+        the host thread is not - the background thread alone can be starved of the GIL by the launch loop)"""
+        if self.nv is None:
+            return
+        try:
+            nv = self.nv
+            self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                              if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+        except Exception as ex:
+            self.err = repr(ex)[:120]
+
     def start(self):
         if self.nv is not None:
             self.th = threading.Thread(target=self._loop, daemon=True)
@@ -109,7 +121,7 @@ class ClockSampler:
         for r in self.rows:
             bits |= int(r[1])
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
-                "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "source": "NVML in-process, %.0f ms period" % (self.period * 1e3)}
+                "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "source": "NVML in-process: one sample per timed step from the launch loop + a %.0f ms background thread" % (self.period * 1e3)}
 
 
 # ================================================================================================ workloads
@@ -139,11 +151,13 @@ def amass_task(envs, device_index, seed, asset="smpl_mesh_humanoid_amass_v1"):
     return model, flat, task
 
 
-def timed_steps(step_fn, K, flush):
+def timed_steps(step_fn, K, flush, sampler=None):
     """K calls of step_fn(i), each between two CUDA events, L2 flushed before each (outside the pair) -> list of ms"""
     import torch
     evs = []
     for i in range(K):
+        if sampler is not None and i > 0:
+            sampler.sample_now()           # while step i-1 runs on the GPU
         if flush is not None:
             flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -609,7 +623,7 @@ def main():
     prof = os.environ.get("B200_BENCH_PROFILE") == "1"      # tools/federer_launches.sh: ncu --profile-from-start off sees the timed loop only
     if prof:
         torch.cuda.cudart().cudaProfilerStart()
-    step_ms = timed_steps(step, K, flush)
+    step_ms = timed_steps(step, K, flush, sampler)
     barrier()
     if prof:
         torch.cuda.cudart().cudaProfilerStop()
