@@ -137,7 +137,7 @@ def test_physics_f32_random_one_step(model, small_lib):
           f"contact force max {np.abs(o[4]).max():.0f} N")
     assert np.abs(o[4]).max() > 50.0
     assert eq.max() < 1e-4
-    assert np.quantile(ev, 0.95) < 5e-3
+    assert np.quantile(ev, 0.95) < 5e-4 and ev.max() < 2e-3     # measured on B200 (round 2): p95 5.5e-5, max 2.1e-4
 
 
 def test_motion_state_golden():

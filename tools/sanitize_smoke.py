@@ -49,3 +49,15 @@ for _ in range(2):
     dual._reset_envs_masked(m)
 torch.cuda.synchronize()
 print("dual masked reset done", bool(torch.isfinite(dual.obs_buf).all()))
+# round 2: the tcgen05 layers and the fused step glue (policy + decoder in the step, masked reset through reset_done)
+cfg = v2p_cfg(40)
+cfg["env"]["motion_player"], cfg["env"]["low_level_policy"] = "stream+decoder", "b200nn"
+env2 = PhysicsMVAEController(cfg, SIM_PARAMS, 1, "cuda", 0, True)
+env2.reset()
+for i in range(3):
+    env2.step(torch.clamp(torch.randn(40, env2.num_actions, device=env2.device), -5, 5))
+    m = torch.zeros(40, dtype=torch.bool, device=env2.device)
+    m[i::7] = True
+    env2._reset_envs_masked(m)
+torch.cuda.synchronize()
+print("fused step + b200nn done", bool(torch.isfinite(env2.obs_buf).all()), bool(torch.isfinite(env2._low_level_policy.out).all()))
