@@ -202,3 +202,64 @@ def test_energy_drift_is_first_order(setup):
         drifts.append(abs((ke1 + pe1) - (ke0 + pe0)) / (ke0 + abs(pe0)))
     assert drifts[0] < 5e-2
     assert 0.3 < drifts[1] / drifts[0] < 0.7 and 0.3 < drifts[2] / drifts[1] < 0.7, drifts
+
+
+def test_ground_contact_against_analytic_coulomb_friction(setup):
+    """the compliant-implicit ground contact against textbook physics: a humanoid held rigid by stiff PD (a ragdoll locked in its pose),
+    lying on the ground and pushed along +x at 2 m/s, (a) carries exactly its weight, (b) decelerates at mu g = 9.81 m/s^2 while it
+    slides (regularised Coulomb friction, mu = 1 from the yaml), (c) comes to rest and stays there (stick)."""
+    from vid2player3d_b200 import abi
+    from oracle import physics_ref as P
+    mod, _, _ = setup
+    m, verts = abi.pack_model(mod, 50.0)                      # very stiff joints: the body behaves as one rigid piece
+    cfg = abi.make_cfg(mod, substeps=8)
+    g = 9.81
+    root = np.zeros((1, 13))
+    root[0, 2], root[0, 3:7] = 0.3, [0.0, 0.0, 0.0, 1.0]      # lying (the asset is y-up in its body frame): drop from 30 cm and settle
+    q, qd, tar = np.zeros((1, 69)), np.zeros((1, 69)), np.zeros((1, 69))
+    P.control_step(m, verts, cfg, root, q, qd, tar, n_steps=90)
+    assert abs(root[0, 9]) < 2e-2 and np.abs(root[0, 7:9]).max() < 2e-2, "did not settle"
+    rb, cf = P.control_step(m, verts, cfg, root, q, qd, tar, n_steps=1)
+    weight = float(mod["mass"].sum()) * g
+    assert abs(cf[0, :, 2].sum() - weight) < 0.02 * weight
+    root[0, 7] = 2.0                                          # push
+    vs = [2.0]
+    for _ in range(12):                                       # 12 control steps = 0.4 s; mu g dt = 0.327 m/s per control step
+        P.control_step(m, verts, cfg, root, q, qd, tar, n_steps=1)
+        vs.append(root[0, 7])
+    vs = np.array(vs)
+    sliding = vs[1:] > 0.4                                    # well above the regularisation speed v_s = 0.05 m/s
+    dec = -(vs[1:] - vs[:-1]) / (2 * (1 / 60.0))
+    assert sliding.sum() >= 3
+    assert np.all(np.abs(dec[sliding] - g) < 0.15 * g), dec
+    assert abs(vs[-1]) < 0.05, vs                             # stuck
+
+
+def test_ball_bounce_and_drag_against_closed_forms():
+    """the ball model against closed forms: (a) a vertical drop rebounds with the restitution the scene's materials give (PhysX 'average'
+    of the ball 0.9 and the plane 0.5 = 0.7, humanoid_smpl_im_mvae.py:414-438), (b) with no spin the horizontal deceleration in flight is
+    the quadratic drag k_f C_d |v| v / m of apply_external_force_to_ball (:711-739; C_d 0.55, rho 1.204 kg/m^3, r 0.032 m, m 0.057 kg)"""
+    from vid2player3d_b200 import abi, model_compiler
+    from oracle import physics_ref as P
+    mod = model_compiler.canonical_racket_last(model_compiler.load_compiled("smpl_mesh_humanoid_federer"))
+    m, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    cfg = abi.make_cfg(mod, substeps=6, task_mode=1, pd_mode=1, contact_bodies=(), key_bodies=(), enable_early_termination=False,
+                       ball=dict(spin_scale=5.0, ball_e_ground=0.7, ball_mu_ground=0.6, ball_e_racket=0.9, ball_mu_racket=0.5))
+    root = np.zeros((1, 13)); root[0, :3] = [50.0, 50.0, 0.95]; root[0, 3:7] = [0.5, 0.5, 0.5, 0.5]     # the player far away from the ball
+    q, qd, tar = np.zeros((1, 69)), np.zeros((1, 69)), np.zeros((1, 69))
+    ball = np.zeros((1, 13)); ball[0, :3] = [0.0, 0.0, 1.0]; ball[0, 6] = 1.0
+    vz = []
+    for _ in range(40):
+        P.control_step(m, verts, cfg, root, q, qd, tar, ball=ball, hits=np.zeros(1, np.int32))
+        vz.append(ball[0, 9])
+    vz = np.array(vz)
+    i = int(np.argmax(vz))                       # first step after the bounce: largest upward speed
+    v_in = -vz[i - 1]
+    assert v_in > 3.0 and abs(vz[i] / v_in - 0.7) < 0.06, (v_in, vz[i])
+    ball[:] = 0; ball[0, :3] = [0.0, 0.0, 30.0]; ball[0, 6] = 1.0; ball[0, 7] = 25.0      # fast, high, no spin
+    v0 = ball[0, 7]
+    P.control_step(m, verts, cfg, root, q, qd, tar, ball=ball, hits=np.zeros(1, np.int32))
+    dt = 1.0 / 30.0
+    kf = 1.204 * np.pi * 0.032 ** 2 / 2
+    a_drag = kf * 0.55 * v0 * v0 / 0.057
+    assert abs((v0 - ball[0, 7]) / dt - a_drag) < 0.1 * a_drag, ((v0 - ball[0, 7]) / dt, a_drag)
