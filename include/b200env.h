@@ -91,8 +91,8 @@ typedef struct b200_cfg {
   float racket_head_quat[4]; /* xyzw, racket frame -> head frame whose +y is the string-bed normal: identity for the right-handed
                                 assets, 45 deg about x for nadal.xml's cylinder fromto="0 -.015 -.015 0 .015 .015" */
   /* --- optional: the other contacts of the ball (in the reference the ball collides with every shape of the env: collision filter 0,
-   * humanoid_smpl_im_mvae.py:436-442).  Default off.  Bodies: every convex-hull vertex is a sphere of a per-body radius (half the mean
-   * vertex spacing); handle: the cylinder fromto="0.5 0 0 0.15 0 0" size 0.016 of the Racket body as a capsule.  The deepest contact of
+   * humanoid_smpl_im_mvae.py:436-442).  Default off.  Bodies: exact sphere / convex-hull query against the faces installed with
+   * b200env_set_hull_faces (a body without faces: every hull vertex is a sphere of half the mean vertex spacing); handle: the cylinder fromto="0.5 0 0 0.15 0 0" size 0.016 of the Racket body as a capsule.  The deepest contact of
    * a substep gets the impulse (restitution / Coulomb friction like the string bed); the obstacle is kinematic (no reaction on it). */
   int32_t ball_body_contact;
   float ball_e_body, ball_mu_body; /* PhysX "average" of the ball (0.9 / 0.2) and a default shape (0 / 1): 0.45, 0.6 */
@@ -224,6 +224,14 @@ int b200env_motion_context(b200env_handle h, const int64_t* env_ids, const int64
  * vid2player/env/tasks/humanoid_smpl_im_mvae.py:270-275 `motion_ids[1::2] = 1`): one handle per asset, all bound to the SAME
  * tensors; handle-local env i of b200env_step is row env_first + env_stride * i.  num_envs at create = envs of the slice. */
 int b200env_set_env_slice(b200env_handle h, int32_t env_first, int32_t env_stride);
+
+/* Faces of every body's convex hull, for the exact sphere / convex-hull query of the ball against the humanoid's bodies
+ * (cfg.ball_body_contact; PhysX collides the ball's sphere shape with the convex meshes of the asset the reference loads with
+ * default AssetOptions - one convex hull per mesh, vid2player/env/tasks/humanoid_smpl.py:277-283).  planes [nb, tmax, 4] float (outward unit normal n, offset d: n.x <= d
+ * inside), tris [nb, tmax, 4] uint8 (three vertex indices into the body's hull vertices, outward winding, one pad byte),
+ * ntris [nb] int32 (0: body keeps the sphere-per-vertex approximation).  HOST pointers; copied.  Without this call every body
+ * uses the approximation. */
+int b200env_set_hull_faces(b200env_handle h, const float* planes, const uint8_t* tris, const int32_t* ntris, int32_t tmax);
 
 /* number of kernels launched by this handle so far (bench.py "gpu_launches") */
 int64_t b200env_launch_count(b200env_handle h);

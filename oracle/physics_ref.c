@@ -451,6 +451,88 @@ static void hull_vertex_radius_ref(const b200_model_t* model, const float* verts
   }
 }
 
+/* ---- exact sphere / convex-hull test (round 2).  The hull faces come with the compiled model (model_compiler.hull_faces: triangles with
+ * outward winding + their plane equations); phys_ref_set_hull_faces installs them (test infrastructure: a process-wide pointer).  A body
+ * without faces falls back to the round-1 stand-in (spheres on the hull vertices).
+ * Query for a ball centre c (body frame) and radius R: (1) s = max over the face planes of n.c - d: s > R separates exactly; (2) s <= 0: the
+ * centre is inside the hull: depth R - s along the least-penetrated face normal; (3) otherwise the closest point of the hull surface =
+ * the closest point over all triangles (Ericson, Real-Time Collision Detection 5.1.5): depth R - distance, normal from it to c. */
+static const float* g_planes = 0;     /* [nb][tmax][4] */
+static const unsigned char* g_tris = 0; /* [nb][tmax][4] (3 vertex indices + pad) */
+static const int32_t* g_ntris = 0;    /* [B200_MAX_BODIES] */
+static int g_tmax = 0;
+int phys_ref_set_hull_faces(const float* planes, const unsigned char* tris, const int32_t* ntris, int tmax) {
+  g_planes = planes; g_tris = tris; g_ntris = ntris; g_tmax = tmax;
+  return 0;
+}
+static void closest_on_triangle(const real* p, const real* a, const real* b, const real* c, real* q) {
+  real ab[3], ac[3], ap[3];
+  for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; }
+  real d1 = ab[0] * ap[0] + ab[1] * ap[1] + ab[2] * ap[2], d2 = ac[0] * ap[0] + ac[1] * ap[1] + ac[2] * ap[2];
+  if (d1 <= 0 && d2 <= 0) { for (int k = 0; k < 3; k++) q[k] = a[k]; return; }
+  real bp[3];
+  for (int k = 0; k < 3; k++) bp[k] = p[k] - b[k];
+  real d3 = ab[0] * bp[0] + ab[1] * bp[1] + ab[2] * bp[2], d4 = ac[0] * bp[0] + ac[1] * bp[1] + ac[2] * bp[2];
+  if (d3 >= 0 && d4 <= d3) { for (int k = 0; k < 3; k++) q[k] = b[k]; return; }
+  real vc = d1 * d4 - d3 * d2;
+  if (vc <= 0 && d1 >= 0 && d3 <= 0) { real v = d1 / (d1 - d3); for (int k = 0; k < 3; k++) q[k] = a[k] + v * ab[k]; return; }
+  real cp[3];
+  for (int k = 0; k < 3; k++) cp[k] = p[k] - c[k];
+  real d5 = ab[0] * cp[0] + ab[1] * cp[1] + ab[2] * cp[2], d6 = ac[0] * cp[0] + ac[1] * cp[1] + ac[2] * cp[2];
+  if (d6 >= 0 && d5 <= d6) { for (int k = 0; k < 3; k++) q[k] = c[k]; return; }
+  real vb = d5 * d2 - d1 * d6;
+  if (vb <= 0 && d2 >= 0 && d6 <= 0) { real w = d2 / (d2 - d6); for (int k = 0; k < 3; k++) q[k] = a[k] + w * ac[k]; return; }
+  real va = d3 * d6 - d5 * d4;
+  if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+    real w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+    for (int k = 0; k < 3; k++) q[k] = b[k] + w * (c[k] - b[k]);
+    return;
+  }
+  real den = 1 / (va + vb + vc), v = vb * den, w = vc * den;
+  for (int k = 0; k < 3; k++) q[k] = a[k] + ab[k] * v + ac[k] * w;
+}
+/* returns 1 and (pen, outward unit normal nl in the body frame) when the sphere (c, R) touches the hull of body b */
+static int hull_sphere_ref(const b200_model_t* m, const float* verts, int b, const real* c, real R, real* pen, real* nl) {
+  const int nt = g_ntris[b];
+  const float* pl = g_planes + (size_t)b * g_tmax * 4;
+  const unsigned char* tr = g_tris + (size_t)b * g_tmax * 4;
+  const float* vb = verts + (size_t)b * m->vmax * 3;
+  real smax = -1e30;
+  int imax = 0;
+  for (int t = 0; t < nt; t++) {
+    real sd = (real)pl[t * 4] * c[0] + (real)pl[t * 4 + 1] * c[1] + (real)pl[t * 4 + 2] * c[2] - (real)pl[t * 4 + 3];
+    if (sd > R) return 0;                          /* separating plane */
+    if (sd > smax) { smax = sd; imax = t; }
+  }
+  if (smax <= 0) {
+    *pen = R - smax;
+    for (int k = 0; k < 3; k++) nl[k] = pl[imax * 4 + k];
+    return 1;
+  }
+  real best = 1e30, qb[3] = {0, 0, 0};
+  for (int t = 0; t < nt; t++) {
+    /* the closest point of a convex body to an outside point lies on a face the point sees: back faces skipped */
+    if (!((real)pl[t * 4] * c[0] + (real)pl[t * 4 + 1] * c[1] + (real)pl[t * 4 + 2] * c[2] - (real)pl[t * 4 + 3] > 0)) continue;
+    real a[3], bb[3], cc[3], q[3];
+    for (int k = 0; k < 3; k++) { a[k] = vb[tr[t * 4] * 3 + k]; bb[k] = vb[tr[t * 4 + 1] * 3 + k]; cc[k] = vb[tr[t * 4 + 2] * 3 + k]; }
+    closest_on_triangle(c, a, bb, cc, q);
+    real e2 = (c[0] - q[0]) * (c[0] - q[0]) + (c[1] - q[1]) * (c[1] - q[1]) + (c[2] - q[2]) * (c[2] - q[2]);
+    if (e2 < best) { best = e2; qb[0] = q[0]; qb[1] = q[1]; qb[2] = q[2]; }
+  }
+  real dist = sqrt(best);
+  if (!(dist < R) || dist <= 1e-9) return 0;
+  *pen = R - dist;
+  for (int k = 0; k < 3; k++) nl[k] = (c[k] - qb[k]) / dist;
+  return 1;
+}
+/* test hook: the query alone (body-frame centre) */
+int phys_ref_hull_sphere(const b200_model_t* m, const float* verts, int b, const double* c, double R, double* pen, double* nl) {
+  real p = 0, n[3] = {0, 0, 0}, cc[3] = {c[0], c[1], c[2]};
+  int hit = (g_planes && g_ntris[b] > 0) ? hull_sphere_ref(m, verts, b, cc, R, &p, n) : -1;
+  *pen = p; nl[0] = n[0]; nl[1] = n[1]; nl[2] = n[2];
+  return hit;
+}
+
 /* float64 restatement of csrc/packed.cuh::pk_ball_contacts_extra: the ball against the bodies (hull vertices as spheres) and the racket
  * handle (capsule), poses of the start of the substep, deepest contact only, kinematic obstacle */
 static void ball_contacts_extra_ref(const b200_model_t* m, const float* verts, const b200_cfg_t* cfg, const float* vrho, const body_t* B,
@@ -468,34 +550,40 @@ static void ball_contacts_extra_ref(const b200_model_t* m, const float* verts, c
     const body_t* bd = &B[b];
     real d[3] = {ball->p[0] - bd->p[0], ball->p[1] - bd->p[1], ball->p[2] - bd->p[2]};
     real d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-    real reach = handle ? (real)0.6 : (real)m->radius[b] + (real)vrho[b] + R;
+    real reach = handle ? (real)0.6 : (real)m->radius[b] + ((g_planes && g_ntris[b] > 0) ? (real)0 : (real)vrho[b]) + R;
     if (d2 > reach * reach) continue;
-    real dl[3], el[3] = {0, 0, 0}, dist = 0, rad = 0;
+    real dl[3], pen = 0, nl[3] = {0, 0, 1};
     q_rot_inv(bd->Q, d, dl);
-    if (handle) {
-      const float* hd = cfg->racket_handle;
-      real a[3] = {(real)hd[3] - hd[0], (real)hd[4] - hd[1], (real)hd[5] - hd[2]};
-      real q0[3] = {dl[0] - hd[0], dl[1] - hd[1], dl[2] - hd[2]};
-      real t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) / (a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-      t = t < 0 ? 0 : (t > 1 ? 1 : t);
-      for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
-      dist = sqrt(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
-      rad = hd[6];
+    if (!handle && g_planes && g_ntris[b] > 0) {     /* exact: the body's convex hull */
+      if (!hull_sphere_ref(m, verts, b, dl, R, &pen, nl)) continue;
     } else {
-      const float* vb = verts + (size_t)b * m->vmax * 3;
-      real m2 = 1e30;
-      for (int k = 0; k < nv; k++) {
-        real ex = dl[0] - vb[k * 3], ey = dl[1] - vb[k * 3 + 1], ez = dl[2] - vb[k * 3 + 2];
-        real e2 = ex * ex + ey * ey + ez * ez;
-        if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+      real el[3] = {0, 0, 0}, dist = 0, rad = 0;
+      if (handle) {
+        const float* hd = cfg->racket_handle;
+        real a[3] = {(real)hd[3] - hd[0], (real)hd[4] - hd[1], (real)hd[5] - hd[2]};
+        real q0[3] = {dl[0] - hd[0], dl[1] - hd[1], dl[2] - hd[2]};
+        real t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) / (a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        t = t < 0 ? 0 : (t > 1 ? 1 : t);
+        for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
+        dist = sqrt(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
+        rad = hd[6];
+      } else {                                         /* no faces installed: spheres on the hull vertices */
+        const float* vb = verts + (size_t)b * m->vmax * 3;
+        real m2 = 1e30;
+        for (int k = 0; k < nv; k++) {
+          real ex = dl[0] - vb[k * 3], ey = dl[1] - vb[k * 3 + 1], ez = dl[2] - vb[k * 3 + 2];
+          real e2 = ex * ex + ey * ey + ez * ez;
+          if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+        }
+        dist = sqrt(m2);
+        rad = vrho[b];
       }
-      dist = sqrt(m2);
-      rad = vrho[b];
+      pen = R + rad - dist;
+      if (!(dist > 1e-9)) continue;
+      nl[0] = el[0] / dist; nl[1] = el[1] / dist; nl[2] = el[2] / dist;
     }
-    real pen = R + rad - dist;
-    if (pen > best && dist > 1e-9) {
+    if (pen > best) {
       best = pen;
-      real nl[3] = {el[0] / dist, el[1] / dist, el[2] / dist};
       q_rot(bd->Q, nl, bn);
       real x[3] = {d[0] - R * bn[0], d[1] - R * bn[1], d[2] - R * bn[2]}, wxx[3];
       cross(bd->w, x, wxx);

@@ -57,6 +57,33 @@ def control_step(model, verts, cfg, root, dof_pos, dof_vel, pd_tar, ext_wrench=N
     return rb, cf
 
 
+_faces_keep = None
+
+
+def set_hull_faces(planes, tris, ntris, tmax):
+    """install the hull faces (abi.pack_faces) for the exact ball / body contact; process-wide, the arrays are kept alive here"""
+    global _faces_keep
+    planes, tris = np.ascontiguousarray(planes, np.float32), np.ascontiguousarray(tris, np.uint8)
+    ntris = np.ascontiguousarray(ntris, np.int32)
+    _faces_keep = (planes, tris, ntris)
+    lib().phys_ref_set_hull_faces(_p(planes), _p(tris), _p(ntris), C.c_int(int(tmax)))
+
+
+def clear_hull_faces():
+    global _faces_keep
+    _faces_keep = None
+    lib().phys_ref_set_hull_faces(None, None, None, C.c_int(0))
+
+
+def hull_sphere(model, verts, body, centre, radius):
+    """the exact query alone: (hit, penetration, outward normal) for a sphere at `centre` (body frame)"""
+    pen, nl = C.c_double(0.0), np.zeros(3)
+    verts = np.ascontiguousarray(verts, np.float32)
+    c = np.ascontiguousarray(centre, np.float64)
+    hit = lib().phys_ref_hull_sphere(C.byref(model), _p(verts), C.c_int(int(body)), _p(c), C.c_double(float(radius)), C.byref(pen), _p(nl))
+    return int(hit), pen.value, nl
+
+
 def set_threads(n):
     """OpenMP threads of the env loop; returns the previous count"""
     return int(lib().phys_ref_set_threads(C.c_int(int(n))))

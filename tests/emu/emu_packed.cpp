@@ -126,6 +126,15 @@ template <typename T> void lane_main(EmuWarp* w, int lane, const Job<T>* J, int6
 }
 }  // namespace
 
+// hull faces of the exact ball / hull query (b200env_set_hull_faces on the product side): host arrays kept by the caller
+static const float* g_face_planes = nullptr;
+static const unsigned char* g_face_tris = nullptr;
+static const int32_t* g_face_ntris = nullptr;
+static int g_face_tmax = 0;
+extern "C" void emu_set_hull_faces(const float* planes, const unsigned char* tris, const int32_t* ntris, int tmax) {
+  g_face_planes = planes; g_face_tris = tris; g_face_ntris = ntris; g_face_tmax = tmax;
+}
+
 template <typename T>
 static int run(const b200_model_t* model, const float* verts, const b200_cfg_t* cfg, int n, int n_steps, T* root, T* dof_pos, T* dof_vel,
                const T* pd_tar, const T* ext, T* rb_out, T* contact_out, T* ballio, int32_t* hits) {
@@ -133,6 +142,12 @@ static int run(const b200_model_t* model, const float* verts, const b200_cfg_t* 
   int slots_ok = 1;
   if (build_dev_blob(model, hb, &slots_ok) != 0 || !slots_ok || model->nb > B200_MAX_BODIES_PK) return -1;
   hull_vertex_radius(model, verts, hb.t.vrho);
+  if (g_face_planes) {
+    hb.t.face_planes = g_face_planes;
+    hb.t.face_tris = g_face_tris;
+    hb.t.face_tmax = g_face_tmax;
+    for (int b = 0; b < model->nb; b++) hb.t.ntris[b] = g_face_ntris[b];
+  }
   std::vector<float> soa((size_t)model->nb * model->vmax * 3 + 16, 0.0f);
   float* sv = soa.data();
   while ((uintptr_t)sv % 16) sv++;   // contact_hull reads the vertices with 128-bit loads

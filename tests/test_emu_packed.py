@@ -21,9 +21,14 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def emu_step(variant, ms, verts, cfg, root, q, qd, tar, ext, n_steps=1, ball=None, hits=None):
+def emu_step(variant, ms, verts, cfg, root, q, qd, tar, ext, n_steps=1, ball=None, hits=None, faces=None):
     import build as emu_build
     lib = C.CDLL(emu_build.build(variant))
+    if faces is not None:                                        # abi.pack_faces: exact ball / hull query
+        planes, tris, ntris, tmax = faces
+        lib.emu_set_hull_faces(_p(planes), _p(tris), _p(ntris), C.c_int(tmax))
+    else:
+        lib.emu_set_hull_faces(None, None, None, C.c_int(0))
     n = root.shape[0]
     rb = np.zeros((n, ms.nb, 13))
     cf = np.zeros((n, ms.nb, 3))
@@ -163,19 +168,29 @@ def test_emulated_ball_body_and_handle_contacts(variant):
         ball[e, 7:10] = rb[e, b, 7:10] - 12.0 * direction                  # 12 m/s towards the target: 3.3 cm per substep
         ball[e, 10:13] = rng.normal(0, 20, 3)
     outs = {}
-    for name, cfg in (("on", cfg_on), ("off", cfg_off)):
+    faces = abi.pack_faces(mod, verts)
+    assert faces[2][names.index("Chest")] > 8 and faces[2][names.index("Racket")] == 0
+    # "on": exact sphere / convex-hull query (hull faces installed on both sides); "approx": no faces - spheres on the hull vertices
+    for name, cfg, fc in (("on", cfg_on, faces), ("approx", cfg_on, None), ("off", cfg_off, None)):
         b1, b2 = ball.copy(), ball.copy()
         h1, h2 = np.zeros(n, np.int32), np.zeros(n, np.int32)
         r1, q1, v1 = root.copy(), q.copy(), qd.copy()
-        emu_step(variant, ms, verts, cfg, r1, q1, v1, tar.copy(), ext.copy(), 1, b1, h1)
+        emu_step(variant, ms, verts, cfg, r1, q1, v1, tar.copy(), ext.copy(), 1, b1, h1, faces=fc)
         r2, q2, v2 = root.copy(), q.copy(), qd.copy()
-        physics_ref.control_step(ms, verts, cfg, r2, q2, v2, tar.copy(), ext.copy(), n_steps=1, ball=b2, hits=h2)
+        if fc is not None:
+            physics_ref.set_hull_faces(*fc)
+        try:
+            physics_ref.control_step(ms, verts, cfg, r2, q2, v2, tar.copy(), ext.copy(), n_steps=1, ball=b2, hits=h2)
+        finally:
+            physics_ref.clear_hull_faces()
         np.testing.assert_allclose(b1, b2, rtol=0, atol=1e-8, err_msg=name)
         np.testing.assert_allclose(q1, q2, rtol=0, atol=1e-9, err_msg=name)
         outs[name] = b2
     dv = np.linalg.norm(outs["on"][:, 7:10] - outs["off"][:, 7:10], axis=1)
     assert (dv > 3.0).sum() >= 5, dv                                        # the ball bounced off the bodies / the handle
     assert np.isfinite(outs["on"]).all()
+    # the exact surface and the vertex-sphere approximation differ (the approximation bulges by up to the vertex radius)
+    assert np.abs(outs["on"][:4] - outs["approx"][:4]).max() > 1e-4
 
 
 def test_compacted_contact_phase_is_bit_identical():

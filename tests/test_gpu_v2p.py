@@ -755,9 +755,16 @@ def test_ball_body_contact_option_on_gpu():
     ball[:, 0:3] = rb[:, b, 0:3] + 0.25 * d
     ball[:, 7:10] = -15.0 * d
     res = {}
-    for on in (0, 1):
-        cfg = abi.make_cfg(mod, substeps=6, ball={"ball_body_contact": on}, task_mode=1, pd_mode=1)
+    faces = abi.pack_faces(mod, verts)
+    # 0: option off; 1: exact sphere / convex-hull query (hull faces installed, what the task does); 2: no faces - vertex spheres
+    for on in (0, 1, 2):
+        cfg = abi.make_cfg(mod, substeps=6, ball={"ball_body_contact": int(on > 0)}, task_mode=1, pd_mode=1)
         env = native.Env(ms, verts, cfg, 4, 0)
+        if on == 1:
+            env.set_hull_faces(*faces)
+            physics_ref.set_hull_faces(*faces)
+        else:
+            physics_ref.clear_hull_faces()
         for dt, prec_tol in ((torch.float32, None), (torch.float64, 1e-8)):
             t = lambda a: torch.tensor(a, dtype=dt, device=DEV).contiguous()  # noqa: E731
             r, qq, vv, tt, ee, bb = t(root), t(q), t(qd), t(tar), t(ext), t(ball)
@@ -771,6 +778,8 @@ def test_ball_body_contact_option_on_gpu():
                 np.testing.assert_allclose(bb.cpu().numpy(), bo, rtol=0, atol=prec_tol)
             else:
                 res[on] = bb.cpu().numpy()
+    physics_ref.clear_hull_faces()
+    assert np.abs(res[1] - res[2]).max() > 1e-4              # the exact hull and the vertex-sphere stand-in are different surfaces
     along_on, along_off = (res[1][:, 7:10] * d).sum(1), (res[0][:, 7:10] * d).sum(1)     # velocity along the approach axis (-15 at launch)
     assert (along_off < -13).all()                          # option off: the ball flies through the body
     assert (along_on > -8).mean() >= 0.9                    # option on: stopped / thrown back by the chest (float64 oracle: -4 .. +6)

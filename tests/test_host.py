@@ -106,6 +106,40 @@ def test_compiled_models():
         assert w.min() > 0 and w[0] + w[1] >= w[2] * (1 - 1e-9)
 
 
+def test_hull_faces_of_compiled_models_are_closed_outward_meshes():
+    """abi.pack_faces (b200env_set_hull_faces): every body's faces form a closed triangle mesh (Euler: F = 2V' - 4 over the vertices
+    used), every hull vertex satisfies every plane, normals point away from the centroid; the body permutation of a left-handed
+    asset carries the faces with it"""
+    from vid2player3d_b200 import abi, model_compiler
+    for name in ("smpl_mesh_humanoid_amass_v1", "smpl_mesh_humanoid_nadal"):
+        mod = model_compiler.canonical_racket_last(model_compiler.load_compiled(name))
+        ms, verts = abi.pack_model(mod, 1.0)
+        planes, tris, ntris, tmax = abi.pack_faces(mod, verts)
+        assert planes.shape == (ms.nb, tmax, 4) and tris.shape == (ms.nb, tmax, 4) and tmax <= 255
+        for b in range(ms.nb):
+            nv, nt = int(ms.nverts[b]), int(ntris[b])
+            if nv == 0:
+                assert nt == 0                                                   # the welded racket has no hull (prims instead)
+                continue
+            assert nt >= 4
+            T = tris[b, :nt, :3].astype(int)
+            assert T.max() < nv
+            used = np.unique(T)
+            edges = {}
+            for t in T:
+                for i in range(3):
+                    e = (t[i], t[(i + 1) % 3])
+                    edges[e] = edges.get(e, 0) + 1
+            assert all(c == 1 for c in edges.values()) and all((e[1], e[0]) in edges for e in edges)   # oriented, closed, manifold
+            assert nt == 2 * len(used) - 4
+            V = verts[b, :nv].astype(np.float64)
+            sd = V @ planes[b, :nt, :3].T.astype(np.float64) - planes[b, :nt, 3]
+            assert sd.max() < 1e-6
+            cen = V[used].mean(0)
+            assert ((cen @ planes[b, :nt, :3].T - planes[b, :nt, 3]) < 0).all()
+            np.testing.assert_allclose(np.linalg.norm(planes[b, :nt, :3], axis=1), 1.0, atol=1e-6)
+
+
 def test_left_handed_asset_in_canonical_order():
     """nadal (Racket welded to L_Wrist, body 19) -> right-handed body order; head slab normal = the semi_western grip normal"""
     from vid2player3d_b200 import abi, model_compiler, native_v2p

@@ -263,3 +263,49 @@ def test_ball_bounce_and_drag_against_closed_forms():
     kf = 1.204 * np.pi * 0.032 ** 2 / 2
     a_drag = kf * 0.55 * v0 * v0 / 0.057
     assert abs((v0 - ball[0, 7]) / dt - a_drag) < 0.1 * a_drag, ((v0 - ball[0, 7]) / dt, a_drag)
+
+
+def test_exact_sphere_hull_query_against_surface_sampling():
+    """oracle/physics_ref.c::hull_sphere_ref (planes for separation / containment, closest point over the hull triangles otherwise)
+    against an independent estimate: the distance to 400 random points on every triangle of the hull (an upper bound that converges
+    to the true distance) and scipy's point-in-hull test."""
+    from scipy.spatial import Delaunay
+    from vid2player3d_b200 import abi, model_compiler
+    from oracle import physics_ref as P
+    mod = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    m, verts = abi.pack_model(mod, 1.0)
+    planes, tris, ntris, tmax = abi.pack_faces(mod, verts)
+    assert ntris[:24].min() >= 50 and tmax == 128
+    P.set_hull_faces(planes, tris, ntris, tmax)
+    rng = np.random.default_rng(0)
+    try:
+        for b in (0, 3, 4, 13, 16, 22):
+            nv, k = int(mod["nverts"][b]), int(ntris[b])
+            V = verts[b, :nv].astype(np.float64)
+            T = V[tris[b, :k, :3].astype(int)]                              # [k, 3, 3]
+            w = rng.dirichlet([1, 1, 1], size=(k, 400))                     # barycentric samples
+            S = np.einsum("ksj,kjd->ksd", w, T).reshape(-1, 3)
+            S = np.concatenate([S, V])
+            tri = Delaunay(V)
+            ctr, ext = V.mean(0), np.ptp(V, axis=0).max()
+            R = 0.032
+            hits = 0
+            for _ in range(300):
+                c = ctr + rng.normal(size=3) * ext * 0.45
+                hit, pen, nl = P.hull_sphere(m, verts, b, c, R)
+                d_s = np.linalg.norm(S - c, axis=1).min()
+                inside = tri.find_simplex(c) >= 0
+                if inside:
+                    assert hit == 1 and pen >= R - 1e-6 and abs(np.linalg.norm(nl) - 1) < 1e-5
+                    hits += 1
+                    continue
+                if hit == 1:
+                    d = R - pen
+                    assert -1e-6 <= d < R and d <= d_s + 1e-6 and d_s - d < 6e-3, (d, d_s)
+                    assert abs(np.linalg.norm(nl) - 1) < 1e-6
+                    hits += 1
+                else:
+                    assert d_s >= R - 1e-6, d_s                             # no contact -> no surface sample inside the sphere
+            assert hits > 10
+    finally:
+        P.clear_hull_faces()

@@ -109,6 +109,33 @@ def pack_model(model, pd_scale=1.0, kd_scale=None):
     return m, verts
 
 
+def pack_faces(model, verts):
+    """hull faces of a compiled model for b200env_set_hull_faces: planes float32 [nb, TMAX, 4] (outward unit normal, offset: n.x <= d
+    inside), tris uint8 [nb, TMAX, 4] (vertex indices + pad), ntris int32 [MAX_BODIES].  `verts` = the float32 array pack_model returns
+    (the planes are computed from exactly the vertex values the kernels see).  Models compiled before round 2 have no faces: ntris = 0."""
+    nb = verts.shape[0]
+    ntris = np.zeros(MAX_BODIES, np.int32)
+    if "tris" not in model:
+        return np.zeros((nb, 4, 4), np.float32), np.zeros((nb, 4, 4), np.uint8), ntris, 4
+    t3 = np.asarray(model["tris"])
+    tmax = int(t3.shape[1])
+    tris = np.zeros((nb, tmax, 4), np.uint8)
+    tris[..., :3] = t3
+    planes = np.zeros((nb, tmax, 4), np.float32)
+    for b in range(nb):
+        k = int(model["ntris"][b])
+        ntris[b] = k
+        if k == 0:
+            continue
+        V = verts[b].astype(np.float64)
+        a, bb, c = V[t3[b, :k, 0]], V[t3[b, :k, 1]], V[t3[b, :k, 2]]
+        n = np.cross(bb - a, c - a)
+        n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-30)
+        planes[b, :k, :3] = n
+        planes[b, :k, 3] = np.max(V[:int(model["nverts"][b])] @ n.T, axis=0)    # support value: every vertex satisfies n.x <= d
+    return planes, tris, ntris, tmax
+
+
 DEFAULT_PHYSICS = dict(contact_kn=6.0e4, contact_cn=6.0e2, friction_mu=1.0, friction_vs=0.05,
                        ang_damping=0.01, max_ang_vel=100.0, limit_k=2000.0, limit_c=20.0)
 

@@ -56,6 +56,8 @@ struct b200env {
   bool bound, has_ml;
   void* d_blob;
   size_t blob_bytes;
+  float* d_face_planes;                // b200env_set_hull_faces
+  unsigned char* d_face_tris;
   b200_cfg_t* d_cfg;
   unsigned long long* d_ticket;
   unsigned long long ticket_base;
@@ -1853,12 +1855,44 @@ int b200env_destroy(b200env_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaFree(h->d_blob);
+  cudaFree(h->d_face_planes); cudaFree(h->d_face_tris);
   cudaFree(h->d_cfg);
   cudaFree(h->d_ticket);
   cudaFree(h->d_ext);
   cudaFree(h->d_bin); cudaFree(h->d_perm); cudaFree(h->d_pos); cudaFree(h->d_cnt);
   if (h->tev) { for (cudaEvent_t e : *h->tev) cudaEventDestroy(e); delete h->tev; }
   delete h;
+  return 0;
+}
+
+int b200env_set_hull_faces(b200env_handle h, const float* planes, const uint8_t* tris, const int32_t* ntris, int32_t tmax) {
+  if (!h || !planes || !tris || !ntris) return fail(-1, "b200env_set_hull_faces: null argument%s");
+  if (tmax < 1 || tmax > 255) return fail(-2, "b200env_set_hull_faces: tmax must be in 1..255%s");
+  const int nb = h->model.nb;
+  for (int b = 0; b < nb; b++) {
+    if (ntris[b] < 0 || ntris[b] > tmax) return fail(-2, "b200env_set_hull_faces: ntris out of range%s");
+    for (int t = 0; t < ntris[b]; t++)
+      for (int k = 0; k < 3; k++)
+        if (tris[((size_t)b * tmax + t) * 4 + k] >= h->model.nverts[b]) return fail(-2, "b200env_set_hull_faces: vertex index out of range%s");
+  }
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  cudaFree(h->d_face_planes); cudaFree(h->d_face_tris);
+  h->d_face_planes = nullptr; h->d_face_tris = nullptr;
+  const size_t nf = (size_t)nb * tmax;
+  CUDA_OK(cudaMalloc(&h->d_face_planes, nf * 4 * sizeof(float)));
+  CUDA_OK(cudaMalloc(&h->d_face_tris, nf * 4));
+  CUDA_OK(cudaMemcpy(h->d_face_planes, planes, nf * 4 * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(h->d_face_tris, tris, nf * 4, cudaMemcpyHostToDevice));
+  // patch the face fields of the tree block in place (the rest of the blob stays what b200env_create uploaded)
+  DevTree t;
+  memset(&t, 0, sizeof(t));
+  t.face_planes = h->d_face_planes;
+  t.face_tris = h->d_face_tris;
+  t.face_tmax = tmax;
+  for (int b = 0; b < nb; b++) t.ntris[b] = ntris[b];
+  const size_t o0 = offsetof(DevTree, face_planes), o1 = sizeof(DevTree);
+  CUDA_OK(cudaMemcpy((char*)h->d_blob + offsetof(DevBlob, t) + o0, (const char*)&t + o0, o1 - o0, cudaMemcpyHostToDevice));
   return 0;
 }
 

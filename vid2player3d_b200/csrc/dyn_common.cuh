@@ -27,6 +27,12 @@ struct DevTree {
   int32_t child_rank[B200_MAX_BODIES];
   int32_t rix[B200_MAX_BODIES];               // record index of a body in the packed kernel's shared-memory layout = breadth-first rank
   float vrho[B200_MAX_BODIES];                // ball-body contact: radius of the sphere every hull vertex of the body stands for (hull_vertex_radius)
+  // exact ball / hull contact (b200env_set_hull_faces): faces of every body's convex hull in global memory - planes [nb][face_tmax] float4
+  // (outward unit normal, offset), tris [nb][face_tmax] 4 x uint8 (vertex indices, outward winding) - and their number per body (0 = none)
+  const float* face_planes;
+  const unsigned char* face_tris;
+  int32_t face_tmax, face_pad_[3];
+  int32_t ntris[B200_MAX_BODIES];
 };
 struct DevBlob {
   b200_model_t m;
@@ -495,6 +501,91 @@ template <typename T>
 __device__ __forceinline__ void contact_hull(const float* __restrict__ vb, int vmax, int nv, const PhysCfg<T>& c, const T* R, const T* p,
                                              const T* v, const T* w, T* A, T* Bm, T* C, T* bn, T* bf, T* cf) {
   contact_apply<T>(vb, vmax, contact_mask<T>(vb, vmax, nv, R, p), c, R, p, v, w, A, Bm, C, bn, bf, cf);
+}
+
+// ---- exact sphere / convex hull query (float64 restatement: oracle/physics_ref.c::hull_sphere_ref).  c: sphere centre in the body frame.
+// (1) s = max over the face planes of n.c - d: s > R separates exactly; (2) s <= 0: centre inside the hull, depth R - s along the
+// least-penetrated face normal; (3) else the closest point of the hull surface = closest point over its triangles (Ericson 5.1.5).
+// vb: the body's hull vertices, SoA [3][vmax] (shared memory); pl / tr: its planes / triangles (global memory, L2-resident).
+template <typename T>
+__device__ __forceinline__ void closest_on_triangle(const T* p, const T* a, const T* b, const T* c, T* q) {
+  T ab[3], ac[3], ap[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; }
+  const T d1 = ab[0] * ap[0] + ab[1] * ap[1] + ab[2] * ap[2], d2 = ac[0] * ap[0] + ac[1] * ap[1] + ac[2] * ap[2];
+  if (d1 <= T(0) && d2 <= T(0)) { q[0] = a[0]; q[1] = a[1]; q[2] = a[2]; return; }
+  T bp[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) bp[k] = p[k] - b[k];
+  const T d3 = ab[0] * bp[0] + ab[1] * bp[1] + ab[2] * bp[2], d4 = ac[0] * bp[0] + ac[1] * bp[1] + ac[2] * bp[2];
+  if (d3 >= T(0) && d4 <= d3) { q[0] = b[0]; q[1] = b[1]; q[2] = b[2]; return; }
+  const T vc = d1 * d4 - d3 * d2;
+  if (vc <= T(0) && d1 >= T(0) && d3 <= T(0)) {
+    const T v = d1 / (d1 - d3);
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[k] = a[k] + v * ab[k];
+    return;
+  }
+  T cp[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) cp[k] = p[k] - c[k];
+  const T d5 = ab[0] * cp[0] + ab[1] * cp[1] + ab[2] * cp[2], d6 = ac[0] * cp[0] + ac[1] * cp[1] + ac[2] * cp[2];
+  if (d6 >= T(0) && d5 <= d6) { q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; return; }
+  const T vb2 = d5 * d2 - d1 * d6;
+  if (vb2 <= T(0) && d2 >= T(0) && d6 <= T(0)) {
+    const T w = d2 / (d2 - d6);
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[k] = a[k] + w * ac[k];
+    return;
+  }
+  const T va = d3 * d6 - d5 * d4;
+  if (va <= T(0) && (d4 - d3) >= T(0) && (d5 - d6) >= T(0)) {
+    const T w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[k] = b[k] + w * (c[k] - b[k]);
+    return;
+  }
+  const T den = T(1) / (va + vb2 + vc), v = vb2 * den, w = vc * den;
+#pragma unroll
+  for (int k = 0; k < 3; k++) q[k] = a[k] + ab[k] * v + ac[k] * w;
+}
+template <typename T>
+__device__ __forceinline__ bool hull_sphere(const float* vb, int vmax, const float* pl, const unsigned char* tr, int nt, const T* c, T R, T& pen,
+                                            T* nl) {
+  T smax = T(-1e30);
+  int imax = 0;
+  for (int t = 0; t < nt; t++) {
+    const float4 P = *reinterpret_cast<const float4*>(pl + 4 * t);
+    const T sd = T(P.x) * c[0] + T(P.y) * c[1] + T(P.z) * c[2] - T(P.w);
+    if (sd > R) return false;   // a separating face plane: the common outcome for a ball that is merely near the body
+    if (sd > smax) { smax = sd; imax = t; }
+  }
+  if (smax <= T(0)) {
+    pen = R - smax;
+    nl[0] = T(pl[4 * imax]); nl[1] = T(pl[4 * imax + 1]); nl[2] = T(pl[4 * imax + 2]);
+    return true;
+  }
+  T best = T(1e30), qb[3] = {T(0), T(0), T(0)};
+  for (int t = 0; t < nt; t++) {
+    // the closest point of a convex hull to an outside point lies on a face the point sees (its offset from that face's plane is
+    // positive): the back faces are skipped
+    const float4 P = *reinterpret_cast<const float4*>(pl + 4 * t);
+    if (!(T(P.x) * c[0] + T(P.y) * c[1] + T(P.z) * c[2] - T(P.w) > T(0))) continue;
+    const int i0 = tr[4 * t], i1 = tr[4 * t + 1], i2 = tr[4 * t + 2];
+    const T a[3] = {T(vb[i0]), T(vb[vmax + i0]), T(vb[2 * vmax + i0])};
+    const T b[3] = {T(vb[i1]), T(vb[vmax + i1]), T(vb[2 * vmax + i1])};
+    const T cc[3] = {T(vb[i2]), T(vb[vmax + i2]), T(vb[2 * vmax + i2])};
+    T q[3];
+    closest_on_triangle<T>(c, a, b, cc, q);
+    const T e2 = (c[0] - q[0]) * (c[0] - q[0]) + (c[1] - q[1]) * (c[1] - q[1]) + (c[2] - q[2]) * (c[2] - q[2]);
+    if (e2 < best) { best = e2; qb[0] = q[0]; qb[1] = q[1]; qb[2] = q[2]; }
+  }
+  const T dist = sqrt_(best);
+  if (!(dist < R) || dist <= T(1e-9)) return false;
+  pen = R - dist;
+  const T id = T(1) / dist;
+  nl[0] = (c[0] - qb[0]) * id; nl[1] = (c[1] - qb[1]) * id; nl[2] = (c[2] - qb[2]) * id;
+  return true;
 }
 
 

@@ -491,36 +491,45 @@ __device__ __forceinline__ void pk_ball_contacts_extra(const DevBlob& B, const f
     const T *Q = s, *p = s + 4, *w = s + 7, *v = s + 10;
     const T d[3] = {ball.p[0] - p[0], ball.p[1] - p[1], ball.p[2] - p[2]};
     const T d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-    const T reach = handle ? T(0.6) : T(M.radius[b]) + T(B.t.vrho[b]) + c.bR;
+    const int nt = handle ? 0 : B.t.ntris[b];
+    const T reach = handle ? T(0.6) : T(M.radius[b]) + (nt > 0 ? T(0) : T(B.t.vrho[b])) + c.bR;
     if (d2 > reach * reach) continue;
     const T cq[4] = {-Q[0], -Q[1], -Q[2], Q[3]};
-    T dl[3], el[3] = {T(0), T(0), T(0)}, dist = T(0), rad = T(0);
+    T dl[3], pen = T(0), nl[3] = {T(0), T(0), T(1)};
     qrot(cq, d, dl);   // ball centre in the body frame
-    if (handle) {
-      const T a[3] = {c.hdl[3] - c.hdl[0], c.hdl[4] - c.hdl[1], c.hdl[5] - c.hdl[2]};
-      const T q0[3] = {dl[0] - c.hdl[0], dl[1] - c.hdl[1], dl[2] - c.hdl[2]};
-      T t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) * rcp_(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-      t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t);
-#pragma unroll
-      for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
-      dist = sqrt_(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
-      rad = c.hdl[6];
+    if (nt > 0) {
+      if (!hull_sphere<T>(verts + (size_t)b * M.vmax * 3, M.vmax, B.t.face_planes + (size_t)b * B.t.face_tmax * 4,
+                          B.t.face_tris + (size_t)b * B.t.face_tmax * 4, nt, dl, c.bR, pen, nl))
+        continue;
     } else {
-      const float* vb = verts + (size_t)b * M.vmax * 3;
-      T m2 = T(1e30);
-      for (int k = 0; k < nv; k++) {
-        const T ex = dl[0] - T(vb[k]), ey = dl[1] - T(vb[M.vmax + k]), ez = dl[2] - T(vb[2 * M.vmax + k]);
-        const T e2 = ex * ex + ey * ey + ez * ez;
-        if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+      T el[3] = {T(0), T(0), T(0)}, dist = T(0), rad = T(0);
+      if (handle) {
+        const T a[3] = {c.hdl[3] - c.hdl[0], c.hdl[4] - c.hdl[1], c.hdl[5] - c.hdl[2]};
+        const T q0[3] = {dl[0] - c.hdl[0], dl[1] - c.hdl[1], dl[2] - c.hdl[2]};
+        T t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) * rcp_(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t);
+#pragma unroll
+        for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
+        dist = sqrt_(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
+        rad = c.hdl[6];
+      } else {
+        const float* vb = verts + (size_t)b * M.vmax * 3;
+        T m2 = T(1e30);
+        for (int k = 0; k < nv; k++) {
+          const T ex = dl[0] - T(vb[k]), ey = dl[1] - T(vb[M.vmax + k]), ez = dl[2] - T(vb[2 * M.vmax + k]);
+          const T e2 = ex * ex + ey * ey + ez * ez;
+          if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+        }
+        dist = sqrt_(m2);
+        rad = T(B.t.vrho[b]);
       }
-      dist = sqrt_(m2);
-      rad = T(B.t.vrho[b]);
-    }
-    const T pen = c.bR + rad - dist;
-    if (pen > best && dist > T(1e-9)) {
-      best = pen;
+      pen = c.bR + rad - dist;
+      if (!(dist > T(1e-9))) continue;
       const T id = rcp_(dist);
-      const T nl[3] = {el[0] * id, el[1] * id, el[2] * id};
+      nl[0] = el[0] * id; nl[1] = el[1] * id; nl[2] = el[2] * id;
+    }
+    if (pen > best) {
+      best = pen;
       qrot(Q, nl, bn);
       // velocity of the obstacle at the contact point x = c - R n
       const T x[3] = {d[0] - c.bR * bn[0], d[1] - c.bR * bn[1], d[2] - c.bR * bn[2]};
@@ -571,37 +580,46 @@ __device__ __forceinline__ void pk_ball_contacts_group(const DevBlob& B, const f
       const T *Q = st, *p = st + 4, *w = st + 7, *v = st + 10;
       const T d[3] = {bp[0] - p[0], bp[1] - p[1], bp[2] - p[2]};
       const T d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-      const T reach = handle ? T(0.6) : T(M.radius[b]) + T(B.t.vrho[b]) + c.bR;
+      const int nt = handle ? 0 : B.t.ntris[b];          // > 0: exact test against the body's convex hull
+      const T reach = handle ? T(0.6) : T(M.radius[b]) + (nt > 0 ? T(0) : T(B.t.vrho[b])) + c.bR;
       if (d2 > reach * reach) continue;
       const T cq[4] = {-Q[0], -Q[1], -Q[2], Q[3]};
-      T dl[3], el[3] = {T(0), T(0), T(0)}, dist = T(0), rad = T(0);
+      T dl[3], pen = T(0), nl[3] = {T(0), T(0), T(1)};
       qrot(cq, d, dl);   // ball centre in the body frame
-      if (handle) {
-        const T a[3] = {c.hdl[3] - c.hdl[0], c.hdl[4] - c.hdl[1], c.hdl[5] - c.hdl[2]};
-        const T q0[3] = {dl[0] - c.hdl[0], dl[1] - c.hdl[1], dl[2] - c.hdl[2]};
-        T t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) * rcp_(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-        t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t);
-#pragma unroll
-        for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
-        dist = sqrt_(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
-        rad = c.hdl[6];
+      if (nt > 0) {      // exact: the body's convex hull
+        if (!hull_sphere<T>(verts + (size_t)b * M.vmax * 3, M.vmax, B.t.face_planes + (size_t)b * B.t.face_tmax * 4,
+                            B.t.face_tris + (size_t)b * B.t.face_tmax * 4, nt, dl, c.bR, pen, nl))
+          continue;
       } else {
-        const float* vb = verts + (size_t)b * M.vmax * 3;
-        T m2 = T(1e30);
-        for (int k = 0; k < nv; k++) {
-          const T ex = dl[0] - T(vb[k]), ey = dl[1] - T(vb[M.vmax + k]), ez = dl[2] - T(vb[2 * M.vmax + k]);
-          const T e2 = ex * ex + ey * ey + ez * ez;
-          if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+        T el[3] = {T(0), T(0), T(0)}, dist = T(0), rad = T(0);
+        if (handle) {
+          const T a[3] = {c.hdl[3] - c.hdl[0], c.hdl[4] - c.hdl[1], c.hdl[5] - c.hdl[2]};
+          const T q0[3] = {dl[0] - c.hdl[0], dl[1] - c.hdl[1], dl[2] - c.hdl[2]};
+          T t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) * rcp_(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+          t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t);
+#pragma unroll
+          for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
+          dist = sqrt_(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
+          rad = c.hdl[6];
+        } else {         // a model compiled without hull faces: spheres on the hull vertices stand in for the hull
+          const float* vb = verts + (size_t)b * M.vmax * 3;
+          T m2 = T(1e30);
+          for (int k = 0; k < nv; k++) {
+            const T ex = dl[0] - T(vb[k]), ey = dl[1] - T(vb[M.vmax + k]), ez = dl[2] - T(vb[2 * M.vmax + k]);
+            const T e2 = ex * ex + ey * ey + ez * ez;
+            if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+          }
+          dist = sqrt_(m2);
+          rad = T(B.t.vrho[b]);
         }
-        dist = sqrt_(m2);
-        rad = T(B.t.vrho[b]);
+        pen = c.bR + rad - dist;
+        if (!(dist > T(1e-9))) continue;
+        const T id = rcp_(dist);
+        nl[0] = el[0] * id; nl[1] = el[1] * id; nl[2] = el[2] * id;
       }
-      const T pen = c.bR + rad - dist;
-      if (pen > best && dist > T(1e-9)) {
+      if (pen > best) {
         best = pen;
         bbody = b;
-        const T id = rcp_(dist);
-        const T nl[3] = {el[0] * id, el[1] * id, el[2] * id};
         qrot(Q, nl, bn);
         const T x[3] = {d[0] - c.bR * bn[0], d[1] - c.bR * bn[1], d[2] - c.bR * bn[2]};   // contact point relative to the body origin
         T wxx[3];

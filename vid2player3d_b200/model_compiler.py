@@ -160,6 +160,35 @@ def compile_mjcf(xml_path):
     return _pack(bodies, os.path.basename(xml_path))
 
 
+TMAX = 128  # hull triangles per body are padded to this many (2 V - 4 <= 124 for V <= 64)
+
+
+def hull_faces(verts, nverts):
+    """Triangulated faces of every body's convex hull (the shapes PhysX collides the ball with): tris [nb, TMAX, 3] uint8 vertex indices,
+    counter-clockwise seen from outside (outward normal = (v1 - v0) x (v2 - v0)), ntris [nb], and tri_lmax [nb] = the longest triangle edge
+    (a point within distance r of the hull is within r + tri_lmax of one of its vertices: the cheap vertex pass filters the exact one)."""
+    from scipy.spatial import ConvexHull
+    nb = len(nverts)
+    tris = np.zeros((nb, TMAX, 3), np.uint8)
+    ntris = np.zeros(nb, np.int32)
+    lmax = np.zeros(nb)
+    for b in range(nb):
+        nv = int(nverts[b])
+        if nv < 4:
+            continue
+        V = np.asarray(verts[b, :nv], np.float64)
+        hull = ConvexHull(V)                       # Qhull with triangulated output: 2 V - 4 facets for points in general position
+        assert len(hull.simplices) <= TMAX
+        for k, (simp, eq) in enumerate(zip(hull.simplices, hull.equations)):
+            i, j, l = (int(x) for x in simp)
+            if np.cross(V[j] - V[i], V[l] - V[i]) @ eq[:3] < 0:
+                j, l = l, j
+            tris[b, k] = (i, j, l)
+            lmax[b] = max(lmax[b], np.linalg.norm(V[j] - V[i]), np.linalg.norm(V[l] - V[j]), np.linalg.norm(V[i] - V[l]))
+        ntris[b] = len(hull.simplices)
+    return tris, ntris, lmax
+
+
 def _pack(bodies, name):
     nb = len(bodies)
     parent = np.array([b["parent"] for b in bodies], np.int32)
@@ -209,7 +238,9 @@ def _pack(bodies, name):
             radius[i] = np.linalg.norm(b["verts"], axis=1).max()
     prims = [np.concatenate([np.full((len(b["prims"]), 1), i), b["prims"]], 1) for i, b in enumerate(bodies) if len(b["prims"])]
     prims = np.concatenate(prims, 0) if prims else np.zeros((0, 8))
+    tris, ntris, tri_lmax = hull_faces(verts, nverts)
     return dict(
+        tris=tris, ntris=ntris, tri_lmax=tri_lmax,
         name=name, body_names=np.array([b["name"] for b in bodies]), dof_names=np.array(dof_names),
         parent=parent, depth=depth, fixed=fixed, dof_of_body=dof_of_body, dof_body_ids=dof_body_ids,
         offset=offset, mass=mass, com=com, inertia=inertia,

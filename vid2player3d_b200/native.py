@@ -14,7 +14,7 @@ _lib = None
 SYMBOLS = ["b200env_abi_version", "b200env_last_error", "b200env_create", "b200env_destroy", "b200env_bind",
            "b200env_set_motion_lib", "b200env_step", "b200env_reset", "b200env_motion_state", "b200env_obs_imitation",
            "b200env_physics_only", "b200env_launch_count", "b200env_set_env_slice", "b200env_motion_context", "b200env_set_kernel_timing",
-           "b200env_kernel_ms", "b200env_obs_imitation_rows"]
+           "b200env_kernel_ms", "b200env_obs_imitation_rows", "b200env_set_hull_faces"]
 
 
 def lib():
@@ -99,6 +99,15 @@ class Env:
         v.total_frames = t["gts"].shape[0]
         self._keep.append(t)
         _check(lib().b200env_set_motion_lib(self._h, C.byref(v)))
+
+    def set_hull_faces(self, planes, tris, ntris, tmax):
+        """hull faces for the exact ball / convex-hull contact (abi.pack_faces); host numpy arrays, copied by the library"""
+        import numpy as np
+        planes = np.ascontiguousarray(planes, np.float32)
+        tris = np.ascontiguousarray(tris, np.uint8)
+        ntris = np.ascontiguousarray(ntris, np.int32)
+        _check(lib().b200env_set_hull_faces(self._h, planes.ctypes.data_as(C.c_void_p), tris.ctypes.data_as(C.c_void_p),
+                                            ntris.ctypes.data_as(C.c_void_p), C.c_int32(int(tmax))))
 
     def set_env_slice(self, first, stride):
         """this handle steps rows first, first+stride, ... of the bound tensors (one handle per asset in dual mode)"""

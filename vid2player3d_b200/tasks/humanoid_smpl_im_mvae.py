@@ -107,7 +107,8 @@ class HumanoidSMPLIMMVAE(BaseTask):
         ball["ball_mu_racket"] = 0.5 * (v2p.get("racket_friction", 0.8) + v2p.get("ball_friction", 0.2))
         ball["ball_mu_ground"] = 0.5 * (env.get("plane", {}).get("dynamicFriction", 1.0) + v2p.get("ball_friction", 0.2))
         # the ball also collides with the humanoid's bodies and the racket handle, as it does in the reference's PhysX scene (ball
-        # collision filter 0, :436-442); include/b200env.h `ball_body_contact`.  On by default since round 2 (the body loop runs on the
+        # collision filter 0, :436-442); include/b200env.h `ball_body_contact`, exact against the bodies' convex hulls
+        # (b200env_set_hull_faces).  On by default since round 2 (the body loop runs on the
         # 8 lanes of the env's group: +59 us per 8192-env step of config 3 without the any-contact skip, profiles/r2m_ball_body.md);
         # vid2player.ball_body_contact: False switches it off
         if v2p.get("ball_body_contact", True):
@@ -131,6 +132,9 @@ class HumanoidSMPLIMMVAE(BaseTask):
             h = native.Env(ms, verts, mk_cfg(m), self.num_envs // K, self.device_id)      # racket head geometry is per asset
             if K > 1:
                 h.set_env_slice(k, K)
+            if ball.get("ball_body_contact"):
+                # exact sphere / convex-hull query against the hull faces the model compiler stored (model_compiler.hull_faces)
+                h.set_hull_faces(*abi.pack_faces(m, verts))
             self._envs.append(h)
         self._env = self._envs[0]
 
