@@ -15,6 +15,9 @@ thread_local int emu_lane = 0;
 #define EMU_STEP control_step_packed3
 #else
 #include "../../vid2player3d_b200/csrc/packed.cuh"
+#ifdef EMU_PACKEDT
+#include "../../vid2player3d_b200/csrc/packed_t.cuh"   // one-wave form: private fields in a per-lane array here (PrivMem), tensor memory on the GPU
+#endif
 #define EMU_EPW EPW
 #define EMU_LPE PK_LANES_PER_ENV
 #define EMU_BALL_SLOT BALL_SLOT
@@ -124,6 +127,89 @@ template <typename T> void lane_main(EmuWarp* w, int lane, const Job<T>* J, int6
     if (J->hits) J->hits[e] = ball.hits;
   }
 }
+
+#ifdef EMU_PACKEDT
+// one warp = the body of physics_kernel_tmem (b200env.cu) for envs eb .. eb + EPW - 1, private store = priv (one array per lane)
+template <typename T> void lane_main_t(EmuWarp* w, int lane, const Job<T>* J, int64_t eb, T* wrec, T* priv) {
+  emu_warp = w;
+  emu_lane = lane;
+  const DevBlob& B = *J->B;
+  const b200_model_t& M = B.m;
+  const int n = J->n, nb = M.nb, nd = M.nd;
+  LaneConst lc = lane_const(M, lane);
+  if (lc.active) lc.rix = B.t.rix[lane];
+  PhysCfg<T> pc = make_phys_cfg<T>(*J->cfg);
+  const bool with_ball = pc.has_ball && J->ballio != nullptr;
+  pc.has_ball = with_ball;
+  const int g = lane / EMU_LPE, s = lane % EMU_LPE;
+  PrivMem<T> ps{priv + (size_t)lane * PT_BLOCKS * PT_COLS};
+  for (int k = 0; k < EMU_EPW; k++) {
+    const int64_t e = eb + k;
+    if (e >= n) break;
+    Lane<T> L;
+    for (int j = 0; j < 4; j++) { L.Q[j] = 0; L.qj[j] = 0; }
+    L.Q[3] = 1; L.qj[3] = 1;
+    for (int j = 0; j < 3; j++) { L.p[j] = 0; L.w[j] = 0; L.v[j] = 0; L.wt[j] = 0; }
+    T pdt[3] = {0, 0, 0}, eF[3] = {0, 0, 0}, eT[3] = {0, 0, 0};
+    if (lane == 0) {
+      const T* rs = J->root + e * 13;
+      for (int j = 0; j < 3; j++) { L.p[j] = rs[j]; L.v[j] = rs[7 + j]; L.w[j] = rs[10 + j]; }
+      for (int j = 0; j < 4; j++) L.Q[j] = rs[3 + j];
+      qnormalize(L.Q);
+      if (J->ext) for (int j = 0; j < 3; j++) { eF[j] = J->ext[e * 6 + j]; eT[j] = J->ext[e * 6 + 3 + j]; }
+    }
+    if (lc.dyn && lane > 0) {
+      T q[3];
+      for (int j = 0; j < 3; j++) { q[j] = J->dof_pos[e * nd + lc.dof0 + j]; L.wt[j] = J->dof_vel[e * nd + lc.dof0 + j]; pdt[j] = J->pd_tar[e * nd + lc.dof0 + j]; }
+      qexp(q, L.qj);
+    }
+    pt_stage_in<T>(wrec + k * PT_ENV_STRIDE, lc, lane, L, pdt, eF, eT);
+  }
+  __syncwarp();
+  const bool valid = g < EMU_EPW && eb + g < n;
+  pt_adopt<T>(B, wrec, lane, valid, ps);
+  Ball<T> ball;
+  ball_clear(ball);
+  if (with_ball && valid && s == EMU_BALL_SLOT) {
+    const int64_t e = eb + g;
+    for (int j = 0; j < 3; j++) { ball.p[j] = J->ballio[e * 13 + j]; ball.v[j] = J->ballio[e * 13 + 7 + j]; ball.w[j] = J->ballio[e * 13 + 10 + j]; }
+  }
+  T* cf_env = (valid && J->contact_out) ? J->contact_out + (eb + g) * nb * 3 : nullptr;
+  for (int st_ = 0; st_ < J->n_steps; st_++) {
+    control_step_t<T>(B, J->verts, pc, wrec, lane, valid, ball, ps, cf_env, false);
+    if (st_ + 1 < J->n_steps) pt_requantize<T>(B, lane, valid, ps);
+  }
+  pt_publish<T>(B, wrec, lane, valid, ps);
+  __syncwarp();
+  for (int k = 0; k < EMU_EPW; k++) {
+    const int64_t e = eb + k;
+    if (e >= n) break;
+    Lane<T> L;
+    pt_load_state<T>(wrec + k * PT_ENV_STRIDE, lc, lane, L);
+    if (lane == 0) {
+      T* rs = J->root + e * 13;
+      for (int j = 0; j < 3; j++) { rs[j] = L.p[j]; rs[7 + j] = L.v[j]; rs[10 + j] = L.w[j]; }
+      for (int j = 0; j < 4; j++) rs[3 + j] = L.Q[j];
+    }
+    if (lc.dyn && lane > 0) {
+      T q[3];
+      qlog(L.qj, q);
+      for (int j = 0; j < 3; j++) { J->dof_pos[e * nd + lc.dof0 + j] = q[j]; J->dof_vel[e * nd + lc.dof0 + j] = L.wt[j]; }
+    }
+    if (lc.active) {
+      T* rb = J->rb_out + (e * nb + lane) * 13;
+      for (int j = 0; j < 3; j++) { rb[j] = L.p[j]; rb[7 + j] = L.v[j]; rb[10 + j] = L.w[j]; }
+      for (int j = 0; j < 4; j++) rb[3 + j] = L.Q[j];
+      if (J->contact_out && !lc.dyn) for (int j = 0; j < 3; j++) J->contact_out[(e * nb + lane) * 3 + j] = T(0);   // welded bodies carry no contact force of their own
+    }
+  }
+  if (with_ball && valid && s == EMU_BALL_SLOT) {
+    const int64_t e = eb + g;
+    for (int j = 0; j < 3; j++) { J->ballio[e * 13 + j] = ball.p[j]; J->ballio[e * 13 + 7 + j] = ball.v[j]; J->ballio[e * 13 + 10 + j] = ball.w[j]; }
+    if (J->hits) J->hits[e] = ball.hits;
+  }
+}
+#endif
 }  // namespace
 
 // hull faces of the exact ball / hull query (b200env_set_hull_faces on the product side): host arrays kept by the caller
@@ -153,13 +239,22 @@ static int run(const b200_model_t* model, const float* verts, const b200_cfg_t* 
   while ((uintptr_t)sv % 16) sv++;   // contact_hull reads the vertices with 128-bit loads
   verts_to_soa(model, verts, sv);
   Job<T> J{&hb, sv, cfg, n, n_steps, root, dof_pos, dof_vel, pd_tar, ext, rb_out, contact_out, ballio, hits};
+#ifdef EMU_PACKEDT
+  if (!hb.t.pt_ok) return -2;
+  std::vector<T> rec((size_t)EMU_EPW * PT_ENV_STRIDE + 8, T(0)), priv((size_t)32 * PT_BLOCKS * PT_COLS, T(0));
+#else
   std::vector<T> rec((size_t)EMU_EPW * ENV_STRIDE + 8, T(0));
+#endif
   T* wrec = rec.data();
   while ((uintptr_t)wrec % 16) wrec++;   // the records are read with 128-bit accesses on the float path
   for (int64_t eb = 0; eb < n; eb += EMU_EPW) {
     EmuWarp w;
     std::vector<std::thread> th;
+#ifdef EMU_PACKEDT
+    for (int lane = 0; lane < 32; lane++) th.emplace_back(lane_main_t<T>, &w, lane, &J, eb, wrec, priv.data());
+#else
     for (int lane = 0; lane < 32; lane++) th.emplace_back(lane_main<T>, &w, lane, &J, eb, wrec);
+#endif
     for (auto& t : th) t.join();
   }
   return 0;

@@ -52,7 +52,7 @@ def states(n, seed, contact):
     return root, q, qd, q + rng.normal(0, 0.2, (n, 69)), rng.normal(0, 30, (n, 6))
 
 
-VARIANTS = ["packed"] + (["packed3"] if os.path.exists(os.path.join(HERE, "..", "tools", "variants", "packed3.cuh")) else [])
+VARIANTS = ["packed", "packedt"] + (["packed3"] if os.path.exists(os.path.join(HERE, "..", "tools", "variants", "packed3.cuh")) else [])
 
 
 @pytest.mark.parametrize("variant", VARIANTS)

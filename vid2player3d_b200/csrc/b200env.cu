@@ -1030,12 +1030,22 @@ post_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __restrict__ gc
 #define PK_WARPS 7          // 7 warps x 4 envs x 7.2 KB records + 20 KB constants = 227 KB of shared memory: one CTA per SM
 #endif
 #define PK_SCRATCH 232
+// PK_SHADOW=1 (experiment, tools/shadow.sh): launch 2 x PK_WARPS warps; warps PK_WARPS.. are "shadows" that run the instruction stream
+// of warp - PK_WARPS on the same records with every store suppressed: what would 14 resident warps cost (issue slots, shared-memory
+// bandwidth, 128 registers)?  Results of the real warps are unchanged.
+#ifndef PK_SHADOW
+#define PK_SHADOW 0
+#endif
+#define PK_LAUNCH_WARPS (PK_WARPS * (PK_SHADOW ? 2 : 1))
+#ifndef PK_BOUND_WARPS
+#define PK_BOUND_WARPS PK_LAUNCH_WARPS    // A/B: a larger bound = the register budget of that many warps at the product's warp count
+#endif
 
 // SPLIT = false: the whole env step in this launch.  SPLIT = true: the middle launch of pre_kernel -> this -> post_kernel; here only
 // the state rows / PD targets / residual wrench are read and the state rows written (the once-per-step task logic runs in the two
 // high-occupancy kernels, where its memory latency is covered by 48+ warps per SM instead of the 7 this kernel can hold).
 template <bool SPLIT>
-__global__ void __launch_bounds__(PK_WARPS * 32, 1)
+__global__ void __launch_bounds__(PK_BOUND_WARPS * 32, 1)
 step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf,
                    b200_motion_lib_t ml, const float* __restrict__ actions, int num_envs, unsigned long long* __restrict__ ticket,
                    int env_first, int env_stride, const float* __restrict__ ext_wrench, const int32_t* __restrict__ perm) {
@@ -1046,7 +1056,8 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
   const b200_model_t& M = B.m;
   const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
   float* scratch_all = reinterpret_cast<float*>(smem + ((blob_bytes + 15) & ~15u));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (threadIdx.x >> 5) % PK_WARPS, lane = threadIdx.x & 31;
+  const bool shadow = PK_SHADOW && (int)threadIdx.x >= PK_WARPS * 32;
   float* scr = scratch_all + warp * PK_SCRATCH;   // prologue / epilogue scratch of the fused form; the split form has none
   float* wrec = scratch_all + (SPLIT ? 0 : PK_WARPS * PK_SCRATCH) + (size_t)warp * EPW * ENV_STRIDE;
   __shared__ b200_cfg_t s_cfg;  // constants in shared memory: no global (long-scoreboard) reloads inside the substep loop
@@ -1069,7 +1080,7 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
   const int grp = warp < G0 ? 0 : 1;
   const int gw0 = grp == 0 ? 0 : G0, gwn = grp == 0 ? G0 : PK_WARPS - G0;     // first warp / number of warps of my group
   const int BATCH = gwn * EPW;
-  const int gthreads = gwn * 32;
+  const int gthreads = gwn * 32 * (PK_SHADOW ? 2 : 1);
   auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(gthreads) : "memory"); };
 
   __shared__ unsigned long long s_tk[2];
@@ -1160,9 +1171,9 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     // state write-back; without the barrier it measured 295.3 vs 298.3 us per 8192-env step (profiles/r1h_ab.log).
     if (!SPLIT && full_batch) group_sync();
 #endif
-    if (cfg.has_ball && valid && s == BALL_SLOT) ball_writeback(bf, erow_g, ball);
+    if (cfg.has_ball && valid && s == BALL_SLOT && !shadow) ball_writeback(bf, erow_g, ball);
     for (int k = 0; k < EPW; k++) {
-      if (eb + k >= num_envs) break;
+      if (eb + k >= num_envs || shadow) break;
       const int64_t e = SPLIT ? row(eb + k) : env_first + (int64_t)env_stride * (eb + k);
       Lane<float> L;
       float cf[3];
@@ -1954,8 +1965,8 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed3, PK3_WARPS * 32, psmem));
       } else
 #endif
-      if (h->split) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<true>, PK_WARPS * 32, psmem)); }
-      else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<false>, PK_WARPS * 32, psmem)); }
+      if (h->split) { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<true>, PK_LAUNCH_WARPS * 32, psmem)); }
+      else { CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_packed<false>, PK_LAUNCH_WARPS * 32, psmem)); }
       CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
       h->step_grid = per_sm * sms < need ? per_sm * sms : need;
       if (h->step_grid < 1) return fail(-5, "b200env_step: step_kernel_packed does not fit on this device%s");
@@ -1992,7 +2003,7 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
             (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->num_envs, h->d_ticket, h->env_first, h->env_stride, h->d_ext);
       else
 #endif
-        step_kernel_packed<true><<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>(
+        step_kernel_packed<true><<<h->step_grid, PK_LAUNCH_WARPS * 32, psmem, (cudaStream_t)stream>>>(
             (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->ml, actions, h->num_envs, h->d_ticket, h->env_first,
             h->env_stride, h->d_ext, h->sort ? h->d_perm : nullptr);
       if (tv0) { cudaEventRecord(tv1, (cudaStream_t)stream); h->tev->push_back(tv0); h->tev->push_back(tv1); }
@@ -2003,7 +2014,7 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
       h->launches += h->cfg.task_mode == 0 ? 3 : 2;
       return 0;
     }
-    step_kernel_packed<false><<<h->step_grid, PK_WARPS * 32, psmem, (cudaStream_t)stream>>>(
+    step_kernel_packed<false><<<h->step_grid, PK_LAUNCH_WARPS * 32, psmem, (cudaStream_t)stream>>>(
         (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->ml, actions, h->num_envs, h->d_ticket, h->env_first,
         h->env_stride, nullptr, nullptr);
     CUDA_OK(cudaGetLastError());

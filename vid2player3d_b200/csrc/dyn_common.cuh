@@ -33,6 +33,15 @@ struct DevTree {
   const unsigned char* face_tris;
   int32_t face_tmax, face_pad_[3];
   int32_t ntris[B200_MAX_BODIES];
+  // packed_t.cuh (one-wave kernel: lane-private fields in tensor memory): every dynamic body has a fixed owner lane slot and one of
+  // three column blocks of its lane; the bodies of one tree depth share a block (one warp-uniform TMEM address per level pass)
+  int8_t pt_blk[B200_MAX_BODIES];             // column block of a dynamic body, -1: welded
+  int8_t pt_slot[B200_MAX_BODIES];            // lane slot of the body in every pass
+  int8_t pt_body[3][PK_SLOTS];                // body pass: the dynamic body of (block, slot), -1 padded
+  int8_t pt_lvl[MAX_LEVELS][PK_SLOTS];        // level passes: body of that depth at its slot (welded ones included), -1 padded
+  int8_t pt_lblk[MAX_LEVELS];                 // block of the depth's dynamic bodies, -1: none
+  int8_t pt_mbox[B200_MAX_BODIES];            // mailbox entry of a dynamic body = its rank among the dynamic bodies of its depth
+  int32_t pt_ok, pt_nmbox, pt_pad_[4];        // pt_ok: the tree fits (3 blocks x 8 slots); pt_nmbox: mailbox entries per env
 };
 struct DevBlob {
   b200_model_t m;
@@ -41,6 +50,58 @@ struct DevBlob {
 };
 static_assert(sizeof(b200_model_t) % 16 == 0, "model block must be a 16-byte multiple for the bulk copy");
 static_assert(sizeof(DevBlob) % 16 == 0, "blob header must be a 16-byte multiple");
+
+// host side: owner slots / column blocks of packed_t.cuh.  The dynamic bodies of every tree depth go into ONE of three blocks of
+// PK_SLOTS slots (exhaustive search over the 3^depths assignments, first fit); inside a block slots are handed out in depth order.
+// A welded body needs a lane at its depth but no column block: it takes a slot its depth does not use.
+static inline void build_pt_tables(const b200_model_t* model, DevTree& t) {
+  t.pt_ok = 0; t.pt_nmbox = 0;
+  for (int b = 0; b < B200_MAX_BODIES; b++) { t.pt_blk[b] = -1; t.pt_slot[b] = -1; t.pt_mbox[b] = -1; }
+  for (int k = 0; k < 3; k++) for (int s = 0; s < PK_SLOTS; s++) t.pt_body[k][s] = -1;
+  for (int d = 0; d < MAX_LEVELS; d++) { t.pt_lblk[d] = -1; for (int s = 0; s < PK_SLOTS; s++) t.pt_lvl[d][s] = -1; }
+  int ndyn[MAX_LEVELS] = {0}, nall[MAX_LEVELS] = {0}, maxd = 0;
+  for (int b = 0; b < model->nb; b++) {
+    const int d = model->depth[b];
+    if (d < 0 || d >= MAX_LEVELS) return;
+    nall[d]++;
+    if (!model->fixed[b]) ndyn[d]++;
+    if (d > maxd) maxd = d;
+  }
+  for (int d = 0; d <= maxd; d++) if (nall[d] > PK_SLOTS) return;
+  int asg[MAX_LEVELS] = {0}, found = 0;
+  long total = 1;
+  for (int d = 0; d <= maxd; d++) total *= 3;
+  for (long code = 0; code < total && !found; code++) {
+    int fill[3] = {0, 0, 0};
+    long c = code;
+    bool ok = true;
+    for (int d = 0; d <= maxd; d++) { asg[d] = (int)(c % 3); c /= 3; fill[asg[d]] += ndyn[d]; if (fill[asg[d]] > PK_SLOTS) { ok = false; break; } }
+    if (ok) found = 1;
+  }
+  if (!found) return;
+  int fill[3] = {0, 0, 0};
+  for (int d = 0; d <= maxd; d++) {
+    unsigned used = 0;
+    int nm = 0;
+    for (int b = 0; b < model->nb; b++) {
+      if (model->depth[b] != d || model->fixed[b]) continue;
+      const int k = asg[d], s = fill[k]++;
+      t.pt_blk[b] = (int8_t)k; t.pt_slot[b] = (int8_t)s; t.pt_body[k][s] = (int8_t)b; t.pt_lvl[d][s] = (int8_t)b; t.pt_mbox[b] = (int8_t)nm++;
+      t.pt_lblk[d] = (int8_t)k;
+      used |= 1u << s;
+    }
+    if (d >= 1 && nm > t.pt_nmbox) t.pt_nmbox = nm;
+    for (int b = 0; b < model->nb; b++) {
+      if (model->depth[b] != d || !model->fixed[b]) continue;
+      int s = 0;
+      while (s < PK_SLOTS && ((used >> s) & 1u)) s++;
+      if (s == PK_SLOTS) return;
+      t.pt_slot[b] = (int8_t)s; t.pt_lvl[d][s] = (int8_t)b;
+      used |= 1u << s;
+    }
+  }
+  t.pt_ok = 1;
+}
 
 // host side: tree tables of a model (used by b200env_create and by the CPU lane emulator).  Returns 0, -1 (bodies not in
 // topological order) or -2 (too many children); *slots_ok = 0 when a tree depth has more bodies than the packed kernels have slots.
@@ -72,6 +133,7 @@ static inline int build_dev_blob(const b200_model_t* model, DevBlob& hb, int* sl
       if (b > 0) hb.t.child_rank[b] = rk[model->parent[b]]++;
     }
   }
+  build_pt_tables(model, hb.t);
   int next = 0;   // breadth-first record order (packed.cuh: neighbouring lanes of a tree depth -> neighbouring records)
   for (int d = 0; d < MAX_LEVELS; d++)
     for (int b = 0; b < model->nb; b++)

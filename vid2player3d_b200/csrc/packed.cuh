@@ -15,6 +15,12 @@
 #ifndef PK_SYNC_EVERY
 #define PK_SYNC_EVERY 1   // CTA barrier every n-th substep (keeps the CTA's warps on the same instruction-cache lines); A/B in profiles/r2n
 #endif
+#ifndef PK_WARPS
+#define PK_WARPS 7          // 7 warps x 4 envs x 7.2 KB records + 20 KB constants = 227 KB of shared memory: one CTA per SM
+#endif
+#ifndef PK_SHADOW
+#define PK_SHADOW 0         // experiment (b200env.cu): twice the warps, the second half running store-less copies of the first
+#endif
 #define EPW 4     // envs per warp
 #define BALL_SLOT 7   // the ball of env g is carried by lane (g, BALL_SLOT) in registers
 #define SLOTS 8   // lanes per env
@@ -71,7 +77,12 @@ template <int OFF, int N, int K> __device__ __forceinline__ void str_f(float* re
   }
 }
 template <int OFF, int N> __device__ __forceinline__ void ldr(const float* rec, float* r) { ldr_f<OFF, N, 0>(rec, r); }
-template <int OFF, int N> __device__ __forceinline__ void str(float* rec, const float* r) { str_f<OFF, N, 0>(rec, r); }
+#if defined(PK_SHADOW) && PK_SHADOW && defined(__CUDA_ARCH__)
+#define PK_IS_SHADOW ((int)threadIdx.x >= PK_WARPS * 32)
+#else
+#define PK_IS_SHADOW false
+#endif
+template <int OFF, int N> __device__ __forceinline__ void str(float* rec, const float* r) { if (PK_IS_SHADOW) return; str_f<OFF, N, 0>(rec, r); }
 template <int OFF, int N> __device__ __forceinline__ void ldr(const double* rec, double* r) {
 #pragma unroll
   for (int k = 0; k < N; k++) r[k] = rec[OFF + k];
@@ -211,7 +222,7 @@ __device__ __forceinline__ void pk_body(const DevBlob& B, const float* __restric
     contact_hull<T>(verts + (size_t)b * M.vmax * 3, M.vmax, nv, c, R, p, v, w, A, Bm, C, bn, bf, cf);
   }
   str<R_A, 28>(rec, ab);
-  rec[R_CFX] = cf[0];
+  if (!PK_IS_SHADOW) rec[R_CFX] = cf[0];
   str<R_CFY, 2>(rec, cf + 1);
   if (b > 0) {
     const int d0 = M.dof_of_body[b];
@@ -461,7 +472,7 @@ __device__ __forceinline__ void pk_contact_phase(const DevBlob& B, const float* 
       qmat(own, R);
       contact_apply<T>(verts + (size_t)b * M.vmax * 3, M.vmax, mask, c, R, own + 4, own + 10, own + 7, ab, ab + 6, ab + 15, ab + 21, ab + 24, cf);
       str<R_A, 28>(rec, ab);
-      rec[R_CFX] = cf[0];
+      if (!PK_IS_SHADOW) rec[R_CFX] = cf[0];
       str<R_CFY, 2>(rec, cf + 1);
     }
   }
@@ -553,7 +564,7 @@ __device__ __forceinline__ void pk_ball_contacts_extra(const DevBlob& B, const f
 // warp ~1 000 instructions per substep: +170 us per 8192-env step of config 3, profiles/r2m_ball_body.md).  Every lane of the warp calls
 // this (the shuffles are warp-wide); lane (g, s) tests bodies s, s + 8, s + 16, (24) of env g against the ball its group's lane
 // BALL_SLOT carries, the deepest contact wins (ties: the lower body index, as in the serial loop) and the ball's lane applies it.
-template <typename T>
+template <typename T, int RS = REC>   // RS: record stride (packed_t.cuh has its own record layout; the pose run is the same)
 __device__ __forceinline__ void pk_ball_contacts_group(const DevBlob& B, const float* verts, const PhysCfg<T>& c, const T* env, int lane, bool valid,
                                                        Ball<T>& ball) {
   const b200_model_t& M = B.m;
@@ -576,7 +587,7 @@ __device__ __forceinline__ void pk_ball_contacts_group(const DevBlob& B, const f
       const int nv = M.nverts[b];
       if (nv == 0 && !handle) continue;
       T st[13];   // Q[4] p[3] w[3] v[3]
-      ldr<R_Q, 13>(env + RIX(B, b) * REC, st);
+      ldr<R_Q, 13>(env + RIX(B, b) * RS, st);
       const T *Q = st, *p = st + 4, *w = st + 7, *v = st + 10;
       const T d[3] = {bp[0] - p[0], bp[1] - p[1], bp[2] - p[2]};
       const T d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
@@ -727,7 +738,7 @@ __device__ __forceinline__ void control_step_packed(const DevBlob& B, const floa
         ball_substep<T>(c, ball, has_racket, rQ, rp, rv, rw);
         T* ext = env + ENV_EXT;
 #pragma unroll
-        for (int k = 0; k < 3; k++) { ext[6 + k] = ball.rF[k]; ext[9 + k] = ball.rX[k]; }
+        for (int k = 0; k < 3; k++) { if (!PK_IS_SHADOW) { ext[6 + k] = ball.rF[k]; ext[9 + k] = ball.rX[k]; } }
       }
       if (c.ball_body) pk_ball_contacts_group<T>(B, verts, c, env, lane, valid, ball);   // all lanes: the body loop is spread over the group
       if (valid && s == 0) pk_root<T>(c, env);
@@ -775,7 +786,7 @@ template <typename T> __device__ __forceinline__ void pk_store_state(T* env, con
       str<R_WT, 3>(rec, L.wt);
     }
   }
-  if (lane == 0) {
+  if (lane == 0 && !PK_IS_SHADOW) {
     T* ext = env + ENV_EXT;
 #pragma unroll
     for (int k = 0; k < 3; k++) { ext[k] = extF[k]; ext[3 + k] = extT[k]; ext[6 + k] = T(0); ext[9 + k] = T(0); }
