@@ -1,0 +1,12 @@
+#!/bin/bash
+# A/B of the one-wave physics kernel (B200ENV_KERNEL=tmem, csrc/packed_t.cuh) against step_kernel_packed on a GPU box:
+# exact-equality tests first, then tools/perf_step.py (config 2) and tools/perf_federer.py (config 3) for both.
+cd "$(dirname "$0")/.."
+timeout 600 python -m pytest tests/test_gpu_tmem.py -x -q 2>&1 | tail -15
+for r in 1 2; do
+  timeout 200 python tools/perf_step.py 8192 160
+  B200ENV_KERNEL=tmem timeout 200 python tools/perf_step.py 8192 160
+done
+for k in packed tmem; do
+  echo "== federer B200ENV_KERNEL=$k"; B200ENV_KERNEL=$k timeout 300 python tools/perf_federer.py 2>&1 | tail -12
+done

@@ -30,6 +30,9 @@
 #ifndef WARPS_PER_CTA
 #define WARPS_PER_CTA 8  // A/B on B200 (profiles/r1_notes.md): 8 warps x 2 CTAs/SM, barrier per substep
 #endif
+#ifndef PT_STEP_SYNC
+#define PT_STEP_SYNC 1   // step_kernel_tmem: CTA barrier at every substep (keeps the 14 warps on the same instruction-cache lines)
+#endif
 #ifndef STEP_SYNC
 #define STEP_SYNC 0  // (packed kernel A/B: 434 us without any barrier, 416 with this one, 391 with POST_SYNC only)
 // legacy note: 1: CTA barrier at every substep boundary keeps the warps of a CTA on the same code (I-cache sharing)
@@ -67,6 +70,7 @@ struct b200env {
   int32_t *d_bin, *d_perm;             // [num_envs]
   uint32_t *d_pos, *d_cnt;             // [num_envs], [SORT_BINS]
   int packed3;                         // 1: the physics launch is step_kernel_packed3 (B200ENV_KERNEL=packed3)
+  int tmem;                            // 1: the physics launch is step_kernel_tmem (one wave, private fields in tensor memory; B200ENV_KERNEL=tmem|packed)
   int split;                           // 1: three launches (pre / physics / post), 0: one fused launch.  env B200ENV_SPLIT=0|1
   int env_first = 0, env_stride = 1;   // b200env_set_env_slice: local env i = row env_first + env_stride * i of the bound tensors
   int step_grid;
@@ -422,6 +426,7 @@ __device__ __forceinline__ void control_step(const DevBlob& B, const float* vert
 }
 
 #include "packed.cuh"
+#include "packed_t.cuh"
 // A/B variants that lost their measurements live outside the product build: -DB200ENV_WITH_PACKED3=1 compiles the
 // 2-envs-per-warp / 3-lanes-per-body kernel of tools/variants/packed3.cuh back in (B200ENV_KERNEL=packed3; 16 % slower, profiles/r1j, r2a)
 #ifndef B200ENV_WITH_PACKED3
@@ -798,7 +803,8 @@ __device__ __forceinline__ void epilogue_writeback(const b200_buffers_t& bf, con
 #pragma unroll
     for (int k = 0; k < 4; k++) rb[3 + k] = L.Q[k];
     float* cfo = bf.contact_forces + (e * bf.bodies_per_env + lane) * 3;
-    cfo[0] = cf[0]; cfo[1] = cf[1]; cfo[2] = cf[2];
+    if (cf) { cfo[0] = cf[0]; cfo[1] = cf[1]; cfo[2] = cf[2]; }
+    else if (!lc.dyn) { cfo[0] = 0.f; cfo[1] = 0.f; cfo[2] = 0.f; }   // step_kernel_tmem: the owners of the dynamic bodies wrote theirs in the last substep
   }
 
   if (cfg.task_mode == 1 && lane == 0) bf.progress_buf[e] += 1;  // vid2player player env: post_physics_step (:785-797) only advances
@@ -1187,6 +1193,231 @@ step_kernel_packed(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const
     }
     __syncwarp();
   }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// One-wave form of the middle launch (pre_kernel -> this -> post_kernel): csrc/packed_t.cuh.  14 warps x 4 envs = 56 envs per CTA
+// (3.5 KB of shared memory per env + the constant block = 220 KB), the lane-private fields of the bodies in tensor memory: warp w owns
+// the 32 TMEM lanes of quadrant w % 4 and the 128 columns starting at 128 * (w / 4).  8192 envs = 147 CTAs: ONE round on 148 SMs.
+#ifndef PT_WARPS
+#define PT_WARPS 14
+#endif
+__device__ __forceinline__ uint32_t pt_tmem_alloc(uint32_t* holder, int warp) {
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(holder)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *holder;
+}
+__device__ __forceinline__ void pt_tmem_free(uint32_t base, int warp) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512) : "memory");
+}
+
+__global__ void __launch_bounds__(PT_WARPS * 32, 1)
+step_kernel_tmem(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf, int num_envs,
+                 unsigned long long* __restrict__ ticket, int env_first, int env_stride, const float* __restrict__ ext_wrench) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t s_tmem;
+  load_blob(smem, gblob, blob_bytes, &mbar);
+  const DevBlob& B = *reinterpret_cast<const DevBlob*>(smem);
+  const b200_model_t& M = B.m;
+  const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* wrec = reinterpret_cast<float*>(smem + ((blob_bytes + 15) & ~15u)) + (size_t)warp * EPW * PT_ENV_STRIDE;
+  __shared__ b200_cfg_t s_cfg;
+  for (int k = threadIdx.x; k < (int)(sizeof(b200_cfg_t) / 4); k += blockDim.x) reinterpret_cast<uint32_t*>(&s_cfg)[k] = reinterpret_cast<const uint32_t*>(gcfg)[k];
+  const uint32_t tbase = pt_tmem_alloc(&s_tmem, warp);   // has a __syncthreads: s_cfg is complete behind it
+  const PrivTmem ps{tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * PT_WARP_COLS};
+  const b200_cfg_t& cfg = s_cfg;
+  LaneConst lc = lane_const(M, lane);
+  if (lc.active) lc.rix = B.t.rix[lane];
+  __shared__ PhysCfg<float> s_pc;   // derived constants in shared memory, not in ~50 registers per thread (128 registers at 14 warps)
+  if (threadIdx.x == 0) s_pc = make_phys_cfg<float>(cfg);
+  __syncthreads();
+  const PhysCfg<float>& pc = s_pc;
+  const int g = lane >> 3, s = lane & 7;
+  auto row = [&](int64_t i) -> int64_t { return env_first + (int64_t)env_stride * i; };
+  constexpr int BATCH = PT_WARPS * EPW;
+  __shared__ unsigned long long s_tk;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tk = atomicAdd(ticket, (unsigned long long)BATCH);
+    __syncthreads();
+    const int64_t e0 = (int64_t)s_tk;
+    if (e0 >= num_envs) break;
+    const bool full_batch = e0 + BATCH <= num_envs;
+    const int64_t eb = e0 + (int64_t)warp * EPW;
+    if (!full_batch && eb >= num_envs) continue;
+    {
+      // all loads of the warp's EPW envs are issued before the first use (one memory latency instead of EPW)
+      float rq[EPW][3], rw[EPW][3], rp[EPW][3], r1[EPW];   // r1: lane j < 13 holds root_states[e][j], 13 <= j < 19 the residual wrench
+      const int nd = M.nd;
+#pragma unroll
+      for (int k = 0; k < EPW; k++) {
+        const int64_t ek = eb + k < num_envs ? eb + k : (int64_t)num_envs - 1;   // ragged tail: re-read the last env, never stored
+        const int64_t e = row(ek);
+        if (lc.dyn && lane > 0) {
+          const float* ds = bf.dof_state + (e * nd + lc.dof0) * 2;
+#pragma unroll
+          for (int j = 0; j < 3; j++) { rq[k][j] = ds[2 * j]; rw[k][j] = ds[2 * j + 1]; rp[k][j] = bf.pd_targets[e * nd + lc.dof0 + j]; }
+        }
+        r1[k] = lane < 13 ? bf.root_states[e * bf.actors_per_env * 13 + lane] : (lane < 19 ? ext_wrench[e * 6 + lane - 13] : 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < EPW; k++) {
+        if (eb + k >= num_envs) break;
+        Lane<float> L;
+        float pdtar[3] = {0.f, 0.f, 0.f}, extF[3] = {0.f, 0.f, 0.f}, extT[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; j++) { L.Q[j] = 0.f; L.qj[j] = 0.f; }
+        L.Q[3] = 1.f; L.qj[3] = 1.f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { L.p[j] = 0.f; L.w[j] = 0.f; L.v[j] = 0.f; L.wt[j] = 0.f; }
+        float rr[19];
+#pragma unroll
+        for (int j = 0; j < 19; j++) rr[j] = __shfl_sync(FULL, r1[k], j);
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 3; j++) { L.p[j] = rr[j]; L.v[j] = rr[7 + j]; L.w[j] = rr[10 + j]; extF[j] = rr[13 + j]; extT[j] = rr[16 + j]; }
+#pragma unroll
+          for (int j = 0; j < 4; j++) L.Q[j] = rr[3 + j];
+          qnormalize(L.Q);
+        }
+        if (lc.dyn && lane > 0) {
+#pragma unroll
+          for (int j = 0; j < 3; j++) { L.wt[j] = rw[k][j]; pdtar[j] = rp[k][j]; }
+          qexp(rq[k], L.qj);
+        }
+        pt_stage_in<float>(wrec + k * PT_ENV_STRIDE, lc, lane, L, pdtar, extF, extT);
+      }
+    }
+    __syncwarp();
+    const bool valid = eb + g < num_envs;
+    pt_adopt<float>(B, wrec, lane, valid, ps);
+    Ball<float> ball;
+    ball_clear(ball);
+    const int64_t erow_g = row(valid ? eb + g : eb);
+    if (cfg.has_ball && valid && s == BALL_SLOT) ball_load(bf, erow_g, ball);
+    float* cf_env = bf.contact_forces + erow_g * bf.bodies_per_env * 3;
+    control_step_t<float>(B, verts, pc, wrec, lane, valid, ball, ps, cf_env, PT_STEP_SYNC && full_batch);
+    if (cfg.has_ball && valid && s == BALL_SLOT) ball_writeback(bf, erow_g, ball);
+    pt_publish<float>(B, wrec, lane, valid, ps);
+    __syncwarp();
+    for (int k = 0; k < EPW; k++) {
+      if (eb + k >= num_envs) break;
+      const int64_t e = row(eb + k);
+      Lane<float> L;
+      float dq[3];
+      pt_load_state<float>(wrec + k * PT_ENV_STRIDE, lc, lane, L);
+      epilogue_writeback(bf, cfg, M, lc, lane, e, L, nullptr, dq);
+    }
+    __syncwarp();
+  }
+  pt_tmem_free(tbase, warp);
+}
+
+// the test entry of the same device code (b200env_physics_only with the handle in tmem mode): float only - the private store of the
+// double instantiation does not fit the tensor memory; float64 parity of this form is checked on the CPU lane emulator (tests/emu)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+physics_kernel_tmem(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b200_cfg_t* __restrict__ gcfg, int n, int n_steps,
+                    float* root, float* dof_pos, float* dof_vel, const float* pd_tar, const float* ext, float* rb_out, float* contact_out,
+                    float* ballio, int32_t* hits) {
+  typedef float T;
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t s_tmem;
+  load_blob(smem, gblob, blob_bytes, &mbar);
+  const DevBlob& B = *reinterpret_cast<const DevBlob*>(smem);
+  const b200_model_t& M = B.m;
+  const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  T* wrec = reinterpret_cast<T*>(smem + ((blob_bytes + 15) & ~15u)) + (size_t)warp * EPW * PT_ENV_STRIDE;
+  const uint32_t tbase = pt_tmem_alloc(&s_tmem, warp);
+  const PrivTmem ps{tbase + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * PT_WARP_COLS};
+  const int64_t eb = ((int64_t)blockIdx.x * WARPS + warp) * EPW;
+  if (eb < n) {
+    LaneConst lc = lane_const(M, lane);
+    if (lc.active) lc.rix = B.t.rix[lane];
+    const int nb = M.nb, nd = M.nd;
+    PhysCfg<T> pc = make_phys_cfg<T>(*gcfg);
+    const bool with_ball = pc.has_ball && ballio != nullptr;
+    pc.has_ball = with_ball;
+    const int g = lane >> 3, s = lane & 7;
+    for (int k = 0; k < EPW; k++) {
+      const int64_t e = eb + k;
+      if (e >= n) break;
+      Lane<T> L;
+      for (int j = 0; j < 4; j++) { L.Q[j] = 0; L.qj[j] = 0; }
+      L.Q[3] = 1; L.qj[3] = 1;
+      for (int j = 0; j < 3; j++) { L.p[j] = 0; L.w[j] = 0; L.v[j] = 0; L.wt[j] = 0; }
+      T pdt[3] = {0, 0, 0}, eF[3] = {0, 0, 0}, eT[3] = {0, 0, 0};
+      if (lane == 0) {
+        const T* rs = root + e * 13;
+        for (int j = 0; j < 3; j++) { L.p[j] = rs[j]; L.v[j] = rs[7 + j]; L.w[j] = rs[10 + j]; }
+        for (int j = 0; j < 4; j++) L.Q[j] = rs[3 + j];
+        qnormalize(L.Q);
+        if (ext) for (int j = 0; j < 3; j++) { eF[j] = ext[e * 6 + j]; eT[j] = ext[e * 6 + 3 + j]; }
+      }
+      if (lc.dyn && lane > 0) {
+        T q[3];
+        for (int j = 0; j < 3; j++) { q[j] = dof_pos[e * nd + lc.dof0 + j]; L.wt[j] = dof_vel[e * nd + lc.dof0 + j]; pdt[j] = pd_tar[e * nd + lc.dof0 + j]; }
+        qexp(q, L.qj);
+      }
+      pt_stage_in<T>(wrec + k * PT_ENV_STRIDE, lc, lane, L, pdt, eF, eT);
+    }
+    __syncwarp();
+    const bool valid = eb + g < n;
+    pt_adopt<T>(B, wrec, lane, valid, ps);
+    Ball<T> ball;
+    ball_clear(ball);
+    if (with_ball && valid && s == BALL_SLOT) {
+      const int64_t e = eb + g;
+      for (int j = 0; j < 3; j++) { ball.p[j] = ballio[e * 13 + j]; ball.v[j] = ballio[e * 13 + 7 + j]; ball.w[j] = ballio[e * 13 + 10 + j]; }
+    }
+    T* cf_env = (valid && contact_out) ? contact_out + (eb + g) * nb * 3 : nullptr;
+    for (int st_ = 0; st_ < n_steps; st_++) {
+      control_step_t<T>(B, verts, pc, wrec, lane, valid, ball, ps, cf_env, false);
+      if (st_ + 1 < n_steps) pt_requantize<T>(B, lane, valid, ps);   // the state crosses control steps as exp-map coordinates
+    }
+    pt_publish<T>(B, wrec, lane, valid, ps);
+    __syncwarp();
+    for (int k = 0; k < EPW; k++) {
+      const int64_t e = eb + k;
+      if (e >= n) break;
+      Lane<T> L;
+      pt_load_state<T>(wrec + k * PT_ENV_STRIDE, lc, lane, L);
+      if (lane == 0) {
+        T* rs = root + e * 13;
+        for (int j = 0; j < 3; j++) { rs[j] = L.p[j]; rs[7 + j] = L.v[j]; rs[10 + j] = L.w[j]; }
+        for (int j = 0; j < 4; j++) rs[3 + j] = L.Q[j];
+      }
+      if (lc.dyn && lane > 0) {
+        T q[3];
+        qlog(L.qj, q);
+        for (int j = 0; j < 3; j++) { dof_pos[e * nd + lc.dof0 + j] = q[j]; dof_vel[e * nd + lc.dof0 + j] = L.wt[j]; }
+      }
+      if (lc.active) {
+        T* rb = rb_out + (e * nb + lane) * 13;
+        for (int j = 0; j < 3; j++) { rb[j] = L.p[j]; rb[7 + j] = L.v[j]; rb[10 + j] = L.w[j]; }
+        for (int j = 0; j < 4; j++) rb[3 + j] = L.Q[j];
+        if (contact_out && !lc.dyn) for (int j = 0; j < 3; j++) contact_out[(e * nb + lane) * 3 + j] = T(0);
+      }
+    }
+    if (with_ball && valid && s == BALL_SLOT) {
+      const int64_t e = eb + g;
+      for (int j = 0; j < 3; j++) { ballio[e * 13 + j] = ball.p[j]; ballio[e * 13 + 7 + j] = ball.v[j]; ballio[e * 13 + 10 + j] = ball.w[j]; }
+      if (hits) hits[e] = ball.hits;
+    }
+  }
+  pt_tmem_free(tbase, warp);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1834,6 +2065,8 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
 #endif
   const char* so = getenv("B200ENV_SORT");
   h->sort = h->split && !h->packed3 && so && strcmp(so, "1") == 0;
+  // one-wave form (csrc/packed_t.cuh): needs the split form and a tree that fits 3 column blocks x 8 owner slots
+  h->tmem = h->split && !h->packed3 && !h->sort && hb.t.pt_ok && hb.t.pt_nmbox <= PT_MBOX_MAX && kv && strcmp(kv, "tmem") == 0;
   if (cfg->has_ball && cfg->ball_body_contact && !h->packed) {
     delete h;
     return fail(-2, "b200env_create: ball_body_contact needs the packed kernels (the lane-per-body kernel does not have it)%s");
@@ -1951,14 +2184,22 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
   if (!h->bound || (!h->has_ml && h->cfg.task_mode == 0)) return fail(-4, "b200env_step: bind buffers and a motion lib first%s");
   cudaSetDevice(h->device);
   if (h->packed) {
-    const size_t psmem = ((h->blob_bytes + 15) & ~(size_t)15) + (h->split ? 0 : PK_WARPS * PK_SCRATCH * sizeof(float)) +
-                         (size_t)PK_WARPS * EPW * ENV_STRIDE * sizeof(float);
-    const int batch = PK_WARPS * EPW;
+    const size_t psmem = h->tmem ? ((h->blob_bytes + 15) & ~(size_t)15) + (size_t)PT_WARPS * EPW * PT_ENV_STRIDE * sizeof(float)
+                                 : ((h->blob_bytes + 15) & ~(size_t)15) + (h->split ? 0 : PK_WARPS * PK_SCRATCH * sizeof(float)) +
+                                       (size_t)PK_WARPS * EPW * ENV_STRIDE * sizeof(float);
+    const int batch = (h->tmem ? PT_WARPS : PK_WARPS) * EPW;
     const int need = (h->num_envs + batch - 1) / batch;
     if (h->step_grid == 0) {
-      CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-      CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      if (!h->tmem) {
+        CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        CUDA_OK(cudaFuncSetAttribute(step_kernel_packed<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      }
       int per_sm = 0, sms = 0;
+      if (h->tmem) {
+        CUDA_OK(cudaFuncSetAttribute(step_kernel_tmem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_tmem, PT_WARPS * 32, psmem));
+        if (per_sm > 1) per_sm = 1;   // the CTA takes the SM's whole tensor memory
+      } else
 #if B200ENV_WITH_PACKED3
       if (h->packed3) {
         CUDA_OK(cudaFuncSetAttribute(step_kernel_packed3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
@@ -1997,6 +2238,10 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
         if (cudaEventCreate(&tv0) == cudaSuccess && cudaEventCreate(&tv1) == cudaSuccess) cudaEventRecord(tv0, (cudaStream_t)stream);
         else tv0 = tv1 = nullptr;
       }
+      if (h->tmem)
+        step_kernel_tmem<<<h->step_grid, PT_WARPS * 32, psmem, (cudaStream_t)stream>>>(
+            (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, h->bufs, h->num_envs, h->d_ticket, h->env_first, h->env_stride, h->d_ext);
+      else
 #if B200ENV_WITH_PACKED3
       if (h->packed3)
         step_kernel_packed3<<<h->step_grid, PK3_WARPS * 32, psmem, (cudaStream_t)stream>>>(
@@ -2143,7 +2388,14 @@ int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_st
   cudaSetDevice(h->device);
   if (h->packed) {
     const size_t bsm = (h->blob_bytes + 15) & ~(size_t)15;
-    if (prec == 0) {
+    if (prec == 0 && h->tmem) {
+      constexpr int W = 6;   // more than 4 warps: windows in two column ranges of the tensor memory
+      const size_t sm = bsm + (size_t)W * EPW * PT_ENV_STRIDE * sizeof(float);
+      CUDA_OK(cudaFuncSetAttribute(physics_kernel_tmem<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      physics_kernel_tmem<W><<<(n + W * EPW - 1) / (W * EPW), W * 32, sm, (cudaStream_t)stream>>>(
+          (const DevBlob*)h->d_blob, (uint32_t)h->blob_bytes, h->d_cfg, n, n_steps, (float*)root, (float*)dof_pos, (float*)dof_vel,
+          (const float*)pd_tar, (const float*)ext_wrench, (float*)rb_out, (float*)contact_out, (float*)ball, ball_hits);
+    } else if (prec == 0) {
       constexpr int W = 4;
       const size_t sm = bsm + (size_t)W * EPW * ENV_STRIDE * sizeof(float);
       CUDA_OK(cudaFuncSetAttribute(physics_kernel_packed<float, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -2185,6 +2437,7 @@ int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_st
 }
 
 int64_t b200env_launch_count(b200env_handle h) { return h ? h->launches : 0; }
+int32_t b200env_kernel_form(b200env_handle h) { return !h ? -1 : (h->tmem ? 3 : (h->packed3 ? 2 : (h->packed ? 1 : 0))); }
 
 int b200env_set_kernel_timing(b200env_handle h, int32_t on) {
   if (!h) return fail(-1, "b200env_set_kernel_timing: null handle%s");

@@ -24,10 +24,15 @@ enum { PT_SQJ = 13, PT_SPD = 17, PT_SWT = 20 };   // staging of joint rotation /
 #define PT_MAXREC B200_MAX_BODIES_PK
 #define PT_MBOX_MAX 6
 #define PT_MB 28
-enum { PT_ENV_MBOX = PT_MAXREC * PT_REC, PT_ENV_EXT = PT_ENV_MBOX + PT_MBOX_MAX * PT_MB, PT_ENV_STRIDE = PT_ENV_EXT + 12 };
+#define PT_BALL_T 24        // the env's ball (Ball<T>) parked in the env's shared memory between its substeps: 24 values of T cover the struct
+enum { PT_ENV_MBOX = PT_MAXREC * PT_REC, PT_ENV_EXT = PT_ENV_MBOX + PT_MBOX_MAX * PT_MB, PT_ENV_BALL = PT_ENV_EXT + 12,
+       PT_ENV_STRIDE = PT_ENV_BALL + PT_BALL_T };
 // private fields of a body: column offsets inside its block (runs start on the boundary of the widest shape that moves them)
 enum { TQ_QJ = 0, TQ_WT = 4, TQ_PD = 7, TQ_R = 10, TQ_ZETA = 13, TQ_U = 19, TQ_E = 22, TQ_C = 28, TQ_BN = 34, TQ_BF = 37, PT_COLS = 40 };
 #define PT_BLOCKS 3
+#ifndef PT_ABL
+#define PT_ABL 0   // ablation of the phases (register-pressure hunting): 1 body pass, 2 backward, 3 forward, 4 root / ball
+#endif
 #define PT_WARP_COLS 128    // tensor-memory columns of one warp (14 warps: at most 4 per lane quadrant -> 4 x 128 = 512)
 
 // private store as plain memory: one array of PT_BLOCKS * PT_COLS values per lane
@@ -246,9 +251,10 @@ __device__ __forceinline__ void pt_body(const DevBlob& B, const float* __restric
 }
 
 // backward step of one dynamic non-root body, registers only: ab = A[6] Bm[9] C[6] bn[3] bf[3] (children already added), rzu = r[3]
-// zeta[6] u[3], E -> D^-1 (in place), u -> u - bn (in rzu[9..11]), out[28] = articulated inertia / bias shifted to the parent origin
+// zeta[6] u[3], E -> D^-1 (in place), u -> u - bn (in rzu[9..11]); the articulated inertia / bias shifted to the parent origin goes to
+// the body's hand-over entry mbox[28]
 template <typename T>
-__device__ __forceinline__ void pt_backward(const T* ab, T* rzu, T* E, T* out) {
+__device__ __forceinline__ void pt_backward(const T* ab, T* rzu, T* E, T* mbox) {
   const T *A = ab, *Bm = ab + 6, *C = ab + 15, *bn = ab + 21, *bf = ab + 24, *r = rzu, *zeta = rzu + 3;
   T u[3] = {rzu[9], rzu[10], rzu[11]};
   T D[6], Dinv[6];
@@ -316,6 +322,7 @@ __device__ __forceinline__ void pt_backward(const T* ab, T* rzu, T* E, T* out) {
     cross3(r, aB + 3 * j, x);
     P2[j] = x[0]; P2[3 + j] = x[1]; P2[6 + j] = x[2];
   }
+  T out[28];
   out[0] = aA[0] + P1[0] + P2[0];
   out[1] = aA[1] + P1[4] + P2[4];
   out[2] = aA[2] + P1[8] + P2[8];
@@ -331,6 +338,7 @@ __device__ __forceinline__ void pt_backward(const T* ab, T* rzu, T* E, T* out) {
 #pragma unroll
   for (int k = 0; k < 3; k++) { out[21 + k] = an[k] + rxf[k]; out[24 + k] = af[k]; }
   out[27] = T(0);
+  str<0, 28>(mbox, out);
 }
 
 // root: 6 x 6 solve by block elimination, registers only (ab: the root's articulated inertia / bias with its children added)
@@ -445,6 +453,12 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
   const int g = lane >> 3, s = lane & 7;
   T* env = wrec + g * PT_ENV_STRIDE;
   const int rblk = B.t.pt_blk[0], rslot = B.t.pt_slot[0];
+  // the ball lives in the env's shared memory during the step (24 registers less in every phase of every lane); the lane that carries
+  // it takes it into registers for its own substep only
+  static_assert(sizeof(Ball<T>) <= PT_BALL_T * sizeof(T), "Ball<T> must fit its parking slot");
+  Ball<T>* sball = reinterpret_cast<Ball<T>*>(env + PT_ENV_BALL);
+  const bool ball_lane = c.has_ball && valid && s == BALL_SLOT;
+  if (ball_lane) *sball = ball;
   // kinematics of the start state, root -> leaves; every later FK is fused into the forward pass of the substep before it
   for (int d = 1; d <= M.max_depth; d++) {
     const int b = valid ? B.t.pt_lvl[d][s] : -1;
@@ -456,19 +470,20 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
     __syncwarp();
   }
   for (int sim = 0; sim < c.cfi; sim++) {
-    if (c.has_ball && valid && s == BALL_SLOT) {
-      ball_aero<T>(ball.v, ball.w, c.spin_scale, ball.fa);
+    if (ball_lane) {
+      Ball<T>& bl = *sball;
+      ball_aero<T>(bl.v, bl.w, c.spin_scale, bl.fa);
       const T thr = c.substeps > 2 ? c.bR * T(6) : c.bR * T(4);
-      if (!ball.has_bounce && ball.p[2] <= thr) {
-        ball.has_bounce = 1; ball.bounce_now = 1;
-        ball.bpos[0] = ball.p[0]; ball.bpos[1] = ball.p[1]; ball.bpos[2] = ball.p[2];
+      if (!bl.has_bounce && bl.p[2] <= thr) {
+        bl.has_bounce = 1; bl.bounce_now = 1;
+        bl.bpos[0] = bl.p[0]; bl.bpos[1] = bl.p[1]; bl.bpos[2] = bl.p[2];
       }
     }
     for (int sub = 0; sub < c.substeps; sub++) {
       if (cta_sync) __syncthreads();
       const bool last = sim == c.cfi - 1 && sub == c.substeps - 1;
       // 1. per-body inertia / bias / ground contact / joint drive: the owner's three bodies, one per column block
-      for (int k = 0; k < PT_BLOCKS; k++) {
+      for (int k = 0; k < (PT_ABL == 1 ? 0 : PT_BLOCKS); k++) {
         const int b = valid ? B.t.pt_body[k][s] : -1;
         T jp[10], cbb[12], E[6], u[3], cf[3];   // jp: qj[4] wt[3] pd[3]
         ps.wait_st();
@@ -481,12 +496,12 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
         ps.template st<TQ_U, 3>(k, u); ps.template st<TQ_E, 6>(k, E); ps.template st<TQ_C, 12>(k, cbb);
       }
       // 2. articulated inertia, leaves -> root
-      for (int d = M.max_depth; d >= 1; d--) {
+      for (int d = (PT_ABL == 2 ? 0 : M.max_depth); d >= 1; d--) {
         const int blk = B.t.pt_lblk[d];
         if (blk < 0) continue;                    // a depth of welded bodies only (warp-uniform)
         int b = valid ? B.t.pt_lvl[d][s] : -1;
         if (b >= 0 && M.fixed[b]) b = -1;
-        T ab[28], rzu[12], E[6], out[28];
+        T ab[28], rzu[12], E[6];
         ps.wait_st();
         ps.template ld<TQ_C, 12>(blk, ab + 15); ps.template ld<TQ_R, 12>(blk, rzu); ps.template ld<TQ_E, 6>(blk, E);
         ps.wait_ld();
@@ -494,10 +509,9 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
           T* rec = env + RIX(B, b) * PT_REC;
           ldr<PT_A, 15>(rec, ab);
           if (pt_add_children<T>(B, env, b, ab) > 0) str<PT_A, 15>(rec, ab);   // the forward step needs A / Bm with the children in
-          pt_backward<T>(ab, rzu, E, out);
         }
         __syncwarp();                             // every lane has taken the entries of depth d + 1 out of the mailbox
-        if (b >= 0) str<0, 28>(env + PT_ENV_MBOX + B.t.pt_mbox[b] * PT_MB, out);
+        if (b >= 0) pt_backward<T>(ab, rzu, E, env + PT_ENV_MBOX + B.t.pt_mbox[b] * PT_MB);   // hand-over entry written as it is computed
         ps.template st<TQ_E, 6>(blk, E); ps.template st<TQ_U, 3>(blk, rzu + 9);
         __syncwarp();
       }
@@ -507,24 +521,27 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       ps.wait_st();
       ps.template ld<TQ_C, 12>(rblk, rab + 15);
       ps.wait_ld();
-      if (c.has_ball && valid && s == BALL_SLOT) {
-        T rQ[4] = {0, 0, 0, 1}, rp[3] = {0, 0, 0}, rv[3] = {0, 0, 0}, rw[3] = {0, 0, 0};
-        const bool has_racket = c.racket_body >= 0;
-        if (has_racket) {
-          const T* rr = env + RIX(B, c.racket_body) * PT_REC;
-          T rs[13];
-          ldr<PT_Q, 13>(rr, rs);
+      if (PT_ABL != 4 && c.has_ball) {
+        Ball<T>& bl = *sball;   // worked on in place (every lane of the group may read it, only the ball's lane writes)
+        if (ball_lane) {
+          T rQ[4] = {0, 0, 0, 1}, rp[3] = {0, 0, 0}, rv[3] = {0, 0, 0}, rw[3] = {0, 0, 0};
+          const bool has_racket = c.racket_body >= 0;
+          if (has_racket) {
+            const T* rr = env + RIX(B, c.racket_body) * PT_REC;
+            T rs[13];
+            ldr<PT_Q, 13>(rr, rs);
 #pragma unroll
-          for (int k = 0; k < 4; k++) rQ[k] = rs[k];
+            for (int k = 0; k < 4; k++) rQ[k] = rs[k];
 #pragma unroll
-          for (int k = 0; k < 3; k++) { rp[k] = rs[4 + k]; rw[k] = rs[7 + k]; rv[k] = rs[10 + k]; }
+            for (int k = 0; k < 3; k++) { rp[k] = rs[4 + k]; rw[k] = rs[7 + k]; rv[k] = rs[10 + k]; }
+          }
+          ball_substep<T>(c, bl, has_racket, rQ, rp, rv, rw);
+          T* ext = env + PT_ENV_EXT;
+#pragma unroll
+          for (int k = 0; k < 3; k++) { ext[6 + k] = bl.rF[k]; ext[9 + k] = bl.rX[k]; }
         }
-        ball_substep<T>(c, ball, has_racket, rQ, rp, rv, rw);
-        T* ext = env + PT_ENV_EXT;
-#pragma unroll
-        for (int k = 0; k < 3; k++) { ext[6 + k] = ball.rF[k]; ext[9 + k] = ball.rX[k]; }
+        if (c.ball_body) pk_ball_contacts_group<T, PT_REC>(B, verts, c, env, lane, valid, bl);   // all lanes: the body loop is spread over the group
       }
-      if (c.ball_body) pk_ball_contacts_group<T, PT_REC>(B, verts, c, env, lane, valid, ball);   // all lanes: the body loop is spread over the group
       if (valid && s == rslot) {
         T acc[6];
         ldr<PT_A, 15>(env, rab);
@@ -537,7 +554,7 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       __syncwarp();
       // 4. root -> leaves: accelerations + joint integration of a body, then at once its kinematics for the next substep
       //    (its parent's new pose is already in place); welded bodies only have the kinematics
-      for (int d = 1; d <= M.max_depth; d++) {
+      for (int d = 1; d <= (PT_ABL == 3 ? 0 : M.max_depth); d++) {
         const int b = valid ? B.t.pt_lvl[d][s] : -1;
         const int blk = B.t.pt_lblk[d];
         T Dinv[6], rzu[12], jq[7];
@@ -555,6 +572,7 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       }
     }
   }
+  if (ball_lane) ball = *sball;
 }
 
 // lane-per-body prologue (lane = body of ONE env) -> records: root pose, and the joint state / PD target of the jointed bodies staged

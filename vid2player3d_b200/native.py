@@ -14,7 +14,7 @@ _lib = None
 SYMBOLS = ["b200env_abi_version", "b200env_last_error", "b200env_create", "b200env_destroy", "b200env_bind",
            "b200env_set_motion_lib", "b200env_step", "b200env_reset", "b200env_motion_state", "b200env_obs_imitation",
            "b200env_physics_only", "b200env_launch_count", "b200env_set_env_slice", "b200env_motion_context", "b200env_set_kernel_timing",
-           "b200env_kernel_ms", "b200env_obs_imitation_rows", "b200env_set_hull_faces"]
+           "b200env_kernel_ms", "b200env_obs_imitation_rows", "b200env_set_hull_faces", "b200env_kernel_form"]
 
 
 def lib():
@@ -166,6 +166,11 @@ class Env:
         _check(lib().b200env_physics_only(self._h, C.c_int32(prec), C.c_int32(int(root.shape[0])), C.c_int32(n_steps),
                                           _ptr(root), _ptr(dof_pos), _ptr(dof_vel), _ptr(pd_tar), _ptr(ext_wrench),
                                           _ptr(rb_out), _ptr(contact_out), _ptr(ball), _ptr(ball_hits), _stream()))
+
+    @property
+    def kernel_form(self):
+        """'lane' | 'packed' | 'packed3' | 'tmem' (include/b200env.h: b200env_kernel_form)"""
+        return ("lane", "packed", "packed3", "tmem")[int(lib().b200env_kernel_form(self._h))]
 
     @property
     def launch_count(self):
