@@ -1,8 +1,11 @@
 #!/bin/bash
 # A/B of the one-wave physics kernel (B200ENV_KERNEL=tmem, csrc/packed_t.cuh) against step_kernel_packed on a GPU box:
-# exact-equality tests first, then tools/perf_step.py (config 2) and tools/perf_federer.py (config 3) for both.
+# equality tests first (exact in a -fmad=false build, rounding-level in the product build), then tools/perf_step.py (config 2) and
+# tools/perf_federer.py (config 3) for both.
 cd "$(dirname "$0")/.."
-timeout 600 python -m pytest tests/test_gpu_tmem.py -x -q 2>&1 | tail -15
+D=$PWD/vid2player3d_b200/lib
+[ -e $D/ab_nofma.so ] && { echo "== exact equality, -fmad=false build"; B200ENV_LIB=$D/ab_nofma.so B200_EXPECT_EXACT=1 timeout 600 python -m pytest tests/test_gpu_tmem.py -q -s 2>&1 | grep -v "^E   \|^    \|^$" | tail -60; }
+echo "== product build"; timeout 600 python -m pytest tests/test_gpu_tmem.py -q -s 2>&1 | grep -v "^E   \|^    \|^$" | tail -80
 for r in 1 2; do
   timeout 200 python tools/perf_step.py 8192 160
   B200ENV_KERNEL=tmem timeout 200 python tools/perf_step.py 8192 160

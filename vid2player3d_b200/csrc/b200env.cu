@@ -2135,7 +2135,7 @@ int b200env_set_hull_faces(b200env_handle h, const float* planes, const uint8_t*
   t.face_tris = h->d_face_tris;
   t.face_tmax = tmax;
   for (int b = 0; b < nb; b++) t.ntris[b] = ntris[b];
-  const size_t o0 = offsetof(DevTree, face_planes), o1 = sizeof(DevTree);
+  const size_t o0 = offsetof(DevTree, face_planes), o1 = offsetof(DevTree, pt_blk);   // the face fields only: the tables behind them stay
   CUDA_OK(cudaMemcpy((char*)h->d_blob + offsetof(DevBlob, t) + o0, (const char*)&t + o0, o1 - o0, cudaMemcpyHostToDevice));
   return 0;
 }
