@@ -58,6 +58,10 @@ def parse():
     return p.parse_args()
 
 
+PHYS_KERNEL_NAME = {"tmem": "step_kernel_tmem (56 envs per SM, lane-private body fields in tensor memory: one round for 8192 envs)",
+                    "packed": "step_kernel_packed<split> (28 envs per SM, two rounds)", "packed3": "step_kernel_packed3", "lane": "step_kernel"}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -780,12 +784,13 @@ def main():
         "gpu_launches": int((graph_nodes + (reset_nodes or 0) + 1) * K) if graph_nodes else int(step_launches),
         "gpu_launches_note": "kernel nodes of the step graph + the reset graph (+ the mask kernel) x timed steps, counted from the graphs' DOT dumps; "
                              "our own kernels among them per step: 22 (step graph) + 7 (reset graph)",
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": 8026112,
-                     "traffic_note": "from_profile: dram__bytes_read.sum + dram__bytes_write.sum of ONE step_kernel_packed<split> launch (the dominant "
-                                     "kernel) in the ncu --set full capture profiles/r2i_step_kernel_ncu.md; not measured by this run",
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": {"tmem": 15862272, "packed": 8026112}.get(task._env.kernel_form),
+                     "traffic_note": "from_profile: dram__bytes_read.sum + dram__bytes_write.sum of ONE physics launch (the dominant kernel) in the "
+                                     "ncu --set full captures profiles/r2i_step_kernel_ncu.md (step_kernel_packed) / profiles/r2t_tmem.md "
+                                     "(step_kernel_tmem: 15.9 MB); not measured by this run",
                      "kernel": "one env step = one CUDA graph (motion targets, FK, 734-d obs, decoder + policy GEMMs, physics, post step); dominant launch "
-                               "step_kernel_packed<split>", "kernel_ms": ms_step, "algorithmic_bytes_per_env_step": ALGO_BYTES_CFG3,
-                     "dominant_kernel": {"name": "step_kernel_packed<split> (12 substeps + ball)", "ms": phys_ms, "launches_timed": 10,
+                               + PHYS_KERNEL_NAME[task._env.kernel_form], "kernel_ms": ms_step, "algorithmic_bytes_per_env_step": ALGO_BYTES_CFG3,
+                     "dominant_kernel": {"name": PHYS_KERNEL_NAME[task._env.kernel_form] + " (12 substeps + ball)", "ms": phys_ms, "launches_timed": 10,
                                          "share_of_step": phys_ms / ms_step if ms_step > 0 else None, "algorithmic_bytes_per_env": PHYS_BYTES_CFG3,
                                          "GBps": PHYS_BYTES_CFG3 * N / (phys_ms * 1e-3) / 1e9 if phys_ms > 0 else None},
                      "peak_source": peak_src,

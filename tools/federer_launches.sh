@@ -11,7 +11,7 @@ rows = [r for r in csv.reader(open("gpurun_out/${TAG}_federer_launches.csv")) if
 h = rows[0]; ki, vi = h.index("Kernel Name"), h.index("Metric Value")
 names = [r[ki] for r in rows[1:]]
 # one step = the launches between two consecutive physics launches of the LAST replays (steady state)
-idx = [i for i, n in enumerate(names) if "step_kernel_packed" in n]
+idx = [i for i, n in enumerate(names) if "step_kernel_packed" in n or "step_kernel_tmem" in n]
 print("launches total", len(names), "physics launches", len(idx))
 if len(idx) >= 3:
     a, b = idx[-3], idx[-2]

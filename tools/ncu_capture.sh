@@ -5,7 +5,7 @@
 TAG=${1:-r2}
 cd "$(dirname "$0")/.."
 export B200_BENCH_PROFILE=1
-timeout 900 ncu --set full --clock-control none --import-source on --graph-profiling node --profile-from-start off -k regex:step_kernel_packed -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on --graph-profiling node --profile-from-start off -k "regex:step_kernel_(packed|tmem)" -c 1 \
   -o gpurun_out/${TAG}_step -f python bench.py --steps 4 --warmup 3 --legs none --no-cpu-baseline > /dev/null 2> gpurun_out/${TAG}_step_ncu.err
 timeout 900 ncu --set full --clock-control none --import-source on --graph-profiling node --profile-from-start off -k regex:linear_kernel -c 9 \
   -o gpurun_out/${TAG}_gemm -f python bench.py --steps 4 --warmup 3 --legs none --no-cpu-baseline > /dev/null 2> gpurun_out/${TAG}_gemm_ncu.err

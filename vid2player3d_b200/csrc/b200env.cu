@@ -1229,7 +1229,8 @@ step_kernel_tmem(const DevBlob* __restrict__ gblob, uint32_t blob_bytes, const b
   const DevBlob& B = *reinterpret_cast<const DevBlob*>(smem);
   const b200_model_t& M = B.m;
   const float* verts = reinterpret_cast<const float*>(smem + sizeof(DevBlob));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // the shuffle tells the compiler that warp is warp-uniform: the
+                                                                                          // window addresses of the private store stay in uniform registers
   float* wrec = reinterpret_cast<float*>(smem + ((blob_bytes + 15) & ~15u)) + (size_t)warp * EPW * PT_ENV_STRIDE;
   __shared__ b200_cfg_t s_cfg;
   for (int k = threadIdx.x; k < (int)(sizeof(b200_cfg_t) / 4); k += blockDim.x) reinterpret_cast<uint32_t*>(&s_cfg)[k] = reinterpret_cast<const uint32_t*>(gcfg)[k];
@@ -2066,7 +2067,9 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   const char* so = getenv("B200ENV_SORT");
   h->sort = h->split && !h->packed3 && so && strcmp(so, "1") == 0;
   // one-wave form (csrc/packed_t.cuh): needs the split form and a tree that fits 3 column blocks x 8 owner slots
-  h->tmem = h->split && !h->packed3 && !h->sort && hb.t.pt_ok && hb.t.pt_nmbox <= PT_MBOX_MAX && kv && strcmp(kv, "tmem") == 0;
+  // It is the default where it applies (round 2: -8 % per config-2 step, -6 % per config-3 step, profiles/r2t_tmem.md);
+  // B200ENV_KERNEL=packed keeps the two-round kernel for A/B.
+  h->tmem = h->split && !h->packed3 && !h->sort && hb.t.pt_ok && hb.t.pt_nmbox <= PT_MBOX_MAX && !(kv && strcmp(kv, "packed") == 0);
   if (cfg->has_ball && cfg->ball_body_contact && !h->packed) {
     delete h;
     return fail(-2, "b200env_create: ball_body_contact needs the packed kernels (the lane-per-body kernel does not have it)%s");

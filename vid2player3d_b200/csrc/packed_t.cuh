@@ -30,6 +30,13 @@ enum { PT_ENV_MBOX = PT_MAXREC * PT_REC, PT_ENV_EXT = PT_ENV_MBOX + PT_MBOX_MAX 
 // private fields of a body: column offsets inside its block (runs start on the boundary of the widest shape that moves them)
 enum { TQ_QJ = 0, TQ_WT = 4, TQ_PD = 7, TQ_R = 10, TQ_ZETA = 13, TQ_U = 19, TQ_E = 22, TQ_C = 28, TQ_BN = 34, TQ_BF = 37, PT_COLS = 40 };
 #define PT_BLOCKS 3
+#ifndef PT_CONTACT_COMPACT
+#define PT_CONTACT_COMPACT 1   // per-vertex ground contact as a compacted phase: the bodies in contact of an env are handed to the env's 8 lanes
+#endif                         // (exchange through the hand-over mailbox, idle between two backward passes); 0: in place on the owner's lane
+#ifndef PT_CX
+#define PT_CX 6
+#endif                         // exchange entries per env = mailbox entries; further bodies in contact are done in place by their owners
+enum { CX_CBB = 0, CX_CF = 12, CX_MASK = 15, CX_BODY = 17 };   // layout of an exchange entry (PT_MB values)
 #ifndef PT_ABL
 #define PT_ABL 0   // ablation of the phases (register-pressure hunting): 1 body pass, 2 backward, 3 forward, 4 root / ball
 #endif
@@ -155,12 +162,14 @@ __device__ __forceinline__ void pt_fk(const DevBlob& B, T* env, int b, const T* 
   }
 }
 
-// rigid-body inertia + bias + external / ground-contact / joint-drive terms of one dynamic body.  jp: qj[4] wt[3] pd[3] (private);
-// A / Bm go to the body's record, the rest comes back in registers for the private store: cbb = C[6] bn[3] bf[3], E[6], u[3]; cf[3]
-// is the ground-contact force on the body.
+// rigid-body inertia + bias + external / ground-contact terms of one dynamic body: A / Bm go to the body's record, the rest comes back
+// in registers for the private store (cbb = C[6] bn[3] bf[3]); cf[3] is the ground-contact force on the body.  The joint drive is a
+// section of its own (pt_body_drive) so that the joint state is only fetched from the private store after the contact code is done with
+// its registers.
+// PT_CONTACT_COMPACT: only the penetration mask of the hull is computed here (returned in mask); pt_contact_phase adds the vertices.
 template <typename T>
-__device__ __forceinline__ void pt_body(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c, T* env, int b, bool ext_on,
-                                        const T* jp, T* cbb, T* E, T* u, T* cf) {
+__device__ __forceinline__ void pt_body_inertia(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c, T* env, int b, bool ext_on,
+                                                T* cbb, T* cf, unsigned long long& mask) {
   const b200_model_t& M = B.m;
   T* rec = env + RIX(B, b) * PT_REC;
   T own[13], R[9];   // Q[4] p[3] w[3] v[3]
@@ -221,32 +230,82 @@ __device__ __forceinline__ void pt_body(const DevBlob& B, const float* __restric
     for (int k = 0; k < 3; k++) { bn[k] -= ext[3 + k] + cxF[k]; bf[k] -= eF[k]; }
   }
   const int nv = M.nverts[b];
-  if (nv > 0 && p[2] - T(M.radius[b]) < T(0))
+  mask = 0ull;
+  if (PT_ABL != 5 && nv > 0 && p[2] - T(M.radius[b]) < T(0)) {
+#if PT_CONTACT_COMPACT
+    mask = contact_mask<T>(verts + (size_t)b * M.vmax * 3, M.vmax, nv, R, p);
+#else
     contact_hull<T>(verts + (size_t)b * M.vmax * 3, M.vmax, nv, c, R, p, v, w, A, Bm, C, bn, bf, cf);
+#endif
+  }
   str<PT_A, 15>(rec, ab);
 #pragma unroll
   for (int k = 0; k < 12; k++) cbb[k] = ab[15 + k];
-  if (b > 0) {
-    const int d0 = M.dof_of_body[b];
-    T q[3], tau[3], e[3];
-    const T *qj = jp, *wt = jp + 4, *pd = jp + 7;
-    qlog(qj, q);
+}
+// implicit PD drive + joint limits of a jointed body: jp = qj[4] wt[3] pd[3] (private) -> E[6] (world-frame diagonal terms), u[3]
+template <typename T>
+__device__ __forceinline__ void pt_body_drive(const DevBlob& B, const PhysCfg<T>& c, const T* env, int b, const T* jp, T* E, T* u) {
+  const b200_model_t& M = B.m;
+  T Q[4], R[9];
+  ldr<PT_Q, 4>(env + RIX(B, b) * PT_REC, Q);
+  qmat(Q, R);
+  const int d0 = M.dof_of_body[b];
+  T q[3], tau[3], e[3];
+  const T *qj = jp, *wt = jp + 4, *pd = jp + 7;
+  qlog(qj, q);
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      T kp = T(M.kp[d0 + k]), kd = T(M.kd[d0 + k]);
-      e[k] = T(M.armature[d0 + k]) + c.h * kd + c.h * c.h * kp;
-      tau[k] = kp * (pd[k] - q[k] - c.h * wt[k]) - kd * wt[k];
-      T lo = T(M.lim_lo[d0 + k]), hi = T(M.lim_hi[d0 + k]);
-      if (q[k] < lo) { tau[k] += c.limk * (lo - q[k] - c.h * wt[k]) - c.limc * wt[k]; e[k] += c.h * c.limc + c.h * c.h * c.limk; }
-      else if (q[k] > hi) { tau[k] += c.limk * (hi - q[k] - c.h * wt[k]) - c.limc * wt[k]; e[k] += c.h * c.limc + c.h * c.h * c.limk; }
-    }
-    mv3(R, tau, u);
-    E[0] = R[0] * R[0] * e[0] + R[1] * R[1] * e[1] + R[2] * R[2] * e[2];
-    E[1] = R[3] * R[3] * e[0] + R[4] * R[4] * e[1] + R[5] * R[5] * e[2];
-    E[2] = R[6] * R[6] * e[0] + R[7] * R[7] * e[1] + R[8] * R[8] * e[2];
-    E[3] = R[0] * R[3] * e[0] + R[1] * R[4] * e[1] + R[2] * R[5] * e[2];
-    E[4] = R[0] * R[6] * e[0] + R[1] * R[7] * e[1] + R[2] * R[8] * e[2];
-    E[5] = R[3] * R[6] * e[0] + R[4] * R[7] * e[1] + R[5] * R[8] * e[2];
+  for (int k = 0; k < 3; k++) {
+    T kp = T(M.kp[d0 + k]), kd = T(M.kd[d0 + k]);
+    e[k] = T(M.armature[d0 + k]) + c.h * kd + c.h * c.h * kp;
+    tau[k] = kp * (pd[k] - q[k] - c.h * wt[k]) - kd * wt[k];
+    T lo = T(M.lim_lo[d0 + k]), hi = T(M.lim_hi[d0 + k]);
+    if (q[k] < lo) { tau[k] += c.limk * (lo - q[k] - c.h * wt[k]) - c.limc * wt[k]; e[k] += c.h * c.limc + c.h * c.h * c.limk; }
+    else if (q[k] > hi) { tau[k] += c.limk * (hi - q[k] - c.h * wt[k]) - c.limc * wt[k]; e[k] += c.h * c.limc + c.h * c.h * c.limk; }
+  }
+  mv3(R, tau, u);
+  E[0] = R[0] * R[0] * e[0] + R[1] * R[1] * e[1] + R[2] * R[2] * e[2];
+  E[1] = R[3] * R[3] * e[0] + R[4] * R[4] * e[1] + R[5] * R[5] * e[2];
+  E[2] = R[6] * R[6] * e[0] + R[7] * R[7] * e[1] + R[8] * R[8] * e[2];
+  E[3] = R[0] * R[3] * e[0] + R[1] * R[4] * e[1] + R[2] * R[5] * e[2];
+  E[4] = R[0] * R[6] * e[0] + R[1] * R[7] * e[1] + R[2] * R[8] * e[2];
+  E[5] = R[3] * R[6] * e[0] + R[4] * R[7] * e[1] + R[5] * R[8] * e[2];
+}
+
+// bit patterns <-> slots of the value type (the mask words and the body index ride in an exchange entry next to the floats)
+template <typename T> __device__ __forceinline__ T pt_bits_to_slot(uint32_t x) { return pk_bits_to_slot<T>(x); }
+__device__ __forceinline__ int pt_popc(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  int n = 0;
+  for (; x; x &= x - 1) n++;
+  return n;
+#endif
+}
+// PT_CONTACT_COMPACT, the worker side: lane s of the env's group takes exchange entry s (body, penetration mask, C / bn / bf as the body
+// pass left them), adds the penetrating vertices in ascending order to A / Bm (the body's record) and C / bn / bf / cf (the entry) - the
+// same sums in the same order as the in-place form - and leaves the results in the entry for the owner.
+template <typename T>
+__device__ __forceinline__ void pt_contact_phase(const DevBlob& B, const float* __restrict__ verts, const PhysCfg<T>& c, T* env, int s, int n,
+                                                 T* cf_env, bool last) {
+  const b200_model_t& M = B.m;
+  if (s < n) {
+    T* ent = env + PT_ENV_MBOX + s * PT_MB;
+    T cbb[12], mk[3], own[13], R[9], ab[28], cf[3] = {T(0), T(0), T(0)};
+    ldr<CX_CBB, 12>(ent, cbb);
+    ldr<CX_MASK, 3>(ent, mk);
+    const int b = (int)pk_slot_to_bits(mk[2]);
+    const unsigned long long mask = (unsigned long long)pk_slot_to_bits(mk[0]) | ((unsigned long long)pk_slot_to_bits(mk[1]) << 32);
+    T* rec = env + RIX(B, b) * PT_REC;
+    ldr<PT_Q, 13>(rec, own);
+    ldr<PT_A, 15>(rec, ab);
+#pragma unroll
+    for (int k = 0; k < 12; k++) ab[15 + k] = cbb[k];
+    qmat(own, R);
+    contact_apply<T>(verts + (size_t)b * M.vmax * 3, M.vmax, mask, c, R, own + 4, own + 10, own + 7, ab, ab + 6, ab + 15, ab + 21, ab + 24, cf);
+    str<PT_A, 15>(rec, ab);
+    str<CX_CBB, 12>(ent, ab + 15);
+    if (last && cf_env) { cf_env[b * 3] = cf[0]; cf_env[b * 3 + 1] = cf[1]; cf_env[b * 3 + 2] = cf[2]; }
   }
 }
 
@@ -483,18 +542,69 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       if (cta_sync) __syncthreads();
       const bool last = sim == c.cfi - 1 && sub == c.substeps - 1;
       // 1. per-body inertia / bias / ground contact / joint drive: the owner's three bodies, one per column block
+      ps.wait_st();
+      int ncx = 0;            // bodies in contact of my env so far (exchange entries handed out)
+      uint32_t xmine = 0;     // per block k: bit 4k = my body of that block was exported, bits 4k+1..4k+3 = its entry
       for (int k = 0; k < (PT_ABL == 1 ? 0 : PT_BLOCKS); k++) {
         const int b = valid ? B.t.pt_body[k][s] : -1;
-        T jp[10], cbb[12], E[6], u[3], cf[3];   // jp: qj[4] wt[3] pd[3]
-        ps.wait_st();
+        {
+          T cbb[12], cf[3];
+          unsigned long long mask = 0ull;
+          if (b >= 0) pt_body_inertia<T>(B, verts, c, env, b, sim == 0, cbb, cf, mask);
+#if PT_CONTACT_COMPACT
+          const bool hit = mask != 0ull;
+          const uint32_t gb = (__ballot_sync(FULL, hit) >> (g * 8)) & 0xFFu;
+          const int idx = ncx + pt_popc(gb & ((1u << s) - 1u));
+          ncx += pt_popc(gb);
+          if (hit) {
+            if (idx < PT_CX) {       // hand the per-vertex part to the env's lanes
+              T* ent = env + PT_ENV_MBOX + idx * PT_MB;
+              const T mk[3] = {pt_bits_to_slot<T>((uint32_t)mask), pt_bits_to_slot<T>((uint32_t)(mask >> 32)), pt_bits_to_slot<T>((uint32_t)b)};
+              str<CX_CBB, 12>(ent, cbb);
+              str<CX_MASK, 3>(ent, mk);
+              xmine |= (1u | ((uint32_t)idx << 1)) << (4 * k);
+            } else {                 // more bodies in contact than entries: this one is done here, in place
+              T* rec = env + RIX(B, b) * PT_REC;
+              T own[13], R[9], ab[28];
+              ldr<PT_Q, 13>(rec, own);
+              ldr<PT_A, 15>(rec, ab);
+#pragma unroll
+              for (int j = 0; j < 12; j++) ab[15 + j] = cbb[j];
+              qmat(own, R);
+              contact_apply<T>(verts + (size_t)b * M.vmax * 3, M.vmax, mask, c, R, own + 4, own + 10, own + 7, ab, ab + 6, ab + 15, ab + 21, ab + 24, cf);
+              str<PT_A, 15>(rec, ab);
+#pragma unroll
+              for (int j = 0; j < 12; j++) cbb[j] = ab[15 + j];
+            }
+          }
+          if (b >= 0 && !(hit && idx < PT_CX) && last && cf_env) { cf_env[b * 3] = cf[0]; cf_env[b * 3 + 1] = cf[1]; cf_env[b * 3 + 2] = cf[2]; }
+#else
+          if (b >= 0 && last && cf_env) { cf_env[b * 3] = cf[0]; cf_env[b * 3 + 1] = cf[1]; cf_env[b * 3 + 2] = cf[2]; }
+#endif
+          ps.template st<TQ_C, 12>(k, cbb);
+        }
+        T jp[10], E[6], u[3];   // jp: qj[4] wt[3] pd[3]
         ps.template ld<TQ_QJ, 10>(k, jp);
         ps.wait_ld();
-        if (b >= 0) {
-          pt_body<T>(B, verts, c, env, b, sim == 0, jp, cbb, E, u, cf);
-          if (last && cf_env) { cf_env[b * 3] = cf[0]; cf_env[b * 3 + 1] = cf[1]; cf_env[b * 3 + 2] = cf[2]; }
-        }
-        ps.template st<TQ_U, 3>(k, u); ps.template st<TQ_E, 6>(k, E); ps.template st<TQ_C, 12>(k, cbb);
+        if (b > 0) pt_body_drive<T>(B, c, env, b, jp, E, u);
+        ps.template st<TQ_U, 3>(k, u); ps.template st<TQ_E, 6>(k, E);
       }
+#if PT_CONTACT_COMPACT
+      if (__any_sync(FULL, ncx > 0)) {            // some env of the warp touches the ground (warp-uniform)
+        __syncwarp();                             // entries and A / Bm records visible to the group
+        pt_contact_phase<T>(B, verts, c, env, s, ncx < PT_CX ? ncx : PT_CX, cf_env, last);
+        __syncwarp();
+        for (int k = 0; k < PT_BLOCKS; k++) {     // owners take C / bn / bf of their exported bodies back into the private store
+          T cbb[12];
+          ps.wait_st();
+          ps.template ld<TQ_C, 12>(k, cbb);
+          ps.wait_ld();
+          if ((xmine >> (4 * k)) & 1u) ldr<CX_CBB, 12>(env + PT_ENV_MBOX + ((xmine >> (4 * k + 1)) & 7u) * PT_MB, cbb);
+          ps.template st<TQ_C, 12>(k, cbb);
+        }
+        __syncwarp();                             // the mailbox is free for the hand-over entries of the backward pass
+      }
+#endif
       // 2. articulated inertia, leaves -> root
       for (int d = (PT_ABL == 2 ? 0 : M.max_depth); d >= 1; d--) {
         const int blk = B.t.pt_lblk[d];
