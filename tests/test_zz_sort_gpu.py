@@ -17,7 +17,8 @@ def _rollout(sort):
     from vid2player3d_b200.tasks import HumanoidSMPLIM
     model = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
     flat = motion_lib.synthetic(model, num_motions=4, num_frames=80, seed=5)
-    old = os.environ.pop("B200ENV_SORT", None)
+    old, oldk = os.environ.pop("B200ENV_SORT", None), os.environ.get("B200ENV_KERNEL")
+    os.environ["B200ENV_KERNEL"] = "packed"               # the sorted hand-out belongs to step_kernel_packed: compare like with like
     if sort:
         os.environ["B200ENV_SORT"] = "1"
     try:
@@ -25,8 +26,11 @@ def _rollout(sort):
         task = HumanoidSMPLIM(im_cfg(150, flat), SIM_PARAMS, 1, "cuda", 0, True)     # 150: ragged last warp and batch
     finally:
         os.environ.pop("B200ENV_SORT", None)
+        os.environ.pop("B200ENV_KERNEL", None)
         if old is not None:
             os.environ["B200ENV_SORT"] = old
+        if oldk is not None:
+            os.environ["B200ENV_KERNEL"] = oldk
     task.reset()
     g = torch.Generator(device=task.device).manual_seed(3)
     out = []

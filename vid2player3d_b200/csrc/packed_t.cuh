@@ -30,13 +30,17 @@ enum { PT_ENV_MBOX = PT_MAXREC * PT_REC, PT_ENV_EXT = PT_ENV_MBOX + PT_MBOX_MAX 
 // private fields of a body: column offsets inside its block (runs start on the boundary of the widest shape that moves them)
 enum { TQ_QJ = 0, TQ_WT = 4, TQ_PD = 7, TQ_R = 10, TQ_ZETA = 13, TQ_U = 19, TQ_E = 22, TQ_C = 28, TQ_BN = 34, TQ_BF = 37, PT_COLS = 40 };
 #define PT_BLOCKS 3
+#ifndef PT_SYNC_EVERY
+#define PT_SYNC_EVERY 1   // CTA barrier every n-th substep (PT_STEP_SYNC): instruction-cache sharing against waiting for the slowest warp
+#endif
 #ifndef PT_CONTACT_COMPACT
 #define PT_CONTACT_COMPACT 1   // per-vertex ground contact as a compacted phase: the bodies in contact of an env are handed to the env's 8 lanes
 #endif                         // (exchange through the hand-over mailbox, idle between two backward passes); 0: in place on the owner's lane
 #ifndef PT_CX
-#define PT_CX 6
-#endif                         // exchange entries per env = mailbox entries; further bodies in contact are done in place by their owners
-enum { CX_CBB = 0, CX_CF = 12, CX_MASK = 15, CX_BODY = 17 };   // layout of an exchange entry (PT_MB values)
+#define PT_CX 8                // exchange entries per env (one per lane of the group), carved out of the mailbox: PT_CX * PT_CXS <= PT_MBOX_MAX * PT_MB;
+#endif                         // further bodies in contact are done in place by their owners
+enum { CX_CBB = 0, CX_MASK = 12, PT_CXS = 16 };   // layout of an exchange entry: C bn bf, mask lo / hi, body index (PT_CXS values, 16-byte aligned)
+static_assert(PT_CX * PT_CXS <= PT_MBOX_MAX * PT_MB && PT_CX <= 8, "exchange entries must fit the mailbox and the 3-bit entry index");
 #ifndef PT_ABL
 #define PT_ABL 0   // ablation of the phases (register-pressure hunting): 1 body pass, 2 backward, 3 forward, 4 root / ball
 #endif
@@ -290,7 +294,7 @@ __device__ __forceinline__ void pt_contact_phase(const DevBlob& B, const float* 
                                                  T* cf_env, bool last) {
   const b200_model_t& M = B.m;
   if (s < n) {
-    T* ent = env + PT_ENV_MBOX + s * PT_MB;
+    T* ent = env + PT_ENV_MBOX + s * PT_CXS;
     T cbb[12], mk[3], own[13], R[9], ab[28], cf[3] = {T(0), T(0), T(0)};
     ldr<CX_CBB, 12>(ent, cbb);
     ldr<CX_MASK, 3>(ent, mk);
@@ -539,7 +543,7 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       }
     }
     for (int sub = 0; sub < c.substeps; sub++) {
-      if (cta_sync) __syncthreads();
+      if (cta_sync && (PT_SYNC_EVERY == 1 || (sim * c.substeps + sub) % PT_SYNC_EVERY == 0)) __syncthreads();
       const bool last = sim == c.cfi - 1 && sub == c.substeps - 1;
       // 1. per-body inertia / bias / ground contact / joint drive: the owner's three bodies, one per column block
       ps.wait_st();
@@ -558,7 +562,7 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
           ncx += pt_popc(gb);
           if (hit) {
             if (idx < PT_CX) {       // hand the per-vertex part to the env's lanes
-              T* ent = env + PT_ENV_MBOX + idx * PT_MB;
+              T* ent = env + PT_ENV_MBOX + idx * PT_CXS;
               const T mk[3] = {pt_bits_to_slot<T>((uint32_t)mask), pt_bits_to_slot<T>((uint32_t)(mask >> 32)), pt_bits_to_slot<T>((uint32_t)b)};
               str<CX_CBB, 12>(ent, cbb);
               str<CX_MASK, 3>(ent, mk);
@@ -599,7 +603,7 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
           ps.wait_st();
           ps.template ld<TQ_C, 12>(k, cbb);
           ps.wait_ld();
-          if ((xmine >> (4 * k)) & 1u) ldr<CX_CBB, 12>(env + PT_ENV_MBOX + ((xmine >> (4 * k + 1)) & 7u) * PT_MB, cbb);
+          if ((xmine >> (4 * k)) & 1u) ldr<CX_CBB, 12>(env + PT_ENV_MBOX + ((xmine >> (4 * k + 1)) & 7u) * PT_CXS, cbb);
           ps.template st<TQ_C, 12>(k, cbb);
         }
         __syncwarp();                             // the mailbox is free for the hand-over entries of the backward pass
