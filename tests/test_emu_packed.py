@@ -228,3 +228,33 @@ def test_compacted_contact_phase_is_bit_identical():
     r2, q2, v2 = root.copy(), q.copy(), qd.copy()
     physics_ref.control_step(ms, verts, cfg, r2, q2, v2, tar.copy(), ext.copy(), n_steps=3)
     np.testing.assert_allclose(res["compact"][1], q2, rtol=0, atol=1e-7)
+
+
+def _emu_f32(variant, flags, ms, verts, cfg, root, q, qd, tar, ext, steps):
+    import build as emu_build
+    lib = C.CDLL(emu_build.build(variant, flags))
+    lib.emu_set_hull_faces(None, None, None, C.c_int(0))
+    n = root.shape[0]
+    rb = np.zeros((n, ms.nb, 13), np.float32)
+    cf = np.zeros((n, ms.nb, 3), np.float32)
+    rc = lib.emu_packed_physics_f32(C.byref(ms), _p(np.ascontiguousarray(verts, np.float32)), C.byref(cfg), C.c_int(n), C.c_int(steps),
+                                    _p(root), _p(q), _p(qd), _p(tar), _p(ext), _p(rb), _p(cf), None, None)
+    assert rc == 0
+    return root, q, qd, rb, cf
+
+
+@pytest.mark.parametrize("flags", [(), ("-DPT_CX=1",), ("-DPT_CONTACT_COMPACT=0",)], ids=["compact", "overflow", "inplace"])
+@pytest.mark.parametrize("asset", ["smpl_mesh_humanoid_amass_v1", "smpl_mesh_humanoid_federer"])
+def test_one_wave_form_is_bit_identical_to_packed_in_float32(asset, flags):
+    """csrc/packed_t.cuh (owner lanes, private store, mailbox hand-over, compacted contact through the mailbox entries - also with one entry
+    only, so that the in-place overflow path runs, and with the in-place contact) runs the operations of csrc/packed.cuh in the same
+    order: in float32 emulation (no FMA contraction on the host) every output is bit-identical, 3 control steps with ground contact."""
+    mod = model_compiler.canonical_racket_last(model_compiler.load_compiled(asset))
+    ms, verts = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    cfg = abi.make_cfg(mod)
+    st = [a.astype(np.float32) for a in states(10, 5, True)]
+    ref = _emu_f32("packed", (), ms, verts, cfg, *[a.copy() for a in st], 3)
+    got = _emu_f32("packedt", flags, ms, verts, cfg, *[a.copy() for a in st], 3)
+    for a, b, name in zip(ref, got, ("root", "dof_pos", "dof_vel", "rigid bodies", "contact forces")):
+        assert np.array_equal(a, b), name
+    assert np.abs(ref[4]).max() > 10.0
