@@ -607,6 +607,7 @@ def main():
     def step(i):
         env.step(pool[i % len(pool)])                              # one graph replay
         env.reset_done()                                           # reset(finished envs) from the device flags: mask + one graph replay
+        # (step + reset captured as ONE graph measured 1.4 % slower than the two replays, profiles/r2z_notes.md: not kept)
     for i in range(4):
         step_ids(i)
     env.enable_cuda_graph(count_nodes=True)

@@ -866,3 +866,4 @@ def test_obs_imitation_rows_matches_gathered_inputs():
     assert torch.equal(out, ref), (float(d.max()), d.nonzero()[:8].tolist(), out[d > 0][:4].tolist(), ref[d > 0][:4].tolist())
     want = torch.clamp((ref - mean) * rstd, -5, 5).to(torch.bfloat16)
     assert torch.equal(op[:96, :734], want) and float(op[96:].abs().max()) == 0 and float(op[:, 734:].abs().max()) == 0
+

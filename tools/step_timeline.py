@@ -23,7 +23,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
 ev.sort(key=lambda e: e.time_range.start)
-phys = [i for i, e in enumerate(ev) if "step_kernel" in e.name]
+phys = [i for i, e in enumerate(ev) if e.name.startswith("step_kernel") or "step_kernel_packed" in e.name]
 if len(phys) < 4:
     print("no per-kernel records for graph replays:", len(ev), "events"); sys.exit(0)
 a, b = phys[2], phys[3]          # one full period: physics launch of step t .. physics launch of step t + 1

@@ -979,9 +979,11 @@ __device__ __forceinline__ void load_state_rows(const b200_buffers_t& bf, const 
 // targets).  Warp per env, lane per body, 8 warps per CTA, no big shared-memory footprint -> full occupancy.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 pre_kernel(const DevBlob* __restrict__ gblob, const b200_cfg_t* __restrict__ gcfg, b200_buffers_t bf, b200_motion_lib_t ml,
-           const float* __restrict__ actions, int num_envs, int env_first, int env_stride, float* __restrict__ ext_wrench) {
+           const float* __restrict__ actions, int num_envs, int env_first, int env_stride, float* __restrict__ ext_wrench,
+           unsigned long long* __restrict__ ticket) {
   __shared__ float s_scr[WARPS_PER_CTA * SCRATCH_FLOATS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0ull;   // hand-out counter of the physics launch that follows (one memset node less per step)
   const int64_t i = (int64_t)blockIdx.x * WARPS_PER_CTA + warp;
   if (i >= num_envs) return;
   const int64_t e = env_first + (int64_t)env_stride * i;
@@ -2217,7 +2219,7 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
     }
     // the ticket counter is re-zeroed on the stream before every launch: nothing in the launch depends on host-side
     // history, so a step can be captured into a CUDA graph and replayed
-    CUDA_OK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    if (!h->split) CUDA_OK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned long long), (cudaStream_t)stream));   // split form: pre_kernel zeroes it
     if (h->split) {
       const int rows = h->env_first + h->env_stride * (h->num_envs - 1) + 1;
       if (rows > h->ext_rows) {  // first step (or a wider env slice): never inside a graph capture - the bound task warms up first
@@ -2235,7 +2237,7 @@ int b200env_step(b200env_handle h, const float* actions, void* stream) {
         h->launches += 2;
       }
       pre_kernel<<<io_grid, WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>((const DevBlob*)h->d_blob, h->d_cfg, h->bufs, h->ml, actions,
-                                                                           h->num_envs, h->env_first, h->env_stride, h->d_ext);
+                                                                           h->num_envs, h->env_first, h->env_stride, h->d_ext, h->d_ticket);
       cudaEvent_t tv0 = nullptr, tv1 = nullptr;
       if (h->timing && h->tev && h->tev->size() < 8192) {
         if (cudaEventCreate(&tv0) == cudaSuccess && cudaEventCreate(&tv1) == cudaSuccess) cudaEventRecord(tv0, (cudaStream_t)stream);
