@@ -131,6 +131,22 @@ struct PrivTmem {
 };
 #endif
 
+// the barrier at the top of a substep: the whole CTA, or (PT_SYNC_GROUPS = 2) the even and the odd warps among themselves - half as many
+// warps to wait for, two instruction streams in the instruction cache
+#ifndef PT_SYNC_GROUPS
+#define PT_SYNC_GROUPS 1
+#endif
+__device__ __forceinline__ void pt_substep_barrier() {
+#if defined(__CUDA_ARCH__)
+  if (PT_SYNC_GROUPS == 1) { __syncthreads(); return; }
+  const unsigned w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned grp = w % PT_SYNC_GROUPS, cnt = (nw - grp + PT_SYNC_GROUPS - 1) / PT_SYNC_GROUPS * 32;   // warps grp, grp + G, ...
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(cnt) : "memory");
+#else
+  __syncthreads();
+#endif
+}
+
 // kinematics of body b from its parent's pose; the joint rotation / velocity come in registers.  Stores the pose of the body origin;
 // a jointed body also returns r = p - p_parent and the velocity-product terms (rz[9], private fields of the owner).
 template <typename T>
@@ -543,7 +559,7 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       }
     }
     for (int sub = 0; sub < c.substeps; sub++) {
-      if (cta_sync && (PT_SYNC_EVERY == 1 || (sim * c.substeps + sub) % PT_SYNC_EVERY == 0)) __syncthreads();
+      if (cta_sync && (PT_SYNC_EVERY == 1 || (sim * c.substeps + sub) % PT_SYNC_EVERY == 0)) pt_substep_barrier();
       const bool last = sim == c.cfi - 1 && sub == c.substeps - 1;
       // 1. per-body inertia / bias / ground contact / joint drive: the owner's three bodies, one per column block
       ps.wait_st();
