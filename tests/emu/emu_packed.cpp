@@ -142,7 +142,7 @@ template <typename T> void lane_main_t(EmuWarp* w, int lane, const Job<T>* J, in
   const bool with_ball = pc.has_ball && J->ballio != nullptr;
   pc.has_ball = with_ball;
   const int g = lane / EMU_LPE, s = lane % EMU_LPE;
-  PrivMem<T> ps{priv + (size_t)lane * PT_BLOCKS * PT_COLS};
+  PrivMem<T> ps{priv + (size_t)lane * PT_WARP_COLS};
   for (int k = 0; k < EMU_EPW; k++) {
     const int64_t e = eb + k;
     if (e >= n) break;
@@ -241,7 +241,7 @@ static int run(const b200_model_t* model, const float* verts, const b200_cfg_t* 
   Job<T> J{&hb, sv, cfg, n, n_steps, root, dof_pos, dof_vel, pd_tar, ext, rb_out, contact_out, ballio, hits};
 #ifdef EMU_PACKEDT
   if (!hb.t.pt_ok) return -2;
-  std::vector<T> rec((size_t)EMU_EPW * PT_ENV_STRIDE + 8, T(0)), priv((size_t)32 * PT_BLOCKS * PT_COLS, T(0));
+  std::vector<T> rec((size_t)EMU_EPW * PT_ENV_STRIDE + 8, T(0)), priv((size_t)32 * PT_WARP_COLS, T(0));
 #else
   std::vector<T> rec((size_t)EMU_EPW * ENV_STRIDE + 8, T(0));
 #endif

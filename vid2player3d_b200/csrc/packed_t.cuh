@@ -38,13 +38,14 @@ enum { TQ_QJ = 0, TQ_WT = 4, TQ_PD = 7, TQ_R = 10, TQ_ZETA = 13, TQ_U = 19, TQ_E
 #endif                         // (exchange through the hand-over mailbox, idle between two backward passes); 0: in place on the owner's lane
 #ifndef PT_CX
 #define PT_CX 8                // exchange entries per env (one per lane of the group), carved out of the mailbox: PT_CX * PT_CXS <= PT_MBOX_MAX * PT_MB;
-#endif                         // further bodies in contact are done in place by their owners
+#endif                         // an env with more bodies in contact takes several chunks (their masks wait in the owners' spare columns)
 enum { CX_CBB = 0, CX_MASK = 12, PT_CXS = 16 };   // layout of an exchange entry: C bn bf, mask lo / hi, body index (PT_CXS values, 16-byte aligned)
-static_assert(PT_CX * PT_CXS <= PT_MBOX_MAX * PT_MB && PT_CX <= 8, "exchange entries must fit the mailbox and the 3-bit entry index");
+static_assert(PT_CX * PT_CXS <= PT_MBOX_MAX * PT_MB && PT_CX <= 8, "exchange entries must fit the mailbox, one per lane of the group at most");
 #ifndef PT_ABL
 #define PT_ABL 0   // ablation of the phases (register-pressure hunting): 1 body pass, 2 backward, 3 forward, 4 root / ball
 #endif
 #define PT_WARP_COLS 128    // tensor-memory columns of one warp (14 warps: at most 4 per lane quadrant -> 4 x 128 = 512)
+#define PT_XMASK (PT_BLOCKS * PT_COLS)   // columns 120..125 of a lane: penetration masks (2 words per block) of bodies waiting for a later contact chunk
 
 // private store as plain memory: one array of PT_BLOCKS * PT_COLS values per lane
 template <typename T> struct PrivMem {
@@ -57,6 +58,8 @@ template <typename T> struct PrivMem {
 #pragma unroll
     for (int k = 0; k < N; k++) base[blk * PT_COLS + OFF + k] = r[k];
   }
+  __device__ __forceinline__ void ld2(int col, T* r) const { r[0] = base[col]; r[1] = base[col + 1]; }   // run-time (even) column
+  __device__ __forceinline__ void st2(int col, const T* r) const { base[col] = r[0]; base[col + 1] = r[1]; }
   __device__ __forceinline__ void wait_ld() const {}
   __device__ __forceinline__ void wait_st() const {}
 };
@@ -126,6 +129,8 @@ struct PrivTmem {
   uint32_t base;   // tensor-memory address of the warp's window: (32 * (warp % 4)) << 16 | first column
   template <int OFF, int N> __device__ __forceinline__ void ld(int blk, float* r) const { tm_ld_run<OFF, N, 0>(base + blk * PT_COLS + OFF, r); }
   template <int OFF, int N> __device__ __forceinline__ void st(int blk, const float* r) const { tm_st_run<OFF, N, 0>(base + blk * PT_COLS + OFF, r); }
+  __device__ __forceinline__ void ld2(int col, float* r) const { tm_ld<2>(base + col, r); }
+  __device__ __forceinline__ void st2(int col, const float* r) const { tm_st<2>(base + col, r); }
   __device__ __forceinline__ void wait_ld() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
   __device__ __forceinline__ void wait_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
@@ -563,8 +568,8 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       const bool last = sim == c.cfi - 1 && sub == c.substeps - 1;
       // 1. per-body inertia / bias / ground contact / joint drive: the owner's three bodies, one per column block
       ps.wait_st();
-      int ncx = 0;            // bodies in contact of my env so far (exchange entries handed out)
-      uint32_t xmine = 0;     // per block k: bit 4k = my body of that block was exported, bits 4k+1..4k+3 = its entry
+      int ncx = 0;            // bodies in contact of my env so far
+      uint32_t xmine = 0;     // per block k, 6 bits: bit 6k = my body of that block is in contact, bits 6k+1..6k+5 = its rank among the env's
       for (int k = 0; k < (PT_ABL == 1 ? 0 : PT_BLOCKS); k++) {
         const int b = valid ? B.t.pt_body[k][s] : -1;
         {
@@ -576,28 +581,20 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
           const uint32_t gb = (__ballot_sync(FULL, hit) >> (g * 8)) & 0xFFu;
           const int idx = ncx + pt_popc(gb & ((1u << s) - 1u));
           ncx += pt_popc(gb);
+          T later[2] = {T(0), T(0)};     // mask words of a body that has to wait for a later chunk
           if (hit) {
-            if (idx < PT_CX) {       // hand the per-vertex part to the env's lanes
+            xmine |= (1u | ((uint32_t)idx << 1)) << (6 * k);
+            if (idx < PT_CX) {       // first chunk: hand the per-vertex part to the env's lanes right away
               T* ent = env + PT_ENV_MBOX + idx * PT_CXS;
               const T mk[3] = {pt_bits_to_slot<T>((uint32_t)mask), pt_bits_to_slot<T>((uint32_t)(mask >> 32)), pt_bits_to_slot<T>((uint32_t)b)};
               str<CX_CBB, 12>(ent, cbb);
               str<CX_MASK, 3>(ent, mk);
-              xmine |= (1u | ((uint32_t)idx << 1)) << (4 * k);
-            } else {                 // more bodies in contact than entries: this one is done here, in place
-              T* rec = env + RIX(B, b) * PT_REC;
-              T own[13], R[9], ab[28];
-              ldr<PT_Q, 13>(rec, own);
-              ldr<PT_A, 15>(rec, ab);
-#pragma unroll
-              for (int j = 0; j < 12; j++) ab[15 + j] = cbb[j];
-              qmat(own, R);
-              contact_apply<T>(verts + (size_t)b * M.vmax * 3, M.vmax, mask, c, R, own + 4, own + 10, own + 7, ab, ab + 6, ab + 15, ab + 21, ab + 24, cf);
-              str<PT_A, 15>(rec, ab);
-#pragma unroll
-              for (int j = 0; j < 12; j++) cbb[j] = ab[15 + j];
+            } else {
+              later[0] = pt_bits_to_slot<T>((uint32_t)mask); later[1] = pt_bits_to_slot<T>((uint32_t)(mask >> 32));
             }
           }
-          if (b >= 0 && !(hit && idx < PT_CX) && last && cf_env) { cf_env[b * 3] = cf[0]; cf_env[b * 3 + 1] = cf[1]; cf_env[b * 3 + 2] = cf[2]; }
+          ps.st2(PT_XMASK + 2 * k, later);
+          if (b >= 0 && !hit && last && cf_env) { cf_env[b * 3] = cf[0]; cf_env[b * 3 + 1] = cf[1]; cf_env[b * 3 + 2] = cf[2]; }
 #else
           if (b >= 0 && last && cf_env) { cf_env[b * 3] = cf[0]; cf_env[b * 3 + 1] = cf[1]; cf_env[b * 3 + 2] = cf[2]; }
 #endif
@@ -611,18 +608,39 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       }
 #if PT_CONTACT_COMPACT
       if (__any_sync(FULL, ncx > 0)) {            // some env of the warp touches the ground (warp-uniform)
-        __syncwarp();                             // entries and A / Bm records visible to the group
-        pt_contact_phase<T>(B, verts, c, env, s, ncx < PT_CX ? ncx : PT_CX, cf_env, last);
-        __syncwarp();
-        for (int k = 0; k < PT_BLOCKS; k++) {     // owners take C / bn / bf of their exported bodies back into the private store
-          T cbb[12];
-          ps.wait_st();
-          ps.template ld<TQ_C, 12>(k, cbb);
-          ps.wait_ld();
-          if ((xmine >> (4 * k)) & 1u) ldr<CX_CBB, 12>(env + PT_ENV_MBOX + ((xmine >> (4 * k + 1)) & 7u) * PT_CXS, cbb);
-          ps.template st<TQ_C, 12>(k, cbb);
+        for (int c0 = 0;; c0 += PT_CX) {          // chunks of PT_CX bodies per env: one body per lane of the group
+          if (c0 > 0) {                           // owners of the bodies ranked c0 .. c0 + PT_CX - 1 hand them over now
+            for (int k = 0; k < PT_BLOCKS; k++) {
+              T cbb[12], mk[3];
+              ps.wait_st();
+              ps.template ld<TQ_C, 12>(k, cbb); ps.ld2(PT_XMASK + 2 * k, mk);
+              ps.wait_ld();
+              const uint32_t f = xmine >> (6 * k);
+              const int idx = (int)((f >> 1) & 31u) - c0;
+              if ((f & 1u) && idx >= 0 && idx < PT_CX) {
+                T* ent = env + PT_ENV_MBOX + idx * PT_CXS;
+                mk[2] = pt_bits_to_slot<T>((uint32_t)B.t.pt_body[k][s]);
+                str<CX_CBB, 12>(ent, cbb);
+                str<CX_MASK, 3>(ent, mk);
+              }
+            }
+          }
+          __syncwarp();                           // entries and A / Bm records visible to the group
+          pt_contact_phase<T>(B, verts, c, env, s, ncx - c0 < PT_CX ? ncx - c0 : PT_CX, cf_env, last);
+          __syncwarp();
+          for (int k = 0; k < PT_BLOCKS; k++) {   // owners take C / bn / bf of their handed-over bodies back into the private store
+            T cbb[12];
+            ps.wait_st();
+            ps.template ld<TQ_C, 12>(k, cbb);
+            ps.wait_ld();
+            const uint32_t f = xmine >> (6 * k);
+            const int idx = (int)((f >> 1) & 31u) - c0;
+            if ((f & 1u) && idx >= 0 && idx < PT_CX) ldr<CX_CBB, 12>(env + PT_ENV_MBOX + idx * PT_CXS, cbb);
+            ps.template st<TQ_C, 12>(k, cbb);
+          }
+          __syncwarp();                           // the entries are free: next chunk, or the hand-over entries of the backward pass
+          if (!__any_sync(FULL, ncx > c0 + PT_CX)) break;
         }
-        __syncwarp();                             // the mailbox is free for the hand-over entries of the backward pass
       }
 #endif
       // 2. articulated inertia, leaves -> root
