@@ -27,7 +27,6 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
-static inline int __ffs(int v) { return __builtin_ffs(v); }
 
 struct EmuWarp {
   std::atomic<int> count{0};

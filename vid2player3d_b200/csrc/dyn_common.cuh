@@ -513,23 +513,15 @@ __device__ __forceinline__ unsigned long long contact_mask(const float* __restri
   if (nv < 64) mask &= (1ull << nv) - 1ull;   // padding vertices (zeros) never count
   return mask;
 }
-// pass 2: the penetrating vertices added to the body's inertia / bias / contact force.  Canonical summation order (every kernel form):
-// the hull vertices in ranges of CONTACT_RANGE = 16 indices; the contributions of one range summed from zero in ascending vertex order
-// (contact_range_delta), the partial sums added to the body's terms in range order (contact_add_delta).  A fixed order keeps the
-// results bit-reproducible whatever lane computes a range - which lets the one-wave kernel give the ranges of one body to different
-// lanes: the longest serial vertex loop is 16, not the 51 of a whole hull (profiles/r2aa_transient.md).
-#define CONTACT_RANGE 16
-#define CONTACT_DELTA 21   // dA[6] dBm{1,2,3,5,6,7} dC[3] dbn[3] df[3] (the contact force: subtracted from bf, added to cf)
+// pass 2: the penetrating vertices, in ascending vertex order, added to the body's inertia / bias / contact force
 template <typename T>
-__device__ __forceinline__ void contact_range_delta(const float* __restrict__ vb, int vmax, unsigned m16, int k0, const PhysCfg<T>& c, const T* R,
-                                                    const T* p, const T* v, const T* w, T* d) {
-#pragma unroll
-  for (int j = 0; j < CONTACT_DELTA; j++) d[j] = T(0);
+__device__ __forceinline__ void contact_apply(const float* __restrict__ vb, int vmax, unsigned long long mask, const PhysCfg<T>& c, const T* R,
+                                              const T* p, const T* v, const T* w, T* A, T* Bm, T* C, T* bn, T* bf, T* cf) {
   const T pz = p[2];
   const T kimp = c.h * c.cn + c.h * c.h * c.kn;
-  while (m16) {
-    const int k = k0 + __ffs((int)m16) - 1;
-    m16 &= m16 - 1u;
+  while (mask) {
+    const int k = __ffsll((long long)mask) - 1;
+    mask &= mask - 1ull;
     const T vl[3] = {T(vb[k]), T(vb[vmax + k]), T(vb[2 * vmax + k])};
     const T rz = R[6] * vl[0] + R[7] * vl[1] + R[8] * vl[2];
     const T pen = -(pz + rz);
@@ -545,46 +537,26 @@ __device__ __forceinline__ void contact_range_delta(const float* __restrict__ vb
     const T ct = c.mu * fn0 * rcp_(ut > c.vs ? ut : c.vs);
     const T hct = c.h * ct;
     // Jn = [(ry, -rx, 0); (0,0,1)], Jx = [(0, rz, -ry); (1,0,0)], Jy = [(-rz, 0, rx); (0,1,0)]
-    d[0] += kimp * ry * ry + hct * rz * rz;
-    d[1] += kimp * rx * rx + hct * rz * rz;
-    d[2] += hct * (ry * ry + rx * rx);
-    d[3] += -kimp * ry * rx;
-    d[4] += -hct * rz * rx;
-    d[5] += -hct * rz * ry;
-    d[6] += -hct * rz;    // Bm[1]  Jy: ang (-rz,0,rx) x lin ey -> column y
-    d[7] += kimp * ry;    // Bm[2]  (Jn_ang)(Jn_lin)^T : column z
-    d[8] += hct * rz;     // Bm[3]  Jx: ang (0,rz,-ry) x lin ex -> column x
-    d[9] += -kimp * rx;   // Bm[5]
-    d[10] += -hct * ry;   // Bm[6]
-    d[11] += hct * rx;    // Bm[7]
-    d[12] += hct; d[13] += hct; d[14] += kimp;
+    A[0] += kimp * ry * ry + hct * rz * rz;
+    A[1] += kimp * rx * rx + hct * rz * rz;
+    A[2] += hct * (ry * ry + rx * rx);
+    A[3] += -kimp * ry * rx;
+    A[4] += -hct * rz * rx;
+    A[5] += -hct * rz * ry;
+    Bm[2] += kimp * ry;   // (Jn_ang)(Jn_lin)^T : column z
+    Bm[5] += -kimp * rx;
+    Bm[3] += hct * rz;    // Jx: ang (0,rz,-ry) x lin ex -> column x
+    Bm[6] += -hct * ry;
+    Bm[1] += -hct * rz;   // Jy: ang (-rz,0,rx) x lin ey -> column y
+    Bm[7] += hct * rx;
+    C[0] += hct; C[1] += hct; C[2] += kimp;
     // wrench W = Jn fn0 - ct (Jx ux + Jy uy);  b -= W
     const T fx = -ct * ux, fy = -ct * uy;
-    d[15] += ry * fn0 - rz * fy;
-    d[16] += -rx * fn0 + rz * fx;
-    d[17] += -ry * fx + rx * fy;
-    d[18] += fx; d[19] += fy; d[20] += fn0;
-  }
-}
-template <typename T>
-__device__ __forceinline__ void contact_add_delta(const T* d, T* A, T* Bm, T* C, T* bn, T* bf, T* cf) {
-#pragma unroll
-  for (int j = 0; j < 6; j++) A[j] += d[j];
-  Bm[1] += d[6]; Bm[2] += d[7]; Bm[3] += d[8]; Bm[5] += d[9]; Bm[6] += d[10]; Bm[7] += d[11];
-  C[0] += d[12]; C[1] += d[13]; C[2] += d[14];
-#pragma unroll
-  for (int j = 0; j < 3; j++) { bn[j] -= d[15 + j]; bf[j] -= d[18 + j]; cf[j] += d[18 + j]; }
-}
-template <typename T>
-__device__ __forceinline__ void contact_apply(const float* __restrict__ vb, int vmax, unsigned long long mask, const PhysCfg<T>& c, const T* R,
-                                              const T* p, const T* v, const T* w, T* A, T* Bm, T* C, T* bn, T* bf, T* cf) {
-#pragma unroll 1
-  for (int k0 = 0; k0 < 64; k0 += CONTACT_RANGE) {
-    const unsigned m16 = (unsigned)(mask >> k0) & 0xFFFFu;
-    if (!m16) continue;
-    T d[CONTACT_DELTA];
-    contact_range_delta<T>(vb, vmax, m16, k0, c, R, p, v, w, d);
-    contact_add_delta<T>(d, A, Bm, C, bn, bf, cf);
+    bn[0] -= ry * fn0 - rz * fy;
+    bn[1] -= -rx * fn0 + rz * fx;
+    bn[2] -= -ry * fx + rx * fy;
+    bf[0] -= fx; bf[1] -= fy; bf[2] -= fn0;
+    cf[0] += fx; cf[1] += fy; cf[2] += fn0;
   }
 }
 template <typename T>
