@@ -9,7 +9,8 @@ import bench
 
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 55
 N = 8192
-env = bench.federer_env(N, 0)
+BB = os.environ.get("BALL_BODY")          # A/B of vid2player.ball_body_contact: BALL_BODY=0 / 1
+env = bench.federer_env(N, 0, **({"ball_body_contact": BB == "1"} if BB is not None else {}))
 dev = env.device
 acts = [torch.clamp(torch.randn(N, env.num_actions, device=dev), -5, 5) for _ in range(8)]
 for i in range(4):

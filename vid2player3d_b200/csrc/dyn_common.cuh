@@ -614,13 +614,22 @@ __device__ __forceinline__ void closest_on_triangle(const T* p, const T* a, cons
 template <typename T>
 __device__ __forceinline__ bool hull_sphere(const float* vb, int vmax, const float* pl, const unsigned char* tr, int nt, const T* c, T R, T& pen,
                                             T* nl) {
+  // The planes and triangles live in global memory (L2): four faces per iteration, their loads issued together, so that a lane pays one
+  // memory latency per four faces instead of one per face (the face loop of ONE lane decides when a one-wave launch ends,
+  // profiles/r2aa_transient.md).  Faces are still examined in ascending order: same separating test, same maximum, same closest point.
   T smax = T(-1e30);
   int imax = 0;
-  for (int t = 0; t < nt; t++) {
-    const float4 P = *reinterpret_cast<const float4*>(pl + 4 * t);
-    const T sd = T(P.x) * c[0] + T(P.y) * c[1] + T(P.z) * c[2] - T(P.w);
-    if (sd > R) return false;   // a separating face plane: the common outcome for a ball that is merely near the body
-    if (sd > smax) { smax = sd; imax = t; }
+  for (int t = 0; t < nt; t += 4) {
+    float4 P[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) P[j] = *reinterpret_cast<const float4*>(pl + 4 * (t + j < nt ? t + j : nt - 1));   // past the end: the last face again
+    T sd[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) sd[j] = T(P[j].x) * c[0] + T(P[j].y) * c[1] + T(P[j].z) * c[2] - T(P[j].w);
+    if (sd[0] > R || sd[1] > R || sd[2] > R || sd[3] > R) return false;   // a separating face plane: the common outcome for a ball that is merely near the body
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (sd[j] > smax) { smax = sd[j]; imax = t + j; }   // (a repeated last face never beats itself)
   }
   if (smax <= T(0)) {
     pen = R - smax;
@@ -628,19 +637,30 @@ __device__ __forceinline__ bool hull_sphere(const float* vb, int vmax, const flo
     return true;
   }
   T best = T(1e30), qb[3] = {T(0), T(0), T(0)};
-  for (int t = 0; t < nt; t++) {
+  for (int t = 0; t < nt; t += 4) {
     // the closest point of a convex hull to an outside point lies on a face the point sees (its offset from that face's plane is
     // positive): the back faces are skipped
-    const float4 P = *reinterpret_cast<const float4*>(pl + 4 * t);
-    if (!(T(P.x) * c[0] + T(P.y) * c[1] + T(P.z) * c[2] - T(P.w) > T(0))) continue;
-    const int i0 = tr[4 * t], i1 = tr[4 * t + 1], i2 = tr[4 * t + 2];
-    const T a[3] = {T(vb[i0]), T(vb[vmax + i0]), T(vb[2 * vmax + i0])};
-    const T b[3] = {T(vb[i1]), T(vb[vmax + i1]), T(vb[2 * vmax + i1])};
-    const T cc[3] = {T(vb[i2]), T(vb[vmax + i2]), T(vb[2 * vmax + i2])};
-    T q[3];
-    closest_on_triangle<T>(c, a, b, cc, q);
-    const T e2 = (c[0] - q[0]) * (c[0] - q[0]) + (c[1] - q[1]) * (c[1] - q[1]) + (c[2] - q[2]) * (c[2] - q[2]);
-    if (e2 < best) { best = e2; qb[0] = q[0]; qb[1] = q[1]; qb[2] = q[2]; }
+    float4 P[4];
+    uint32_t tri[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int tt = t + j < nt ? t + j : nt - 1;
+      P[j] = *reinterpret_cast<const float4*>(pl + 4 * tt);
+      tri[j] = *reinterpret_cast<const uint32_t*>(tr + 4 * tt);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (t + j >= nt) break;
+      if (!(T(P[j].x) * c[0] + T(P[j].y) * c[1] + T(P[j].z) * c[2] - T(P[j].w) > T(0))) continue;
+      const int i0 = tri[j] & 0xFFu, i1 = (tri[j] >> 8) & 0xFFu, i2 = (tri[j] >> 16) & 0xFFu;
+      const T a[3] = {T(vb[i0]), T(vb[vmax + i0]), T(vb[2 * vmax + i0])};
+      const T b[3] = {T(vb[i1]), T(vb[vmax + i1]), T(vb[2 * vmax + i1])};
+      const T cc[3] = {T(vb[i2]), T(vb[vmax + i2]), T(vb[2 * vmax + i2])};
+      T q[3];
+      closest_on_triangle<T>(c, a, b, cc, q);
+      const T e2 = (c[0] - q[0]) * (c[0] - q[0]) + (c[1] - q[1]) * (c[1] - q[1]) + (c[2] - q[2]) * (c[2] - q[2]);
+      if (e2 < best) { best = e2; qb[0] = q[0]; qb[1] = q[1]; qb[2] = q[2]; }
+    }
   }
   const T dist = sqrt_(best);
   if (!(dist < R) || dist <= T(1e-9)) return false;
