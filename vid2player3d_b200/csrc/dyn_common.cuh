@@ -173,6 +173,11 @@ static inline void verts_to_soa(const b200_model_t* model, const float* verts, f
 
 // ------------------------------------------------------------------------------------------
 // small math (templated on float / double)
+#if defined(__CUDACC__)
+__device__ __forceinline__ int emu_lane_id() { return (int)(threadIdx.x & 31); }
+#else
+static inline int emu_lane_id() { return emu_lane; }   // tests/emu/cuda_compat.h: the lane this host thread plays
+#endif
 template <typename T> __device__ __forceinline__ T shfl(T v, int src) { return __shfl_sync(FULL, v, src); }
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
@@ -662,6 +667,105 @@ __device__ __forceinline__ bool hull_sphere(const float* vb, int vmax, const flo
       if (e2 < best) { best = e2; qb[0] = q[0]; qb[1] = q[1]; qb[2] = q[2]; }
     }
   }
+  const T dist = sqrt_(best);
+  if (!(dist < R) || dist <= T(1e-9)) return false;
+  pen = R - dist;
+  const T id = T(1) / dist;
+  nl[0] = (c[0] - qb[0]) * id; nl[1] = (c[1] - qb[1]) * id; nl[2] = (c[2] - qb[2]) * id;
+  return true;
+}
+
+
+// hull_sphere with the faces of ONE body spread over the 8 lanes of an env's group (lane slot s takes the faces s, s + 8, s + 16, ...,
+// four of them per iteration): what bounds a launch is the longest serial face walk of a single lane (profiles/r2aa_transient.md) -
+// ~2 x 100 dependent L2 round trips when one lane does a whole hull.  Every lane of the WARP calls this together (the exchanges are
+// warp shuffles); act: this lane's group has a body to test (its arguments are the same on the 8 lanes).  The outcome is the serial
+// function's bit for bit: the same per-face values, the maximum / the minimum taken with the serial loop's tie rule (the lowest face).
+template <typename T>
+__device__ __forceinline__ bool hull_sphere_coop(const float* vb, int vmax, const float* pl, const unsigned char* tr, int nt, const T* c, T R, int s,
+                                                 bool act, T& pen, T* nl) {
+  // ---- pass 1: separating plane / deepest face
+  T smax = T(-1e30);
+  int imax = 1 << 30;
+  bool sep = false, done = !act;
+  for (int t0 = 0;; t0 += 32) {
+    if (!done) {
+      float4 P[4];
+      int ti[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) { ti[j] = t0 + 8 * j + s; P[j] = *reinterpret_cast<const float4*>(pl + 4 * (ti[j] < nt ? ti[j] : nt - 1)); }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (ti[j] >= nt) continue;
+        const T sd = T(P[j].x) * c[0] + T(P[j].y) * c[1] + T(P[j].z) * c[2] - T(P[j].w);
+        if (sd > R) sep = true;
+        if (sd > smax) { smax = sd; imax = ti[j]; }
+      }
+    }
+    // a separating plane anywhere in my group ends the group's walk (the serial loop returns at the first one: no side effects either way)
+    const uint32_t gs = (__ballot_sync(FULL, sep) >> ((emu_lane_id() >> 3) * 8)) & 0xFFu;
+    if (gs) sep = true;
+    if (sep || t0 + 32 >= nt) done = true;
+    if (!__any_sync(FULL, !done)) break;
+  }
+  // deepest face of the group: maximum, ties to the lowest face index (= the serial loop's first maximum)
+#pragma unroll
+  for (int off = 1; off < 8; off <<= 1) {
+    const T os = __shfl_xor_sync(FULL, smax, off);
+    const int oi = __shfl_xor_sync(FULL, imax, off);
+    if (os > smax || (os == smax && oi < imax)) { smax = os; imax = oi; }
+  }
+  const bool inside = act && !sep && smax <= T(0);
+  if (inside) {
+    pen = R - smax;
+    nl[0] = T(pl[4 * imax]); nl[1] = T(pl[4 * imax + 1]); nl[2] = T(pl[4 * imax + 2]);
+  }
+  // ---- pass 2: closest point over the faces the centre sees (groups that are decided idle through it)
+  const bool need = act && !sep && !inside;
+  T best = T(1e30), qb[3] = {T(0), T(0), T(0)};
+  int ibest = 1 << 30;
+  if (__any_sync(FULL, need)) {
+    bool fin = !need;
+    for (int t0 = 0;; t0 += 32) {
+      if (!fin) {
+        float4 P[4];
+        uint32_t tri[4];
+        int ti[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          ti[j] = t0 + 8 * j + s;
+          const int tt = ti[j] < nt ? ti[j] : nt - 1;
+          P[j] = *reinterpret_cast<const float4*>(pl + 4 * tt);
+          tri[j] = *reinterpret_cast<const uint32_t*>(tr + 4 * tt);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (ti[j] >= nt) continue;
+          if (!(T(P[j].x) * c[0] + T(P[j].y) * c[1] + T(P[j].z) * c[2] - T(P[j].w) > T(0))) continue;
+          const int i0 = tri[j] & 0xFFu, i1 = (tri[j] >> 8) & 0xFFu, i2 = (tri[j] >> 16) & 0xFFu;
+          const T a[3] = {T(vb[i0]), T(vb[vmax + i0]), T(vb[2 * vmax + i0])};
+          const T b[3] = {T(vb[i1]), T(vb[vmax + i1]), T(vb[2 * vmax + i1])};
+          const T cc[3] = {T(vb[i2]), T(vb[vmax + i2]), T(vb[2 * vmax + i2])};
+          T q[3];
+          closest_on_triangle<T>(c, a, b, cc, q);
+          const T e2 = (c[0] - q[0]) * (c[0] - q[0]) + (c[1] - q[1]) * (c[1] - q[1]) + (c[2] - q[2]) * (c[2] - q[2]);
+          if (e2 < best) { best = e2; ibest = ti[j]; qb[0] = q[0]; qb[1] = q[1]; qb[2] = q[2]; }
+        }
+        if (t0 + 32 >= nt) fin = true;
+      }
+      if (!__any_sync(FULL, !fin)) break;
+    }
+    // nearest face of the group: minimum, ties to the lowest face index (= the serial loop's first minimum)
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+      const T ob = __shfl_xor_sync(FULL, best, off);
+      const int oi = __shfl_xor_sync(FULL, ibest, off);
+      const T o0 = __shfl_xor_sync(FULL, qb[0], off), o1 = __shfl_xor_sync(FULL, qb[1], off), o2 = __shfl_xor_sync(FULL, qb[2], off);
+      if (ob < best || (ob == best && oi < ibest)) { best = ob; ibest = oi; qb[0] = o0; qb[1] = o1; qb[2] = o2; }
+    }
+  }
+  if (!act || sep) return false;
+  if (inside) return true;
   const T dist = sqrt_(best);
   if (!(dist < R) || dist <= T(1e-9)) return false;
   pen = R - dist;

@@ -560,15 +560,18 @@ __device__ __forceinline__ void pk_ball_contacts_extra(const DevBlob& B, const f
   }
 }
 
-// The same contacts with the body loop spread over the 8 lanes of the env's group (the serial form on the ball's lane costs the whole
-// warp ~1 000 instructions per substep: +170 us per 8192-env step of config 3, profiles/r2m_ball_body.md).  Every lane of the warp calls
-// this (the shuffles are warp-wide); lane (g, s) tests bodies s, s + 8, s + 16, (24) of env g against the ball its group's lane
-// BALL_SLOT carries, the deepest contact wins (ties: the lower body index, as in the serial loop) and the ball's lane applies it.
+// The same contacts on the 8 lanes of the env's group.  Every lane of the warp calls this (the exchanges are warp shuffles).  Two stages:
+// (1) lane (g, s) pre-tests bodies s, s + 8, s + 16, (24) of env g against the ball its group's lane BALL_SLOT carries (reach test
+// against the bounding sphere); the cheap shapes - the racket handle capsule, bodies of a model without hull faces - are finished
+// right there; (2) the bodies with a convex hull that passed the reach test are taken one after the other, in ascending body order, by
+// the WHOLE group (hull_sphere_coop: the hull's faces over 8 lanes).  The first version walked a hull's ~100 faces twice on one lane,
+// one dependent L2 round trip per face, and that one lane decided when a one-wave launch ended (profiles/r2aa_transient.md).  The
+// deepest contact wins (ties: the lower body index, as in the serial loop of the restatement) and the ball's lane applies it.
 template <typename T, int RS = REC>   // RS: record stride (packed_t.cuh has its own record layout; the pose run is the same)
 __device__ __forceinline__ void pk_ball_contacts_group(const DevBlob& B, const float* verts, const PhysCfg<T>& c, const T* env, int lane, bool valid,
                                                        Ball<T>& ball) {
   const b200_model_t& M = B.m;
-  const int s = lane & 7, src = (lane & ~7) | BALL_SLOT;
+  const int g = lane >> 3, s = lane & 7, src = (lane & ~7) | BALL_SLOT;
   T bp[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) bp[k] = __shfl_sync(FULL, ball.p[k], src);
@@ -579,68 +582,99 @@ __device__ __forceinline__ void pk_ball_contacts_group(const DevBlob& B, const f
     const T dx = bp[0] - rp[0], dy = bp[1] - rp[1], dz = bp[2] - rp[2];
     near = dx * dx + dy * dy + dz * dz <= T(2.25);       // nothing of the player beyond 1.5 m of the pelvis
   }
+  if (!__any_sync(FULL, near)) return;                   // no ball of this warp is near its player (warp-uniform)
   T best = T(0), bn[3] = {T(0), T(0), T(1)}, bvo[3] = {T(0), T(0), T(0)}, be = c.eb, bmu = c.mub;
   int bbody = 1 << 20;
-  if (near) {
-    for (int b = s; b < M.nb; b += SLOTS) {
+  auto take = [&](int b, bool handle, T pen, const T* nl, const T* st, const T* d) {   // contact of depth pen with body b (pose st): keep the deepest
+    if (pen > best || (pen == best && b < bbody)) {
+      const T *Q = st, *w = st + 7, *v = st + 10;
+      best = pen;
+      bbody = b;
+      qrot(Q, nl, bn);
+      const T x[3] = {d[0] - c.bR * bn[0], d[1] - c.bR * bn[1], d[2] - c.bR * bn[2]};   // contact point relative to the body origin
+      T wxx[3];
+      cross3(w, x, wxx);
+#pragma unroll
+      for (int k = 0; k < 3; k++) bvo[k] = v[k] + wxx[k];
+      be = handle ? c.er : c.eb;
+      bmu = handle ? c.mur : c.mub;
+    }
+  };
+  // ---- stage 1: reach tests; cheap shapes finished; hull bodies in reach -> candidate bits of my env
+  uint32_t cand = 0;
+  for (int rr = 0; rr * SLOTS < M.nb; rr++) {
+    const int b = rr * SLOTS + s;
+    bool hull = false;
+    if (near && b < M.nb) {
       const bool handle = b == c.racket_body && c.hdl[6] > T(0);
       const int nv = M.nverts[b];
-      if (nv == 0 && !handle) continue;
-      T st[13];   // Q[4] p[3] w[3] v[3]
-      ldr<R_Q, 13>(env + RIX(B, b) * RS, st);
-      const T *Q = st, *p = st + 4, *w = st + 7, *v = st + 10;
-      const T d[3] = {bp[0] - p[0], bp[1] - p[1], bp[2] - p[2]};
-      const T d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-      const int nt = handle ? 0 : B.t.ntris[b];          // > 0: exact test against the body's convex hull
-      const T reach = handle ? T(0.6) : T(M.radius[b]) + (nt > 0 ? T(0) : T(B.t.vrho[b])) + c.bR;
-      if (d2 > reach * reach) continue;
-      const T cq[4] = {-Q[0], -Q[1], -Q[2], Q[3]};
-      T dl[3], pen = T(0), nl[3] = {T(0), T(0), T(1)};
-      qrot(cq, d, dl);   // ball centre in the body frame
-      if (nt > 0) {      // exact: the body's convex hull
-        if (!hull_sphere<T>(verts + (size_t)b * M.vmax * 3, M.vmax, B.t.face_planes + (size_t)b * B.t.face_tmax * 4,
-                            B.t.face_tris + (size_t)b * B.t.face_tmax * 4, nt, dl, c.bR, pen, nl))
-          continue;
-      } else {
-        T el[3] = {T(0), T(0), T(0)}, dist = T(0), rad = T(0);
-        if (handle) {
-          const T a[3] = {c.hdl[3] - c.hdl[0], c.hdl[4] - c.hdl[1], c.hdl[5] - c.hdl[2]};
-          const T q0[3] = {dl[0] - c.hdl[0], dl[1] - c.hdl[1], dl[2] - c.hdl[2]};
-          T t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) * rcp_(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-          t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t);
+      if (nv > 0 || handle) {
+        T st[13];   // Q[4] p[3] w[3] v[3]
+        ldr<R_Q, 13>(env + RIX(B, b) * RS, st);
+        const T *Q = st, *p = st + 4;
+        const T d[3] = {bp[0] - p[0], bp[1] - p[1], bp[2] - p[2]};
+        const T d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        const int nt = handle ? 0 : B.t.ntris[b];          // > 0: exact test against the body's convex hull
+        const T reach = handle ? T(0.6) : T(M.radius[b]) + (nt > 0 ? T(0) : T(B.t.vrho[b])) + c.bR;
+        if (!(d2 > reach * reach)) {
+          if (nt > 0) {
+            hull = true;
+          } else {
+            const T cq[4] = {-Q[0], -Q[1], -Q[2], Q[3]};
+            T dl[3], el[3] = {T(0), T(0), T(0)}, dist = T(0), rad = T(0);
+            qrot(cq, d, dl);   // ball centre in the body frame
+            if (handle) {
+              const T a[3] = {c.hdl[3] - c.hdl[0], c.hdl[4] - c.hdl[1], c.hdl[5] - c.hdl[2]};
+              const T q0[3] = {dl[0] - c.hdl[0], dl[1] - c.hdl[1], dl[2] - c.hdl[2]};
+              T t = (q0[0] * a[0] + q0[1] * a[1] + q0[2] * a[2]) * rcp_(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+              t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t);
 #pragma unroll
-          for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
-          dist = sqrt_(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
-          rad = c.hdl[6];
-        } else {         // a model compiled without hull faces: spheres on the hull vertices stand in for the hull
-          const float* vb = verts + (size_t)b * M.vmax * 3;
-          T m2 = T(1e30);
-          for (int k = 0; k < nv; k++) {
-            const T ex = dl[0] - T(vb[k]), ey = dl[1] - T(vb[M.vmax + k]), ez = dl[2] - T(vb[2 * M.vmax + k]);
-            const T e2 = ex * ex + ey * ey + ez * ez;
-            if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+              for (int k = 0; k < 3; k++) el[k] = q0[k] - t * a[k];
+              dist = sqrt_(el[0] * el[0] + el[1] * el[1] + el[2] * el[2]);
+              rad = c.hdl[6];
+            } else {         // a model compiled without hull faces: spheres on the hull vertices stand in for the hull
+              const float* vb = verts + (size_t)b * M.vmax * 3;
+              T m2 = T(1e30);
+              for (int k = 0; k < nv; k++) {
+                const T ex = dl[0] - T(vb[k]), ey = dl[1] - T(vb[M.vmax + k]), ez = dl[2] - T(vb[2 * M.vmax + k]);
+                const T e2 = ex * ex + ey * ey + ez * ez;
+                if (e2 < m2) { m2 = e2; el[0] = ex; el[1] = ey; el[2] = ez; }
+              }
+              dist = sqrt_(m2);
+              rad = T(B.t.vrho[b]);
+            }
+            const T pen = c.bR + rad - dist;
+            if (dist > T(1e-9)) {
+              const T id = rcp_(dist);
+              const T nl[3] = {el[0] * id, el[1] * id, el[2] * id};
+              if (pen > T(0)) take(b, handle, pen, nl, st, d);
+            }
           }
-          dist = sqrt_(m2);
-          rad = T(B.t.vrho[b]);
         }
-        pen = c.bR + rad - dist;
-        if (!(dist > T(1e-9))) continue;
-        const T id = rcp_(dist);
-        nl[0] = el[0] * id; nl[1] = el[1] * id; nl[2] = el[2] * id;
-      }
-      if (pen > best) {
-        best = pen;
-        bbody = b;
-        qrot(Q, nl, bn);
-        const T x[3] = {d[0] - c.bR * bn[0], d[1] - c.bR * bn[1], d[2] - c.bR * bn[2]};   // contact point relative to the body origin
-        T wxx[3];
-        cross3(w, x, wxx);
-#pragma unroll
-        for (int k = 0; k < 3; k++) bvo[k] = v[k] + wxx[k];
-        be = handle ? c.er : c.eb;
-        bmu = handle ? c.mur : c.mub;
       }
     }
+    cand |= ((__ballot_sync(FULL, hull) >> (g * 8)) & 0xFFu) << (rr * SLOTS);
+  }
+  // ---- stage 2: the hull bodies in reach, one at a time, the hull's faces over the 8 lanes of the group
+  while (__any_sync(FULL, cand != 0u)) {
+    const bool act = cand != 0u;
+    int b = 0;
+    if (act) {
+      b = pk_nth_set_bit(cand, 0);
+      cand &= cand - 1u;
+    }
+    T st[13], d[3] = {T(0), T(0), T(0)}, dl[3] = {T(0), T(0), T(0)}, pen = T(0), nl[3] = {T(0), T(0), T(1)};
+    ldr<R_Q, 13>(env + RIX(B, b) * RS, st);       // (lanes without a candidate read body 0: unused)
+    if (act) {
+      const T *Q = st, *p = st + 4;
+      d[0] = bp[0] - p[0]; d[1] = bp[1] - p[1]; d[2] = bp[2] - p[2];
+      const T cq[4] = {-Q[0], -Q[1], -Q[2], Q[3]};
+      qrot(cq, d, dl);   // ball centre in the body frame
+    }
+    const int nt = act ? B.t.ntris[b] : 1;
+    const bool hit = hull_sphere_coop<T>(verts + (size_t)b * M.vmax * 3, M.vmax, B.t.face_planes + (size_t)b * B.t.face_tmax * 4,
+                                         B.t.face_tris + (size_t)b * B.t.face_tmax * 4, nt, dl, c.bR, s, act, pen, nl);
+    if (hit && pen > T(0)) take(b, false, pen, nl, st, d);
   }
   // deepest contact of the group (butterfly over the 8 lanes; equal depths: the lower body index, like the serial loop); skipped by
   // the whole warp when no lane found a contact (the common substep)
