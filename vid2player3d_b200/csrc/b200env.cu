@@ -2441,6 +2441,12 @@ int b200env_physics_only(b200env_handle h, int32_t prec, int32_t n, int32_t n_st
   return 0;
 }
 
+#if PT_PROF
+// debug builds only (tools/pt_prof.sh): the per-warp phase cycle counts of the last step_kernel_tmem launch
+extern "C" int b200env_debug_prof(unsigned long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, g_pt_prof, sizeof(unsigned long long) * (size_t)n) == cudaSuccess ? 0 : -1;
+}
+#endif
 int64_t b200env_launch_count(b200env_handle h) { return h ? h->launches : 0; }
 int32_t b200env_kernel_form(b200env_handle h) { return !h ? -1 : (h->tmem ? 3 : (h->packed3 ? 2 : (h->packed ? 1 : 0))); }
 

@@ -30,6 +30,18 @@ enum { PT_ENV_MBOX = PT_MAXREC * PT_REC, PT_ENV_EXT = PT_ENV_MBOX + PT_MBOX_MAX 
 // private fields of a body: column offsets inside its block (runs start on the boundary of the widest shape that moves them)
 enum { TQ_QJ = 0, TQ_WT = 4, TQ_PD = 7, TQ_R = 10, TQ_ZETA = 13, TQ_U = 19, TQ_E = 22, TQ_C = 28, TQ_BN = 34, TQ_BF = 37, PT_COLS = 40 };
 #define PT_BLOCKS 3
+#ifndef PT_PROF
+#define PT_PROF 0   // 1 (tools/pt_prof.sh): per-warp cycle counts of the phases of a control step -> g_pt_prof (which warp ends last, and in what)
+#endif
+#if PT_PROF && defined(__CUDACC__)
+#define PT_PROF_SLOTS 8
+__device__ unsigned long long g_pt_prof[4096 * PT_PROF_SLOTS];
+#define PT_T0() unsigned long long pt_t_ = clock64()
+#define PT_TICK(i) do { const unsigned long long n_ = clock64(); pt_acc_[i] += n_ - pt_t_; pt_t_ = n_; } while (0)
+#else
+#define PT_T0() do {} while (0)
+#define PT_TICK(i) do {} while (0)
+#endif
 #ifndef PT_SYNC_EVERY
 #define PT_SYNC_EVERY 1   // CTA barrier every n-th substep (PT_STEP_SYNC): instruction-cache sharing against waiting for the slowest warp
 #endif
@@ -553,6 +565,10 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
     if (blk >= 0) ps.template st<TQ_R, 9>(blk, rz);
     __syncwarp();
   }
+#if PT_PROF && defined(__CUDACC__)
+  unsigned long long pt_acc_[PT_PROF_SLOTS] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+  PT_T0();
   for (int sim = 0; sim < c.cfi; sim++) {
     if (ball_lane) {
       Ball<T>& bl = *sball;
@@ -564,7 +580,9 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       }
     }
     for (int sub = 0; sub < c.substeps; sub++) {
+      PT_TICK(7);
       if (cta_sync && (PT_SYNC_EVERY == 1 || (sim * c.substeps + sub) % PT_SYNC_EVERY == 0)) pt_substep_barrier();
+      PT_TICK(0);
       const bool last = sim == c.cfi - 1 && sub == c.substeps - 1;
       // 1. per-body inertia / bias / ground contact / joint drive: the owner's three bodies, one per column block
       ps.wait_st();
@@ -606,6 +624,7 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
         if (b > 0) pt_body_drive<T>(B, c, env, b, jp, E, u);
         ps.template st<TQ_U, 3>(k, u); ps.template st<TQ_E, 6>(k, E);
       }
+      PT_TICK(1);
 #if PT_CONTACT_COMPACT
       if (__any_sync(FULL, ncx > 0)) {            // some env of the warp touches the ground (warp-uniform)
         for (int c0 = 0;; c0 += PT_CX) {          // chunks of PT_CX bodies per env: one body per lane of the group
@@ -643,6 +662,7 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
         }
       }
 #endif
+      PT_TICK(2);
       // 2. articulated inertia, leaves -> root
       for (int d = (PT_ABL == 2 ? 0 : M.max_depth); d >= 1; d--) {
         const int blk = B.t.pt_lblk[d];
@@ -663,6 +683,7 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
         ps.template st<TQ_E, 6>(blk, E); ps.template st<TQ_U, 3>(blk, rzu + 9);
         __syncwarp();
       }
+      PT_TICK(3);
       // 3. root acceleration (the root's owner lane) next to the ball (slot 7: uses the racket's start-of-substep pose / velocity, which
       //    the fused pass below is about to overwrite), then the root is integrated
       T rab[28];
@@ -700,6 +721,7 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       if (c.ball_body) __syncwarp();   // the extra ball contacts read the root's pose: integrate it only after every lane is done
       if (valid && s == rslot) pt_root_integrate<T>(c, env);
       __syncwarp();
+      PT_TICK(4);
       // 4. root -> leaves: accelerations + joint integration of a body, then at once its kinematics for the next substep
       //    (its parent's new pose is already in place); welded bodies only have the kinematics
       for (int d = 1; d <= (PT_ABL == 3 ? 0 : M.max_depth); d++) {
@@ -720,6 +742,13 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
       }
     }
   }
+  PT_TICK(5);
+#if PT_PROF && defined(__CUDACC__)
+  if (lane == 0) {
+    const unsigned wid = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & 4095u;
+    for (int i = 0; i < PT_PROF_SLOTS; i++) g_pt_prof[wid * PT_PROF_SLOTS + i] = pt_acc_[i];
+  }
+#endif
   if (ball_lane) ball = *sball;
 }
 
