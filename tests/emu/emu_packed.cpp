@@ -228,6 +228,7 @@ static int run(const b200_model_t* model, const float* verts, const b200_cfg_t* 
   int slots_ok = 1;
   if (build_dev_blob(model, hb, &slots_ok) != 0 || !slots_ok || model->nb > B200_MAX_BODIES_PK) return -1;
   hull_vertex_radius(model, verts, hb.t.vrho);
+  hull_bounding_spheres(model, verts, hb.t.bs);
   if (g_face_planes) {
     hb.t.face_planes = g_face_planes;
     hb.t.face_tris = g_face_tris;

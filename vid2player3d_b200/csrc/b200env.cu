@@ -2053,6 +2053,7 @@ int b200env_create(const b200_model_t* model, const float* verts, const b200_cfg
   if (trc == -2) { delete h; return fail(-2, "b200env_create: too many children per body%s"); }
   h->packed_ok = model->nb <= B200_MAX_BODIES_PK && slots_ok;
   hull_vertex_radius(model, verts, hb.t.vrho);
+  hull_bounding_spheres(model, verts, hb.t.bs);
   const char* kv = getenv("B200ENV_KERNEL");
   h->packed = h->packed_ok && !(kv && strcmp(kv, "lane") == 0);
   const char* sv = getenv("B200ENV_SPLIT");

@@ -42,6 +42,11 @@ struct DevTree {
   int8_t pt_lblk[MAX_LEVELS];                 // block of the depth's dynamic bodies, -1: none
   int8_t pt_mbox[B200_MAX_BODIES];            // mailbox entry of a dynamic body = its rank among the dynamic bodies of its depth
   int32_t pt_ok, pt_nmbox, pt_pad_[4];        // pt_ok: the tree fits (3 blocks x 8 slots); pt_nmbox: mailbox entries per env
+  // ball-body contact: bounding sphere of every hull about the centroid of its vertices (body frame: centre xyz, radius) - the reach
+  // test in front of the exact hull query.  The sphere about the body ORIGIN (b200_model_t::radius, what the ground contact uses) is
+  // up to a limb's length for a hull that starts at its joint; a ball near a lying player passed it for ten bodies at a time
+  // (profiles/r2ad_pt_prof.log).  Pruning only: a ball outside this sphere + its radius is outside the hull + its radius.
+  float bs[B200_MAX_BODIES][4];
 };
 struct DevBlob {
   b200_model_t m;
@@ -139,6 +144,27 @@ static inline int build_dev_blob(const b200_model_t* model, DevBlob& hb, int* sl
     for (int b = 0; b < model->nb; b++)
       if (model->depth[b] == d) hb.t.rix[b] = next++;
   return 0;
+}
+// bounding spheres of the hulls about their vertex centroids (DevTree::bs); verts: AoS [nb][vmax][3] as the ABI hands them over
+static inline void hull_bounding_spheres(const b200_model_t* model, const float* verts, float (*bs)[4]) {
+  for (int b = 0; b < B200_MAX_BODIES; b++) bs[b][0] = bs[b][1] = bs[b][2] = bs[b][3] = 0.0f;
+  for (int b = 0; b < model->nb; b++) {
+    const int nv = model->nverts[b];
+    if (nv < 1) continue;
+    const float* v = verts + (size_t)b * model->vmax * 3;
+    double c[3] = {0, 0, 0};
+    for (int i = 0; i < nv; i++) for (int k = 0; k < 3; k++) c[k] += v[i * 3 + k];
+    for (int k = 0; k < 3; k++) c[k] /= nv;
+    const float cf[3] = {(float)c[0], (float)c[1], (float)c[2]};
+    double r2 = 0;
+    for (int i = 0; i < nv; i++) {
+      const double dx = (double)v[i * 3] - cf[0], dy = (double)v[i * 3 + 1] - cf[1], dz = (double)v[i * 3 + 2] - cf[2];
+      const double d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 > r2) r2 = d2;
+    }
+    bs[b][0] = cf[0]; bs[b][1] = cf[1]; bs[b][2] = cf[2];
+    bs[b][3] = (float)(sqrt(r2) * 1.0001 + 1e-6);     // conservative against the float arithmetic of the device-side test
+  }
 }
 // ball-body contact (b200_cfg_t::ball_body_contact): a body's hull is stood in for by spheres on its vertices; radius = half the mean
 // distance of a vertex to its nearest neighbour, kept within [5 mm, 5 cm].  Same function (same float arithmetic) in oracle/physics_ref.c.

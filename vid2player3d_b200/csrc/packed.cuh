@@ -617,8 +617,12 @@ __device__ __forceinline__ void pk_ball_contacts_group(const DevBlob& B, const f
         const int nt = handle ? 0 : B.t.ntris[b];          // > 0: exact test against the body's convex hull
         const T reach = handle ? T(0.6) : T(M.radius[b]) + (nt > 0 ? T(0) : T(B.t.vrho[b])) + c.bR;
         if (!(d2 > reach * reach)) {
-          if (nt > 0) {
-            hull = true;
+          if (nt > 0) {      // second reach test: the hull's own bounding sphere (about its centroid; DevTree::bs)
+            const T cl[3] = {T(B.t.bs[b][0]), T(B.t.bs[b][1]), T(B.t.bs[b][2])};
+            T cw[3];
+            qrot(Q, cl, cw);
+            const T e[3] = {d[0] - cw[0], d[1] - cw[1], d[2] - cw[2]}, rr2 = T(B.t.bs[b][3]) + c.bR;
+            hull = !(e[0] * e[0] + e[1] * e[1] + e[2] * e[2] > rr2 * rr2);
           } else {
             const T cq[4] = {-Q[0], -Q[1], -Q[2], Q[3]};
             T dl[3], el[3] = {T(0), T(0), T(0)}, dist = T(0), rad = T(0);
