@@ -601,46 +601,63 @@ __device__ __forceinline__ void contact_hull(const float* __restrict__ vb, int v
 // least-penetrated face normal; (3) else the closest point of the hull surface = closest point over its triangles (Ericson 5.1.5).
 // vb: the body's hull vertices, SoA [3][vmax] (shared memory); pl / tr: its planes / triangles (global memory, L2-resident).
 template <typename T>
-__device__ __forceinline__ void closest_on_triangle(const T* p, const T* a, const T* b, const T* c, T* q) {
+__device__ __forceinline__ bool closest_on_triangle(const T* p, const T* a, const T* b, const T* c, T* q) {
   T ab[3], ac[3], ap[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; }
   const T d1 = ab[0] * ap[0] + ab[1] * ap[1] + ab[2] * ap[2], d2 = ac[0] * ap[0] + ac[1] * ap[1] + ac[2] * ap[2];
-  if (d1 <= T(0) && d2 <= T(0)) { q[0] = a[0]; q[1] = a[1]; q[2] = a[2]; return; }
+  if (d1 <= T(0) && d2 <= T(0)) { q[0] = a[0]; q[1] = a[1]; q[2] = a[2]; return false; }
   T bp[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) bp[k] = p[k] - b[k];
   const T d3 = ab[0] * bp[0] + ab[1] * bp[1] + ab[2] * bp[2], d4 = ac[0] * bp[0] + ac[1] * bp[1] + ac[2] * bp[2];
-  if (d3 >= T(0) && d4 <= d3) { q[0] = b[0]; q[1] = b[1]; q[2] = b[2]; return; }
+  if (d3 >= T(0) && d4 <= d3) { q[0] = b[0]; q[1] = b[1]; q[2] = b[2]; return false; }
   const T vc = d1 * d4 - d3 * d2;
   if (vc <= T(0) && d1 >= T(0) && d3 <= T(0)) {
     const T v = d1 / (d1 - d3);
 #pragma unroll
     for (int k = 0; k < 3; k++) q[k] = a[k] + v * ab[k];
-    return;
+    return false;
   }
   T cp[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) cp[k] = p[k] - c[k];
   const T d5 = ab[0] * cp[0] + ab[1] * cp[1] + ab[2] * cp[2], d6 = ac[0] * cp[0] + ac[1] * cp[1] + ac[2] * cp[2];
-  if (d6 >= T(0) && d5 <= d6) { q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; return; }
+  if (d6 >= T(0) && d5 <= d6) { q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; return false; }
   const T vb2 = d5 * d2 - d1 * d6;
   if (vb2 <= T(0) && d2 >= T(0) && d6 <= T(0)) {
     const T w = d2 / (d2 - d6);
 #pragma unroll
     for (int k = 0; k < 3; k++) q[k] = a[k] + w * ac[k];
-    return;
+    return false;
   }
   const T va = d3 * d6 - d5 * d4;
   if (va <= T(0) && (d4 - d3) >= T(0) && (d5 - d6) >= T(0)) {
     const T w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
 #pragma unroll
     for (int k = 0; k < 3; k++) q[k] = b[k] + w * (c[k] - b[k]);
-    return;
+    return false;
   }
   const T den = T(1) / (va + vb2 + vc), v = vb2 * den, w = vc * den;
 #pragma unroll
   for (int k = 0; k < 3; k++) q[k] = a[k] + ab[k] * v + ac[k] * w;
+  return true;   // the projection of p onto the triangle's plane lies inside the triangle
+}
+// Shortcut of the closest-point pass.  For a point outside a convex hull, the largest plane offset smax (face imax, pass 1) is a lower bound
+// of its distance to the hull, attained iff the projection onto that plane lies inside the face - then the other faces need not be
+// walked.  Returns whether it applied; best / qb = squared distance / closest point on face imax in that case (untouched otherwise).
+template <typename T>
+__device__ __forceinline__ bool hull_nearest_on_face(const float* vb, int vmax, const unsigned char* tr, int imax, const T* c, T& best, T* qb) {
+  const uint32_t tri = *reinterpret_cast<const uint32_t*>(tr + 4 * imax);
+  const int i0 = tri & 0xFFu, i1 = (tri >> 8) & 0xFFu, i2 = (tri >> 16) & 0xFFu;
+  const T a[3] = {T(vb[i0]), T(vb[vmax + i0]), T(vb[2 * vmax + i0])};
+  const T b[3] = {T(vb[i1]), T(vb[vmax + i1]), T(vb[2 * vmax + i1])};
+  const T cc[3] = {T(vb[i2]), T(vb[vmax + i2]), T(vb[2 * vmax + i2])};
+  T q[3];
+  if (!closest_on_triangle<T>(c, a, b, cc, q)) return false;
+  best = (c[0] - q[0]) * (c[0] - q[0]) + (c[1] - q[1]) * (c[1] - q[1]) + (c[2] - q[2]) * (c[2] - q[2]);
+  qb[0] = q[0]; qb[1] = q[1]; qb[2] = q[2];
+  return true;
 }
 template <typename T>
 __device__ __forceinline__ bool hull_sphere(const float* vb, int vmax, const float* pl, const unsigned char* tr, int nt, const T* c, T R, T& pen,
@@ -668,6 +685,7 @@ __device__ __forceinline__ bool hull_sphere(const float* vb, int vmax, const flo
     return true;
   }
   T best = T(1e30), qb[3] = {T(0), T(0), T(0)};
+  if (hull_nearest_on_face<T>(vb, vmax, tr, imax, c, best, qb)) nt = 0;   // the projection onto the farthest face plane lies inside that face: done
   for (int t = 0; t < nt; t += 4) {
     // the closest point of a convex hull to an outside point lies on a face the point sees (its offset from that face's plane is
     // positive): the back faces are skipped
@@ -747,9 +765,10 @@ __device__ __forceinline__ bool hull_sphere_coop(const float* vb, int vmax, cons
     nl[0] = T(pl[4 * imax]); nl[1] = T(pl[4 * imax + 1]); nl[2] = T(pl[4 * imax + 2]);
   }
   // ---- pass 2: closest point over the faces the centre sees (groups that are decided idle through it)
-  const bool need = act && !sep && !inside;
+  bool need = act && !sep && !inside;
   T best = T(1e30), qb[3] = {T(0), T(0), T(0)};
   int ibest = 1 << 30;
+  if (need && hull_nearest_on_face<T>(vb, vmax, tr, imax, c, best, qb)) need = false;   // same on the 8 lanes of the group (same arguments)
   if (__any_sync(FULL, need)) {
     bool fin = !need;
     for (int t0 = 0;; t0 += 32) {
