@@ -11,13 +11,32 @@ import bench
 from vid2player3d_b200 import native
 
 N = 8192
-steps = [int(a) for a in sys.argv[1:]] or [10, 45, 55, 70]
-env = bench.federer_env(N, 0)
-dev = env.device
-acts = [torch.clamp(torch.randn(N, env.num_actions, device=dev), -5, 5) for _ in range(8)]
-for i in range(4):
-    env.step(acts[i]); env.reset(env.reset_buf.nonzero(as_tuple=False).flatten())
-env.enable_cuda_graph()
+AMASS = len(sys.argv) > 1 and sys.argv[1] == "amass"      # config 2 (embodied_pose task, random policy) instead of the primary workload
+steps = [int(a) for a in sys.argv[(2 if AMASS else 1):]] or ([5, 30] if AMASS else [10, 45, 55, 70])
+if AMASS:
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import SIM_PARAMS, im_cfg
+    from vid2player3d_b200 import model_compiler, motion_lib
+    from vid2player3d_b200.tasks import HumanoidSMPLIM
+    model = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    flat = motion_lib.synthetic(model, num_motions=64, num_frames=300, seed=7)
+    torch.manual_seed(7)
+    task = HumanoidSMPLIM(im_cfg(N, flat), SIM_PARAMS, 1, "cuda", 0, True)
+    g = torch.Generator(device=task.device).manual_seed(1)
+    acts = [torch.rand(N, 75, device=task.device, generator=g) * 2 - 1 for _ in range(8)]
+    task.reset()
+
+    class _E:      # the two calls the loop below makes
+        def step(self, a): task.step(a)
+        def reset_done(self): pass
+    env = _E()
+else:
+    env = bench.federer_env(N, 0)
+    dev = env.device
+    acts = [torch.clamp(torch.randn(N, env.num_actions, device=dev), -5, 5) for _ in range(8)]
+    for i in range(4):
+        env.step(acts[i]); env.reset(env.reset_buf.nonzero(as_tuple=False).flatten())
+    env.enable_cuda_graph()
 names = ["barrier", "body pass", "contact", "backward", "root+ball", "last fwd", "-", "forward"]
 buf = np.zeros((4096, 8), np.uint64)
 nw = (N + 55) // 56 * 14

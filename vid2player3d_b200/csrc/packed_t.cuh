@@ -13,9 +13,12 @@
 //     instead of read-modify-write on the parent's record; the parent adds its children in rank order (same order, same bits);
 //   * what stays in shared memory per body is the pose / velocity of its origin (13 floats, read by children, the ball, contacts)
 //     and A / Bm of the articulated inertia (15; the accelerations alias A after the body's forward step): 28 floats, a stride that
-//     keeps the 128-bit accesses of neighbouring lanes conflict-free.  3.5 KB per env.
-// The arithmetic is that of packed.cuh with the in-place ground contact (bit-identical results; tests/test_gpu_parity.py holds the two
-// kernels to exact equality).  PS is the private store: PrivTmem (device, float) or PrivMem (plain memory: CPU lane emulator, double).
+//     keeps the 128-bit accesses of neighbouring lanes conflict-free.  3.6 KB per env with the mailbox, the residual wrench and the ball;
+//   * ground contact: masks in the body pass, the bodies in contact of an env compacted into exchange entries carved out of the mailbox
+//     (idle between two backward passes) and applied by the env's 8 lanes, 8 bodies per chunk.
+// The arithmetic is that of packed.cuh, operation for operation (tests/test_gpu_tmem.py holds the two kernels to exact equality in a
+// -fmad=false build; tests/test_emu_packed.py in float32 emulation).  PS is the private store: PrivTmem (device, float) or PrivMem
+// (plain memory: CPU lane emulator, double).  Measurements: profiles/r2t_tmem.md, r2aa_transient.md, r2ad_pt_prof.md.
 #pragma once
 
 enum { PT_Q = 0, PT_P = 4, PT_W = 7, PT_V = 10, PT_A = 13, PT_BM = 19, PT_REC = 28 };
@@ -54,7 +57,7 @@ __device__ unsigned long long g_pt_prof[4096 * PT_PROF_SLOTS];
 enum { CX_CBB = 0, CX_MASK = 12, PT_CXS = 16 };   // layout of an exchange entry: C bn bf, mask lo / hi, body index (PT_CXS values, 16-byte aligned)
 static_assert(PT_CX * PT_CXS <= PT_MBOX_MAX * PT_MB && PT_CX <= 8, "exchange entries must fit the mailbox, one per lane of the group at most");
 #ifndef PT_ABL
-#define PT_ABL 0   // ablation of the phases (register-pressure hunting): 1 body pass, 2 backward, 3 forward, 4 root / ball
+#define PT_ABL 0   // ablation of the phases (timing / register-pressure experiments only): 1 body pass, 2 backward, 3 forward, 4 root / ball, 5 no ground contact
 #endif
 #define PT_WARP_COLS 128    // tensor-memory columns of one warp (14 warps: at most 4 per lane quadrant -> 4 x 128 = 512)
 #define PT_XMASK (PT_BLOCKS * PT_COLS)   // columns 120..125 of a lane: penetration masks (2 words per block) of bodies waiting for a later contact chunk
