@@ -273,3 +273,17 @@ extern "C" int emu_packed_physics_f32(const b200_model_t* model, const float* ve
                                       float* contact_out, float* ballio, int32_t* hits) {
   return run<float>(model, verts, cfg, n, n_steps, root, dof_pos, dof_vel, pd_tar, ext, rb_out, contact_out, ballio, hits);
 }
+
+// owner-slot tables of the one-wave form (DevTree::pt_*, csrc/dyn_common.cuh::build_pt_tables) for a model: tests/test_emu_packed.py checks
+// their invariants on the shipped assets and on a tree that does not fit
+extern "C" int emu_pt_tables(const b200_model_t* model, int8_t* blk, int8_t* slot, int8_t* body, int8_t* lvl, int8_t* lblk, int8_t* mbox,
+                             int32_t* nmbox) {
+  static DevBlob hb;
+  int slots_ok = 1;
+  if (build_dev_blob(model, hb, &slots_ok) != 0) return -1;
+  memcpy(blk, hb.t.pt_blk, sizeof(hb.t.pt_blk)); memcpy(slot, hb.t.pt_slot, sizeof(hb.t.pt_slot));
+  memcpy(body, hb.t.pt_body, sizeof(hb.t.pt_body)); memcpy(lvl, hb.t.pt_lvl, sizeof(hb.t.pt_lvl));
+  memcpy(lblk, hb.t.pt_lblk, sizeof(hb.t.pt_lblk)); memcpy(mbox, hb.t.pt_mbox, sizeof(hb.t.pt_mbox));
+  *nmbox = hb.t.pt_nmbox;
+  return hb.t.pt_ok;
+}

@@ -258,3 +258,58 @@ def test_one_wave_form_is_bit_identical_to_packed_in_float32(asset, flags):
     for a, b, name in zip(ref, got, ("root", "dof_pos", "dof_vel", "rigid bodies", "contact forces")):
         assert np.array_equal(a, b), name
     assert np.abs(ref[4]).max() > 10.0
+
+
+def _pt_tables(ms):
+    import build as emu_build
+    lib = C.CDLL(emu_build.build("packedt"))
+    MB, LV, SL = 32, 16, 8
+    blk, slot, mbox = (np.zeros(MB, np.int8) for _ in range(3))
+    body, lvl, lblk = np.zeros((3, SL), np.int8), np.zeros((LV, SL), np.int8), np.zeros(LV, np.int8)
+    nm = C.c_int32(0)
+    ok = lib.emu_pt_tables(C.byref(ms), _p(blk), _p(slot), _p(body), _p(lvl), _p(lblk), _p(mbox), C.byref(nm))
+    return ok, blk, slot, body, lvl, lblk, mbox, nm.value
+
+
+@pytest.mark.parametrize("asset", ["smpl_mesh_humanoid_amass_v1", "smpl_mesh_humanoid_federer", "smpl_mesh_humanoid_djokovic", "smpl_mesh_humanoid_nadal"])
+def test_owner_slot_tables_of_the_one_wave_form(asset):
+    """csrc/dyn_common.cuh::build_pt_tables: every dynamic body has one (block, slot) of its own; the bodies of a tree depth share a block
+    (one warp-uniform TMEM address per level pass) and sit in different slots; a welded body has a lane at its depth but no block; the
+    mailbox rank of a body is its rank among the dynamic bodies of its depth"""
+    mod = model_compiler.canonical_racket_last(model_compiler.load_compiled(asset))
+    ms, _ = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    ok, blk, slot, body, lvl, lblk, mbox, nm = _pt_tables(ms)
+    assert ok == 1
+    nb, depth, fixed = ms.nb, list(ms.depth)[:ms.nb], list(ms.fixed)[:ms.nb]
+    seen = set()
+    for b in range(nb):
+        d = depth[b]
+        assert 0 <= slot[b] < 8 and lvl[d][slot[b]] == b
+        if fixed[b]:
+            assert blk[b] == -1
+            continue
+        assert 0 <= blk[b] < 3 and blk[b] == lblk[d] and body[blk[b]][slot[b]] == b
+        assert (blk[b], slot[b]) not in seen
+        seen.add((blk[b], slot[b]))
+        assert mbox[b] == sum(1 for c in range(b) if depth[c] == d and not fixed[c])
+    assert len(seen) == sum(1 for b in range(nb) if not fixed[b])
+    for d in range(16):
+        on = [lvl[d][s] for s in range(8) if lvl[d][s] >= 0]
+        assert sorted(on) == [b for b in range(nb) if depth[b] == d]
+    assert nm == max(sum(1 for b in range(nb) if depth[b] == d and not fixed[b]) for d in range(1, 16))
+
+
+def test_owner_slot_tables_reject_a_tree_that_does_not_fit():
+    """a tree with 11 jointed bodies at one depth: more than the 8 lane slots of an env's group -> pt_ok = 0 (b200env_create then keeps
+    the two-round packed kernel)"""
+    mod = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    ms, _ = abi.pack_model(mod, float(mod["mass"].sum()) / 90.0)
+    import copy
+    m2 = copy.deepcopy(ms)
+    m2.nb = 26
+    for b in range(26):
+        m2.parent[b] = b - 1
+        m2.depth[b] = b if b < 16 else 15          # 16 depths are what the tables hold; bodies 15.. share the last one
+        m2.fixed[b] = 0
+    ok = _pt_tables(m2)[0]
+    assert ok == 0
