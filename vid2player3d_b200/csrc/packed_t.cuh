@@ -633,13 +633,15 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
         for (int c0 = 0;; c0 += PT_CX) {          // chunks of PT_CX bodies per env: one body per lane of the group
           if (c0 > 0) {                           // owners of the bodies ranked c0 .. c0 + PT_CX - 1 hand them over now
             for (int k = 0; k < PT_BLOCKS; k++) {
+              const uint32_t f = xmine >> (6 * k);
+              const int idx = (int)((f >> 1) & 31u) - c0;
+              const bool mine = (f & 1u) && idx >= 0 && idx < PT_CX;
+              if (!__any_sync(FULL, mine)) continue;   // (warp-uniform)
               T cbb[12], mk[3];
               ps.wait_st();
               ps.template ld<TQ_C, 12>(k, cbb); ps.ld2(PT_XMASK + 2 * k, mk);
               ps.wait_ld();
-              const uint32_t f = xmine >> (6 * k);
-              const int idx = (int)((f >> 1) & 31u) - c0;
-              if ((f & 1u) && idx >= 0 && idx < PT_CX) {
+              if (mine) {
                 T* ent = env + PT_ENV_MBOX + idx * PT_CXS;
                 mk[2] = pt_bits_to_slot<T>((uint32_t)B.t.pt_body[k][s]);
                 str<CX_CBB, 12>(ent, cbb);
@@ -651,13 +653,15 @@ __device__ __forceinline__ void control_step_t(const DevBlob& B, const float* ve
           pt_contact_phase<T>(B, verts, c, env, s, ncx - c0 < PT_CX ? ncx - c0 : PT_CX, cf_env, last);
           __syncwarp();
           for (int k = 0; k < PT_BLOCKS; k++) {   // owners take C / bn / bf of their handed-over bodies back into the private store
+            const uint32_t f = xmine >> (6 * k);
+            const int idx = (int)((f >> 1) & 31u) - c0;
+            const bool mine = (f & 1u) && idx >= 0 && idx < PT_CX;
+            if (!__any_sync(FULL, mine)) continue;   // no lane of the warp handed a body of this block over in this chunk (warp-uniform)
             T cbb[12];
             ps.wait_st();
             ps.template ld<TQ_C, 12>(k, cbb);
             ps.wait_ld();
-            const uint32_t f = xmine >> (6 * k);
-            const int idx = (int)((f >> 1) & 31u) - c0;
-            if ((f & 1u) && idx >= 0 && idx < PT_CX) ldr<CX_CBB, 12>(env + PT_ENV_MBOX + idx * PT_CXS, cbb);
+            if (mine) ldr<CX_CBB, 12>(env + PT_ENV_MBOX + idx * PT_CXS, cbb);
             ps.template st<TQ_C, 12>(k, cbb);
           }
           __syncwarp();                           // the entries are free: next chunk, or the hand-over entries of the backward pass
