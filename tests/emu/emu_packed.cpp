@@ -287,3 +287,42 @@ extern "C" int emu_pt_tables(const b200_model_t* model, int8_t* blk, int8_t* slo
   *nmbox = hb.t.pt_nmbox;
   return hb.t.pt_ok;
 }
+
+// The exact ball / convex-hull query on its own: form 0 = hull_sphere (one lane walks the hull), form 1 = hull_sphere_coop (the hull's faces
+// over the 8 lanes of a group; 4 groups = 4 query points per emulated warp).  Float64.  centres [n][3] in the body frame of `body`;
+// out_hit [n], out_pen [n], out_nl [n][3].  Faces from emu_set_hull_faces.
+namespace {
+struct HsJob { const float* sv; int vmax; const float* pl; const unsigned char* tr; int nt; const double* c; double R; int n, form; int32_t* hit; double* pen; double* nl; };
+void hs_lane(EmuWarp* w, int lane, const HsJob* J, int q0) {
+  emu_warp = w;
+  emu_lane = lane;
+  const int g = lane >> 3, s = lane & 7, q = q0 + g;
+  const bool act = q < J->n;
+  double c[3] = {0, 0, 0}, pen = 0, nl[3] = {0, 0, 1};
+  if (act) for (int k = 0; k < 3; k++) c[k] = J->c[q * 3 + k];
+  bool hit;
+  if (J->form == 1) hit = hull_sphere_coop<double>(J->sv, J->vmax, J->pl, J->tr, J->nt, c, J->R, s, act, pen, nl);
+  else hit = act && s == 0 && hull_sphere<double>(J->sv, J->vmax, J->pl, J->tr, J->nt, c, J->R, pen, nl);
+  if (act && s == (J->form == 1 ? 5 : 0)) {       // any lane of the group holds the cooperative result: take lane 5's
+    J->hit[q] = hit ? 1 : 0; J->pen[q] = pen;
+    for (int k = 0; k < 3; k++) J->nl[q * 3 + k] = nl[k];
+  }
+}
+}  // namespace
+extern "C" int emu_hull_sphere(const b200_model_t* model, const float* verts, int body, int form, int n, const double* centres, double R,
+                               int32_t* out_hit, double* out_pen, double* out_nl) {
+  if (!g_face_planes || g_face_ntris[body] <= 0) return -1;
+  std::vector<float> soa((size_t)model->nb * model->vmax * 3 + 16, 0.0f);
+  float* sv = soa.data();
+  while ((uintptr_t)sv % 16) sv++;
+  verts_to_soa(model, verts, sv);
+  HsJob J{sv + (size_t)body * model->vmax * 3, model->vmax, g_face_planes + (size_t)body * g_face_tmax * 4, g_face_tris + (size_t)body * g_face_tmax * 4,
+          g_face_ntris[body], centres, R, n, form, out_hit, out_pen, out_nl};
+  for (int q0 = 0; q0 < n; q0 += 4) {
+    EmuWarp w;
+    std::vector<std::thread> th;
+    for (int lane = 0; lane < 32; lane++) th.emplace_back(hs_lane, &w, lane, &J, q0);
+    for (auto& t : th) t.join();
+  }
+  return 0;
+}

@@ -313,3 +313,48 @@ def test_owner_slot_tables_reject_a_tree_that_does_not_fit():
         m2.fixed[b] = 0
     ok = _pt_tables(m2)[0]
     assert ok == 0
+
+
+@pytest.mark.parametrize("form", [0, 1], ids=["one_lane", "eight_lanes"])
+def test_hull_query_of_the_kernels_matches_the_restatement(form):
+    """csrc/dyn_common.cuh::hull_sphere (one lane walks the hull, four faces per iteration, nearest-face shortcut) and hull_sphere_coop (the
+    hull's faces over the 8 lanes of an env's group: ballot for the separating plane, shuffle reductions with the serial tie rule) in
+    float64 on the lane emulator against oracle/physics_ref.c::hull_sphere_ref, which walks every face: hit / miss identical, depth and
+    normal to 1e-12, on points inside the hull, just outside faces, near edges and vertices, and far away"""
+    import build as emu_build
+    from oracle import physics_ref as P
+    mod = model_compiler.load_compiled("smpl_mesh_humanoid_amass_v1")
+    ms, verts = abi.pack_model(mod, 1.0)
+    planes, tris, ntris, tmax = abi.pack_faces(mod, verts)
+    lib = C.CDLL(emu_build.build("packedt"))
+    lib.emu_set_hull_faces(_p(planes), _p(tris), _p(ntris), C.c_int(tmax))
+    P.set_hull_faces(planes, tris, ntris, tmax)
+    rng = np.random.default_rng(4)
+    R = 0.032
+    try:
+        seen = {"inside": 0, "contact": 0, "miss": 0}
+        for b in (0, 4, 9, 13, 18, 23):
+            nv = int(mod["nverts"][b])
+            V = verts[b, :nv].astype(np.float64)
+            ctr, ext = V.mean(0), np.ptp(V, axis=0).max()
+            pts = [ctr + rng.normal(size=3) * ext * sc for sc in (0.1, 0.3, 0.45, 0.6) for _ in range(10)]
+            pts += [V[i] + rng.normal(size=3) * 0.01 for i in rng.integers(0, nv, 12)]                       # near vertices
+            pts += [0.5 * (V[i] + V[j]) + rng.normal(size=3) * 0.01 for i, j in rng.integers(0, nv, (12, 2))]   # near edges / through the hull
+            pts = np.ascontiguousarray(np.array(pts))
+            n = len(pts)
+            hit, pen, nl = np.zeros(n, np.int32), np.zeros(n), np.zeros((n, 3))
+            rc = lib.emu_hull_sphere(C.byref(ms), _p(np.ascontiguousarray(verts, np.float32)), C.c_int(b), C.c_int(form), C.c_int(n), _p(pts),
+                                     C.c_double(R), _p(hit), _p(pen), _p(nl))
+            assert rc == 0
+            for i in range(n):
+                h0, p0, n0 = P.hull_sphere(ms, verts, b, pts[i], R)
+                assert hit[i] == h0, (b, i)
+                if h0:
+                    assert abs(pen[i] - p0) < 1e-12 and np.abs(nl[i] - n0).max() < 1e-9, (b, i, pen[i], p0)
+                    seen["inside" if p0 >= R else "contact"] += 1
+                else:
+                    seen["miss"] += 1
+        assert min(seen.values()) > 20, seen
+    finally:
+        P.clear_hull_faces()
+        lib.emu_set_hull_faces(None, None, None, C.c_int(0))
