@@ -786,10 +786,10 @@ def main():
         "gpu_launches": int((graph_nodes + (reset_nodes or 0) + 1) * K) if graph_nodes else int(step_launches),
         "gpu_launches_note": "kernel nodes of the step graph + the reset graph (+ the mask kernel) x timed steps, counted from the graphs' DOT dumps; "
                              "our own kernels among them per step: 22 (step graph) + 7 (reset graph)",
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": {"tmem": 15862272, "packed": 8026112}.get(kform),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": {"tmem": 17394176, "packed": 8026112}.get(kform),
                      "traffic_note": "from_profile: dram__bytes_read.sum + dram__bytes_write.sum of ONE physics launch (the dominant kernel) in the "
                                      "ncu --set full captures profiles/r2i_step_kernel_ncu.md (step_kernel_packed) / profiles/r2t_tmem.md "
-                                     "(step_kernel_tmem: 15.9 MB); not measured by this run",
+                                     "(step_kernel_tmem, capture r2ac_c3: 17.4 MB); not measured by this run",
                      "kernel": "one env step = one CUDA graph (motion targets, FK, 734-d obs, decoder + policy GEMMs, physics, post step); dominant launch "
                                + PHYS_KERNEL_NAME[kform], "kernel_ms": ms_step, "algorithmic_bytes_per_env_step": ALGO_BYTES_CFG3,
                      "dominant_kernel": {"name": PHYS_KERNEL_NAME[kform] + " (12 substeps + ball)", "ms": phys_ms, "launches_timed": 10,
